@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- microbe-steps/s (advect + interact) of the B200 hot path, one JSON line on stdout.
+
+    python bench.py --gpus 1 --steps 20 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...          # the reference's CPU path on the host cores
+
+A *step* is one pass of the hot path over all microbes: RK4 advection, binning, radius pair search
+fused with rock-paper-scissors resolution, pair list emitted (BASELINE.json metric:
+"microbe-steps/sec (advect+interact)").
+
+Workloads (``config.workload``):
+  shard    (default) the per-GPU shard of BASELINE config 4 "100M microbes basin-scale North Pacific
+           across 8xB200": 12.5M microbes per GPU, uniform-random over lon 180-240 x a 7.5-degree
+           latitude strip per GPU (N = 8 gives lat 0-60 and exactly config 4), r = 0.01 deg, p = 0.55,
+           time-varying synthetic random-Fourier velocity on the OSCAR 1/3-degree grid, dt = 1 h.
+           Weak scaling: per-GPU work fixed as N grows.
+  config2  BASELINE config 2: 490,000 microbes (700x700 lattice, 25-35N 205-215E), time-varying field,
+           spun up ``--spinup`` steps so that the timed steps see the stirred state.
+  config3  BASELINE config 3: 10M microbes uniform in the 10x10-degree patch (rho = 15.7).
+Inputs are larger than L2 for shard/config3 (state 162 MB + pair list 440 MB per step vs 126 MB L2).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "microbe-steps/sec (advect+interact)"
+UNIT = "microbe-steps/s"
+RADIUS = 0.01
+P_RPS = (0.55, 0.55, 0.55)
+DT = 3600.0
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+# workloads
+# ------------------------------------------------------------------------------------------------------
+def workload_particles(name, n, rank, world, seed=0):
+    """Returns lon, lat (float64), species int8, description dict."""
+    rng = np.random.default_rng(seed * 1000 + rank)
+    if name == "shard":
+        strip = 7.5
+        lat0 = 30.0 - 0.5 * strip * world + strip * rank
+        lon = 180.0 + 60.0 * rng.random(n)
+        lat = lat0 + strip * rng.random(n)
+        desc = dict(lon=[180.0, 240.0], lat=[30.0 - 0.5 * strip * world, 30.0 + 0.5 * strip * world])
+    elif name == "config3":
+        lon = 205.0 + 10.0 * rng.random(n)
+        lat = 25.0 + 10.0 * rng.random(n)
+        desc = dict(lon=[205.0, 215.0], lat=[25.0, 35.0])
+    elif name == "config2":
+        from lagrangian_microbes_b200.particle_advecter import uniform_particle_locations
+        lon, lat = uniform_particle_locations(n, 25, 35, 205, 215)
+        desc = dict(lon=[205.0, 215.0], lat=[25.0, 35.0])
+    else:
+        raise ValueError(name)
+    species = rng.integers(1, 4, n).astype(np.int8)
+    return lon, lat, species, desc
+
+
+def default_n(name):
+    return {"shard": 12_500_000, "config3": 10_000_000, "config2": 490_000}[name]
+
+
+def make_fieldset(n_modes):
+    from lagrangian_microbes_b200 import velocity_fields
+    from lagrangian_microbes_b200.particle_advecter import HostFieldSet
+    velocity_fields.configure_synthetic(kind="random_fourier", seed=0, n_modes=n_modes, rms_speed=0.2)
+    return HostFieldSet(velocity_fields.oscar_dataset(2017))
+
+
+# ------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], [], set(), []
+        for ts, line in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples in the timed region"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU reference arm / baseline
+# ------------------------------------------------------------------------------------------------------
+def cpu_reference_step_setup(workload, n_sample, n_modes):
+    """A bounded sample of the workload: the same areal density, fewer microbes."""
+    from oracle import rk4 as ork4
+    n_full = default_n(workload)
+    lon, lat, species, desc = workload_particles(workload, n_full if workload == "config2" else n_sample, 0, 1)
+    if workload != "config2":
+        # shrink the box so that the density (hence pairs per microbe) is that of the full workload
+        frac = n_sample / float(n_full)
+        lon_w, lat_w = desc["lon"][1] - desc["lon"][0], desc["lat"][1] - desc["lat"][0]
+        if workload == "shard":
+            lat_w = 7.5
+            lat_lo = 30.0 - 3.75
+        else:
+            lat_lo = desc["lat"][0]
+        s = np.sqrt(frac)
+        lon = desc["lon"][0] + (lon - desc["lon"][0]) * s
+        lat = lat_lo + (lat - lat_lo) * s
+    elif n_sample < n_full:
+        lon, lat, species = lon[:n_sample], lat[:n_sample], species[:n_sample]
+    hfs = make_fieldset(n_modes)
+    fs = ork4.FieldSet(hfs.lon, hfs.lat, hfs.time, hfs.u, hfs.v)
+    return fs, lon.astype(np.float32), lat.astype(np.float32), species
+
+
+def cpu_reference_step(fs, lon, lat, species, t, ti, step, threads):
+    """One step of the reference's CPU path.  Returns (ti, n_pairs, dict of phase seconds)."""
+    from oracle import pairs as opairs, philox, rk4 as ork4, rps as orps
+    t0 = time.perf_counter()
+    ti, _ = ork4.rk4_step_c(fs, lon, lat, t, DT, ti, threads=threads)            # parcels' JIT'd C, restated
+    t1 = time.perf_counter()
+    pair_set = opairs.query_pairs_reference(lon, lat, RADIUS)                    # cKDTree build + query_pairs (set)
+    t2 = time.perf_counter()
+    # the reference's Python loop over the set (interaction_simulator.py:104-105), rule restated in Python
+    pr = np.array(list(pair_set), dtype=np.int64).reshape(-1, 2)
+    u = philox.pair_uniforms(np.minimum(pr[:, 0], pr[:, 1]), np.maximum(pr[:, 0], pr[:, 1]), step, 0)
+    t3 = time.perf_counter()
+    k = 0
+    for pair in pair_set:
+        orps.rps_pair(species, pair[0], pair[1], u[k], *P_RPS)
+        k += 1
+    t4 = time.perf_counter()
+    return ti, len(pair_set), {"advect_s": t1 - t0, "tree_query_s": t2 - t1, "rps_loop_s": t4 - t3}
+
+
+def run_cpu_reference(workload, n_sample, steps, warmup, n_modes):
+    from oracle import rps as orps
+    orps.build_c()
+    threads = os.cpu_count() or 1
+    fs, lon, lat, species = cpu_reference_step_setup(workload, n_sample, n_modes)
+    t, ti = 0.0, 0
+    phases = {"advect_s": 0.0, "tree_query_s": 0.0, "rps_loop_s": 0.0}
+    pairs = 0
+    tot = 0.0
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        ti, npairs, ph = cpu_reference_step(fs, lon, lat, species, t, ti, s, threads)
+        el = time.perf_counter() - t0
+        t += DT
+        if s >= warmup:
+            # only the reference's own phases count (advect, tree build + query, pair loop); building the
+            # injected per-pair stream is harness work that np.random.rand() does inside the loop upstream
+            tot += ph["advect_s"] + ph["tree_query_s"] + ph["rps_loop_s"]
+            pairs += npairs
+            for k2 in phases:
+                phases[k2] += ph[k2]
+    value = lon.size * steps / tot
+    return {"value": value, "seconds": tot, "n_sample": int(lon.size), "pairs_per_step": pairs / max(steps, 1),
+            "phases_s_per_step": {k2: v / max(steps, 1) for k2, v in phases.items()}, "threads": threads}
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="shard", choices=["shard", "config2", "config3"])
+    ap.add_argument("--microbes", type=int, default=0, help="microbes per GPU (0 = the workload's size)")
+    ap.add_argument("--spinup", type=int, default=-1, help="untimed steps before warm-up (config2 default 1500)")
+    ap.add_argument("--modes", type=int, default=64, help="Fourier modes of the synthetic velocity field")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="microbes in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_per_gpu = args.microbes or default_n(args.workload)
+    config = {"workload": args.workload, "microbes_per_gpu": n_per_gpu, "microbes_total": n_per_gpu * world,
+              "radius_deg": RADIUS, "p": P_RPS[0], "dt_s": DT, "field": "synthetic random-Fourier, OSCAR 1/3-degree grid "
+              "(72x481x1201), %d modes" % args.modes, "l2": "inputs larger than L2" if n_per_gpu >= 5_000_000
+              else "state fits L2 (config as specified)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = max(1, min(args.steps, 3))
+        warm = 1 if args.warmup > 0 else 0
+        res = run_cpu_reference(args.workload, args.cpu_sample, steps, warm, args.modes)
+        sample = "%d steps of a %d-microbe sub-box of the workload at the same areal density (%.0f pairs/step)" % (
+            steps, res["n_sample"], res["pairs_per_step"])
+        line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "ms_per_step": 1e3 * res["seconds"] / steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 state / f64 arithmetic", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["threads"], "kind": "port",
+                                 "sample": sample, "phases_s_per_step": res["phases_s_per_step"],
+                                 "note": "advect: C restatement of parcels' JIT kernel, OpenMP over all cores; pair "
+                                         "search: the reference's own cKDTree.query_pairs (1 core); RPS: the reference's "
+                                         "Python loop over the set with the rule restated in Python (1 core)"},
+                "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from lagrangian_microbes_b200.simulation import FusedSimulation
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t_setup = time.time()
+    hfs = make_fieldset(args.modes)
+    lon, lat, species, desc = workload_particles(args.workload, n_per_gpu, rank, world)
+    config.update(desc)
+    log("[rank %d] setup: field + particles in %.1f s" % (rank, time.time() - t_setup))
+
+    def new_sim(stream_field):
+        return FusedSimulation(lon, lat, species, RADIUS, *P_RPS, hfs, dt_seconds=DT, seed=0, emit_pairs=True,
+                               pair_capacity=int(max(1 << 20, (8 if args.workload != "config3" else 20) * n_per_gpu)),
+                               regrid_every=0 if args.workload != "config2" else 16, grid_margin=0.5,
+                               stream_field=stream_field)
+
+    sim = new_sim(False)
+    spinup = args.spinup if args.spinup >= 0 else (1500 if args.workload == "config2" else 0)
+    for _ in range(spinup):
+        sim.step()
+    if args.workload == "config2":
+        sim.regrid_every = 0                       # no host syncs inside the timed region
+        sim.step(check=True)
+    for _ in range(args.warmup):
+        sim.step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches0 = sim.engine.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        sim.step()
+    ev1.record()
+    barrier()
+    wall1 = time.time()
+    ms = ev0.elapsed_time(ev1)
+    launches = sim.engine.launch_count() - launches0
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
+    st = sim.stats()
+    rho = st.n_pairs / float(n_per_gpu)
+
+    # per-phase device times (3 extra steps with events between the phases)
+    phase = np.zeros(4)
+    for _ in range(3):
+        sim.step(timing=True)
+        phase += np.array(sim.engine.phase_times())
+    phase /= 3.0
+    barrier()
+
+    # end to end: velocity snapshots streamed H2D from pinned host memory every step, per-step record
+    # (lon, lat, species in particle-id order) read back D2H into pinned host buffers every step.
+    e2e = None
+    if not args.no_e2e:
+        del sim
+        torch.cuda.empty_cache()
+        sim2 = new_sim(True)
+        for _ in range(spinup):
+            sim2.step()
+        rec = [(torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(), torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(),
+                torch.empty(n_per_gpu, dtype=torch.int8).pin_memory()) for _ in range(2)]
+        for k in range(args.warmup):
+            sim2.step()
+            sim2.record_to_host(*rec[k & 1])
+        sim2.engine.host_copies_sync()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tw0 = time.perf_counter()
+        e0.record()
+        h2d = 0
+        for k in range(args.steps):
+            sim2.step()
+            h2d += sim2.h2d_bytes_last_step
+            sim2.record_to_host(*rec[k & 1])
+        sim2.engine.host_copies_sync()
+        e1.record()
+        barrier()
+        tw1 = time.perf_counter()
+        ms_e2e = max(e0.elapsed_time(e1), 1e3 * (tw1 - tw0))     # device events and the host clock around the copies
+        e2e = {"ms": ms_e2e, "h2d": h2d / args.steps, "d2h": 9 * n_per_gpu}
+        lon_chk = rec[(args.steps - 1) & 1][0].numpy()
+        assert np.isfinite(lon_chk).all() and lon_chk.min() > 100.0
+        sim = sim2
+
+    # max over ranks
+    vals = torch.tensor([ms, e2e["ms"] if e2e else 0.0, float(st.n_pairs), float(launches)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, ms_e2e = float(mx[0]), float(mx[1])
+        pairs_total, launches_total = float(sm[2]), int(sm[3])
+    else:
+        ms_e2e = e2e["ms"] if e2e else None
+        pairs_total, launches_total = float(st.n_pairs), int(launches)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    n_total = n_per_gpu * world
+    value = n_total * args.steps / (ms * 1e-3)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = json.load(open(peaks_path))["hbm_gbs"]
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    field_bytes = 2 * 2 * hfs.u.shape[1] * hfs.u.shape[2] * 4              # two snapshots of U and V
+    b_alg = 26.0 + 8.0 * rho + field_bytes / float(n_per_gpu)             # bytes per microbe-step
+    # dominant kernel: pair_units_kernel (9 launches per step): 10 + 8 rho bytes per microbe
+    pair_bytes = (10.0 + 8.0 * rho) * n_per_gpu
+    pair_gbs = pair_bytes / (phase[2] * 1e-3) / 1e9 if phase[2] > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 state / f64 arithmetic", "data": "synthetic", "config": config,
+        "pairs_per_step": pairs_total, "pairs_per_s": pairs_total * args.steps / (ms * 1e-3), "rho": rho,
+        "gpu_launches": launches_total,
+        "clocks": clocks,
+        "phases_ms": {"advect": float(phase[0]), "bin": float(phase[1]), "pairs_rps": float(phase[2]), "stats": float(phase[3])},
+        "step_roofline": {"b_alg_bytes_per_microbe_step": b_alg, "achieved_gbs_per_gpu": value * b_alg / 1e9 / world,
+                          "frac": value * b_alg / 1e9 / world / peak},
+        "roofline": {"kernel": "pair_units_kernel<RPS,EMIT> (9 phase launches per step)", "bound": "hbm",
+                     "achieved": pair_gbs, "peak": peak, "unit": "GB/s", "frac": pair_gbs / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": pair_bytes / 9.0},
+    }
+    if e2e:
+        line["e2e"] = {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                       "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": ms_e2e / args.steps}
+    if world == 1 and not args.no_cpu_baseline:
+        res = run_cpu_reference(args.workload, args.cpu_sample, 2, 1, args.modes)
+        line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["threads"], "kind": "port",
+                                "sample": "2 steps of a %d-microbe sub-box at the workload's areal density (%.0f pairs/step)"
+                                          % (res["n_sample"], res["pairs_per_step"]),
+                                "phases_s_per_step": res["phases_s_per_step"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

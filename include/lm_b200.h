@@ -1,0 +1,168 @@
+/* lm_b200.h -- C ABI of the B200-native lagrangian-microbes hot path.
+ *
+ * The reference (ali-ramadhan/lagrangian-microbes) is pure Python with no FFI of its own; its
+ * hot path is three call sites into third-party native code plus one Python loop:
+ *
+ *   (A3) pset.execute(parcels.AdvectionRK4, runtime=dt, dt=dt, ...)     particle_advecter.py:222-223
+ *   (A5) the random-walk diffusion kick                                  particle_advecter.py:240-242
+ *   (P1/P2) cKDTree(locations).query_pairs(r, p)                         interaction_simulator.py:93,98
+ *   (R1/R2) for pair in pairs: rock_paper_scissors_interaction(...)      interaction_simulator.py:104-105,
+ *                                                                        interactions.py:13-40
+ *
+ * Each entry point below names the call site it replaces.  A maintainer of the reference would
+ * bind these with ctypes (see INTEGRATION.md for the stubs).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - Every function returns an int status: LM_OK (0) or a negative LM_E* code; nothing throws.
+ *   - Unless a parameter says "host", pointers are DEVICE pointers owned by the caller
+ *     (e.g. torch tensors' data_ptr()); all work is enqueued on the given stream (a cudaStream_t
+ *     passed as void*; NULL = default stream) and is asynchronous unless stated otherwise.
+ *   - No function allocates device memory per call: workspaces are sized at lm_create.
+ *   - A handle is bound to one device and may be used from one host thread at a time.
+ *   - Particle ids are int32 (N < 2^31 per handle); species are int8 with ROCK=1, PAPER=2,
+ *     SCISSORS=3 (interactions.py:5).
+ */
+#ifndef LM_B200_H
+#define LM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LM_OK 0
+#define LM_EINVAL (-1)    /* bad argument */
+#define LM_ENOMEM (-2)    /* allocation failed at lm_create */
+#define LM_ECUDA (-3)     /* CUDA runtime error (lm_last_cuda_error has the text) */
+#define LM_ENOSPC (-4)    /* capacity exceeded (particles / cells / pairs) */
+#define LM_ESTATE (-5)    /* call order violated (no field / grid / state yet) */
+#define LM_ENOCONV (-6)   /* explicit-order resolver exceeded its round limit */
+
+typedef struct lm_handle_s *lm_handle;
+
+/* Per-stage time decisions of one RK4 step (stages sample at t, t+dt/2, t+dt/2, t+dt).  All
+ * particles share one clock, so Parcels' cached time index / interpolate-or-hold decision /
+ * float time fraction are the same for every particle; the host computes them once per step
+ * (host mirror: lagrangian_microbes_b200/particle_advecter.py::StageClock). */
+typedef struct {
+    int32_t ti[4];       /* lower time level of each stage */
+    int32_t interp[4];   /* 1: f0 + (f1 - f0) * frac;  0: hold f0 */
+    float frac[4];       /* (float)((t - t0) / (t1 - t0)) */
+} lm_stage_times;
+
+/* Uniform cell grid used for binning: cell = clamp(floor((double(v) - origin) * inv_h), 0, n-1).
+ * 1/inv_h must exceed the interaction radius. */
+typedef struct {
+    double x0, y0, inv_h;
+    int32_t ncx, ncy;
+} lm_grid;
+
+/* Rock-paper-scissors parameters (interactions.py:47-51) + the per-pair random stream key. */
+typedef struct {
+    double pRS, pPR, pSP;
+    uint64_t seed, step;   /* u(i,j) = Philox4x32-10(counter=(i,j,step), key=seed) -> 53-bit double */
+} lm_rps_params;
+
+/* Counters of the last lm_step / lm_interact (host-readable after lm_sync_stats). */
+typedef struct {
+    int64_t n_pairs;          /* pairs found (may exceed the emit capacity) */
+    int64_t n_out_of_bounds;  /* particles that left the velocity grid (left unchanged) */
+    int64_t n_clamped;        /* particles outside the cell grid (binned into edge cells) */
+    int64_t species_count[4]; /* [0]=other, [1]=rock, [2]=paper, [3]=scissors, after the step */
+    float bbox[4];            /* lon_min, lon_max, lat_min, lat_max of the particles */
+} lm_stats;
+
+int lm_version(void);
+const char *lm_error_string(int code);
+const char *lm_last_cuda_error(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cells, int64_t max_pairs);
+int lm_destroy(lm_handle h);
+
+/* ---- inputs -------------------------------------------------------------------------------- */
+/* Replaces Grid/Field/FieldSet construction (particle_advecter.py:177-184).  Borrowed device
+ * pointers: U, V float32 [T][Y][X] (NaN already zeroed), lon float32[X] ascending, lat float32[Y]
+ * ascending.  They must stay valid while the handle uses them. */
+int lm_set_field(lm_handle h, const float *U, const float *V, const float *lon, const float *lat,
+                 int32_t T, int32_t Y, int32_t X);
+/* Swap the U/V data (same lon/lat axes) for another set of T time levels -- for callers that stream
+ * a window of snapshots through a small device buffer.  No synchronisation. */
+int lm_update_field_data(lm_handle h, const float *U, const float *V, int32_t T);
+int lm_set_grid(lm_handle h, const lm_grid *grid);
+int lm_get_grid(lm_handle h, lm_grid *grid_out /* host */);
+
+/* ---- stateless operators on caller-owned arrays in particle-id order ------------------------ */
+/* (A3) One AdvectionRK4 step in place on lon/lat float32[n].  Particles that leave the velocity
+ * grid are left unchanged and counted in lm_stats.n_out_of_bounds, which accumulates over calls
+ * until lm_reset_stats (Parcels raises OutOfBoundsError; the host mirror raises after the sync). */
+int lm_advect_rk4(lm_handle h, float *lon, float *lat, int64_t n, const lm_stage_times *st /* host */,
+                  float dt, void *stream);
+/* (A5) lat += U(-1,1)*amp, then lon += U(-1,1)*amp; Philox keyed (seed, step, id = array index). */
+int lm_diffuse(lm_handle h, float *lon, float *lat, int64_t n, double amp_deg, uint64_t seed, uint64_t step,
+               void *stream);
+/* (P1/P2) All pairs (i<j, array indices) with dx*dx + dy*dy <= r*r evaluated exactly as SciPy does
+ * (float32 positions widened to double).  pairs_out int32[cap][2] in unspecified order;
+ * *n_pairs_out (device int64) receives the number found; LM_ENOSPC is reported by
+ * lm_sync_stats when it exceeded cap (the first cap pairs are valid). */
+int lm_find_pairs(lm_handle h, const float *lon, const float *lat, int64_t n, double r,
+                  int32_t *pairs_out, int64_t cap, int64_t *n_pairs_out, void *stream);
+/* (P1/P2 + R1/R2) Pair search fused with RPS resolution in the canonical cell-phase order
+ * (DESIGN.md §4.3).  species int8[n] updated in place; pairs_out may be NULL (cap = 0). */
+int lm_interact_rps(lm_handle h, const float *lon, const float *lat, int8_t *species, int64_t n, double r,
+                    const lm_rps_params *prm /* host */, int32_t *pairs_out, int64_t cap,
+                    int64_t *n_pairs_out, void *stream);
+/* Per-pair uniforms of the stream above for an explicit pair list (rows i<j). */
+int lm_pair_uniforms(const int32_t *pairs, int64_t n_pairs, uint64_t seed, uint64_t step, double *u_out,
+                     void *stream);
+/* (R1/R2) The reference's sequential in-place loop for an EXPLICIT pair order: pair k = pairs[k],
+ * random draw u[k] consumed iff the species differ when pair k is reached.  Resolved in
+ * conflict-free rounds (a pair fires when it is the lowest-rank pending pair at both of its
+ * particles).  Synchronous; *rounds_out (host) receives the number of rounds. */
+int lm_resolve_rps(lm_handle h, const int32_t *pairs, const double *u, int64_t n_pairs, int8_t *species,
+                   int64_t n, double pRS, double pPR, double pSP, int32_t *rounds_out /* host */, void *stream);
+
+/* ---- resident pipeline (state owned by the handle, kept in (cell, id) order) ------------------ */
+/* Upload n particles (arrays in id order; ids NULL = 0..n-1; device pointers) and bin them. */
+int lm_state_set(lm_handle h, const float *lon, const float *lat, const int8_t *species, const int32_t *ids,
+                 int64_t n, void *stream);
+int64_t lm_state_size(lm_handle h);
+/* One fused step k = prm->step:  [diffuse: the kick the reference applies at the end of iteration
+ * k-1, keyed (seed, k-1)] -> [advect] -> bin -> pair search + RPS keyed (seed, k) (-> emit pairs).
+ * flags: LM_STEP_* below.  st may be NULL when LM_STEP_ADVECT is not set. */
+#define LM_STEP_ADVECT 1
+#define LM_STEP_DIFFUSE 2
+#define LM_STEP_INTERACT 4
+#define LM_STEP_EMIT_PAIRS 8
+#define LM_STEP_STATS 16
+#define LM_STEP_TIMING 32 /* record CUDA events between the phases (read with lm_phase_times) */
+int lm_step(lm_handle h, int32_t flags, const lm_stage_times *st /* host */, float dt, double diffuse_amp_deg,
+            double r, const lm_rps_params *prm /* host */, int32_t *pairs_out, int64_t cap, void *stream);
+/* Scatter the state back to id order: out[id] = value (device outputs, any may be NULL). */
+int lm_state_get(lm_handle h, float *lon_out, float *lat_out, int8_t *species_out, void *stream);
+/* Same, into pinned HOST buffers (device scatter + async D2H on the stream). */
+int lm_state_get_host(lm_handle h, float *lon_host, float *lat_host, int8_t *species_host, void *stream);
+/* Wait for every D2H copy issued by lm_state_get_host (they run on an internal copy stream so
+ * that the next step's kernels overlap them; up to two may be in flight). */
+int lm_host_copies_sync(lm_handle h);
+/* Raw view of the resident arrays in storage order (for halo exchange / tests). */
+int lm_state_view(lm_handle h, float **lon, float **lat, int8_t **species, int32_t **ids, int32_t **cell_start);
+
+/* ---- status -------------------------------------------------------------------------------- */
+/* Synchronise the stream and copy the device counters; returns LM_ENOSPC if pairs overflowed the
+ * emit capacity, LM_OK otherwise. */
+int lm_sync_stats(lm_handle h, lm_stats *out /* host */, void *stream);
+/* Zero the device counters (lm_step and the pair-search operators do this themselves). */
+int lm_reset_stats(lm_handle h, void *stream);
+/* Number of kernels this library launched since the handle was created. */
+int64_t lm_launch_count(lm_handle h);
+/* Device time of the phases of the last lm_step run with LM_STEP_TIMING (synchronises on it):
+ * ms_out[0] diffuse+advect, [1] binning, [2] pair search + RPS, [3] stats.  Host float[4]. */
+int lm_phase_times(lm_handle h, float *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LM_B200_H */

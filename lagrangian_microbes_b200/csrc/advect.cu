@@ -1,0 +1,160 @@
+// RK4 advection + diffusion kick.
+//
+// Replaces  pset.execute(parcels.AdvectionRK4, runtime=dt, dt=dt, ...)   (particle_advecter.py:222-223)
+// and       p.lat += uniform(-1,1)*sqrt(6|dt|Kh); p.lon += ...            (particle_advecter.py:240-242)
+//
+// The arithmetic follows the float32-faithful statement of parcels 2.0.0beta2's JIT path in
+// DESIGN.md §4.1 (the CPU restatement the tests compare against is oracle/rk4.py): float32
+// particle state and grid, float32 xsi/eta widened to double, double bilinear sums rounded to
+// float32, float32 time interpolation, double unit conversion with the SAMPLE point's latitude,
+// double stage updates rounded to float32 (stage 3 pure float32).  Every operation is written
+// with an explicit-rounding intrinsic so nvcc can not contract a*b+c into an FMA: the x86-64
+// code Parcels compiles has none.
+//
+// One thread per particle; the state is kept in (cell, id) order by the binning stage, so the
+// 32 particles of a warp sit within a few 0.01-degree cells and their 16 corner reads per stage
+// collapse to a handful of broadcast L1 hits: the kernel is bound by its fp64 arithmetic
+// (4 x cos + 8 x div per particle), not by HBM (16 B per particle).
+#include "lm_internal.cuh"
+#include "philox.cuh"
+
+namespace lm {
+
+struct StageDev {
+    int ti[4];
+    int interp[4];
+    float frac[4];
+};
+
+__device__ __forceinline__ int search_axis(const float *__restrict__ vals, int n, float x, float v0, float inv_d)
+{
+    if (!(x >= __ldg(vals)) || !(x <= __ldg(vals + n - 1))) return -1;   // also catches NaN
+    int i = (int)((x - v0) * inv_d);
+    i = max(0, min(i, n - 2));
+    while (i < n - 2 && x > __ldg(vals + i + 1)) ++i;
+    while (i > 0 && x < __ldg(vals + i)) --i;
+    return i;
+}
+
+// Sample converted (u, v) [deg/s] at the float32 point (x, y).  Returns false when out of bounds.
+__device__ __forceinline__ bool sample_uv(const FieldDev &f, float x, float y, int ti, int interp, float frac,
+                                          float &u, float &v)
+{
+    const int xi = search_axis(f.lon, f.X, x, f.lon0, f.inv_dx);
+    const int yi = search_axis(f.lat, f.Y, y, f.lat0, f.inv_dy);
+    if (xi < 0 || yi < 0) return false;
+    const float lx0 = __ldg(f.lon + xi), lx1 = __ldg(f.lon + xi + 1);
+    const float ly0 = __ldg(f.lat + yi), ly1 = __ldg(f.lat + yi + 1);
+    const double xsi = (double)__fdiv_rn(__fsub_rn(x, lx0), __fsub_rn(lx1, lx0));
+    const double eta = (double)__fdiv_rn(__fsub_rn(y, ly0), __fsub_rn(ly1, ly0));
+    const double omx = __dsub_rn(1.0, xsi), ome = __dsub_rn(1.0, eta);
+    const double w00 = __dmul_rn(omx, ome), w01 = __dmul_rn(xsi, ome);
+    const double w11 = __dmul_rn(xsi, eta), w10 = __dmul_rn(omx, eta);
+    const size_t slab = (size_t)f.Y * f.X;
+    const size_t off = (size_t)ti * slab + (size_t)yi * f.X + xi;
+
+    auto bilinear = [&](const float *__restrict__ d) -> float {
+        const float d00 = __ldg(d), d01 = __ldg(d + 1), d10 = __ldg(d + f.X), d11 = __ldg(d + f.X + 1);
+        double t = __dmul_rn(w00, (double)d00);
+        t = __dadd_rn(t, __dmul_rn(w01, (double)d01));
+        t = __dadd_rn(t, __dmul_rn(w11, (double)d11));
+        t = __dadd_rn(t, __dmul_rn(w10, (double)d10));
+        return __double2float_rn(t);
+    };
+
+    float uu = bilinear(f.U + off), vv = bilinear(f.V + off);
+    if (interp) {
+        const float u1 = bilinear(f.U + off + slab), v1 = bilinear(f.V + off + slab);
+        uu = __fadd_rn(uu, __fmul_rn(__fsub_rn(u1, uu), frac));
+        vv = __fadd_rn(vv, __fmul_rn(__fsub_rn(v1, vv), frac));
+    }
+    // u *= 1.0 / (1852. * 60. * cos(y * M_PI / 180));   v *= 1.0 / (1852. * 60.)
+    const double ang = __ddiv_rn(__dmul_rn((double)y, 3.14159265358979323846), 180.0);
+    const double cu = __ddiv_rn(1.0, __dmul_rn(111120.0, cos(ang)));
+    constexpr double cv = 1.0 / 111120.0;
+    u = __double2float_rn(__dmul_rn((double)uu, cu));
+    v = __double2float_rn(__dmul_rn((double)vv, cv));
+    return true;
+}
+
+__global__ void __launch_bounds__(256) advect_rk4_kernel(FieldDev f, float *__restrict__ lon, float *__restrict__ lat,
+                                                         int n, StageDev st, float dt, Counters *ctr)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float x = lon[p], y = lat[p];
+    const double xd = (double)x, yd = (double)y, dtd = (double)dt;
+    float u1, v1, u2, v2, u3, v3, u4, v4;
+    bool ok = sample_uv(f, x, y, st.ti[0], st.interp[0], st.frac[0], u1, v1);
+    if (ok) {
+        const float x1 = __double2float_rn(__dadd_rn(xd, __dmul_rn(__dmul_rn((double)u1, .5), dtd)));
+        const float y1 = __double2float_rn(__dadd_rn(yd, __dmul_rn(__dmul_rn((double)v1, .5), dtd)));
+        ok = sample_uv(f, x1, y1, st.ti[1], st.interp[1], st.frac[1], u2, v2);
+    }
+    if (ok) {
+        const float x2 = __double2float_rn(__dadd_rn(xd, __dmul_rn(__dmul_rn((double)u2, .5), dtd)));
+        const float y2 = __double2float_rn(__dadd_rn(yd, __dmul_rn(__dmul_rn((double)v2, .5), dtd)));
+        ok = sample_uv(f, x2, y2, st.ti[2], st.interp[2], st.frac[2], u3, v3);
+    }
+    if (ok) {
+        const float x3 = __fadd_rn(x, __fmul_rn(u3, dt));     // no double literal on this line in the reference
+        const float y3 = __fadd_rn(y, __fmul_rn(v3, dt));
+        ok = sample_uv(f, x3, y3, st.ti[3], st.interp[3], st.frac[3], u4, v4);
+    }
+    if (!ok) {   // Parcels raises OutOfBoundsError; we leave the particle where it is and count it
+        atomicAdd(&ctr->n_oob, 1ull);
+        return;
+    }
+    const float su = __fadd_rn(__fadd_rn(__fadd_rn(u1, __fmul_rn(2.f, u2)), __fmul_rn(2.f, u3)), u4);
+    const float sv = __fadd_rn(__fadd_rn(__fadd_rn(v1, __fmul_rn(2.f, v2)), __fmul_rn(2.f, v3)), v4);
+    lon[p] = __double2float_rn(__dadd_rn(xd, __dmul_rn(__ddiv_rn((double)su, 6.0), dtd)));
+    lat[p] = __double2float_rn(__dadd_rn(yd, __dmul_rn(__ddiv_rn((double)sv, 6.0), dtd)));
+}
+
+cudaError_t launch_advect(const FieldDev &f, float *lon, float *lat, int n, const lm_stage_times &st, float dt,
+                          Counters *ctr, cudaStream_t s, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    StageDev sd;
+    for (int k = 0; k < 4; ++k) {
+        sd.ti[k] = st.ti[k];
+        sd.interp[k] = st.interp[k];
+        sd.frac[k] = st.frac[k];
+    }
+    const int block = 256;
+    advect_rk4_kernel<<<(n + block - 1) / block, block, 0, s>>>(f, lon, lat, n, sd, dt, ctr);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+// p.lat += uniform(-1, 1) * amp; p.lon += uniform(-1, 1) * amp   (lat drawn first; numpy's
+// uniform(-1,1) = -1 + 2*u).  float32 attribute + Python float -> double sum, stored as float32.
+__global__ void __launch_bounds__(256) diffuse_kernel(float *__restrict__ lon, float *__restrict__ lat,
+                                                      const int32_t *__restrict__ ids, int n, double amp,
+                                                      uint32_t seed_lo, uint32_t seed_hi, uint32_t step_lo,
+                                                      uint32_t step_hi)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const uint32_t pid = ids ? (uint32_t)ids[p] : (uint32_t)p;
+    double ua, ub;
+    particle_uniforms(pid, 0u, step_lo, step_hi, seed_lo, seed_hi, ua, ub);
+    const double ka = __dmul_rn(__dadd_rn(-1.0, __dmul_rn(2.0, ua)), amp);
+    const double kb = __dmul_rn(__dadd_rn(-1.0, __dmul_rn(2.0, ub)), amp);
+    lat[p] = __double2float_rn(__dadd_rn((double)lat[p], ka));
+    lon[p] = __double2float_rn(__dadd_rn((double)lon[p], kb));
+}
+
+cudaError_t launch_diffuse(float *lon, float *lat, const int32_t *ids, int n, double amp, uint64_t seed, uint64_t step,
+                           cudaStream_t s, int64_t *launches)
+{
+    if (n <= 0) return cudaSuccess;
+    const int block = 256;
+    diffuse_kernel<<<(n + block - 1) / block, block, 0, s>>>(lon, lat, ids, n, amp, (uint32_t)seed,
+                                                              (uint32_t)(seed >> 32), (uint32_t)step,
+                                                              (uint32_t)(step >> 32));
+    ++*launches;
+    return cudaGetLastError();
+}
+
+}  // namespace lm

@@ -1,0 +1,160 @@
+// Explicit-order rock-paper-scissors resolver + per-pair uniforms.
+//
+// Replaces the reference's sequential in-place loop
+//     for pair in microbe_pairs: pair_interaction(params, props, pair[0], pair[1])
+// (interaction_simulator.py:104-105 -> interactions.py:13-40) for an ARBITRARY caller-given pair
+// order -- in particular the CPython-set iteration order the reference itself uses, which the
+// parity tests feed in verbatim.  rank(pair) = its index k in the array; u[k] is the random draw
+// the reference would make for it (consumed only if the species differ when the pair is reached).
+//
+// Conflict-free rounds: a pending pair fires in a round iff it is the lowest-rank pending pair at
+// BOTH of its particles, so no two firing pairs share a particle and every pair sees exactly the
+// species the sequential loop would have shown it.  Per round:
+//     mark:  head[i] = min(head[i], tag(k)),  head[j] = min(head[j], tag(k))      (64-bit atomicMin)
+//     fire:  head[i] == head[j] == tag(k) ? apply rule : append k to the next pending list
+// tag(k) = (ROUND_MAX - round) << 40 | k, so tags of later rounds are smaller than any left-over of
+// earlier rounds and head[] never needs clearing.
+#include "lm_internal.cuh"
+#include "philox.cuh"
+
+namespace lm {
+
+constexpr unsigned long long ROUND_MAX = (1ull << 23) - 1;
+
+__global__ void __launch_bounds__(256) pair_uniforms_kernel(const int2 *__restrict__ pairs, long long np,
+                                                            uint32_t seed_lo, uint32_t seed_hi, uint32_t step_lo,
+                                                            uint32_t step_hi, double *__restrict__ u)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= np) return;
+    const int2 p = pairs[k];
+    const uint32_t i = (uint32_t)min(p.x, p.y), j = (uint32_t)max(p.x, p.y);
+    u[k] = pair_uniform(i, j, step_lo, step_hi, seed_lo, seed_hi);
+}
+
+cudaError_t launch_pair_uniforms(const int2 *pairs, int64_t np, uint64_t seed, uint64_t step, double *u, cudaStream_t s)
+{
+    if (np <= 0) return cudaSuccess;
+    const int block = 256;
+    pair_uniforms_kernel<<<(unsigned)((np + block - 1) / block), block, 0, s>>>(
+        pairs, np, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, (uint32_t)(step >> 32), u);
+    return cudaGetLastError();
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, long long n, unsigned long long v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// list == nullptr: the pending set is all pairs [0, *cnt_in)
+__global__ void __launch_bounds__(256) resolve_mark_kernel(const int2 *__restrict__ pairs,
+                                                           const int32_t *__restrict__ list,
+                                                           const unsigned int *__restrict__ cnt_in,
+                                                           unsigned int *cnt_zero, unsigned long long round_tag,
+                                                           unsigned long long *head)
+{
+    const unsigned int n = *cnt_in;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *cnt_zero = 0;   // counter of the list after next
+    for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const unsigned int k = list ? (unsigned int)list[t] : t;
+        const int2 p = pairs[k];
+        const unsigned long long tag = round_tag | k;
+        atomicMin(head + p.x, tag);
+        atomicMin(head + p.y, tag);
+    }
+}
+
+__global__ void __launch_bounds__(256) resolve_fire_kernel(const int2 *__restrict__ pairs,
+                                                           const double *__restrict__ u,
+                                                           const int32_t *__restrict__ list,
+                                                           const unsigned int *__restrict__ cnt_in,
+                                                           int32_t *__restrict__ list_out, unsigned int *cnt_out,
+                                                           unsigned long long round_tag,
+                                                           const unsigned long long *__restrict__ head,
+                                                           int8_t *species, double pRS, double pPR, double pSP,
+                                                           unsigned int *rounds_used, unsigned int round_no)
+{
+    const unsigned int n = *cnt_in;
+    const int lane = threadIdx.x & 31;
+    if (n > 0 && blockIdx.x == 0 && threadIdx.x == 0) *rounds_used = round_no + 1;
+    // grid-stride over whole warps so the ballots below are warp-uniform
+    for (unsigned int t0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; t0 < n; t0 += gridDim.x * blockDim.x) {
+        const unsigned int t = t0 + lane;
+        bool defer = false;
+        unsigned int k = 0;
+        if (t < n) {
+            k = list ? (unsigned int)list[t] : t;
+            const int2 p = pairs[k];
+            const unsigned long long tag = round_tag | k;
+            if (head[p.x] == tag && head[p.y] == tag) {
+                const int s1 = species[p.x], s2 = species[p.y];
+                if (s1 != s2 && s1 >= 1 && s1 <= 3 && s2 >= 1 && s2 <= 3) {
+                    int d = s1 - s2;
+                    if (d < 0) d += 3;
+                    const int w = (d == 1) ? s1 : s2, l = (d == 1) ? s2 : s1;
+                    const double pw = (w == 1) ? pRS : ((w == 2) ? pPR : pSP);
+                    const int8_t ns = (int8_t)((u[k] < pw) ? w : l);
+                    species[p.x] = ns;
+                    species[p.y] = ns;
+                }
+            } else {
+                defer = true;
+            }
+        }
+        const unsigned dm = __ballot_sync(0xffffffffu, defer);
+        if (dm) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(cnt_out, (unsigned int)__popc(dm));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (defer) list_out[base + __popc(dm & ((1u << lane) - 1u))] = (int32_t)k;
+        }
+    }
+}
+
+int resolve_explicit(lm_handle_s *h, const int2 *pairs, const double *u, int64_t np, int8_t *species, int64_t n,
+                     double pRS, double pPR, double pSP, int32_t *rounds_out, cudaStream_t s)
+{
+    if (rounds_out) *rounds_out = 0;
+    if (np <= 0) return LM_OK;
+    if (np > h->max_pairs || n > h->max_particles || np >= (1ll << 32)) return LM_ENOSPC;
+    const int block = 256;
+    fill_u64_kernel<<<(unsigned)((n + block - 1) / block), block, 0, s>>>(h->head, n, ~0ull);
+    ++h->launches;
+    unsigned int cnt0[4] = {(unsigned int)np, 0u, 0u, 0u};   // [0],[1] list counters, [2] rounds used
+    cudaError_t e = cudaMemcpyAsync(h->pending_cnt, cnt0, sizeof(cnt0), cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) { set_last_cuda_error(e, "resolve: counter upload"); return LM_ECUDA; }
+    e = cudaStreamSynchronize(s);   // cnt0 is a stack buffer
+    if (e != cudaSuccess) { set_last_cuda_error(e, "resolve: sync"); return LM_ECUDA; }
+
+    unsigned long long pending = (unsigned long long)np;
+    unsigned long long round = 0;
+    const int BATCH = 8;   // rounds between host checks of the pending count
+    while (pending > 0) {
+        unsigned long long want = (pending + block - 1) / block;
+        if (want > kNumSMs * 16ull) want = kNumSMs * 16ull;
+        const unsigned int grid = (unsigned int)want;
+        for (int b = 0; b < BATCH; ++b, ++round) {
+            if (round >= ROUND_MAX) return LM_ENOCONV;
+            const int in = (int)(round & 1), out = in ^ 1;
+            const int32_t *list = (round == 0) ? nullptr : h->pending[in];
+            const unsigned long long tag = (ROUND_MAX - round) << 40;
+            // round r reads counter[in]; it zeroes counter[in] of round r+1 ... i.e. counter[out] must be zero
+            // before fire appends to it: mark(r) zeroes counter[out] (last read by round r-1).
+            resolve_mark_kernel<<<grid, block, 0, s>>>(pairs, list, h->pending_cnt + in, h->pending_cnt + out, tag, h->head);
+            resolve_fire_kernel<<<grid, block, 0, s>>>(pairs, u, list, h->pending_cnt + in, h->pending[out],
+                                                       h->pending_cnt + out, tag, h->head, species, pRS, pPR, pSP,
+                                                       h->pending_cnt + 2, (unsigned int)round);
+            h->launches += 2;
+        }
+        unsigned int c[4] = {0, 0, 0, 0};
+        e = cudaMemcpyAsync(c, h->pending_cnt, sizeof(c), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) { set_last_cuda_error(e, "resolve: round loop"); return LM_ECUDA; }
+        pending = c[round & 1];
+        if (rounds_out) *rounds_out = (int32_t)c[2];
+    }
+    return LM_OK;
+}
+
+}  // namespace lm

@@ -1,0 +1,231 @@
+"""Thin Python wrapper over the C ABI (include/lm_b200.h) on PyTorch CUDA tensors.
+
+PyTorch is used here only for device memory, streams and (elsewhere) torch.distributed; every
+computation is a hand-written CUDA kernel in liblm_b200.so.  There is no CPU path: constructing
+an ``Engine`` without a CUDA device raises.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Grid, RpsParams, StageTimes, Stats, check
+
+
+def make_grid(lon_min, lon_max, lat_min, lat_max, radius, n_particles, max_cells, margin=0.5, cells_per_particle=2.0):
+    """Host policy for the binning grid.
+
+    Cell edge h = k * r * (1 + 2^-20) with the smallest integer k >= 1 whose grid over the
+    margin-padded bounding box has at most ``min(max_cells, max(cells_per_particle * n, 2^16))``
+    cells.  The origin is integral so that ``double(x) - x0`` is exact.  Particles that leave the
+    box are clamped into edge cells by the device (correct, only slower).
+    """
+    r = float(radius)
+    base = (r if r > 0 else 1e-3) * (1.0 + 2.0 ** -20)
+    x0 = math.floor(lon_min - margin)
+    y0 = math.floor(lat_min - margin)
+    sx = (lon_max + margin) - x0
+    sy = (lat_max + margin) - y0
+    budget = int(min(max_cells, max(cells_per_particle * n_particles, 1 << 16)))
+    k = max(1, int(math.ceil(math.sqrt(max(sx * sy, 1e-30) / (base * base) / budget))))
+    while True:
+        h = base * k
+        ncx = int(sx / h) + 2
+        ncy = int(sy / h) + 2
+        if ncx * ncy <= budget:
+            break
+        k += 1
+    return Grid(float(x0), float(y0), 1.0 / h, ncx, ncy)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _f32(t, n=None):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), "expected contiguous CUDA float32"
+    if n is not None:
+        assert t.numel() == n
+    return t
+
+
+class Engine:
+    """One lm_handle bound to one CUDA device."""
+
+    def __init__(self, max_particles, max_cells=None, max_pairs=0, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("lagrangian_microbes_b200 needs a CUDA device: the hot path has no CPU fallback")
+        self.L = _lib.lib()
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.max_particles = int(max_particles)
+        self.max_cells = int(max_cells if max_cells is not None else max(4 * max_particles, 1 << 20))
+        self.max_pairs = int(max_pairs)
+        h = ctypes.c_void_p()
+        check(self.L.lm_create(ctypes.byref(h), self.device.index, self.max_particles, self.max_cells, self.max_pairs),
+              "lm_create")
+        self.h = h
+        self._field = None            # keeps the borrowed field tensors alive
+        self._n_pairs_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _stream():
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    # ---- inputs --------------------------------------------------------------------------------
+    def set_field(self, u, v, lon, lat):
+        """u, v float32 (T, Y, X) NaN-free; lon (X,), lat (Y,) ascending -- CUDA tensors (borrowed)."""
+        u, v, lon, lat = _f32(u), _f32(v), _f32(lon), _f32(lat)
+        T, Y, X = u.shape
+        assert v.shape == u.shape and lon.numel() == X and lat.numel() == Y
+        check(self.L.lm_set_field(self.h, _ptr(u), _ptr(v), _ptr(lon), _ptr(lat), T, Y, X), "lm_set_field")
+        self._field = (u, v, lon, lat)
+
+    def update_field_data(self, u, v):
+        """Swap in another window of time levels (same axes); u, v CUDA float32 (T, Y, X), borrowed."""
+        u, v = _f32(u), _f32(v)
+        assert self._field is not None and u.shape == v.shape and u.shape[1:] == self._field[0].shape[1:]
+        check(self.L.lm_update_field_data(self.h, _ptr(u), _ptr(v), u.shape[0]), "lm_update_field_data")
+        self._field = (u, v, self._field[2], self._field[3])
+
+    def set_grid(self, grid):
+        check(self.L.lm_set_grid(self.h, ctypes.byref(grid)), "lm_set_grid")
+
+    def get_grid(self):
+        g = Grid()
+        check(self.L.lm_get_grid(self.h, ctypes.byref(g)), "lm_get_grid")
+        return g
+
+    # ---- stateless operators ---------------------------------------------------------------------
+    def advect_rk4(self, lon, lat, stage_times, dt):
+        n = lon.numel()
+        check(self.L.lm_advect_rk4(self.h, _ptr(_f32(lon)), _ptr(_f32(lat, n)), n, ctypes.byref(stage_times),
+                                   float(dt), self._stream()), "lm_advect_rk4")
+
+    def diffuse(self, lon, lat, amp_deg, seed, step):
+        n = lon.numel()
+        check(self.L.lm_diffuse(self.h, _ptr(_f32(lon)), _ptr(_f32(lat, n)), n, float(amp_deg), int(seed), int(step),
+                                self._stream()), "lm_diffuse")
+
+    def find_pairs(self, lon, lat, r, pairs_out):
+        """pairs_out: CUDA int32 (cap, 2).  Returns the number of pairs found (host int, synchronises)."""
+        n = lon.numel()
+        assert pairs_out.dtype == torch.int32 and pairs_out.is_contiguous() and pairs_out.shape[1] == 2
+        check(self.L.lm_find_pairs(self.h, _ptr(_f32(lon)), _ptr(_f32(lat, n)), n, float(r), _ptr(pairs_out),
+                                   pairs_out.shape[0], _ptr(self._n_pairs_dev), self._stream()), "lm_find_pairs")
+        st = self.sync_stats()
+        return st.n_pairs
+
+    def interact_rps(self, lon, lat, species, r, pRS, pPR, pSP, seed, step, pairs_out=None):
+        n = lon.numel()
+        assert species.dtype == torch.int8 and species.is_cuda and species.is_contiguous() and species.numel() == n
+        prm = RpsParams(float(pRS), float(pPR), float(pSP), int(seed), int(step))
+        cap = pairs_out.shape[0] if pairs_out is not None else 0
+        check(self.L.lm_interact_rps(self.h, _ptr(_f32(lon)), _ptr(_f32(lat, n)), _ptr(species), n, float(r),
+                                     ctypes.byref(prm), _ptr(pairs_out), cap, _ptr(self._n_pairs_dev),
+                                     self._stream()), "lm_interact_rps")
+
+    def pair_uniforms(self, pairs, seed, step):
+        assert pairs.dtype == torch.int32 and pairs.is_cuda and pairs.is_contiguous()
+        P = pairs.shape[0]
+        u = torch.empty(P, dtype=torch.float64, device=pairs.device)
+        check(self.L.lm_pair_uniforms(_ptr(pairs), P, int(seed), int(step), _ptr(u), self._stream()), "lm_pair_uniforms")
+        return u
+
+    def resolve_rps(self, pairs, u, species, pRS, pPR, pSP):
+        """Explicit-order resolver; returns the number of rounds."""
+        assert pairs.dtype == torch.int32 and pairs.is_contiguous() and u.dtype == torch.float64 and u.is_contiguous()
+        assert species.dtype == torch.int8 and species.is_contiguous()
+        rounds = ctypes.c_int32(0)
+        check(self.L.lm_resolve_rps(self.h, _ptr(pairs), _ptr(u), pairs.shape[0], _ptr(species), species.numel(),
+                                    float(pRS), float(pPR), float(pSP), ctypes.byref(rounds), self._stream()),
+              "lm_resolve_rps")
+        return rounds.value
+
+    # ---- resident pipeline -------------------------------------------------------------------------
+    def state_set(self, lon, lat, species=None, ids=None):
+        n = lon.numel()
+        if species is not None:
+            assert species.dtype == torch.int8 and species.is_cuda and species.numel() == n
+        if ids is not None:
+            assert ids.dtype == torch.int32 and ids.is_cuda and ids.numel() == n
+        check(self.L.lm_state_set(self.h, _ptr(_f32(lon)), _ptr(_f32(lat, n)), _ptr(species), _ptr(ids), n,
+                                  self._stream()), "lm_state_set")
+
+    def state_size(self):
+        return int(self.L.lm_state_size(self.h))
+
+    def step(self, flags, stage_times=None, dt=0.0, diffuse_amp_deg=0.0, r=0.0, rps=None, pairs_out=None):
+        cap = pairs_out.shape[0] if pairs_out is not None else 0
+        check(self.L.lm_step(self.h, int(flags), ctypes.byref(stage_times) if stage_times is not None else None,
+                             float(dt), float(diffuse_amp_deg), float(r),
+                             ctypes.byref(rps) if rps is not None else None, _ptr(pairs_out), cap, self._stream()),
+              "lm_step")
+
+    def state_get(self, lon_out=None, lat_out=None, species_out=None):
+        check(self.L.lm_state_get(self.h, _ptr(lon_out), _ptr(lat_out), _ptr(species_out), self._stream()), "lm_state_get")
+
+    def state_get_host(self, lon_host=None, lat_host=None, species_host=None):
+        """Outputs are pinned CPU tensors (or None); copies complete after ``host_copies_sync``."""
+        for t in (lon_host, lat_host, species_host):
+            assert t is None or (not t.is_cuda and t.is_pinned() and t.is_contiguous())
+        check(self.L.lm_state_get_host(self.h, _ptr(lon_host), _ptr(lat_host), _ptr(species_host), self._stream()),
+              "lm_state_get_host")
+
+    def host_copies_sync(self):
+        check(self.L.lm_host_copies_sync(self.h), "lm_host_copies_sync")
+
+    def state_view(self):
+        """Raw resident arrays in storage (cell, id) order as torch tensors (no copy): lon, lat, species, ids, cell_start."""
+        p = [ctypes.c_void_p() for _ in range(5)]
+        check(self.L.lm_state_view(self.h, *[ctypes.byref(x) for x in p]), "lm_state_view")
+        n = self.state_size()
+        g = self.get_grid()
+
+        def view(ptr, count, dtype, itemsize):
+            if count == 0:
+                return torch.empty(0, dtype=dtype, device=self.device)
+            arr = _CudaArray(ptr.value, count, itemsize, np.dtype({torch.float32: "f4", torch.int8: "i1", torch.int32: "i4"}[dtype]).str)
+            return torch.as_tensor(arr, device=self.device)
+        return (view(p[0], n, torch.float32, 4), view(p[1], n, torch.float32, 4), view(p[2], n, torch.int8, 1),
+                view(p[3], n, torch.int32, 4), view(p[4], g.ncx * g.ncy + 1, torch.int32, 4))
+
+    # ---- status ----------------------------------------------------------------------------------
+    def sync_stats(self, raise_on_overflow=True):
+        st = Stats()
+        rc = self.L.lm_sync_stats(self.h, ctypes.byref(st), self._stream())
+        if rc == _lib.LM_ENOSPC and not raise_on_overflow:
+            return st
+        check(rc, "lm_sync_stats")
+        return st
+
+    def reset_stats(self):
+        check(self.L.lm_reset_stats(self.h, self._stream()), "lm_reset_stats")
+
+    def phase_times(self):
+        """[advect, bin, pairs+rps, stats] device milliseconds of the last step run with LM_STEP_TIMING."""
+        ms = (ctypes.c_float * 4)()
+        check(self.L.lm_phase_times(self.h, ms), "lm_phase_times")
+        return list(ms)
+
+    def launch_count(self):
+        return int(self.L.lm_launch_count(self.h))
+
+
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier so torch can wrap a raw device pointer without copying."""
+
+    def __init__(self, ptr, count, itemsize, typestr):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 2}

@@ -1,0 +1,105 @@
+"""File formats either side of the hot path: the reference's chunk pickles
+and its two NetCDF files, written without xarray/netCDF4 (absent here).
+
+* chunk pickles  ``particle_locations_{start:05d}_{end:05d}_tile{id:02d}.pickle``:
+  ``joblib.dump({"time": [...], "lat": f32(iters, n), "lon": f32(iters, n)}, compress=("zlib", 3))``
+  -- byte-compatible with /root/reference/particle_advecter.py:201-214,246-249.
+* ``particle_data.nc`` (particle_advecter.py:262-303) and ``microbe_data.nc``
+  (interaction_simulator.py:68-77,119-122): dims ("particle number", "time"), float32
+  ``longitude`` / ``latitude`` (+ int8 ``species``), coordinate ``particle number`` = 1..N.
+  Written as NetCDF-3 (64-bit offset) through ``scipy.io.netcdf_file``, which xarray opens; the
+  time coordinate is CF-encoded ("seconds since <start>").  NetCDF-3 caps a variable at 4 GiB; past
+  that the same arrays go to ``<name>.npz.d/<var>.npy`` and readers here accept either.
+"""
+import os
+import pickle
+from datetime import datetime, timedelta
+
+import numpy as np
+
+_NC3_VAR_LIMIT = (1 << 32) - 4
+
+
+def chunk_pickle_name(start_iter, end_iter, tile_id):
+    return "particle_locations_" + str(start_iter).zfill(5) + "_" + str(end_iter).zfill(5) + \
+           "_tile" + str(tile_id).zfill(2) + ".pickle"
+
+
+def dump_chunk(filepath, times, lat, lon):
+    import joblib
+    with open(filepath, "wb") as f:
+        joblib.dump({"time": list(times), "lat": lat, "lon": lon}, f, compress=("zlib", 3),
+                    protocol=pickle.HIGHEST_PROTOCOL)
+
+
+def parse_chunk_name(filename):
+    """-> (start_iter, end_iter, tile_id), as particle_advecter.py:287-290 does."""
+    parts = os.path.basename(filename).split("_")
+    return int(parts[2]), int(parts[3]), int(parts[4][4:6])
+
+
+class ParticleFile:
+    """In-memory view of particle_data.nc / microbe_data.nc: dict of (N, Nt) arrays + times."""
+
+    def __init__(self, variables, times):
+        self.variables = variables
+        self.times = list(times)
+
+    def __getitem__(self, name):
+        return self.variables[name]
+
+
+def write_particle_file(filepath, variables, times):
+    """variables: {"longitude": f32 (N, Nt), "latitude": ..., ["species": int8 (N, Nt)]}."""
+    first = next(iter(variables.values()))
+    N, Nt = first.shape
+    t0 = times[0] if len(times) else datetime(1970, 1, 1)
+    secs = np.array([(t - t0).total_seconds() for t in times], dtype=np.float64)
+    if all(v.nbytes <= _NC3_VAR_LIMIT for v in variables.values()):
+        from scipy.io import netcdf_file
+        with netcdf_file(filepath, "w", version=2) as nc:
+            nc.createDimension("particle number", N)
+            nc.createDimension("time", Nt)
+            pn = nc.createVariable("particle number", np.dtype("int32"), ("particle number",))
+            pn[:] = np.arange(1, N + 1, dtype=np.int32)
+            tv = nc.createVariable("time", np.dtype("float64"), ("time",))
+            tv[:] = secs
+            tv.units = "seconds since " + t0.strftime("%Y-%m-%d %H:%M:%S")
+            tv.calendar = "proleptic_gregorian"
+            for name, arr in variables.items():
+                var = nc.createVariable(name, arr.dtype, ("particle number", "time"))
+                var[:] = arr
+        return filepath
+    d = filepath + ".npz.d"
+    os.makedirs(d, exist_ok=True)
+    np.save(os.path.join(d, "time_seconds.npy"), secs)
+    with open(os.path.join(d, "time_origin.txt"), "w") as f:
+        f.write(t0.strftime("%Y-%m-%d %H:%M:%S"))
+    for name, arr in variables.items():
+        np.save(os.path.join(d, name + ".npy"), arr)
+    return d
+
+
+def read_particle_file(filepath):
+    if os.path.isfile(filepath):
+        from scipy.io import netcdf_file
+        with netcdf_file(filepath, "r", mmap=False) as nc:
+            names = [k for k in nc.variables if k not in ("particle number", "time")]
+            # NetCDF-3 stores big-endian; hand back native-endian arrays
+            variables = {k: np.ascontiguousarray(nc.variables[k][:]).astype(nc.variables[k][:].dtype.newbyteorder("="))
+                         for k in names}
+            secs = np.array(nc.variables["time"][:], dtype=np.float64)
+            units = nc.variables["time"].units
+            units = units.decode() if isinstance(units, bytes) else units
+        t0 = datetime.strptime(units.replace("seconds since ", ""), "%Y-%m-%d %H:%M:%S")
+    else:
+        d = filepath + ".npz.d"
+        if not os.path.isdir(d):
+            raise FileNotFoundError(filepath)
+        secs = np.load(os.path.join(d, "time_seconds.npy"))
+        with open(os.path.join(d, "time_origin.txt")) as f:
+            t0 = datetime.strptime(f.read().strip(), "%Y-%m-%d %H:%M:%S")
+        variables = {fn[:-4]: np.load(os.path.join(d, fn), mmap_mode="r") for fn in sorted(os.listdir(d))
+                     if fn.endswith(".npy") and fn != "time_seconds.npy"}
+    times = [t0 + timedelta(seconds=float(s)) for s in secs]
+    return ParticleFile(variables, times)

@@ -1,0 +1,187 @@
+"""FusedSimulation: advect -> (diffuse) -> bin -> pair search + RPS in one device-resident loop.
+
+The reference couples its two phases through disk: ``ParticleAdvecter`` writes every position to
+``particle_data.nc`` and ``InteractionSimulator`` reads it back step by step
+(/root/reference/rock_paper_scissors_example.py:25-36).  Species never feed back into advection,
+so running both per step on resident state is semantically identical and removes
+the disk round trip.  This class is that fused driver loop; it produces the same per-step record
+the two reference classes produce between them (positions after step n, species after step n's
+interactions: particle_advecter.py:233-235, interaction_simulator.py:108-110).
+
+One ``step()`` is one ``lm_step`` call (include/lm_b200.h): ~17 kernel launches, no host
+synchronisation.  Every ``regrid_every`` steps the particles' bounding box is read back (one
+small sync) and the binning grid is re-fitted if particles approach its edge.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import RpsParams
+from .engine import Engine, make_grid
+from .particle_advecter import OutOfBoundsError, StageClock
+
+
+class FusedSimulation:
+    def __init__(self, lons, lats, species, radius, pRS, pPR, pSP, fieldset, dt_seconds=3600.0, Kh=0.0, seed=0,
+                 emit_pairs=True, pair_capacity=None, regrid_every=16, grid_margin=0.5, cells_per_particle=2.0,
+                 max_cells=None, device=None, interact=True, advect=True, stream_field=False):
+        lons = np.ascontiguousarray(lons, dtype=np.float32)      # Parcels keeps float32 positions
+        lats = np.ascontiguousarray(lats, dtype=np.float32)
+        species = np.ascontiguousarray(species, dtype=np.int8)
+        n = lons.size
+        assert lats.size == n and species.size == n
+        self.n = n
+        self.radius = float(radius)
+        self.rps = RpsParams(float(pRS), float(pPR), float(pSP), int(seed), 0)
+        self.dt = float(dt_seconds)
+        self.Kh_deg2 = float(Kh) / 1e10                          # particle_advecter.py:121
+        self.diffuse_amp = float(np.sqrt(6 * np.fabs(np.float32(self.dt)) * self.Kh_deg2))
+        self.seed = int(seed)
+        self.iteration = 0
+        self.regrid_every = int(regrid_every)
+        self.grid_margin = float(grid_margin)
+        self.cells_per_particle = float(cells_per_particle)
+        self.interact = bool(interact)
+        self.advect = bool(advect)
+
+        if max_cells is None:
+            max_cells = int(max(4 * cells_per_particle * n, 1 << 20))
+        self.engine = Engine(max_particles=n, max_cells=max_cells, max_pairs=0, device=device)
+        dev = self.engine.device
+        self.fieldset = fieldset
+        self.stream_field = bool(stream_field) and fieldset is not None
+        self.h2d_bytes_last_step = 0
+        if fieldset is not None and self.stream_field:
+            # Velocity snapshots stay in pinned host memory; each step uploads the (2 or 3) time levels
+            # its four RK4 stages bracket into one of two device windows on a side stream, overlapped
+            # with the previous step's kernels (velocity input path).
+            self._u_host = torch.from_numpy(fieldset.u).pin_memory()
+            self._v_host = torch.from_numpy(fieldset.v).pin_memory()
+            _, Y, X = fieldset.u.shape
+            self._win_u = [torch.zeros((3, Y, X), dtype=torch.float32, device=dev) for _ in range(2)]
+            self._win_v = [torch.zeros((3, Y, X), dtype=torch.float32, device=dev) for _ in range(2)]
+            self._grid_lon = torch.from_numpy(fieldset.lon).to(dev)
+            self._grid_lat = torch.from_numpy(fieldset.lat).to(dev)
+            self.engine.set_field(self._win_u[0], self._win_v[0], self._grid_lon, self._grid_lat)
+            self._h2d_stream = torch.cuda.Stream(device=dev)
+            self._win_ready = [torch.cuda.Event() for _ in range(2)]
+            self._win_free = [torch.cuda.Event() for _ in range(2)]
+            for e in self._win_free:
+                e.record()
+            self._win_idx = 0
+            self.clock = StageClock(fieldset.time)
+        elif fieldset is not None:
+            self.engine.set_field(*fieldset.to_device(dev))
+            self.clock = StageClock(fieldset.time)
+        else:
+            assert not advect, "advection needs a fieldset"
+            self.clock = None
+
+        self.emit_pairs = bool(emit_pairs) and self.interact
+        if self.emit_pairs:
+            if pair_capacity is None:
+                pair_capacity = max(1 << 20, 8 * n)
+            self.pairs = torch.empty((int(pair_capacity), 2), dtype=torch.int32, device=dev)
+        else:
+            self.pairs = None
+
+        self._fit_grid(float(lons.min()), float(lons.max()), float(lats.min()), float(lats.max()))
+        self.engine.state_set(torch.from_numpy(lons).to(dev), torch.from_numpy(lats).to(dev),
+                              torch.from_numpy(species).to(dev))
+        self.total_pairs = 0
+        self.last_stats = None
+
+    # ---- grid policy -------------------------------------------------------------------------------
+    def _fit_grid(self, x0, x1, y0, y1):
+        self._bbox = (x0, x1, y0, y1)
+        g = make_grid(x0, x1, y0, y1, self.radius, self.n, self.engine.max_cells, margin=self.grid_margin,
+                      cells_per_particle=self.cells_per_particle)
+        self.engine.set_grid(g)
+        self.grid = g
+
+    def _maybe_regrid(self, st):
+        x0, x1, y0, y1 = st.bbox[0], st.bbox[1], st.bbox[2], st.bbox[3]
+        bx0, bx1, by0, by1 = self._bbox
+        m = self.grid_margin
+        guard = 0.25 * m
+        grew = (x0 < bx0 - m + guard) or (x1 > bx1 + m - guard) or (y0 < by0 - m + guard) or (y1 > by1 + m - guard)
+        shrank = (x1 - x0 + 2 * m) * (y1 - y0 + 2 * m) < 0.5 * (bx1 - bx0 + 2 * m) * (by1 - by0 + 2 * m)
+        if grew or shrank:
+            self._fit_grid(x0, x1, y0, y1)
+
+    # ---- stepping ----------------------------------------------------------------------------------
+    def _stream_window(self, st_times):
+        """Upload the time levels this step samples and point the engine at them."""
+        lo = min(st_times.ti[k] for k in range(4))
+        hi = max(st_times.ti[k] + (1 if st_times.interp[k] else 0) for k in range(4))
+        cnt = hi - lo + 1
+        assert cnt <= 3, "one RK4 step spans more than three velocity snapshots"
+        k = self._win_idx
+        self._win_idx ^= 1
+        with torch.cuda.stream(self._h2d_stream):
+            self._h2d_stream.wait_event(self._win_free[k])        # the step that last read window k is done
+            self._win_u[k][:cnt].copy_(self._u_host[lo:hi + 1], non_blocking=True)
+            self._win_v[k][:cnt].copy_(self._v_host[lo:hi + 1], non_blocking=True)
+            self._win_ready[k].record(self._h2d_stream)
+        torch.cuda.current_stream().wait_event(self._win_ready[k])
+        self.engine.update_field_data(self._win_u[k], self._win_v[k])
+        for j in range(4):
+            st_times.ti[j] -= lo
+        self.h2d_bytes_last_step = 2 * cnt * self._win_u[k][0].numel() * 4
+        return k
+
+    def step(self, check=False, timing=False):
+        flags = 0
+        st_times = None
+        win = None
+        if self.advect:
+            flags |= _lib.LM_STEP_ADVECT
+            st_times = self.clock.next_step(self.dt)
+            if self.stream_field:
+                win = self._stream_window(st_times)
+        if timing:
+            flags |= _lib.LM_STEP_TIMING
+        self.rps.step = self.iteration          # 0-based step index = InteractionSimulator's ``i``
+        if self.Kh_deg2 > 0 and self.iteration > 0:
+            flags |= _lib.LM_STEP_DIFFUSE       # kick of the previous iteration (particle_advecter.py:240-242)
+        self.iteration += 1
+        if self.interact:
+            flags |= _lib.LM_STEP_INTERACT
+        if self.emit_pairs:
+            flags |= _lib.LM_STEP_EMIT_PAIRS
+        want_stats = check or (self.regrid_every > 0 and self.iteration % self.regrid_every == 0)
+        if want_stats:
+            flags |= _lib.LM_STEP_STATS
+        self.engine.step(flags, st_times, self.dt, self.diffuse_amp, self.radius, self.rps, self.pairs)
+        if win is not None:
+            self._win_free[win].record()
+        if want_stats:
+            st = self.engine.sync_stats()
+            self.last_stats = st
+            if st.n_out_of_bounds:
+                raise OutOfBoundsError("%d particle(s) left the velocity grid at iteration %d"
+                                       % (st.n_out_of_bounds, self.iteration))
+            self._maybe_regrid(st)
+            return st
+        return None
+
+    def run(self, n_steps):
+        for _ in range(n_steps):
+            self.step()
+
+    def stats(self):
+        """Counters of the most recent step (synchronises)."""
+        return self.engine.sync_stats()
+
+    def download(self):
+        """(lon, lat, species) in particle-id order as NumPy arrays."""
+        dev = self.engine.device
+        lon = torch.empty(self.n, dtype=torch.float32, device=dev)
+        lat = torch.empty(self.n, dtype=torch.float32, device=dev)
+        sp = torch.empty(self.n, dtype=torch.int8, device=dev)
+        self.engine.state_get(lon, lat, sp)
+        return lon.cpu().numpy(), lat.cpu().numpy(), sp.cpu().numpy()
+
+    def record_to_host(self, lon_pin, lat_pin, sp_pin):
+        """Asynchronous per-step record into pinned host tensors (call engine.host_copies_sync() before reading)."""
+        self.engine.state_get_host(lon_pin, lat_pin, sp_pin)

@@ -1,0 +1,150 @@
+"""Rock-paper-scissors oracle (TEST INFRASTRUCTURE ONLY).
+
+Restates /root/reference/interactions.py:13-40 (``rock_paper_scissors_interaction``)
+and the sequential in-place pair loop of /root/reference/interaction_simulator.py:104-105:
+
+    for pair in microbe_pairs:
+        pair_interaction(parameters, microbe_properties, pair[0], pair[1])
+
+The reference draws ``np.random.rand()`` only when the two species differ
+(interactions.py:17-20).  Parity is defined with an injected per-pair stream
+``u[k]``: pair k consumes ``u[k]`` iff its species differ at the
+moment it is processed -- which is what patching ``np.random.rand`` with
+``lambda: u[k]`` does to the unmodified function (tests/golden/make_golden.py).
+
+Pinned by tests/golden/rps_*.npz, produced by the UNMODIFIED reference function.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROCK, PAPER, SCISSORS = 1, 2, 3   # interactions.py:5
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def rps_pair(species, p1, p2, r, pRS, pPR, pSP):
+    """One call of interactions.py:13-40 with the random draw ``r`` supplied by the caller.
+
+    Returns True iff the draw was consumed (species differed).
+    """
+    if species[p1] != species[p2]:                       # :17
+        s1, s2 = species[p1], species[p2]                # :18
+        winner = None                                    # :22
+        if s1 == ROCK and s2 == SCISSORS:                # :24-35
+            winner = p1 if r < pRS else p2
+        elif s1 == ROCK and s2 == PAPER:
+            winner = p2 if r < pPR else p1
+        elif s1 == PAPER and s2 == ROCK:
+            winner = p1 if r < pPR else p2
+        elif s1 == PAPER and s2 == SCISSORS:
+            winner = p2 if r < pSP else p1
+        elif s1 == SCISSORS and s2 == ROCK:
+            winner = p2 if r < pRS else p1
+        elif s1 == SCISSORS and s2 == PAPER:
+            winner = p1 if r < pSP else p2
+        if winner == p1:                                 # :37-40
+            species[p2] = species[p1]
+        elif winner == p2:
+            species[p1] = species[p2]
+        return True
+    return False
+
+
+def rps_sequential_py(species, pairs, u, pRS, pPR, pSP):
+    """Pure-Python sequential loop (small cases).  Mutates and returns ``species`` (int8)."""
+    species = np.asarray(species)
+    assert species.dtype == np.int8
+    pairs = np.asarray(pairs).reshape(-1, 2)
+    u = np.asarray(u, dtype=np.float64)
+    draws = 0
+    for k in range(pairs.shape[0]):
+        draws += rps_pair(species, int(pairs[k, 0]), int(pairs[k, 1]), float(u[k]), pRS, pPR, pSP)
+    return species, draws
+
+
+# ---------------------------------------------------------------------------------------------
+# C restatement (same rule, same order) for cases too large for a Python loop.
+# ---------------------------------------------------------------------------------------------
+_lib = None
+
+
+def build_c(force=False):
+    """Compile oracle/rps_seq.c + oracle/rk4_c.c into oracle/_build/liboracle.so (gcc -O2 -fopenmp)."""
+    out_dir = os.path.join(_HERE, "_build")
+    so = os.path.join(out_dir, "liboracle.so")
+    srcs = [os.path.join(_HERE, "rps_seq.c"), os.path.join(_HERE, "rk4_c.c")]
+    if (not force) and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(s) for s in srcs):
+        return so
+    os.makedirs(out_dir, exist_ok=True)
+    # -ffp-contract=off: the restated C must not fuse multiply-adds (Parcels' JIT'd C on
+    # x86-64 without -march flags has no FMA); keeps the arithmetic IEEE-reproducible.
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-fopenmp", "-ffp-contract=off", "-o", so] + srcs + ["-lm"]
+    subprocess.check_call(cmd)
+    return so
+
+
+def load_c():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build_c())
+        _lib.rps_sequential.restype = ctypes.c_int64
+        _lib.rps_sequential.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.c_double, ctypes.c_double, ctypes.c_double]
+    return _lib
+
+
+def rps_sequential_c(species, pairs, u, pRS, pPR, pSP):
+    """C sequential loop.  Mutates and returns ``species`` (int8 C-contiguous) and the draw count."""
+    lib = load_c()
+    species = np.ascontiguousarray(species)
+    assert species.dtype == np.int8
+    pairs = np.ascontiguousarray(np.asarray(pairs, dtype=np.int64).reshape(-1, 2))
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    assert u.shape[0] == pairs.shape[0]
+    draws = lib.rps_sequential(species.ctypes.data, pairs.ctypes.data, u.ctypes.data, pairs.shape[0],
+                               float(pRS), float(pPR), float(pSP))
+    return species, int(draws)
+
+
+# ---------------------------------------------------------------------------------------------
+# Canonical pair order of the fused device path ("cell-phase order").
+# ---------------------------------------------------------------------------------------------
+def cell_phase_order(pairs, lon32, lat32, grid):
+    """Return ``pairs`` (rows i<j, original ids) re-ordered into the device's canonical order.
+
+    grid = dict(x0, y0, inv_h, ncx, ncy) as reported by ``lm_get_grid``.  Every pair joins two
+    particles whose cells differ by at most one in each direction.  Order key:
+
+        phase   0: same cell                                   unit = that cell
+                1+(cx&1): east neighbour  (cx,cy)-(cx+1,cy)    unit = west cell
+                3*(cy&1)+3: north-west    (cx,cy)-(cx-1,cy+1)  unit = south cell
+                3*(cy&1)+4: north         (cx,cy)-(cx  ,cy+1)
+                3*(cy&1)+5: north-east    (cx,cy)-(cx+1,cy+1)
+        then unit (anchor cell key cy*ncx+cx), then id of the particle in the anchor cell,
+        then id of the other particle (same cell: smaller id, larger id).
+
+    Units inside one phase touch disjoint particles, so their relative order is immaterial;
+    the device runs them concurrently.
+    """
+    from .pairs import cell_index
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    i, j = pairs[:, 0], pairs[:, 1]
+    cx = cell_index(lon32, grid["x0"], grid["inv_h"], grid["ncx"])
+    cy = cell_index(lat32, grid["y0"], grid["inv_h"], grid["ncy"])
+    cxi, cyi, cxj, cyj = cx[i], cy[i], cx[j], cy[j]
+    assert np.all(np.abs(cxi - cxj) <= 1) and np.all(np.abs(cyi - cyj) <= 1), "pair spans non-adjacent cells"
+    same = (cxi == cxj) & (cyi == cyj)
+    # anchor = i unless j's cell is "before" i's: lower row, or same row and smaller cx
+    j_anchor = (cyj < cyi) | ((cyj == cyi) & (cxj < cxi))
+    a = np.where(j_anchor, j, i)
+    b = np.where(j_anchor, i, j)
+    cxa, cya, cxb, cyb = cx[a], cy[a], cx[b], cy[b]
+    d = cxb - cxa
+    phase = np.where(same, 0,
+                     np.where(cya == cyb, 1 + (cxa & 1), 3 * (cya & 1) + 4 + d))
+    unit = cya * np.int64(grid["ncx"]) + cxa
+    order = np.lexsort((b, a, unit, phase))
+    return pairs[order], phase[order]

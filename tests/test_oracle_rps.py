@@ -1,0 +1,87 @@
+"""RPS oracle: restatements (Python + C) against goldens made by the UNMODIFIED reference function."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import pairs as opairs
+from oracle import philox
+from oracle import rps as orps
+
+CASES = ["rps_uniform", "rps_clustered", "rps_oddspecies"]
+
+
+def _grid(g):
+    return dict(x0=float(g["grid"][0]), y0=float(g["grid"][1]), inv_h=float(g["grid"][2]),
+                ncx=int(g["grid_n"][0]), ncy=int(g["grid_n"][1]))
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("impl", ["py", "c"])
+def test_restatement_matches_reference_in_reference_order(name, impl):
+    g = golden(name + ".npz")
+    fn = orps.rps_sequential_py if impl == "py" else orps.rps_sequential_c
+    sp, draws = fn(g["species0"].copy(), g["pairs_ref_order"], g["u_ref"], float(g["pRS"]), float(g["pPR"]), float(g["pSP"]))
+    assert np.array_equal(sp, g["species_ref"])
+    assert 0 < draws <= g["pairs_ref_order"].shape[0]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_restatement_matches_reference_in_cell_phase_order(name):
+    g = golden(name + ".npz")
+    sp, _ = orps.rps_sequential_c(g["species0"].copy(), g["pairs_cell_order"], philox.pair_uniforms(
+        g["pairs_cell_order"][:, 0], g["pairs_cell_order"][:, 1], int(g["step"]), int(g["seed"])),
+        float(g["pRS"]), float(g["pPR"]), float(g["pSP"]))
+    assert np.array_equal(sp, g["species_cell"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_cell_phase_order_is_reproducible_and_conflict_free(name):
+    g = golden(name + ".npz")
+    lon, lat, grid = g["lon"], g["lat"], _grid(g)
+    pairs = opairs.sort_pairs(g["pairs_ref_order"])
+    order, phase = orps.cell_phase_order(pairs, lon, lat, grid)
+    assert np.array_equal(order.astype(np.int32), g["pairs_cell_order"])
+    assert np.all(np.diff(phase) >= 0) and phase.min() >= 0 and phase.max() <= 8
+    # inside a phase, a particle belongs to exactly one unit (anchor cell)
+    cx = opairs.cell_index(lon, grid["x0"], grid["inv_h"], grid["ncx"])
+    cy = opairs.cell_index(lat, grid["y0"], grid["inv_h"], grid["ncy"])
+    key = cy * grid["ncx"] + cx
+    for ph in range(9):
+        sel = order[phase == ph]
+        if sel.shape[0] == 0:
+            continue
+        ka, kb = key[sel[:, 0]], key[sel[:, 1]]
+        anchor = np.minimum(ka, kb) if ph != 3 and ph != 6 else None
+        if ph == 0:
+            assert np.array_equal(ka, kb)
+            continue
+        # unit id = unordered cell pair; every cell may appear in at most one unit of the phase
+        units = {(int(min(a, b)), int(max(a, b))) for a, b in zip(ka, kb)}
+        cells = [c for u in units for c in u]
+        assert len(cells) == len(set(cells))
+
+
+def test_order_matters_and_stream_is_per_pair():
+    g = golden("rps_uniform.npz")
+    # the two orders give different species fields: the sequential semantics are order-sensitive
+    assert not np.array_equal(g["species_ref"], g["species_cell"])
+    # draws are consumed only when species differ: equal-species pairs leave everything untouched
+    sp = np.ones(10, dtype=np.int8)
+    out, draws = orps.rps_sequential_py(sp.copy(), np.array([[0, 1], [2, 3]]), np.array([0.1, 0.9]), 0.5, 0.5, 0.5)
+    assert draws == 0 and np.array_equal(out, sp)
+
+
+def test_rule_table():
+    R, P, S = 1, 2, 3
+    # (s1, s2, r, expected pair of species) with pRS=.2, pPR=.5, pSP=.8
+    table = [(R, S, 0.1, (R, R)), (R, S, 0.3, (S, S)), (S, R, 0.1, (R, R)), (S, R, 0.3, (S, S)),
+             (R, P, 0.4, (P, P)), (R, P, 0.6, (R, R)), (P, R, 0.4, (P, P)), (P, R, 0.6, (R, R)),
+             (P, S, 0.7, (S, S)), (P, S, 0.9, (P, P)), (S, P, 0.7, (S, S)), (S, P, 0.9, (P, P)),
+             (R, S, 0.2, (S, S))]      # strict '<': r == pRS is the backward outcome
+    for s1, s2, r, want in table:
+        sp = np.array([s1, s2], dtype=np.int8)
+        orps.rps_pair(sp, 0, 1, r, 0.2, 0.5, 0.8)
+        assert tuple(sp) == want
+        sp = np.array([s1, s2], dtype=np.int8)
+        orps.rps_sequential_c(sp, np.array([[0, 1]]), np.array([r]), 0.2, 0.5, 0.8)
+        assert tuple(sp) == want
