@@ -73,6 +73,7 @@ int lm_destroy(lm_handle h)
     cudaFree(h->keys); cudaFree(h->slots); cudaFree(h->cell_count); cudaFree(h->cell_start);
     cudaFree(h->cell_cursor); cudaFree(h->block_sums); cudaFree(h->ctr); cudaFree(h->head);
     cudaFree(h->pending_cnt);
+    cudaFree(h->hits); cudaFree(h->meta);
     for (int k = 0; k < 5; ++k)
         if (h->ev_phase[k]) cudaEventDestroy(h->ev_phase[k]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -93,6 +94,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     h->max_particles = max_particles;
     h->max_cells = max_cells;
     h->max_pairs = max_pairs;
+    h->emit_cap = h->rps_cap = -1;
     bool ok = true;
     for (int k = 0; k < 2; ++k) {
         ok = ok && dev_alloc(&h->lon[k], max_particles) && dev_alloc(&h->lat[k], max_particles);
@@ -104,6 +106,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     ok = ok && dev_alloc(&h->keys, max_particles) && dev_alloc(&h->slots, max_particles);
     ok = ok && dev_alloc(&h->cell_count, max_cells) && dev_alloc(&h->cell_start, max_cells + 1);
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
+    ok = ok && dev_alloc(&h->hits, max_pairs) && dev_alloc(&h->meta, max_particles);
     ok = ok && dev_alloc(&h->ctr, 1) && dev_alloc(&h->head, max_particles) && dev_alloc(&h->pending_cnt, 4);
     if (ok) ok = cudaMemset(h->cell_count, 0, (size_t)max_cells * sizeof(int32_t)) == cudaSuccess;
     if (ok) ok = cudaMemset(h->ctr, 0, sizeof(Counters)) == cudaSuccess;
@@ -199,7 +202,7 @@ int lm_reset_stats(lm_handle h, void *stream)
 {
     if (!h) return LM_EINVAL;
     LM_CUDA(cudaSetDevice(h->device));
-    h->emit_cap = -1;
+    h->emit_cap = h->rps_cap = -1;
     return reset_counters(h, as_stream(stream));
 }
 
@@ -441,7 +444,9 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
         out->bbox[2] = dec_f(~c.bbox_enc[2]);
         out->bbox[3] = dec_f(c.bbox_enc[3]);
     }
-    if (h->emit_cap >= 0 && (int64_t)c.n_pairs > h->emit_cap) return LM_ENOSPC;
+    if (h->emit_cap >= 0 && (int64_t)c.n_pairs > h->emit_cap) return LM_ENOSPC;   // pair list truncated
+    if (h->rps_cap >= 0 && (int64_t)c.n_pairs > h->rps_cap) return LM_ENOSPC;     // RPS hand-off buffer too small: species invalid
+    if (c.n_overflow) return LM_ENOSPC;
     return LM_OK;
 }
 

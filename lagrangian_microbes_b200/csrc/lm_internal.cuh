@@ -22,7 +22,7 @@ struct Counters {
     unsigned long long n_clamped;
     unsigned long long species[4];
     unsigned int bbox_enc[4];   // order-preserving uint encodings: min lon, max lon, min lat, max lat
-    unsigned int pad[2];
+    unsigned long long n_overflow;   // neighbourhoods too dense for the 16-bit per-direction hit counts
 };
 
 struct RpsDev {
@@ -57,7 +57,11 @@ struct lm_handle_s {
     int32_t *block_sums;   // [ceil(max_cells / SCAN_TILE) + 1]
     // counters
     lm::Counters *ctr;     // device
-    int64_t emit_cap;      // capacity of the pair buffer passed to the last call
+    int64_t emit_cap;      // capacity of the pair buffer passed to the last call (-1: none)
+    int64_t rps_cap;       // capacity of hits[] if the last call resolved RPS (-1: it did not)
+    // pair search -> resolver hand-off
+    uint32_t *hits;        // [max_pairs] partner index | decision bits << 29, grouped per particle
+    int4 *meta;            // [max_particles] (offset into hits, 5 x 16-bit hit counts per direction)
     // explicit-order resolver workspace
     unsigned long long *head;   // [max_particles]
     int32_t *pending[2];        // [max_pairs] each

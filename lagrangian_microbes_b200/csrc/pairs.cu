@@ -1,5 +1,5 @@
-// Radius pair search on the binned particle arrays, optionally fused with rock-paper-scissors
-// resolution in the canonical cell-phase order.
+// Radius pair search on the binned particle arrays + rock-paper-scissors resolution in the
+// canonical cell-phase order.
 //
 // Replaces  kdt.query_pairs(r=interaction_radius, p=2)          (interaction_simulator.py:98)
 // and       for pair in microbe_pairs: pair_interaction(...)    (interaction_simulator.py:104-105)
@@ -11,70 +11,226 @@
 // r*r; the rest (a ~1e-5 fraction) take the exact double path, so the result is bit-exact while
 // the inner loop stays in fp32.
 //
-// Work decomposition.  A *unit* is a cell (pairs inside it) or two adjacent cells (pairs across
-// them): same cell, E, NW, N, NE -- the half stencil.  Units of one *phase* touch disjoint
-// particles:
-//     phase 0        same cell
-//     phase 1,2      E neighbour, anchor cx even / odd
-//     phase 3,4,5    NW, N, NE neighbour, anchor cy even
-//     phase 6,7,8    NW, N, NE neighbour, anchor cy odd
-// so with RPS fused in, each phase is one conflict-free launch and a unit is resolved sequentially
-// by one lane in (anchor id, other id) order -- the reference's sequential in-place semantics under
-// the canonical total order (phase, unit, id_a, id_b); see DESIGN.md §4.3 and
-// oracle/rps.py::cell_phase_order.  Without RPS all five directions run in a single launch.
+// Two stages:
 //
-// Lanes of a warp pull units from the warp's contiguous chunk as they go idle (unit sizes are
-// Poisson-distributed; a static unit-per-thread mapping would idle ~3/4 of the lanes), test one
-// candidate pair per iteration, and append hits to a per-warp shared-memory buffer that is flushed
-// to the global pair list with one atomic per ~200 pairs.
+//  find_pairs_kernel   one thread per particle a, half stencil (rest of its own cell, E, NW, N, NE):
+//      everything that does not depend on species is done here, once, densely -- distance tests,
+//      the per-pair Philox draw reduced to three decision bits (u < pRS, u < pPR, u < pSP, as exact
+//      integer compares of the 53-bit draw against ceil(p * 2^53)), the pair list (ids, i < j).
+//      Per particle it leaves meta[a] = (offset, hits per direction) and hits[offset + k] =
+//      b | decision_bits << 29 in (direction, b) order.
+//
+//  resolve_phase_kernel   the sequential part.  A *unit* is a cell (pairs inside it) or two
+//      adjacent cells; units of one *phase* touch disjoint particles:
+//          phase 0        same cell
+//          phase 1,2      E neighbour, anchor cx even / odd
+//          phase 3,4,5    NW, N, NE neighbour, anchor cy even
+//          phase 6,7,8    NW, N, NE neighbour, anchor cy odd
+//      so each phase is one conflict-free launch, one lane walks a unit's hit lists in (id_a, id_b)
+//      order and applies interactions.py:13-40 with table look-ups: the reference's sequential
+//      in-place semantics under the canonical total order (phase, unit, id_a, id_b)
+//      (oracle/rps.py::cell_phase_order).  Units with more than HEAVY_TESTS candidate pairs (dense
+//      clusters) are resolved by the whole warp: a row's hits are independent except through the
+//      anchor particle's species, a 3-state value, so the row is a prefix scan over 3->3 maps.
 #include "lm_internal.cuh"
 #include "philox.cuh"
 
 namespace lm {
 
-constexpr int PAIR_WARPS = 8;            // warps per CTA
-constexpr int PAIR_BUF = 256;            // pairs buffered per warp (2 KB)
-constexpr int UNITS_PER_WARP = 256;      // contiguous units owned by one warp
-constexpr int REFILL_IDLE = 12;          // refill when at least this many lanes are idle
+constexpr int FIND_THREADS = 256;
+constexpr int FIND_WARPS = FIND_THREADS / 32;
+constexpr int STAGE = 512;               // staged hits per warp (dense Philox / coalesced stores)
+constexpr uint32_t HIT_MASK = (1u << 29) - 1u;
+constexpr int HEAVY_TESTS = 2048;        // candidate pairs above which a unit is resolved by the warp
 
-enum UnitMode { MODE_ALL = 0, MODE_SAME = 1, MODE_EAST = 2, MODE_CROSS = 3 };
-
-struct PairArgs {
+struct FindArgs {
     const float *__restrict__ lon;
     const float *__restrict__ lat;
     const int32_t *__restrict__ id;
-    int8_t *sp;
     const int32_t *__restrict__ cell_start;
-    int ncx, ncy;
+    lm_grid g;
+    int n;
     float r2_lo, r2_hi;
     double r2;
-    RpsDev rps;
-    int2 *pairs;
-    unsigned long long cap;
+    uint32_t seed_lo, seed_hi, step_lo, step_hi;
+    unsigned long long thr[3];           // ceil(p * 2^53) for pRS, pPR, pSP
+    uint32_t *__restrict__ hits;
+    int4 *__restrict__ meta;
+    int2 *__restrict__ pairs;
+    unsigned long long cap_hits, cap_pairs;
     Counters *ctr;
-    long long n_units;
-    int mode, parity, dir;   // dir in {-1,0,+1} for MODE_CROSS
 };
 
-// Decode unit u of the launch into anchor / other particle ranges.  Returns false for units that
-// cannot contain a pair.
-__device__ __forceinline__ bool decode_unit(const PairArgs &A, long long u, int &aBeg, int &aEnd, int &bBeg, int &bEnd,
-                                            bool &same)
+__device__ __forceinline__ int cell_coord2(float v, double origin, double inv_h, int n)
 {
-    int anchor, other;
-    const int ncx = A.ncx, ncy = A.ncy;
-    if (A.mode == MODE_ALL) {
-        const int c = (int)(u / 5), d = (int)(u - 5ll * c);
-        const int cy = c / ncx, cx = c - cy * ncx;
-        anchor = c;
-        if (d == 0) other = c;
-        else if (d == 1) { if (cx + 1 >= ncx) return false; other = c + 1; }
-        else {
-            const int ox = cx + d - 3;   // d = 2,3,4 -> NW, N, NE
-            if (cy + 1 >= ncy || ox < 0 || ox >= ncx) return false;
-            other = c + ncx + d - 3;
+    const double q = floor(__dmul_rn(__dsub_rn((double)v, origin), inv_h));   // == bin.cu::cell_coord
+    if (!(q >= 0.0)) return 0;
+    if (q >= (double)n) return n - 1;
+    return (int)q;
+}
+
+__device__ __forceinline__ bool within_exact(float xa, float ya, float xb, float yb, double r2)
+{
+    const double dx = __dsub_rn((double)xa, (double)xb), dy = __dsub_rn((double)ya, (double)yb);
+    const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+    return s <= r2;
+}
+
+__device__ __forceinline__ bool within(const FindArgs &A, float xa, float ya, int b)
+{
+    const float xb = __ldg(A.lon + b), yb = __ldg(A.lat + b);
+    const float dx = xa - xb, dy = ya - yb;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    if (d2 > A.r2_hi) return false;
+    if (d2 < A.r2_lo) return true;
+    return within_exact(xa, ya, xb, yb, A.r2);
+}
+
+// three decision bits of the pair's draw: bit k set <=> u < p_k  (k = 0: pRS, 1: pPR, 2: pSP)
+__device__ __forceinline__ uint32_t decision_bits(const FindArgs &A, int i, int j)
+{
+    uint32_t x[4];
+    philox4x32_10((uint32_t)i, (uint32_t)j, A.step_lo, A.step_hi, A.seed_lo, A.seed_hi, x);
+    const unsigned long long m = ((unsigned long long)(x[0] >> 5) << 26) | (unsigned long long)(x[1] >> 6);
+    return (m < A.thr[0] ? 1u : 0u) | (m < A.thr[1] ? 2u : 0u) | (m < A.thr[2] ? 4u : 0u);
+}
+
+template <bool DO_RPS, bool EMIT>
+__global__ void __launch_bounds__(FIND_THREADS) find_pairs_kernel(FindArgs A)
+{
+    __shared__ uint32_t s_b[FIND_WARPS][STAGE];
+    __shared__ uint8_t s_owner[FIND_WARPS][STAGE];
+    __shared__ unsigned int s_wtot[FIND_WARPS];
+    __shared__ unsigned long long s_base;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int a = blockIdx.x * FIND_THREADS + threadIdx.x;
+    const bool valid = a < A.n;
+
+    float xa = 0.f, ya = 0.f;
+    int my_id = 0;
+    int r1_beg = 0, r1_end = 0, r2_beg = 0, r2_end = 0, sE = 0, sN = 0, sNE = 0;
+    if (valid) {
+        xa = __ldg(A.lon + a); ya = __ldg(A.lat + a);
+        my_id = __ldg(A.id + a);
+        const int ncx = A.g.ncx, ncy = A.g.ncy;
+        const int cx = cell_coord2(xa, A.g.x0, A.g.inv_h, ncx), cy = cell_coord2(ya, A.g.y0, A.g.inv_h, ncy);
+        const int c = cy * ncx + cx;
+        const bool e_ok = cx + 1 < ncx;
+        sE = __ldg(A.cell_start + c + 1);
+        r1_beg = a + 1;
+        r1_end = e_ok ? __ldg(A.cell_start + c + 2) : sE;
+        if (cy + 1 < ncy) {
+            const int up = c + ncx;
+            sN = __ldg(A.cell_start + up);
+            sNE = __ldg(A.cell_start + up + 1);
+            r2_beg = (cx > 0) ? __ldg(A.cell_start + up - 1) : sN;
+            r2_end = e_ok ? __ldg(A.cell_start + up + 2) : sNE;
         }
-    } else if (A.mode == MODE_SAME) {
+        if (r1_end - r1_beg > 65535 || r2_end - r2_beg > 65535) {     // 16-bit per-direction counts
+            atomicAdd(&A.ctr->n_overflow, 1ull);
+            r1_end = min(r1_end, r1_beg + 65535);
+            r2_end = min(r2_end, r2_beg + 65535);
+        }
+    }
+
+    // ---- pass 1: count hits per direction (S, E | NW, N, NE), 16 bits each
+    unsigned long long cnt03 = 0;     // directions 0..3
+    unsigned int cnt4 = 0;
+    for (int b = r1_beg; b < r1_end; ++b)
+        if (within(A, xa, ya, b)) cnt03 += (b >= sE) ? (1ull << 16) : 1ull;
+    for (int b = r2_beg; b < r2_end; ++b)
+        if (within(A, xa, ya, b)) {
+            if (b >= sNE) ++cnt4;
+            else cnt03 += (b >= sN) ? (1ull << 48) : (1ull << 32);
+        }
+    const unsigned int c0 = (unsigned int)(cnt03 & 0xffff), c1 = (unsigned int)((cnt03 >> 16) & 0xffff);
+    const unsigned int c2 = (unsigned int)((cnt03 >> 32) & 0xffff), c3 = (unsigned int)(cnt03 >> 48);
+    const unsigned int tot = c0 + c1 + c2 + c3 + cnt4;
+
+    // ---- allocate: exclusive scan over the CTA, one atomic per CTA
+    unsigned int inc = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    const unsigned int wtot = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 31) s_wtot[warp] = wtot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int btot = 0;
+#pragma unroll
+        for (int w = 0; w < FIND_WARPS; ++w) btot += s_wtot[w];
+        s_base = btot ? atomicAdd(&A.ctr->n_pairs, (unsigned long long)btot) : 0ull;
+    }
+    __syncthreads();
+    unsigned long long wbase = s_base;
+    for (int w = 0; w < warp; ++w) wbase += s_wtot[w];
+    const unsigned int off = inc - tot;                    // within the warp
+    if (DO_RPS && valid)
+        A.meta[a] = make_int4((int)(unsigned int)(wbase + off), (int)(c0 | (c1 << 16)), (int)(c2 | (c3 << 16)), (int)cnt4);
+    if (wtot == 0) return;                                 // warp-uniform
+    if (!DO_RPS && !EMIT) return;
+
+    if (wtot <= (unsigned int)STAGE) {
+        // ---- pass 2 (staged): regenerate the hits into shared memory, then finish them densely
+        unsigned int k = off;
+        for (int b = r1_beg; b < r1_end; ++b)
+            if (within(A, xa, ya, b)) { s_b[warp][k] = (uint32_t)b; s_owner[warp][k] = (uint8_t)lane; ++k; }
+        for (int b = r2_beg; b < r2_end; ++b)
+            if (within(A, xa, ya, b)) { s_b[warp][k] = (uint32_t)b; s_owner[warp][k] = (uint8_t)lane; ++k; }
+        __syncwarp();
+        for (unsigned int e0 = 0; e0 < wtot; e0 += 32) {
+            const unsigned int e = e0 + lane;
+            const bool act = e < wtot;
+            const uint32_t b = act ? s_b[warp][e] : 0u;
+            const int owner = act ? (int)s_owner[warp][e] : 0;
+            const int ia = __shfl_sync(0xffffffffu, my_id, owner);
+            if (act) {
+                const int ib = __ldg(A.id + b);
+                const int i = min(ia, ib), j = max(ia, ib);
+                const unsigned long long g = wbase + e;
+                if (DO_RPS && g < A.cap_hits) A.hits[g] = b | (decision_bits(A, i, j) << 29);
+                if (EMIT && g < A.cap_pairs) A.pairs[g] = make_int2(i, j);
+            }
+        }
+    } else {
+        // ---- pass 2 (direct): a dense neighbourhood; every lane has many hits, finish them in place
+        unsigned long long g = wbase + off;
+        for (int pass = 0; pass < 2; ++pass) {
+            const int beg = pass ? r2_beg : r1_beg, end = pass ? r2_end : r1_end;
+            for (int b = beg; b < end; ++b)
+                if (within(A, xa, ya, b)) {
+                    const int ib = __ldg(A.id + b);
+                    const int i = min(my_id, ib), j = max(my_id, ib);
+                    if (DO_RPS && g < A.cap_hits) A.hits[g] = (uint32_t)b | (decision_bits(A, i, j) << 29);
+                    if (EMIT && g < A.cap_pairs) A.pairs[g] = make_int2(i, j);
+                    ++g;
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+enum UnitMode { MODE_SAME = 1, MODE_EAST = 2, MODE_CROSS = 3 };
+
+struct ResolveArgs {
+    int8_t *sp;
+    const int32_t *__restrict__ cell_start;
+    const int4 *__restrict__ meta;
+    const uint32_t *__restrict__ hits;
+    unsigned long long cap_hits;
+    int ncx, ncy;
+    long long n_units;
+    int mode, parity, dir;   // dir in {-1,0,+1} for MODE_CROSS
+    int d_idx;               // which of the five per-particle hit lists this phase consumes
+};
+
+__device__ __forceinline__ bool decode_unit(const ResolveArgs &A, long long u, int &anchor, int &other)
+{
+    const int ncx = A.ncx;
+    if (A.mode == MODE_SAME) {
         anchor = other = (int)u;
     } else if (A.mode == MODE_EAST) {
         const int half = (ncx - A.parity) / 2;          // anchors per row with cx % 2 == parity, cx + 1 < ncx
@@ -89,210 +245,196 @@ __device__ __forceinline__ bool decode_unit(const PairArgs &A, long long u, int 
         anchor = cy * ncx + cx;
         other = anchor + ncx + A.dir;
     }
-    aBeg = __ldg(A.cell_start + anchor);
-    aEnd = __ldg(A.cell_start + anchor + 1);
-    if (aBeg == aEnd) return false;
-    same = (anchor == other);
-    if (same) {
-        if (aEnd - aBeg < 2) return false;
-        bBeg = aBeg; bEnd = aEnd;
-    } else {
-        bBeg = __ldg(A.cell_start + other);
-        bEnd = __ldg(A.cell_start + other + 1);
-        if (bBeg == bEnd) return false;
-    }
     return true;
 }
 
-__device__ __forceinline__ bool within_exact(float xa, float ya, float xb, float yb, double r2)
+// offset and length of particle a's hit list for direction d
+__device__ __forceinline__ void hit_list(const int4 m, int d, unsigned int &off, unsigned int &n)
 {
-    const double dx = __dsub_rn((double)xa, (double)xb), dy = __dsub_rn((double)ya, (double)yb);
-    const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-    return s <= r2;
+    const unsigned int c0 = (unsigned int)m.y & 0xffffu, c1 = (unsigned int)m.y >> 16;
+    const unsigned int c2 = (unsigned int)m.z & 0xffffu, c3 = (unsigned int)m.z >> 16;
+    const unsigned int c4 = (unsigned int)m.w;
+    off = (unsigned int)m.x;
+    switch (d) {
+        case 0: n = c0; break;
+        case 1: off += c0; n = c1; break;
+        case 2: off += c0 + c1; n = c2; break;
+        case 3: off += c0 + c1 + c2; n = c3; break;
+        default: off += c0 + c1 + c2 + c3; n = c4; break;
+    }
 }
 
-// interactions.py:13-40 for a pair whose species differ.  Returns the species both particles end
-// up with (the rule always leaves them equal), or -1 when either is not rock/paper/scissors
-// (winner = None: the draw is consumed, nothing changes).
-__device__ __forceinline__ int rps_outcome(int s1, int s2, double u, const RpsDev &R)
+// interactions.py:13-40 for species s1 != s2, both in {1,2,3}: the species both end up with.
+// The forward winner (rock beats scissors, paper beats rock, scissors beats paper) wins iff its
+// decision bit is set.
+__device__ __forceinline__ int rps_apply(int s1, int s2, uint32_t dec)
 {
-    if (s1 < 1 || s1 > 3 || s2 < 1 || s2 > 3) return -1;
-    // forward winner: rock beats scissors, paper beats rock, scissors beats paper
     int d = s1 - s2;
     if (d < 0) d += 3;
     const int w = (d == 1) ? s1 : s2, l = (d == 1) ? s2 : s1;
-    const double p = (w == 1) ? R.pRS : ((w == 2) ? R.pPR : R.pSP);
-    return (u < p) ? w : l;
+    return ((dec >> (w - 1)) & 1u) ? w : l;
 }
 
-template <bool DO_RPS, bool EMIT>
-__global__ void __launch_bounds__(PAIR_WARPS * 32) pair_units_kernel(PairArgs A)
+__device__ __forceinline__ bool is_rps(int s) { return s >= 1 && s <= 3; }
+
+// 3->3 maps packed 2 bits per entry: M(s) = (M >> 2(s-1)) & 3
+constexpr uint32_t MAP_ID = 1u | (2u << 2) | (3u << 4);
+__device__ __forceinline__ uint32_t map_apply(uint32_t M, int s) { return (M >> (2 * (s - 1))) & 3u; }
+__device__ __forceinline__ uint32_t map_compose(uint32_t second, uint32_t first)   // s -> second(first(s))
 {
-    __shared__ int2 s_buf[EMIT ? PAIR_WARPS : 1][EMIT ? PAIR_BUF : 1];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const long long wid = (long long)blockIdx.x * PAIR_WARPS + warp;
-    long long u_next = wid * UNITS_PER_WARP;
-    const long long u_end = min(u_next + UNITS_PER_WARP, A.n_units);
-    if (u_next >= u_end) return;   // warp-uniform
-
-    bool busy = false, same = false;
-    int a = 0, aEnd = 0, b = 0, bBeg = 0, bEnd = 0;
-    float xa = 0.f, ya = 0.f;
-    int nbuf = 0;                       // warp-uniform
-    unsigned long long my_hits = 0;     // per lane (used when !EMIT)
-
-    for (;;) {
-        const unsigned busy_mask = __ballot_sync(0xffffffffu, busy);
-        const int n_idle = 32 - __popc(busy_mask);
-        if (u_next < u_end && (n_idle >= REFILL_IDLE || busy_mask == 0u)) {
-            const int rank = __popc(~busy_mask & lt_mask);
-            const long long myu = u_next + rank;
-            if (!busy && myu < u_end) {
-                int aBeg;
-                if (decode_unit(A, myu, aBeg, aEnd, bBeg, bEnd, same)) {
-                    busy = true;
-                    a = aBeg;
-                    xa = __ldg(A.lon + a); ya = __ldg(A.lat + a);
-                    b = same ? a + 1 : bBeg;
-                }
-            }
-            u_next += n_idle;
-            continue;
-        }
-        if (busy_mask == 0u) break;
-
-        bool hit = false;
-        int2 pr = make_int2(0, 0);
-        if (busy) {
-            const float xb = __ldg(A.lon + b), yb = __ldg(A.lat + b);
-            const float dx = xa - xb, dy = ya - yb;
-            const float d2 = fmaf(dx, dx, dy * dy);
-            if (d2 <= A.r2_hi) hit = (d2 < A.r2_lo) ? true : within_exact(xa, ya, xb, yb, A.r2);
-            if (hit) {
-                const int ia = __ldg(A.id + a), ib = __ldg(A.id + b);
-                pr = (ia < ib) ? make_int2(ia, ib) : make_int2(ib, ia);
-                if (DO_RPS) {
-                    // the unit's particles are owned by this lane for the whole launch
-                    const int s1 = A.sp[a], s2 = A.sp[b];
-                    if (s1 != s2) {
-                        const double u = pair_uniform((uint32_t)pr.x, (uint32_t)pr.y, A.rps.step_lo, A.rps.step_hi,
-                                                      A.rps.seed_lo, A.rps.seed_hi);
-                        const int ns = rps_outcome(s1, s2, u, A.rps);
-                        if (ns >= 0) {
-                            if (ns != s1) A.sp[a] = (int8_t)ns;
-                            if (ns != s2) A.sp[b] = (int8_t)ns;
-                        }
-                    }
-                }
-                if (!EMIT) ++my_hits;
-            }
-            // advance to the next candidate of the unit
-            if (++b == bEnd) {
-                ++a;
-                if (a == aEnd || (same && a + 1 == aEnd)) busy = false;
-                else {
-                    xa = __ldg(A.lon + a); ya = __ldg(A.lat + a);
-                    b = same ? a + 1 : bBeg;
-                }
-            }
-        }
-        if (EMIT) {
-            const unsigned hm = __ballot_sync(0xffffffffu, hit);
-            if (hm) {
-                if (hit) s_buf[warp][nbuf + __popc(hm & lt_mask)] = pr;
-                nbuf += __popc(hm);
-                if (nbuf > PAIR_BUF - 32) {
-                    __syncwarp();
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(&A.ctr->n_pairs, (unsigned long long)nbuf);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    for (int i = lane; i < nbuf; i += 32)
-                        if (base + i < A.cap) A.pairs[base + i] = s_buf[warp][i];
-                    __syncwarp();
-                    nbuf = 0;
-                }
-            }
-        }
-    }
-    if (EMIT) {
-        if (nbuf > 0) {
-            __syncwarp();
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(&A.ctr->n_pairs, (unsigned long long)nbuf);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            for (int i = lane; i < nbuf; i += 32)
-                if (base + i < A.cap) A.pairs[base + i] = s_buf[warp][i];
-        }
-    } else {
-        for (int d = 16; d > 0; d >>= 1) my_hits += __shfl_xor_sync(0xffffffffu, my_hits, d);
-        if (lane == 0 && my_hits) atomicAdd(&A.ctr->n_pairs, my_hits);
-    }
+    return map_apply(second, (int)map_apply(first, 1)) | (map_apply(second, (int)map_apply(first, 2)) << 2) |
+           (map_apply(second, (int)map_apply(first, 3)) << 4);
 }
 
-static cudaError_t launch_units(const PairArgs &A, bool do_rps, bool emit, cudaStream_t s, int64_t *launches)
+// Whole-warp resolution of one unit (all lanes call this with the same arguments).
+__device__ void resolve_unit_warp(const ResolveArgs &A, int aBeg, int aEnd)
 {
-    if (A.n_units <= 0) return cudaSuccess;
-    const long long per_block = (long long)PAIR_WARPS * UNITS_PER_WARP;
-    const long long grid = (A.n_units + per_block - 1) / per_block;
-    const dim3 g((unsigned)grid), b(PAIR_WARPS * 32);
-    if (do_rps) {
-        if (emit) pair_units_kernel<true, true><<<g, b, 0, s>>>(A);
-        else pair_units_kernel<true, false><<<g, b, 0, s>>>(A);
-    } else {
-        if (emit) pair_units_kernel<false, true><<<g, b, 0, s>>>(A);
-        else pair_units_kernel<false, false><<<g, b, 0, s>>>(A);
+    const int lane = threadIdx.x & 31;
+    for (int a = aBeg; a < aEnd; ++a) {
+        unsigned int off, n;
+        hit_list(A.meta[a], A.d_idx, off, n);
+        if (n == 0) continue;
+        __syncwarp();                                  // species written by earlier rows are visible
+        int sa = ((volatile int8_t *)A.sp)[a];
+        if (!is_rps(sa)) continue;                     // winner = None for every pair of this row
+        const int sa0 = sa;
+        for (unsigned int k0 = 0; k0 < n; k0 += 32) {
+            const unsigned int k = k0 + lane;
+            const bool act = k < n && (unsigned long long)off + k < A.cap_hits;
+            uint32_t M = MAP_ID, dec = 0;
+            int b = 0, sb = 0;
+            if (act) {
+                const uint32_t h = A.hits[off + k];
+                b = (int)(h & HIT_MASK); dec = h >> 29;
+                sb = ((volatile int8_t *)A.sp)[b];
+                if (is_rps(sb)) {
+                    M = 0;
+#pragma unroll
+                    for (int s = 1; s <= 3; ++s) M |= (uint32_t)((s == sb) ? s : rps_apply(s, sb, dec)) << (2 * (s - 1));
+                }
+            }
+            uint32_t P = M;                            // inclusive scan of maps in lane (= id_b) order
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, P, d);
+                if (lane >= d) P = map_compose(P, t);
+            }
+            uint32_t E = __shfl_up_sync(0xffffffffu, P, 1);
+            if (lane == 0) E = MAP_ID;
+            if (act && is_rps(sb)) {
+                const int s_before = (int)map_apply(E, sa);
+                if (s_before != sb) A.sp[b] = (int8_t)rps_apply(s_before, sb, dec);
+            }
+            sa = (int)map_apply(__shfl_sync(0xffffffffu, P, 31), sa);
+        }
+        if (lane == 0 && sa != sa0) A.sp[a] = (int8_t)sa;
     }
-    ++*launches;
-    return cudaGetLastError();
+    __syncwarp();
 }
 
+__global__ void __launch_bounds__(256) resolve_phase_kernel(ResolveArgs A)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int anchor = 0, other = 0, aBeg = 0, aEnd = 0;
+    bool heavy = false;
+    if (u < A.n_units && decode_unit(A, u, anchor, other)) {
+        aBeg = __ldg(A.cell_start + anchor);
+        aEnd = __ldg(A.cell_start + anchor + 1);
+        if (aEnd > aBeg) {
+            const int nb = (anchor == other) ? (aEnd - aBeg) : (__ldg(A.cell_start + other + 1) - __ldg(A.cell_start + other));
+            if (nb == 0 || (anchor == other && nb < 2)) aEnd = aBeg;
+            else heavy = (long long)(aEnd - aBeg) * nb > HEAVY_TESTS;
+        }
+    }
+    if (!heavy) {
+        // one lane, one unit: rows in id order, each row's hits in id order
+        for (int a = aBeg; a < aEnd; ++a) {
+            unsigned int off, n;
+            hit_list(__ldg(A.meta + a), A.d_idx, off, n);
+            if (n == 0) continue;
+            int sa = A.sp[a];
+            const int sa0 = sa;
+            for (unsigned int k = 0; k < n && (unsigned long long)off + k < A.cap_hits; ++k) {
+                const uint32_t h = __ldg(A.hits + off + k);
+                const int b = (int)(h & HIT_MASK);
+                const int sb = A.sp[b];
+                if (sa != sb && is_rps(sa) && is_rps(sb)) {
+                    sa = rps_apply(sa, sb, h >> 29);
+                    A.sp[b] = (int8_t)sa;
+                }
+            }
+            if (sa != sa0) A.sp[a] = (int8_t)sa;
+        }
+    }
+    // dense clusters: the warp resolves them together, one after the other
+    unsigned hm = __ballot_sync(0xffffffffu, heavy);
+    while (hm) {
+        const int src = __ffs(hm) - 1;
+        hm &= hm - 1;
+        resolve_unit_warp(A, __shfl_sync(0xffffffffu, aBeg, src), __shfl_sync(0xffffffffu, aEnd, src));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 cudaError_t launch_pairs(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
                          double r, const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s)
 {
     if (n <= 0) return cudaSuccess;
-    PairArgs A;
-    A.lon = lon; A.lat = lat; A.id = id; A.sp = sp;
-    A.cell_start = h->cell_start;
-    A.ncx = h->grid.ncx; A.ncy = h->grid.ncy;
-    A.r2 = r * r;
-    A.r2_lo = (float)(A.r2 * (1.0 - 4e-6));
-    A.r2_hi = (float)(A.r2 * (1.0 + 4e-6));
-    if (rps) A.rps = *rps;
-    else A.rps = RpsDev{0, 0, 0, 0, 0, 0, 0};
-    A.pairs = pairs_out;
-    A.cap = (pairs_out && cap > 0) ? (unsigned long long)cap : 0ull;
-    A.ctr = h->ctr;
-    const bool emit = A.cap > 0;
-    const long long ncx = A.ncx, ncy = A.ncy;
-    cudaError_t e = cudaSuccess;
-    if (!rps) {
-        A.mode = MODE_ALL; A.parity = 0; A.dir = 0;
-        A.n_units = 5ll * ncx * ncy;
-        return launch_units(A, false, emit, s, &h->launches);
-    }
-    // phase 0
-    A.mode = MODE_SAME; A.parity = 0; A.dir = 0; A.n_units = ncx * ncy;
-    e = launch_units(A, true, emit, s, &h->launches);
-    if (e != cudaSuccess) return e;
-    // phases 1, 2
-    for (int q = 0; q < 2; ++q) {
-        A.mode = MODE_EAST; A.parity = q; A.dir = 0;
-        const long long half = (ncx - q) / 2;
-        A.n_units = half * ncy;
-        e = launch_units(A, true, emit, s, &h->launches);
-        if (e != cudaSuccess) return e;
-    }
-    // phases 3..8
-    for (int q = 0; q < 2; ++q) {
-        const long long rows = (ncy - q) / 2;     // anchors rows cy = q, q+2, ... with cy + 1 < ncy
-        for (int d = -1; d <= 1; ++d) {
-            A.mode = MODE_CROSS; A.parity = q; A.dir = d;
-            A.n_units = rows * ncx;
-            e = launch_units(A, true, emit, s, &h->launches);
-            if (e != cudaSuccess) return e;
+    FindArgs F;
+    F.lon = lon; F.lat = lat; F.id = id; F.cell_start = h->cell_start;
+    F.g = h->grid; F.n = n;
+    F.r2 = r * r;
+    F.r2_lo = (float)(F.r2 * (1.0 - 4e-6));
+    F.r2_hi = (float)(F.r2 * (1.0 + 4e-6));
+    F.seed_lo = F.seed_hi = F.step_lo = F.step_hi = 0;
+    F.thr[0] = F.thr[1] = F.thr[2] = 0;
+    if (rps) {
+        F.seed_lo = rps->seed_lo; F.seed_hi = rps->seed_hi; F.step_lo = rps->step_lo; F.step_hi = rps->step_hi;
+        const double p[3] = {rps->pRS, rps->pPR, rps->pSP};
+        for (int k = 0; k < 3; ++k) {
+            // u = m * 2^-53 with integer m < 2^53:  u < p  <=>  m < ceil(p * 2^53)   (the scaling is exact)
+            if (!(p[k] > 0.0)) F.thr[k] = 0;
+            else if (p[k] >= 1.0) F.thr[k] = 1ull << 53;
+            else F.thr[k] = (unsigned long long)ceil(p[k] * 9007199254740992.0);
         }
     }
+    F.hits = h->hits; F.meta = h->meta;
+    F.pairs = pairs_out;
+    F.cap_hits = rps ? (unsigned long long)h->max_pairs : 0ull;
+    F.cap_pairs = (pairs_out && cap > 0) ? (unsigned long long)cap : 0ull;
+    F.ctr = h->ctr;
+    h->rps_cap = rps ? h->max_pairs : -1;
+    const bool emit = F.cap_pairs > 0;
+    const int grid = (n + FIND_THREADS - 1) / FIND_THREADS;
+    if (rps) {
+        if (emit) find_pairs_kernel<true, true><<<grid, FIND_THREADS, 0, s>>>(F);
+        else find_pairs_kernel<true, false><<<grid, FIND_THREADS, 0, s>>>(F);
+    } else {
+        if (emit) find_pairs_kernel<false, true><<<grid, FIND_THREADS, 0, s>>>(F);
+        else find_pairs_kernel<false, false><<<grid, FIND_THREADS, 0, s>>>(F);
+    }
+    ++h->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess || !rps) return e;
+
+    ResolveArgs R;
+    R.sp = sp; R.cell_start = h->cell_start; R.meta = h->meta; R.hits = h->hits;
+    R.cap_hits = F.cap_hits;
+    R.ncx = h->grid.ncx; R.ncy = h->grid.ncy;
+    const long long ncx = R.ncx, ncy = R.ncy;
+    auto launch = [&](int mode, int parity, int dir, int d_idx, long long n_units) -> cudaError_t {
+        if (n_units <= 0) return cudaSuccess;
+        R.mode = mode; R.parity = parity; R.dir = dir; R.d_idx = d_idx; R.n_units = n_units;
+        resolve_phase_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, s>>>(R);
+        ++h->launches;
+        return cudaGetLastError();
+    };
+    if ((e = launch(MODE_SAME, 0, 0, 0, ncx * ncy)) != cudaSuccess) return e;                    // phase 0
+    for (int q = 0; q < 2; ++q)                                                                   // phases 1, 2
+        if ((e = launch(MODE_EAST, q, 0, 1, ((ncx - q) / 2) * ncy)) != cudaSuccess) return e;
+    for (int q = 0; q < 2; ++q)                                                                   // phases 3..8
+        for (int d = -1; d <= 1; ++d)
+            if ((e = launch(MODE_CROSS, q, d, 3 + d, ((ncy - q) / 2) * ncx)) != cudaSuccess) return e;
     return cudaSuccess;
 }
 

@@ -39,6 +39,7 @@ class InteractionSimulator:
             advection_dir=".",
             output_dir=".",
             seed=0,
+            pair_capacity=None,
     ):
         output_dir = os.path.abspath(output_dir)
         if not os.path.exists(output_dir):
@@ -62,6 +63,7 @@ class InteractionSimulator:
         self.output_dir = output_dir
         self.iteration = 0
         self.seed = seed
+        self.pair_capacity = pair_capacity   # pairs per step the device buffers hold (default 32 per microbe)
         self.pairs_found = []          # per-step pair counts of the last time_step call
         self._engine = None
 
@@ -79,7 +81,8 @@ class InteractionSimulator:
         species_out = zeros((N_particles, Nt), dtype=int8)
 
         if self._engine is None or self._engine.max_particles < N_particles:
-            self._engine = Engine(max_particles=N_particles, max_cells=max(4 * N_particles, 1 << 18), max_pairs=0)
+            cap = self.pair_capacity if self.pair_capacity is not None else max(32 * N_particles, 1 << 20)
+            self._engine = Engine(max_particles=N_particles, max_cells=max(4 * N_particles, 1 << 18), max_pairs=int(cap))
         eng = self._engine
         dev = eng.device
         prm = self.pair_interaction_parameters

@@ -46,7 +46,11 @@ class FusedSimulation:
 
         if max_cells is None:
             max_cells = int(max(4 * cells_per_particle * n, 1 << 20))
-        self.engine = Engine(max_particles=n, max_cells=max_cells, max_pairs=0, device=device)
+        if pair_capacity is None:
+            pair_capacity = max(1 << 20, 8 * n)
+        # max_pairs sizes the pair-search -> resolver hand-off buffer (4 B per pair per step)
+        self.engine = Engine(max_particles=n, max_cells=max_cells, max_pairs=int(pair_capacity) if interact else 0,
+                             device=device)
         dev = self.engine.device
         self.fieldset = fieldset
         self.stream_field = bool(stream_field) and fieldset is not None

@@ -121,7 +121,7 @@ def test_large_n_properties():
     lon = (205 + side * rng.random(n)).astype(np.float32)
     lat = (25 + side * rng.random(n)).astype(np.float32)
     sp0 = rng.integers(1, 4, n).astype(np.int8)
-    eng = Engine(max_particles=n, max_cells=1 << 24)
+    eng = Engine(max_particles=n, max_cells=1 << 24, max_pairs=int(17.0 * n))
     try:
         eng.set_grid(make_grid(205, 205 + side, 25, 25 + side, r, n, eng.max_cells, margin=0.0))
         cap = int(17.0 * n)
