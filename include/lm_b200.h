@@ -72,7 +72,36 @@ typedef struct {
     int64_t n_clamped;        /* particles outside the cell grid (binned into edge cells) */
     int64_t species_count[4]; /* [0]=other, [1]=rock, [2]=paper, [3]=scissors, after the step */
     float bbox[4];            /* lon_min, lon_max, lat_min, lat_max of the particles */
+    int64_t n_particles;      /* particles owned by this handle after the step */
+    int64_t n_moved_in;       /* strips: particles that arrived from / left to the neighbour strips in the */
+    int64_t n_moved_out;      /*         last step that re-binned */
+    int64_t n_misrouted;      /* strips: arrivals belonging to neither strip (moved more than one strip per step) */
 } lm_stats;
+
+/* Latitude strip of one handle inside the GLOBAL cell grid (multi-GPU): the handle owns
+ * the particles of cell rows [row0, row0 + rows_owned).  row0 must be even; has_south / has_north say whether
+ * a neighbouring strip exists (they must be consistent with row0 == 0 / row0 + rows_owned == ncy). */
+typedef struct {
+    int32_t row0, rows_owned;
+    int32_t has_south, has_north;
+} lm_strip;
+
+/* Exchange buffers of a strip (device memory owned by the handle; sizes are fixed so the transfers can be
+ * posted without negotiating counts -- the live counts travel in the messages' headers).  The caller moves,
+ * between the stages of a step (see lm_step_move):
+ *     mig_send[0]  -> the southern neighbour's mig_recv[1]        mig_send[1] -> the northern one's mig_recv[0]
+ *     ghost_send   -> the southern neighbour's ghost_recv
+ *     gsp_send     -> the southern neighbour's gsp_recv
+ *     gret_send    -> the northern neighbour's gret_recv
+ * i.e. index 0 = south side, 1 = north side of THIS strip, for send and recv alike. */
+typedef struct {
+    void *mig_send[2], *mig_recv[2];
+    int64_t mig_bytes;
+    void *ghost_send, *ghost_recv;
+    int64_t ghost_bytes;
+    void *gsp_send, *gsp_recv, *gret_send, *gret_recv;
+    int64_t species_bytes;
+} lm_strip_buffers;
 
 int lm_version(void);
 const char *lm_error_string(int code);
@@ -140,6 +169,28 @@ int64_t lm_state_size(lm_handle h);
 #define LM_STEP_TIMING 32 /* record CUDA events between the phases (read with lm_phase_times) */
 int lm_step(lm_handle h, int32_t flags, const lm_stage_times *st /* host */, float dt, double diffuse_amp_deg,
             double r, const lm_rps_params *prm /* host */, int32_t *pairs_out, int64_t cap, void *stream);
+/* ---- the same step in five stages, for latitude strips (one handle per GPU) ----------------------------
+ * The reference has no counterpart: its interaction phase is one serial process
+ * (interaction_simulator.py:82-117) and only advection is tiled (particle_advecter.py:143-148).
+ * lm_step == move, bin, interact_begin, interact_end, finish back to back.  With strips the caller moves the
+ * exchange buffers between the stages (NCCL send/recv between neighbours, or device copies):
+ *     lm_step_move            [diffuse] [advect], cell keys, leavers packed      -> exchange mig_send
+ *     lm_step_bin             arrivals unpacked, binning, first row packed         -> exchange ghost_send
+ *                             (synchronises the stream once to read the migration counts)
+ *     lm_step_interact_begin  ghost row appended, pair search, RPS phases 0-5      -> exchange gsp_send
+ *     lm_step_interact_end    ghost species refreshed, RPS phases 6-8             -> exchange gret_send
+ *     lm_step_finish          first row's species taken back, [stats]
+ * The result (pair set, species, positions) is bit-identical to a single handle running lm_step on all
+ * particles with the same grid. */
+int lm_strip_alloc(lm_handle h, int64_t send_cap, int64_t ghost_cap, int32_t row_cap);
+int lm_set_strip(lm_handle h, const lm_strip *strip /* host */);   /* after lm_set_grid (which resets it) */
+int lm_strip_buffers_get(lm_handle h, lm_strip_buffers *out /* host */);
+int lm_step_move(lm_handle h, int32_t flags, const lm_stage_times *st /* host */, float dt, double diffuse_amp_deg,
+                 const lm_rps_params *prm /* host */, void *stream);
+int lm_step_bin(lm_handle h, void *stream);
+int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t cap, void *stream);
+int lm_step_interact_end(lm_handle h, void *stream);
+int lm_step_finish(lm_handle h, void *stream);
 /* Scatter the state back to id order: out[id] = value (device outputs, any may be NULL). */
 int lm_state_get(lm_handle h, float *lon_out, float *lat_out, int8_t *species_out, void *stream);
 /* Same, into pinned HOST buffers (device scatter + async D2H on the stream). */

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "liblm_b200.so")
-_SOURCES = ["api.cu", "advect.cu", "bin.cu", "pairs.cu", "resolve.cu"]
+_SOURCES = ["api.cu", "advect.cu", "bin.cu", "strip.cu", "pairs.cu", "resolve.cu"]
 _HEADERS = ["lm_internal.cuh", "philox.cuh", os.path.join("..", "..", "include", "lm_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -48,7 +48,21 @@ class RpsParams(ctypes.Structure):
 
 class Stats(ctypes.Structure):
     _fields_ = [("n_pairs", ctypes.c_int64), ("n_out_of_bounds", ctypes.c_int64), ("n_clamped", ctypes.c_int64),
-                ("species_count", ctypes.c_int64 * 4), ("bbox", ctypes.c_float * 4)]
+                ("species_count", ctypes.c_int64 * 4), ("bbox", ctypes.c_float * 4),
+                ("n_particles", ctypes.c_int64), ("n_moved_in", ctypes.c_int64), ("n_moved_out", ctypes.c_int64),
+                ("n_misrouted", ctypes.c_int64)]
+
+
+class Strip(ctypes.Structure):
+    _fields_ = [("row0", ctypes.c_int32), ("rows_owned", ctypes.c_int32), ("has_south", ctypes.c_int32),
+                ("has_north", ctypes.c_int32)]
+
+
+class StripBuffers(ctypes.Structure):
+    _fields_ = [("mig_send", ctypes.c_void_p * 2), ("mig_recv", ctypes.c_void_p * 2), ("mig_bytes", ctypes.c_int64),
+                ("ghost_send", ctypes.c_void_p), ("ghost_recv", ctypes.c_void_p), ("ghost_bytes", ctypes.c_int64),
+                ("gsp_send", ctypes.c_void_p), ("gsp_recv", ctypes.c_void_p), ("gret_send", ctypes.c_void_p),
+                ("gret_recv", ctypes.c_void_p), ("species_bytes", ctypes.c_int64)]
 
 
 def _stale():
@@ -108,6 +122,14 @@ def lib():
         "lm_state_set": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, vp]),
         "lm_state_size": (i64, [vp]),
         "lm_step": (ctypes.c_int, [vp, i32, P(StageTimes), flt, dbl, dbl, P(RpsParams), vp, i64, vp]),
+        "lm_strip_alloc": (ctypes.c_int, [vp, i64, i64, i32]),
+        "lm_set_strip": (ctypes.c_int, [vp, P(Strip)]),
+        "lm_strip_buffers_get": (ctypes.c_int, [vp, P(StripBuffers)]),
+        "lm_step_move": (ctypes.c_int, [vp, i32, P(StageTimes), flt, dbl, P(RpsParams), vp]),
+        "lm_step_bin": (ctypes.c_int, [vp, vp]),
+        "lm_step_interact_begin": (ctypes.c_int, [vp, dbl, vp, i64, vp]),
+        "lm_step_interact_end": (ctypes.c_int, [vp, vp]),
+        "lm_step_finish": (ctypes.c_int, [vp, vp]),
         "lm_state_get": (ctypes.c_int, [vp, vp, vp, vp, vp]),
         "lm_state_get_host": (ctypes.c_int, [vp, vp, vp, vp, vp]),
         "lm_host_copies_sync": (ctypes.c_int, [vp]),
@@ -129,7 +151,8 @@ EXPORTS = ["lm_version", "lm_error_string", "lm_last_cuda_error", "lm_create", "
            "lm_update_field_data", "lm_set_grid", "lm_get_grid", "lm_advect_rk4", "lm_diffuse", "lm_find_pairs", "lm_interact_rps",
            "lm_pair_uniforms", "lm_resolve_rps", "lm_state_set", "lm_state_size", "lm_step", "lm_state_get",
            "lm_state_get_host", "lm_host_copies_sync", "lm_state_view", "lm_sync_stats", "lm_reset_stats", "lm_launch_count",
-           "lm_phase_times"]
+           "lm_phase_times", "lm_strip_alloc", "lm_set_strip", "lm_strip_buffers_get", "lm_step_move", "lm_step_bin",
+           "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish"]
 
 
 def check(code, what):

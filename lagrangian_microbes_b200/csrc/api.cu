@@ -74,6 +74,10 @@ int lm_destroy(lm_handle h)
     cudaFree(h->cell_cursor); cudaFree(h->block_sums); cudaFree(h->ctr); cudaFree(h->head);
     cudaFree(h->pending_cnt);
     cudaFree(h->hits); cudaFree(h->meta);
+    for (int k = 0; k < 2; ++k) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); }
+    cudaFree(h->ghost_send); cudaFree(h->ghost_recv);
+    cudaFree(h->gsp_send); cudaFree(h->gsp_recv); cudaFree(h->gret_send); cudaFree(h->gret_recv);
+    if (h->xfer_counts_host) cudaFreeHost(h->xfer_counts_host);
     for (int k = 0; k < 5; ++k)
         if (h->ev_phase[k]) cudaEventDestroy(h->ev_phase[k]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -157,10 +161,87 @@ int lm_update_field_data(lm_handle h, const float *U, const float *V, int32_t T)
 int lm_set_grid(lm_handle h, const lm_grid *g)
 {
     if (!h || !g || g->ncx < 1 || g->ncy < 1 || !(g->inv_h > 0.0)) return LM_EINVAL;
-    if ((int64_t)g->ncx * g->ncy > h->max_cells) return LM_ENOSPC;
+    // a handle with strip buffers may be given a GLOBAL grid larger than its own cell table: it then needs
+    // lm_set_strip before anything else (rows_owned = 0 until then)
+    const bool fits = (int64_t)g->ncx * g->ncy <= h->max_cells;
+    if (!fits && !h->send_cap) return LM_ENOSPC;
     h->grid = *g;
     h->have_grid = true;
     h->binned = false;
+    // a new grid drops any strip: the handle owns all rows until lm_set_strip says otherwise
+    h->strip.row0 = 0;
+    h->strip.rows_owned = h->strip.rows_local = fits ? g->ncy : 0;
+    h->strip.migrate = 0;
+    h->has_south = h->has_north = false;
+    h->stage = 0;
+    return LM_OK;
+}
+
+int lm_strip_alloc(lm_handle h, int64_t send_cap, int64_t ghost_cap, int32_t row_cap)
+{
+    if (!h || send_cap < 1 || ghost_cap < 1 || row_cap < 1) return LM_EINVAL;
+    if (h->send_cap) return LM_ESTATE;   // once per handle
+    LM_CUDA(cudaSetDevice(h->device));
+    const int64_t ghost_words = GHOST_HDR + (int64_t)row_cap + 1 + 3 * ghost_cap;
+    bool ok = true;
+    for (int k = 0; k < 2; ++k) ok = ok && dev_alloc(&h->mig_send[k], send_cap + 1) && dev_alloc(&h->mig_recv[k], send_cap + 1);
+    ok = ok && dev_alloc(&h->ghost_send, ghost_words) && dev_alloc(&h->ghost_recv, ghost_words);
+    ok = ok && dev_alloc(&h->gsp_send, ghost_cap) && dev_alloc(&h->gsp_recv, ghost_cap);
+    ok = ok && dev_alloc(&h->gret_send, ghost_cap) && dev_alloc(&h->gret_recv, ghost_cap);
+    ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&h->xfer_counts_host), 4 * sizeof(int32_t), cudaHostAllocDefault) == cudaSuccess;
+    for (int k = 0; ok && k < 2; ++k) {
+        ok = ok && cudaMemset(h->mig_send[k], 0, (size_t)(send_cap + 1) * sizeof(int4)) == cudaSuccess;
+        ok = ok && cudaMemset(h->mig_recv[k], 0, (size_t)(send_cap + 1) * sizeof(int4)) == cudaSuccess;
+    }
+    if (ok) ok = cudaMemset(h->ghost_send, 0, (size_t)ghost_words * 4) == cudaSuccess;
+    if (ok) ok = cudaMemset(h->ghost_recv, 0, (size_t)ghost_words * 4) == cudaSuccess;
+    if (ok) ok = cudaMemset(h->gsp_send, 0, (size_t)ghost_cap) == cudaSuccess && cudaMemset(h->gsp_recv, 0, (size_t)ghost_cap) == cudaSuccess;
+    if (ok) ok = cudaMemset(h->gret_send, 0, (size_t)ghost_cap) == cudaSuccess && cudaMemset(h->gret_recv, 0, (size_t)ghost_cap) == cudaSuccess;
+    if (!ok) {
+        set_last_cuda_error(cudaGetLastError(), "lm_strip_alloc");
+        return LM_ENOMEM;
+    }
+    h->send_cap = send_cap; h->ghost_cap = ghost_cap; h->row_cap = row_cap;
+    return LM_OK;
+}
+
+int lm_set_strip(lm_handle h, const lm_strip *st)
+{
+    if (!h || !st) return LM_EINVAL;
+    if (!h->have_grid || !h->send_cap) return LM_ESTATE;
+    const lm_grid &g = h->grid;
+    if (st->row0 < 0 || st->rows_owned < 1 || st->row0 + st->rows_owned > g.ncy) return LM_EINVAL;
+    if (st->row0 & 1) return LM_EINVAL;                                  // boundaries on even rows
+    if (st->has_south && st->row0 == 0) return LM_EINVAL;
+    if (st->has_north && st->row0 + st->rows_owned >= g.ncy) return LM_EINVAL;
+    if (!st->has_south && st->row0 != 0) return LM_EINVAL;
+    if (!st->has_north && st->row0 + st->rows_owned != g.ncy) return LM_EINVAL;
+    if (g.ncx > h->row_cap) return LM_ENOSPC;
+    const int rows_local = st->rows_owned + (st->has_north ? 1 : 0);
+    if ((int64_t)rows_local * g.ncx > h->max_cells) return LM_ENOSPC;
+    LM_CUDA(cudaSetDevice(h->device));
+    h->strip.row0 = st->row0;
+    h->strip.rows_owned = st->rows_owned;
+    h->strip.rows_local = rows_local;
+    h->strip.migrate = 0;
+    h->has_south = st->has_south != 0;
+    h->has_north = st->has_north != 0;
+    h->binned = false;
+    h->stage = 0;
+    return LM_OK;
+}
+
+int lm_strip_buffers_get(lm_handle h, lm_strip_buffers *out)
+{
+    if (!h || !out) return LM_EINVAL;
+    if (!h->send_cap) return LM_ESTATE;
+    for (int k = 0; k < 2; ++k) { out->mig_send[k] = h->mig_send[k]; out->mig_recv[k] = h->mig_recv[k]; }
+    out->mig_bytes = (h->send_cap + 1) * (int64_t)sizeof(int4);
+    out->ghost_send = h->ghost_send; out->ghost_recv = h->ghost_recv;
+    out->ghost_bytes = (GHOST_HDR + h->row_cap + 1 + 3 * h->ghost_cap) * 4;
+    out->gsp_send = h->gsp_send; out->gsp_recv = h->gsp_recv;
+    out->gret_send = h->gret_send; out->gret_recv = h->gret_recv;
+    out->species_bytes = h->ghost_cap;
     return LM_OK;
 }
 
@@ -220,11 +301,27 @@ int lm_state_set(lm_handle h, const float *lon, const float *lat, const int8_t *
 {
     if (!h || !lon || !lat || n < 0) return LM_EINVAL;
     if (n > h->max_particles) return LM_ENOSPC;
-    if (!h->have_grid) return LM_ESTATE;
+    if (!h->have_grid || h->strip.rows_owned < 1) return LM_ESTATE;
     LM_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = as_stream(stream);
     int rc = reset_counters(h, s);
     if (rc) return rc;
+    h->stage = 0;
+    if (h->has_south || h->has_north) {
+        // strips: the particles are only loaded; the first step bins them and sends those that belong to a
+        // neighbouring strip on their way (repeat a flags = 0 step until lm_stats.n_misrouted == 0 everywhere)
+        if (!ids) return LM_EINVAL;                        // global ids are required
+        const int c = h->cur;
+        const size_t m = (size_t)n;
+        LM_CUDA(cudaMemcpyAsync(h->lon[c], lon, m * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        LM_CUDA(cudaMemcpyAsync(h->lat[c], lat, m * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        LM_CUDA(cudaMemcpyAsync(h->id[c], ids, m * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+        if (species) LM_CUDA(cudaMemcpyAsync(h->sp[c], species, m, cudaMemcpyDeviceToDevice, s));
+        else LM_CUDA(cudaMemsetAsync(h->sp[c], 0, m, s));
+        h->n = n;
+        h->binned = false;
+        return LM_OK;
+    }
     const int d = h->cur ^ 1;
     LM_CUDA(launch_bin(h, lon, lat, species, ids, (int)n, h->lon[d], h->lat[d], h->sp[d], h->id[d], s));
     h->cur = d;
@@ -247,6 +344,7 @@ int lm_find_pairs(lm_handle h, const float *lon, const float *lat, int64_t n, do
                   int64_t *n_pairs_out, void *stream)
 {
     if (!h) return LM_EINVAL;
+    if (h->has_south || h->has_north) return LM_ESTATE;   // stateless operators work on a whole domain
     int rc = check_radius(h, r);
     if (rc) return rc;
     rc = lm_state_set(h, lon, lat, nullptr, nullptr, n, stream);
@@ -271,6 +369,7 @@ int lm_interact_rps(lm_handle h, const float *lon, const float *lat, int8_t *spe
                     const lm_rps_params *prm, int32_t *pairs_out, int64_t cap, int64_t *n_pairs_out, void *stream)
 {
     if (!h || !species || !prm) return LM_EINVAL;
+    if (h->has_south || h->has_north) return LM_ESTATE;
     int rc = check_radius(h, r);
     if (rc) return rc;
     rc = lm_state_set(h, lon, lat, species, nullptr, n, stream);
@@ -301,61 +400,171 @@ int lm_resolve_rps(lm_handle h, const int32_t *pairs, const double *u, int64_t n
                             rounds_out, as_stream(stream));
 }
 
-int lm_step(lm_handle h, int32_t flags, const lm_stage_times *st, float dt, double diffuse_amp_deg, double r,
-            const lm_rps_params *prm, int32_t *pairs_out, int64_t cap, void *stream)
+static inline bool in_strip_mode(lm_handle h) { return h->has_south || h->has_north; }
+
+int lm_step_move(lm_handle h, int32_t flags, const lm_stage_times *st, float dt, double diffuse_amp_deg,
+                 const lm_rps_params *prm, void *stream)
 {
     if (!h) return LM_EINVAL;
-    if (!h->have_grid) return LM_ESTATE;
-    if (h->n <= 0) return LM_OK;
-    LM_CUDA(cudaSetDevice(h->device));
-    cudaStream_t s = as_stream(stream);
-    const int n = (int)h->n;
-    int rc = reset_counters(h, s);
-    if (rc) return rc;
-    int c = h->cur;
-    bool moved = false;
-    const bool timing = (flags & LM_STEP_TIMING) != 0;
-    if (timing) LM_CUDA(cudaEventRecord(h->ev_phase[0], s));
-    if (flags & LM_STEP_DIFFUSE) {
-        // The reference kicks the particles at the END of an iteration, after the positions were
-        // stored (particle_advecter.py:233-242): the stored positions -- the ones interactions see --
-        // are pre-kick.  So the kick of iteration step-1 is applied here, before this step's advection.
-        if (!prm) return LM_EINVAL;
-        LM_CUDA(launch_diffuse(h->lon[c], h->lat[c], h->id[c], n, diffuse_amp_deg, prm->seed, prm->step - 1, s,
-                               &h->launches));
-        moved = true;
-    }
+    if (!h->have_grid || h->strip.rows_owned < 1) return LM_ESTATE;
+    if ((flags & (LM_STEP_DIFFUSE | LM_STEP_INTERACT)) && !prm) return LM_EINVAL;
     if (flags & LM_STEP_ADVECT) {
         if (!st) return LM_EINVAL;
         if (!h->have_field) return LM_ESTATE;
         for (int k = 0; k < 4; ++k)
             if (st->ti[k] < 0 || st->ti[k] + (st->interp[k] ? 1 : 0) >= h->field.T) return LM_EINVAL;
+    }
+    LM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = as_stream(stream);
+    const int n = (int)h->n;
+    int rc = reset_counters(h, s);
+    if (rc) return rc;
+    const int c = h->cur;
+    bool moved = false;
+    const bool timing = (flags & LM_STEP_TIMING) != 0;
+    h->timed = false;
+    if (timing) LM_CUDA(cudaEventRecord(h->ev_phase[0], s));
+    if (flags & LM_STEP_DIFFUSE) {
+        // The reference kicks the particles at the END of an iteration, after the positions were
+        // stored (particle_advecter.py:233-242): the stored positions -- the ones interactions see --
+        // are pre-kick.  So the kick of iteration step-1 is applied here, before this step's advection.
+        LM_CUDA(launch_diffuse(h->lon[c], h->lat[c], h->id[c], n, diffuse_amp_deg, prm->seed, prm->step - 1, s,
+                               &h->launches));
+        moved = true;
+    }
+    if (flags & LM_STEP_ADVECT) {
         LM_CUDA(launch_advect(h->field, h->lon[c], h->lat[c], n, *st, dt, h->ctr, s, &h->launches));
         moved = true;
     }
     if (timing) LM_CUDA(cudaEventRecord(h->ev_phase[1], s));
-    if (moved || !h->binned) {
+    h->step_moved = moved || !h->binned;
+    if (h->step_moved) {
+        for (int d = 0; d < 2; ++d)
+            if (d ? h->has_north : h->has_south) LM_CUDA(cudaMemsetAsync(h->mig_send[d], 0, sizeof(int4), s));
+        LM_CUDA(launch_bin_count(h, h->lon[c], h->lat[c], h->sp[c], h->id[c], 0, n, in_strip_mode(h), s));
+    }
+    h->step_flags = flags;
+    if (prm) h->step_rps = to_dev(prm);
+    h->stage = 1;
+    return LM_OK;
+}
+
+int lm_step_bin(lm_handle h, void *stream)
+{
+    if (!h) return LM_EINVAL;
+    if (h->stage != 1) return LM_ESTATE;
+    LM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = as_stream(stream);
+    int c = h->cur;
+    if (h->step_moved) {
+        int n_in = (int)h->n, n_out = (int)h->n;
+        h->n_moved_in = h->n_moved_out = 0;
+        if (in_strip_mode(h)) {
+            // the one host synchronisation of a multi-GPU step: how many left, how many arrived
+            int32_t *cnt = h->xfer_counts_host;
+            cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
+            for (int d = 0; d < 2; ++d) {
+                if (!(d ? h->has_north : h->has_south)) continue;
+                LM_CUDA(cudaMemcpyAsync(cnt + d, h->mig_send[d], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+                LM_CUDA(cudaMemcpyAsync(cnt + 2 + d, h->mig_recv[d], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+            }
+            LM_CUDA(cudaStreamSynchronize(s));
+            for (int k = 0; k < 4; ++k)
+                if (cnt[k] < 0 || cnt[k] > h->send_cap) return LM_ENOSPC;      // migration buffer too small
+            const int n_arr = cnt[2] + cnt[3];
+            if ((int64_t)n_in + n_arr > h->max_particles) return LM_ENOSPC;
+            int first = n_in;
+            for (int d = 0; d < 2; ++d) {
+                LM_CUDA(launch_unpack_arrivals(h, d, cnt[2 + d], first, h->lon[c], h->lat[c], h->sp[c], h->id[c], s));
+                first += cnt[2 + d];
+            }
+            LM_CUDA(launch_bin_count(h, h->lon[c], h->lat[c], h->sp[c], h->id[c], n_in, n_arr, false, s));
+            n_out = n_in - cnt[0] - cnt[1] + n_arr;
+            n_in += n_arr;
+            h->n_moved_out = cnt[0] + cnt[1];
+            h->n_moved_in = n_arr;
+        }
         const int d = c ^ 1;
-        LM_CUDA(launch_bin(h, h->lon[c], h->lat[c], h->sp[c], h->id[c], n, h->lon[d], h->lat[d], h->sp[d], h->id[d], s));
+        LM_CUDA(launch_bin_finish(h, h->lon[c], h->lat[c], h->sp[c], h->id[c], n_in, n_out, h->lon[d], h->lat[d],
+                                  h->sp[d], h->id[d], s));
         h->cur = c = d;
+        h->n = n_out;
         h->binned = true;
     }
-    if (timing) LM_CUDA(cudaEventRecord(h->ev_phase[2], s));
-    if (flags & LM_STEP_INTERACT) {
-        if (!prm) return LM_EINVAL;
-        rc = check_radius(h, r);
-        if (rc) return rc;
-        const RpsDev rd = to_dev(prm);
-        const bool emit = (flags & LM_STEP_EMIT_PAIRS) && pairs_out && cap > 0;
-        LM_CUDA(launch_pairs(h, h->lon[c], h->lat[c], h->id[c], h->sp[c], n, r, &rd,
-                             emit ? reinterpret_cast<int2 *>(pairs_out) : nullptr, emit ? cap : 0, s));
-        h->emit_cap = emit ? cap : -1;
-    }
-    if (timing) LM_CUDA(cudaEventRecord(h->ev_phase[3], s));
-    if (flags & LM_STEP_STATS) LM_CUDA(launch_stats(h->lon[c], h->lat[c], h->sp[c], n, h->ctr, s, &h->launches));
-    if (timing) LM_CUDA(cudaEventRecord(h->ev_phase[4], s));
-    h->timed = timing;
+    if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[2], s));
+    if (h->has_south) LM_CUDA(launch_ghost_pack(h, h->lon[c], h->lat[c], h->id[c], s));
+    h->stage = 2;
     return LM_OK;
+}
+
+int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t cap, void *stream)
+{
+    if (!h) return LM_EINVAL;
+    if (h->stage != 2) return LM_ESTATE;
+    LM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = as_stream(stream);
+    const int c = h->cur, n = (int)h->n;
+    if (h->has_north) LM_CUDA(launch_ghost_unpack(h, h->lon[c], h->lat[c], h->id[c], n, s));
+    h->rps_cap = -1;
+    h->emit_cap = -1;
+    if (h->step_flags & LM_STEP_INTERACT) {
+        const int rc = check_radius(h, r);
+        if (rc) return rc;
+        const bool emit = (h->step_flags & LM_STEP_EMIT_PAIRS) && pairs_out && cap > 0;
+        LM_CUDA(launch_find(h, h->lon[c], h->lat[c], h->id[c], n, r, &h->step_rps,
+                            emit ? reinterpret_cast<int2 *>(pairs_out) : nullptr, emit ? cap : 0, s));
+        h->emit_cap = emit ? cap : -1;
+        if (n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 0, 5, s));
+    }
+    if (h->has_south) LM_CUDA(launch_row0_species_pack(h, h->sp[c], s));
+    h->stage = 3;
+    return LM_OK;
+}
+
+int lm_step_interact_end(lm_handle h, void *stream)
+{
+    if (!h) return LM_EINVAL;
+    if (h->stage != 3) return LM_ESTATE;
+    LM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = as_stream(stream);
+    const int c = h->cur, n = (int)h->n;
+    if (h->has_north) LM_CUDA(launch_ghost_species_unpack(h, h->sp[c], n, s));
+    if ((h->step_flags & LM_STEP_INTERACT) && n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, s));
+    if (h->has_north) LM_CUDA(launch_ghost_species_pack(h, h->sp[c], n, s));
+    if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[3], s));
+    h->stage = 4;
+    return LM_OK;
+}
+
+int lm_step_finish(lm_handle h, void *stream)
+{
+    if (!h) return LM_EINVAL;
+    if (h->stage != 4) return LM_ESTATE;
+    LM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = as_stream(stream);
+    const int c = h->cur, n = (int)h->n;
+    if (h->has_south) LM_CUDA(launch_row0_species_unpack(h, h->sp[c], s));
+    if (h->step_flags & LM_STEP_STATS) LM_CUDA(launch_stats(h->lon[c], h->lat[c], h->sp[c], n, h->ctr, s, &h->launches));
+    if (h->step_flags & LM_STEP_TIMING) {
+        LM_CUDA(cudaEventRecord(h->ev_phase[4], s));
+        h->timed = true;
+    }
+    h->stage = 0;
+    return LM_OK;
+}
+
+int lm_step(lm_handle h, int32_t flags, const lm_stage_times *st, float dt, double diffuse_amp_deg, double r,
+            const lm_rps_params *prm, int32_t *pairs_out, int64_t cap, void *stream)
+{
+    if (!h) return LM_EINVAL;
+    if (in_strip_mode(h)) return LM_ESTATE;   // strips need the exchanges between the stages: use lm_step_move ...
+    int rc = lm_step_move(h, flags, st, dt, diffuse_amp_deg, prm, stream);
+    if (rc == LM_OK) rc = lm_step_bin(h, stream);
+    if (rc == LM_OK) rc = lm_step_interact_begin(h, r, pairs_out, cap, stream);
+    if (rc == LM_OK) rc = lm_step_interact_end(h, stream);
+    if (rc == LM_OK) rc = lm_step_finish(h, stream);
+    if (rc != LM_OK) h->stage = 0;
+    return rc;
 }
 
 int lm_phase_times(lm_handle h, float *ms_out)
@@ -443,7 +652,13 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
         out->bbox[1] = dec_f(c.bbox_enc[1]);
         out->bbox[2] = dec_f(~c.bbox_enc[2]);
         out->bbox[3] = dec_f(c.bbox_enc[3]);
+        out->n_particles = h->n;
+        out->n_moved_in = h->n_moved_in;
+        out->n_moved_out = h->n_moved_out;
+        out->n_misrouted = (int64_t)c.n_misrouted;
     }
+    if (c.n_xfer_overflow) return LM_ENOSPC;                                       // migration / ghost buffers too small
+    if (c.n_misrouted) return LM_ESTATE;                                           // a particle crossed more than one strip
     if (h->emit_cap >= 0 && (int64_t)c.n_pairs > h->emit_cap) return LM_ENOSPC;   // pair list truncated
     if (h->rps_cap >= 0 && (int64_t)c.n_pairs > h->rps_cap) return LM_ENOSPC;     // RPS hand-off buffer too small: species invalid
     if (c.n_overflow) return LM_ENOSPC;

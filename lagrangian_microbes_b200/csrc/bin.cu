@@ -32,15 +32,38 @@ __device__ __forceinline__ int cell_coord(float v, double origin, double inv_h, 
     return (int)q;
 }
 
+// A particle whose global row lies outside [row0, row0 + rows_owned) has left the strip (multi-GPU latitude
+// strips): with st.migrate it is packed into the send buffer of the neighbour it moved towards
+// (record k at [1 + k], running count in [0].x) and dropped from the local state (key = -1).
 __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict__ lon, const float *__restrict__ lat,
-                                                        int n, lm_grid g, int32_t *__restrict__ keys,
-                                                        int32_t *__restrict__ cell_count, Counters *ctr)
+                                                        const int8_t *__restrict__ sp, const int32_t *__restrict__ id,
+                                                        int first, int n, lm_grid g, Strip st,
+                                                        int32_t *__restrict__ keys, int32_t *__restrict__ cell_count,
+                                                        int4 *__restrict__ send_south, int4 *__restrict__ send_north,
+                                                        int send_cap, Counters *ctr)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    const int p = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= first + n) return;
     bool clamped = false;
-    const int cx = cell_coord(lon[p], g.x0, g.inv_h, g.ncx, clamped);
-    const int cy = cell_coord(lat[p], g.y0, g.inv_h, g.ncy, clamped);
+    const float x = lon[p], y = lat[p];
+    const int cx = cell_coord(x, g.x0, g.inv_h, g.ncx, clamped);
+    int cy = cell_coord(y, g.y0, g.inv_h, g.ncy, clamped) - st.row0;
+    if (cy < 0 || cy >= st.rows_owned) {
+        int4 *buf = (cy < 0) ? send_south : send_north;
+        if (st.migrate && buf) {
+            const unsigned int slot = atomicAdd(reinterpret_cast<unsigned int *>(&buf[0].x), 1u);
+            if (slot < (unsigned int)send_cap)
+                buf[1 + slot] = make_int4(__float_as_int(x), __float_as_int(y), id ? id[p] : p, sp ? (int)sp[p] : 0);
+            else
+                atomicAdd(&ctr->n_xfer_overflow, 1u);
+            keys[p] = -1;
+            return;
+        }
+        // an arrival that does not belong here either (it crossed more than one strip in one step), or a
+        // particle handed to lm_state_set on the wrong rank: kept in an edge row and reported
+        if (st.rows_owned < g.ncy) atomicAdd(&ctr->n_misrouted, 1u);
+        cy = (cy < 0) ? 0 : st.rows_owned - 1;
+    }
     const int key = cy * g.ncx + cx;
     keys[p] = key;
     atomicAdd(cell_count + key, 1);
@@ -147,7 +170,9 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const int32_t *__restr
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const int slot = atomicAdd(cell_cursor + keys[p], 1);
+    const int key = keys[p];
+    if (key < 0) return;                     // left the strip
+    const int slot = atomicAdd(cell_cursor + key, 1);
     slots[slot] = make_int2(p, id ? id[p] : p);
 }
 
@@ -173,30 +198,49 @@ __global__ void __launch_bounds__(256) bin_reorder_kernel(const int2 *__restrict
     id_o[dst] = me.y;
 }
 
-cudaError_t launch_bin(lm_handle_s *h, const float *lon, const float *lat, const int8_t *sp, const int32_t *id, int n,
-                       float *lon_o, float *lat_o, int8_t *sp_o, int32_t *id_o, cudaStream_t s)
+cudaError_t launch_bin_count(lm_handle_s *h, const float *lon, const float *lat, const int8_t *sp, const int32_t *id,
+                             int first, int n, bool migrate, cudaStream_t s)
 {
-    const int ncells = h->grid.ncx * h->grid.ncy;
+    if (n <= 0) return cudaSuccess;
+    Strip st = h->strip;
+    st.migrate = migrate ? 1 : 0;
+    bin_count_kernel<<<(n + 255) / 256, 256, 0, s>>>(lon, lat, sp, id, first, n, h->grid, st, h->keys, h->cell_count,
+                                                      h->has_south ? h->mig_send[0] : nullptr,
+                                                      h->has_north ? h->mig_send[1] : nullptr, (int)h->send_cap, h->ctr);
+    ++h->launches;
+    return cudaGetLastError();
+}
+
+// scan + scatter + reorder: n_in source records (leavers have key -1), n_out of them stay
+cudaError_t launch_bin_finish(lm_handle_s *h, const float *lon, const float *lat, const int8_t *sp, const int32_t *id,
+                              int n_in, int n_out, float *lon_o, float *lat_o, int8_t *sp_o, int32_t *id_o, cudaStream_t s)
+{
+    const int ncells = h->grid.ncx * h->strip.rows_owned;
     const int ntiles = (ncells + SCAN_TILE - 1) / SCAN_TILE;
-    const int block = 256;
-    const int pgrid = (n + block - 1) / block;
     // cell_count is left zeroed by scan_apply (and by lm_create / lm_set_grid)
-    if (n > 0) {
-        bin_count_kernel<<<pgrid, block, 0, s>>>(lon, lat, n, h->grid, h->keys, h->cell_count, h->ctr);
-        ++h->launches;
-    }
     scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(h->cell_count, ncells, h->block_sums);
     scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(h->block_sums, ntiles);
     scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(h->cell_count, ncells, h->block_sums, h->cell_start,
-                                                       h->cell_cursor, n);
+                                                       h->cell_cursor, n_out);
     h->launches += 3;
-    if (n > 0) {
-        bin_scatter_kernel<<<pgrid, block, 0, s>>>(h->keys, id, n, h->cell_cursor, h->slots);
-        bin_reorder_kernel<<<pgrid, block, 0, s>>>(h->slots, h->keys, h->cell_start, lon, lat, sp, n, lon_o, lat_o,
-                                                    sp_o, id_o);
-        h->launches += 2;
+    if (n_in > 0) {
+        bin_scatter_kernel<<<(n_in + 255) / 256, 256, 0, s>>>(h->keys, id, n_in, h->cell_cursor, h->slots);
+        ++h->launches;
+    }
+    if (n_out > 0) {
+        bin_reorder_kernel<<<(n_out + 255) / 256, 256, 0, s>>>(h->slots, h->keys, h->cell_start, lon, lat, sp, n_out,
+                                                                lon_o, lat_o, sp_o, id_o);
+        ++h->launches;
     }
     return cudaGetLastError();
+}
+
+cudaError_t launch_bin(lm_handle_s *h, const float *lon, const float *lat, const int8_t *sp, const int32_t *id, int n,
+                       float *lon_o, float *lat_o, int8_t *sp_o, int32_t *id_o, cudaStream_t s)
+{
+    cudaError_t e = launch_bin_count(h, lon, lat, sp, id, 0, n, false, s);
+    if (e != cudaSuccess) return e;
+    return launch_bin_finish(h, lon, lat, sp, id, n, n, lon_o, lat_o, sp_o, id_o, s);
 }
 
 // out[id[p]] = value[p]   (the reference's per-step record is in particle-id order:

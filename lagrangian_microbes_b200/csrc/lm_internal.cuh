@@ -23,7 +23,22 @@ struct Counters {
     unsigned long long species[4];
     unsigned int bbox_enc[4];   // order-preserving uint encodings: min lon, max lon, min lat, max lat
     unsigned long long n_overflow;   // neighbourhoods too dense for the 16-bit per-direction hit counts
+    unsigned int n_leave[2];         // particles that left the strip this step: [0] southwards, [1] northwards
+    unsigned int n_misrouted;        // arrivals that belong to neither this strip nor ... (moved > 1 strip in a step)
+    unsigned int n_xfer_overflow;    // migration / ghost records that did not fit the exchange buffers
 };
+
+// Strip geometry of one handle inside the GLOBAL cell grid (multi-GPU latitude strips).
+// Single GPU: row0 = 0, rows_owned = rows_local = ncy, no neighbours.
+struct Strip {
+    int row0;         // first global cell row owned by this handle (even)
+    int rows_owned;   // rows owned: particles of these rows live here
+    int rows_local;   // rows_owned + 1 when a ghost row (first row of the strip to the north) is appended
+    int migrate;      // bin_count: pack particles outside the strip into the send buffers (else clamp)
+};
+
+// layout of the ghost-row message (int32 words): header | cell_start row [row_cap + 1] | lon | lat | id [ghost_cap each]
+constexpr int GHOST_HDR = 4;
 
 struct RpsDev {
     double pRS, pPR, pSP;
@@ -75,6 +90,24 @@ struct lm_handle_s {
     bool timed;
     int stage_idx;
     int64_t launches;
+    // ---- latitude-strip decomposition (lm_strip_alloc / lm_set_strip); all zero for a single GPU
+    lm::Strip strip;
+    bool has_south, has_north;
+    int64_t send_cap, ghost_cap, row_cap;
+    int4 *mig_send[2], *mig_recv[2];     // [send_cap + 1] records (lon bits, lat bits, id, species); [0].x = count
+    int32_t *ghost_send, *ghost_recv;    // GHOST_HDR + row_cap + 1 + 3 * ghost_cap words
+    int8_t *gsp_send, *gsp_recv;         // [ghost_cap] species of the ghost row, north -> south after phase 5
+    int8_t *gret_send, *gret_recv;       // [ghost_cap] species of the ghost row, south -> north after phase 8
+    int32_t *xfer_counts_host;           // pinned: n_leave[2], n_arrive[2]
+    int n_moved_in, n_moved_out;         // last step (host copies)
+    // staged step (lm_step_move .. lm_step_finish)
+    int32_t step_flags;
+    int stage;                           // 0 idle | 1 moved | 2 binned | 3 interact begun | 4 interact ended
+    bool step_moved;
+    double step_r;
+    lm::RpsDev step_rps;
+    int2 *step_pairs;
+    int64_t step_cap;
 };
 
 namespace lm {
@@ -87,6 +120,21 @@ cudaError_t launch_diffuse(float *lon, float *lat, const int32_t *ids, int n, do
 // bins (lon,lat,sp,id)[src] into (cell,id) order in dst; sp / id may be null (id -> source index)
 cudaError_t launch_bin(lm_handle_s *h, const float *lon, const float *lat, const int8_t *sp, const int32_t *id, int n,
                        float *lon_o, float *lat_o, int8_t *sp_o, int32_t *id_o, cudaStream_t s);
+// the same in two halves, with migration between strips in the middle (csrc/bin.cu, csrc/strip.cu)
+cudaError_t launch_bin_count(lm_handle_s *h, const float *lon, const float *lat, const int8_t *sp, const int32_t *id,
+                             int first, int n, bool migrate, cudaStream_t s);
+cudaError_t launch_bin_finish(lm_handle_s *h, const float *lon, const float *lat, const int8_t *sp, const int32_t *id,
+                              int n_in, int n_out, float *lon_o, float *lat_o, int8_t *sp_o, int32_t *id_o,
+                              cudaStream_t s);
+cudaError_t launch_unpack_arrivals(lm_handle_s *h, int dir, int n_arrive, int first, float *lon, float *lat, int8_t *sp,
+                                   int32_t *id, cudaStream_t s);
+cudaError_t launch_ghost_pack(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, cudaStream_t s);
+cudaError_t launch_ghost_unpack(lm_handle_s *h, float *lon, float *lat, int32_t *id, int n_owned, cudaStream_t s);
+// species of the first owned row -> gsp_send (pack) / gsp_recv -> ghost particles (unpack); and the way back
+cudaError_t launch_row0_species_pack(lm_handle_s *h, const int8_t *sp, cudaStream_t s);
+cudaError_t launch_ghost_species_unpack(lm_handle_s *h, int8_t *sp, int n_owned, cudaStream_t s);
+cudaError_t launch_ghost_species_pack(lm_handle_s *h, const int8_t *sp, int n_owned, cudaStream_t s);
+cudaError_t launch_row0_species_unpack(lm_handle_s *h, int8_t *sp, cudaStream_t s);
 cudaError_t launch_scatter_by_id(const float *lon, const float *lat, const int8_t *sp, const int32_t *id, int n,
                                  float *lon_o, float *lat_o, int8_t *sp_o, cudaStream_t s, int64_t *launches);
 cudaError_t launch_stats(const float *lon, const float *lat, const int8_t *sp, int n, Counters *ctr, cudaStream_t s,
@@ -95,6 +143,10 @@ cudaError_t launch_stats(const float *lon, const float *lat, const int8_t *sp, i
 cudaError_t launch_pairs(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
                          double r, const RpsDev *rps /* null = find only */, int2 *pairs_out, int64_t cap,
                          cudaStream_t s);
+// the two halves: find (+ hand-off lists when rps != null), then resolve phases [first, last] of 0..8
+cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int n, double r,
+                        const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s);
+cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int last, cudaStream_t s);
 cudaError_t launch_pair_uniforms(const int2 *pairs, int64_t np, uint64_t seed, uint64_t step, double *u,
                                  cudaStream_t s);
 int resolve_explicit(lm_handle_s *h, const int2 *pairs, const double *u, int64_t np, int8_t *species, int64_t n,

@@ -49,7 +49,8 @@ struct FindArgs {
     const int32_t *__restrict__ id;
     const int32_t *__restrict__ cell_start;
     lm_grid g;
-    int n;
+    int row0, rows_owned, rows_local;    // strip geometry (single GPU: 0, ncy, ncy)
+    int n;                               // anchors = owned particles (ghost-row particles are partners only)
     float r2_lo, r2_hi;
     double r2;
     uint32_t seed_lo, seed_hi, step_lo, step_hi;
@@ -113,8 +114,9 @@ __global__ void __launch_bounds__(FIND_THREADS) find_pairs_kernel(FindArgs A)
     if (valid) {
         xa = __ldg(A.lon + a); ya = __ldg(A.lat + a);
         my_id = __ldg(A.id + a);
-        const int ncx = A.g.ncx, ncy = A.g.ncy;
-        const int cx = cell_coord2(xa, A.g.x0, A.g.inv_h, ncx), cy = cell_coord2(ya, A.g.y0, A.g.inv_h, ncy);
+        const int ncx = A.g.ncx, ncy = A.rows_local;
+        const int cx = cell_coord2(xa, A.g.x0, A.g.inv_h, ncx);
+        const int cy = max(0, min(cell_coord2(ya, A.g.y0, A.g.inv_h, A.g.ncy) - A.row0, A.rows_owned - 1));   // == bin.cu
         const int c = cy * ncx + cx;
         const bool e_ok = cx + 1 < ncx;
         sE = __ldg(A.cell_start + c + 1);
@@ -376,13 +378,15 @@ __global__ void __launch_bounds__(256) resolve_phase_kernel(ResolveArgs A)
 }
 
 // ---------------------------------------------------------------------------------------------------
-cudaError_t launch_pairs(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
-                         double r, const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s)
+cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int n, double r,
+                        const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s)
 {
+    h->rps_cap = rps ? h->max_pairs : -1;
     if (n <= 0) return cudaSuccess;
     FindArgs F;
     F.lon = lon; F.lat = lat; F.id = id; F.cell_start = h->cell_start;
     F.g = h->grid; F.n = n;
+    F.row0 = h->strip.row0; F.rows_owned = h->strip.rows_owned; F.rows_local = h->strip.rows_local;
     F.r2 = r * r;
     F.r2_lo = (float)(F.r2 * (1.0 - 4e-6));
     F.r2_hi = (float)(F.r2 * (1.0 + 4e-6));
@@ -403,7 +407,6 @@ cudaError_t launch_pairs(lm_handle_s *h, const float *lon, const float *lat, con
     F.cap_hits = rps ? (unsigned long long)h->max_pairs : 0ull;
     F.cap_pairs = (pairs_out && cap > 0) ? (unsigned long long)cap : 0ull;
     F.ctr = h->ctr;
-    h->rps_cap = rps ? h->max_pairs : -1;
     const bool emit = F.cap_pairs > 0;
     const int grid = (n + FIND_THREADS - 1) / FIND_THREADS;
     if (rps) {
@@ -414,28 +417,46 @@ cudaError_t launch_pairs(lm_handle_s *h, const float *lon, const float *lat, con
         else find_pairs_kernel<false, false><<<grid, FIND_THREADS, 0, s>>>(F);
     }
     ++h->launches;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess || !rps) return e;
+    return cudaGetLastError();
+}
 
+// phases [first, last] of the canonical cell-phase order on the local rows.  Strip boundaries sit on even
+// global rows, so local and global row parities agree; same-cell and east units cover the owned rows,
+// cross-row units may reach into the ghost row (local row rows_owned), only in phases 6-8.
+cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int last, cudaStream_t s)
+{
+    if (h->rps_cap < 0) return cudaSuccess;
     ResolveArgs R;
     R.sp = sp; R.cell_start = h->cell_start; R.meta = h->meta; R.hits = h->hits;
-    R.cap_hits = F.cap_hits;
-    R.ncx = h->grid.ncx; R.ncy = h->grid.ncy;
-    const long long ncx = R.ncx, ncy = R.ncy;
-    auto launch = [&](int mode, int parity, int dir, int d_idx, long long n_units) -> cudaError_t {
-        if (n_units <= 0) return cudaSuccess;
-        R.mode = mode; R.parity = parity; R.dir = dir; R.d_idx = d_idx; R.n_units = n_units;
+    R.cap_hits = (unsigned long long)h->max_pairs;
+    R.ncx = h->grid.ncx; R.ncy = h->strip.rows_local;
+    const long long ncx = R.ncx, rows_owned = h->strip.rows_owned, rows_local = h->strip.rows_local;
+    for (int ph = first; ph <= last; ++ph) {
+        long long n_units;
+        if (ph == 0) { R.mode = MODE_SAME; R.parity = 0; R.dir = 0; R.d_idx = 0; n_units = ncx * rows_owned; }
+        else if (ph <= 2) {
+            R.mode = MODE_EAST; R.parity = ph - 1; R.dir = 0; R.d_idx = 1;
+            n_units = ((ncx - R.parity) / 2) * rows_owned;
+        } else {
+            R.mode = MODE_CROSS; R.parity = (ph - 3) / 3; R.dir = (ph - 3) % 3 - 1; R.d_idx = 3 + R.dir;
+            n_units = ((rows_local - R.parity) / 2) * ncx;
+        }
+        if (n_units <= 0) continue;
+        R.n_units = n_units;
         resolve_phase_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, s>>>(R);
         ++h->launches;
-        return cudaGetLastError();
-    };
-    if ((e = launch(MODE_SAME, 0, 0, 0, ncx * ncy)) != cudaSuccess) return e;                    // phase 0
-    for (int q = 0; q < 2; ++q)                                                                   // phases 1, 2
-        if ((e = launch(MODE_EAST, q, 0, 1, ((ncx - q) / 2) * ncy)) != cudaSuccess) return e;
-    for (int q = 0; q < 2; ++q)                                                                   // phases 3..8
-        for (int d = -1; d <= 1; ++d)
-            if ((e = launch(MODE_CROSS, q, d, 3 + d, ((ncy - q) / 2) * ncx)) != cudaSuccess) return e;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
     return cudaSuccess;
+}
+
+cudaError_t launch_pairs(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
+                         double r, const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s)
+{
+    cudaError_t e = launch_find(h, lon, lat, id, n, r, rps, pairs_out, cap, s);
+    if (e != cudaSuccess || !rps || n <= 0) return e;
+    return launch_resolve_phases(h, sp, 0, 8, s);
 }
 
 }  // namespace lm

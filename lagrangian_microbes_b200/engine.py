@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import Grid, RpsParams, StageTimes, Stats, check
+from ._lib import Grid, RpsParams, StageTimes, Stats, Strip, StripBuffers, check
 
 
 def make_grid(lon_min, lon_max, lat_min, lat_max, radius, n_particles, max_cells, margin=0.5, cells_per_particle=2.0):
@@ -174,6 +174,46 @@ class Engine:
                              ctypes.byref(rps) if rps is not None else None, _ptr(pairs_out), cap, self._stream()),
               "lm_step")
 
+    # ---- latitude strips (multi-GPU): staged step, the caller exchanges the buffers between the stages ----
+    def strip_alloc(self, send_cap, ghost_cap, row_cap):
+        check(self.L.lm_strip_alloc(self.h, int(send_cap), int(ghost_cap), int(row_cap)), "lm_strip_alloc")
+
+    def set_strip(self, row0, rows_owned, has_south, has_north):
+        st = Strip(int(row0), int(rows_owned), int(bool(has_south)), int(bool(has_north)))
+        check(self.L.lm_set_strip(self.h, ctypes.byref(st)), "lm_set_strip")
+
+    def strip_buffers(self):
+        """Exchange buffers as uint8 CUDA tensors (no copy): dict name -> tensor / [south, north] pair."""
+        b = StripBuffers()
+        check(self.L.lm_strip_buffers_get(self.h, ctypes.byref(b)), "lm_strip_buffers_get")
+
+        def view(ptr, nbytes):
+            return torch.as_tensor(_CudaArray(int(ptr), int(nbytes), 1, "|u1"), device=self.device)
+        return {"mig_send": [view(b.mig_send[k], b.mig_bytes) for k in range(2)],
+                "mig_recv": [view(b.mig_recv[k], b.mig_bytes) for k in range(2)],
+                "ghost_send": view(b.ghost_send, b.ghost_bytes), "ghost_recv": view(b.ghost_recv, b.ghost_bytes),
+                "gsp_send": view(b.gsp_send, b.species_bytes), "gsp_recv": view(b.gsp_recv, b.species_bytes),
+                "gret_send": view(b.gret_send, b.species_bytes), "gret_recv": view(b.gret_recv, b.species_bytes)}
+
+    def step_move(self, flags, stage_times=None, dt=0.0, diffuse_amp_deg=0.0, rps=None):
+        check(self.L.lm_step_move(self.h, int(flags), ctypes.byref(stage_times) if stage_times is not None else None,
+                                  float(dt), float(diffuse_amp_deg), ctypes.byref(rps) if rps is not None else None,
+                                  self._stream()), "lm_step_move")
+
+    def step_bin(self):
+        check(self.L.lm_step_bin(self.h, self._stream()), "lm_step_bin")
+
+    def step_interact_begin(self, r=0.0, pairs_out=None):
+        cap = pairs_out.shape[0] if pairs_out is not None else 0
+        check(self.L.lm_step_interact_begin(self.h, float(r), _ptr(pairs_out), cap, self._stream()),
+              "lm_step_interact_begin")
+
+    def step_interact_end(self):
+        check(self.L.lm_step_interact_end(self.h, self._stream()), "lm_step_interact_end")
+
+    def step_finish(self):
+        check(self.L.lm_step_finish(self.h, self._stream()), "lm_step_finish")
+
     def state_get(self, lon_out=None, lat_out=None, species_out=None):
         check(self.L.lm_state_get(self.h, _ptr(lon_out), _ptr(lat_out), _ptr(species_out), self._stream()), "lm_state_get")
 
@@ -187,12 +227,14 @@ class Engine:
     def host_copies_sync(self):
         check(self.L.lm_host_copies_sync(self.h), "lm_host_copies_sync")
 
-    def state_view(self):
-        """Raw resident arrays in storage (cell, id) order as torch tensors (no copy): lon, lat, species, ids, cell_start."""
+    def state_view(self, rows=None):
+        """Raw resident arrays in storage (cell, id) order as torch tensors (no copy): lon, lat, species, ids,
+        cell_start (``rows`` = number of local cell rows of a strip; default: the whole grid)."""
         p = [ctypes.c_void_p() for _ in range(5)]
         check(self.L.lm_state_view(self.h, *[ctypes.byref(x) for x in p]), "lm_state_view")
         n = self.state_size()
         g = self.get_grid()
+        rows = g.ncy if rows is None else int(rows)
 
         def view(ptr, count, dtype, itemsize):
             if count == 0:
@@ -200,13 +242,15 @@ class Engine:
             arr = _CudaArray(ptr.value, count, itemsize, np.dtype({torch.float32: "f4", torch.int8: "i1", torch.int32: "i4"}[dtype]).str)
             return torch.as_tensor(arr, device=self.device)
         return (view(p[0], n, torch.float32, 4), view(p[1], n, torch.float32, 4), view(p[2], n, torch.int8, 1),
-                view(p[3], n, torch.int32, 4), view(p[4], g.ncx * g.ncy + 1, torch.int32, 4))
+                view(p[3], n, torch.int32, 4), view(p[4], g.ncx * rows + 1, torch.int32, 4))
 
     # ---- status ----------------------------------------------------------------------------------
-    def sync_stats(self, raise_on_overflow=True):
+    def sync_stats(self, raise_on_overflow=True, allow_misrouted=False):
         st = Stats()
         rc = self.L.lm_sync_stats(self.h, ctypes.byref(st), self._stream())
         if rc == _lib.LM_ENOSPC and not raise_on_overflow:
+            return st
+        if rc == _lib.LM_ESTATE and allow_misrouted and st.n_misrouted > 0:
             return st
         check(rc, "lm_sync_stats")
         return st

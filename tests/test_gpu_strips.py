@@ -1,0 +1,198 @@
+"""GPU parity of the latitude-strip decomposition: G strips -- several handles on one device
+with device-copy exchanges, or one process per GPU with NCCL send/recv -- must reproduce the single-handle
+fused step BIT FOR BIT (positions, pair set, species), which in turn is checked against the oracle in
+tests/test_gpu_parity.py::test_fused_simulation_matches_oracle_loop."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import pairs as opairs
+from oracle import rk4 as ork4
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+P = (0.55, 0.6, 0.9)
+R = 0.01
+
+
+class HostFS:
+    def __init__(self, fs):
+        self.u, self.v, self.lon, self.lat, self.time = fs.u, fs.v, fs.lon, fs.lat, fs.time
+
+    def to_device(self, device):
+        return tuple(torch.from_numpy(a).to(device) for a in (self.u, self.v, self.lon, self.lat))
+
+
+def small_fs():
+    g = golden("rk4_small.npz")
+    return HostFS(ork4.FieldSet(g["grid_lon"], g["grid_lat"], g["grid_time"], g["u"], g["v"]))
+
+
+def particles(n, seed, clustered=False):
+    rng = np.random.default_rng(seed)
+    lon = 205.0 + 1.2 * rng.random(n)
+    lat = 32.0 + 1.2 * rng.random(n)
+    if clustered:                       # a dense blob: unbalanced rows, heavy cells next to a strip boundary
+        k = n // 3
+        lon[:k] = 205.6 + 0.05 * rng.standard_normal(k)
+        lat[:k] = 32.55 + 0.05 * rng.standard_normal(k)
+    sp = rng.integers(1, 4, n).astype(np.int8)
+    return lon.astype(np.float32), lat.astype(np.float32), sp
+
+
+def single(lon, lat, sp, grid, fs, seed, Kh=0.0):
+    """The single-handle reference run on the SAME grid as the strips."""
+    from lagrangian_microbes_b200.simulation import FusedSimulation
+    sim = FusedSimulation(lon, lat, sp, R, *P, fs, dt_seconds=3600.0, Kh=Kh, seed=seed, emit_pairs=True,
+                          pair_capacity=40 * lon.size, regrid_every=0, max_cells=max(1 << 20, 2 * grid.ncx * grid.ncy))
+    sim.engine.set_grid(grid)
+    sim.grid = grid
+    sim.engine.state_set(torch.from_numpy(lon).cuda(), torch.from_numpy(lat).cuda(), torch.from_numpy(sp).cuda())
+    return sim
+
+
+def compare_step(ss, sim, step):
+    st = sim.step(check=True)
+    ss.step(check=True)
+    n_pairs, n_part, counts = ss.totals()
+    assert n_part == sim.n
+    lon, lat, sp = ss.gather()
+    wl, wa, ws = sim.download()
+    assert np.array_equal(lon, wl) and np.array_equal(lat, wa), "positions differ at step %d" % step
+    assert n_pairs == st.n_pairs, "pair count %d != %d at step %d" % (n_pairs, st.n_pairs, step)
+    got = opairs.sort_pairs(np.concatenate([p.reshape(-1, 2) for p in ss.local_pairs()]))
+    want = opairs.sort_pairs(sim.pairs[:st.n_pairs].cpu().numpy())
+    assert np.array_equal(got, want), "pair set differs at step %d" % step
+    assert np.array_equal(sp, ws), "species differ at step %d (%d microbes)" % (step, int((sp != ws).sum()))
+    assert counts == list(st.species_count)
+    return st.n_pairs
+
+
+@pytest.mark.parametrize("G,clustered", [(2, False), (3, True), (4, False), (7, True)])
+def test_strips_on_one_device_equal_single_handle(G, clustered):
+    from lagrangian_microbes_b200.strips import LocalTransport, StripSet
+    n, seed = 40000, 11 + G
+    fs = small_fs()
+    lon, lat, sp = particles(n, seed, clustered)
+    ids = np.arange(n, dtype=np.int32)
+    # hand every strip a contiguous TILE of the particles (the reference's split): settle() must route them
+    per = n // G
+    cut = [slice(g * per, (g + 1) * per if g < G - 1 else n) for g in range(G)]
+    ss = StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
+                  [ids[c] for c in cut], n, R, *P, fs, seed=seed, local_strips=list(range(G)), slack=3.0,
+                  pairs_per_particle=40, grid_margin=0.25)
+    assert all(e % 2 == 0 for e in ss.edges[:-1]) and ss.edges[-1] == ss.grid.ncy
+    sim = single(lon, lat, sp, ss.grid, fs, seed)
+    total, moved = 0, 0
+    for step in range(6):
+        total += compare_step(ss, sim, step)
+        moved += sum(st.n_moved_in for st in ss.last_stats)
+    print("G=%d: %d pairs, %d migrations, edges %s" % (G, total, moved, ss.edges))
+    assert total > 1000 and moved > 0
+    ss.close()
+
+
+def test_strips_with_diffusion_and_rebalancing():
+    from lagrangian_microbes_b200.strips import LocalTransport, StripSet
+    G, n, seed = 3, 30000, 3
+    fs = small_fs()
+    lon, lat, sp = particles(n, seed, clustered=True)
+    ids = np.arange(n, dtype=np.int32)
+    row_of = lambda ss_: None
+    cut = [slice(g, n, G) for g in range(G)]                # round-robin: almost everybody starts on the wrong strip
+    ss = StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
+                  [ids[c] for c in cut], n, R, *P, fs, seed=seed, Kh=20.0, local_strips=list(range(G)), slack=3.0,
+                  pairs_per_particle=40, grid_margin=0.25, rebalance_every=2)
+    sim = single(lon, lat, sp, ss.grid, fs, seed, Kh=20.0)
+    edges0 = list(ss.edges)
+    for step in range(6):
+        compare_step(ss, sim, step)
+    sizes = [s.engine.state_size() for s in ss.strips]
+    print("edges %s -> %s, strip sizes %s" % (edges0, ss.edges, sizes))
+    assert max(sizes) < 1.5 * n / G                          # rebalancing keeps the strips level
+    ss.close()
+
+
+def test_exchange_buffer_overflow_is_reported():
+    from lagrangian_microbes_b200._lib import LmError, LM_ENOSPC
+    from lagrangian_microbes_b200.strips import LocalTransport, StripSet
+    G, n = 2, 20000
+    fs = small_fs()
+    lon, lat, sp = particles(n, 0)
+    ids = np.arange(n, dtype=np.int32)
+    cut = [slice(g, n, G) for g in range(G)]
+    with pytest.raises(LmError) as ei:                      # half of each tile must migrate: 16 records are not enough
+        StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
+                 [ids[c] for c in cut], n, R, *P, fs, local_strips=list(range(G)), slack=3.0, send_cap=16)
+    assert ei.value.code == LM_ENOSPC
+    with pytest.raises(LmError) as ei:                      # the ghost row does not fit 8 records
+        ss = StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
+                      [ids[c] for c in cut], n, R, *P, fs, local_strips=list(range(G)), slack=3.0, ghost_cap=8)
+        ss.step(check=True)
+    assert ei.value.code == LM_ENOSPC
+
+
+# ------------------------------------------------------------------------------------------------------
+def _nccl_worker(rank, world, port, n, seed, steps, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from lagrangian_microbes_b200.strips import DistTransport, StripSet
+        fs = small_fs()
+        lon, lat, sp = particles(n, seed, clustered=True)
+        ids = np.arange(n, dtype=np.int32)
+        per = n // world
+        c = slice(rank * per, (rank + 1) * per if rank < world - 1 else n)
+        ss = StripSet(DistTransport(), lon[c], lat[c], sp[c], ids[c], n, R, *P, fs, seed=seed, slack=3.0,
+                      pairs_per_particle=40, grid_margin=0.25)
+        rec = []
+        for step in range(steps):
+            ss.step(check=True)
+            n_pairs, n_part, counts = ss.totals()
+            lo, la, s_ = ss.gather()
+            prs = ss.local_pairs()[0]
+            rec.append((n_pairs, lo, la, s_, prs))
+        if True:
+            np.savez(os.path.join(out_dir, "rank%d.npz" % rank), grid=np.array([ss.grid.x0, ss.grid.y0, ss.grid.inv_h]),
+                     grid_n=np.array([ss.grid.ncx, ss.grid.ncy]), n_pairs=np.array([r[0] for r in rec]),
+                     **{"lon%d" % k: r[1] for k, r in enumerate(rec)}, **{"lat%d" % k: r[2] for k, r in enumerate(rec)},
+                     **{"sp%d" % k: r[3] for k, r in enumerate(rec)}, **{"pairs%d" % k: r[4] for k, r in enumerate(rec)})
+        ss.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_strips_over_nccl_equal_single_handle(tmp_path, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    import torch.multiprocessing as mp
+    from lagrangian_microbes_b200._lib import Grid
+    n, seed, steps = 60000, 21, 5
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_worker, args=(world, port, n, seed, steps, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
+    g = parts[0]
+    grid = Grid(float(g["grid"][0]), float(g["grid"][1]), float(g["grid"][2]), int(g["grid_n"][0]), int(g["grid_n"][1]))
+    fs = small_fs()
+    lon, lat, sp = particles(n, seed, clustered=True)
+    sim = single(lon, lat, sp, grid, fs, seed)
+    for k in range(steps):
+        st = sim.step(check=True)
+        wl, wa, ws = sim.download()
+        assert int(g["n_pairs"][k]) == st.n_pairs
+        for p in parts:                                      # every rank gathered the same global record
+            assert np.array_equal(p["lon%d" % k], wl) and np.array_equal(p["lat%d" % k], wa)
+            assert np.array_equal(p["sp%d" % k], ws)
+        got = opairs.sort_pairs(np.concatenate([p["pairs%d" % k].reshape(-1, 2) for p in parts]))
+        assert np.array_equal(got, opairs.sort_pairs(sim.pairs[:st.n_pairs].cpu().numpy()))
