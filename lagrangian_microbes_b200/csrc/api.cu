@@ -469,8 +469,10 @@ int lm_step_bin(lm_handle h, void *stream)
                 LM_CUDA(cudaMemcpyAsync(cnt + 2 + d, h->mig_recv[d], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
             }
             LM_CUDA(cudaStreamSynchronize(s));
-            for (int k = 0; k < 4; ++k)
-                if (cnt[k] < 0 || cnt[k] > h->send_cap) return LM_ENOSPC;      // migration buffer too small
+            for (int k = 0; k < 4; ++k) {       // a full message holds send_cap records; the rest stayed behind
+                if (cnt[k] < 0) return LM_EINVAL;
+                if (cnt[k] > h->send_cap) cnt[k] = (int32_t)h->send_cap;
+            }
             const int n_arr = cnt[2] + cnt[3];
             if ((int64_t)n_in + n_arr > h->max_particles) return LM_ENOSPC;
             int first = n_in;
@@ -492,7 +494,8 @@ int lm_step_bin(lm_handle h, void *stream)
         h->binned = true;
     }
     if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[2], s));
-    if (h->has_south) LM_CUDA(launch_ghost_pack(h, h->lon[c], h->lat[c], h->id[c], s));
+    // the halo is only needed by (and only sized for) interacting steps; routing passes skip it
+    if (h->has_south && (h->step_flags & LM_STEP_INTERACT)) LM_CUDA(launch_ghost_pack(h, h->lon[c], h->lat[c], h->id[c], s));
     h->stage = 2;
     return LM_OK;
 }
@@ -504,7 +507,8 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
     LM_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = as_stream(stream);
     const int c = h->cur, n = (int)h->n;
-    if (h->has_north) LM_CUDA(launch_ghost_unpack(h, h->lon[c], h->lat[c], h->id[c], n, s));
+    const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
+    if (h->has_north && interact) LM_CUDA(launch_ghost_unpack(h, h->lon[c], h->lat[c], h->id[c], n, s));
     h->rps_cap = -1;
     h->emit_cap = -1;
     if (h->step_flags & LM_STEP_INTERACT) {
@@ -516,7 +520,7 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
         h->emit_cap = emit ? cap : -1;
         if (n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 0, 5, s));
     }
-    if (h->has_south) LM_CUDA(launch_row0_species_pack(h, h->sp[c], s));
+    if (h->has_south && interact) LM_CUDA(launch_row0_species_pack(h, h->sp[c], s));
     h->stage = 3;
     return LM_OK;
 }
@@ -528,9 +532,10 @@ int lm_step_interact_end(lm_handle h, void *stream)
     LM_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = as_stream(stream);
     const int c = h->cur, n = (int)h->n;
-    if (h->has_north) LM_CUDA(launch_ghost_species_unpack(h, h->sp[c], n, s));
-    if ((h->step_flags & LM_STEP_INTERACT) && n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, s));
-    if (h->has_north) LM_CUDA(launch_ghost_species_pack(h, h->sp[c], n, s));
+    const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
+    if (h->has_north && interact) LM_CUDA(launch_ghost_species_unpack(h, h->sp[c], n, s));
+    if (interact && n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, s));
+    if (h->has_north && interact) LM_CUDA(launch_ghost_species_pack(h, h->sp[c], n, s));
     if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[3], s));
     h->stage = 4;
     return LM_OK;
@@ -543,7 +548,7 @@ int lm_step_finish(lm_handle h, void *stream)
     LM_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = as_stream(stream);
     const int c = h->cur, n = (int)h->n;
-    if (h->has_south) LM_CUDA(launch_row0_species_unpack(h, h->sp[c], s));
+    if (h->has_south && (h->step_flags & LM_STEP_INTERACT)) LM_CUDA(launch_row0_species_unpack(h, h->sp[c], s));
     if (h->step_flags & LM_STEP_STATS) LM_CUDA(launch_stats(h->lon[c], h->lat[c], h->sp[c], n, h->ctr, s, &h->launches));
     if (h->step_flags & LM_STEP_TIMING) {
         LM_CUDA(cudaEventRecord(h->ev_phase[4], s));
@@ -658,7 +663,7 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
         out->n_misrouted = (int64_t)c.n_misrouted;
     }
     if (c.n_xfer_overflow) return LM_ENOSPC;                                       // migration / ghost buffers too small
-    if (c.n_misrouted) return LM_ESTATE;                                           // a particle crossed more than one strip
+    if (c.n_misrouted) return LM_ESTATE;   // particles held by a strip that does not own them (see bin.cu)
     if (h->emit_cap >= 0 && (int64_t)c.n_pairs > h->emit_cap) return LM_ENOSPC;   // pair list truncated
     if (h->rps_cap >= 0 && (int64_t)c.n_pairs > h->rps_cap) return LM_ENOSPC;     // RPS hand-off buffer too small: species invalid
     if (c.n_overflow) return LM_ENOSPC;

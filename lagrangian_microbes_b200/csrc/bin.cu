@@ -52,15 +52,16 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const float *__restrict_
         int4 *buf = (cy < 0) ? send_south : send_north;
         if (st.migrate && buf) {
             const unsigned int slot = atomicAdd(reinterpret_cast<unsigned int *>(&buf[0].x), 1u);
-            if (slot < (unsigned int)send_cap)
+            if (slot < (unsigned int)send_cap) {
                 buf[1 + slot] = make_int4(__float_as_int(x), __float_as_int(y), id ? id[p] : p, sp ? (int)sp[p] : 0);
-            else
-                atomicAdd(&ctr->n_xfer_overflow, 1u);
-            keys[p] = -1;
-            return;
+                keys[p] = -1;
+                return;
+            }
+            // this step's message is full: the particle stays one more step (the host clamps the count)
         }
-        // an arrival that does not belong here either (it crossed more than one strip in one step), or a
-        // particle handed to lm_state_set on the wrong rank: kept in an edge row and reported
+        // Held by a strip that does not own its row: an arrival that crossed more than one strip in a step, a
+        // leaver that did not fit the message, or a particle loaded on the wrong rank.  Kept in an edge row
+        // and reported; the next binning pass sends it on (StripSet.settle loops until there are none).
         if (st.rows_owned < g.ncy) atomicAdd(&ctr->n_misrouted, 1u);
         cy = (cy < 0) ? 0 : st.rows_owned - 1;
     }

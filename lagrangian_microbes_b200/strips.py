@@ -276,33 +276,41 @@ class StripSet:
         T, S = self.transport, self.strips
         for s in S:
             s.engine.step_move(flags, st_times, self.dt, self.diffuse_amp, self.rps)
+        halo = bool(flags & _lib.LM_STEP_INTERACT)        # routing passes move particles only
         T.exchange("mig", S)
         for s in S:
             s.engine.step_bin()
-        T.exchange("ghost", S)
+        if halo:
+            T.exchange("ghost", S)
         for s in S:
             s.engine.step_interact_begin(self.radius, s.pairs)
-        T.exchange("gsp", S)
+        if halo:
+            T.exchange("gsp", S)
         for s in S:
             s.engine.step_interact_end()
-        T.exchange("gret", S)
+        if halo:
+            T.exchange("gret", S)
         for s in S:
             s.engine.step_finish()
 
-    def settle(self, max_hops=None):
+    def settle(self, max_passes=100000):
         """Route every particle to the strip that owns its row: empty steps (no advection, no interaction)
-        until no particle is held by a strip it does not belong to.  One hop per pass."""
-        hops = 0
+        until no particle is held by a strip it does not belong to.  One hop and at most ``send_cap``
+        particles per boundary and pass."""
+        passes, best, stalled = 0, None, 0
         while True:
             for s in self.strips:       # (re)declare the strip: marks the state as not binned, so the pass re-bins
                 s.engine.set_strip(s.rows[0], s.rows[1] - s.rows[0], s.index > 0, s.index < self.n_strips - 1)
             self._staged(0)
             mis = [[s.engine.sync_stats(allow_misrouted=True).n_misrouted] for s in self.strips]
-            if self.transport.all_sum(mis)[0] == 0:
-                return hops
-            hops += 1
-            if hops > (max_hops if max_hops is not None else self.n_strips):
-                raise RuntimeError("particles could not be routed to their strips")
+            left = int(self.transport.all_sum(mis)[0])
+            if left == 0:
+                return passes
+            passes += 1
+            stalled = 0 if (best is None or left < best) else stalled + 1
+            best = left if best is None else min(best, left)
+            if passes > max_passes or stalled > self.n_strips + 2:
+                raise RuntimeError("particles could not be routed to their strips (%d left)" % left)
 
     def rebalance(self):
         """Re-cut the strips from the current per-row particle counts (read from the device cell tables) and

@@ -35,11 +35,11 @@ def small_fs():
 
 def particles(n, seed, clustered=False):
     rng = np.random.default_rng(seed)
-    lon = 205.0 + 1.2 * rng.random(n)
+    lon = 201.0 + 1.2 * rng.random(n)          # open water in the golden field (its land block starts at 204.67E)
     lat = 32.0 + 1.2 * rng.random(n)
     if clustered:                       # a dense blob: unbalanced rows, heavy cells next to a strip boundary
         k = n // 3
-        lon[:k] = 205.6 + 0.05 * rng.standard_normal(k)
+        lon[:k] = 201.6 + 0.05 * rng.standard_normal(k)
         lat[:k] = 32.55 + 0.05 * rng.standard_normal(k)
     sp = rng.integers(1, 4, n).astype(np.int8)
     return lon.astype(np.float32), lat.astype(np.float32), sp
@@ -85,7 +85,7 @@ def test_strips_on_one_device_equal_single_handle(G, clustered):
     cut = [slice(g * per, (g + 1) * per if g < G - 1 else n) for g in range(G)]
     ss = StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
                   [ids[c] for c in cut], n, R, *P, fs, seed=seed, local_strips=list(range(G)), slack=3.0,
-                  pairs_per_particle=40, grid_margin=0.25)
+                  pairs_per_particle=40 * G, grid_margin=0.25)     # a dense blob puts most pairs into one strip
     assert all(e % 2 == 0 for e in ss.edges[:-1]) and ss.edges[-1] == ss.grid.ncy
     sim = single(lon, lat, sp, ss.grid, fs, seed)
     total, moved = 0, 0
@@ -119,17 +119,28 @@ def test_strips_with_diffusion_and_rebalancing():
 
 
 def test_exchange_buffer_overflow_is_reported():
-    from lagrangian_microbes_b200._lib import LmError, LM_ENOSPC
+    from lagrangian_microbes_b200._lib import LmError, LM_ENOSPC, LM_ESTATE
     from lagrangian_microbes_b200.strips import LocalTransport, StripSet
     G, n = 2, 20000
     fs = small_fs()
     lon, lat, sp = particles(n, 0)
     ids = np.arange(n, dtype=np.int32)
     cut = [slice(g, n, G) for g in range(G)]
-    with pytest.raises(LmError) as ei:                      # half of each tile must migrate: 16 records are not enough
-        StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
-                 [ids[c] for c in cut], n, R, *P, fs, local_strips=list(range(G)), slack=3.0, send_cap=16)
-    assert ei.value.code == LM_ENOSPC
+    # 64-record messages: the initial routing (half of each tile) takes many passes but loses nobody ...
+    ss = StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
+                  [ids[c] for c in cut], n, R, *P, fs, local_strips=list(range(G)), slack=3.0, send_cap=64,
+                  pairs_per_particle=40)
+    got = np.sort(np.concatenate([p[0] for p in ss.local_state()]))
+    assert np.array_equal(got, ids)
+    # ... while a real step whose migrants do not fit must not pass silently
+    ss.edges = [0, ss.edges[1] + 8, ss.grid.ncy]           # move the boundary by 8 rows: > 64 particles change hands
+    for s in ss.strips:
+        s.rows = (ss.edges[s.index], ss.edges[s.index + 1])
+        s.engine.set_strip(s.rows[0], s.rows[1] - s.rows[0], s.index > 0, s.index < G - 1)
+    with pytest.raises(LmError) as ei:
+        ss.step(check=True)
+    assert ei.value.code == LM_ESTATE
+    ss.close()
     with pytest.raises(LmError) as ei:                      # the ghost row does not fit 8 records
         ss = StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
                       [ids[c] for c in cut], n, R, *P, fs, local_strips=list(range(G)), slack=3.0, ghost_cap=8)
