@@ -255,6 +255,11 @@ def main():
         print(json.dumps(line))
         return
 
+    # stdout carries exactly ONE JSON line: anything libraries print there (NCCL's version banner ...) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in the product path)"
@@ -274,9 +279,40 @@ def main():
     config.update(desc)
     log("[rank %d] setup: field + particles in %.1f s" % (rank, time.time() - t_setup))
 
+    ppp = 8 if args.workload != "config3" else 20           # pair-list capacity per microbe
+
+    class Sharded:
+        """N > 1: one latitude strip per rank (lagrangian_microbes_b200/strips.py), NCCL between neighbours."""
+
+        def __init__(self, stream_field):
+            from lagrangian_microbes_b200.strips import DistTransport, StripSet
+            ids = (rank * n_per_gpu + np.arange(n_per_gpu)).astype(np.int32)
+            self.ss = StripSet(DistTransport(), lon, lat, species, ids, n_per_gpu * world, RADIUS, *P_RPS, hfs,
+                               dt_seconds=DT, seed=0, emit_pairs=True, pairs_per_particle=ppp, slack=1.25,
+                               grid_margin=0.5, stream_field=stream_field)
+            self.engine = self.ss.strips[0].engine
+            self.regrid_every = 0
+            self.k = 0
+
+        def step(self, check=False, timing=False):
+            self.ss.step(check=check, timing=timing)
+
+        def stats(self):
+            return self.ss.stats()[0]
+
+        @property
+        def h2d_bytes_last_step(self):
+            return self.ss.streamer.h2d_bytes_last_step if self.ss.streamer is not None else 0
+
+        def record_to_host(self, *_):
+            self.k ^= 1
+            return self.ss.record_to_host(self.k)
+
     def new_sim(stream_field):
+        if world > 1:
+            return Sharded(stream_field)
         return FusedSimulation(lon, lat, species, RADIUS, *P_RPS, hfs, dt_seconds=DT, seed=0, emit_pairs=True,
-                               pair_capacity=int(max(1 << 20, (8 if args.workload != "config3" else 20) * n_per_gpu)),
+                               pair_capacity=int(max(1 << 20, ppp * n_per_gpu)),
                                regrid_every=0 if args.workload != "config2" else 16, grid_margin=0.5,
                                stream_field=stream_field)
 
@@ -309,6 +345,9 @@ def main():
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     st = sim.stats()
     rho = st.n_pairs / float(n_per_gpu)
+    if world > 1:
+        config["parallelism"] = "%d latitude strips (one per GPU), NCCL send/recv between neighbours: migration + " \
+                                "one-row halo + boundary species, strip edges %s" % (world, sim.ss.edges)
 
     # per-phase device times (3 extra steps with events between the phases)
     phase = np.zeros(4)
@@ -328,11 +367,11 @@ def main():
         for _ in range(spinup):
             sim2.step()
         rec = [(torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(), torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(),
-                torch.empty(n_per_gpu, dtype=torch.int8).pin_memory()) for _ in range(2)]
+                torch.empty(n_per_gpu, dtype=torch.int8).pin_memory()) if world == 1 else () for _ in range(2)]
         for k in range(args.warmup):
             sim2.step()
             sim2.record_to_host(*rec[k & 1])
-        sim2.engine.host_copies_sync()
+        (sim2.ss if world > 1 else sim2.engine).host_copies_sync()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tw0 = time.perf_counter()
@@ -342,13 +381,17 @@ def main():
             sim2.step()
             h2d += sim2.h2d_bytes_last_step
             sim2.record_to_host(*rec[k & 1])
-        sim2.engine.host_copies_sync()
+        (sim2.ss if world > 1 else sim2.engine).host_copies_sync()
         e1.record()
         barrier()
         tw1 = time.perf_counter()
         ms_e2e = max(e0.elapsed_time(e1), 1e3 * (tw1 - tw0))     # device events and the host clock around the copies
-        e2e = {"ms": ms_e2e, "h2d": h2d / args.steps, "d2h": 9 * n_per_gpu}
-        lon_chk = rec[(args.steps - 1) & 1][0].numpy()
+        # N = 1: lon, lat, species in particle-id order (9 B); strips: ids travel with the record (13 B)
+        e2e = {"ms": ms_e2e, "h2d": h2d / args.steps, "d2h": (9 if world == 1 else 13) * n_per_gpu}
+        if world == 1:
+            lon_chk = rec[(args.steps - 1) & 1][0].numpy()
+        else:
+            lon_chk = sim2.ss._record["host"][1][sim2.k][:sim2.engine.state_size()].numpy()
         assert np.isfinite(lon_chk).all() and lon_chk.min() > 100.0
         sim = sim2
 
@@ -405,7 +448,8 @@ def main():
                                 "sample": "2 steps of a %d-microbe sub-box at the workload's areal density (%.0f pairs/step)"
                                           % (res["n_sample"], res["pairs_per_step"]),
                                 "phases_s_per_step": res["phases_s_per_step"]}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -21,6 +21,58 @@ from .engine import Engine, make_grid
 from .particle_advecter import OutOfBoundsError, StageClock
 
 
+class FieldWindowStreamer:
+    """Velocity snapshots stay in pinned host memory; each step uploads the (2 or 3) time levels its four RK4
+    stages bracket into one of two device windows on a side stream, overlapped with the previous step's
+    kernels (velocity input path; the reference re-opens the year's NetCDF file per
+    ``time_step`` call instead: particle_advecter.py:160-183)."""
+
+    def __init__(self, fieldset, engines):
+        self.engines = list(engines)
+        dev = self.engines[0].device
+        self._u_host = torch.from_numpy(fieldset.u).pin_memory()
+        self._v_host = torch.from_numpy(fieldset.v).pin_memory()
+        _, Y, X = fieldset.u.shape
+        self._win_u = [torch.zeros((3, Y, X), dtype=torch.float32, device=dev) for _ in range(2)]
+        self._win_v = [torch.zeros((3, Y, X), dtype=torch.float32, device=dev) for _ in range(2)]
+        self._grid_lon = torch.from_numpy(fieldset.lon).to(dev)
+        self._grid_lat = torch.from_numpy(fieldset.lat).to(dev)
+        for e in self.engines:
+            e.set_field(self._win_u[0], self._win_v[0], self._grid_lon, self._grid_lat)
+        self._h2d_stream = torch.cuda.Stream(device=dev)
+        self._win_ready = [torch.cuda.Event() for _ in range(2)]
+        self._win_free = [torch.cuda.Event() for _ in range(2)]
+        for e in self._win_free:
+            e.record()
+        self._win_idx = 0
+        self.h2d_bytes_last_step = 0
+
+    def upload(self, st_times):
+        """Upload the time levels this step samples, point the engines at them and rebase ``st_times.ti``.
+        Returns the window index to hand to ``release`` once the step's kernels are queued."""
+        lo = min(st_times.ti[k] for k in range(4))
+        hi = max(st_times.ti[k] + (1 if st_times.interp[k] else 0) for k in range(4))
+        cnt = hi - lo + 1
+        assert cnt <= 3, "one RK4 step spans more than three velocity snapshots"
+        k = self._win_idx
+        self._win_idx ^= 1
+        with torch.cuda.stream(self._h2d_stream):
+            self._h2d_stream.wait_event(self._win_free[k])        # the step that last read window k is done
+            self._win_u[k][:cnt].copy_(self._u_host[lo:hi + 1], non_blocking=True)
+            self._win_v[k][:cnt].copy_(self._v_host[lo:hi + 1], non_blocking=True)
+            self._win_ready[k].record(self._h2d_stream)
+        torch.cuda.current_stream().wait_event(self._win_ready[k])
+        for e in self.engines:
+            e.update_field_data(self._win_u[k], self._win_v[k])
+        for j in range(4):
+            st_times.ti[j] -= lo
+        self.h2d_bytes_last_step = 2 * cnt * self._win_u[k][0].numel() * 4
+        return k
+
+    def release(self, k):
+        self._win_free[k].record()
+
+
 class FusedSimulation:
     def __init__(self, lons, lats, species, radius, pRS, pPR, pSP, fieldset, dt_seconds=3600.0, Kh=0.0, seed=0,
                  emit_pairs=True, pair_capacity=None, regrid_every=16, grid_margin=0.5, cells_per_particle=2.0,
@@ -55,24 +107,9 @@ class FusedSimulation:
         self.fieldset = fieldset
         self.stream_field = bool(stream_field) and fieldset is not None
         self.h2d_bytes_last_step = 0
+        self.streamer = None
         if fieldset is not None and self.stream_field:
-            # Velocity snapshots stay in pinned host memory; each step uploads the (2 or 3) time levels
-            # its four RK4 stages bracket into one of two device windows on a side stream, overlapped
-            # with the previous step's kernels (velocity input path).
-            self._u_host = torch.from_numpy(fieldset.u).pin_memory()
-            self._v_host = torch.from_numpy(fieldset.v).pin_memory()
-            _, Y, X = fieldset.u.shape
-            self._win_u = [torch.zeros((3, Y, X), dtype=torch.float32, device=dev) for _ in range(2)]
-            self._win_v = [torch.zeros((3, Y, X), dtype=torch.float32, device=dev) for _ in range(2)]
-            self._grid_lon = torch.from_numpy(fieldset.lon).to(dev)
-            self._grid_lat = torch.from_numpy(fieldset.lat).to(dev)
-            self.engine.set_field(self._win_u[0], self._win_v[0], self._grid_lon, self._grid_lat)
-            self._h2d_stream = torch.cuda.Stream(device=dev)
-            self._win_ready = [torch.cuda.Event() for _ in range(2)]
-            self._win_free = [torch.cuda.Event() for _ in range(2)]
-            for e in self._win_free:
-                e.record()
-            self._win_idx = 0
+            self.streamer = FieldWindowStreamer(fieldset, [self.engine])
             self.clock = StageClock(fieldset.time)
         elif fieldset is not None:
             self.engine.set_field(*fieldset.to_device(dev))
@@ -114,26 +151,6 @@ class FusedSimulation:
             self._fit_grid(x0, x1, y0, y1)
 
     # ---- stepping ----------------------------------------------------------------------------------
-    def _stream_window(self, st_times):
-        """Upload the time levels this step samples and point the engine at them."""
-        lo = min(st_times.ti[k] for k in range(4))
-        hi = max(st_times.ti[k] + (1 if st_times.interp[k] else 0) for k in range(4))
-        cnt = hi - lo + 1
-        assert cnt <= 3, "one RK4 step spans more than three velocity snapshots"
-        k = self._win_idx
-        self._win_idx ^= 1
-        with torch.cuda.stream(self._h2d_stream):
-            self._h2d_stream.wait_event(self._win_free[k])        # the step that last read window k is done
-            self._win_u[k][:cnt].copy_(self._u_host[lo:hi + 1], non_blocking=True)
-            self._win_v[k][:cnt].copy_(self._v_host[lo:hi + 1], non_blocking=True)
-            self._win_ready[k].record(self._h2d_stream)
-        torch.cuda.current_stream().wait_event(self._win_ready[k])
-        self.engine.update_field_data(self._win_u[k], self._win_v[k])
-        for j in range(4):
-            st_times.ti[j] -= lo
-        self.h2d_bytes_last_step = 2 * cnt * self._win_u[k][0].numel() * 4
-        return k
-
     def step(self, check=False, timing=False):
         flags = 0
         st_times = None
@@ -141,8 +158,9 @@ class FusedSimulation:
         if self.advect:
             flags |= _lib.LM_STEP_ADVECT
             st_times = self.clock.next_step(self.dt)
-            if self.stream_field:
-                win = self._stream_window(st_times)
+            if self.streamer is not None:
+                win = self.streamer.upload(st_times)
+                self.h2d_bytes_last_step = self.streamer.h2d_bytes_last_step
         if timing:
             flags |= _lib.LM_STEP_TIMING
         self.rps.step = self.iteration          # 0-based step index = InteractionSimulator's ``i``
@@ -158,7 +176,7 @@ class FusedSimulation:
             flags |= _lib.LM_STEP_STATS
         self.engine.step(flags, st_times, self.dt, self.diffuse_amp, self.radius, self.rps, self.pairs)
         if win is not None:
-            self._win_free[win].record()
+            self.streamer.release(win)
         if want_stats:
             st = self.engine.sync_stats()
             self.last_stats = st

@@ -188,7 +188,7 @@ class StripSet:
     def __init__(self, transport, lons, lats, species, ids, n_total, radius, pRS, pPR, pSP, fieldset, dt_seconds=3600.0,
                  Kh=0.0, seed=0, emit_pairs=True, pairs_per_particle=8, slack=1.3, send_cap=None, ghost_cap=None,
                  grid_margin=0.5, cells_per_particle=2.0, local_strips=None, device=None, interact=True, advect=True,
-                 rebalance_every=0):
+                 rebalance_every=0, stream_field=False):
         from .particle_advecter import StageClock
         self.transport = transport
         G = transport.n_strips
@@ -250,10 +250,15 @@ class StripSet:
                          max_pairs=pair_cap if self.interact else 0, device=device)
             eng.strip_alloc(self.send_cap, self.ghost_cap, g.ncx)
             eng.set_grid(g)
-            if fieldset is not None:
+            if fieldset is not None and not stream_field:
                 eng.set_field(*fieldset.to_device(eng.device))
             pairs = torch.empty((pair_cap, 2), dtype=torch.int32, device=eng.device) if self.emit_pairs else None
             self.strips.append(Strip(idx, eng, pairs))
+        self.streamer = None
+        if fieldset is not None and stream_field:
+            from .simulation import FieldWindowStreamer
+            self.streamer = FieldWindowStreamer(fieldset, [s.engine for s in self.strips])
+        self._record = None
         self._apply_edges()
         for s, lo, la, sp, i in zip(self.strips, lons, lats, species, ids):
             if lo.size > s.engine.max_particles:
@@ -337,9 +342,12 @@ class StripSet:
     def step(self, check=False, timing=False):
         flags = 0
         st_times = None
+        win = None
         if self.advect:
             flags |= _lib.LM_STEP_ADVECT
             st_times = self.clock.next_step(self.dt)
+            if self.streamer is not None:
+                win = self.streamer.upload(st_times)
         if timing:
             flags |= _lib.LM_STEP_TIMING
         self.rps.step = self.iteration
@@ -353,6 +361,8 @@ class StripSet:
         if check:
             flags |= _lib.LM_STEP_STATS
         self._staged(flags, st_times)
+        if win is not None:
+            self.streamer.release(win)
         out = None
         if check:
             out = self.stats()
@@ -389,6 +399,42 @@ class StripSet:
         """Per local strip: the (P, 2) global-id pairs of the last step (needs emit_pairs and a stats() sync)."""
         st = self.last_stats if self.last_stats is not None else self.stats()
         return [s.pairs[:x.n_pairs].cpu().numpy() for s, x in zip(self.strips, st)]
+
+    def record_to_host(self, slot):
+        """Asynchronous per-step record of the FIRST local strip into pinned host buffers: (ids, lon, lat,
+        species) of its owned particles in storage order -- what a per-strip output file holds, like the
+        reference's per-tile chunk pickles (particle_advecter.py:201-214).  Two slots alternate; returns the
+        number of particles recorded.  Call ``host_copies_sync()`` before reading the buffers."""
+        s = self.strips[0]
+        dev = s.engine.device
+        if self._record is None:
+            cap = s.engine.max_particles
+            mk = lambda dt: [torch.empty(cap, dtype=dt, device=dev) for _ in range(2)]
+            pin = lambda dt: [torch.empty(cap, dtype=dt).pin_memory() for _ in range(2)]
+            self._record = dict(stage=[mk(torch.int32), mk(torch.float32), mk(torch.float32), mk(torch.int8)],
+                                host=[pin(torch.int32), pin(torch.float32), pin(torch.float32), pin(torch.int8)],
+                                stream=torch.cuda.Stream(device=dev), copied=[torch.cuda.Event() for _ in range(2)])
+            for e in self._record["copied"]:
+                e.record()
+        R = self._record
+        n = s.engine.state_size()
+        lon, lat, sp, ids, _ = s.engine.state_view(rows=1)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(R["copied"][slot])                    # the staging slot was drained two records ago
+        for k, src in enumerate((ids, lon, lat, sp)):
+            R["stage"][k][slot][:n].copy_(src[:n], non_blocking=True)
+        staged = torch.cuda.Event()
+        staged.record(cur)
+        with torch.cuda.stream(R["stream"]):
+            R["stream"].wait_event(staged)
+            for k in range(4):
+                R["host"][k][slot][:n].copy_(R["stage"][k][slot][:n], non_blocking=True)
+            R["copied"][slot].record(R["stream"])
+        return n
+
+    def host_copies_sync(self):
+        if self._record is not None:
+            self._record["stream"].synchronize()
 
     def gather(self):
         """Global (lon, lat, species) in particle-id order on every process (the reference's per-step record,
