@@ -207,6 +207,11 @@ int lm_state_view(lm_handle h, float **lon, float **lat, int8_t **species, int32
 int lm_sync_stats(lm_handle h, lm_stats *out /* host */, void *stream);
 /* Zero the device counters (lm_step and the pair-search operators do this themselves). */
 int lm_reset_stats(lm_handle h, void *stream);
+/* Tuning knobs (defaults are right for production; tests use them to force a code path).
+ *   LM_OPT_RESOLVE  how the nine RPS phases are launched: 0 = auto, 1 = three row-fused launches (needs a grid
+ *                   whose rows are long; same result), 2 = one launch per phase. */
+#define LM_OPT_RESOLVE 1
+int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Number of kernels this library launched since the handle was created. */
 int64_t lm_launch_count(lm_handle h);
 /* Device time of the phases of the last lm_step run with LM_STEP_TIMING (synchronises on it):

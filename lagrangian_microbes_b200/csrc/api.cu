@@ -672,4 +672,16 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
 
 int64_t lm_launch_count(lm_handle h) { return h ? h->launches : 0; }
 
+int lm_set_option(lm_handle h, int32_t option, int64_t value)
+{
+    if (!h) return LM_EINVAL;
+    switch (option) {
+        case LM_OPT_RESOLVE:
+            if (value < 0 || value > 2) return LM_EINVAL;
+            h->resolve_mode = (int)value;
+            return LM_OK;
+        default: return LM_EINVAL;
+    }
+}
+
 }  // extern "C"

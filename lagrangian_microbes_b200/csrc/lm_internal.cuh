@@ -90,6 +90,7 @@ struct lm_handle_s {
     bool timed;
     int stage_idx;
     int64_t launches;
+    int resolve_mode;                    // LM_OPT_RESOLVE: 0 auto | 1 row-fused groups | 2 one launch per phase
     // ---- latitude-strip decomposition (lm_strip_alloc / lm_set_strip); all zero for a single GPU
     lm::Strip strip;
     bool has_south, has_north;

@@ -289,12 +289,12 @@ __device__ __forceinline__ uint32_t map_compose(uint32_t second, uint32_t first)
 }
 
 // Whole-warp resolution of one unit (all lanes call this with the same arguments).
-__device__ void resolve_unit_warp(const ResolveArgs &A, int aBeg, int aEnd)
+__device__ void resolve_unit_warp(const ResolveArgs &A, int d_idx, int aBeg, int aEnd)
 {
     const int lane = threadIdx.x & 31;
     for (int a = aBeg; a < aEnd; ++a) {
         unsigned int off, n;
-        hit_list(A.meta[a], A.d_idx, off, n);
+        hit_list(A.meta[a], d_idx, off, n);
         if (n == 0) continue;
         __syncwarp();                                  // species written by earlier rows are visible
         int sa = ((volatile int8_t *)A.sp)[a];
@@ -334,12 +334,14 @@ __device__ void resolve_unit_warp(const ResolveArgs &A, int aBeg, int aEnd)
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(256) resolve_phase_kernel(ResolveArgs A)
+// One unit = the pairs between the particles of `anchor` and those of `other` (or inside `anchor`), resolved in
+// (id_a, id_b) order.  Called by all 32 lanes of a warp (valid = this lane has a unit): light units are walked
+// by their lane, dense ones by the whole warp, one after the other.
+__device__ __forceinline__ void resolve_unit(const ResolveArgs &A, bool valid, int anchor, int other, int d_idx)
 {
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int anchor = 0, other = 0, aBeg = 0, aEnd = 0;
+    int aBeg = 0, aEnd = 0;
     bool heavy = false;
-    if (u < A.n_units && decode_unit(A, u, anchor, other)) {
+    if (valid) {
         aBeg = __ldg(A.cell_start + anchor);
         aEnd = __ldg(A.cell_start + anchor + 1);
         if (aEnd > aBeg) {
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(256) resolve_phase_kernel(ResolveArgs A)
         // one lane, one unit: rows in id order, each row's hits in id order
         for (int a = aBeg; a < aEnd; ++a) {
             unsigned int off, n;
-            hit_list(__ldg(A.meta + a), A.d_idx, off, n);
+            hit_list(__ldg(A.meta + a), d_idx, off, n);
             if (n == 0) continue;
             int sa = A.sp[a];
             const int sa0 = sa;
@@ -373,7 +375,53 @@ __global__ void __launch_bounds__(256) resolve_phase_kernel(ResolveArgs A)
     while (hm) {
         const int src = __ffs(hm) - 1;
         hm &= hm - 1;
-        resolve_unit_warp(A, __shfl_sync(0xffffffffu, aBeg, src), __shfl_sync(0xffffffffu, aEnd, src));
+        resolve_unit_warp(A, d_idx, __shfl_sync(0xffffffffu, aBeg, src), __shfl_sync(0xffffffffu, aEnd, src));
+    }
+}
+
+// One phase per launch, one lane per unit: the general path (any grid shape).
+__global__ void __launch_bounds__(256) resolve_phase_kernel(ResolveArgs A)
+{
+    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int anchor = 0, other = 0;
+    const bool valid = u < A.n_units && decode_unit(A, u, anchor, other);
+    resolve_unit(A, valid, anchor, other, A.d_idx);
+}
+
+// Three phases per launch for grids with many long rows.  The phases of one group couple cells of ONE row
+// (group 0: phases 0,1,2 = same cell, east even, east odd) or of ONE pair of rows (group 1: phases 3,4,5 =
+// NW, N, NE from an even anchor row; group 2: phases 6,7,8 from an odd one), so a CTA that owns the row
+// (pair) can run its three phases back to back with a block barrier in between: 3 launches instead of 9,
+// and every particle's meta / hit list is read once per group instead of once per phase.
+constexpr int ROW_THREADS = 1024;
+template <int GROUP>
+__global__ void __launch_bounds__(ROW_THREADS) resolve_rows_kernel(ResolveArgs A)
+{
+    const int ncx = A.ncx;
+    const int cy = (GROUP == 0) ? (int)blockIdx.x : 2 * (int)blockIdx.x + (GROUP - 1);
+    const int row = cy * ncx;
+#pragma unroll 1
+    for (int ph = 0; ph < 3; ++ph) {
+        const int n_units = (GROUP == 0 && ph > 0) ? (ncx - (ph - 1)) / 2 : ncx;
+        const int d_idx = (GROUP == 0) ? (ph > 0 ? 1 : 0) : 2 + ph;
+        for (int u0 = 0; u0 < n_units; u0 += blockDim.x) {     // block-uniform trip count
+            const int u = u0 + (int)threadIdx.x;
+            bool valid = u < n_units;
+            int anchor = 0, other = 0;
+            if (valid) {
+                if (GROUP == 0) {
+                    anchor = (ph == 0) ? row + u : row + 2 * u + (ph - 1);
+                    other = (ph == 0) ? anchor : anchor + 1;
+                } else {
+                    const int ox = u + ph - 1;
+                    valid = ox >= 0 && ox < ncx;
+                    anchor = row + u;
+                    other = row + ncx + ox;
+                }
+            }
+            resolve_unit(A, valid, anchor, other, d_idx);
+        }
+        __syncthreads();
     }
 }
 
@@ -430,8 +478,28 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
     R.sp = sp; R.cell_start = h->cell_start; R.meta = h->meta; R.hits = h->hits;
     R.cap_hits = (unsigned long long)h->max_pairs;
     R.ncx = h->grid.ncx; R.ncy = h->strip.rows_local;
+    R.mode = R.parity = R.dir = R.d_idx = 0; R.n_units = 0;
     const long long ncx = R.ncx, rows_owned = h->strip.rows_owned, rows_local = h->strip.rows_local;
-    for (int ph = first; ph <= last; ++ph) {
+    // row-fused path: whole groups of three phases, enough rows to fill the GPU, rows long enough for a CTA
+    const bool fused = h->resolve_mode == 1 ||
+                       (h->resolve_mode == 0 && rows_owned >= 2 * kNumSMs && ncx >= ROW_THREADS / 2);
+    int ph = first;
+    while (ph <= last) {
+        cudaError_t e;
+        if (fused && ph % 3 == 0 && ph + 2 <= last) {
+            const int group = ph / 3;
+            const int threads = (int)(ncx >= ROW_THREADS ? ROW_THREADS : ((ncx + 31) / 32) * 32);
+            const long long rows = group == 0 ? rows_owned : (rows_local - (group - 1)) / 2;
+            if (rows > 0) {
+                if (group == 0) resolve_rows_kernel<0><<<(unsigned)rows, threads, 0, s>>>(R);
+                else if (group == 1) resolve_rows_kernel<1><<<(unsigned)rows, threads, 0, s>>>(R);
+                else resolve_rows_kernel<2><<<(unsigned)rows, threads, 0, s>>>(R);
+                ++h->launches;
+                if ((e = cudaGetLastError()) != cudaSuccess) return e;
+            }
+            ph += 3;
+            continue;
+        }
         long long n_units;
         if (ph == 0) { R.mode = MODE_SAME; R.parity = 0; R.dir = 0; R.d_idx = 0; n_units = ncx * rows_owned; }
         else if (ph <= 2) {
@@ -441,12 +509,12 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
             R.mode = MODE_CROSS; R.parity = (ph - 3) / 3; R.dir = (ph - 3) % 3 - 1; R.d_idx = 3 + R.dir;
             n_units = ((rows_local - R.parity) / 2) * ncx;
         }
+        ++ph;
         if (n_units <= 0) continue;
         R.n_units = n_units;
         resolve_phase_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, s>>>(R);
         ++h->launches;
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     return cudaSuccess;
 }

@@ -264,6 +264,9 @@ class Engine:
         check(self.L.lm_phase_times(self.h, ms), "lm_phase_times")
         return list(ms)
 
+    def set_option(self, option, value):
+        check(self.L.lm_set_option(self.h, int(option), int(value)), "lm_set_option")
+
     def launch_count(self):
         return int(self.L.lm_launch_count(self.h))
 
