@@ -208,9 +208,9 @@ int lm_sync_stats(lm_handle h, lm_stats *out /* host */, void *stream);
 /* Zero the device counters (lm_step and the pair-search operators do this themselves). */
 int lm_reset_stats(lm_handle h, void *stream);
 /* Tuning knobs (defaults are right for production; tests use them to force a code path).
- *   LM_OPT_RESOLVE  how the nine RPS phases are launched: 0 = auto, 1 = three row-fused launches (needs a grid
- *                   whose rows are long; same result), 2 = one launch per phase. */
-#define LM_OPT_RESOLVE 1
+ *   LM_OPT_FIND_PATH  0 = auto; 1 = every warp of the pair search takes the two-pass path that is normally
+ *                   reserved for dense clusters (more than 64 candidate partners for one microbe). */
+#define LM_OPT_FIND_PATH 2
 int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Number of kernels this library launched since the handle was created. */
 int64_t lm_launch_count(lm_handle h);

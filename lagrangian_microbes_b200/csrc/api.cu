@@ -73,7 +73,7 @@ int lm_destroy(lm_handle h)
     cudaFree(h->keys); cudaFree(h->slots); cudaFree(h->cell_count); cudaFree(h->cell_start);
     cudaFree(h->cell_cursor); cudaFree(h->block_sums); cudaFree(h->ctr); cudaFree(h->head);
     cudaFree(h->pending_cnt);
-    cudaFree(h->hits); cudaFree(h->meta);
+    cudaFree(h->hits); cudaFree(h->rec); cudaFree(h->rec2);
     for (int k = 0; k < 2; ++k) { cudaFree(h->mig_send[k]); cudaFree(h->mig_recv[k]); }
     cudaFree(h->ghost_send); cudaFree(h->ghost_recv);
     cudaFree(h->gsp_send); cudaFree(h->gsp_recv); cudaFree(h->gret_send); cudaFree(h->gret_recv);
@@ -89,6 +89,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
 {
     if (!out || max_particles <= 0 || max_cells <= 0 || max_pairs < 0) return LM_EINVAL;
     if (max_particles >= (1ll << 31) - 64 || max_cells >= (1ll << 31) - 64) return LM_EINVAL;
+    if (max_pairs > 0 && max_particles >= (1ll << 29)) return LM_EINVAL;     // staged hits carry a 29-bit partner index
     *out = nullptr;
     LM_CUDA(cudaSetDevice(device));
     lm_handle h = new (std::nothrow) lm_handle_s();
@@ -110,7 +111,9 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     ok = ok && dev_alloc(&h->keys, max_particles) && dev_alloc(&h->slots, max_particles);
     ok = ok && dev_alloc(&h->cell_count, max_cells) && dev_alloc(&h->cell_start, max_cells + 1);
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
-    ok = ok && dev_alloc(&h->hits, max_pairs) && dev_alloc(&h->meta, max_particles);
+    if (max_pairs >= (1ll << 32) - 8) return (delete h, LM_EINVAL);          // 32-bit entry offsets
+    ok = ok && dev_alloc(&h->hits, max_pairs + 4);
+    if (max_pairs > 0) ok = ok && dev_alloc(&h->rec, 5 * max_cells) && dev_alloc(&h->rec2, 5 * (max_particles / 32 + 2));
     ok = ok && dev_alloc(&h->ctr, 1) && dev_alloc(&h->head, max_particles) && dev_alloc(&h->pending_cnt, 4);
     if (ok) ok = cudaMemset(h->cell_count, 0, (size_t)max_cells * sizeof(int32_t)) == cudaSuccess;
     if (ok) ok = cudaMemset(h->ctr, 0, sizeof(Counters)) == cudaSuccess;
@@ -676,9 +679,9 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
 {
     if (!h) return LM_EINVAL;
     switch (option) {
-        case LM_OPT_RESOLVE:
-            if (value < 0 || value > 2) return LM_EINVAL;
-            h->resolve_mode = (int)value;
+        case LM_OPT_FIND_PATH:
+            if (value < 0 || value > 1) return LM_EINVAL;
+            h->find_path = (int)value;
             return LM_OK;
         default: return LM_EINVAL;
     }

@@ -75,8 +75,10 @@ struct lm_handle_s {
     int64_t emit_cap;      // capacity of the pair buffer passed to the last call (-1: none)
     int64_t rps_cap;       // capacity of hits[] if the last call resolved RPS (-1: it did not)
     // pair search -> resolver hand-off
-    uint32_t *hits;        // [max_pairs] partner index | decision bits << 29, grouped per particle
-    int4 *meta;            // [max_particles] (offset into hits, 5 x 16-bit hit counts per direction)
+    uint32_t *hits;        // [max_pairs + 4] hand-off entries (layout: csrc/pairs.cu)
+    uint2 *rec;            // [5][max_cells] (first entry, count) of each cell's first segment, per direction
+    uint2 *rec2;           // [5][max_particles / 32 + 2] the same for a cell continued at the start of a chunk
+    int find_path;         // LM_OPT_FIND_PATH: 0 auto | 1 every warp takes the two-pass (dense cluster) path
     // explicit-order resolver workspace
     unsigned long long *head;   // [max_particles]
     int32_t *pending[2];        // [max_pairs] each
@@ -90,7 +92,6 @@ struct lm_handle_s {
     bool timed;
     int stage_idx;
     int64_t launches;
-    int resolve_mode;                    // LM_OPT_RESOLVE: 0 auto | 1 row-fused groups | 2 one launch per phase
     // ---- latitude-strip decomposition (lm_strip_alloc / lm_set_strip); all zero for a single GPU
     lm::Strip strip;
     bool has_south, has_north;

@@ -13,25 +13,38 @@
 //
 // Two stages:
 //
-//  find_pairs_kernel   one thread per particle a, half stencil (rest of its own cell, E, NW, N, NE):
-//      everything that does not depend on species is done here, once, densely -- distance tests,
-//      the per-pair Philox draw reduced to three decision bits (u < pRS, u < pPR, u < pSP, as exact
-//      integer compares of the 53-bit draw against ceil(p * 2^53)), the pair list (ids, i < j).
-//      Per particle it leaves meta[a] = (offset, hits per direction) and hits[offset + k] =
-//      b | decision_bits << 29 in (direction, b) order.
+//  find_pairs_kernel   one thread per particle a, ONE pass over its half stencil (rest of its own cell,
+//      E, NW, N, NE): hits are staged per lane in shared memory, then finished densely by the whole warp --
+//      everything that does not depend on species is done here, once: the per-pair Philox draw reduced to
+//      three decision bits (u < pRS, u < pPR, u < pSP, as exact integer compares of the 53-bit draw against
+//      ceil(p * 2^53)), the pair list (ids, i < j), and the hand-off to the resolver.
 //
-//  resolve_phase_kernel   the sequential part.  A *unit* is a cell (pairs inside it) or two
-//      adjacent cells; units of one *phase* touch disjoint particles:
+//      Hand-off layout, built for the resolver's access pattern.  A SEGMENT is the run of particles of one
+//      cell inside one 32-particle chunk (= one warp of this kernel); a cell has one segment, two if it
+//      straddles a chunk boundary (9 %), more only in dense clusters.  hits[] is allocated in blocks of one
+//      CTA (256 particles); inside a block the entries are DIRECTION-MAJOR (0 same cell, 1 E, 2 NW, 3 N, 4 NE),
+//      then by warp, segment, anchor, partner -- so the pairs of one resolver unit (cell x direction) are one
+//      contiguous stream in canonical (a, b) order, and a resolver phase, which consumes one direction,
+//      streams 1/5 of the array instead of dragging every sector through the L2.
+//          entry = b_rel (24 bits, index relative to the partner cell's start) | a_rel (5 bits, anchor index
+//                  inside the segment) << 24 | decision bits << 29
+//          rec[d][cell]   = (first entry, count) of the cell's FIRST segment in direction d
+//          rec2[d][chunk] = the same for the segment that continues a cell at the start of a chunk
+//      Both tables are read coalesced (consecutive lanes <-> consecutive cells).
+//
+//  resolve kernels   the sequential part.  A *unit* is a cell (pairs inside it) or two adjacent cells;
+//      units of one *phase* touch disjoint particles:
 //          phase 0        same cell
 //          phase 1,2      E neighbour, anchor cx even / odd
 //          phase 3,4,5    NW, N, NE neighbour, anchor cy even
 //          phase 6,7,8    NW, N, NE neighbour, anchor cy odd
-//      so each phase is one conflict-free launch, one lane walks a unit's hit lists in (id_a, id_b)
-//      order and applies interactions.py:13-40 with table look-ups: the reference's sequential
-//      in-place semantics under the canonical total order (phase, unit, id_a, id_b)
-//      (oracle/rps.py::cell_phase_order).  Units with more than HEAVY_TESTS candidate pairs (dense
-//      clusters) are resolved by the whole warp: a row's hits are independent except through the
-//      anchor particle's species, a 3-state value, so the row is a prefix scan over 3->3 maps.
+//      so each phase is conflict-free; a lane walks the entry streams of its units (eight per lane, back to
+//      back, as a small state machine so that lanes with short units do not wait for long ones) and applies
+//      interactions.py:13-40 with table look-ups: the reference's sequential in-place semantics under the
+//      canonical total order (phase, unit, id_a, id_b) (oracle/rps.py::cell_phase_order).  Units with more
+//      than HEAVY_TESTS candidate pairs (dense clusters) are resolved by the whole warp: the hits of one
+//      anchor are independent except through the anchor's species, a 3-state value, so a run of them is a
+//      prefix scan over 3->3 maps.
 #include "lm_internal.cuh"
 #include "philox.cuh"
 
@@ -39,9 +52,9 @@ namespace lm {
 
 constexpr int FIND_THREADS = 256;
 constexpr int FIND_WARPS = FIND_THREADS / 32;
-constexpr int STAGE = 512;               // staged hits per warp (dense Philox / coalesced stores)
-constexpr uint32_t HIT_MASK = (1u << 29) - 1u;
-constexpr int HEAVY_TESTS = 2048;        // candidate pairs above which a unit is resolved by the warp
+constexpr uint32_t B_REL_MASK = (1u << 24) - 1u;     // entry: b_rel | a_rel << 24 | decision bits << 29
+constexpr unsigned int HEAVY_ENTRIES = 160;          // entries of one segment x direction above which the warp resolves the unit together
+constexpr int CELL_BITS = 21;                        // particles per cell < 2^21 (packed per-direction hit counters)
 
 struct FindArgs {
     const float *__restrict__ lon;
@@ -51,14 +64,17 @@ struct FindArgs {
     lm_grid g;
     int row0, rows_owned, rows_local;    // strip geometry (single GPU: 0, ncy, ncy)
     int n;                               // anchors = owned particles (ghost-row particles are partners only)
+    int force_two_pass;                  // LM_OPT_FIND_PATH = 1 (tests)
     float r2_lo, r2_hi;
     double r2;
     uint32_t seed_lo, seed_hi, step_lo, step_hi;
     unsigned long long thr[3];           // ceil(p * 2^53) for pRS, pPR, pSP
     uint32_t *__restrict__ hits;
-    int4 *__restrict__ meta;
+    uint2 *__restrict__ rec;             // [5][rec_stride]
+    uint2 *__restrict__ rec2;            // [5][rec2_stride]
+    long long rec_stride, rec2_stride;
     int2 *__restrict__ pairs;
-    unsigned long long cap_hits, cap_pairs;
+    unsigned long long cap_words, cap_pairs;
     Counters *ctr;
 };
 
@@ -96,120 +112,228 @@ __device__ __forceinline__ uint32_t decision_bits(const FindArgs &A, int i, int 
     return (m < A.thr[0] ? 1u : 0u) | (m < A.thr[1] ? 2u : 0u) | (m < A.thr[2] ? 4u : 0u);
 }
 
+__device__ __forceinline__ unsigned int warp_incl_scan(unsigned int v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// bits [0, t) of a 64-bit mask
+__device__ __forceinline__ unsigned long long bits_below(int t)
+{
+    return t <= 0 ? 0ull : (t >= 64 ? ~0ull : ((1ull << t) - 1ull));
+}
+
+constexpr int FILL_CAP = 1024;       // hits of one warp that the dense finishing stage can take
+constexpr int OWN_WORDS = 12;        // per lane, for the finishing stage: rel[5], base0, sE, begNW, sN, sNE, beg0, n1
+
 template <bool DO_RPS, bool EMIT>
 __global__ void __launch_bounds__(FIND_THREADS) find_pairs_kernel(FindArgs A)
 {
-    __shared__ uint32_t s_b[FIND_WARPS][STAGE];
-    __shared__ uint8_t s_owner[FIND_WARPS][STAGE];
-    __shared__ unsigned int s_wtot[FIND_WARPS];
+    __shared__ uint16_t s_fill_all[FIND_WARPS][FILL_CAP];      // compact hit e of the warp -> owner lane | candidate index << 5
+    __shared__ uint32_t s_own_all[FIND_WARPS][OWN_WORDS][32];
+    __shared__ unsigned int s_wtot[FIND_WARPS][5];             // hits of warp w in direction d
+    __shared__ unsigned int s_dbase[FIND_WARPS][5];            // first slot of (warp, direction) inside the CTA's block
     __shared__ unsigned long long s_base;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int a = blockIdx.x * FIND_THREADS + threadIdx.x;
     const bool valid = a < A.n;
+    uint16_t *s_fill = s_fill_all[warp];
+    uint32_t (*s_own)[32] = s_own_all[warp];
 
     float xa = 0.f, ya = 0.f;
-    int my_id = 0;
-    int r1_beg = 0, r1_end = 0, r2_beg = 0, r2_end = 0, sE = 0, sN = 0, sNE = 0;
+    int my_id = 0, c = -1 - lane;        // invalid lanes get distinct negative "cells"
+    // candidate ranges per direction: same cell [beg0, sE), E [sE, endE), NW [begNW, sN), N [sN, sNE), NE [sNE, endNE)
+    int beg0 = 0, sE = 0, endE = 0, begNW = 0, sN = 0, sNE = 0, endNE = 0, base0 = 0;
     if (valid) {
         xa = __ldg(A.lon + a); ya = __ldg(A.lat + a);
         my_id = __ldg(A.id + a);
         const int ncx = A.g.ncx, ncy = A.rows_local;
         const int cx = cell_coord2(xa, A.g.x0, A.g.inv_h, ncx);
         const int cy = max(0, min(cell_coord2(ya, A.g.y0, A.g.inv_h, A.g.ncy) - A.row0, A.rows_owned - 1));   // == bin.cu
-        const int c = cy * ncx + cx;
+        c = cy * ncx + cx;
         const bool e_ok = cx + 1 < ncx;
+        base0 = __ldg(A.cell_start + c);
         sE = __ldg(A.cell_start + c + 1);
-        r1_beg = a + 1;
-        r1_end = e_ok ? __ldg(A.cell_start + c + 2) : sE;
+        beg0 = a + 1;
+        endE = e_ok ? __ldg(A.cell_start + c + 2) : sE;
+        begNW = sN = sNE = endNE = endE;                 // no row to the north: empty ranges that keep the starts monotone
         if (cy + 1 < ncy) {
             const int up = c + ncx;
             sN = __ldg(A.cell_start + up);
             sNE = __ldg(A.cell_start + up + 1);
-            r2_beg = (cx > 0) ? __ldg(A.cell_start + up - 1) : sN;
-            r2_end = e_ok ? __ldg(A.cell_start + up + 2) : sNE;
+            begNW = (cx > 0) ? __ldg(A.cell_start + up - 1) : sN;
+            endNE = e_ok ? __ldg(A.cell_start + up + 2) : sNE;
         }
-        if (r1_end - r1_beg > 65535 || r2_end - r2_beg > 65535) {     // 16-bit per-direction counts
+        constexpr int CELL_MAX = (1 << CELL_BITS) - 1;
+        if (sE - base0 > CELL_MAX || endE - sE > CELL_MAX || sN - begNW > CELL_MAX || sNE - sN > CELL_MAX ||
+            endNE - sNE > CELL_MAX) {                                          // packed counters / relative partner index
             atomicAdd(&A.ctr->n_overflow, 1ull);
-            r1_end = min(r1_end, r1_beg + 65535);
-            r2_end = min(r2_end, r2_beg + 65535);
+            beg0 = sE = endE = begNW = sN = sNE = endNE = 0;
         }
     }
 
-    // ---- pass 1: count hits per direction (S, E | NW, N, NE), 16 bits each
-    unsigned long long cnt03 = 0;     // directions 0..3
-    unsigned int cnt4 = 0;
-    for (int b = r1_beg; b < r1_end; ++b)
-        if (within(A, xa, ya, b)) cnt03 += (b >= sE) ? (1ull << 16) : 1ull;
-    for (int b = r2_beg; b < r2_end; ++b)
-        if (within(A, xa, ya, b)) {
-            if (b >= sNE) ++cnt4;
-            else cnt03 += (b >= sN) ? (1ull << 48) : (1ull << 32);
+    // ---- the candidates of a lane: the concatenation of two index ranges (same row: rest of its cell + E;
+    // next row: NW, N, NE), i = 0 .. ntot-1.  ONE loop, so a warp iterates max-of-sums, not sum-of-maxes, of
+    // its lanes' candidate counts; hits are recorded as bits of a 64-bit mask -- nothing else happens in the
+    // loop.  Warps with a lane of more than 64 candidates (dense clusters) count per direction instead and
+    // regenerate the hits in a second pass.
+    const int n1 = endE - beg0, ntot = n1 + (endNE - begNW);
+    const int t1 = sE - beg0, t3 = n1 + (sN - begNW), t4 = n1 + (sNE - begNW);     // first candidate of E | N | NE (NW: n1)
+    const bool warp_big = __any_sync(0xffffffffu, ntot > 64) || A.force_two_pass;
+    unsigned long long mask = 0;
+    unsigned int cnt[5], tot;
+    if (!warp_big) {
+        for (int i = 0; i < ntot; ++i) {
+            const int b = (i < n1) ? beg0 + i : begNW + (i - n1);
+            if (within(A, xa, ya, b)) mask |= 1ull << i;
         }
-    const unsigned int c0 = (unsigned int)(cnt03 & 0xffff), c1 = (unsigned int)((cnt03 >> 16) & 0xffff);
-    const unsigned int c2 = (unsigned int)((cnt03 >> 32) & 0xffff), c3 = (unsigned int)(cnt03 >> 48);
-    const unsigned int tot = c0 + c1 + c2 + c3 + cnt4;
+        const unsigned int p1 = __popcll(mask & bits_below(t1)), p2 = __popcll(mask & bits_below(n1));
+        const unsigned int p3 = __popcll(mask & bits_below(t3)), p4 = __popcll(mask & bits_below(t4));
+        tot = __popcll(mask);
+        cnt[0] = p1; cnt[1] = p2 - p1; cnt[2] = p3 - p2; cnt[3] = p4 - p3; cnt[4] = tot - p4;
+    } else {
+        unsigned long long acc0 = 0, acc1 = 0;                 // hit counters, CELL_BITS each: d0 d1 d2 | d3 d4
+        for (int i = 0; i < ntot; ++i) {
+            const int b = (i < n1) ? beg0 + i : begNW + (i - n1);
+            if (within(A, xa, ya, b)) {
+                const int d = (i >= t1) + (i >= n1) + (i >= t3) + (i >= t4);
+                if (d < 3) acc0 += 1ull << (CELL_BITS * d); else acc1 += 1ull << (CELL_BITS * (d - 3));
+            }
+        }
+        constexpr unsigned int CM = (1u << CELL_BITS) - 1u;
+        cnt[0] = (unsigned int)acc0 & CM; cnt[1] = (unsigned int)(acc0 >> CELL_BITS) & CM;
+        cnt[2] = (unsigned int)(acc0 >> (2 * CELL_BITS)) & CM;
+        cnt[3] = (unsigned int)acc1 & CM; cnt[4] = (unsigned int)(acc1 >> CELL_BITS) & CM;
+        tot = cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4];
+    }
 
-    // ---- allocate: exclusive scan over the CTA, one atomic per CTA
-    unsigned int inc = tot;
+    // ---- layout: segments = runs of equal cell among the lanes; one block of hits[] per CTA, direction-major
+    const int c_prev = __shfl_up_sync(0xffffffffu, c, 1);
+    const bool head = valid && (lane == 0 || c != c_prev);
+    const unsigned int heads = __ballot_sync(0xffffffffu, head);
+    const unsigned int valid_mask = __ballot_sync(0xffffffffu, valid);
+    unsigned int incl[5], total[5];
+    unsigned int wpairs = 0;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
+    for (int d = 0; d < 5; ++d) {
+        incl[d] = warp_incl_scan(cnt[d], lane);
+        total[d] = __shfl_sync(0xffffffffu, incl[d], 31);
+        wpairs += total[d];
     }
-    const unsigned int wtot = __shfl_sync(0xffffffffu, inc, 31);
-    if (lane == 31) s_wtot[warp] = wtot;
+    if (lane < 5) s_wtot[warp][lane] = lane == 0 ? total[0] : (lane == 1 ? total[1] : (lane == 2 ? total[2] : (lane == 3 ? total[3] : total[4])));
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int btot = 0;
+        unsigned int run = 0;
 #pragma unroll
-        for (int w = 0; w < FIND_WARPS; ++w) btot += s_wtot[w];
-        s_base = btot ? atomicAdd(&A.ctr->n_pairs, (unsigned long long)btot) : 0ull;
+        for (int d = 0; d < 5; ++d)
+#pragma unroll
+            for (int w = 0; w < FIND_WARPS; ++w) { s_dbase[w][d] = run; run += s_wtot[w][d]; }
+        s_base = run ? atomicAdd(&A.ctr->n_pairs, (unsigned long long)run) : 0ull;     // one atomic per CTA
     }
     __syncthreads();
-    unsigned long long wbase = s_base;
-    for (int w = 0; w < warp; ++w) wbase += s_wtot[w];
-    const unsigned int off = inc - tot;                    // within the warp
-    if (DO_RPS && valid)
-        A.meta[a] = make_int4((int)(unsigned int)(wbase + off), (int)(c0 | (c1 << 16)), (int)(c2 | (c3 << 16)), (int)cnt4);
-    if (wtot == 0) return;                                 // warp-uniform
     if (!DO_RPS && !EMIT) return;
+    if (valid_mask == 0u || wpairs == 0) {                                  // warp-uniform
+        // segments without pairs still need their (empty) records
+        if (DO_RPS && head) {
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                if (a == base0) A.rec[d * A.rec_stride + c] = make_uint2(0u, 0u);
+                else A.rec2[d * A.rec2_stride + (a >> 5)] = make_uint2(0u, 0u);
+            }
+        }
+        return;
+    }
+    const unsigned long long cta_base = s_base;
 
-    if (wtot <= (unsigned int)STAGE) {
-        // ---- pass 2 (staged): regenerate the hits into shared memory, then finish them densely
-        unsigned int k = off;
-        for (int b = r1_beg; b < r1_end; ++b)
-            if (within(A, xa, ya, b)) { s_b[warp][k] = (uint32_t)b; s_owner[warp][k] = (uint8_t)lane; ++k; }
-        for (int b = r2_beg; b < r2_end; ++b)
-            if (within(A, xa, ya, b)) { s_b[warp][k] = (uint32_t)b; s_owner[warp][k] = (uint8_t)lane; ++k; }
+    const unsigned int incl_tot = incl[0] + incl[1] + incl[2] + incl[3] + incl[4];
+    const unsigned int excl_tot = incl_tot - tot;
+    int H = 0;                                                               // head lane of my segment
+    unsigned long long rel[5];                                               // hit k of this lane, of direction d, lands at rel[d] + k
+    {
+        const unsigned int below = heads & (0xffffffffu >> (31 - lane));     // heads at or below my lane
+        H = below ? 31 - __clz(below) : 0;
+        const unsigned int above = (lane == 31) ? 0u : (heads & (0xffffffffu << (lane + 1)));
+        const int Hn = above ? __ffs(above) - 1 : 32;                        // head lane of the next segment
+        unsigned int start_d = 0;
+#pragma unroll
+        for (int d = 0; d < 5; ++d) {
+            const unsigned int excl = incl[d] - cnt[d];
+            const unsigned long long first = cta_base + s_dbase[warp][d] + excl;   // my first hit of direction d
+            rel[d] = first - start_d;
+            start_d += cnt[d];
+            if (DO_RPS) {
+                const unsigned int pN_s = __shfl_sync(0xffffffffu, excl, Hn & 31);
+                const unsigned int T = ((Hn < 32) ? pN_s : total[d]) - excl;    // for a head lane: the segment's count
+                if (head) {
+                    const uint2 r = make_uint2((uint32_t)first, T);
+                    if (a == base0) A.rec[d * A.rec_stride + c] = r;              // the cell's first segment
+                    else A.rec2[d * A.rec2_stride + (a >> 5)] = r;              // a cell continued from the previous chunk
+                }
+            }
+        }
+    }
+
+    if (!warp_big && wpairs <= (unsigned int)FILL_CAP) {
+        // ---- finish densely: lanes <-> hits of the whole warp (id look-up, Philox, hand-off entry, pair)
+#pragma unroll
+        for (int d = 0; d < 5; ++d) s_own[d][lane] = (uint32_t)(rel[d] - cta_base);  // relative to the CTA's block (may wrap: mod 2^32)
+        s_own[5][lane] = (uint32_t)base0; s_own[6][lane] = (uint32_t)sE; s_own[7][lane] = (uint32_t)begNW;
+        s_own[8][lane] = (uint32_t)sN; s_own[9][lane] = (uint32_t)sNE; s_own[10][lane] = (uint32_t)beg0;
+        s_own[11][lane] = (uint32_t)n1;
+        {
+            unsigned int kk = excl_tot;
+            for (unsigned long long m = mask; m; m &= m - 1) s_fill[kk++] = (uint16_t)(lane | ((__ffsll((long long)m) - 1) << 5));
+        }
         __syncwarp();
-        for (unsigned int e0 = 0; e0 < wtot; e0 += 32) {
+        for (unsigned int e0 = 0; e0 < wpairs; e0 += 32) {
             const unsigned int e = e0 + lane;
-            const bool act = e < wtot;
-            const uint32_t b = act ? s_b[warp][e] : 0u;
-            const int owner = act ? (int)s_owner[warp][e] : 0;
+            const bool act = e < wpairs;
+            const unsigned int f = act ? s_fill[e] : 0u;
+            const int owner = (int)(f & 31u), i = (int)(f >> 5);
             const int ia = __shfl_sync(0xffffffffu, my_id, owner);
+            const int oH = __shfl_sync(0xffffffffu, H, owner);
+            const unsigned int oex = __shfl_sync(0xffffffffu, excl_tot, owner);
             if (act) {
+                const int o_n1 = (int)s_own[11][owner];
+                const int b = (i < o_n1) ? (int)s_own[10][owner] + i : (int)s_own[7][owner] + (i - o_n1);
                 const int ib = __ldg(A.id + b);
-                const int i = min(ia, ib), j = max(ia, ib);
-                const unsigned long long g = wbase + e;
-                if (DO_RPS && g < A.cap_hits) A.hits[g] = b | (decision_bits(A, i, j) << 29);
-                if (EMIT && g < A.cap_pairs) A.pairs[g] = make_int2(i, j);
+                const int lo = min(ia, ib), hi = max(ia, ib);
+                // direction from the partner's index: the cell starts are non-decreasing (empty ranges collapse)
+                const int oE = (int)s_own[6][owner], oNW = (int)s_own[7][owner], oN = (int)s_own[8][owner], oNE = (int)s_own[9][owner];
+                const int d = (b >= oE) + (b >= oNW) + (b >= oN) + (b >= oNE);
+                const unsigned long long dst = cta_base + (uint32_t)(s_own[d][owner] + (e - oex));
+                if (DO_RPS && dst < A.cap_words) {
+                    const int bbase = d == 0 ? (int)s_own[5][owner] : (d == 1 ? oE : (d == 2 ? oNW : (d == 3 ? oN : oNE)));
+                    A.hits[dst] = (uint32_t)(b - bbase) | ((uint32_t)(owner - oH) << 24) | (decision_bits(A, lo, hi) << 29);
+                }
+                if (EMIT && dst < A.cap_pairs) A.pairs[dst] = make_int2(lo, hi);
             }
         }
     } else {
-        // ---- pass 2 (direct): a dense neighbourhood; every lane has many hits, finish them in place
-        unsigned long long g = wbase + off;
-        for (int pass = 0; pass < 2; ++pass) {
-            const int beg = pass ? r2_beg : r1_beg, end = pass ? r2_end : r1_end;
-            for (int b = beg; b < end; ++b)
-                if (within(A, xa, ya, b)) {
-                    const int ib = __ldg(A.id + b);
-                    const int i = min(my_id, ib), j = max(my_id, ib);
-                    if (DO_RPS && g < A.cap_hits) A.hits[g] = (uint32_t)b | (decision_bits(A, i, j) << 29);
-                    if (EMIT && g < A.cap_pairs) A.pairs[g] = make_int2(i, j);
-                    ++g;
+        // ---- a dense neighbourhood: every lane has many hits, regenerate them and finish them in place
+        const int base[5] = {base0, sE, begNW, sN, sNE};
+        unsigned int kk = 0;
+        for (int i = 0; i < ntot; ++i) {
+            const int b = (i < n1) ? beg0 + i : begNW + (i - n1);
+            if (within(A, xa, ya, b)) {
+                const int d = (i >= t1) + (i >= n1) + (i >= t3) + (i >= t4);
+                const int ib = __ldg(A.id + b);
+                const int lo = min(my_id, ib), hi = max(my_id, ib);
+                const unsigned long long r_d = d == 0 ? rel[0] : (d == 1 ? rel[1] : (d == 2 ? rel[2] : (d == 3 ? rel[3] : rel[4])));
+                const unsigned long long dst = r_d + kk;
+                if (DO_RPS && dst < A.cap_words) {
+                    const int b_d = d == 0 ? base[0] : (d == 1 ? base[1] : (d == 2 ? base[2] : (d == 3 ? base[3] : base[4])));
+                    A.hits[dst] = (uint32_t)(b - b_d) | ((uint32_t)(lane - H) << 24) | (decision_bits(A, lo, hi) << 29);
                 }
+                if (EMIT && dst < A.cap_pairs) A.pairs[dst] = make_int2(lo, hi);
+                ++kk;
+            }
         }
     }
 }
@@ -217,54 +341,22 @@ __global__ void __launch_bounds__(FIND_THREADS) find_pairs_kernel(FindArgs A)
 // ---------------------------------------------------------------------------------------------------
 enum UnitMode { MODE_SAME = 1, MODE_EAST = 2, MODE_CROSS = 3 };
 
+constexpr int RES_THREADS = 128;
+constexpr int UNITS_PER_LANE = 8;                          // a warp streams 256 consecutive units of one row
+
 struct ResolveArgs {
     int8_t *sp;
     const int32_t *__restrict__ cell_start;
-    const int4 *__restrict__ meta;
     const uint32_t *__restrict__ hits;
-    unsigned long long cap_hits;
-    int ncx, ncy;
-    long long n_units;
+    const uint2 *__restrict__ rec;       // + d * rec_stride already applied
+    const uint2 *__restrict__ rec2;      // + d * rec2_stride already applied
+    const Counters *ctr;
+    unsigned long long cap_words;
+    int ncx;
+    int units_per_row, warps_per_row;
+    long long n_warps;
     int mode, parity, dir;   // dir in {-1,0,+1} for MODE_CROSS
-    int d_idx;               // which of the five per-particle hit lists this phase consumes
 };
-
-__device__ __forceinline__ bool decode_unit(const ResolveArgs &A, long long u, int &anchor, int &other)
-{
-    const int ncx = A.ncx;
-    if (A.mode == MODE_SAME) {
-        anchor = other = (int)u;
-    } else if (A.mode == MODE_EAST) {
-        const int half = (ncx - A.parity) / 2;          // anchors per row with cx % 2 == parity, cx + 1 < ncx
-        const int cy = (int)(u / half), i = (int)(u - (long long)cy * half);
-        anchor = cy * ncx + 2 * i + A.parity;
-        other = anchor + 1;
-    } else {
-        const int ry = (int)(u / ncx), cx = (int)(u - (long long)ry * ncx);
-        const int cy = 2 * ry + A.parity;                // cy + 1 < ncy by construction of n_units
-        const int ox = cx + A.dir;
-        if (ox < 0 || ox >= ncx) return false;
-        anchor = cy * ncx + cx;
-        other = anchor + ncx + A.dir;
-    }
-    return true;
-}
-
-// offset and length of particle a's hit list for direction d
-__device__ __forceinline__ void hit_list(const int4 m, int d, unsigned int &off, unsigned int &n)
-{
-    const unsigned int c0 = (unsigned int)m.y & 0xffffu, c1 = (unsigned int)m.y >> 16;
-    const unsigned int c2 = (unsigned int)m.z & 0xffffu, c3 = (unsigned int)m.z >> 16;
-    const unsigned int c4 = (unsigned int)m.w;
-    off = (unsigned int)m.x;
-    switch (d) {
-        case 0: n = c0; break;
-        case 1: off += c0; n = c1; break;
-        case 2: off += c0 + c1; n = c2; break;
-        case 3: off += c0 + c1 + c2; n = c3; break;
-        default: off += c0 + c1 + c2 + c3; n = c4; break;
-    }
-}
 
 // interactions.py:13-40 for species s1 != s2, both in {1,2,3}: the species both end up with.
 // The forward winner (rock beats scissors, paper beats rock, scissors beats paper) wins iff its
@@ -288,141 +380,185 @@ __device__ __forceinline__ uint32_t map_compose(uint32_t second, uint32_t first)
            (map_apply(second, (int)map_apply(first, 3)) << 4);
 }
 
-// Whole-warp resolution of one unit (all lanes call this with the same arguments).
-__device__ void resolve_unit_warp(const ResolveArgs &A, int d_idx, int aBeg, int aEnd)
+// Whole-warp resolution of one unit (all lanes call this with the same arguments): its entry streams, segment
+// after segment, in chunks of 32 entries; inside a chunk, one run of equal anchor after the other.
+__device__ void resolve_unit_warp(const ResolveArgs &A, int cell, int cs0, int cs1, int oBeg)
 {
     const int lane = threadIdx.x & 31;
-    for (int a = aBeg; a < aEnd; ++a) {
-        unsigned int off, n;
-        hit_list(A.meta[a], d_idx, off, n);
-        if (n == 0) continue;
-        __syncwarp();                                  // species written by earlier rows are visible
-        int sa = ((volatile int8_t *)A.sp)[a];
-        if (!is_rps(sa)) continue;                     // winner = None for every pair of this row
-        const int sa0 = sa;
-        for (unsigned int k0 = 0; k0 < n; k0 += 32) {
+    int cur_a = -1, sa = 0, sa0 = 0;
+    __syncwarp();
+    int a0 = cs0;
+    uint2 R = __ldg(A.rec + cell);
+    while (true) {
+        const uint32_t *ent = A.hits + R.x;
+        for (unsigned int k0 = 0; k0 < R.y; k0 += 32) {
             const unsigned int k = k0 + lane;
-            const bool act = k < n && (unsigned long long)off + k < A.cap_hits;
-            uint32_t M = MAP_ID, dec = 0;
-            int b = 0, sb = 0;
-            if (act) {
-                const uint32_t h = A.hits[off + k];
-                b = (int)(h & HIT_MASK); dec = h >> 29;
-                sb = ((volatile int8_t *)A.sp)[b];
-                if (is_rps(sb)) {
-                    M = 0;
-#pragma unroll
-                    for (int s = 1; s <= 3; ++s) M |= (uint32_t)((s == sb) ? s : rps_apply(s, sb, dec)) << (2 * (s - 1));
+            const bool act = k < R.y;
+            const uint32_t en = act ? __ldg(ent + k) : 0u;
+            const int ar = (int)((en >> 24) & 31u);
+            unsigned int todo = __ballot_sync(0xffffffffu, act);
+            while (todo) {
+                const int lead = __ffs(todo) - 1;
+                const int ar0 = __shfl_sync(0xffffffffu, ar, lead);
+                const unsigned int m = __ballot_sync(0xffffffffu, act && ar == ar0) & todo;   // entries are sorted by anchor
+                todo &= ~m;
+                const int a = a0 + ar0;
+                if (a != cur_a) {
+                    if (cur_a >= 0 && sa != sa0 && lane == 0) A.sp[cur_a] = (int8_t)sa;
+                    __syncwarp();
+                    cur_a = a;
+                    sa = sa0 = ((volatile int8_t *)A.sp)[a];
                 }
-            }
-            uint32_t P = M;                            // inclusive scan of maps in lane (= id_b) order
+                if (!is_rps(sa)) continue;                     // winner = None for every pair of this anchor
+                const bool mine = (m >> lane) & 1u;
+                uint32_t M = MAP_ID, dec = 0;
+                int b = 0, sb = 0;
+                if (mine) {
+                    b = oBeg + (int)(en & B_REL_MASK); dec = en >> 29;
+                    sb = ((volatile int8_t *)A.sp)[b];
+                    if (is_rps(sb)) {
+                        M = 0;
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, P, d);
-                if (lane >= d) P = map_compose(P, t);
+                        for (int s = 1; s <= 3; ++s) M |= (uint32_t)((s == sb) ? s : rps_apply(s, sb, dec)) << (2 * (s - 1));
+                    }
+                }
+                uint32_t P = M;                                // inclusive scan of maps in lane (= id_b) order
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, P, dd);
+                    if (lane >= dd) P = map_compose(P, t);
+                }
+                uint32_t E = __shfl_up_sync(0xffffffffu, P, 1);
+                if (lane == 0) E = MAP_ID;
+                if (mine && is_rps(sb)) {
+                    const int s_before = (int)map_apply(E, sa);
+                    if (s_before != sb) A.sp[b] = (int8_t)rps_apply(s_before, sb, dec);
+                }
+                sa = (int)map_apply(__shfl_sync(0xffffffffu, P, 31), sa);
+                __syncwarp();                                  // partner species written above are visible to later runs
             }
-            uint32_t E = __shfl_up_sync(0xffffffffu, P, 1);
-            if (lane == 0) E = MAP_ID;
-            if (act && is_rps(sb)) {
-                const int s_before = (int)map_apply(E, sa);
-                if (s_before != sb) A.sp[b] = (int8_t)rps_apply(s_before, sb, dec);
-            }
-            sa = (int)map_apply(__shfl_sync(0xffffffffu, P, 31), sa);
         }
-        if (lane == 0 && sa != sa0) A.sp[a] = (int8_t)sa;
+        a0 = (a0 | 31) + 1;                                    // the cell continues in the next 32-particle chunk?
+        if (a0 >= cs1) break;
+        R = __ldg(A.rec2 + (a0 >> 5));
     }
+    if (cur_a >= 0 && sa != sa0 && lane == 0) A.sp[cur_a] = (int8_t)sa;
     __syncwarp();
 }
 
-// One unit = the pairs between the particles of `anchor` and those of `other` (or inside `anchor`), resolved in
-// (id_a, id_b) order.  Called by all 32 lanes of a warp (valid = this lane has a unit): light units are walked
-// by their lane, dense ones by the whole warp, one after the other.
-__device__ __forceinline__ void resolve_unit(const ResolveArgs &A, bool valid, int anchor, int other, int d_idx)
+// One phase.  A warp takes 32 * UNITS_PER_LANE consecutive units of one cell row, lane l the units l, l + 32, ...
+// Pair counts per unit are heavy-tailed (same-cell units: ~m^2/2 for m microbes in the cell) and most units
+// are short, so "one lane walks one unit" leaves the warp waiting for its longest unit with a handful of lanes
+// active.  Instead, in two warp-uniform stages:
+//   A  every lane looks at its units (loads batched four units at a time) and pushes one descriptor per
+//      non-empty (segment, direction) entry stream -- (first entry, count, first anchor, partner cell start)
+//      -- onto its private list in shared memory; dense clusters are resolved right away by the whole warp;
+//   B  every lane walks the concatenation of its entry streams, one pair per iteration: all lanes execute
+//      the same instruction stream until their lists run out, and a lane's work is the SUM over its units.
+constexpr int DCAP = 10;             // descriptors per lane: 8 units + continuation segments (more: warp path)
+__global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs A)
 {
-    int aBeg = 0, aEnd = 0;
-    bool heavy = false;
-    if (valid) {
-        aBeg = __ldg(A.cell_start + anchor);
-        aEnd = __ldg(A.cell_start + anchor + 1);
-        if (aEnd > aBeg) {
-            const int nb = (anchor == other) ? (aEnd - aBeg) : (__ldg(A.cell_start + other + 1) - __ldg(A.cell_start + other));
-            if (nb == 0 || (anchor == other && nb < 2)) aEnd = aBeg;
-            else heavy = (long long)(aEnd - aBeg) * nb > HEAVY_TESTS;
-        }
-    }
-    if (!heavy) {
-        // one lane, one unit: rows in id order, each row's hits in id order
-        for (int a = aBeg; a < aEnd; ++a) {
-            unsigned int off, n;
-            hit_list(__ldg(A.meta + a), d_idx, off, n);
-            if (n == 0) continue;
-            int sa = A.sp[a];
-            const int sa0 = sa;
-            for (unsigned int k = 0; k < n && (unsigned long long)off + k < A.cap_hits; ++k) {
-                const uint32_t h = __ldg(A.hits + off + k);
-                const int b = (int)(h & HIT_MASK);
-                const int sb = A.sp[b];
-                if (sa != sb && is_rps(sa) && is_rps(sb)) {
-                    sa = rps_apply(sa, sb, h >> 29);
-                    A.sp[b] = (int8_t)sa;
-                }
-            }
-            if (sa != sa0) A.sp[a] = (int8_t)sa;
-        }
-    }
-    // dense clusters: the warp resolves them together, one after the other
-    unsigned hm = __ballot_sync(0xffffffffu, heavy);
-    while (hm) {
-        const int src = __ffs(hm) - 1;
-        hm &= hm - 1;
-        resolve_unit_warp(A, d_idx, __shfl_sync(0xffffffffu, aBeg, src), __shfl_sync(0xffffffffu, aEnd, src));
-    }
-}
-
-// One phase per launch, one lane per unit: the general path (any grid shape).
-__global__ void __launch_bounds__(256) resolve_phase_kernel(ResolveArgs A)
-{
-    const long long u = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    int anchor = 0, other = 0;
-    const bool valid = u < A.n_units && decode_unit(A, u, anchor, other);
-    resolve_unit(A, valid, anchor, other, A.d_idx);
-}
-
-// Three phases per launch for grids with many long rows.  The phases of one group couple cells of ONE row
-// (group 0: phases 0,1,2 = same cell, east even, east odd) or of ONE pair of rows (group 1: phases 3,4,5 =
-// NW, N, NE from an even anchor row; group 2: phases 6,7,8 from an odd one), so a CTA that owns the row
-// (pair) can run its three phases back to back with a block barrier in between: 3 launches instead of 9,
-// and every particle's meta / hit list is read once per group instead of once per phase.
-constexpr int ROW_THREADS = 1024;
-template <int GROUP>
-__global__ void __launch_bounds__(ROW_THREADS) resolve_rows_kernel(ResolveArgs A)
-{
+    __shared__ uint4 s_desc_all[RES_THREADS / 32][DCAP][32];
+    if (A.ctr->n_pairs > A.cap_words) return;          // the hand-off overflowed: reported by lm_sync_stats
+    const int lane = threadIdx.x & 31;
+    const long long wid = ((long long)blockIdx.x * RES_THREADS + threadIdx.x) >> 5;
+    if (wid >= A.n_warps) return;                      // warp-uniform
+    uint4 (*s_desc)[32] = s_desc_all[threadIdx.x >> 5];
+    const int row = (int)(wid / A.warps_per_row);
+    const int u_base = (int)(wid - (long long)row * A.warps_per_row) * (32 * UNITS_PER_LANE) + lane;
     const int ncx = A.ncx;
-    const int cy = (GROUP == 0) ? (int)blockIdx.x : 2 * (int)blockIdx.x + (GROUP - 1);
-    const int row = cy * ncx;
+    const int cy = (A.mode == MODE_CROSS) ? 2 * row + A.parity : row;
+    const int row_cell = cy * ncx;
+
+    // ---- stage A: four units at a time, all loads independent and coalesced across the lanes
+    int nd = 0;
 #pragma unroll 1
-    for (int ph = 0; ph < 3; ++ph) {
-        const int n_units = (GROUP == 0 && ph > 0) ? (ncx - (ph - 1)) / 2 : ncx;
-        const int d_idx = (GROUP == 0) ? (ph > 0 ? 1 : 0) : 2 + ph;
-        for (int u0 = 0; u0 < n_units; u0 += blockDim.x) {     // block-uniform trip count
-            const int u = u0 + (int)threadIdx.x;
-            bool valid = u < n_units;
-            int anchor = 0, other = 0;
-            if (valid) {
-                if (GROUP == 0) {
-                    anchor = (ph == 0) ? row + u : row + 2 * u + (ph - 1);
-                    other = (ph == 0) ? anchor : anchor + 1;
-                } else {
-                    const int ox = u + ph - 1;
-                    valid = ox >= 0 && ox < ncx;
-                    anchor = row + u;
-                    other = row + ncx + ox;
-                }
+    for (int j0 = 0; j0 < UNITS_PER_LANE; j0 += 4) {
+        int cell[4], other[4];
+        bool on[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int u = u_base + 32 * (j0 + q);
+            on[q] = u < A.units_per_row;
+            if (A.mode == MODE_SAME) { cell[q] = row_cell + u; other[q] = cell[q]; }
+            else if (A.mode == MODE_EAST) { cell[q] = row_cell + 2 * u + A.parity; other[q] = cell[q] + 1; }
+            else {
+                const int ox = u + A.dir;
+                on[q] = on[q] && ox >= 0 && ox < ncx;
+                cell[q] = row_cell + u; other[q] = cell[q] + ncx + A.dir;
             }
-            resolve_unit(A, valid, anchor, other, d_idx);
         }
-        __syncthreads();
+        int cs0[4], cs1[4], ob[4];
+        uint2 R[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            cs0[q] = on[q] ? __ldg(A.cell_start + cell[q]) : 0;
+            cs1[q] = on[q] ? __ldg(A.cell_start + cell[q] + 1) : 0;
+            ob[q] = on[q] ? __ldg(A.cell_start + other[q]) : 0;
+            R[q] = on[q] ? __ldg(A.rec + cell[q]) : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            bool heavy = false;
+            if (on[q] && cs1[q] > cs0[q]) {
+                const int mark = nd;
+                uint2 r = R[q];
+                int a0 = cs0[q];
+                while (true) {
+                    if (r.y > HEAVY_ENTRIES || (r.y && nd == DCAP)) { heavy = true; break; }
+                    if (r.y) { s_desc[nd][lane] = make_uint4(r.x, r.y, (unsigned int)a0, (unsigned int)ob[q]); ++nd; }
+                    a0 = (a0 | 31) + 1;                        // the cell goes on in the next 32-particle chunk?
+                    if (a0 >= cs1[q]) break;
+                    r = __ldg(A.rec2 + (a0 >> 5));
+                }
+                if (heavy) nd = mark;                          // the whole unit goes to the warp
+            }
+            unsigned int hm = __ballot_sync(0xffffffffu, heavy);
+            while (hm) {
+                const int src = __ffs(hm) - 1;
+                hm &= hm - 1;
+                resolve_unit_warp(A, __shfl_sync(0xffffffffu, cell[q], src), __shfl_sync(0xffffffffu, cs0[q], src),
+                                  __shfl_sync(0xffffffffu, cs1[q], src), __shfl_sync(0xffffffffu, ob[q], src));
+            }
+        }
     }
+
+    // ---- stage B.  Entries are fetched four at a time (aligned 16-byte loads: one memory round trip per four
+    // pairs), the first quad of the NEXT stream is requested when a stream is opened, and the two species
+    // loads of a pair are issued together.
+    int di = 0, cur_a = -1, sa = 0, sa0 = 0;
+    unsigned int k = 0, k_end = 0, a0 = 0, q_at = 0xffffffffu, qn_at = 0xffffffffu;
+    uint4 quad = make_uint4(0, 0, 0, 0), quad_n = make_uint4(0, 0, 0, 0);
+    int oBeg = 0;
+    if (nd > 0) { qn_at = s_desc[0][lane].x & ~3u; quad_n = __ldg(reinterpret_cast<const uint4 *>(A.hits + qn_at)); }
+    while (__any_sync(0xffffffffu, k < k_end || di < nd)) {
+        if (k == k_end && di < nd) {
+            const uint4 D = s_desc[di][lane];
+            k = D.x; k_end = D.x + D.y; a0 = D.z; oBeg = (int)D.w;
+            quad = quad_n; q_at = qn_at;
+            ++di;
+            if (di < nd) { qn_at = s_desc[di][lane].x & ~3u; quad_n = __ldg(reinterpret_cast<const uint4 *>(A.hits + qn_at)); }
+        }
+        if (k < k_end) {
+            const unsigned int q = k & ~3u;
+            if (q != q_at) { quad = __ldg(reinterpret_cast<const uint4 *>(A.hits + q)); q_at = q; }
+            const unsigned int sel = k & 3u;
+            const uint32_t en = sel == 0 ? quad.x : (sel == 1 ? quad.y : (sel == 2 ? quad.z : quad.w));
+            const int a = (int)a0 + (int)((en >> 24) & 31u), b = oBeg + (int)(en & B_REL_MASK);
+            const bool new_a = a != cur_a;
+            if (new_a && cur_a >= 0 && sa != sa0) A.sp[cur_a] = (int8_t)sa;     // never aliases the two loads below
+            int sa_l = 0;
+            if (new_a) sa_l = A.sp[a];
+            const int sb = A.sp[b];
+            if (new_a) { cur_a = a; sa = sa0 = sa_l; }
+            if (sa != sb && is_rps(sa) && is_rps(sb)) {
+                sa = rps_apply(sa, sb, en >> 29);
+                A.sp[b] = (int8_t)sa;
+            }
+            ++k;
+        }
+    }
+    if (cur_a >= 0 && sa != sa0) A.sp[cur_a] = (int8_t)sa;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -434,6 +570,7 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
     FindArgs F;
     F.lon = lon; F.lat = lat; F.id = id; F.cell_start = h->cell_start;
     F.g = h->grid; F.n = n;
+    F.force_two_pass = h->find_path == 1 ? 1 : 0;
     F.row0 = h->strip.row0; F.rows_owned = h->strip.rows_owned; F.rows_local = h->strip.rows_local;
     F.r2 = r * r;
     F.r2_lo = (float)(F.r2 * (1.0 - 4e-6));
@@ -450,13 +587,14 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
             else F.thr[k] = (unsigned long long)ceil(p[k] * 9007199254740992.0);
         }
     }
-    F.hits = h->hits; F.meta = h->meta;
+    F.hits = h->hits; F.rec = h->rec; F.rec2 = h->rec2; F.rec_stride = h->max_cells; F.rec2_stride = h->max_particles / 32 + 2;
     F.pairs = pairs_out;
-    F.cap_hits = rps ? (unsigned long long)h->max_pairs : 0ull;
+    F.cap_words = rps ? (unsigned long long)h->max_pairs : 0ull;
     F.cap_pairs = (pairs_out && cap > 0) ? (unsigned long long)cap : 0ull;
     F.ctr = h->ctr;
     const bool emit = F.cap_pairs > 0;
     const int grid = (n + FIND_THREADS - 1) / FIND_THREADS;
+    ++h->launches;
     if (rps) {
         if (emit) find_pairs_kernel<true, true><<<grid, FIND_THREADS, 0, s>>>(F);
         else find_pairs_kernel<true, false><<<grid, FIND_THREADS, 0, s>>>(F);
@@ -464,7 +602,6 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
         if (emit) find_pairs_kernel<false, true><<<grid, FIND_THREADS, 0, s>>>(F);
         else find_pairs_kernel<false, false><<<grid, FIND_THREADS, 0, s>>>(F);
     }
-    ++h->launches;
     return cudaGetLastError();
 }
 
@@ -475,46 +612,32 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
 {
     if (h->rps_cap < 0) return cudaSuccess;
     ResolveArgs R;
-    R.sp = sp; R.cell_start = h->cell_start; R.meta = h->meta; R.hits = h->hits;
-    R.cap_hits = (unsigned long long)h->max_pairs;
-    R.ncx = h->grid.ncx; R.ncy = h->strip.rows_local;
-    R.mode = R.parity = R.dir = R.d_idx = 0; R.n_units = 0;
+    R.sp = sp; R.cell_start = h->cell_start; R.hits = h->hits;
+    R.ctr = h->ctr;
+    R.cap_words = (unsigned long long)h->max_pairs;
+    R.ncx = h->grid.ncx;
     const long long ncx = R.ncx, rows_owned = h->strip.rows_owned, rows_local = h->strip.rows_local;
-    // row-fused path: whole groups of three phases, enough rows to fill the GPU, rows long enough for a CTA
-    const bool fused = h->resolve_mode == 1 ||
-                       (h->resolve_mode == 0 && rows_owned >= 2 * kNumSMs && ncx >= ROW_THREADS / 2);
-    int ph = first;
-    while (ph <= last) {
-        cudaError_t e;
-        if (fused && ph % 3 == 0 && ph + 2 <= last) {
-            const int group = ph / 3;
-            const int threads = (int)(ncx >= ROW_THREADS ? ROW_THREADS : ((ncx + 31) / 32) * 32);
-            const long long rows = group == 0 ? rows_owned : (rows_local - (group - 1)) / 2;
-            if (rows > 0) {
-                if (group == 0) resolve_rows_kernel<0><<<(unsigned)rows, threads, 0, s>>>(R);
-                else if (group == 1) resolve_rows_kernel<1><<<(unsigned)rows, threads, 0, s>>>(R);
-                else resolve_rows_kernel<2><<<(unsigned)rows, threads, 0, s>>>(R);
-                ++h->launches;
-                if ((e = cudaGetLastError()) != cudaSuccess) return e;
-            }
-            ph += 3;
-            continue;
-        }
-        long long n_units;
-        if (ph == 0) { R.mode = MODE_SAME; R.parity = 0; R.dir = 0; R.d_idx = 0; n_units = ncx * rows_owned; }
+    for (int ph = first; ph <= last; ++ph) {
+        long long rows;
+        int d_idx;
+        if (ph == 0) { R.mode = MODE_SAME; R.parity = 0; R.dir = 0; d_idx = 0; R.units_per_row = (int)ncx; rows = rows_owned; }
         else if (ph <= 2) {
-            R.mode = MODE_EAST; R.parity = ph - 1; R.dir = 0; R.d_idx = 1;
-            n_units = ((ncx - R.parity) / 2) * rows_owned;
+            R.mode = MODE_EAST; R.parity = ph - 1; R.dir = 0; d_idx = 1;
+            R.units_per_row = (int)((ncx - R.parity) / 2); rows = rows_owned;
         } else {
-            R.mode = MODE_CROSS; R.parity = (ph - 3) / 3; R.dir = (ph - 3) % 3 - 1; R.d_idx = 3 + R.dir;
-            n_units = ((rows_local - R.parity) / 2) * ncx;
+            R.mode = MODE_CROSS; R.parity = (ph - 3) / 3; R.dir = (ph - 3) % 3 - 1; d_idx = 3 + R.dir;
+            R.units_per_row = (int)ncx; rows = (rows_local - R.parity) / 2;       // anchor rows cy = 2 i + parity, cy + 1 < rows_local
         }
-        ++ph;
-        if (n_units <= 0) continue;
-        R.n_units = n_units;
-        resolve_phase_kernel<<<(unsigned)((n_units + 255) / 256), 256, 0, s>>>(R);
+        R.rec = h->rec + (size_t)d_idx * h->max_cells;
+        R.rec2 = h->rec2 + (size_t)d_idx * (h->max_particles / 32 + 2);
+        if (rows <= 0 || R.units_per_row <= 0) continue;
+        R.warps_per_row = (R.units_per_row + 32 * UNITS_PER_LANE - 1) / (32 * UNITS_PER_LANE);
+        R.n_warps = rows * R.warps_per_row;
+        const long long blocks = (R.n_warps * 32 + RES_THREADS - 1) / RES_THREADS;
+        resolve_phase_kernel<<<(unsigned)blocks, RES_THREADS, 0, s>>>(R);
         ++h->launches;
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
 }

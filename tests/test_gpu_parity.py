@@ -164,7 +164,7 @@ def test_resolve_rps_lexicographic_and_reversed_orders(engine_factory, name):
         assert np.array_equal(species.cpu().numpy(), want)
 
 
-RESOLVE_MODES = [1, 2]      # LM_OPT_RESOLVE: 1 = three row-fused launches, 2 = one launch per phase
+RESOLVE_MODES = [0, 1]      # LM_OPT_FIND_PATH: 0 = auto; 1 = every warp takes the two-pass (dense cluster) path
 
 
 @pytest.mark.parametrize("mode", RESOLVE_MODES)
@@ -172,11 +172,11 @@ RESOLVE_MODES = [1, 2]      # LM_OPT_RESOLVE: 1 = three row-fused launches, 2 = 
 def test_interact_rps_cell_phase_order_golden(engine_factory, name, mode):
     """Fused pair search + RPS on the grid the golden was made for; golden species come from the
     unmodified reference function run in the canonical cell-phase order."""
-    from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE
+    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH
     g = golden(name + ".npz")
     n = g["lon"].size
     eng = engine_factory(max_particles=n, max_cells=1 << 22, max_pairs=g["pairs_ref_order"].shape[0] + 64)
-    eng.set_option(LM_OPT_RESOLVE, mode)
+    eng.set_option(LM_OPT_FIND_PATH, mode)
     eng.set_grid(grid_from_golden(g))
     species = dev(g["species0"].copy())
     out = torch.empty((g["pairs_ref_order"].shape[0] + 64, 2), dtype=torch.int32, device="cuda")
@@ -198,7 +198,7 @@ def test_interact_rps_cell_phase_order_golden(engine_factory, name, mode):
 @pytest.mark.parametrize("n,r,p", [(100000, 0.01, (0.55, 0.55, 0.55)), (150000, 0.02, (0.5, 0.6, 0.9)),
                                    (40000, 0.05, (0.9, 0.9, 0.9)), (600000, 0.004, (0.55, 0.55, 0.55))])
 def test_interact_rps_vs_oracle_live(engine_factory, n, r, p, mode):
-    from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE
+    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH
     rng = np.random.default_rng(n + 1)
     side = np.sqrt(n / 4900.0)
     lon = (205 + side * rng.random(n)).astype(np.float32)
@@ -206,8 +206,8 @@ def test_interact_rps_vs_oracle_live(engine_factory, n, r, p, mode):
     sp0 = rng.integers(1, 4, n).astype(np.int8)
     want_pairs = opairs.query_pairs_reference_array(lon, lat, r)
     eng = engine_factory(max_particles=n, max_cells=1 << 22, max_pairs=want_pairs.shape[0] + 64)
-    eng.set_option(LM_OPT_RESOLVE, mode)
-    grid = auto_grid(eng, lon, lat, r, margin=0.25)       # the 600k case: 2770 x 2770 cells, rows longer than a CTA
+    eng.set_option(LM_OPT_FIND_PATH, mode)
+    grid = auto_grid(eng, lon, lat, r, margin=0.25)       # the 600k case: 2770 x 2770 cells, several warps per row
     out = torch.empty((want_pairs.shape[0] + 64, 2), dtype=torch.int32, device="cuda")
     species = dev(sp0.copy())
     eng.interact_rps(dev(lon), dev(lat), species, r, *p, 77, 1234, pairs_out=out)
@@ -422,9 +422,9 @@ def test_interact_rps_dense_clusters_take_the_warp_cooperative_path(engine_facto
     r, p = 0.01, (0.55, 0.6, 0.5)
     want_pairs = opairs.query_pairs_reference_array(lon, lat, r)
     assert want_pairs.shape[0] > 2_000_000
-    from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE
+    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH
     eng = engine_factory(max_particles=n, max_cells=1 << 20, max_pairs=want_pairs.shape[0] + 64)
-    eng.set_option(LM_OPT_RESOLVE, mode)
+    eng.set_option(LM_OPT_FIND_PATH, mode)
     grid = auto_grid(eng, lon, lat, r, margin=0.1)
     out = torch.empty((want_pairs.shape[0] + 64, 2), dtype=torch.int32, device="cuda")
     species = dev(sp0.copy())
