@@ -132,7 +132,7 @@ constexpr int FILL_CAP = 1024;       // hits of one warp that the dense finishin
 constexpr int OWN_WORDS = 12;        // per lane, for the finishing stage: rel[5], base0, sE, begNW, sN, sNE, beg0, n1
 
 template <bool DO_RPS, bool EMIT>
-__global__ void __launch_bounds__(FIND_THREADS) find_pairs_kernel(FindArgs A)
+__global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
 {
     __shared__ uint16_t s_fill_all[FIND_WARPS][FILL_CAP];      // compact hit e of the warp -> owner lane | candidate index << 5
     __shared__ uint32_t s_own_all[FIND_WARPS][OWN_WORDS][32];
@@ -288,7 +288,8 @@ __global__ void __launch_bounds__(FIND_THREADS) find_pairs_kernel(FindArgs A)
         s_own[11][lane] = (uint32_t)n1;
         {
             unsigned int kk = excl_tot;
-            for (unsigned long long m = mask; m; m &= m - 1) s_fill[kk++] = (uint16_t)(lane | ((__ffsll((long long)m) - 1) << 5));
+            for (unsigned int m = (unsigned int)mask; m; m &= m - 1) s_fill[kk++] = (uint16_t)(lane | ((__ffs((int)m) - 1) << 5));
+            for (unsigned int m = (unsigned int)(mask >> 32); m; m &= m - 1) s_fill[kk++] = (uint16_t)(lane | ((__ffs((int)m) + 31) << 5));
         }
         __syncwarp();
         for (unsigned int e0 = 0; e0 < wpairs; e0 += 32) {
@@ -450,28 +451,35 @@ __device__ void resolve_unit_warp(const ResolveArgs &A, int cell, int cs0, int c
 // Pair counts per unit are heavy-tailed (same-cell units: ~m^2/2 for m microbes in the cell) and most units
 // are short, so "one lane walks one unit" leaves the warp waiting for its longest unit with a handful of lanes
 // active.  Instead, in two warp-uniform stages:
-//   A  every lane looks at its units (loads batched four units at a time) and pushes one descriptor per
-//      non-empty (segment, direction) entry stream -- (first entry, count, first anchor, partner cell start)
-//      -- onto its private list in shared memory; dense clusters are resolved right away by the whole warp;
-//   B  every lane walks the concatenation of its entry streams, one pair per iteration: all lanes execute
-//      the same instruction stream until their lists run out, and a lane's work is the SUM over its units.
-constexpr int DCAP = 10;             // descriptors per lane: 8 units + continuation segments (more: warp path)
+//   A  every lane looks at its units (loads batched four units at a time, all coalesced) and pushes one
+//      descriptor per non-empty (segment, direction) entry stream -- (first entry, count, first anchor,
+//      partner cell start) -- onto the WARP's list in shared memory; dense clusters are resolved right away
+//      by the whole warp;
+//   B  the lanes pull units from that list (a shared-memory ticket) and walk their entry streams, one pair
+//      per iteration: all lanes execute the same instruction stream, and a lane that finishes a short unit
+//      takes the next one instead of idling.
+constexpr int HEAD_CAP = 32 * UNITS_PER_LANE;      // at most one head descriptor per unit
+constexpr int CONT_CAP = 64;                       // descriptors of continuation segments (more: warp path)
+constexpr unsigned int NO_LINK = 0xffffffu;
 __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs A)
 {
-    __shared__ uint4 s_desc_all[RES_THREADS / 32][DCAP][32];
+    __shared__ uint4 s_desc_all[RES_THREADS / 32][HEAD_CAP + CONT_CAP];   // x first entry | y count + link << 8 | z first anchor | w partner cell start
+    __shared__ unsigned int s_ctr_all[RES_THREADS / 32][4];               // heads, continuations, next ticket
     if (A.ctr->n_pairs > A.cap_words) return;          // the hand-off overflowed: reported by lm_sync_stats
     const int lane = threadIdx.x & 31;
     const long long wid = ((long long)blockIdx.x * RES_THREADS + threadIdx.x) >> 5;
     if (wid >= A.n_warps) return;                      // warp-uniform
-    uint4 (*s_desc)[32] = s_desc_all[threadIdx.x >> 5];
+    uint4 *s_desc = s_desc_all[threadIdx.x >> 5];
+    unsigned int *s_ctr = s_ctr_all[threadIdx.x >> 5];
     const int row = (int)(wid / A.warps_per_row);
     const int u_base = (int)(wid - (long long)row * A.warps_per_row) * (32 * UNITS_PER_LANE) + lane;
     const int ncx = A.ncx;
     const int cy = (A.mode == MODE_CROSS) ? 2 * row + A.parity : row;
     const int row_cell = cy * ncx;
+    if (lane < 4) s_ctr[lane] = 0;
+    __syncwarp();
 
     // ---- stage A: four units at a time, all loads independent and coalesced across the lanes
-    int nd = 0;
 #pragma unroll 1
     for (int j0 = 0; j0 < UNITS_PER_LANE; j0 += 4) {
         int cell[4], other[4];
@@ -501,17 +509,28 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
         for (int q = 0; q < 4; ++q) {
             bool heavy = false;
             if (on[q] && cs1[q] > cs0[q]) {
-                const int mark = nd;
                 uint2 r = R[q];
                 int a0 = cs0[q];
+                int head_slot = -1, prev_slot = -1;
                 while (true) {
-                    if (r.y > HEAVY_ENTRIES || (r.y && nd == DCAP)) { heavy = true; break; }
-                    if (r.y) { s_desc[nd][lane] = make_uint4(r.x, r.y, (unsigned int)a0, (unsigned int)ob[q]); ++nd; }
+                    if (r.y > HEAVY_ENTRIES) { heavy = true; break; }
+                    if (r.y) {
+                        int slot;
+                        if (head_slot < 0) slot = head_slot = (int)atomicAdd(&s_ctr[0], 1u);          // < HEAD_CAP by construction
+                        else {
+                            const unsigned int cs = atomicAdd(&s_ctr[1], 1u);
+                            if (cs >= (unsigned int)CONT_CAP) { heavy = true; break; }
+                            slot = HEAD_CAP + (int)cs;
+                            s_desc[prev_slot].y = (s_desc[prev_slot].y & 255u) | ((unsigned int)slot << 8);
+                        }
+                        s_desc[slot] = make_uint4(r.x, r.y | (NO_LINK << 8), (unsigned int)a0, (unsigned int)ob[q]);
+                        prev_slot = slot;
+                    }
                     a0 = (a0 | 31) + 1;                        // the cell goes on in the next 32-particle chunk?
                     if (a0 >= cs1[q]) break;
                     r = __ldg(A.rec2 + (a0 >> 5));
                 }
-                if (heavy) nd = mark;                          // the whole unit goes to the warp
+                if (heavy && head_slot >= 0) s_desc[head_slot].y = NO_LINK << 8;      // void what was pushed: the whole unit goes to the warp
             }
             unsigned int hm = __ballot_sync(0xffffffffu, heavy);
             while (hm) {
@@ -522,28 +541,32 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
             }
         }
     }
+    __syncwarp();
+    const unsigned int n_heads = s_ctr[0];
 
-    // ---- stage B.  Entries are fetched four at a time (aligned 16-byte loads: one memory round trip per four
-    // pairs), the first quad of the NEXT stream is requested when a stream is opened, and the two species
-    // loads of a pair are issued together.
-    int di = 0, cur_a = -1, sa = 0, sa0 = 0;
-    unsigned int k = 0, k_end = 0, a0 = 0, q_at = 0xffffffffu, qn_at = 0xffffffffu;
-    uint4 quad = make_uint4(0, 0, 0, 0), quad_n = make_uint4(0, 0, 0, 0);
-    int oBeg = 0;
-    if (nd > 0) { qn_at = s_desc[0][lane].x & ~3u; quad_n = __ldg(reinterpret_cast<const uint4 *>(A.hits + qn_at)); }
-    while (__any_sync(0xffffffffu, k < k_end || di < nd)) {
-        if (k == k_end && di < nd) {
-            const uint4 D = s_desc[di][lane];
-            k = D.x; k_end = D.x + D.y; a0 = D.z; oBeg = (int)D.w;
-            quad = quad_n; q_at = qn_at;
-            ++di;
-            if (di < nd) { qn_at = s_desc[di][lane].x & ~3u; quad_n = __ldg(reinterpret_cast<const uint4 *>(A.hits + qn_at)); }
+    // ---- stage B: a lane holds the unit it is walking and the ticket of its next one (whose first sector is
+    // already on its way); the two species loads of a pair are issued together.
+    int cur_a = -1, sa = 0, sa0 = 0, oBeg = 0;
+    unsigned int k = 0, k_end = 0, a0 = 0, link = NO_LINK;
+    unsigned int nxt = atomicAdd(&s_ctr[2], 1u);
+    bool active = nxt < n_heads;
+    while (__any_sync(0xffffffffu, active)) {
+        if (active && k == k_end) {
+            unsigned int take = link;
+            if (take == NO_LINK) {
+                take = nxt;
+                if (take < n_heads) {
+                    nxt = atomicAdd(&s_ctr[2], 1u);
+                    if (nxt < n_heads) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.hits + s_desc[nxt].x));
+                } else active = false;
+            }
+            if (active) {
+                const uint4 D = s_desc[take];
+                k = D.x; k_end = D.x + (D.y & 255u); link = D.y >> 8; a0 = D.z; oBeg = (int)D.w;
+            }
         }
-        if (k < k_end) {
-            const unsigned int q = k & ~3u;
-            if (q != q_at) { quad = __ldg(reinterpret_cast<const uint4 *>(A.hits + q)); q_at = q; }
-            const unsigned int sel = k & 3u;
-            const uint32_t en = sel == 0 ? quad.x : (sel == 1 ? quad.y : (sel == 2 ? quad.z : quad.w));
+        if (active && k < k_end) {
+            const uint32_t en = __ldg(A.hits + k);
             const int a = (int)a0 + (int)((en >> 24) & 31u), b = oBeg + (int)(en & B_REL_MASK);
             const bool new_a = a != cur_a;
             if (new_a && cur_a >= 0 && sa != sa0) A.sp[cur_a] = (int8_t)sa;     // never aliases the two loads below
