@@ -26,25 +26,54 @@ struct StageDev {
     float frac[4];
 };
 
-__device__ __forceinline__ int search_axis(const float *__restrict__ vals, int n, float x, float v0, float inv_d)
+// Index search on one grid axis (parcels.h::search_indices_rectilinear restated): the cell i with
+// vals[i] <= x <= vals[i+1], found from a uniform-spacing guess and fixed up -- the result is that of Parcels'
+// linear search for any ascending axis.  Returns the two bracketing axis values, which the caller needs anyway,
+// so a regular axis costs two independent loads and no dependent ones.  v_first / v_last are the axis ends
+// (kernel parameters).  Returns -1 out of bounds (also catches NaN).
+__device__ __forceinline__ int search_axis(const float *__restrict__ vals, int n, float x, float v_first, float v_last,
+                                           float inv_d, float &lo, float &hi)
 {
-    if (!(x >= __ldg(vals)) || !(x <= __ldg(vals + n - 1))) return -1;   // also catches NaN
-    int i = (int)((x - v0) * inv_d);
+    if (!(x >= v_first) || !(x <= v_last)) return -1;
+    int i = (int)((x - v_first) * inv_d);
     i = max(0, min(i, n - 2));
-    while (i < n - 2 && x > __ldg(vals + i + 1)) ++i;
-    while (i > 0 && x < __ldg(vals + i)) --i;
+    lo = __ldg(vals + i);
+    hi = __ldg(vals + i + 1);
+    while (i < n - 2 && x > hi) { ++i; lo = hi; hi = __ldg(vals + i + 1); }
+    while (i > 0 && x < lo) { --i; hi = lo; lo = __ldg(vals + i); }
     return i;
+}
+
+// cos(x) for |x| <= pi/2 (latitudes): fdlibm's __kernel_cos / __kernel_sin polynomials (error < 1 ulp, as is
+// the libm the CPU restatement links), without the generic argument reduction of the CUDA library routine.
+__device__ __noinline__ double cos_generic(double x) { return cos(x); }
+
+__device__ __forceinline__ double cos_lat(double x)
+{
+    const double ax = fabs(x);
+    if (!(ax <= 1.5707963267948966)) return cos_generic(x);       // not a latitude: the library routine
+    if (ax <= 0.78539816339744830962) {
+        const double z = x * x;
+        const double r = z * (4.16666666666666019037e-02 + z * (-1.38888888888741095749e-03 + z * (2.48015872894767294178e-05 +
+                         z * (-2.75573143513906633035e-07 + z * (2.08757232129817482790e-09 + z * -1.13596475577881948265e-11)))));
+        return 1.0 - (0.5 * z - z * r);
+    }
+    // cos(x) = sin(pi/2 - |x|), pi/2 in two parts
+    const double y = (1.57079632679489655800e+00 - ax) + 6.12323399573676603587e-17;
+    const double z = y * y;
+    const double r = 8.33333333332248946124e-03 + z * (-1.98412698298579493134e-04 + z * (2.75573137070700676789e-06 +
+                     z * (-2.50507602534068634195e-08 + z * 1.58969099521155010221e-10)));
+    return y + y * z * (-1.66666666666666324348e-01 + z * r);
 }
 
 // Sample converted (u, v) [deg/s] at the float32 point (x, y).  Returns false when out of bounds.
 __device__ __forceinline__ bool sample_uv(const FieldDev &f, float x, float y, int ti, int interp, float frac,
                                           float &u, float &v)
 {
-    const int xi = search_axis(f.lon, f.X, x, f.lon0, f.inv_dx);
-    const int yi = search_axis(f.lat, f.Y, y, f.lat0, f.inv_dy);
+    float lx0, lx1, ly0, ly1;
+    const int xi = search_axis(f.lon, f.X, x, f.lon0, f.lon1, f.inv_dx, lx0, lx1);
+    const int yi = search_axis(f.lat, f.Y, y, f.lat0, f.lat1, f.inv_dy, ly0, ly1);
     if (xi < 0 || yi < 0) return false;
-    const float lx0 = __ldg(f.lon + xi), lx1 = __ldg(f.lon + xi + 1);
-    const float ly0 = __ldg(f.lat + yi), ly1 = __ldg(f.lat + yi + 1);
     const double xsi = (double)__fdiv_rn(__fsub_rn(x, lx0), __fsub_rn(lx1, lx0));
     const double eta = (double)__fdiv_rn(__fsub_rn(y, ly0), __fsub_rn(ly1, ly0));
     const double omx = __dsub_rn(1.0, xsi), ome = __dsub_rn(1.0, eta);
@@ -70,7 +99,7 @@ __device__ __forceinline__ bool sample_uv(const FieldDev &f, float x, float y, i
     }
     // u *= 1.0 / (1852. * 60. * cos(y * M_PI / 180));   v *= 1.0 / (1852. * 60.)
     const double ang = __ddiv_rn(__dmul_rn((double)y, 3.14159265358979323846), 180.0);
-    const double cu = __ddiv_rn(1.0, __dmul_rn(111120.0, cos(ang)));
+    const double cu = __ddiv_rn(1.0, __dmul_rn(111120.0, cos_lat(ang)));
     constexpr double cv = 1.0 / 111120.0;
     u = __double2float_rn(__dmul_rn((double)uu, cu));
     v = __double2float_rn(__dmul_rn((double)vv, cv));

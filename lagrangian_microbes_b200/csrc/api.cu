@@ -147,6 +147,7 @@ int lm_set_field(lm_handle h, const float *U, const float *V, const float *lon, 
     h->field.U = U; h->field.V = V; h->field.lon = lon; h->field.lat = lat;
     h->field.T = T; h->field.Y = Y; h->field.X = X;
     h->field.lon0 = ends[0]; h->field.lat0 = ends[2];
+    h->field.lon1 = ends[1]; h->field.lat1 = ends[3];
     h->field.inv_dx = (float)(X - 1) / (ends[1] - ends[0]);
     h->field.inv_dy = (float)(Y - 1) / (ends[3] - ends[2]);
     h->have_field = true;

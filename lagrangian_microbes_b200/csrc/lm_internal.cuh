@@ -12,7 +12,7 @@ constexpr int kNumSMs = 148;   // B200
 struct FieldDev {
     const float *U, *V, *lon, *lat;
     int T, Y, X;
-    float lon0, lat0, inv_dx, inv_dy;   // index guess: i = (x - lon0) * inv_dx
+    float lon0, lat0, lon1, lat1, inv_dx, inv_dy;   // axis ends; index guess: i = (x - lon0) * inv_dx
 };
 
 // device-side counters, reset at the start of every step / interact call
