@@ -215,7 +215,8 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Number of kernels this library launched since the handle was created. */
 int64_t lm_launch_count(lm_handle h);
 /* Device time of the phases of the last lm_step run with LM_STEP_TIMING (synchronises on it):
- * ms_out[0] diffuse+advect, [1] binning, [2] pair search + RPS, [3] stats.  Host float[4]. */
+ * ms_out[0] diffuse+advect, [1] binning, [2] pair search, [3] RPS resolution (with strips: including the
+ * waits for the halo exchanges), [4] stats.  Host float[5]. */
 int lm_phase_times(lm_handle h, float *ms_out);
 
 #ifdef __cplusplus

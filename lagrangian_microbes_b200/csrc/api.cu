@@ -78,7 +78,7 @@ int lm_destroy(lm_handle h)
     cudaFree(h->ghost_send); cudaFree(h->ghost_recv);
     cudaFree(h->gsp_send); cudaFree(h->gsp_recv); cudaFree(h->gret_send); cudaFree(h->gret_recv);
     if (h->xfer_counts_host) cudaFreeHost(h->xfer_counts_host);
-    for (int k = 0; k < 5; ++k)
+    for (int k = 0; k < 6; ++k)
         if (h->ev_phase[k]) cudaEventDestroy(h->ev_phase[k]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -122,7 +122,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
         ok = ok && cudaEventCreateWithFlags(&h->ev_scatter[k], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming) == cudaSuccess;
     }
-    for (int k = 0; ok && k < 5; ++k) ok = ok && cudaEventCreate(&h->ev_phase[k]) == cudaSuccess;
+    for (int k = 0; ok && k < 6; ++k) ok = ok && cudaEventCreate(&h->ev_phase[k]) == cudaSuccess;
     if (!ok) {
         cudaError_t e = cudaGetLastError();
         set_last_cuda_error(e, "lm_create");
@@ -522,6 +522,7 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
         LM_CUDA(launch_find(h, h->lon[c], h->lat[c], h->id[c], n, r, &h->step_rps,
                             emit ? reinterpret_cast<int2 *>(pairs_out) : nullptr, emit ? cap : 0, s));
         h->emit_cap = emit ? cap : -1;
+        if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[3], s));
         if (n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 0, 5, s));
     }
     if (h->has_south && interact) LM_CUDA(launch_row0_species_pack(h, h->sp[c], s));
@@ -540,7 +541,10 @@ int lm_step_interact_end(lm_handle h, void *stream)
     if (h->has_north && interact) LM_CUDA(launch_ghost_species_unpack(h, h->sp[c], n, s));
     if (interact && n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, s));
     if (h->has_north && interact) LM_CUDA(launch_ghost_species_pack(h, h->sp[c], n, s));
-    if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[3], s));
+    if (h->step_flags & LM_STEP_TIMING) {
+        if (!interact) LM_CUDA(cudaEventRecord(h->ev_phase[3], s));
+        LM_CUDA(cudaEventRecord(h->ev_phase[4], s));
+    }
     h->stage = 4;
     return LM_OK;
 }
@@ -555,7 +559,7 @@ int lm_step_finish(lm_handle h, void *stream)
     if (h->has_south && (h->step_flags & LM_STEP_INTERACT)) LM_CUDA(launch_row0_species_unpack(h, h->sp[c], s));
     if (h->step_flags & LM_STEP_STATS) LM_CUDA(launch_stats(h->lon[c], h->lat[c], h->sp[c], n, h->ctr, s, &h->launches));
     if (h->step_flags & LM_STEP_TIMING) {
-        LM_CUDA(cudaEventRecord(h->ev_phase[4], s));
+        LM_CUDA(cudaEventRecord(h->ev_phase[5], s));
         h->timed = true;
     }
     h->stage = 0;
@@ -581,8 +585,8 @@ int lm_phase_times(lm_handle h, float *ms_out)
     if (!h || !ms_out) return LM_EINVAL;
     if (!h->timed) return LM_ESTATE;
     LM_CUDA(cudaSetDevice(h->device));
-    LM_CUDA(cudaEventSynchronize(h->ev_phase[4]));
-    for (int k = 0; k < 4; ++k) LM_CUDA(cudaEventElapsedTime(ms_out + k, h->ev_phase[k], h->ev_phase[k + 1]));
+    LM_CUDA(cudaEventSynchronize(h->ev_phase[5]));
+    for (int k = 0; k < 5; ++k) LM_CUDA(cudaEventElapsedTime(ms_out + k, h->ev_phase[k], h->ev_phase[k + 1]));
     return LM_OK;
 }
 

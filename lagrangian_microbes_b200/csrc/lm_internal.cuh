@@ -88,7 +88,7 @@ struct lm_handle_s {
     int8_t *stage_sp[2];
     cudaStream_t copy_stream;
     cudaEvent_t ev_scatter[2], ev_copied[2];
-    cudaEvent_t ev_phase[5];   // LM_STEP_TIMING: step start | advect done | bin done | pairs done | stats done
+    cudaEvent_t ev_phase[6];   // LM_STEP_TIMING: step start | advect done | bin done | pair search done | RPS done | stats done
     bool timed;
     int stage_idx;
     int64_t launches;

@@ -189,9 +189,13 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
     unsigned long long mask = 0;
     unsigned int cnt[5], tot;
     if (!warp_big) {
+        int b = beg0;
+        unsigned long long bit = 1ull;
         for (int i = 0; i < ntot; ++i) {
-            const int b = (i < n1) ? beg0 + i : begNW + (i - n1);
-            if (within(A, xa, ya, b)) mask |= 1ull << i;
+            if (i == n1) b = begNW;
+            if (within(A, xa, ya, b)) mask |= bit;
+            ++b;
+            bit <<= 1;
         }
         const unsigned int p1 = __popcll(mask & bits_below(t1)), p2 = __popcll(mask & bits_below(n1));
         const unsigned int p3 = __popcll(mask & bits_below(t3)), p4 = __popcll(mask & bits_below(t4));

@@ -259,8 +259,9 @@ class Engine:
         check(self.L.lm_reset_stats(self.h, self._stream()), "lm_reset_stats")
 
     def phase_times(self):
-        """[advect, bin, pairs+rps, stats] device milliseconds of the last step run with LM_STEP_TIMING."""
-        ms = (ctypes.c_float * 4)()
+        """[advect, bin, pair search, RPS resolution, stats] device milliseconds of the last step run with
+        LM_STEP_TIMING."""
+        ms = (ctypes.c_float * 5)()
         check(self.L.lm_phase_times(self.h, ms), "lm_phase_times")
         return list(ms)
 
