@@ -188,7 +188,7 @@ class StripSet:
     def __init__(self, transport, lons, lats, species, ids, n_total, radius, pRS, pPR, pSP, fieldset, dt_seconds=3600.0,
                  Kh=0.0, seed=0, emit_pairs=True, pairs_per_particle=8, slack=1.3, send_cap=None, ghost_cap=None,
                  grid_margin=0.5, cells_per_particle=2.0, local_strips=None, device=None, interact=True, advect=True,
-                 rebalance_every=0, stream_field=False):
+                 rebalance_every=0, stream_field=False, regrid_every=16, cells_headroom=1.5):
         from .particle_advecter import StageClock
         self.transport = transport
         G = transport.n_strips
@@ -204,6 +204,9 @@ class StripSet:
         self.advect = bool(advect)
         self.emit_pairs = bool(emit_pairs) and self.interact
         self.rebalance_every = int(rebalance_every)
+        self.regrid_every = int(regrid_every)
+        self.grid_margin = float(grid_margin)
+        self.cells_per_particle = float(cells_per_particle)
         # which strips this process holds; lons/lats/... are then lists, one entry per local strip
         if local_strips is None:
             local_strips = [transport.rank]
@@ -230,7 +233,8 @@ class StripSet:
             raise ValueError("the cell grid has %d rows: too few for %d strips" % (g.ncy, G))
         # rows a strip may own: room for the balanced share with the same slack as the particles
         self.max_rows = min(g.ncy, max(4, int(slack * math.ceil(g.ncy / float(G))) + 2))
-        self.max_cells = (self.max_rows + 1) * g.ncx
+        self.max_cells = int(cells_headroom * (self.max_rows + 1) * g.ncx)      # room for re-fitted grids
+        self._bbox = (x0, x1, y0, y1)
         row_density = self.n_total / float(g.ncy)
         self.ghost_cap = int(ghost_cap if ghost_cap is not None else max(4096, 4 * row_density))
         self.send_cap = int(send_cap if send_cap is not None else max(4096, 8 * row_density))
@@ -248,7 +252,7 @@ class StripSet:
         for k, idx in enumerate(self.local):
             eng = Engine(max_particles=self.max_particles + self.ghost_cap, max_cells=self.max_cells,
                          max_pairs=pair_cap if self.interact else 0, device=device)
-            eng.strip_alloc(self.send_cap, self.ghost_cap, g.ncx)
+            eng.strip_alloc(self.send_cap, self.ghost_cap, int(cells_headroom * g.ncx) + 8)
             eng.set_grid(g)
             if fieldset is not None and not stream_field:
                 eng.set_field(*fieldset.to_device(eng.device))
@@ -317,6 +321,47 @@ class StripSet:
             if passes > max_passes or stalled > self.n_strips + 2:
                 raise RuntimeError("particles could not be routed to their strips (%d left)" % left)
 
+    def regrid(self, x0, x1, y0, y1):
+        """Re-fit the global cell grid to the bounding box (x0, x1, y0, y1) of all particles, keep every strip
+        boundary at (nearly) the latitude it had, and route the particles of the rows that changed hands."""
+        old, old_edges = self.grid, self.edges
+        g = make_grid(x0, x1, y0, y1, self.radius, self.n_total, int(max(4 * self.cells_per_particle * self.n_total, 1 << 20)),
+                      margin=self.grid_margin, cells_per_particle=self.cells_per_particle)
+        G = self.n_strips
+        edges = [0]
+        for k in range(1, G):
+            lat_edge = old.y0 + old_edges[k] / old.inv_h
+            e = 2 * int(round((lat_edge - g.y0) * g.inv_h / 2.0))
+            e = max(edges[-1] + 2, min(e, g.ncy - 2 * (G - k)))
+            edges.append(e - (e & 1))
+        edges.append(g.ncy)
+        rows = max(b - a for a, b in zip(edges[:-1], edges[1:]))
+        if (rows + 1) * g.ncx > self.max_cells or g.ncy < 2 * G:
+            raise RuntimeError("the re-fitted cell grid (%d x %d) does not fit the strips' cell tables" % (g.ncx, g.ncy))
+        self.grid, self.edges, self._bbox = g, edges, (x0, x1, y0, y1)
+        for s in self.strips:
+            s.engine.set_grid(g)
+            s.rows = (edges[s.index], edges[s.index + 1])
+        self.settle()
+        return g
+
+    def _maybe_regrid(self, stats):
+        """Same policy as FusedSimulation._maybe_regrid, on the bounding box of ALL strips."""
+        big = 1e30
+        box = [[-st.bbox[0] if st.n_particles else -big, st.bbox[1] if st.n_particles else -big,
+                -st.bbox[2] if st.n_particles else -big, st.bbox[3] if st.n_particles else -big] for st in stats]
+        m = self.transport.all_max(box)
+        x0, x1, y0, y1 = -m[0], m[1], -m[2], m[3]
+        bx0, bx1, by0, by1 = self._bbox
+        mg = self.grid_margin
+        guard = 0.25 * mg
+        grew = (x0 < bx0 - mg + guard) or (x1 > bx1 + mg - guard) or (y0 < by0 - mg + guard) or (y1 > by1 + mg - guard)
+        shrank = (x1 - x0 + 2 * mg) * (y1 - y0 + 2 * mg) < 0.5 * (bx1 - bx0 + 2 * mg) * (by1 - by0 + 2 * mg)
+        if grew or shrank:
+            self.regrid(x0, x1, y0, y1)
+            return True
+        return False
+
     def rebalance(self):
         """Re-cut the strips from the current per-row particle counts (read from the device cell tables) and
         route the particles of the rows that changed hands."""
@@ -358,14 +403,17 @@ class StripSet:
             flags |= _lib.LM_STEP_INTERACT
         if self.emit_pairs:
             flags |= _lib.LM_STEP_EMIT_PAIRS
-        if check:
+        regrid_now = self.regrid_every > 0 and self.iteration % self.regrid_every == 0
+        if check or regrid_now:
             flags |= _lib.LM_STEP_STATS
         self._staged(flags, st_times)
         if win is not None:
             self.streamer.release(win)
         out = None
-        if check:
+        if check or regrid_now:
             out = self.stats()
+            if regrid_now:
+                self._maybe_regrid(out)
         if self.rebalance_every > 0 and self.iteration % self.rebalance_every == 0:
             self.rebalance()
         return out

@@ -45,11 +45,12 @@ def particles(n, seed, clustered=False):
     return lon.astype(np.float32), lat.astype(np.float32), sp
 
 
-def single(lon, lat, sp, grid, fs, seed, Kh=0.0):
+def single(lon, lat, sp, grid, fs, seed, Kh=0.0, regrid_every=0, grid_margin=0.5):
     """The single-handle reference run on the SAME grid as the strips."""
     from lagrangian_microbes_b200.simulation import FusedSimulation
     sim = FusedSimulation(lon, lat, sp, R, *P, fs, dt_seconds=3600.0, Kh=Kh, seed=seed, emit_pairs=True,
-                          pair_capacity=40 * lon.size, regrid_every=0, max_cells=max(1 << 20, 2 * grid.ncx * grid.ncy))
+                          pair_capacity=40 * lon.size, regrid_every=regrid_every, grid_margin=grid_margin,
+                          max_cells=max(1 << 20, 4 * grid.ncx * grid.ncy))
     sim.engine.set_grid(grid)
     sim.grid = grid
     sim.engine.state_set(torch.from_numpy(lon).cuda(), torch.from_numpy(lat).cuda(), torch.from_numpy(sp).cuda())
@@ -85,7 +86,7 @@ def test_strips_on_one_device_equal_single_handle(G, clustered):
     cut = [slice(g * per, (g + 1) * per if g < G - 1 else n) for g in range(G)]
     ss = StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
                   [ids[c] for c in cut], n, R, *P, fs, seed=seed, local_strips=list(range(G)), slack=3.0,
-                  pairs_per_particle=40 * G, grid_margin=0.25)     # a dense blob puts most pairs into one strip
+                  pairs_per_particle=40 * G, grid_margin=0.25, regrid_every=0)     # a dense blob puts most pairs into one strip
     assert all(e % 2 == 0 for e in ss.edges[:-1]) and ss.edges[-1] == ss.grid.ncy
     sim = single(lon, lat, sp, ss.grid, fs, seed)
     total, moved = 0, 0
@@ -115,6 +116,29 @@ def test_strips_with_diffusion_and_rebalancing():
     sizes = [s.engine.state_size() for s in ss.strips]
     print("edges %s -> %s, strip sizes %s" % (edges0, ss.edges, sizes))
     assert max(sizes) < 1.5 * n / G                          # rebalancing keeps the strips level
+    ss.close()
+
+
+def test_strips_regrid_with_the_single_handle():
+    """A tight grid (margin 0.03 degrees) that has to be re-fitted as the cloud moves: strips and single handle
+    follow the same policy, must pick the same grids at the same steps and stay bit-identical."""
+    from lagrangian_microbes_b200.strips import LocalTransport, StripSet
+    G, n, seed = 3, 30000, 8
+    fs = small_fs()
+    lon, lat, sp = particles(n, seed)
+    ids = np.arange(n, dtype=np.int32)
+    cut = [slice(g, n, G) for g in range(G)]
+    ss = StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
+                  [ids[c] for c in cut], n, R, *P, fs, seed=seed, local_strips=list(range(G)), slack=3.0,
+                  pairs_per_particle=40, grid_margin=0.03, regrid_every=2, cells_headroom=3.0)
+    sim = single(lon, lat, sp, ss.grid, fs, seed, regrid_every=2, grid_margin=0.03)
+    grids = set()
+    for step in range(12):
+        assert ss.grid.as_dict() == sim.grid.as_dict(), "grids diverged before step %d" % step
+        grids.add(tuple(sorted(ss.grid.as_dict().items())))
+        compare_step(ss, sim, step)
+    print("%d different grids in 12 steps" % len(grids))
+    assert len(grids) >= 2
     ss.close()
 
 
