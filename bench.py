@@ -222,6 +222,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="microbes in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--resolve-upl", type=int, default=0, help="LM_OPT_RESOLVE_UPL (tuning experiments)")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
 
@@ -317,6 +318,9 @@ def main():
                                regrid_every=16, grid_margin=0.5, stream_field=stream_field)
 
     sim = new_sim(False)
+    if args.resolve_upl:
+        from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_UPL
+        sim.engine.set_option(LM_OPT_RESOLVE_UPL, args.resolve_upl)
     spinup = args.spinup if args.spinup >= 0 else (1500 if args.workload == "config2" else 0)
     for _ in range(spinup):
         sim.step()

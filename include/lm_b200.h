@@ -211,6 +211,9 @@ int lm_reset_stats(lm_handle h, void *stream);
  *   LM_OPT_FIND_PATH  0 = auto; 1 = every warp of the pair search takes the two-pass path that is normally
  *                   reserved for dense clusters (more than 64 candidate partners for one microbe). */
 #define LM_OPT_FIND_PATH 2
+/*   LM_OPT_RESOLVE_UPL  units (cell x direction) per lane in the RPS resolver: 0 = auto (as many as keeps the GPU
+ *                   full of warps), or 1, 2, 4, 8. */
+#define LM_OPT_RESOLVE_UPL 3
 int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Number of kernels this library launched since the handle was created. */
 int64_t lm_launch_count(lm_handle h);

@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 LM_OK, LM_EINVAL, LM_ENOMEM, LM_ECUDA, LM_ENOSPC, LM_ESTATE, LM_ENOCONV = 0, -1, -2, -3, -4, -5, -6
 LM_STEP_ADVECT, LM_STEP_DIFFUSE, LM_STEP_INTERACT, LM_STEP_EMIT_PAIRS, LM_STEP_STATS = 1, 2, 4, 8, 16
 LM_STEP_TIMING = 32
-LM_OPT_FIND_PATH = 2
+LM_OPT_FIND_PATH, LM_OPT_RESOLVE_UPL = 2, 3
 
 
 class LmError(RuntimeError):

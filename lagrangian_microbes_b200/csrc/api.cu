@@ -684,6 +684,10 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
 {
     if (!h) return LM_EINVAL;
     switch (option) {
+        case LM_OPT_RESOLVE_UPL:
+            if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return LM_EINVAL;
+            h->resolve_upl = (int)value;
+            return LM_OK;
         case LM_OPT_FIND_PATH:
             if (value < 0 || value > 1) return LM_EINVAL;
             h->find_path = (int)value;

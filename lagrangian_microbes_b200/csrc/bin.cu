@@ -144,23 +144,48 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(int32_t *__res
                                                                   int32_t *__restrict__ cell_cursor, int n_total)
 {
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    const bool full = base + SCAN_ITEMS <= ncells;          // the arrays are 16-byte aligned and base is a multiple of 16
     int v[SCAN_ITEMS];
     int s = 0;
+    if (full) {
+        const int4 *p4 = reinterpret_cast<const int4 *>(cnt + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = (base + k < ncells) ? cnt[base + k] : 0;
-        s += v[k];
+        for (int k = 0; k < SCAN_ITEMS / 4; ++k) {
+            const int4 q = p4[k];
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) v[k] = (base + k < ncells) ? cnt[base + k] : 0;
     }
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) s += v[k];
     int total;
     int run = block_exclusive_scan(s, total) + tile_offsets[blockIdx.x];
+    if (full) {
+        int4 *cs4 = reinterpret_cast<int4 *>(cell_start + base), *cc4 = reinterpret_cast<int4 *>(cell_cursor + base);
+        int4 *z4 = reinterpret_cast<int4 *>(cnt + base);
 #pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (base + k < ncells) {
-            cell_start[base + k] = run;
-            cell_cursor[base + k] = run;
-            cnt[base + k] = 0;
+        for (int k = 0; k < SCAN_ITEMS / 4; ++k) {
+            int4 o;
+            o.x = run; run += v[4 * k];
+            o.y = run; run += v[4 * k + 1];
+            o.z = run; run += v[4 * k + 2];
+            o.w = run; run += v[4 * k + 3];
+            cs4[k] = o;
+            cc4[k] = o;
+            z4[k] = make_int4(0, 0, 0, 0);
         }
-        run += v[k];
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (base + k < ncells) {
+                cell_start[base + k] = run;
+                cell_cursor[base + k] = run;
+                cnt[base + k] = 0;
+            }
+            run += v[k];
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) cell_start[ncells] = n_total;
 }

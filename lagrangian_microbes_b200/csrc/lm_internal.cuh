@@ -78,6 +78,7 @@ struct lm_handle_s {
     uint32_t *hits;        // [max_pairs + 4] hand-off entries (layout: csrc/pairs.cu)
     uint2 *rec;            // [5][max_cells] (first entry, count) of each cell's first segment, per direction
     uint2 *rec2;           // [5][max_particles / 32 + 2] the same for a cell continued at the start of a chunk
+    int resolve_upl;       // LM_OPT_RESOLVE_UPL: units per lane in the resolver (0 = auto)
     int find_path;         // LM_OPT_FIND_PATH: 0 auto | 1 every warp takes the two-pass (dense cluster) path
     // explicit-order resolver workspace
     unsigned long long *head;   // [max_particles]

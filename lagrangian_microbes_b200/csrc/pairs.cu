@@ -181,25 +181,35 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
     // ---- the candidates of a lane: the concatenation of two index ranges (same row: rest of its cell + E;
     // next row: NW, N, NE), i = 0 .. ntot-1.  ONE loop, so a warp iterates max-of-sums, not sum-of-maxes, of
     // its lanes' candidate counts; hits are recorded as bits of a 64-bit mask -- nothing else happens in the
-    // loop.  Warps with a lane of more than 64 candidates (dense clusters) count per direction instead and
+    // loop.  Warps with a lane of more than 128 candidates (dense clusters) count per direction instead and
     // regenerate the hits in a second pass.
     const int n1 = endE - beg0, ntot = n1 + (endNE - begNW);
     const int t1 = sE - beg0, t3 = n1 + (sN - begNW), t4 = n1 + (sNE - begNW);     // first candidate of E | N | NE (NW: n1)
-    const bool warp_big = __any_sync(0xffffffffu, ntot > 64) || A.force_two_pass;
-    unsigned long long mask = 0;
+    const bool warp_big = __any_sync(0xffffffffu, ntot > 128) || A.force_two_pass;
+    unsigned long long mask = 0, mask_hi = 0;                  // hit bits of candidates 0..63 | 64..127
     unsigned int cnt[5], tot;
     if (!warp_big) {
         int b = beg0;
+        const int n_lo = min(ntot, 64);
         unsigned long long bit = 1ull;
-        for (int i = 0; i < ntot; ++i) {
+        for (int i = 0; i < n_lo; ++i) {
             if (i == n1) b = begNW;
             if (within(A, xa, ya, b)) mask |= bit;
             ++b;
             bit <<= 1;
         }
-        const unsigned int p1 = __popcll(mask & bits_below(t1)), p2 = __popcll(mask & bits_below(n1));
-        const unsigned int p3 = __popcll(mask & bits_below(t3)), p4 = __popcll(mask & bits_below(t4));
-        tot = __popcll(mask);
+        bit = 1ull;
+        for (int i = 64; i < ntot; ++i) {
+            if (i == n1) b = begNW;
+            if (within(A, xa, ya, b)) mask_hi |= bit;
+            ++b;
+            bit <<= 1;
+        }
+        const unsigned int p1 = __popcll(mask & bits_below(t1)) + __popcll(mask_hi & bits_below(t1 - 64));
+        const unsigned int p2 = __popcll(mask & bits_below(n1)) + __popcll(mask_hi & bits_below(n1 - 64));
+        const unsigned int p3 = __popcll(mask & bits_below(t3)) + __popcll(mask_hi & bits_below(t3 - 64));
+        const unsigned int p4 = __popcll(mask & bits_below(t4)) + __popcll(mask_hi & bits_below(t4 - 64));
+        tot = __popcll(mask) + __popcll(mask_hi);
         cnt[0] = p1; cnt[1] = p2 - p1; cnt[2] = p3 - p2; cnt[3] = p4 - p3; cnt[4] = tot - p4;
     } else {
         unsigned long long acc0 = 0, acc1 = 0;                 // hit counters, CELL_BITS each: d0 d1 d2 | d3 d4
@@ -294,6 +304,8 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
             unsigned int kk = excl_tot;
             for (unsigned int m = (unsigned int)mask; m; m &= m - 1) s_fill[kk++] = (uint16_t)(lane | ((__ffs((int)m) - 1) << 5));
             for (unsigned int m = (unsigned int)(mask >> 32); m; m &= m - 1) s_fill[kk++] = (uint16_t)(lane | ((__ffs((int)m) + 31) << 5));
+            for (unsigned int m = (unsigned int)mask_hi; m; m &= m - 1) s_fill[kk++] = (uint16_t)(lane | ((__ffs((int)m) + 63) << 5));
+            for (unsigned int m = (unsigned int)(mask_hi >> 32); m; m &= m - 1) s_fill[kk++] = (uint16_t)(lane | ((__ffs((int)m) + 95) << 5));
         }
         __syncwarp();
         for (unsigned int e0 = 0; e0 < wpairs; e0 += 32) {
@@ -347,7 +359,7 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
 enum UnitMode { MODE_SAME = 1, MODE_EAST = 2, MODE_CROSS = 3 };
 
 constexpr int RES_THREADS = 128;
-constexpr int UNITS_PER_LANE = 8;                          // a warp streams 256 consecutive units of one row
+constexpr int MAX_UNITS_PER_LANE = 8;                      // a warp streams up to 256 consecutive units of one row
 
 struct ResolveArgs {
     int8_t *sp;
@@ -359,6 +371,7 @@ struct ResolveArgs {
     unsigned long long cap_words;
     int ncx;
     int units_per_row, warps_per_row;
+    int upl;                 // units per lane: 1, 2, 4 or 8 (fewer when the grid has few cells, to keep enough warps in flight)
     long long n_warps;
     int mode, parity, dir;   // dir in {-1,0,+1} for MODE_CROSS
 };
@@ -451,7 +464,7 @@ __device__ void resolve_unit_warp(const ResolveArgs &A, int cell, int cs0, int c
     __syncwarp();
 }
 
-// One phase.  A warp takes 32 * UNITS_PER_LANE consecutive units of one cell row, lane l the units l, l + 32, ...
+// One phase.  A warp takes 32 * upl (upl = 4 or 8) consecutive units of one cell row, lane l the units l, l + 32, ...
 // Pair counts per unit are heavy-tailed (same-cell units: ~m^2/2 for m microbes in the cell) and most units
 // are short, so "one lane walks one unit" leaves the warp waiting for its longest unit with a handful of lanes
 // active.  Instead, in two warp-uniform stages:
@@ -462,9 +475,10 @@ __device__ void resolve_unit_warp(const ResolveArgs &A, int cell, int cs0, int c
 //   B  the lanes pull units from that list (a shared-memory ticket) and walk their entry streams, one pair
 //      per iteration: all lanes execute the same instruction stream, and a lane that finishes a short unit
 //      takes the next one instead of idling.
-constexpr int HEAD_CAP = 32 * UNITS_PER_LANE;      // at most one head descriptor per unit
+constexpr int HEAD_CAP = 32 * MAX_UNITS_PER_LANE;  // at most one head descriptor per unit
 constexpr int CONT_CAP = 64;                       // descriptors of continuation segments (more: warp path)
 constexpr unsigned int NO_LINK = 0xffffffu;
+template <int BATCH>
 __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs A)
 {
     __shared__ uint4 s_desc_all[RES_THREADS / 32][HEAD_CAP + CONT_CAP];   // x first entry | y count + link << 8 | z first anchor | w partner cell start
@@ -476,20 +490,20 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
     uint4 *s_desc = s_desc_all[threadIdx.x >> 5];
     unsigned int *s_ctr = s_ctr_all[threadIdx.x >> 5];
     const int row = (int)(wid / A.warps_per_row);
-    const int u_base = (int)(wid - (long long)row * A.warps_per_row) * (32 * UNITS_PER_LANE) + lane;
+    const int u_base = (int)(wid - (long long)row * A.warps_per_row) * (32 * A.upl) + lane;
     const int ncx = A.ncx;
     const int cy = (A.mode == MODE_CROSS) ? 2 * row + A.parity : row;
     const int row_cell = cy * ncx;
     if (lane < 4) s_ctr[lane] = 0;
     __syncwarp();
 
-    // ---- stage A: four units at a time, all loads independent and coalesced across the lanes
+    // ---- stage A: BATCH units at a time, all loads independent and coalesced across the lanes
 #pragma unroll 1
-    for (int j0 = 0; j0 < UNITS_PER_LANE; j0 += 4) {
-        int cell[4], other[4];
-        bool on[4];
+    for (int j0 = 0; j0 < A.upl; j0 += BATCH) {
+        int cell[BATCH], other[BATCH];
+        bool on[BATCH];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < BATCH; ++q) {
             const int u = u_base + 32 * (j0 + q);
             on[q] = u < A.units_per_row;
             if (A.mode == MODE_SAME) { cell[q] = row_cell + u; other[q] = cell[q]; }
@@ -500,17 +514,17 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
                 cell[q] = row_cell + u; other[q] = cell[q] + ncx + A.dir;
             }
         }
-        int cs0[4], cs1[4], ob[4];
-        uint2 R[4];
+        int cs0[BATCH], cs1[BATCH], ob[BATCH];
+        uint2 R[BATCH];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < BATCH; ++q) {
             cs0[q] = on[q] ? __ldg(A.cell_start + cell[q]) : 0;
             cs1[q] = on[q] ? __ldg(A.cell_start + cell[q] + 1) : 0;
             ob[q] = on[q] ? __ldg(A.cell_start + other[q]) : 0;
             R[q] = on[q] ? __ldg(A.rec + cell[q]) : make_uint2(0u, 0u);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < BATCH; ++q) {
             bool heavy = false;
             if (on[q] && cs1[q] > cs0[q]) {
                 uint2 r = R[q];
@@ -658,10 +672,19 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
         R.rec = h->rec + (size_t)d_idx * h->max_cells;
         R.rec2 = h->rec2 + (size_t)d_idx * (h->max_particles / 32 + 2);
         if (rows <= 0 || R.units_per_row <= 0) continue;
-        R.warps_per_row = (R.units_per_row + 32 * UNITS_PER_LANE - 1) / (32 * UNITS_PER_LANE);
+        // units per lane, measured on B200 (profiles/): 8 wins on large sparse grids (12.5 M microbes, 5.2 M
+        // cells, 2 pairs per unit: 0.81 vs 0.90 ms), 4 on smaller / denser ones (10 M microbes, 1.2 M cells, 27
+        // pairs per unit: 2.2 vs 3.6 ms) where eight long streams per lane leave too few warps in flight
+        const long long units = rows * R.units_per_row;
+        int upl = units >= 3000000 ? MAX_UNITS_PER_LANE : 4;
+        if (h->resolve_upl == 1 || h->resolve_upl == 2 || h->resolve_upl == 4 || h->resolve_upl == 8) upl = h->resolve_upl;
+        R.upl = upl;
+        R.warps_per_row = (R.units_per_row + 32 * upl - 1) / (32 * upl);
         R.n_warps = rows * R.warps_per_row;
         const long long blocks = (R.n_warps * 32 + RES_THREADS - 1) / RES_THREADS;
-        resolve_phase_kernel<<<(unsigned)blocks, RES_THREADS, 0, s>>>(R);
+        if (upl >= 4) resolve_phase_kernel<4><<<(unsigned)blocks, RES_THREADS, 0, s>>>(R);
+        else if (upl == 2) resolve_phase_kernel<2><<<(unsigned)blocks, RES_THREADS, 0, s>>>(R);
+        else resolve_phase_kernel<1><<<(unsigned)blocks, RES_THREADS, 0, s>>>(R);
         ++h->launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
