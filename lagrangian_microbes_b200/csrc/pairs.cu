@@ -676,7 +676,7 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
         // cells, 2 pairs per unit: 0.81 vs 0.90 ms), 4 on smaller / denser ones (10 M microbes, 1.2 M cells, 27
         // pairs per unit: 2.2 vs 3.6 ms) where eight long streams per lane leave too few warps in flight
         const long long units = rows * R.units_per_row;
-        int upl = units >= 3000000 ? MAX_UNITS_PER_LANE : 4;
+        int upl = units >= 3000000 ? MAX_UNITS_PER_LANE : (units >= 600000 ? 4 : (units >= 300000 ? 2 : 1));   // small grids: keep >= ~5k warps
         if (h->resolve_upl == 1 || h->resolve_upl == 2 || h->resolve_upl == 4 || h->resolve_upl == 8) upl = h->resolve_upl;
         R.upl = upl;
         R.warps_per_row = (R.units_per_row + 32 * upl - 1) / (32 * upl);
