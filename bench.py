@@ -223,6 +223,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--resolve-upl", type=int, default=0, help="LM_OPT_RESOLVE_UPL (tuning experiments)")
+    ap.add_argument("--no-overlap", action="store_true", help="LM_OPT_OVERLAP = 0 (tuning experiments)")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
 
@@ -321,6 +322,9 @@ def main():
     if args.resolve_upl:
         from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_UPL
         sim.engine.set_option(LM_OPT_RESOLVE_UPL, args.resolve_upl)
+    if args.no_overlap:
+        from lagrangian_microbes_b200._lib import LM_OPT_OVERLAP
+        sim.engine.set_option(LM_OPT_OVERLAP, 0)
     spinup = args.spinup if args.spinup >= 0 else (1500 if args.workload == "config2" else 0)
     for _ in range(spinup):
         sim.step()
@@ -340,6 +344,7 @@ def main():
     ev0.record()
     for _ in range(args.steps):
         sim.step()
+    sim.engine.join()                              # the last step's RPS phases run on the library's side stream
     ev1.record()
     barrier()
     wall1 = time.time()

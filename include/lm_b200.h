@@ -214,7 +214,15 @@ int lm_reset_stats(lm_handle h, void *stream);
 /*   LM_OPT_RESOLVE_UPL  units (cell x direction) per lane in the RPS resolver: 0 = auto (as many as keeps the GPU
  *                   full of warps), or 1, 2, 4, 8. */
 #define LM_OPT_RESOLVE_UPL 3
+/*   LM_OPT_OVERLAP    1 (default): on a single handle the RPS phases of a step run on an internal stream and overlap
+ *                   the advection of the next lm_step; every entry point that reads species or the state orders
+ *                   itself after them, lm_join does so explicitly.  0: everything on the caller's stream. */
+#define LM_OPT_OVERLAP 4
 int lm_set_option(lm_handle h, int32_t option, int64_t value);
+/* Make `stream` wait for work of the last lm_step that is still running on the handle's internal stream
+ * (LM_OPT_OVERLAP).  Only needed before the caller reads the resident arrays through pointers obtained earlier,
+ * or before it records an end-of-run timing event. */
+int lm_join(lm_handle h, void *stream);
 /* Number of kernels this library launched since the handle was created. */
 int64_t lm_launch_count(lm_handle h);
 /* Device time of the phases of the last lm_step run with LM_STEP_TIMING (synchronises on it):

@@ -21,7 +21,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 LM_OK, LM_EINVAL, LM_ENOMEM, LM_ECUDA, LM_ENOSPC, LM_ESTATE, LM_ENOCONV = 0, -1, -2, -3, -4, -5, -6
 LM_STEP_ADVECT, LM_STEP_DIFFUSE, LM_STEP_INTERACT, LM_STEP_EMIT_PAIRS, LM_STEP_STATS = 1, 2, 4, 8, 16
 LM_STEP_TIMING = 32
-LM_OPT_FIND_PATH, LM_OPT_RESOLVE_UPL = 2, 3
+LM_OPT_FIND_PATH, LM_OPT_RESOLVE_UPL, LM_OPT_OVERLAP = 2, 3, 4
 
 
 class LmError(RuntimeError):
@@ -139,6 +139,7 @@ def lib():
         "lm_reset_stats": (ctypes.c_int, [vp, vp]),
         "lm_launch_count": (i64, [vp]),
         "lm_set_option": (ctypes.c_int, [vp, i32, i64]),
+        "lm_join": (ctypes.c_int, [vp, vp]),
         "lm_phase_times": (ctypes.c_int, [vp, P(flt)]),
     }
     for name, (res, args) in sig.items():
@@ -154,7 +155,7 @@ EXPORTS = ["lm_version", "lm_error_string", "lm_last_cuda_error", "lm_create", "
            "lm_pair_uniforms", "lm_resolve_rps", "lm_state_set", "lm_state_size", "lm_step", "lm_state_get",
            "lm_state_get_host", "lm_host_copies_sync", "lm_state_view", "lm_sync_stats", "lm_reset_stats", "lm_launch_count",
            "lm_phase_times", "lm_strip_alloc", "lm_set_strip", "lm_strip_buffers_get", "lm_step_move", "lm_step_bin",
-           "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option"]
+           "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option", "lm_join"]
 
 
 def check(code, what):

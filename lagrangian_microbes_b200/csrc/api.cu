@@ -70,7 +70,11 @@ int lm_destroy(lm_handle h)
         if (h->ev_scatter[k]) cudaEventDestroy(h->ev_scatter[k]);
         if (h->ev_copied[k]) cudaEventDestroy(h->ev_copied[k]);
     }
-    cudaFree(h->keys); cudaFree(h->slots); cudaFree(h->cell_count); cudaFree(h->cell_start);
+    cudaFree(h->keys); cudaFree(h->slots); cudaFree(h->cell_count); cudaFree(h->cell_start_buf[0]); cudaFree(h->cell_start_buf[1]);
+    cudaFree(h->n_pairs_snap);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_find_done) cudaEventDestroy(h->ev_find_done);
+    if (h->ev_resolve_done) cudaEventDestroy(h->ev_resolve_done);
     cudaFree(h->cell_cursor); cudaFree(h->block_sums); cudaFree(h->ctr); cudaFree(h->head);
     cudaFree(h->pending_cnt);
     cudaFree(h->hits); cudaFree(h->rec); cudaFree(h->rec2);
@@ -109,7 +113,10 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
         ok = ok && dev_alloc(&h->stage_sp[k], max_particles);
     }
     ok = ok && dev_alloc(&h->keys, max_particles) && dev_alloc(&h->slots, max_particles);
-    ok = ok && dev_alloc(&h->cell_count, max_cells) && dev_alloc(&h->cell_start, max_cells + 1);
+    ok = ok && dev_alloc(&h->cell_count, max_cells) && dev_alloc(&h->cell_start_buf[0], max_cells + 1);
+    ok = ok && dev_alloc(&h->cell_start_buf[1], max_cells + 1) && dev_alloc(&h->n_pairs_snap, 1);
+    h->cell_start = h->cell_start_buf[0];
+    h->overlap = 1;
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
     if (max_pairs >= (1ll << 32) - 8) return (delete h, LM_EINVAL);          // 32-bit entry offsets
     ok = ok && dev_alloc(&h->hits, max_pairs + 4);
@@ -118,6 +125,10 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     if (ok) ok = cudaMemset(h->cell_count, 0, (size_t)max_cells * sizeof(int32_t)) == cudaSuccess;
     if (ok) ok = cudaMemset(h->ctr, 0, sizeof(Counters)) == cudaSuccess;
     if (ok) ok = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) ok = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&h->ev_find_done, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&h->ev_resolve_done, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaMemset(h->n_pairs_snap, 0, sizeof(unsigned long long)) == cudaSuccess;
     for (int k = 0; ok && k < 2; ++k) {
         ok = ok && cudaEventCreateWithFlags(&h->ev_scatter[k], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming) == cudaSuccess;
@@ -263,6 +274,17 @@ static int reset_counters(lm_handle h, cudaStream_t s)
     return LM_OK;
 }
 
+// RPS phases of the last step may still be running on the side stream: make `s` wait for them before it
+// touches species / the hand-off / the state.
+static int join_side(lm_handle h, cudaStream_t s)
+{
+    if (h->resolve_pending) {
+        LM_CUDA(cudaStreamWaitEvent(s, h->ev_resolve_done, 0));
+        h->resolve_pending = false;
+    }
+    return LM_OK;
+}
+
 static int check_radius(lm_handle h, double r)
 {
     if (!(r >= 0.0)) return LM_EINVAL;
@@ -308,6 +330,7 @@ int lm_state_set(lm_handle h, const float *lon, const float *lat, const int8_t *
     if (!h->have_grid || h->strip.rows_owned < 1) return LM_ESTATE;
     LM_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = as_stream(stream);
+    { const int rcj = join_side(h, s); if (rcj) return rcj; }
     int rc = reset_counters(h, s);
     if (rc) return rc;
     h->stage = 0;
@@ -423,6 +446,7 @@ int lm_step_move(lm_handle h, int32_t flags, const lm_stage_times *st, float dt,
     const int n = (int)h->n;
     int rc = reset_counters(h, s);
     if (rc) return rc;
+    if (in_strip_mode(h)) { rc = join_side(h, s); if (rc) return rc; }     // leavers are packed with their species
     const int c = h->cur;
     bool moved = false;
     const bool timing = (flags & LM_STEP_TIMING) != 0;
@@ -461,6 +485,8 @@ int lm_step_bin(lm_handle h, void *stream)
     cudaStream_t s = as_stream(stream);
     int c = h->cur;
     if (h->step_moved) {
+        // the re-binning gathers species: the previous step's RPS phases must be done
+        { const int rcj = join_side(h, s); if (rcj) return rcj; }
         int n_in = (int)h->n, n_out = (int)h->n;
         h->n_moved_in = h->n_moved_out = 0;
         if (in_strip_mode(h)) {
@@ -510,6 +536,7 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
     if (h->stage != 2) return LM_ESTATE;
     LM_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = as_stream(stream);
+    { const int rcj = join_side(h, s); if (rcj) return rcj; }
     const int c = h->cur, n = (int)h->n;
     const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
     if (h->has_north && interact) LM_CUDA(launch_ghost_unpack(h, h->lon[c], h->lat[c], h->id[c], n, s));
@@ -522,8 +549,19 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
         LM_CUDA(launch_find(h, h->lon[c], h->lat[c], h->id[c], n, r, &h->step_rps,
                             emit ? reinterpret_cast<int2 *>(pairs_out) : nullptr, emit ? cap : 0, s));
         h->emit_cap = emit ? cap : -1;
+        LM_CUDA(cudaMemcpyAsync(h->n_pairs_snap, &h->ctr->n_pairs, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
         if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[3], s));
-        if (n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 0, 5, s));
+        // Species never feed back into advection, so on a single handle the nine RPS phases -- latency
+        // bound, half-empty warps -- go to a side stream and run under the issue-bound advection of the NEXT step;
+        // whatever touches species, the hand-off or the state next waits for them (join_side).
+        h->resolve_on_side = h->overlap && !in_strip_mode(h) && !(h->step_flags & (LM_STEP_TIMING | LM_STEP_STATS)) && n > 0;
+        cudaStream_t rs = s;
+        if (h->resolve_on_side) {
+            LM_CUDA(cudaEventRecord(h->ev_find_done, s));
+            LM_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_find_done, 0));
+            rs = h->side_stream;
+        }
+        if (n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 0, 5, rs));
     }
     if (h->has_south && interact) LM_CUDA(launch_row0_species_pack(h, h->sp[c], s));
     h->stage = 3;
@@ -539,7 +577,14 @@ int lm_step_interact_end(lm_handle h, void *stream)
     const int c = h->cur, n = (int)h->n;
     const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
     if (h->has_north && interact) LM_CUDA(launch_ghost_species_unpack(h, h->sp[c], n, s));
-    if (interact && n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, s));
+    if (interact && n > 0) {
+        LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, h->resolve_on_side ? h->side_stream : s));
+        if (h->resolve_on_side) {
+            LM_CUDA(cudaEventRecord(h->ev_resolve_done, h->side_stream));
+            h->resolve_pending = true;
+            h->resolve_on_side = false;
+        }
+    }
     if (h->has_north && interact) LM_CUDA(launch_ghost_species_pack(h, h->sp[c], n, s));
     if (h->step_flags & LM_STEP_TIMING) {
         if (!interact) LM_CUDA(cudaEventRecord(h->ev_phase[3], s));
@@ -595,6 +640,7 @@ int lm_state_get(lm_handle h, float *lon_out, float *lat_out, int8_t *species_ou
     if (!h) return LM_EINVAL;
     LM_CUDA(cudaSetDevice(h->device));
     const int c = h->cur;
+    { const int rcj = join_side(h, as_stream(stream)); if (rcj) return rcj; }
     LM_CUDA(launch_scatter_by_id(h->lon[c], h->lat[c], h->sp[c], h->id[c], (int)h->n, lon_out, lat_out, species_out,
                                  as_stream(stream), &h->launches));
     return LM_OK;
@@ -607,6 +653,7 @@ int lm_state_get_host(lm_handle h, float *lon_host, float *lat_host, int8_t *spe
     cudaStream_t s = as_stream(stream);
     const int c = h->cur, k = h->stage_idx;
     const size_t n = (size_t)h->n;
+    { const int rcj = join_side(h, s); if (rcj) return rcj; }
     // the staging buffers of slot k were last read by the copy issued two calls ago
     LM_CUDA(cudaStreamWaitEvent(s, h->ev_copied[k], 0));
     LM_CUDA(launch_scatter_by_id(h->lon[c], h->lat[c], h->sp[c], h->id[c], (int)n, lon_host ? h->stage_lon[k] : nullptr,
@@ -632,6 +679,10 @@ int lm_host_copies_sync(lm_handle h)
 int lm_state_view(lm_handle h, float **lon, float **lat, int8_t **species, int32_t **ids, int32_t **cell_start)
 {
     if (!h) return LM_EINVAL;
+    if (h->resolve_pending) {            // raw pointers escape: finish the side-stream work on the host side
+        LM_CUDA(cudaEventSynchronize(h->ev_resolve_done));
+        h->resolve_pending = false;
+    }
     const int c = h->cur;
     if (lon) *lon = h->lon[c];
     if (lat) *lat = h->lat[c];
@@ -653,6 +704,7 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
 {
     if (!h) return LM_EINVAL;
     LM_CUDA(cudaSetDevice(h->device));
+    { const int rcj = join_side(h, as_stream(stream)); if (rcj) return rcj; }
     Counters c;
     LM_CUDA(cudaMemcpyAsync(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost, as_stream(stream)));
     LM_CUDA(cudaStreamSynchronize(as_stream(stream)));
@@ -680,6 +732,13 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
 
 int64_t lm_launch_count(lm_handle h) { return h ? h->launches : 0; }
 
+int lm_join(lm_handle h, void *stream)
+{
+    if (!h) return LM_EINVAL;
+    LM_CUDA(cudaSetDevice(h->device));
+    return join_side(h, as_stream(stream));
+}
+
 int lm_set_option(lm_handle h, int32_t option, int64_t value)
 {
     if (!h) return LM_EINVAL;
@@ -687,6 +746,10 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
         case LM_OPT_RESOLVE_UPL:
             if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return LM_EINVAL;
             h->resolve_upl = (int)value;
+            return LM_OK;
+        case LM_OPT_OVERLAP:
+            if (value < 0 || value > 1) return LM_EINVAL;
+            h->overlap = (int)value;
             return LM_OK;
         case LM_OPT_FIND_PATH:
             if (value < 0 || value > 1) return LM_EINVAL;

@@ -243,6 +243,8 @@ cudaError_t launch_bin_finish(lm_handle_s *h, const float *lon, const float *lat
 {
     const int ncells = h->grid.ncx * h->strip.rows_owned;
     const int ntiles = (ncells + SCAN_TILE - 1) / SCAN_TILE;
+    h->cs_idx ^= 1;                                  // the previous table may still be read by pending RPS phases
+    h->cell_start = h->cell_start_buf[h->cs_idx];
     // cell_count is left zeroed by scan_apply (and by lm_create / lm_set_grid)
     scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, s>>>(h->cell_count, ncells, h->block_sums);
     scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, s>>>(h->block_sums, ntiles);

@@ -67,7 +67,10 @@ struct lm_handle_s {
     int32_t *keys;         // [max_particles] cell key of each particle (input order)
     int2 *slots;           // [max_particles] (source index, id) in arbitrary within-cell order
     int32_t *cell_count;   // [max_cells]
-    int32_t *cell_start;   // [max_cells + 1]
+    int32_t *cell_start;   // [max_cells + 1] the current one of cell_start_buf[2] (double-buffered: the RPS phases of step k
+                           //                 may still read theirs while step k+1 builds its own)
+    int32_t *cell_start_buf[2];
+    int cs_idx;
     int32_t *cell_cursor;  // [max_cells]
     int32_t *block_sums;   // [ceil(max_cells / SCAN_TILE) + 1]
     // counters
@@ -78,6 +81,13 @@ struct lm_handle_s {
     uint32_t *hits;        // [max_pairs + 4] hand-off entries (layout: csrc/pairs.cu)
     uint2 *rec;            // [5][max_cells] (first entry, count) of each cell's first segment, per direction
     uint2 *rec2;           // [5][max_particles / 32 + 2] the same for a cell continued at the start of a chunk
+    // RPS phases of step k on a side stream, under the advection of step k+1 (single handle, no strips)
+    cudaStream_t side_stream;
+    cudaEvent_t ev_find_done, ev_resolve_done;
+    bool resolve_pending;  // ev_resolve_done has not been waited for yet
+    bool resolve_on_side;  // this step's phases go to the side stream
+    int overlap;           // LM_OPT_OVERLAP (default 1)
+    unsigned long long *n_pairs_snap;   // device copy of ctr->n_pairs taken after the search (the resolver's overflow guard)
     int resolve_upl;       // LM_OPT_RESOLVE_UPL: units per lane in the resolver (0 = auto)
     int find_path;         // LM_OPT_FIND_PATH: 0 auto | 1 every warp takes the two-pass (dense cluster) path
     // explicit-order resolver workspace

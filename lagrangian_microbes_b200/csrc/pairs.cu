@@ -367,7 +367,7 @@ struct ResolveArgs {
     const uint32_t *__restrict__ hits;
     const uint2 *__restrict__ rec;       // + d * rec_stride already applied
     const uint2 *__restrict__ rec2;      // + d * rec2_stride already applied
-    const Counters *ctr;
+    const unsigned long long *n_pairs;   // pairs found by the search (snapshot: the counters are reset by the next step)
     unsigned long long cap_words;
     int ncx;
     int units_per_row, warps_per_row;
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
 {
     __shared__ uint4 s_desc_all[RES_THREADS / 32][HEAD_CAP + CONT_CAP];   // x first entry | y count + link << 8 | z first anchor | w partner cell start
     __shared__ unsigned int s_ctr_all[RES_THREADS / 32][4];               // heads, continuations, next ticket
-    if (A.ctr->n_pairs > A.cap_words) return;          // the hand-off overflowed: reported by lm_sync_stats
+    if (*A.n_pairs > A.cap_words) return;              // the hand-off overflowed: reported by lm_sync_stats
     const int lane = threadIdx.x & 31;
     const long long wid = ((long long)blockIdx.x * RES_THREADS + threadIdx.x) >> 5;
     if (wid >= A.n_warps) return;                      // warp-uniform
@@ -654,7 +654,7 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
     if (h->rps_cap < 0) return cudaSuccess;
     ResolveArgs R;
     R.sp = sp; R.cell_start = h->cell_start; R.hits = h->hits;
-    R.ctr = h->ctr;
+    R.n_pairs = h->n_pairs_snap;
     R.cap_words = (unsigned long long)h->max_pairs;
     R.ncx = h->grid.ncx;
     const long long ncx = R.ncx, rows_owned = h->strip.rows_owned, rows_local = h->strip.rows_local;

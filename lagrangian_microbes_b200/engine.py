@@ -268,6 +268,10 @@ class Engine:
     def set_option(self, option, value):
         check(self.L.lm_set_option(self.h, int(option), int(value)), "lm_set_option")
 
+    def join(self):
+        """Order the current stream after the RPS phases still running on the handle's internal stream."""
+        check(self.L.lm_join(self.h, self._stream()), "lm_join")
+
     def launch_count(self):
         return int(self.L.lm_launch_count(self.h))
 
