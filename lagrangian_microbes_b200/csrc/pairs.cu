@@ -188,7 +188,21 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
     const bool warp_big = __any_sync(0xffffffffu, ntot > 128) || A.force_two_pass;
     unsigned long long mask = 0, mask_hi = 0;                  // hit bits of candidates 0..63 | 64..127
     unsigned int cnt[5], tot;
-    if (!warp_big) {
+    if (!warp_big && !__any_sync(0xffffffffu, ntot > 64)) {
+        // the common case: every lane of the warp has at most 64 candidates
+        int b = beg0;
+        unsigned long long bit = 1ull;
+        for (int i = 0; i < ntot; ++i) {
+            if (i == n1) b = begNW;
+            if (within(A, xa, ya, b)) mask |= bit;
+            ++b;
+            bit <<= 1;
+        }
+        const unsigned int p1 = __popcll(mask & bits_below(t1)), p2 = __popcll(mask & bits_below(n1));
+        const unsigned int p3 = __popcll(mask & bits_below(t3)), p4 = __popcll(mask & bits_below(t4));
+        tot = __popcll(mask);
+        cnt[0] = p1; cnt[1] = p2 - p1; cnt[2] = p3 - p2; cnt[3] = p4 - p3; cnt[4] = tot - p4;
+    } else if (!warp_big) {
         int b = beg0;
         const int n_lo = min(ntot, 64);
         unsigned long long bit = 1ull;
