@@ -376,9 +376,15 @@ def main():
             sim2.step()
         rec = [(torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(), torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(),
                 torch.empty(n_per_gpu, dtype=torch.int8).pin_memory()) if world == 1 else () for _ in range(2)]
+        def e2e_step(k):
+            if world == 1:
+                sim2.step(record=rec[k & 1])       # record scattered + copied under the step (lm_record_next_step)
+            else:
+                sim2.step()
+                sim2.record_to_host()
+
         for k in range(args.warmup):
-            sim2.step()
-            sim2.record_to_host(*rec[k & 1])
+            e2e_step(k)
         (sim2.ss if world > 1 else sim2.engine).host_copies_sync()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -386,9 +392,8 @@ def main():
         e0.record()
         h2d = 0
         for k in range(args.steps):
-            sim2.step()
+            e2e_step(k)
             h2d += sim2.h2d_bytes_last_step
-            sim2.record_to_host(*rec[k & 1])
         (sim2.ss if world > 1 else sim2.engine).host_copies_sync()
         e1.record()
         barrier()

@@ -195,6 +195,12 @@ int lm_step_finish(lm_handle h, void *stream);
 int lm_state_get(lm_handle h, float *lon_out, float *lat_out, int8_t *species_out, void *stream);
 /* Same, into pinned HOST buffers (device scatter + async D2H on the stream). */
 int lm_state_get_host(lm_handle h, float *lon_host, float *lat_host, int8_t *species_host, void *stream);
+/* The per-step record without holding up the step: the NEXT lm_step also writes, into pinned HOST buffers (any may
+ * be NULL) in particle-id order, the positions after its advection (sent while the pair search runs) and the species
+ * after its interactions (sent while the next step advects) -- what the reference stores per iteration
+ * (particle_advecter.py:233-235, interaction_simulator.py:108-110).  Complete after lm_host_copies_sync; alternate
+ * two sets of buffers.  Single handle only (strips: lm_state_view + the ids). */
+int lm_record_next_step(lm_handle h, float *lon_host, float *lat_host, int8_t *species_host);
 /* Wait for every D2H copy issued by lm_state_get_host (they run on an internal copy stream so
  * that the next step's kernels overlap them; up to two may be in flight). */
 int lm_host_copies_sync(lm_handle h);

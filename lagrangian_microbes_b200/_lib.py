@@ -133,6 +133,7 @@ def lib():
         "lm_step_finish": (ctypes.c_int, [vp, vp]),
         "lm_state_get": (ctypes.c_int, [vp, vp, vp, vp, vp]),
         "lm_state_get_host": (ctypes.c_int, [vp, vp, vp, vp, vp]),
+        "lm_record_next_step": (ctypes.c_int, [vp, vp, vp, vp]),
         "lm_host_copies_sync": (ctypes.c_int, [vp]),
         "lm_state_view": (ctypes.c_int, [vp, P(vp), P(vp), P(vp), P(vp), P(vp)]),
         "lm_sync_stats": (ctypes.c_int, [vp, P(Stats), vp]),
@@ -155,7 +156,7 @@ EXPORTS = ["lm_version", "lm_error_string", "lm_last_cuda_error", "lm_create", "
            "lm_pair_uniforms", "lm_resolve_rps", "lm_state_set", "lm_state_size", "lm_step", "lm_state_get",
            "lm_state_get_host", "lm_host_copies_sync", "lm_state_view", "lm_sync_stats", "lm_reset_stats", "lm_launch_count",
            "lm_phase_times", "lm_strip_alloc", "lm_set_strip", "lm_strip_buffers_get", "lm_step_move", "lm_step_bin",
-           "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option", "lm_join"]
+           "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option", "lm_join", "lm_record_next_step"]
 
 
 def check(code, what):

@@ -75,6 +75,9 @@ int lm_destroy(lm_handle h)
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_find_done) cudaEventDestroy(h->ev_find_done);
     if (h->ev_resolve_done) cudaEventDestroy(h->ev_resolve_done);
+    if (h->ev_pos_ready) cudaEventDestroy(h->ev_pos_ready);
+    if (h->ev_pos_scattered) cudaEventDestroy(h->ev_pos_scattered);
+    if (h->ev_sp_ready) cudaEventDestroy(h->ev_sp_ready);
     cudaFree(h->cell_cursor); cudaFree(h->block_sums); cudaFree(h->ctr); cudaFree(h->head);
     cudaFree(h->pending_cnt);
     cudaFree(h->hits); cudaFree(h->rec); cudaFree(h->rec2);
@@ -128,6 +131,9 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     if (ok) ok = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_find_done, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_resolve_done, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&h->ev_pos_ready, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&h->ev_pos_scattered, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&h->ev_sp_ready, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaMemset(h->n_pairs_snap, 0, sizeof(unsigned long long)) == cudaSuccess;
     for (int k = 0; ok && k < 2; ++k) {
         ok = ok && cudaEventCreateWithFlags(&h->ev_scatter[k], cudaEventDisableTiming) == cudaSuccess;
@@ -331,6 +337,8 @@ int lm_state_set(lm_handle h, const float *lon, const float *lat, const int8_t *
     LM_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = as_stream(stream);
     { const int rcj = join_side(h, s); if (rcj) return rcj; }
+    for (int k = 0; k < 2; ++k) LM_CUDA(cudaStreamWaitEvent(s, h->ev_copied[k], 0));   // records still reading the old state
+    h->pos_scatter_pending = false;
     int rc = reset_counters(h, s);
     if (rc) return rc;
     h->stage = 0;
@@ -447,6 +455,12 @@ int lm_step_move(lm_handle h, int32_t flags, const lm_stage_times *st, float dt,
     int rc = reset_counters(h, s);
     if (rc) return rc;
     if (in_strip_mode(h)) { rc = join_side(h, s); if (rc) return rc; }     // leavers are packed with their species
+    if (h->pos_scatter_pending) {       // the previous step's record still reads the positions this step updates in place
+        LM_CUDA(cudaStreamWaitEvent(s, h->ev_pos_scattered, 0));
+        h->pos_scatter_pending = false;
+    }
+    h->rec_active = h->rec_armed && !in_strip_mode(h);
+    h->rec_armed = false;
     const int c = h->cur;
     bool moved = false;
     const bool timing = (flags & LM_STEP_TIMING) != 0;
@@ -524,6 +538,21 @@ int lm_step_bin(lm_handle h, void *stream)
         h->binned = true;
     }
     if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[2], s));
+    if (h->rec_active) {
+        // positions and ids of this step are final: scatter them to id order and send them to the host on the copy
+        // stream, under the pair search (which only reads them)
+        const int k = h->rec_slot = h->stage_idx;
+        h->stage_idx = k ^ 1;
+        const size_t nn = (size_t)h->n;
+        LM_CUDA(cudaEventRecord(h->ev_pos_ready, s));
+        LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_pos_ready, 0));
+        LM_CUDA(launch_scatter_by_id(h->lon[c], h->lat[c], nullptr, h->id[c], (int)nn, h->rec_lon_host ? h->stage_lon[k] : nullptr,
+                                     h->rec_lat_host ? h->stage_lat[k] : nullptr, nullptr, h->copy_stream, &h->launches));
+        LM_CUDA(cudaEventRecord(h->ev_pos_scattered, h->copy_stream));
+        h->pos_scatter_pending = true;
+        if (h->rec_lon_host) LM_CUDA(cudaMemcpyAsync(h->rec_lon_host, h->stage_lon[k], nn * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (h->rec_lat_host) LM_CUDA(cudaMemcpyAsync(h->rec_lat_host, h->stage_lat[k], nn * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+    }
     // the halo is only needed by (and only sized for) interacting steps; routing passes skip it
     if (h->has_south && (h->step_flags & LM_STEP_INTERACT)) LM_CUDA(launch_ghost_pack(h, h->lon[c], h->lat[c], h->id[c], s));
     h->stage = 2;
@@ -607,6 +636,23 @@ int lm_step_finish(lm_handle h, void *stream)
         LM_CUDA(cudaEventRecord(h->ev_phase[5], s));
         h->timed = true;
     }
+    if (h->rec_active) {
+        // species after this step's interactions (interaction_simulator.py:108-110): after the RPS phases, wherever
+        // they run; the copy stream does not hold up the caller's stream
+        const int k = h->rec_slot;
+        if (h->rec_sp_host) {
+            if (h->resolve_pending) LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_resolve_done, 0));
+            else {
+                LM_CUDA(cudaEventRecord(h->ev_sp_ready, s));
+                LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_sp_ready, 0));
+            }
+            LM_CUDA(launch_scatter_by_id(nullptr, nullptr, h->sp[c], h->id[c], n, nullptr, nullptr, h->stage_sp[k], h->copy_stream,
+                                         &h->launches));
+            LM_CUDA(cudaMemcpyAsync(h->rec_sp_host, h->stage_sp[k], (size_t)n, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+        LM_CUDA(cudaEventRecord(h->ev_copied[k], h->copy_stream));
+        h->rec_active = false;
+    }
     h->stage = 0;
     return LM_OK;
 }
@@ -666,6 +712,15 @@ int lm_state_get_host(lm_handle h, float *lon_host, float *lat_host, int8_t *spe
     if (species_host) LM_CUDA(cudaMemcpyAsync(species_host, h->stage_sp[k], n, cudaMemcpyDeviceToHost, h->copy_stream));
     LM_CUDA(cudaEventRecord(h->ev_copied[k], h->copy_stream));
     h->stage_idx = k ^ 1;
+    return LM_OK;
+}
+
+int lm_record_next_step(lm_handle h, float *lon_host, float *lat_host, int8_t *species_host)
+{
+    if (!h) return LM_EINVAL;
+    if (h->has_south || h->has_north) return LM_ESTATE;      // strips: ids travel with the record, see lm_state_view
+    h->rec_lon_host = lon_host; h->rec_lat_host = lat_host; h->rec_sp_host = species_host;
+    h->rec_armed = lon_host || lat_host || species_host;
     return LM_OK;
 }
 

@@ -102,6 +102,13 @@ struct lm_handle_s {
     cudaEvent_t ev_phase[6];   // LM_STEP_TIMING: step start | advect done | bin done | pair search done | RPS done | stats done
     bool timed;
     int stage_idx;
+    // per-step record requested for the next step (lm_record_next_step): scattered + copied on copy_stream
+    float *rec_lon_host, *rec_lat_host;
+    int8_t *rec_sp_host;
+    bool rec_armed, rec_active;      // armed: next step records; active: this step is recording
+    int rec_slot;
+    cudaEvent_t ev_pos_ready, ev_pos_scattered, ev_sp_ready;
+    bool pos_scatter_pending;        // the in-place advection of the next step must wait for ev_pos_scattered
     int64_t launches;
     // ---- latitude-strip decomposition (lm_strip_alloc / lm_set_strip); all zero for a single GPU
     lm::Strip strip;

@@ -224,6 +224,12 @@ class Engine:
         check(self.L.lm_state_get_host(self.h, _ptr(lon_host), _ptr(lat_host), _ptr(species_host), self._stream()),
               "lm_state_get_host")
 
+    def record_next_step(self, lon_host=None, lat_host=None, species_host=None):
+        """Arm the next ``step`` to write its per-step record into pinned CPU tensors, overlapped with the step."""
+        for t in (lon_host, lat_host, species_host):
+            assert t is None or (not t.is_cuda and t.is_pinned() and t.is_contiguous())
+        check(self.L.lm_record_next_step(self.h, _ptr(lon_host), _ptr(lat_host), _ptr(species_host)), "lm_record_next_step")
+
     def host_copies_sync(self):
         check(self.L.lm_host_copies_sync(self.h), "lm_host_copies_sync")
 

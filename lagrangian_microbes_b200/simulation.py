@@ -151,7 +151,11 @@ class FusedSimulation:
             self._fit_grid(x0, x1, y0, y1)
 
     # ---- stepping ----------------------------------------------------------------------------------
-    def step(self, check=False, timing=False):
+    def step(self, check=False, timing=False, record=None):
+        """One fused step.  ``record`` = (lon, lat, species) pinned CPU tensors: the step's record is written there
+        asynchronously, overlapped with the step (engine.host_copies_sync() before reading)."""
+        if record is not None:
+            self.engine.record_next_step(*record)
         flags = 0
         st_times = None
         win = None

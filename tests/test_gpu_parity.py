@@ -404,6 +404,46 @@ def test_fused_simulation_matches_oracle_loop(engine_factory):
     assert np.bincount(sp_ref, minlength=4)[1:].sum() == n
 
 
+def test_overlapped_record_and_side_stream_phases_match_the_serial_path(engine_factory):
+    """lm_record_next_step (record scattered + copied under the step) and LM_OPT_OVERLAP (RPS phases of step k
+    under the advection of step k+1) against the same run with everything on one stream."""
+    from lagrangian_microbes_b200._lib import LM_OPT_OVERLAP
+    from lagrangian_microbes_b200.simulation import FusedSimulation
+
+    class HostFS:
+        def __init__(self, fs):
+            self.u, self.v, self.lon, self.lat, self.time = fs.u, fs.v, fs.lon, fs.lat, fs.time
+
+        def to_device(self, device):
+            return tuple(torch.from_numpy(a).to(device) for a in (self.u, self.v, self.lon, self.lat))
+
+    g, fs = _small_fs()
+    n = 120000
+    rng = np.random.default_rng(12)
+    lons = (201.0 + 2.0 * rng.random(n)).astype(np.float32)
+    lats = (31.0 + 2.0 * rng.random(n)).astype(np.float32)
+    sp0 = rng.integers(1, 4, n).astype(np.int8)
+    p = (0.55, 0.6, 0.9)
+    sims = []
+    for overlap in (1, 0):
+        sim = FusedSimulation(lons, lats, sp0, 0.01, *p, HostFS(fs), dt_seconds=3600.0, seed=9, emit_pairs=True,
+                              regrid_every=4, grid_margin=0.25)
+        sim.engine.set_option(LM_OPT_OVERLAP, overlap)
+        sims.append(sim)
+    rec = [tuple(torch.empty(n, dtype=dt).pin_memory() for dt in (torch.float32, torch.float32, torch.int8)) for _ in range(2)]
+    for step in range(10):
+        sims[0].step(record=rec[step & 1])
+        sims[1].step()
+        wl, wa, ws = sims[1].download()
+        sims[0].engine.host_copies_sync()
+        r = rec[step & 1]
+        assert np.array_equal(r[0].numpy(), wl) and np.array_equal(r[1].numpy(), wa), "recorded positions, step %d" % step
+        assert np.array_equal(r[2].numpy(), ws), "recorded species, step %d" % step
+    gl, ga, gs = sims[0].download()
+    assert np.array_equal(gl, wl) and np.array_equal(ga, wa) and np.array_equal(gs, ws)
+    assert int((ws != sp0).sum()) > 1000
+
+
 @pytest.mark.parametrize("mode", RESOLVE_MODES)
 def test_interact_rps_dense_clusters_take_the_warp_cooperative_path(engine_factory, mode):
     """Clusters of ~1500 microbes inside one or two cells: candidate pairs per unit >> HEAVY_TESTS, so the
