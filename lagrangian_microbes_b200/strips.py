@@ -79,6 +79,23 @@ def strip_edges(row_counts, n_strips, max_rows=None):
     return edges
 
 
+def remap_edges(old_grid, old_edges, new_grid):
+    """Strip boundaries on a re-fitted grid: every interior boundary keeps (nearly) its latitude, snapped to an
+    even row of the new grid, every strip keeps at least two rows."""
+    G = len(old_edges) - 1
+    if new_grid.ncy < 2 * G:
+        raise ValueError("the cell grid has %d rows: too few for %d strips" % (new_grid.ncy, G))
+    edges = [0]
+    for k in range(1, G):
+        lat_edge = old_grid.y0 + old_edges[k] / old_grid.inv_h
+        e = 2 * int(round((lat_edge - new_grid.y0) * new_grid.inv_h / 2.0))
+        hi = new_grid.ncy - 2 * (G - k)
+        e = max(edges[-1] + 2, min(e, hi - (hi & 1)))
+        edges.append(e)
+    edges.append(new_grid.ncy)
+    return edges
+
+
 # ------------------------------------------------------------------------------------------------------
 # transports
 # ------------------------------------------------------------------------------------------------------
@@ -328,13 +345,7 @@ class StripSet:
         g = make_grid(x0, x1, y0, y1, self.radius, self.n_total, int(max(4 * self.cells_per_particle * self.n_total, 1 << 20)),
                       margin=self.grid_margin, cells_per_particle=self.cells_per_particle)
         G = self.n_strips
-        edges = [0]
-        for k in range(1, G):
-            lat_edge = old.y0 + old_edges[k] / old.inv_h
-            e = 2 * int(round((lat_edge - g.y0) * g.inv_h / 2.0))
-            e = max(edges[-1] + 2, min(e, g.ncy - 2 * (G - k)))
-            edges.append(e - (e & 1))
-        edges.append(g.ncy)
+        edges = remap_edges(old, old_edges, g)
         rows = max(b - a for a, b in zip(edges[:-1], edges[1:]))
         if (rows + 1) * g.ncx > self.max_cells or g.ncy < 2 * G:
             raise RuntimeError("the re-fitted cell grid (%d x %d) does not fit the strips' cell tables" % (g.ncx, g.ncy))

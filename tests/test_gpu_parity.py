@@ -104,6 +104,74 @@ def test_find_pairs_vs_live_ckdtree(engine_factory, n, r, kind):
     assert got.shape == want.shape and np.array_equal(got, want)
 
 
+def test_find_pairs_property_based(engine_factory):
+    """Hypothesis: random clouds (uniform / clustered / duplicated / collinear, any radius) -- the pair set equals
+    cKDTree.query_pairs, for pair search alone and fused with RPS (whose species then equal the oracle's)."""
+    from hypothesis import HealthCheck, given, settings, strategies as st_
+
+    eng = engine_factory(max_particles=4096, max_cells=1 << 20, max_pairs=4_000_000)
+    out = torch.empty((4_000_000, 2), dtype=torch.int32, device="cuda")
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+    @given(n=st_.integers(0, 3000), kind=st_.sampled_from(["uniform", "clustered", "dups", "line"]),
+           r=st_.sampled_from([0.003, 0.01, 0.05, 0.3]), seed=st_.integers(0, 2**31 - 1), coarse=st_.sampled_from([1.0, 0.02]))
+    def check(n, kind, r, seed, coarse):
+        rng = np.random.default_rng(seed)
+        if kind == "uniform":
+            lon, lat = 205 + rng.random(n), 30 + rng.random(n)
+        elif kind == "clustered":
+            c = rng.integers(0, 5, n)
+            lon, lat = 205 + 0.2 * c + rng.normal(0, 0.004, n), 30 + 0.1 * c + rng.normal(0, 0.004, n)
+        elif kind == "dups":
+            base = rng.integers(0, max(n // 3, 1), n)
+            lon, lat = 205 + (base % 37) * 0.007, 30 + (base // 37) * 0.007
+        else:
+            lon, lat = 205 + np.arange(n) * (r / 3.0), np.full(n, 30.25)
+        lon, lat = lon.astype(np.float32), lat.astype(np.float32)
+        want = opairs.query_pairs_reference_array(lon, lat, r)
+        if want.shape[0] > 3_900_000 or n == 0:
+            return
+        grid = auto_grid(eng, lon, lat, r, margin=0.0, cells_per_particle=2.0 * coarse)
+        assert np.array_equal(gpu_pairs(eng, lon, lat, r, cap=want.shape[0] + 8), want)
+        sp0 = rng.integers(0, 4, n).astype(np.int8)
+        species = dev(sp0.copy())
+        eng.interact_rps(dev(lon), dev(lat), species, r, 0.3, 0.6, 0.9, seed % 1000, seed % 7, pairs_out=out)
+        st = eng.sync_stats()
+        assert st.n_pairs == want.shape[0]
+        assert np.array_equal(opairs.sort_pairs(out[:st.n_pairs].cpu().numpy()), want)
+        order, _ = orps.cell_phase_order(want, lon, lat, grid.as_dict())
+        u = philox.pair_uniforms(order[:, 0], order[:, 1], seed % 7, seed % 1000)
+        want_sp, _ = orps.rps_sequential_c(sp0.copy(), order, u, 0.3, 0.6, 0.9)
+        assert np.array_equal(species.cpu().numpy(), want_sp)
+
+    check()
+
+
+def test_dense_uniform_cloud_fills_both_mask_words_and_the_fill_buffer(engine_factory):
+    """~28 microbes per cell: lanes with 65-128 candidates (second mask word), warps with more than 1024 hits
+    (fill buffer overflow) and warps with more than 128 candidates per lane (two-pass path) side by side."""
+    rng = np.random.default_rng(31)
+    n, r = 60000, 0.05
+    side = np.sqrt(n / 11200.0)
+    lon = (205 + side * rng.random(n)).astype(np.float32)
+    lat = (30 + side * rng.random(n)).astype(np.float32)
+    sp0 = rng.integers(1, 4, n).astype(np.int8)
+    want = opairs.query_pairs_reference_array(lon, lat, r)
+    assert want.shape[0] > 2_000_000
+    eng = engine_factory(max_particles=n, max_cells=1 << 20, max_pairs=want.shape[0] + 64)
+    grid = auto_grid(eng, lon, lat, r, margin=0.1)
+    out = torch.empty((want.shape[0] + 64, 2), dtype=torch.int32, device="cuda")
+    species = dev(sp0.copy())
+    eng.interact_rps(dev(lon), dev(lat), species, r, 0.55, 0.55, 0.55, 4, 2, pairs_out=out)
+    st = eng.sync_stats()
+    assert st.n_pairs == want.shape[0]
+    assert np.array_equal(opairs.sort_pairs(out[:st.n_pairs].cpu().numpy()), want)
+    order, _ = orps.cell_phase_order(want, lon, lat, grid.as_dict())
+    u = philox.pair_uniforms(order[:, 0], order[:, 1], 2, 4)
+    want_sp, _ = orps.rps_sequential_c(sp0.copy(), order, u, 0.55, 0.55, 0.55)
+    assert np.array_equal(species.cpu().numpy(), want_sp)
+
+
 def test_pairs_outside_grid_are_clamped_not_lost(engine_factory):
     rng = np.random.default_rng(5)
     n = 20000

@@ -44,6 +44,26 @@ def test_strip_edges_are_even_balanced_and_cover_all_rows():
     assert max(b - a for a, b in zip(e[:-1], e[1:])) <= 24
 
 
+def test_remap_edges_keeps_latitudes_even_rows_and_room_for_every_strip():
+    from lagrangian_microbes_b200.engine import make_grid
+    from lagrangian_microbes_b200.strips import remap_edges, strip_edges
+    old = make_grid(200.0, 210.0, 20.0, 40.0, 0.01, 4_000_000, 1 << 24)
+    edges = strip_edges(np.full(old.ncy, 10), 8)
+    for box in ((200.5, 211.0, 21.0, 41.5), (199.0, 209.0, 18.5, 38.0), (200.0, 210.0, 20.0, 40.0)):
+        for r in (0.01, 0.02):
+            new = make_grid(*box, r, 4_000_000, 1 << 24)
+            e = remap_edges(old, edges, new)
+            assert e[0] == 0 and e[-1] == new.ncy and len(e) == 9
+            assert all(x % 2 == 0 for x in e[:-1]) and all(b - a >= 2 for a, b in zip(e[:-1], e[1:]))
+            lat_old = [old.y0 + k / old.inv_h for k in edges[1:-1]]
+            lat_new = [new.y0 + k / new.inv_h for k in e[1:-1]]
+            inside = [(a, b) for a, b in zip(lat_old, lat_new) if new.y0 + 4 / new.inv_h < a < new.y0 + (new.ncy - 4) / new.inv_h]
+            assert inside and all(abs(a - b) <= 1.01 / new.inv_h for a, b in inside)       # within one (even) row
+    tiny = make_grid(200.0, 200.01, 20.0, 20.01, 0.01, 100, 1 << 16, margin=0.0)
+    with pytest.raises(ValueError):
+        remap_edges(old, edges, tiny)
+
+
 def test_cell_rows_matches_the_oracle_cell_index():
     from lagrangian_microbes_b200.engine import make_grid
     from lagrangian_microbes_b200.strips import cell_rows
