@@ -578,7 +578,6 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
         LM_CUDA(launch_find(h, h->lon[c], h->lat[c], h->id[c], n, r, &h->step_rps,
                             emit ? reinterpret_cast<int2 *>(pairs_out) : nullptr, emit ? cap : 0, s));
         h->emit_cap = emit ? cap : -1;
-        LM_CUDA(cudaMemcpyAsync(h->n_pairs_snap, &h->ctr->n_pairs, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s));
         if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[3], s));
         // Species never feed back into advection, so on a single handle the nine RPS phases -- latency
         // bound, half-empty warps -- go to a side stream and run under the issue-bound advection of the NEXT step;

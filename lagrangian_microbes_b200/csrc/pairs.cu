@@ -657,7 +657,11 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
         if (emit) find_pairs_kernel<false, true><<<grid, FIND_THREADS, 0, s>>>(F);
         else find_pairs_kernel<false, false><<<grid, FIND_THREADS, 0, s>>>(F);
     }
-    return cudaGetLastError();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    // the resolver's overflow guard reads a snapshot: the counters themselves are reset by the next step while the
+    // phases of this one may still be running on the side stream
+    return cudaMemcpyAsync(h->n_pairs_snap, &h->ctr->n_pairs, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s);
 }
 
 // phases [first, last] of the canonical cell-phase order on the local rows.  Strip boundaries sit on even
