@@ -478,6 +478,89 @@ __device__ void resolve_unit_warp(const ResolveArgs &A, int cell, int cs0, int c
     __syncwarp();
 }
 
+// The same with the species of the unit's particles staged in shared memory: a dense unit is m_a x m_b / 2
+// SEQUENTIAL pairs for one warp, and against global memory every run of 32 of them pays an L2 round trip (config 2
+// in its stirred state: one same-cell unit of a few hundred microbes held up the whole phase for 0.45 ms).  `buf`
+// (cap bytes) is the warp's descriptor buffer, free once stage B is done.  Falls back to the global-memory version
+// when the two cells do not fit.
+__device__ void resolve_unit_warp_staged(const ResolveArgs &A, int cell, int other, int8_t *buf, int cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int cs0 = __ldg(A.cell_start + cell), cs1 = __ldg(A.cell_start + cell + 1);
+    const bool same = cell == other;
+    const int oBeg = same ? cs0 : __ldg(A.cell_start + other), oEnd = same ? cs1 : __ldg(A.cell_start + other + 1);
+    const int m_a = cs1 - cs0, m_b = same ? 0 : oEnd - oBeg;
+    if (m_a + m_b > cap) { resolve_unit_warp(A, cell, cs0, cs1, oBeg); return; }
+    int8_t *s_a = buf, *s_b = same ? buf : buf + m_a;
+    __syncwarp();
+    for (int i = lane; i < m_a; i += 32) s_a[i] = A.sp[cs0 + i];
+    for (int i = lane; i < m_b; i += 32) s_b[i] = A.sp[oBeg + i];
+    __syncwarp();
+    int cur_a = -1, sa = 0, sa0 = 0;
+    int a0 = cs0;
+    uint2 R = __ldg(A.rec + cell);
+    while (true) {
+        const uint32_t *ent = A.hits + R.x;
+        uint32_t en_next = lane < (int)R.y ? __ldg(ent + lane) : 0u;
+        for (unsigned int k0 = 0; k0 < R.y; k0 += 32) {
+            const unsigned int k = k0 + lane;
+            const bool act = k < R.y;
+            const uint32_t en = en_next;
+            en_next = (k + 32 < R.y) ? __ldg(ent + k + 32) : 0u;      // the next chunk is on its way while this one is resolved
+            const int ar = (int)((en >> 24) & 31u);
+            unsigned int todo = __ballot_sync(0xffffffffu, act);
+            while (todo) {
+                const int lead = __ffs(todo) - 1;
+                const int ar0 = __shfl_sync(0xffffffffu, ar, lead);
+                const unsigned int m = __ballot_sync(0xffffffffu, act && ar == ar0) & todo;   // entries are sorted by anchor
+                todo &= ~m;
+                const int a = a0 - cs0 + ar0;                  // index into s_a
+                if (a != cur_a) {
+                    if (cur_a >= 0 && sa != sa0 && lane == 0) s_a[cur_a] = (int8_t)sa;
+                    __syncwarp();
+                    cur_a = a;
+                    sa = sa0 = ((volatile int8_t *)s_a)[a];
+                }
+                if (!is_rps(sa)) continue;                     // winner = None for every pair of this anchor
+                const bool mine = (m >> lane) & 1u;
+                uint32_t M = MAP_ID, dec = 0;
+                int b = 0, sb = 0;
+                if (mine) {
+                    b = (int)(en & B_REL_MASK); dec = en >> 29;   // index into s_b
+                    sb = ((volatile int8_t *)s_b)[b];
+                    if (is_rps(sb)) {
+                        M = 0;
+#pragma unroll
+                        for (int q = 1; q <= 3; ++q) M |= (uint32_t)((q == sb) ? q : rps_apply(q, sb, dec)) << (2 * (q - 1));
+                    }
+                }
+                uint32_t P = M;                                // inclusive scan of maps in lane (= id_b) order
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, P, dd);
+                    if (lane >= dd) P = map_compose(P, t);
+                }
+                uint32_t E = __shfl_up_sync(0xffffffffu, P, 1);
+                if (lane == 0) E = MAP_ID;
+                if (mine && is_rps(sb)) {
+                    const int s_before = (int)map_apply(E, sa);
+                    if (s_before != sb) s_b[b] = (int8_t)rps_apply(s_before, sb, dec);
+                }
+                sa = (int)map_apply(__shfl_sync(0xffffffffu, P, 31), sa);
+                __syncwarp();                                  // partner species written above are visible to later runs
+            }
+        }
+        a0 = (a0 | 31) + 1;                                    // the cell continues in the next 32-particle chunk?
+        if (a0 >= cs1) break;
+        R = __ldg(A.rec2 + (a0 >> 5));
+    }
+    if (cur_a >= 0 && sa != sa0 && lane == 0) s_a[cur_a] = (int8_t)sa;
+    __syncwarp();
+    for (int i = lane; i < m_a; i += 32) A.sp[cs0 + i] = s_a[i];
+    for (int i = lane; i < m_b; i += 32) A.sp[oBeg + i] = s_b[i];
+    __syncwarp();
+}
+
 // One phase.  A warp takes 32 * upl (upl = 4 or 8) consecutive units of one cell row, lane l the units l, l + 32, ...
 // Pair counts per unit are heavy-tailed (same-cell units: ~m^2/2 for m microbes in the cell) and most units
 // are short, so "one lane walks one unit" leaves the warp waiting for its longest unit with a handful of lanes
@@ -492,17 +575,20 @@ __device__ void resolve_unit_warp(const ResolveArgs &A, int cell, int cs0, int c
 constexpr int HEAD_CAP = 32 * MAX_UNITS_PER_LANE;  // at most one head descriptor per unit
 constexpr int CONT_CAP = 64;                       // descriptors of continuation segments (more: warp path)
 constexpr unsigned int NO_LINK = 0xffffffu;
+constexpr int HEAVY_CAP = 16;                      // dense units queued per warp (more: resolved on the spot, against global memory)
 template <int BATCH>
 __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs A)
 {
     __shared__ uint4 s_desc_all[RES_THREADS / 32][HEAD_CAP + CONT_CAP];   // x first entry | y count + link << 8 | z first anchor | w partner cell start
-    __shared__ unsigned int s_ctr_all[RES_THREADS / 32][4];               // heads, continuations, next ticket
+    __shared__ unsigned int s_ctr_all[RES_THREADS / 32][4];               // heads, continuations, next ticket, dense units
+    __shared__ int s_heavy_all[RES_THREADS / 32][2 * HEAVY_CAP];           // (cell, other) of the dense units of this warp
     if (*A.n_pairs > A.cap_words) return;              // the hand-off overflowed: reported by lm_sync_stats
     const int lane = threadIdx.x & 31;
     const long long wid = ((long long)blockIdx.x * RES_THREADS + threadIdx.x) >> 5;
     if (wid >= A.n_warps) return;                      // warp-uniform
     uint4 *s_desc = s_desc_all[threadIdx.x >> 5];
     unsigned int *s_ctr = s_ctr_all[threadIdx.x >> 5];
+    int *s_heavy = s_heavy_all[threadIdx.x >> 5];
     const int row = (int)(wid / A.warps_per_row);
     const int u_base = (int)(wid - (long long)row * A.warps_per_row) * (32 * A.upl) + lane;
     const int ncx = A.ncx;
@@ -564,12 +650,20 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
                 }
                 if (heavy && head_slot >= 0) s_desc[head_slot].y = NO_LINK << 8;      // void what was pushed: the whole unit goes to the warp
             }
+            // dense units wait until stage B is done: then the descriptor buffer is free to stage their species in
             unsigned int hm = __ballot_sync(0xffffffffu, heavy);
             while (hm) {
                 const int src = __ffs(hm) - 1;
                 hm &= hm - 1;
-                resolve_unit_warp(A, __shfl_sync(0xffffffffu, cell[q], src), __shfl_sync(0xffffffffu, cs0[q], src),
-                                  __shfl_sync(0xffffffffu, cs1[q], src), __shfl_sync(0xffffffffu, ob[q], src));
+                const int hc = __shfl_sync(0xffffffffu, cell[q], src), ho = __shfl_sync(0xffffffffu, other[q], src);
+                const unsigned int slot = s_ctr[3];            // warp-uniform
+                if (slot < (unsigned int)HEAVY_CAP) {
+                    if (lane == 0) { s_heavy[2 * slot] = hc; s_heavy[2 * slot + 1] = ho; s_ctr[3] = slot + 1; }
+                    __syncwarp();
+                } else {
+                    resolve_unit_warp(A, hc, __shfl_sync(0xffffffffu, cs0[q], src), __shfl_sync(0xffffffffu, cs1[q], src),
+                                      __shfl_sync(0xffffffffu, ob[q], src));
+                }
             }
         }
     }
@@ -614,6 +708,13 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
         }
     }
     if (cur_a >= 0 && sa != sa0) A.sp[cur_a] = (int8_t)sa;
+
+    // ---- dense units, one after the other, with their species staged in the (now free) descriptor buffer
+    __syncwarp();
+    const unsigned int n_heavy = s_ctr[3];
+    for (unsigned int q = 0; q < n_heavy; ++q)
+        resolve_unit_warp_staged(A, s_heavy[2 * q], s_heavy[2 * q + 1], reinterpret_cast<int8_t *>(s_desc),
+                                 (int)((HEAD_CAP + CONT_CAP) * sizeof(uint4)));
 }
 
 // ---------------------------------------------------------------------------------------------------
