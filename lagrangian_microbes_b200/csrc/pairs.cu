@@ -403,13 +403,22 @@ __device__ __forceinline__ int rps_apply(int s1, int s2, uint32_t dec)
 
 __device__ __forceinline__ bool is_rps(int s) { return s >= 1 && s <= 3; }
 
-// 3->3 maps packed 2 bits per entry: M(s) = (M >> 2(s-1)) & 3
-constexpr uint32_t MAP_ID = 1u | (2u << 2) | (3u << 4);
-__device__ __forceinline__ uint32_t map_apply(uint32_t M, int s) { return (M >> (2 * (s - 1))) & 3u; }
+// 3->3 maps of species, one byte per entry: byte s-1 holds M(s)-1 (byte 3 = 3, unused).  Composition is one PRMT:
+// byte i of compose(second, first) = second[first[i]].
+constexpr uint32_t MAP_ID = 0x03020100u;
+__device__ __forceinline__ int map_apply(uint32_t M, int s) { return (int)((M >> (8 * (s - 1))) & 0xffu) + 1; }
 __device__ __forceinline__ uint32_t map_compose(uint32_t second, uint32_t first)   // s -> second(first(s))
 {
-    return map_apply(second, (int)map_apply(first, 1)) | (map_apply(second, (int)map_apply(first, 2)) << 2) |
-           (map_apply(second, (int)map_apply(first, 3)) << 4);
+    const uint32_t sel = (first & 0xfu) | ((first >> 4) & 0xf0u) | ((first >> 8) & 0xf00u) | 0x3000u;
+    return __byte_perm(second, 0u, sel);
+}
+// the map "interact with a partner of species sb (in 1..3), draw dec"
+__device__ __forceinline__ uint32_t map_of_partner(int sb, uint32_t dec)
+{
+    uint32_t M = 0x03000000u;
+#pragma unroll
+    for (int q = 1; q <= 3; ++q) M |= (uint32_t)(((q == sb) ? q : rps_apply(q, sb, dec)) - 1) << (8 * (q - 1));
+    return M;
 }
 
 // Whole-warp resolution of one unit (all lanes call this with the same arguments): its entry streams, segment
@@ -448,11 +457,7 @@ __device__ void resolve_unit_warp(const ResolveArgs &A, int cell, int cs0, int c
                 if (mine) {
                     b = oBeg + (int)(en & B_REL_MASK); dec = en >> 29;
                     sb = ((volatile int8_t *)A.sp)[b];
-                    if (is_rps(sb)) {
-                        M = 0;
-#pragma unroll
-                        for (int s = 1; s <= 3; ++s) M |= (uint32_t)((s == sb) ? s : rps_apply(s, sb, dec)) << (2 * (s - 1));
-                    }
+                    if (is_rps(sb)) M = map_of_partner(sb, dec);
                 }
                 uint32_t P = M;                                // inclusive scan of maps in lane (= id_b) order
 #pragma unroll
@@ -463,10 +468,10 @@ __device__ void resolve_unit_warp(const ResolveArgs &A, int cell, int cs0, int c
                 uint32_t E = __shfl_up_sync(0xffffffffu, P, 1);
                 if (lane == 0) E = MAP_ID;
                 if (mine && is_rps(sb)) {
-                    const int s_before = (int)map_apply(E, sa);
+                    const int s_before = map_apply(E, sa);
                     if (s_before != sb) A.sp[b] = (int8_t)rps_apply(s_before, sb, dec);
                 }
-                sa = (int)map_apply(__shfl_sync(0xffffffffu, P, 31), sa);
+                sa = map_apply(__shfl_sync(0xffffffffu, P, 31), sa);
                 __syncwarp();                                  // partner species written above are visible to later runs
             }
         }
@@ -528,11 +533,7 @@ __device__ void resolve_unit_warp_staged(const ResolveArgs &A, int cell, int oth
                 if (mine) {
                     b = (int)(en & B_REL_MASK); dec = en >> 29;   // index into s_b
                     sb = ((volatile int8_t *)s_b)[b];
-                    if (is_rps(sb)) {
-                        M = 0;
-#pragma unroll
-                        for (int q = 1; q <= 3; ++q) M |= (uint32_t)((q == sb) ? q : rps_apply(q, sb, dec)) << (2 * (q - 1));
-                    }
+                    if (is_rps(sb)) M = map_of_partner(sb, dec);
                 }
                 uint32_t P = M;                                // inclusive scan of maps in lane (= id_b) order
 #pragma unroll
@@ -543,10 +544,10 @@ __device__ void resolve_unit_warp_staged(const ResolveArgs &A, int cell, int oth
                 uint32_t E = __shfl_up_sync(0xffffffffu, P, 1);
                 if (lane == 0) E = MAP_ID;
                 if (mine && is_rps(sb)) {
-                    const int s_before = (int)map_apply(E, sa);
+                    const int s_before = map_apply(E, sa);
                     if (s_before != sb) s_b[b] = (int8_t)rps_apply(s_before, sb, dec);
                 }
-                sa = (int)map_apply(__shfl_sync(0xffffffffu, P, 31), sa);
+                sa = map_apply(__shfl_sync(0xffffffffu, P, 31), sa);
                 __syncwarp();                                  // partner species written above are visible to later runs
             }
         }
