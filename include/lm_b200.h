@@ -108,6 +108,9 @@ const char *lm_error_string(int code);
 const char *lm_last_cuda_error(void);
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
+/* max_particles < 2^31 (< 2^29 when max_pairs > 0), max_cells < 2^31; max_pairs (< 2^32) sizes the pair-search ->
+ * RPS hand-off (4 B per pair + 40 B per cell of record tables) and may be 0 for a handle that only advects or
+ * only searches.  All device memory of the handle is allocated here. */
 int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cells, int64_t max_pairs);
 int lm_destroy(lm_handle h);
 
@@ -135,7 +138,7 @@ int lm_diffuse(lm_handle h, float *lon, float *lat, int64_t n, double amp_deg, u
 /* (P1/P2) All pairs (i<j, array indices) with dx*dx + dy*dy <= r*r evaluated exactly as SciPy does
  * (float32 positions widened to double).  pairs_out int32[cap][2] in unspecified order;
  * *n_pairs_out (device int64) receives the number found; LM_ENOSPC is reported by
- * lm_sync_stats when it exceeded cap (the first cap pairs are valid). */
+ * lm_sync_stats when it exceeded cap (the list is then incomplete: size it from the reported count and repeat). */
 int lm_find_pairs(lm_handle h, const float *lon, const float *lat, int64_t n, double r,
                   int32_t *pairs_out, int64_t cap, int64_t *n_pairs_out, void *stream);
 /* (P1/P2 + R1/R2) Pair search fused with RPS resolution in the canonical cell-phase order
@@ -154,13 +157,16 @@ int lm_resolve_rps(lm_handle h, const int32_t *pairs, const double *u, int64_t n
                    int64_t n, double pRS, double pPR, double pSP, int32_t *rounds_out /* host */, void *stream);
 
 /* ---- resident pipeline (state owned by the handle, kept in (cell, id) order) ------------------ */
-/* Upload n particles (arrays in id order; ids NULL = 0..n-1; device pointers) and bin them. */
+/* Upload n particles (arrays in id order; ids NULL = 0..n-1; device pointers) and bin them.  On a strip
+ * (lm_set_strip) the particles are only loaded -- ids are then required and global -- and the first step bins
+ * them and sends those that belong to a neighbouring strip on their way. */
 int lm_state_set(lm_handle h, const float *lon, const float *lat, const int8_t *species, const int32_t *ids,
                  int64_t n, void *stream);
 int64_t lm_state_size(lm_handle h);
 /* One fused step k = prm->step:  [diffuse: the kick the reference applies at the end of iteration
  * k-1, keyed (seed, k-1)] -> [advect] -> bin -> pair search + RPS keyed (seed, k) (-> emit pairs).
- * flags: LM_STEP_* below.  st may be NULL when LM_STEP_ADVECT is not set. */
+ * flags: LM_STEP_* below.  st may be NULL when LM_STEP_ADVECT is not set.  Asynchronous; with LM_OPT_OVERLAP
+ * (default) the RPS phases run on an internal stream and later calls order themselves after them. */
 #define LM_STEP_ADVECT 1
 #define LM_STEP_DIFFUSE 2
 #define LM_STEP_INTERACT 4
