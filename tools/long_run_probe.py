@@ -9,6 +9,10 @@ n = bench.default_n(workload)
 lon, lat, sp, _ = bench.workload_particles(workload, n, 0, 1)
 sim = FusedSimulation(lon, lat, sp, 0.01, 0.55, 0.55, 0.55, hfs, dt_seconds=3600.0, seed=0, emit_pairs=True,
                       pair_capacity=(20 if workload == "config3" else 8) * n, regrid_every=16, grid_margin=0.5)
+import os
+if os.environ.get('LM_RESOLVE_UPL'):
+    from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_UPL
+    sim.engine.set_option(LM_OPT_RESOLVE_UPL, int(os.environ['LM_RESOLVE_UPL']))
 done = 0
 while done < total:
     for _ in range(every - 1):
