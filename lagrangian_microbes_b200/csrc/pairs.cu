@@ -53,6 +53,7 @@ namespace lm {
 constexpr int FIND_THREADS = 256;
 constexpr int FIND_WARPS = FIND_THREADS / 32;
 constexpr uint32_t B_REL_MASK = (1u << 24) - 1u;     // entry: b_rel | a_rel << 24 | decision bits << 29
+constexpr unsigned int HEAVY_MIN = 160;              // a segment below this many pairs is never worth a whole warp
 constexpr int CELL_BITS = 21;                        // particles per cell < 2^21 (packed per-direction hit counters)
 
 struct FindArgs {
@@ -573,28 +574,21 @@ __device__ void resolve_unit_warp_staged(const ResolveArgs &A, int cell, int oth
 //      per iteration: all lanes execute the same instruction stream, and a lane that finishes a short unit
 //      takes the next one instead of idling.
 constexpr int HEAD_CAP = 32 * MAX_UNITS_PER_LANE;  // at most one head descriptor per unit
-constexpr int CONT_CAP = 64;                       // descriptors of continuation segments (more: the unit goes to the warp)
-constexpr int DESC_CAP = HEAD_CAP + CONT_CAP;
-constexpr unsigned int NO_LINK = 0xffffu;
-constexpr int HEAVY_CAP = 16;                      // dense units queued per warp (at most ~10 can exceed 3x the fair share)
-constexpr unsigned int HEAVY_MIN = 96;             // a unit below this many pairs is never worth a whole warp
+constexpr int CONT_CAP = 64;                       // descriptors of continuation segments (more: warp path)
+constexpr unsigned int NO_LINK = 0xffffu;            // descriptor .y = count (16 bits) | link << 16
+constexpr int HEAVY_CAP = 16;                      // dense units queued per warp (more: resolved on the spot, against global memory;
+                                                   // with the relative limit at most ~10 segments of a warp can exceed it)
 template <int BATCH>
 __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs A)
 {
-    __shared__ uint4 s_desc_all[RES_THREADS / 32][DESC_CAP];     // x first entry | y count | z first anchor | w partner cell start
-    __shared__ uint16_t s_link_all[RES_THREADS / 32][DESC_CAP];  // next descriptor of the same unit
-    __shared__ unsigned int s_tot_all[RES_THREADS / 32][HEAD_CAP];   // pairs of the unit whose head this is
-    __shared__ int s_cell_all[RES_THREADS / 32][HEAD_CAP];       // its anchor cell
-    __shared__ unsigned int s_ctr_all[RES_THREADS / 32][8];      // heads, continuations, next ticket, dense units, pairs of the warp
-    __shared__ int s_heavy_all[RES_THREADS / 32][HEAVY_CAP];     // head slots of the dense units
+    __shared__ uint4 s_desc_all[RES_THREADS / 32][HEAD_CAP + CONT_CAP];   // x first entry | y count + link << 16 | z first anchor | w partner cell start
+    __shared__ unsigned int s_ctr_all[RES_THREADS / 32][4];               // heads, continuations, next ticket, dense units
+    __shared__ int s_heavy_all[RES_THREADS / 32][2 * HEAVY_CAP];           // (cell, other) of the dense units of this warp
     if (*A.n_pairs > A.cap_words) return;              // the hand-off overflowed: reported by lm_sync_stats
     const int lane = threadIdx.x & 31;
     const long long wid = ((long long)blockIdx.x * RES_THREADS + threadIdx.x) >> 5;
     if (wid >= A.n_warps) return;                      // warp-uniform
     uint4 *s_desc = s_desc_all[threadIdx.x >> 5];
-    uint16_t *s_link = s_link_all[threadIdx.x >> 5];
-    unsigned int *s_tot = s_tot_all[threadIdx.x >> 5];
-    int *s_cell = s_cell_all[threadIdx.x >> 5];
     unsigned int *s_ctr = s_ctr_all[threadIdx.x >> 5];
     int *s_heavy = s_heavy_all[threadIdx.x >> 5];
     const int row = (int)(wid / A.warps_per_row);
@@ -602,25 +596,43 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
     const int ncx = A.ncx;
     const int cy = (A.mode == MODE_CROSS) ? 2 * row + A.parity : row;
     const int row_cell = cy * ncx;
-    const int other_off = (A.mode == MODE_SAME) ? 0 : (A.mode == MODE_EAST ? 1 : ncx + A.dir);
-    if (lane < 8) s_ctr[lane] = 0;
+    if (lane < 4) s_ctr[lane] = 0;
     __syncwarp();
+
+    // ---- how loaded is this warp?  (first segments only: one coalesced 8-byte load per unit, the same lines stage A
+    // reads again.)  A segment is "dense" -- handed to the whole warp -- not when it has many pairs: in a crowded
+    // region every unit has many, the lanes are evenly loaded and walking the streams lane by lane is the efficient
+    // way; but when it has many more than a lane's fair share of this warp's pairs.
+    unsigned int limit;
+    {
+        unsigned int mine = 0;
+        for (int j = 0; j < A.upl; ++j) {
+            const int u = u_base + 32 * j;
+            if (u < A.units_per_row) {
+                const int c = (A.mode == MODE_EAST) ? row_cell + 2 * u + A.parity : row_cell + u;
+                if (__ldg(A.cell_start + c + 1) > __ldg(A.cell_start + c)) mine += __ldg(A.rec + c).y;
+            }
+        }
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, dd);
+        limit = min(max(HEAVY_MIN, 3u * (mine / 32u)), 0xffffu);
+    }
 
     // ---- stage A: BATCH units at a time, all loads independent and coalesced across the lanes
 #pragma unroll 1
     for (int j0 = 0; j0 < A.upl; j0 += BATCH) {
-        int cell[BATCH];
+        int cell[BATCH], other[BATCH];
         bool on[BATCH];
 #pragma unroll
         for (int q = 0; q < BATCH; ++q) {
             const int u = u_base + 32 * (j0 + q);
             on[q] = u < A.units_per_row;
-            if (A.mode == MODE_SAME) cell[q] = row_cell + u;
-            else if (A.mode == MODE_EAST) cell[q] = row_cell + 2 * u + A.parity;
+            if (A.mode == MODE_SAME) { cell[q] = row_cell + u; other[q] = cell[q]; }
+            else if (A.mode == MODE_EAST) { cell[q] = row_cell + 2 * u + A.parity; other[q] = cell[q] + 1; }
             else {
                 const int ox = u + A.dir;
                 on[q] = on[q] && ox >= 0 && ox < ncx;
-                cell[q] = row_cell + u;
+                cell[q] = row_cell + u; other[q] = cell[q] + ncx + A.dir;
             }
         }
         int cs0[BATCH], cs1[BATCH], ob[BATCH];
@@ -629,74 +641,55 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
         for (int q = 0; q < BATCH; ++q) {
             cs0[q] = on[q] ? __ldg(A.cell_start + cell[q]) : 0;
             cs1[q] = on[q] ? __ldg(A.cell_start + cell[q] + 1) : 0;
-            ob[q] = on[q] ? __ldg(A.cell_start + cell[q] + other_off) : 0;
+            ob[q] = on[q] ? __ldg(A.cell_start + other[q]) : 0;
             R[q] = on[q] ? __ldg(A.rec + cell[q]) : make_uint2(0u, 0u);
         }
 #pragma unroll
         for (int q = 0; q < BATCH; ++q) {
+            bool heavy = false;
             if (on[q] && cs1[q] > cs0[q]) {
                 uint2 r = R[q];
                 int a0 = cs0[q];
                 int head_slot = -1, prev_slot = -1;
-                unsigned int total = 0;
-                bool spilled = false;
                 while (true) {
+                    if (r.y > limit) { heavy = true; break; }
                     if (r.y) {
                         int slot;
                         if (head_slot < 0) slot = head_slot = (int)atomicAdd(&s_ctr[0], 1u);          // < HEAD_CAP by construction
                         else {
                             const unsigned int cs = atomicAdd(&s_ctr[1], 1u);
-                            if (cs >= (unsigned int)CONT_CAP) { spilled = true; break; }
+                            if (cs >= (unsigned int)CONT_CAP) { heavy = true; break; }
                             slot = HEAD_CAP + (int)cs;
-                            s_link[prev_slot] = (uint16_t)slot;
+                            s_desc[prev_slot].y = (s_desc[prev_slot].y & 0xffffu) | ((unsigned int)slot << 16);
                         }
-                        s_desc[slot] = make_uint4(r.x, r.y, (unsigned int)a0, (unsigned int)ob[q]);
-                        s_link[slot] = (uint16_t)NO_LINK;
+                        s_desc[slot] = make_uint4(r.x, r.y | (NO_LINK << 16), (unsigned int)a0, (unsigned int)ob[q]);
                         prev_slot = slot;
-                        total += r.y;
                     }
                     a0 = (a0 | 31) + 1;                        // the cell goes on in the next 32-particle chunk?
                     if (a0 >= cs1[q]) break;
                     r = __ldg(A.rec2 + (a0 >> 5));
                 }
-                if (head_slot >= 0) {
-                    s_tot[head_slot] = spilled ? 0xffffffffu : total;      // no room for its descriptors: the warp takes it
-                    s_cell[head_slot] = cell[q];
-                    atomicAdd(&s_ctr[4], total);
+                if (heavy && head_slot >= 0) s_desc[head_slot].y = NO_LINK << 16;      // void what was pushed: the whole unit goes to the warp
+            }
+            // dense units wait until stage B is done: then the descriptor buffer is free to stage their species in
+            unsigned int hm = __ballot_sync(0xffffffffu, heavy);
+            while (hm) {
+                const int src = __ffs(hm) - 1;
+                hm &= hm - 1;
+                const int hc = __shfl_sync(0xffffffffu, cell[q], src), ho = __shfl_sync(0xffffffffu, other[q], src);
+                const unsigned int slot = s_ctr[3];            // warp-uniform
+                if (slot < (unsigned int)HEAVY_CAP) {
+                    if (lane == 0) { s_heavy[2 * slot] = hc; s_heavy[2 * slot + 1] = ho; s_ctr[3] = slot + 1; }
+                    __syncwarp();
+                } else {
+                    resolve_unit_warp(A, hc, __shfl_sync(0xffffffffu, cs0[q], src), __shfl_sync(0xffffffffu, cs1[q], src),
+                                      __shfl_sync(0xffffffffu, ob[q], src));
                 }
             }
         }
     }
     __syncwarp();
     const unsigned int n_heads = s_ctr[0];
-
-    // ---- which units are dense?  Not "many pairs" -- in a crowded region every unit has many, the lanes are evenly
-    // loaded and walking the streams lane by lane is the efficient way -- but "many more than this warp's fair share
-    // per lane": those would leave 31 lanes waiting, so the whole warp resolves them together after stage B.
-    {
-        const unsigned int fair = s_ctr[4] / 32u;
-        const unsigned int limit = max(HEAVY_MIN, 3u * fair);
-        for (unsigned int base = 0; base < n_heads; base += 32) {
-            const unsigned int slot = base + lane;
-            const bool heavy = slot < n_heads && s_tot[slot] > limit;
-            unsigned int hm = __ballot_sync(0xffffffffu, heavy);
-            if (heavy) { s_desc[slot].y = 0; s_link[slot] = (uint16_t)NO_LINK; }       // out of the ticket queue
-            while (hm) {
-                const int src = __ffs(hm) - 1;
-                hm &= hm - 1;
-                const unsigned int hs = base + src;
-                const unsigned int k = s_ctr[3];               // warp-uniform
-                if (k < (unsigned int)HEAVY_CAP) {
-                    if (lane == 0) { s_heavy[k] = (int)hs; s_ctr[3] = k + 1; }
-                    __syncwarp();
-                } else {                                       // cannot happen with limit >= 3 x fair share unless descriptors spilled
-                    const int hc = s_cell[hs];
-                    resolve_unit_warp(A, hc, __ldg(A.cell_start + hc), __ldg(A.cell_start + hc + 1), __ldg(A.cell_start + hc + other_off));
-                }
-            }
-        }
-        __syncwarp();
-    }
 
     // ---- stage B: a lane holds the unit it is walking and the ticket of its next one (whose first sector is
     // already on its way); the two species loads of a pair are issued together.
@@ -716,7 +709,7 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
             }
             if (active) {
                 const uint4 D = s_desc[take];
-                k = D.x; k_end = D.x + D.y; link = s_link[take]; a0 = D.z; oBeg = (int)D.w;
+                k = D.x; k_end = D.x + (D.y & 0xffffu); link = D.y >> 16; a0 = D.z; oBeg = (int)D.w;
             }
         }
         if (active && k < k_end) {
@@ -740,10 +733,9 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
     // ---- dense units, one after the other, with their species staged in the (now free) descriptor buffer
     __syncwarp();
     const unsigned int n_heavy = s_ctr[3];
-    for (unsigned int q = 0; q < n_heavy; ++q) {
-        const int hc = s_cell[s_heavy[q]];
-        resolve_unit_warp_staged(A, hc, hc + other_off, reinterpret_cast<int8_t *>(s_desc), (int)(DESC_CAP * sizeof(uint4)));
-    }
+    for (unsigned int q = 0; q < n_heavy; ++q)
+        resolve_unit_warp_staged(A, s_heavy[2 * q], s_heavy[2 * q + 1], reinterpret_cast<int8_t *>(s_desc),
+                                 (int)((HEAD_CAP + CONT_CAP) * sizeof(uint4)));
 }
 
 // ---------------------------------------------------------------------------------------------------
