@@ -34,7 +34,10 @@ pa.create_netcdf_file(start_time, end_time, dt)
 
 # Create an interaction simulator that uses the rock-paper-scissors pair interaction.
 rps_interaction = rock_paper_scissors(N_microbes=N, pRS=0.5, pPR=0.5, pSP=0.5)
-isim = InteractionSimulator(pair_interaction=rps_interaction, interaction_radius=0.05, output_dir=output_dir)
+# (advection_dir defaults to "." as in the reference, interaction_simulator.py:29: the reference script only works
+# when run from inside output_dir; say where particle_data.nc is.)
+isim = InteractionSimulator(pair_interaction=rps_interaction, interaction_radius=0.05, advection_dir=output_dir,
+                            output_dir=output_dir)
 
 # Simulate the interactions.
 isim.time_step(start_time, end_time, dt)
