@@ -112,7 +112,12 @@ def test_find_pairs_property_based(engine_factory):
     eng = engine_factory(max_particles=4096, max_cells=1 << 20, max_pairs=4_000_000)
     out = torch.empty((4_000_000, 2), dtype=torch.int32, device="cuda")
 
-    @settings(max_examples=40, deadline=None, derandomize=True, database=None, suppress_health_check=list(HealthCheck))
+    # deterministic by default; LM_HYPOTHESIS_EXAMPLES=N runs a randomised campaign of N examples instead
+    import os
+    campaign = int(os.environ.get("LM_HYPOTHESIS_EXAMPLES", "0"))
+
+    @settings(max_examples=campaign or 40, deadline=None, derandomize=not campaign, database=None,
+              suppress_health_check=list(HealthCheck))
     @given(n=st_.integers(0, 3000), kind=st_.sampled_from(["uniform", "clustered", "dups", "line"]),
            r=st_.sampled_from([0.003, 0.01, 0.05, 0.3]), seed=st_.integers(0, 2**31 - 1), coarse=st_.sampled_from([1.0, 0.02]))
     def check(n, kind, r, seed, coarse):
