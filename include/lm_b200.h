@@ -136,7 +136,7 @@ int lm_advect_rk4(lm_handle h, float *lon, float *lat, int64_t n, const lm_stage
 int lm_diffuse(lm_handle h, float *lon, float *lat, int64_t n, double amp_deg, uint64_t seed, uint64_t step,
                void *stream);
 /* (P1/P2) All pairs (i<j, array indices) with dx*dx + dy*dy <= r*r evaluated exactly as SciPy does
- * (float32 positions widened to double).  pairs_out int32[cap][2] in unspecified order;
+ * (float32 positions widened to double; other norms: LM_OPT_NORM).  pairs_out int32[cap][2] in unspecified order;
  * *n_pairs_out (device int64) receives the number found; LM_ENOSPC is reported by
  * lm_sync_stats when it exceeded cap (the list is then incomplete: size it from the reported count and repeat). */
 int lm_find_pairs(lm_handle h, const float *lon, const float *lat, int64_t n, double r,
@@ -230,6 +230,25 @@ int lm_reset_stats(lm_handle h, void *stream);
  *                   the advection of the next lm_step; every entry point that reads species or the state orders
  *                   itself after them, lm_join does so explicitly.  0: everything on the caller's stream. */
 #define LM_OPT_OVERLAP 4
+/*   LM_OPT_NORM       the Minkowski norm of the radius query, query_pairs(r, p=interaction_norm)
+ *                   (interaction_simulator.py:27,98): LM_NORM_2 (default; the only one the reference's scripts use),
+ *                   LM_NORM_1 or LM_NORM_INF, each evaluated exactly as SciPy does for that p:
+ *                       p=2    fl(fl(dx*dx) + fl(dy*dy)) <= fl(r*r)
+ *                       p=1    fl(|dx| + |dy|) <= r
+ *                       p=inf  max(|dx|, |dy|) <= r
+ *                   (dx, dy: differences of the float32 coordinates widened to double).  Other p need pow() and are
+ *                   not offered.  Applies to lm_find_pairs, lm_interact_rps, lm_step and the staged step. */
+#define LM_OPT_NORM 5
+#define LM_NORM_INF 0
+#define LM_NORM_1 1
+#define LM_NORM_2 2
+/*   LM_OPT_RESOLVE_HEAVY_MIN  RPS resolver: a (cell x direction) unit with fewer pairs than this is always walked by one
+ *                   lane, never handed to a whole warp (0 = default, 160). */
+#define LM_OPT_RESOLVE_HEAVY_MIN 6
+/*   LM_OPT_RESOLVE_BATCH  RPS resolver: pairs a lane loads ahead per iteration of its stream walk: 1, 4 (default)
+ *                   or 8.  Results are identical for every value; only the number of dependent memory round trips per
+ *                   unit changes. */
+#define LM_OPT_RESOLVE_BATCH 7
 int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Make `stream` wait for work of the last lm_step that is still running on the handle's internal stream
  * (LM_OPT_OVERLAP).  Only needed before the caller reads the resident arrays through pointers obtained earlier,

@@ -21,7 +21,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 LM_OK, LM_EINVAL, LM_ENOMEM, LM_ECUDA, LM_ENOSPC, LM_ESTATE, LM_ENOCONV = 0, -1, -2, -3, -4, -5, -6
 LM_STEP_ADVECT, LM_STEP_DIFFUSE, LM_STEP_INTERACT, LM_STEP_EMIT_PAIRS, LM_STEP_STATS = 1, 2, 4, 8, 16
 LM_STEP_TIMING = 32
-LM_OPT_FIND_PATH, LM_OPT_RESOLVE_UPL, LM_OPT_OVERLAP = 2, 3, 4
+LM_OPT_FIND_PATH, LM_OPT_RESOLVE_UPL, LM_OPT_OVERLAP, LM_OPT_NORM = 2, 3, 4, 5
+LM_OPT_RESOLVE_HEAVY_MIN, LM_OPT_RESOLVE_BATCH = 6, 7
+LM_NORM_INF, LM_NORM_1, LM_NORM_2 = 0, 1, 2
 
 
 class LmError(RuntimeError):

@@ -120,6 +120,8 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     ok = ok && dev_alloc(&h->cell_start_buf[1], max_cells + 1) && dev_alloc(&h->n_pairs_snap, 1);
     h->cell_start = h->cell_start_buf[0];
     h->overlap = 1;
+    h->norm = LM_NORM_2;
+    h->resolve_batch = 4;      // measured on B200 (profiles/r1y_sweep_resolve.jsonl): 4 beats 1 and 8 on every workload
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
     if (max_pairs >= (1ll << 32) - 8) return (delete h, LM_EINVAL);          // 32-bit entry offsets
     ok = ok && dev_alloc(&h->hits, max_pairs + 4);
@@ -808,6 +810,18 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
         case LM_OPT_FIND_PATH:
             if (value < 0 || value > 1) return LM_EINVAL;
             h->find_path = (int)value;
+            return LM_OK;
+        case LM_OPT_RESOLVE_HEAVY_MIN:
+            if (value < 0 || value > 0xffff) return LM_EINVAL;
+            h->resolve_heavy_min = (int)value;
+            return LM_OK;
+        case LM_OPT_RESOLVE_BATCH:
+            if (value != 1 && value != 4 && value != 8) return LM_EINVAL;
+            h->resolve_batch = (int)value;
+            return LM_OK;
+        case LM_OPT_NORM:
+            if (value != LM_NORM_1 && value != LM_NORM_2 && value != LM_NORM_INF) return LM_EINVAL;
+            h->norm = (int)value;
             return LM_OK;
         default: return LM_EINVAL;
     }

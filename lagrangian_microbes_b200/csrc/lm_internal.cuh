@@ -90,6 +90,9 @@ struct lm_handle_s {
     unsigned long long *n_pairs_snap;   // device copy of ctr->n_pairs taken after the search (the resolver's overflow guard)
     int resolve_upl;       // LM_OPT_RESOLVE_UPL: units per lane in the resolver (0 = auto)
     int find_path;         // LM_OPT_FIND_PATH: 0 auto | 1 every warp takes the two-pass (dense cluster) path
+    int resolve_heavy_min; // LM_OPT_RESOLVE_HEAVY_MIN: 0 = default (160)
+    int resolve_batch;     // LM_OPT_RESOLVE_BATCH: pairs per lane and iteration in the resolver's stream walk (1, 4, 8)
+    int norm;              // LM_OPT_NORM: LM_NORM_2 (default) | LM_NORM_1 | LM_NORM_INF
     // explicit-order resolver workspace
     unsigned long long *head;   // [max_particles]
     int32_t *pending[2];        // [max_pairs] each

@@ -10,6 +10,9 @@
 // A float32 evaluation decides every pair whose squared distance is not within 4e-6 (relative) of
 // r*r; the rest (a ~1e-5 fraction) take the exact double path, so the result is bit-exact while
 // the inner loop stays in fp32.
+// The other Minkowski norms SciPy evaluates without pow() (interaction_norm, interaction_simulator.py:27,98)
+// are template variants of the same kernel (LM_OPT_NORM):  p=1  fl(|dx| + |dy|) <= r,  p=inf  max(|dx|, |dy|) <= r.
+// Every norm with p >= 1 bounds |dx| and |dy| by r, so the same half stencil of cells with edge >= r finds them.
 //
 // Two stages:
 //
@@ -65,8 +68,8 @@ struct FindArgs {
     int row0, rows_owned, rows_local;    // strip geometry (single GPU: 0, ncy, ncy)
     int n;                               // anchors = owned particles (ghost-row particles are partners only)
     int force_two_pass;                  // LM_OPT_FIND_PATH = 1 (tests)
-    float r2_lo, r2_hi;
-    double r2;
+    float r2_lo, r2_hi;                  // float32 pre-filter window around the threshold (r*r for p=2, r for p=1 and p=inf)
+    double r2;                           // the exact threshold
     uint32_t seed_lo, seed_hi, step_lo, step_hi;
     unsigned long long thr[3];           // ceil(p * 2^53) for pRS, pPR, pSP
     uint32_t *__restrict__ hits;
@@ -86,21 +89,24 @@ __device__ __forceinline__ int cell_coord2(float v, double origin, double inv_h,
     return (int)q;
 }
 
-__device__ __forceinline__ bool within_exact(float xa, float ya, float xb, float yb, double r2)
+template <int NORM>
+__device__ __forceinline__ bool within_exact(float xa, float ya, float xb, float yb, double thr)
 {
     const double dx = __dsub_rn((double)xa, (double)xb), dy = __dsub_rn((double)ya, (double)yb);
-    const double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-    return s <= r2;
+    if (NORM == LM_NORM_2) return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= thr;
+    if (NORM == LM_NORM_1) return __dadd_rn(fabs(dx), fabs(dy)) <= thr;
+    return fmax(fabs(dx), fabs(dy)) <= thr;
 }
 
+template <int NORM>
 __device__ __forceinline__ bool within(const FindArgs &A, float xa, float ya, int b)
 {
     const float xb = __ldg(A.lon + b), yb = __ldg(A.lat + b);
     const float dx = xa - xb, dy = ya - yb;
-    const float d2 = fmaf(dx, dx, dy * dy);
+    const float d2 = NORM == LM_NORM_2 ? fmaf(dx, dx, dy * dy) : (NORM == LM_NORM_1 ? fabsf(dx) + fabsf(dy) : fmaxf(fabsf(dx), fabsf(dy)));
     if (d2 > A.r2_hi) return false;
     if (d2 < A.r2_lo) return true;
-    return within_exact(xa, ya, xb, yb, A.r2);
+    return within_exact<NORM>(xa, ya, xb, yb, A.r2);
 }
 
 // three decision bits of the pair's draw: bit k set <=> u < p_k  (k = 0: pRS, 1: pPR, 2: pSP)
@@ -131,7 +137,7 @@ __device__ __forceinline__ unsigned long long bits_below(int t)
 constexpr int FILL_CAP = 1024;       // hits of one warp that the dense finishing stage can take
 constexpr int OWN_WORDS = 12;        // per lane, for the finishing stage: rel[5], base0, sE, begNW, sN, sNE, beg0, n1
 
-template <bool DO_RPS, bool EMIT>
+template <bool DO_RPS, bool EMIT, int NORM>
 __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
 {
     __shared__ uint16_t s_fill_all[FIND_WARPS][FILL_CAP];      // compact hit e of the warp -> owner lane | candidate index << 5
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
         unsigned long long bit = 1ull;
         for (int i = 0; i < ntot; ++i) {
             if (i == n1) b = begNW;
-            if (within(A, xa, ya, b)) mask |= bit;
+            if (within<NORM>(A, xa, ya, b)) mask |= bit;
             ++b;
             bit <<= 1;
         }
@@ -208,14 +214,14 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
         unsigned long long bit = 1ull;
         for (int i = 0; i < n_lo; ++i) {
             if (i == n1) b = begNW;
-            if (within(A, xa, ya, b)) mask |= bit;
+            if (within<NORM>(A, xa, ya, b)) mask |= bit;
             ++b;
             bit <<= 1;
         }
         bit = 1ull;
         for (int i = 64; i < ntot; ++i) {
             if (i == n1) b = begNW;
-            if (within(A, xa, ya, b)) mask_hi |= bit;
+            if (within<NORM>(A, xa, ya, b)) mask_hi |= bit;
             ++b;
             bit <<= 1;
         }
@@ -229,7 +235,7 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
         unsigned long long acc0 = 0, acc1 = 0;                 // hit counters, CELL_BITS each: d0 d1 d2 | d3 d4
         for (int i = 0; i < ntot; ++i) {
             const int b = (i < n1) ? beg0 + i : begNW + (i - n1);
-            if (within(A, xa, ya, b)) {
+            if (within<NORM>(A, xa, ya, b)) {
                 const int d = (i >= t1) + (i >= n1) + (i >= t3) + (i >= t4);
                 if (d < 3) acc0 += 1ull << (CELL_BITS * d); else acc1 += 1ull << (CELL_BITS * (d - 3));
             }
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
         unsigned int kk = 0;
         for (int i = 0; i < ntot; ++i) {
             const int b = (i < n1) ? beg0 + i : begNW + (i - n1);
-            if (within(A, xa, ya, b)) {
+            if (within<NORM>(A, xa, ya, b)) {
                 const int d = (i >= t1) + (i >= n1) + (i >= t3) + (i >= t4);
                 const int ib = __ldg(A.id + b);
                 const int lo = min(my_id, ib), hi = max(my_id, ib);
@@ -388,6 +394,7 @@ struct ResolveArgs {
     int upl;                 // units per lane: 1, 2, 4 or 8 (fewer when the grid has few cells, to keep enough warps in flight)
     long long n_warps;
     int mode, parity, dir;   // dir in {-1,0,+1} for MODE_CROSS
+    unsigned int heavy_min;  // a segment with fewer pairs than this is never handed to the whole warp (LM_OPT_RESOLVE_HEAVY_MIN)
 };
 
 // interactions.py:13-40 for species s1 != s2, both in {1,2,3}: the species both end up with.
@@ -578,7 +585,7 @@ constexpr int CONT_CAP = 64;                       // descriptors of continuatio
 constexpr unsigned int NO_LINK = 0xffffu;            // descriptor .y = count (16 bits) | link << 16
 constexpr int HEAVY_CAP = 16;                      // dense units queued per warp (more: resolved on the spot, against global memory;
                                                    // with the relative limit at most ~10 segments of a warp can exceed it)
-template <int BATCH>
+template <int BATCH, int PB>
 __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs A)
 {
     __shared__ uint4 s_desc_all[RES_THREADS / 32][HEAD_CAP + CONT_CAP];   // x first entry | y count + link << 16 | z first anchor | w partner cell start
@@ -615,7 +622,7 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
         }
 #pragma unroll
         for (int dd = 16; dd > 0; dd >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, dd);
-        limit = min(max(HEAVY_MIN, 3u * (mine / 32u)), 0xffffu);
+        limit = min(max(A.heavy_min, 3u * (mine / 32u)), 0xffffu);
     }
 
     // ---- stage A: BATCH units at a time, all loads independent and coalesced across the lanes
@@ -692,7 +699,15 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
     const unsigned int n_heads = s_ctr[0];
 
     // ---- stage B: a lane holds the unit it is walking and the ticket of its next one (whose first sector is
-    // already on its way); the two species loads of a pair are issued together.
+    // already on its way).  PB == 1: one pair per iteration, the two species loads of a pair issued together.
+    // PB > 1 (LM_OPT_RESOLVE_BATCH): up to PB consecutive pairs of the unit per iteration -- their entries, then all
+    // their species, are loaded before the first of them is resolved, so a unit of m pairs costs ~2 m / PB dependent
+    // memory round trips instead of 2 m (a phase lasts as long as its longest lane-walked unit).  The sequential
+    // semantics are kept by forwarding inside the batch: a species loaded early is replaced when an earlier pair of
+    // the batch rewrote that microbe (same partner b again, or -- same-cell units -- the partner becoming the anchor).
+    // Earlier batches' stores precede these loads in program order, and no pair writes anything but its own b
+    // (the anchor's species lives in a register and is written back when the anchor changes; a retired anchor is
+    // never a partner or an anchor again: entries are sorted by anchor, partners of a same-cell unit lie above it).
     int cur_a = -1, sa = 0, sa0 = 0, oBeg = 0;
     unsigned int k = 0, k_end = 0, a0 = 0, link = NO_LINK;
     unsigned int nxt = atomicAdd(&s_ctr[2], 1u);
@@ -712,20 +727,59 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
                 k = D.x; k_end = D.x + (D.y & 0xffffu); link = D.y >> 16; a0 = D.z; oBeg = (int)D.w;
             }
         }
-        if (active && k < k_end) {
-            const uint32_t en = __ldg(A.hits + k);
-            const int a = (int)a0 + (int)((en >> 24) & 31u), b = oBeg + (int)(en & B_REL_MASK);
-            const bool new_a = a != cur_a;
-            if (new_a && cur_a >= 0 && sa != sa0) A.sp[cur_a] = (int8_t)sa;     // never aliases the two loads below
-            int sa_l = 0;
-            if (new_a) sa_l = A.sp[a];
-            const int sb = A.sp[b];
-            if (new_a) { cur_a = a; sa = sa0 = sa_l; }
-            if (sa != sb && is_rps(sa) && is_rps(sb)) {
-                sa = rps_apply(sa, sb, en >> 29);
-                A.sp[b] = (int8_t)sa;
+        if (PB == 1) {
+            if (active && k < k_end) {
+                const uint32_t en = __ldg(A.hits + k);
+                const int a = (int)a0 + (int)((en >> 24) & 31u), b = oBeg + (int)(en & B_REL_MASK);
+                const bool new_a = a != cur_a;
+                if (new_a && cur_a >= 0 && sa != sa0) A.sp[cur_a] = (int8_t)sa;     // never aliases the two loads below
+                int sa_l = 0;
+                if (new_a) sa_l = A.sp[a];
+                const int sb = A.sp[b];
+                if (new_a) { cur_a = a; sa = sa0 = sa_l; }
+                if (sa != sb && is_rps(sa) && is_rps(sb)) {
+                    sa = rps_apply(sa, sb, en >> 29);
+                    A.sp[b] = (int8_t)sa;
+                }
+                ++k;
             }
-            ++k;
+        } else if (active && k < k_end) {
+            const int nb = min((int)(k_end - k), PB);
+            uint32_t en[PB];
+            int av[PB], bv[PB], sbv[PB], sav[PB];
+#pragma unroll
+            for (int j = 0; j < PB; ++j) en[j] = j < nb ? __ldg(A.hits + k + j) : 0u;
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                av[j] = (int)a0 + (int)((en[j] >> 24) & 31u);
+                bv[j] = oBeg + (int)(en[j] & B_REL_MASK);
+            }
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {                       // every load of the batch before its first store
+                sbv[j] = j < nb ? (int)A.sp[bv[j]] : 0;
+                sav[j] = (j < nb && av[j] != (j == 0 ? cur_a : av[j - 1])) ? (int)A.sp[av[j]] : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                if (j < nb) {
+                    if (av[j] != cur_a) {
+                        if (cur_a >= 0 && sa != sa0) A.sp[cur_a] = (int8_t)sa;
+                        cur_a = av[j]; sa = sa0 = sav[j];
+                    }
+                    int sb = sbv[j];
+                    if (sa != sb && is_rps(sa) && is_rps(sb)) {
+                        sa = rps_apply(sa, sb, en[j] >> 29);
+                        sb = sa;
+                        A.sp[bv[j]] = (int8_t)sa;
+#pragma unroll
+                        for (int i = j + 1; i < PB; ++i) {       // later pairs of the batch that loaded this microbe too early
+                            if (bv[i] == bv[j]) sbv[i] = sb;
+                            if (av[i] == bv[j]) sav[i] = sb;
+                        }
+                    }
+                }
+            }
+            k += (unsigned int)nb;
         }
     }
     if (cur_a >= 0 && sa != sa0) A.sp[cur_a] = (int8_t)sa;
@@ -739,6 +793,18 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
 }
 
 // ---------------------------------------------------------------------------------------------------
+template <int NORM>
+static void launch_find_norm(const FindArgs &F, bool rps, bool emit, int grid, cudaStream_t s)
+{
+    if (rps) {
+        if (emit) find_pairs_kernel<true, true, NORM><<<grid, FIND_THREADS, 0, s>>>(F);
+        else find_pairs_kernel<true, false, NORM><<<grid, FIND_THREADS, 0, s>>>(F);
+    } else {
+        if (emit) find_pairs_kernel<false, true, NORM><<<grid, FIND_THREADS, 0, s>>>(F);
+        else find_pairs_kernel<false, false, NORM><<<grid, FIND_THREADS, 0, s>>>(F);
+    }
+}
+
 cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int n, double r,
                         const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s)
 {
@@ -749,7 +815,7 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
     F.g = h->grid; F.n = n;
     F.force_two_pass = h->find_path == 1 ? 1 : 0;
     F.row0 = h->strip.row0; F.rows_owned = h->strip.rows_owned; F.rows_local = h->strip.rows_local;
-    F.r2 = r * r;
+    F.r2 = h->norm == LM_NORM_2 ? r * r : r;           // SciPy: tub = r*r for p=2, pow(r, 1) for p=1, r for p=inf
     F.r2_lo = (float)(F.r2 * (1.0 - 4e-6));
     F.r2_hi = (float)(F.r2 * (1.0 + 4e-6));
     F.seed_lo = F.seed_hi = F.step_lo = F.step_hi = 0;
@@ -772,18 +838,22 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
     const bool emit = F.cap_pairs > 0;
     const int grid = (n + FIND_THREADS - 1) / FIND_THREADS;
     ++h->launches;
-    if (rps) {
-        if (emit) find_pairs_kernel<true, true><<<grid, FIND_THREADS, 0, s>>>(F);
-        else find_pairs_kernel<true, false><<<grid, FIND_THREADS, 0, s>>>(F);
-    } else {
-        if (emit) find_pairs_kernel<false, true><<<grid, FIND_THREADS, 0, s>>>(F);
-        else find_pairs_kernel<false, false><<<grid, FIND_THREADS, 0, s>>>(F);
-    }
+    if (h->norm == LM_NORM_1) launch_find_norm<LM_NORM_1>(F, rps != nullptr, emit, grid, s);
+    else if (h->norm == LM_NORM_INF) launch_find_norm<LM_NORM_INF>(F, rps != nullptr, emit, grid, s);
+    else launch_find_norm<LM_NORM_2>(F, rps != nullptr, emit, grid, s);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     // the resolver's overflow guard reads a snapshot: the counters themselves are reset by the next step while the
     // phases of this one may still be running on the side stream
     return cudaMemcpyAsync(h->n_pairs_snap, &h->ctr->n_pairs, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s);
+}
+
+template <int PB>
+static void launch_resolve_pb(const ResolveArgs &R, int upl, unsigned int blocks, cudaStream_t s)
+{
+    if (upl >= 4) resolve_phase_kernel<4, PB><<<blocks, RES_THREADS, 0, s>>>(R);
+    else if (upl == 2) resolve_phase_kernel<2, PB><<<blocks, RES_THREADS, 0, s>>>(R);
+    else resolve_phase_kernel<1, PB><<<blocks, RES_THREADS, 0, s>>>(R);
 }
 
 // phases [first, last] of the canonical cell-phase order on the local rows.  Strip boundaries sit on even
@@ -797,6 +867,7 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
     R.n_pairs = h->n_pairs_snap;
     R.cap_words = (unsigned long long)h->max_pairs;
     R.ncx = h->grid.ncx;
+    R.heavy_min = h->resolve_heavy_min > 0 ? (unsigned int)h->resolve_heavy_min : HEAVY_MIN;
     const long long ncx = R.ncx, rows_owned = h->strip.rows_owned, rows_local = h->strip.rows_local;
     for (int ph = first; ph <= last; ++ph) {
         long long rows;
@@ -822,9 +893,10 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
         R.warps_per_row = (R.units_per_row + 32 * upl - 1) / (32 * upl);
         R.n_warps = rows * R.warps_per_row;
         const long long blocks = (R.n_warps * 32 + RES_THREADS - 1) / RES_THREADS;
-        if (upl >= 4) resolve_phase_kernel<4><<<(unsigned)blocks, RES_THREADS, 0, s>>>(R);
-        else if (upl == 2) resolve_phase_kernel<2><<<(unsigned)blocks, RES_THREADS, 0, s>>>(R);
-        else resolve_phase_kernel<1><<<(unsigned)blocks, RES_THREADS, 0, s>>>(R);
+        const int pb = h->resolve_batch;                       // LM_OPT_RESOLVE_BATCH: pairs per stage-B iteration
+        if (pb == 8) launch_resolve_pb<8>(R, upl, (unsigned)blocks, s);
+        else if (pb == 4) launch_resolve_pb<4>(R, upl, (unsigned)blocks, s);
+        else launch_resolve_pb<1>(R, upl, (unsigned)blocks, s);
         ++h->launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -40,6 +40,20 @@ def make_grid(lon_min, lon_max, lat_min, lat_max, radius, n_particles, max_cells
     return Grid(float(x0), float(y0), 1.0 / h, ncx, ncy)
 
 
+def norm_code(p):
+    """LM_NORM_* for the ``p`` of ``cKDTree.query_pairs(r, p)`` (interaction_simulator.py:27,98).  SciPy evaluates
+    p = 1, 2 and infinity with plain adds / multiplies / max, which the device reproduces bit for bit; any other p
+    goes through pow() and is not offered."""
+    if isinstance(p, (int, float, np.integer, np.floating)) and not isinstance(p, bool):
+        if p == 2:
+            return _lib.LM_NORM_2
+        if p == 1:
+            return _lib.LM_NORM_1
+        if p == math.inf:
+            return _lib.LM_NORM_INF
+    raise NotImplementedError("interaction_norm=%r: the device offers the Minkowski norms p = 1, 2 and inf" % (p,))
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
@@ -273,6 +287,10 @@ class Engine:
 
     def set_option(self, option, value):
         check(self.L.lm_set_option(self.h, int(option), int(value)), "lm_set_option")
+
+    def set_norm(self, p):
+        """The Minkowski norm of the radius query: p = 1, 2 (default) or math.inf (``query_pairs(r, p)``)."""
+        self.set_option(_lib.LM_OPT_NORM, norm_code(p))
 
     def join(self):
         """Order the current stream after the RPS phases still running on the handle's internal stream."""

@@ -13,8 +13,9 @@ Philox(seed, step=iteration, i, j) instead of NumPy's global stream (interaction
 
 Only the rock-paper-scissors triple can run on the device; any other ``pair_interaction`` callable
 raises NotImplementedError (arbitrary Python cannot execute in a kernel, and there is no CPU path).
-``interaction_norm`` must be 2 (the only value the reference ever uses); ``self_interaction`` is
-accepted and ignored exactly as in the reference (:28, :49).
+``interaction_norm`` may be 1, 2 (the only value the reference's scripts use) or ``math.inf`` -- the norms
+SciPy evaluates without pow(), reproduced bit for bit (LM_OPT_NORM); ``self_interaction`` is accepted and
+ignored exactly as in the reference (:28, :49).
 """
 import logging
 import os
@@ -50,8 +51,8 @@ class InteractionSimulator:
         if not is_rock_paper_scissors(pair_interaction_function):
             raise NotImplementedError("only the rock_paper_scissors interaction exists as a CUDA kernel; "
                                       "arbitrary Python pair interactions cannot run on the device")
-        if interaction_norm != 2:
-            raise NotImplementedError("interaction_norm=%r: only the Euclidean norm (p=2) is implemented" % (interaction_norm,))
+        from .engine import norm_code
+        norm_code(interaction_norm)          # raises NotImplementedError for any p other than 1, 2, inf
 
         self.microbe_properties = microbe_properties
         self.pair_interaction = pair_interaction_function
@@ -84,6 +85,7 @@ class InteractionSimulator:
             cap = self.pair_capacity if self.pair_capacity is not None else max(32 * N_particles, 1 << 20)
             self._engine = Engine(max_particles=N_particles, max_cells=max(4 * N_particles, 1 << 18), max_pairs=int(cap))
         eng = self._engine
+        eng.set_norm(self.interaction_norm)
         dev = eng.device
         prm = self.pair_interaction_parameters
         r = float(self.interaction_radius)

@@ -76,7 +76,7 @@ class FieldWindowStreamer:
 class FusedSimulation:
     def __init__(self, lons, lats, species, radius, pRS, pPR, pSP, fieldset, dt_seconds=3600.0, Kh=0.0, seed=0,
                  emit_pairs=True, pair_capacity=None, regrid_every=16, grid_margin=0.5, cells_per_particle=2.0,
-                 max_cells=None, device=None, interact=True, advect=True, stream_field=False):
+                 max_cells=None, device=None, interact=True, advect=True, stream_field=False, interaction_norm=2):
         lons = np.ascontiguousarray(lons, dtype=np.float32)      # Parcels keeps float32 positions
         lats = np.ascontiguousarray(lats, dtype=np.float32)
         species = np.ascontiguousarray(species, dtype=np.int8)
@@ -103,6 +103,7 @@ class FusedSimulation:
         # max_pairs sizes the pair-search -> resolver hand-off buffer (4 B per pair per step)
         self.engine = Engine(max_particles=n, max_cells=max_cells, max_pairs=int(pair_capacity) if interact else 0,
                              device=device)
+        self.engine.set_norm(interaction_norm)                   # query_pairs(r, p=interaction_norm)
         dev = self.engine.device
         self.fieldset = fieldset
         self.stream_field = bool(stream_field) and fieldset is not None
@@ -175,7 +176,9 @@ class FusedSimulation:
             flags |= _lib.LM_STEP_INTERACT
         if self.emit_pairs:
             flags |= _lib.LM_STEP_EMIT_PAIRS
-        want_stats = check or (self.regrid_every > 0 and self.iteration % self.regrid_every == 0)
+        # the grid fixes the canonical pair order, so it is re-fitted on a fixed schedule: ``check`` must not change results
+        regrid_now = self.regrid_every > 0 and self.iteration % self.regrid_every == 0
+        want_stats = check or regrid_now
         if want_stats:
             flags |= _lib.LM_STEP_STATS
         self.engine.step(flags, st_times, self.dt, self.diffuse_amp, self.radius, self.rps, self.pairs)
@@ -187,7 +190,8 @@ class FusedSimulation:
             if st.n_out_of_bounds:
                 raise OutOfBoundsError("%d particle(s) left the velocity grid at iteration %d"
                                        % (st.n_out_of_bounds, self.iteration))
-            self._maybe_regrid(st)
+            if regrid_now:
+                self._maybe_regrid(st)
             return st
         return None
 

@@ -205,7 +205,7 @@ class StripSet:
     def __init__(self, transport, lons, lats, species, ids, n_total, radius, pRS, pPR, pSP, fieldset, dt_seconds=3600.0,
                  Kh=0.0, seed=0, emit_pairs=True, pairs_per_particle=8, slack=1.3, send_cap=None, ghost_cap=None,
                  grid_margin=0.5, cells_per_particle=2.0, local_strips=None, device=None, interact=True, advect=True,
-                 rebalance_every=0, stream_field=False, regrid_every=16, cells_headroom=1.5):
+                 rebalance_every=0, stream_field=False, regrid_every=16, cells_headroom=1.5, interaction_norm=2):
         from .particle_advecter import StageClock
         self.transport = transport
         G = transport.n_strips
@@ -270,6 +270,7 @@ class StripSet:
             eng = Engine(max_particles=self.max_particles + self.ghost_cap, max_cells=self.max_cells,
                          max_pairs=pair_cap if self.interact else 0, device=device)
             eng.strip_alloc(self.send_cap, self.ghost_cap, int(cells_headroom * g.ncx) + 8)
+            eng.set_norm(interaction_norm)
             eng.set_grid(g)
             if fieldset is not None and not stream_field:
                 eng.set_field(*fieldset.to_device(eng.device))

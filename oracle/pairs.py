@@ -15,6 +15,12 @@ GPU box, so this is the reference's own third-party implementation, not a port).
 
 (inclusive, i < j, coincident points are pairs) on a uniform cell grid; it is
 checked against cKDTree in tests/test_oracle_pairs.py.
+
+``interaction_norm`` (interaction_simulator.py:27) is handed to SciPy as ``p``.  SciPy 1.2.1 .. 1.18
+(ckdtree/src/rectangle.h, query_pairs.cxx) keeps distances as d**p: the bound is ``r*r`` for p=2,
+``pow(r, 1) = r`` for p=1, ``r`` for p=inf, and the point-to-point value is accumulated from 0 as
+``+= fabs(d)`` (p=1) / ``fmax(., fabs(d))`` (p=inf).  Restated here for p in {1, 2, inf}; other p use pow()
+and are outside the device's contract.
 """
 import numpy as np
 
@@ -56,13 +62,19 @@ def pairs_from_set(pair_set):
     return sort_pairs(np.array(sorted(pair_set), dtype=np.int64).reshape(-1, 2))
 
 
-def within_radius(x_a, y_a, x_b, y_b, r):
-    """The exact fp64 predicate (see module docstring).  Inputs float32-valued arrays."""
+def within_radius(x_a, y_a, x_b, y_b, r, p=2):
+    """The exact fp64 predicate (see module docstring).  Inputs float32-valued arrays; p in {1, 2, inf}."""
     dx = x_a.astype(np.float64) - x_b.astype(np.float64)
     dy = y_a.astype(np.float64) - y_b.astype(np.float64)
-    s = dx * dx
-    s = s + dy * dy
-    return s <= np.float64(r) * np.float64(r)
+    if p == 2:
+        s = dx * dx
+        s = s + dy * dy
+        return s <= np.float64(r) * np.float64(r)
+    if p == 1:
+        return np.abs(dx) + np.abs(dy) <= np.float64(r)
+    if p == np.inf:
+        return np.maximum(np.abs(dx), np.abs(dy)) <= np.float64(r)
+    raise ValueError("p must be 1, 2 or inf")
 
 
 def cell_index(v32, origin, inv_h, ncell):
@@ -78,8 +90,9 @@ def cell_index(v32, origin, inv_h, ncell):
     return q.astype(np.int64)
 
 
-def query_pairs_bruteforce(lon32, lat32, r):
-    """All pairs within r (p=2) via a cell grid + the exact predicate; sorted (P,2) int64."""
+def query_pairs_bruteforce(lon32, lat32, r, p=2):
+    """All pairs within r (Minkowski p in {1, 2, inf}) via a cell grid + the exact predicate; sorted (P,2) int64.
+    Any p >= 1 bounds |dx| and |dy| by r, so cells of edge >= r and the half stencil serve every norm."""
     lon32 = np.asarray(lon32, dtype=np.float32)
     lat32 = np.asarray(lat32, dtype=np.float32)
     n = lon32.size
@@ -111,7 +124,7 @@ def query_pairs_bruteforce(lon32, lat32, r):
         if dxc == 0 and dyc == 0:
             keep = a < b
             a, b = a[keep], b[keep]
-        ok = within_radius(lon32[a], lat32[a], lon32[b], lat32[b], r)
+        ok = within_radius(lon32[a], lat32[a], lon32[b], lat32[b], r, p)
         out.append(np.stack((a[ok], b[ok]), axis=-1))
     if not out:
         return np.zeros((0, 2), dtype=np.int64)

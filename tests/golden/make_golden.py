@@ -144,6 +144,37 @@ def make_pairs():
     np.savez_compressed(os.path.join(HERE, "pairs_cases.npz"), **out)
 
 
+def make_pairs_norms():
+    """pairs_norms.npz: ``cKDTree(...).query_pairs(r, p)`` for the other norms SciPy evaluates without pow():
+    p = 1 and p = inf (interaction_norm, interaction_simulator.py:27,98)."""
+    rng = np.random.default_rng(12)
+    cases = {}
+    # float32-exact coordinates at distance EXACTLY r in the 1-norm (0.125 + 0.25) / in the max norm (0.375)
+    base = np.array([[0.0, 0.0], [0.125, 0.25], [0.25, 0.5], [0.375, 0.0], [0.375, 0.375], [0.25, 0.125],
+                     [0.75, 0.375], [0.375, -0.375]]) + np.array([208.0, 30.0])
+    cases["exact"] = (base[:, 0], base[:, 1], 0.375)
+    n = 20000
+    side = np.sqrt(n / 4900.0)
+    cases["uniform"] = (205 + side * rng.random(n), 25 + side * rng.random(n), 0.01)
+    # a dense blob: cells with hundreds of particles (the pair search's two-pass path)
+    cases["blob"] = (210 + 0.006 * rng.standard_normal(700), 30 + 0.006 * rng.standard_normal(700), 0.01)
+    # near-zero latitudes, both signs: differences are not Sterbenz-exact in float32
+    cases["tiny_lat"] = (180 + 0.2 * rng.random(4000), 1e-3 * (rng.random(4000) - 0.5), 2e-5)
+    x = np.concatenate([np.full(20, 210.5), np.linspace(210.0, 210.2, 41)])
+    y = np.concatenate([np.full(20, 31.25), np.full(41, 31.0)])
+    cases["dups_collinear"] = (x, y, 0.01)
+    out = {}
+    for name, (lon, lat, r) in cases.items():
+        lon = lon.astype(np.float32)
+        lat = lat.astype(np.float32)
+        out[name + "_lon"], out[name + "_lat"], out[name + "_r"] = lon, lat, np.float64(r)
+        for tag, p in (("p1", 1), ("pinf", np.inf)):
+            pr = opairs.pairs_from_set(opairs.query_pairs_reference(lon, lat, r, p=p))
+            out["%s_pairs_%s" % (name, tag)] = pr.astype(np.int32)
+            print("pairs %-16s p=%-4s N=%d P=%d" % (name, p, lon.size, pr.shape[0]))
+    np.savez_compressed(os.path.join(HERE, "pairs_norms.npz"), **out)
+
+
 def small_fieldset(seed=0, T=5, Y=31, X=46, land=True):
     from lagrangian_microbes_b200.velocity_fields import synthetic_uv
     lon = (200.0 + np.arange(X) / 3.0).astype(np.float32)
@@ -179,6 +210,7 @@ def make_rk4():
 
 
 if __name__ == "__main__":
-    make_rps()
-    make_pairs()
-    make_rk4()
+    only = sys.argv[1:]                       # e.g. ``make_golden.py pairs_norms``; default: everything
+    for name, fn in (("rps", make_rps), ("pairs", make_pairs), ("pairs_norms", make_pairs_norms), ("rk4", make_rk4)):
+        if not only or name in only:
+            fn()

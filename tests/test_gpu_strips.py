@@ -187,7 +187,8 @@ def _nccl_worker(rank, world, port, n, seed, steps, out_dir):
         per = n // world
         c = slice(rank * per, (rank + 1) * per if rank < world - 1 else n)
         ss = StripSet(DistTransport(), lon[c], lat[c], sp[c], ids[c], n, R, *P, fs, seed=seed, slack=3.0,
-                      pairs_per_particle=40, grid_margin=0.25)
+                      pairs_per_particle=40, grid_margin=0.05, regrid_every=4, cells_headroom=3.0)
+        grid0 = (ss.grid.x0, ss.grid.y0, ss.grid.inv_h, ss.grid.ncx, ss.grid.ncy)      # the grid of step 0 (re-fitted later)
         rec = []
         for step in range(steps):
             ss.step(check=True)
@@ -196,8 +197,8 @@ def _nccl_worker(rank, world, port, n, seed, steps, out_dir):
             prs = ss.local_pairs()[0]
             rec.append((n_pairs, lo, la, s_, prs))
         if True:
-            np.savez(os.path.join(out_dir, "rank%d.npz" % rank), grid=np.array([ss.grid.x0, ss.grid.y0, ss.grid.inv_h]),
-                     grid_n=np.array([ss.grid.ncx, ss.grid.ncy]), n_pairs=np.array([r[0] for r in rec]),
+            np.savez(os.path.join(out_dir, "rank%d.npz" % rank), grid=np.array(grid0[:3]),
+                     grid_n=np.array(grid0[3:]), n_pairs=np.array([r[0] for r in rec]),
                      **{"lon%d" % k: r[1] for k, r in enumerate(rec)}, **{"lat%d" % k: r[2] for k, r in enumerate(rec)},
                      **{"sp%d" % k: r[3] for k, r in enumerate(rec)}, **{"pairs%d" % k: r[4] for k, r in enumerate(rec)})
         ss.close()
@@ -211,7 +212,7 @@ def test_strips_over_nccl_equal_single_handle(tmp_path, world):
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     from lagrangian_microbes_b200._lib import Grid
-    n, seed, steps = 60000, 21, 5
+    n, seed, steps = 60000, 21, 16          # tight grid margin: the grid is re-fitted several times on the way
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -221,7 +222,7 @@ def test_strips_over_nccl_equal_single_handle(tmp_path, world):
     grid = Grid(float(g["grid"][0]), float(g["grid"][1]), float(g["grid"][2]), int(g["grid_n"][0]), int(g["grid_n"][1]))
     fs = small_fs()
     lon, lat, sp = particles(n, seed, clustered=True)
-    sim = single(lon, lat, sp, grid, fs, seed)
+    sim = single(lon, lat, sp, grid, fs, seed, regrid_every=4, grid_margin=0.05)
     for k in range(steps):
         st = sim.step(check=True)
         wl, wa, ws = sim.download()

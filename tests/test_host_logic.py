@@ -78,9 +78,19 @@ def test_interactions_factory_contract():
     assert fn is lm.rock_paper_scissors_interaction
     with pytest.raises(NotImplementedError):
         lm.InteractionSimulator(pair_interaction=(lambda *a: None, {}, {}), interaction_radius=0.01, output_dir="/tmp/lm_x")
-    with pytest.raises(NotImplementedError):
-        lm.InteractionSimulator(pair_interaction=(fn, params, props), interaction_radius=0.01, interaction_norm=1,
-                                output_dir="/tmp/lm_x")
+    # interaction_norm is SciPy's p: 1, 2 and inf exist on the device, anything else needs pow()
+    for p_bad in (3, 1.5, 0.5, "2"):
+        with pytest.raises(NotImplementedError):
+            lm.InteractionSimulator(pair_interaction=(fn, params, props), interaction_radius=0.01, interaction_norm=p_bad,
+                                    output_dir="/tmp/lm_x")
+    from lagrangian_microbes_b200 import _lib
+    from lagrangian_microbes_b200.engine import norm_code
+    assert [norm_code(p) for p in (1, 2, 2.0, np.inf, float("inf"))] == \
+        [_lib.LM_NORM_1, _lib.LM_NORM_2, _lib.LM_NORM_2, _lib.LM_NORM_INF, _lib.LM_NORM_INF]
+    for p_ok in (1, 2, np.inf):
+        sim = lm.InteractionSimulator(pair_interaction=(fn, params, props), interaction_radius=0.01, interaction_norm=p_ok,
+                                      output_dir="/tmp/lm_x")
+        assert sim.interaction_norm == p_ok
 
 
 def test_stage_clock_matches_oracle_time_search():
