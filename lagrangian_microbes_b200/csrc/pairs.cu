@@ -617,7 +617,9 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
             const int u = u_base + 32 * j;
             if (u < A.units_per_row) {
                 const int c = (A.mode == MODE_EAST) ? row_cell + 2 * u + A.parity : row_cell + u;
-                if (__ldg(A.cell_start + c + 1) > __ldg(A.cell_start + c)) mine += __ldg(A.rec + c).y;
+                // three independent loads (the record of an empty cell is stale and is not counted): one round trip
+                const unsigned int cnt = __ldg(A.rec + c).y;
+                if (__ldg(A.cell_start + c + 1) > __ldg(A.cell_start + c)) mine += cnt;
             }
         }
 #pragma unroll
