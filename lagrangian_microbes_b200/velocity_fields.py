@@ -1,21 +1,28 @@
-"""Velocity-field inputs: the reference's ``oscar_dataset(year)`` contract, synthetic data.
+"""Velocity-field inputs: the reference's ``oscar_dataset(year)`` contract.
 
-Mirrors /root/reference/velocity_fields.py:21-32.  The reference downloads the OSCAR
-third-degree surface-current product over OPeNDAP and opens it with xarray; neither the
-network nor xarray exists here, so ``oscar_dataset`` returns a small
-dataset object that supports exactly the accesses the advecter makes
+Mirrors /root/reference/velocity_fields.py:21-32.  The reference opens ``oscar_vel<year>.nc`` from the
+working directory with xarray, downloading the OSCAR third-degree surface-current product over OPeNDAP
+first when the file is missing.  Neither the network nor xarray exists here, so
+``oscar_dataset`` returns a small dataset object that supports exactly the accesses the advecter makes
 (/root/reference/particle_advecter.py:160-180):
 
     ds["depth"].values[0];  ds.sel(depth=d);  sub["time"|"latitude"|"longitude"|"u"|"v"].values
 
-filled with an analytic (steady) or random-Fourier (time-varying) eddy field on the OSCAR
-grid: longitude float32(20 + k/3), k=0..1200; latitude float32(80 - j/3), j=0..480
-(DESCENDING, like the product); 72 snapshots 432000 s apart; depth [15.0];
-``u``/``v`` float32 (time, depth, latitude, longitude) in m/s.
+* ``oscar_vel<year>.nc`` present in the working directory (or in ``$LM_OSCAR_DIR``): read with
+  ``scipy.io.netcdf_file`` (NetCDF-3 classic / 64-bit offset, the format of the product's files) and decoded
+  the way ``xarray.open_dataset`` decodes it -- CF time units to datetime64[ns], ``_FillValue`` /
+  ``missing_value`` to NaN, ``scale_factor`` / ``add_offset`` applied (``NetcdfDataset``);
+* otherwise (there is nothing to download from): an analytic (steady) or random-Fourier (time-varying) eddy
+  field on the OSCAR grid: longitude float32(20 + k/3), k=0..1200; latitude float32(80 - j/3), j=0..480
+  (DESCENDING, like the product); 72 snapshots 432000 s apart; depth [15.0]; ``u``/``v`` float32
+  (time, depth, latitude, longitude) in m/s.  ``save_dataset`` writes any such dataset in the product's layout
+  (the reference's ``dataset.to_netcdf(dataset_filepath)``, velocity_fields.py:30).
 
-A user with the real NetCDF files can register any object with the same accessors via
-``register_dataset_provider``.
+Any other source can be plugged in with ``register_dataset_provider``.
 """
+import os
+import re
+
 import numpy as np
 
 OSCAR_NX, OSCAR_NY, OSCAR_NT = 1201, 481, 72
@@ -133,10 +140,168 @@ def register_dataset_provider(fn):
     _CACHE.clear()
 
 
+# ------------------------------------------------------------------------------------------------------
+# the product's own files
+# ------------------------------------------------------------------------------------------------------
+_TIME_UNIT_NS = {"day": 86400 * 10**9, "hour": 3600 * 10**9, "minute": 60 * 10**9, "second": 10**9,
+                 "millisecond": 10**6, "microsecond": 10**3}
+
+
+def decode_cf_time(values, units):
+    """``<unit>(s) since <date>[ <time>]`` -> datetime64[ns], as xarray's decode_times does for the standard
+    calendar (OSCAR: int32 ``day since 1992-10-05 00:00:00``)."""
+    m = re.match(r"\s*(\w+?)s?\s+since\s+(\d{1,4}-\d{1,2}-\d{1,2})(?:[T\s]+(\d{1,2}:\d{1,2}(?::\d{1,2}(?:\.\d+)?)?))?",
+                 units.strip(), re.IGNORECASE)
+    if m is None or m.group(1).lower() not in _TIME_UNIT_NS:
+        raise ValueError("cannot decode time units %r" % units)
+    y, mo, d = (int(x) for x in m.group(2).split("-"))
+    base = np.datetime64("%04d-%02d-%02d" % (y, mo, d), "ns")
+    if m.group(3):
+        hms = [float(x) for x in m.group(3).split(":")] + [0.0, 0.0]
+        base = base + np.timedelta64(int(round((hms[0] * 3600 + hms[1] * 60 + hms[2]) * 1e9)), "ns")
+    unit_ns = _TIME_UNIT_NS[m.group(1).lower()]
+    values = np.asarray(values)
+    if np.issubdtype(values.dtype, np.integer):
+        offs = values.astype(np.int64) * unit_ns
+    else:
+        offs = np.round(values.astype(np.float64) * unit_ns).astype(np.int64)
+    return base + offs.astype("timedelta64[ns]")
+
+
+def _attr(var, name):
+    a = getattr(var, name, None)
+    if a is None:
+        return None
+    a = np.asarray(a)
+    return a.reshape(-1)[0] if a.size else None
+
+
+def decode_cf_variable(var, data):
+    """Mask-and-scale of one variable as xarray.open_dataset applies it: fill / missing values become NaN,
+    then ``data * scale_factor + add_offset``; float32 stays float32 unless scaling promotes it."""
+    data = np.asarray(data)
+    fills = [f for f in (_attr(var, "_FillValue"), _attr(var, "missing_value")) if f is not None]
+    scale, offset = _attr(var, "scale_factor"), _attr(var, "add_offset")
+    if not fills and scale is None and offset is None:
+        return np.array(data)
+    if np.issubdtype(data.dtype, np.floating) and scale is None and offset is None:
+        out = np.array(data)
+    else:
+        out = data.astype(np.float32 if data.dtype.itemsize <= 2 and scale is None and offset is None else np.float64)
+    for f in fills:
+        if not (isinstance(f, (float, np.floating)) and np.isnan(f)):
+            out[data == f] = np.nan
+    if scale is not None:
+        out = out * np.float64(scale)
+    if offset is not None:
+        out = out + np.float64(offset)
+    return out
+
+
+class NetcdfDataset:
+    """A NetCDF-3 file with the dataset accessors the advecter uses.  Variables are read (and decoded) on first
+    access; ``sel(depth=...)`` picks the nearest depth level of every variable that has a depth dimension."""
+
+    def __init__(self, path, _depth_index=None, _file=None):
+        from scipy.io import netcdf_file
+        self.path = path
+        if _file is None:
+            with open(path, "rb") as fh:
+                magic = fh.read(4)
+            if magic[:3] != b"CDF":
+                kind = "NetCDF-4 / HDF5" if magic[1:4] == b"HDF" else "not a NetCDF-3"
+                raise OSError("%s is a %s file; this reader handles NetCDF-3 (classic, 64-bit offset). Convert it "
+                              "with `nccopy -k classic`, or plug another reader in with register_dataset_provider()."
+                              % (path, kind))
+            _file = netcdf_file(path, "r", mmap=False)
+        self._file = _file
+        self._depth_index = _depth_index
+        self._cache = {}
+
+    def _depth_dim(self):
+        return "depth" if "depth" in self._file.dimensions else None
+
+    def __getitem__(self, name):
+        if name not in self._cache:
+            var = self._file.variables[name]
+            data = np.asarray(var[:])
+            data = data.astype(data.dtype.newbyteorder("="))         # the file is big-endian; xarray hands out native arrays
+            dd = self._depth_dim()
+            if self._depth_index is not None and dd is not None and dd in var.dimensions:
+                axis = var.dimensions.index(dd)
+                if name == dd:
+                    data = data[self._depth_index:self._depth_index + 1]
+                else:
+                    data = np.take(data, self._depth_index, axis=axis)
+            units = getattr(var, "units", b"")
+            units = units.decode() if isinstance(units, bytes) else str(units)
+            if " since " in units:
+                values = decode_cf_time(data, units)
+            else:
+                values = decode_cf_variable(var, data)
+            self._cache[name] = _Var(values)
+        return self._cache[name]
+
+    def sel(self, depth):
+        depths = np.asarray(self._file.variables["depth"][:], dtype=np.float64)
+        idx = int(np.argmin(np.abs(depths - float(depth))))
+        return NetcdfDataset(self.path, _depth_index=idx, _file=self._file)
+
+    def close(self):
+        self._file.close()
+
+
+def save_dataset(dataset, path, time_units="day since 1992-10-05 00:00:00"):
+    """Write a dataset (synthetic or otherwise) as NetCDF-3 in the layout of the OSCAR product: dimensions
+    (time, depth, latitude, longitude), integer ``time`` in ``time_units``, NaN as the missing value --
+    the counterpart of ``dataset.to_netcdf(dataset_filepath)`` (velocity_fields.py:30)."""
+    from scipy.io import netcdf_file
+    t = np.asarray(dataset["time"].values).astype("datetime64[ns]")
+    ref = decode_cf_time(np.zeros(1, dtype=np.int64), time_units)[0]
+    unit_ns = (decode_cf_time(np.ones(1, dtype=np.int64), time_units)[0] - ref) // np.timedelta64(1, "ns")
+    tv = (t - ref) // np.timedelta64(1, "ns")
+    if np.any(tv % unit_ns):
+        raise ValueError("the time axis is not a whole number of %r" % time_units)
+    u, v = np.asarray(dataset["u"].values), np.asarray(dataset["v"].values)
+    with netcdf_file(path, "w", version=2) as f:
+        for name, n in (("time", t.size), ("depth", u.shape[1]), ("latitude", u.shape[2]), ("longitude", u.shape[3])):
+            f.createDimension(name, n)
+        tvar = f.createVariable("time", "i4", ("time",))
+        tvar[:] = (tv // unit_ns).astype(np.int32)
+        tvar.units = time_units
+        for name, dtype in (("depth", "f4"), ("latitude", "f8"), ("longitude", "f8")):
+            var = f.createVariable(name, dtype, (name,))
+            var[:] = np.asarray(dataset[name].values)
+        for name, data in (("u", u), ("v", v)):
+            var = f.createVariable(name, "f4" if data.dtype == np.float32 else "f8", ("time", "depth", "latitude", "longitude"))
+            var[:] = data
+            var.units = "meter/sec"
+            var.missing_value = np.array(np.nan, dtype=data.dtype if data.dtype == np.float32 else np.float64)
+    return path
+
+
+def oscar_dataset_path(year):
+    """Where ``oscar_dataset`` looks for the product's file: the working directory (as the reference does,
+    velocity_fields.py:22-23), then ``$LM_OSCAR_DIR``.  None if it is in neither."""
+    name = oscar_dataset_filename(year)
+    for d in (os.getcwd(), os.environ.get("LM_OSCAR_DIR")):
+        if d and os.path.isfile(os.path.join(d, name)):
+            return os.path.join(d, name)
+    return None
+
+
 def oscar_dataset(year):
-    """velocity_fields.py:21-32 -- same name, same return contract, synthetic contents."""
+    """velocity_fields.py:21-32 -- same name, same return contract: the product's file when it is there, the
+    synthetic field otherwise (the reference would download it; there is no network here)."""
     if _PROVIDER is not None:
         return _PROVIDER(year)
+    path = oscar_dataset_path(year)
+    if path is not None:
+        key = ("file", path, os.path.getmtime(path))
+        if key not in _CACHE:
+            _CACHE.clear()
+            _CACHE[key] = NetcdfDataset(path)
+        return _CACHE[key]
     key = (year,) + tuple(sorted(_CONFIG.items()))
     if key not in _CACHE:
         lon, lat = oscar_grid()

@@ -164,3 +164,122 @@ def test_file_formats_round_trip(tmp_path):
     with netcdf_file(path, "r", mmap=False) as nc:
         assert nc.variables["longitude"].dimensions == ("particle number", "time")
         assert list(nc.variables["particle number"][:]) == [1, 2, 3, 4]
+
+
+# ---- the product's own files: oscar_vel<year>.nc read the way xarray.open_dataset decodes it --------------------
+def _write_oscar_like(path, fill=None, packed=False):
+    """A small file in the OSCAR product's layout (velocity_fields.py:21-32 opens such a file with xarray)."""
+    from scipy.io import netcdf_file
+    rng = np.random.default_rng(4)
+    T, Y, X = 4, 7, 9
+    days = np.array([8852, 8857, 8862, 8868], dtype=np.int32)               # irregular last step
+    lat = 40.0 - np.arange(Y) / 3.0                                         # descending, like the product
+    lon = 200.0 + np.arange(X) / 3.0
+    u = rng.normal(0, 0.3, (T, 2, Y, X))
+    v = rng.normal(0, 0.3, (T, 2, Y, X))
+    land = np.zeros((Y, X), dtype=bool)
+    land[2:4, 5:8] = True
+    with netcdf_file(path, "w") as f:
+        for name, n in (("time", T), ("depth", 2), ("latitude", Y), ("longitude", X)):
+            f.createDimension(name, n)
+        tv = f.createVariable("time", "i4", ("time",))
+        tv[:] = days
+        tv.units = "day since 1992-10-05 00:00:00"
+        for name, vals, dt in (("depth", [15.0, 30.0], "f4"), ("latitude", lat, "f8"), ("longitude", lon, "f8")):
+            var = f.createVariable(name, dt, (name,))
+            var[:] = np.asarray(vals)
+        for name, data in (("u", u), ("v", v)):
+            if packed:                                                      # int16 with scale/offset and a fill value
+                var = f.createVariable(name, "i2", ("time", "depth", "latitude", "longitude"))
+                q = np.round((data - 0.25) / 1e-3).astype(np.int16)
+                q[:, :, land] = -32767
+                var[:] = q
+                var.scale_factor = np.float64(1e-3)
+                var.add_offset = np.float64(0.25)
+                var._FillValue = np.int16(-32767)
+            else:
+                var = f.createVariable(name, "f8", ("time", "depth", "latitude", "longitude"))
+                d = data.copy()
+                d[:, :, land] = np.nan if fill is None else fill
+                var[:] = d
+                var.missing_value = np.float64(np.nan if fill is None else fill)
+    return days, lat, lon, u, v, land
+
+
+@pytest.mark.parametrize("kind", ["nan", "fill", "packed"])
+def test_oscar_file_in_the_working_directory_is_read_like_xarray_would(tmp_path, monkeypatch, kind):
+    from lagrangian_microbes_b200 import velocity_fields as vf
+    from lagrangian_microbes_b200.particle_advecter import HostFieldSet
+    path = str(tmp_path / vf.oscar_dataset_filename(2017))
+    days, lat, lon, u, v, land = _write_oscar_like(path, fill={"nan": None, "fill": -9999.0, "packed": None}[kind],
+                                                   packed=kind == "packed")
+    monkeypatch.chdir(tmp_path)
+    vf.register_dataset_provider(None)
+    ds = vf.oscar_dataset(2017)
+    assert isinstance(ds, vf.NetcdfDataset) and vf.oscar_dataset(2017) is ds          # cached
+    assert ds["depth"].values[0] == np.float32(15.0)
+    t = ds["time"].values
+    assert t.dtype == np.dtype("datetime64[ns]") and t[0] == np.datetime64("2016-12-30T00:00:00")
+    assert ds["u"].values.shape == (4, 2, 7, 9)
+    sub = ds.sel(depth=ds["depth"].values[0])
+    assert sub["u"].values.shape == (4, 7, 9) and list(sub["depth"].values) == [15.0]
+    got = sub["u"].values
+    assert np.isnan(got[:, land]).all() and not np.isnan(got[:, ~land]).any()
+    want = u[:, 0] if kind != "packed" else np.round((u[:, 0] - 0.25) / 1e-3) * 1e-3 + 0.25
+    assert np.allclose(got[:, ~land], want[:, ~land], rtol=0, atol=1e-12)
+    deeper = ds.sel(depth=29.0)["v"].values                                            # nearest level
+    assert np.allclose(deeper[:, ~land], (v[:, 1] if kind != "packed" else np.round((v[:, 1] - 0.25) / 1e-3) * 1e-3 + 0.25)[:, ~land],
+                       rtol=0, atol=1e-12)
+    # what Parcels' field construction makes of it (particle_advecter.py:160-184)
+    fs = HostFieldSet(ds)
+    assert list(fs.time) == [0.0, 5 * 86400.0, 10 * 86400.0, 16 * 86400.0]
+    assert fs.lat[0] < fs.lat[-1] and fs.lat.dtype == np.float32 and fs.u.dtype == np.float32
+    assert np.array_equal(fs.lat, lat[::-1].astype(np.float32)) and np.array_equal(fs.lon, lon.astype(np.float32))
+    assert (fs.u[:, land[::-1]] == 0).all() and np.array_equal(fs.u[:, ~land[::-1]], want[:, ::-1][:, ~land[::-1]].astype(np.float32))
+
+
+def test_synthetic_dataset_round_trips_through_the_product_layout(tmp_path, monkeypatch):
+    """save_dataset (the reference's dataset.to_netcdf, velocity_fields.py:30) + the file reader give back the
+    dataset bit for bit; without a file, and with nothing to download from, the synthetic field is served."""
+    from lagrangian_microbes_b200 import velocity_fields as vf
+    monkeypatch.chdir(tmp_path)
+    vf.register_dataset_provider(None)
+    lon, lat = vf.oscar_grid()
+    lon, lat = lon[540:560], lat[130:150]
+    times_s = vf.OSCAR_DT_SECONDS * np.arange(3, dtype=np.int64)
+    u, v = vf.synthetic_uv(lon, lat, times_s, n_modes=5, land=False)
+    u[:, 3:5, 6:9] = np.nan
+    time = (np.datetime64("2017-01-01T00:00:00", "s") + times_s.astype("timedelta64[s]")).astype("datetime64[ns]")
+    ds = vf.SyntheticDataset({"time": time, "depth": np.array([15.0], dtype=np.float32), "latitude": lat.astype(np.float64),
+                              "longitude": lon.astype(np.float64), "u": u[:, None], "v": v[:, None]})
+    assert vf.oscar_dataset_path(2017) is None
+    vf.save_dataset(ds, vf.oscar_dataset_filename(2017))
+    back = vf.oscar_dataset(2017)
+    assert isinstance(back, vf.NetcdfDataset)
+    for name in ("time", "depth", "latitude", "longitude", "u", "v"):
+        a, b = ds[name].values, back[name].values
+        assert a.dtype == b.dtype and a.shape == b.shape, name
+        assert np.array_equal(a, b, equal_nan=name in ("u", "v")), name
+    # $LM_OSCAR_DIR is searched after the working directory
+    other = tmp_path / "elsewhere"
+    other.mkdir()
+    monkeypatch.chdir(other)
+    assert vf.oscar_dataset_path(2017) is None
+    monkeypatch.setenv("LM_OSCAR_DIR", str(tmp_path))
+    assert vf.oscar_dataset_path(2017) == str(tmp_path / "oscar_vel2017.nc")
+    with pytest.raises(ValueError):
+        vf.save_dataset(ds, "x.nc", time_units="day since 1992-10-05 07:00:00")      # not a whole number of days
+    # a NetCDF-4 (HDF5) file is refused with a message that says what to do
+    with open("oscar_vel2018.nc", "wb") as fh:
+        fh.write(b"\x89HDF\r\n\x1a\n" + b"\0" * 64)
+    with pytest.raises(OSError, match="NetCDF-4"):
+        vf.oscar_dataset(2018)
+
+
+def test_cf_time_units():
+    from lagrangian_microbes_b200.velocity_fields import decode_cf_time
+    assert decode_cf_time(np.array([0, 1], dtype=np.int32), "days since 2000-01-01")[1] == np.datetime64("2000-01-02")
+    assert decode_cf_time(np.array([1.5]), "hours since 2000-01-01T06:30:00")[0] == np.datetime64("2000-01-01T08:00:00")
+    assert decode_cf_time(np.array([90], dtype=np.int64), "seconds since 1970-1-1 0:0:0")[0] == np.datetime64("1970-01-01T00:01:30")
+    with pytest.raises(ValueError):
+        decode_cf_time(np.array([1]), "fortnights since 2000-01-01")
