@@ -261,6 +261,40 @@ int64_t lm_launch_count(lm_handle h);
  * waits for the halo exchanges), [4] stats.  Host float[5]. */
 int lm_phase_times(lm_handle h, float *ms_out);
 
+/* ---- analysis reductions on a snapshot (handle-free) ---------------- */
+/* The reference's pair-distance histogram (sandbox/pairwise_distance_histogram_distributed.jl:33-44, :54-64; its
+ * unfinished CUDA kernel: sandbox/pairwise_distance_histogram_gpu.jl:14-43): for every unordered pair i < j of the
+ * n points (float32 degrees; the reference calls it once per species on that species' microbes)
+ *     d   = haversine_distance32(lat_i, lon_i, lat_j, lon_j, radius_m)        float32, the reference's operation order
+ *     bin = round(10 * log10(max(1, d)))
+ * hist_out: device uint64[bins + 2], zeroed by the call: [b] = pairs of bin b for b = 0..bins ([0]: d < 10^0.05 m,
+ * which the reference's 1-based hist[bin] cannot hold), [bins + 1] = pairs beyond the last bin.  The entries always
+ * sum to n (n - 1) / 2.  The bin is decided on the float32 haversine argument `a` against bin edges computed in
+ * double, so a pair whose distance is within float32 rounding of an edge may land in the neighbouring bin compared
+ * with a float32 evaluation of asin / log10 (tests/test_gpu_analysis.py states the band).  n < 2^24,
+ * 1 <= bins <= LM_PDH_MAX_BINS (the reference uses 70).  Compute-bound: n^2 / 2 pair evaluations. */
+#define LM_PDH_MAX_BINS 126
+int lm_pair_distance_hist(const float *lat, const float *lon, int64_t n, float radius_m, int32_t bins,
+                          uint64_t *hist_out, void *stream);
+/* The frame of microbe_plotter.py:82-155 (plt.scatter of every microbe coloured by species, :132-146) as a raster of
+ * width x height pixels over [lon_min, lon_max) x [lat_min, lat_max), row 0 = northern edge:
+ *     column = floor((double(lon) - lon_min) * (width / (lon_max - lon_min))),  row likewise from the north;
+ * microbes outside the extent are skipped.  counts_out: device uint32[3][height][width], microbes of species 1, 2, 3
+ * per pixel; top_out: device int32[height][width], the highest array index in the pixel (-1: none) -- matplotlib draws
+ * the markers of one scatter call in array order, so that microbe's marker is the visible one.  species may be NULL
+ * (everything counts as species 1).  Both outputs are initialised by the call. */
+int lm_rasterize(const float *lon, const float *lat, const int8_t *species, int64_t n, double lon_min, double lon_max,
+                 double lat_min, double lat_max, int32_t width, int32_t height, uint32_t *counts_out, int32_t *top_out,
+                 void *stream);
+/* RGB image (device uint8[height][width][3]) from lm_rasterize's outputs.  palette_rgb: HOST uint8[4][3] --
+ * background, rock, paper, scissors (interactions.py:8-10: red, limegreen, blue).  mode LM_FRAME_LAST_DRAWN: the colour
+ * of the microbe drawn last (needs top + the species array given to lm_rasterize); LM_FRAME_PLURALITY: the colour of
+ * the most numerous species in the pixel (ties: the lower species number; needs counts). */
+#define LM_FRAME_LAST_DRAWN 0
+#define LM_FRAME_PLURALITY 1
+int lm_compose_frame(const uint32_t *counts, const int32_t *top, const int8_t *species, int32_t width, int32_t height,
+                     int32_t mode, const uint8_t *palette_rgb /* host */, uint8_t *rgb_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "liblm_b200.so")
-_SOURCES = ["api.cu", "advect.cu", "bin.cu", "strip.cu", "pairs.cu", "resolve.cu"]
+_SOURCES = ["api.cu", "advect.cu", "bin.cu", "strip.cu", "pairs.cu", "resolve.cu", "analysis.cu"]
 _HEADERS = ["lm_internal.cuh", "philox.cuh", os.path.join("..", "..", "include", "lm_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -24,6 +24,8 @@ LM_STEP_TIMING = 32
 LM_OPT_FIND_PATH, LM_OPT_RESOLVE_UPL, LM_OPT_OVERLAP, LM_OPT_NORM = 2, 3, 4, 5
 LM_OPT_RESOLVE_HEAVY_MIN, LM_OPT_RESOLVE_BATCH = 6, 7
 LM_NORM_INF, LM_NORM_1, LM_NORM_2 = 0, 1, 2
+LM_PDH_MAX_BINS = 126
+LM_FRAME_LAST_DRAWN, LM_FRAME_PLURALITY = 0, 1
 
 
 class LmError(RuntimeError):
@@ -144,6 +146,9 @@ def lib():
         "lm_set_option": (ctypes.c_int, [vp, i32, i64]),
         "lm_join": (ctypes.c_int, [vp, vp]),
         "lm_phase_times": (ctypes.c_int, [vp, P(flt)]),
+        "lm_pair_distance_hist": (ctypes.c_int, [vp, vp, i64, flt, i32, vp, vp]),
+        "lm_rasterize": (ctypes.c_int, [vp, vp, vp, i64, dbl, dbl, dbl, dbl, i32, i32, vp, vp, vp]),
+        "lm_compose_frame": (ctypes.c_int, [vp, vp, vp, i32, i32, i32, ctypes.c_char_p, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -158,7 +163,8 @@ EXPORTS = ["lm_version", "lm_error_string", "lm_last_cuda_error", "lm_create", "
            "lm_pair_uniforms", "lm_resolve_rps", "lm_state_set", "lm_state_size", "lm_step", "lm_state_get",
            "lm_state_get_host", "lm_host_copies_sync", "lm_state_view", "lm_sync_stats", "lm_reset_stats", "lm_launch_count",
            "lm_phase_times", "lm_strip_alloc", "lm_set_strip", "lm_strip_buffers_get", "lm_step_move", "lm_step_bin",
-           "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option", "lm_join", "lm_record_next_step"]
+           "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option", "lm_join", "lm_record_next_step",
+           "lm_pair_distance_hist", "lm_rasterize", "lm_compose_frame"]
 
 
 def check(code, what):

@@ -827,4 +827,36 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
     }
 }
 
+// ---- analysis reductions on a snapshot (csrc/analysis.cu); handle-free like lm_pair_uniforms -----------------
+int lm_pair_distance_hist(const float *lat, const float *lon, int64_t n, float radius_m, int32_t bins,
+                          uint64_t *hist_out, void *stream)
+{
+    if (n < 0 || n >= (1ll << 24) || bins < 1 || bins > LM_PDH_MAX_BINS || !hist_out || !(radius_m > 0.f)) return LM_EINVAL;
+    if (n > 0 && (!lat || !lon)) return LM_EINVAL;
+    LM_CUDA(launch_pair_distance_hist(lat, lon, n, radius_m, bins, reinterpret_cast<unsigned long long *>(hist_out),
+                                      as_stream(stream), nullptr));
+    return LM_OK;
+}
+
+int lm_rasterize(const float *lon, const float *lat, const int8_t *species, int64_t n, double lon_min, double lon_max,
+                 double lat_min, double lat_max, int32_t width, int32_t height, uint32_t *counts_out, int32_t *top_out,
+                 void *stream)
+{
+    if (n < 0 || n >= (1ll << 31) || width < 1 || height < 1 || (int64_t)width * height >= (1ll << 30)) return LM_EINVAL;
+    if (!(lon_max > lon_min) || !(lat_max > lat_min) || !counts_out || !top_out) return LM_EINVAL;
+    if (n > 0 && (!lon || !lat)) return LM_EINVAL;
+    LM_CUDA(launch_raster(lon, lat, species, n, lon_min, lon_max, lat_min, lat_max, width, height, counts_out, top_out,
+                          as_stream(stream), nullptr));
+    return LM_OK;
+}
+
+int lm_compose_frame(const uint32_t *counts, const int32_t *top, const int8_t *species, int32_t width, int32_t height,
+                     int32_t mode, const uint8_t *palette_rgb, uint8_t *rgb_out, void *stream)
+{
+    if (width < 1 || height < 1 || (int64_t)width * height >= (1ll << 30) || !palette_rgb || !rgb_out) return LM_EINVAL;
+    if ((mode != LM_FRAME_LAST_DRAWN && mode != LM_FRAME_PLURALITY) || (mode == LM_FRAME_LAST_DRAWN ? !top : !counts)) return LM_EINVAL;
+    LM_CUDA(launch_compose(counts, top, species, width, height, mode, palette_rgb, rgb_out, as_stream(stream), nullptr));
+    return LM_OK;
+}
+
 }  // extern "C"

@@ -175,6 +175,15 @@ cudaError_t launch_pair_uniforms(const int2 *pairs, int64_t np, uint64_t seed, u
 int resolve_explicit(lm_handle_s *h, const int2 *pairs, const double *u, int64_t np, int8_t *species, int64_t n,
                      double pRS, double pPR, double pSP, int32_t *rounds_out, cudaStream_t s);
 
+// analysis reductions on a snapshot (csrc/analysis.cu)
+cudaError_t launch_pair_distance_hist(const float *lat, const float *lon, int64_t n, float radius_m, int bins,
+                                      unsigned long long *hist, cudaStream_t s, int64_t *launches);
+cudaError_t launch_raster(const float *lon, const float *lat, const int8_t *sp, int64_t n, double lon_min, double lon_max,
+                          double lat_min, double lat_max, int width, int height, uint32_t *counts, int32_t *top,
+                          cudaStream_t s, int64_t *launches);
+cudaError_t launch_compose(const uint32_t *counts, const int32_t *top, const int8_t *sp, int width, int height, int mode,
+                           const uint8_t *palette_rgb, uint8_t *rgb, cudaStream_t s, int64_t *launches);
+
 void set_last_cuda_error(cudaError_t e, const char *where);
 
 }  // namespace lm

@@ -103,3 +103,25 @@ def read_particle_file(filepath):
                      if fn.endswith(".npy") and fn != "time_seconds.npy"}
     times = [t0 + timedelta(seconds=float(s)) for s in secs]
     return ParticleFile(variables, times)
+
+
+def write_png(filepath, rgb):
+    """8-bit RGB PNG from a uint8 (height, width, 3) array (zlib + CRCs by hand: matplotlib / PIL are not required)."""
+    import struct
+    import zlib
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+    assert rgb.ndim == 3 and rgb.shape[2] == 3
+    h, w, _ = rgb.shape
+    raw = np.empty((h, 1 + 3 * w), dtype=np.uint8)
+    raw[:, 0] = 0                                       # filter type 0 on every scanline
+    raw[:, 1:] = rgb.reshape(h, 3 * w)
+
+    def chunk(tag, data):
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+
+    with open(filepath, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n")
+        f.write(chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)))
+        f.write(chunk(b"IDAT", zlib.compress(raw.tobytes(), 6)))
+        f.write(chunk(b"IEND", b""))
+    return filepath
