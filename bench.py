@@ -224,6 +224,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--resolve-upl", type=int, default=0, help="LM_OPT_RESOLVE_UPL (tuning experiments)")
     ap.add_argument("--no-overlap", action="store_true", help="LM_OPT_OVERLAP = 0 (tuning experiments)")
+    ap.add_argument("--resolve-mode", type=int, default=0, choices=[0, 1],
+                    help="LM_OPT_RESOLVE_MODE: 0 nine phase launches (default), 1 tiled resolver (experimental)")
+    ap.add_argument("--tile-smem", type=int, default=0, help="LM_OPT_RESOLVE_TILE_SMEM (with --resolve-mode 1)")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
 
@@ -237,6 +240,8 @@ def main():
               else "state fits L2 (config as specified)",
               "regrid": "bounding box read back every 16 steps (one small sync), cell grid re-fitted when the cloud nears its edge"}
 
+    if args.resolve_mode:
+        config["resolver"] = "tiled (LM_OPT_RESOLVE_MODE=1, experimental)"
     if args.impl == "reference":
         if rank != 0:
             return
@@ -327,6 +332,11 @@ def main():
     if args.no_overlap:
         from lagrangian_microbes_b200._lib import LM_OPT_OVERLAP
         sim.engine.set_option(LM_OPT_OVERLAP, 0)
+    if args.resolve_mode:
+        from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_MODE, LM_OPT_RESOLVE_TILE_SMEM
+        sim.engine.set_option(LM_OPT_RESOLVE_MODE, args.resolve_mode)
+        if args.tile_smem:
+            sim.engine.set_option(LM_OPT_RESOLVE_TILE_SMEM, args.tile_smem)
     spinup = args.spinup if args.spinup >= 0 else (1500 if args.workload == "config2" else 0)
     for _ in range(spinup):
         sim.step()

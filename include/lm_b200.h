@@ -249,6 +249,16 @@ int lm_reset_stats(lm_handle h, void *stream);
  *                   or 8.  Results are identical for every value; only the number of dependent memory round trips per
  *                   unit changes. */
 #define LM_OPT_RESOLVE_BATCH 7
+/*   LM_OPT_RESOLVE_MODE  RPS resolver: 0 (default) nine phase launches on the live species; 1 (EXPERIMENTAL, not yet
+ *                   measured) one launch per phase range over tiles of 64 x 16 cells: each CTA copies the species of
+ *                   its tile plus a halo of 6 columns / 2 rows from a snapshot into shared memory, runs every phase
+ *                   there and writes back the tile's interior (DESIGN.md 4.3 "Tiled resolver").  Same results.
+ *                   Switching it on allocates 5 bytes per particle + 1 per cell (the only allocation outside
+ *                   lm_create); not allowed between the stages of a step (LM_ESTATE).
+ *   LM_OPT_RESOLVE_TILE_SMEM  bytes of species a tile may keep in shared memory (default 32768); fuller tiles work on a
+ *                   private slice of global memory instead. */
+#define LM_OPT_RESOLVE_MODE 8
+#define LM_OPT_RESOLVE_TILE_SMEM 9
 int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Make `stream` wait for work of the last lm_step that is still running on the handle's internal stream
  * (LM_OPT_OVERLAP).  Only needed before the caller reads the resident arrays through pointers obtained earlier,

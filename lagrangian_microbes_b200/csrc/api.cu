@@ -72,6 +72,7 @@ int lm_destroy(lm_handle h)
     }
     cudaFree(h->keys); cudaFree(h->slots); cudaFree(h->cell_count); cudaFree(h->cell_start_buf[0]); cudaFree(h->cell_start_buf[1]);
     cudaFree(h->n_pairs_snap);
+    cudaFree(h->sp_snap); cudaFree(h->tile_scratch); cudaFree(h->tile_scratch_used);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_find_done) cudaEventDestroy(h->ev_find_done);
     if (h->ev_resolve_done) cudaEventDestroy(h->ev_resolve_done);
@@ -121,6 +122,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     h->cell_start = h->cell_start_buf[0];
     h->overlap = 1;
     h->norm = LM_NORM_2;
+    h->resolve_tile_smem = 32768;
     h->resolve_batch = 4;      // measured on B200 (profiles/r1y_sweep_resolve.jsonl): 4 beats 1 and 8 on every workload
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
     if (max_pairs >= (1ll << 32) - 8) return (delete h, LM_EINVAL);          // 32-bit entry offsets
@@ -591,7 +593,9 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
             LM_CUDA(cudaStreamWaitEvent(h->side_stream, h->ev_find_done, 0));
             rs = h->side_stream;
         }
-        if (n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 0, 5, rs));
+        // the tiled resolver takes all nine phases in one launch when no halo exchange has to happen after phase 5
+        h->resolve_all_in_begin = h->resolve_mode == 1 && !in_strip_mode(h);
+        if (n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 0, h->resolve_all_in_begin ? 8 : 5, rs));
     }
     if (h->has_south && interact) LM_CUDA(launch_row0_species_pack(h, h->sp[c], s));
     h->stage = 3;
@@ -608,7 +612,8 @@ int lm_step_interact_end(lm_handle h, void *stream)
     const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
     if (h->has_north && interact) LM_CUDA(launch_ghost_species_unpack(h, h->sp[c], n, s));
     if (interact && n > 0) {
-        LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, h->resolve_on_side ? h->side_stream : s));
+        if (!h->resolve_all_in_begin) LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, h->resolve_on_side ? h->side_stream : s));
+        h->resolve_all_in_begin = false;
         if (h->resolve_on_side) {
             LM_CUDA(cudaEventRecord(h->ev_resolve_done, h->side_stream));
             h->resolve_pending = true;
@@ -822,6 +827,27 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
         case LM_OPT_NORM:
             if (value != LM_NORM_1 && value != LM_NORM_2 && value != LM_NORM_INF) return LM_EINVAL;
             h->norm = (int)value;
+            return LM_OK;
+        case LM_OPT_RESOLVE_MODE: {
+            if (value < 0 || value > 1) return LM_EINVAL;
+            if (h->stage != 0) return LM_ESTATE;                 // not between the stages of a step
+            if (value == 1 && !h->sp_snap) {
+                LM_CUDA(cudaSetDevice(h->device));
+                bool ok = dev_alloc(&h->sp_snap, h->max_particles);
+                ok = ok && dev_alloc(&h->tile_scratch, 4 * h->max_particles + h->max_cells + 64);
+                ok = ok && dev_alloc(&h->tile_scratch_used, 1);
+                if (!ok) {
+                    cudaFree(h->sp_snap); cudaFree(h->tile_scratch); cudaFree(h->tile_scratch_used);
+                    h->sp_snap = nullptr; h->tile_scratch = nullptr; h->tile_scratch_used = nullptr;
+                    return LM_ENOMEM;
+                }
+            }
+            h->resolve_mode = (int)value;
+            return LM_OK;
+        }
+        case LM_OPT_RESOLVE_TILE_SMEM:
+            if (value < 1024 || value > 200 * 1024) return LM_EINVAL;
+            h->resolve_tile_smem = (int)value;
             return LM_OK;
         default: return LM_EINVAL;
     }

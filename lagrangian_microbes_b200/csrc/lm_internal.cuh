@@ -93,6 +93,13 @@ struct lm_handle_s {
     int resolve_heavy_min; // LM_OPT_RESOLVE_HEAVY_MIN: 0 = default (160)
     int resolve_batch;     // LM_OPT_RESOLVE_BATCH: pairs per lane and iteration in the resolver's stream walk (1, 4, 8)
     int norm;              // LM_OPT_NORM: LM_NORM_2 (default) | LM_NORM_1 | LM_NORM_INF
+    // tiled resolver (LM_OPT_RESOLVE_MODE = 1; csrc/pairs.cu): allocated when the mode is first switched on
+    int resolve_mode;      // 0: nine phase launches (default) | 1: one tiled launch per phase range
+    int resolve_tile_smem; // LM_OPT_RESOLVE_TILE_SMEM: bytes of species a tile keeps in shared memory
+    bool resolve_all_in_begin;   // this step's phases 6-8 already ran with 0-5 (tiled, single handle)
+    int8_t *sp_snap;       // [max_particles] species before the first phase of a tiled launch
+    int8_t *tile_scratch;  // [4 * max_particles + 16 * tiles] tiles that do not fit in shared memory
+    unsigned long long *tile_scratch_used;
     // explicit-order resolver workspace
     unsigned long long *head;   // [max_particles]
     int32_t *pending[2];        // [max_pairs] each

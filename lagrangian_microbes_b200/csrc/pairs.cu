@@ -48,6 +48,8 @@
 //      than HEAVY_TESTS candidate pairs (dense clusters) are resolved by the whole warp: the hits of one
 //      anchor are independent except through the anchor's species, a 3-state value, so a run of them is a
 //      prefix scan over 3->3 maps.
+#include <algorithm>
+
 #include "lm_internal.cuh"
 #include "philox.cuh"
 
@@ -850,6 +852,240 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
     return cudaMemcpyAsync(h->n_pairs_snap, &h->ctr->n_pairs, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, s);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Tiled resolver (LM_OPT_RESOLVE_MODE = 1; experimental, default off).  ONE launch for a whole range of phases.
+//
+// The nine phase launches above are latency-bound: every pair costs a dependent chain entry -> species (L2 round
+// trips, 1 useful byte per 32-byte sector), and every phase waits for its slowest warp.  But the canonical order only
+// couples NEIGHBOURING cells, phase by phase: what an earlier phase did wrong at a cell can reach at most one cell
+// further per coupling phase.  East units couple columns (2k, 2k+1) in phase 1 and (2k+1, 2k+2) in phase 2; the cross
+// phases couple rows (2k, 2k+1) in 3-5 and (2k+1, 2k+2) in 6-8, and columns by one in 3, 5, 6, 8.  So a CTA that loads a
+// tile of cells plus a halo of TILE_HX = 6 columns and TILE_HY = 2 rows on every side (tile origin on even rows and
+// columns), copies the species of those cells from a SNAPSHOT taken before the first phase into shared memory, and runs
+// every unit that lies completely inside the loaded region, phase after phase with __syncthreads() in between, ends up
+// with exactly the sequential result on the INTERIOR of its tile -- the halo is computed redundantly (and possibly
+// wrongly at its rim), and only the interior is written back.  (Halo widths: tests/test_resolver_tiling_cpu.py runs
+// this scheme in NumPy against the global sequential order.)  Cost: the entries of the halo are read by more than one
+// CTA (loaded / interior = 1.5x at 64 x 16), which is bandwidth the path has to spare; gain: species accesses are
+// shared-memory accesses, there is one launch instead of nine, and a tile's slow unit delays only its own CTA.
+// A tile whose loaded region holds more microbes than fit the CTA's shared memory works on a private slice of a global
+// scratch array instead (same code through a generic pointer); a cell is loaded by at most four tiles, which bounds it.
+constexpr int TILE_X = 64, TILE_Y = 16, TILE_HX = 6, TILE_HY = 2;
+constexpr int TILE_LY = TILE_Y + 2 * TILE_HY;              // loaded rows
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_HEAVY_Q = 128;                          // dense units queued per phase for whole warps
+
+struct TileArgs {
+    const int8_t *__restrict__ sp_in;    // snapshot of the species before the first phase of this launch
+    int8_t *sp_out;                      // the live species (only interiors are written)
+    int8_t *scratch;                     // tiles that do not fit in shared memory
+    unsigned long long *scratch_used;
+    const int32_t *__restrict__ cell_start;
+    const uint32_t *__restrict__ hits;
+    const uint2 *__restrict__ rec;       // [5][rec_stride]
+    const uint2 *__restrict__ rec2;      // [5][rec2_stride]
+    long long rec_stride, rec2_stride;
+    const unsigned long long *n_pairs;
+    unsigned long long cap_words;
+    int ncx, rows_owned, rows_local;
+    int tiles_x;
+    int first, last;                     // phases
+    int smem_cap;                        // bytes of species a CTA can hold in shared memory
+    unsigned int heavy_min;
+};
+
+// Whole-warp resolution of one unit against the tile's private species (resolve_unit_warp above, with the two cells'
+// species reached through spA / spB: index = particle index in storage order).
+__device__ void resolve_unit_warp_tile(const uint32_t *__restrict__ hits, const uint2 *__restrict__ rec_d,
+                                       const uint2 *__restrict__ rec2_d, int cell, int cs0, int cs1, int oBeg,
+                                       int8_t *spA, int8_t *spB)
+{
+    const int lane = threadIdx.x & 31;
+    int cur_a = -1, sa = 0, sa0 = 0;
+    __syncwarp();
+    int a0 = cs0;
+    uint2 R = __ldg(rec_d + cell);
+    while (true) {
+        const uint32_t *ent = hits + R.x;
+        for (unsigned int k0 = 0; k0 < R.y; k0 += 32) {
+            const unsigned int k = k0 + lane;
+            const bool act = k < R.y;
+            const uint32_t en = act ? __ldg(ent + k) : 0u;
+            const int ar = (int)((en >> 24) & 31u);
+            unsigned int todo = __ballot_sync(0xffffffffu, act);
+            while (todo) {
+                const int lead = __ffs(todo) - 1;
+                const int ar0 = __shfl_sync(0xffffffffu, ar, lead);
+                const unsigned int m = __ballot_sync(0xffffffffu, act && ar == ar0) & todo;   // entries are sorted by anchor
+                todo &= ~m;
+                const int a = a0 + ar0;
+                if (a != cur_a) {
+                    if (cur_a >= 0 && sa != sa0 && lane == 0) spA[cur_a] = (int8_t)sa;
+                    __syncwarp();
+                    cur_a = a;
+                    sa = sa0 = ((volatile int8_t *)spA)[a];
+                }
+                if (!is_rps(sa)) continue;                     // winner = None for every pair of this anchor
+                const bool mine = (m >> lane) & 1u;
+                uint32_t M = MAP_ID, dec = 0;
+                int b = 0, sb = 0;
+                if (mine) {
+                    b = oBeg + (int)(en & B_REL_MASK); dec = en >> 29;
+                    sb = ((volatile int8_t *)spB)[b];
+                    if (is_rps(sb)) M = map_of_partner(sb, dec);
+                }
+                uint32_t P = M;                                // inclusive scan of maps in lane (= id_b) order
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, P, dd);
+                    if (lane >= dd) P = map_compose(P, t);
+                }
+                uint32_t E = __shfl_up_sync(0xffffffffu, P, 1);
+                if (lane == 0) E = MAP_ID;
+                if (mine && is_rps(sb)) {
+                    const int s_before = map_apply(E, sa);
+                    if (s_before != sb) spB[b] = (int8_t)rps_apply(s_before, sb, dec);
+                }
+                sa = map_apply(__shfl_sync(0xffffffffu, P, 31), sa);
+                __syncwarp();                                  // partner species written above are visible to later runs
+            }
+        }
+        a0 = (a0 | 31) + 1;                                    // the cell continues in the next 32-particle chunk?
+        if (a0 >= cs1) break;
+        R = __ldg(rec2_d + (a0 >> 5));
+    }
+    if (cur_a >= 0 && sa != sa0 && lane == 0) spA[cur_a] = (int8_t)sa;
+    __syncwarp();
+}
+
+// geometry of phase ph: which direction table it reads and which cells anchor a unit
+struct PhaseGeom { int mode, parity, dir, d_idx; };
+__device__ __forceinline__ PhaseGeom phase_geom(int ph)
+{
+    PhaseGeom g;
+    if (ph == 0) { g.mode = MODE_SAME; g.parity = 0; g.dir = 0; g.d_idx = 0; }
+    else if (ph <= 2) { g.mode = MODE_EAST; g.parity = ph - 1; g.dir = 0; g.d_idx = 1; }
+    else { g.mode = MODE_CROSS; g.parity = (ph - 3) / 3; g.dir = (ph - 3) % 3 - 1; g.d_idx = 3 + g.dir; }
+    return g;
+}
+
+__global__ void __launch_bounds__(TILE_THREADS) resolve_tiled_kernel(TileArgs A)
+{
+    extern __shared__ __align__(16) int8_t s_species[];    // [smem_cap]
+    __shared__ int s_p0[TILE_LY], s_cnt[TILE_LY], s_delta[TILE_LY];   // loaded row: first particle, particles, index delta
+    __shared__ long long s_off;                            // >= 0: this tile works in the global scratch
+    __shared__ int s_heavy[TILE_HEAVY_Q];
+    __shared__ unsigned int s_nheavy;
+    if (*A.n_pairs > A.cap_words) return;                  // the hand-off overflowed: reported by lm_sync_stats
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ncx = A.ncx;
+    const int tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x;
+    const int ix0 = tx * TILE_X, ix1 = min(ncx, ix0 + TILE_X);
+    const int iy0 = ty * TILE_Y, iy1 = min(A.rows_local, iy0 + TILE_Y);
+    const int lx0 = max(0, ix0 - TILE_HX), lx1 = min(ncx, ix1 + TILE_HX);
+    const int ly0 = max(0, iy0 - TILE_HY), ly1 = min(A.rows_local, iy1 + TILE_HY);
+    const int lw = lx1 - lx0, lh = ly1 - ly0;
+    if (tid < lh) {
+        const long long rc = (long long)(ly0 + tid) * ncx;
+        const int p0 = __ldg(A.cell_start + rc + lx0), p1 = __ldg(A.cell_start + rc + lx1);
+        s_p0[tid] = p0; s_cnt[tid] = p1 - p0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int off = 0;
+        for (int t = 0; t < lh; ++t) { s_delta[t] = off - s_p0[t]; off += s_cnt[t]; }
+        s_off = off > A.smem_cap ? (long long)atomicAdd(A.scratch_used, (unsigned long long)((off + 15) & ~15)) : -1ll;
+    }
+    __syncthreads();
+    int8_t *tsp = s_off >= 0 ? A.scratch + s_off : s_species;
+    for (int t = 0; t < lh; ++t) {
+        const int p0 = s_p0[t], cnt = s_cnt[t];
+        int8_t *dst = tsp + s_delta[t] + p0;
+        for (int i = tid; i < cnt; i += TILE_THREADS) dst[i] = __ldg(A.sp_in + p0 + i);
+    }
+    __syncthreads();
+
+    for (int ph = A.first; ph <= A.last; ++ph) {
+        const PhaseGeom G = phase_geom(ph);
+        const uint2 *rec_d = A.rec + (size_t)G.d_idx * A.rec_stride;
+        const uint2 *rec2_d = A.rec2 + (size_t)G.d_idx * A.rec2_stride;
+        if (tid == 0) s_nheavy = 0u;
+        __syncthreads();
+        for (int u = tid; u < lw * lh; u += TILE_THREADS) {
+            const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
+            int oy = cy, ox = cx;
+            bool on;
+            if (G.mode == MODE_SAME) on = cy < A.rows_owned;
+            else if (G.mode == MODE_EAST) { ox = cx + 1; on = cy < A.rows_owned && (cx & 1) == G.parity && ox < lx1; }
+            else { oy = cy + 1; ox = cx + G.dir; on = (cy & 1) == G.parity && oy < ly1 && ox >= lx0 && ox < lx1; }
+            if (!on) continue;
+            const int cell = cy * ncx + cx;
+            const int cs0 = __ldg(A.cell_start + cell), cs1 = __ldg(A.cell_start + cell + 1);
+            if (cs1 <= cs0) continue;                          // an empty cell's record is stale
+            const int ob = __ldg(A.cell_start + oy * ncx + ox);
+            uint2 r = __ldg(rec_d + cell);
+            unsigned int total = r.y;
+            for (int a0 = (cs0 | 31) + 1; a0 < cs1; a0 = (a0 | 31) + 1) total += __ldg(rec2_d + (a0 >> 5)).y;
+            if (total == 0u) continue;
+            if (total > A.heavy_min) {
+                const unsigned int q = atomicAdd(&s_nheavy, 1u);
+                if (q < (unsigned int)TILE_HEAVY_Q) { s_heavy[q] = u; continue; }
+            }
+            int8_t *spA = tsp + s_delta[ry], *spB = tsp + s_delta[oy - ly0];
+            int cur_a = -1, sa = 0, sa0 = 0, a0 = cs0;
+            while (true) {
+                const uint32_t *ent = A.hits + r.x;
+                for (unsigned int k = 0; k < r.y; k += 4) {
+                    const int nb = (int)min(4u, r.y - k);
+                    uint32_t en[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) en[j] = j < nb ? __ldg(ent + k + j) : 0u;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j < nb) {
+                            const int a = a0 + (int)((en[j] >> 24) & 31u), b = ob + (int)(en[j] & B_REL_MASK);
+                            if (a != cur_a) {
+                                if (cur_a >= 0 && sa != sa0) spA[cur_a] = (int8_t)sa;
+                                cur_a = a; sa = sa0 = spA[a];
+                            }
+                            const int sb = spB[b];
+                            if (sa != sb && is_rps(sa) && is_rps(sb)) {
+                                sa = rps_apply(sa, sb, en[j] >> 29);
+                                spB[b] = (int8_t)sa;
+                            }
+                        }
+                    }
+                }
+                a0 = (a0 | 31) + 1;                            // the cell goes on in the next 32-particle chunk?
+                if (a0 >= cs1) break;
+                r = __ldg(rec2_d + (a0 >> 5));
+            }
+            if (cur_a >= 0 && sa != sa0) spA[cur_a] = (int8_t)sa;
+        }
+        __syncthreads();
+        const unsigned int n_heavy = min(s_nheavy, (unsigned int)TILE_HEAVY_Q);
+        for (unsigned int q = warp; q < n_heavy; q += TILE_THREADS / 32) {      // dense units: one warp each
+            const int u = s_heavy[q];
+            const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
+            int oy = cy, ox = cx;
+            if (G.mode == MODE_EAST) ox = cx + 1;
+            else if (G.mode == MODE_CROSS) { oy = cy + 1; ox = cx + G.dir; }
+            const int cell = cy * ncx + cx;
+            resolve_unit_warp_tile(A.hits, rec_d, rec2_d, cell, __ldg(A.cell_start + cell), __ldg(A.cell_start + cell + 1),
+                                   __ldg(A.cell_start + oy * ncx + ox), tsp + s_delta[ry], tsp + s_delta[oy - ly0]);
+        }
+        __syncthreads();                                       // the phase is complete on the whole loaded region
+    }
+
+    // the interior of the tile is exact: write it back
+    for (int y = iy0; y < iy1; ++y) {
+        const long long rc = (long long)y * ncx;
+        const int p0 = __ldg(A.cell_start + rc + ix0), p1 = __ldg(A.cell_start + rc + ix1);
+        const int8_t *src = tsp + s_delta[y - ly0];
+        for (int p = p0 + tid; p < p1; p += TILE_THREADS) A.sp_out[p] = src[p];
+    }
+}
+
 template <int PB>
 static void launch_resolve_pb(const ResolveArgs &R, int upl, unsigned int blocks, cudaStream_t s)
 {
@@ -861,9 +1097,37 @@ static void launch_resolve_pb(const ResolveArgs &R, int upl, unsigned int blocks
 // phases [first, last] of the canonical cell-phase order on the local rows.  Strip boundaries sit on even
 // global rows, so local and global row parities agree; same-cell and east units cover the owned rows,
 // cross-row units may reach into the ghost row (local row rows_owned), only in phases 6-8.
+// LM_OPT_RESOLVE_MODE = 1: phases [first, last] as ONE launch of resolve_tiled_kernel on a snapshot of the species
+static cudaError_t launch_resolve_tiled(lm_handle_s *h, int8_t *sp, int first, int last, cudaStream_t s)
+{
+    const int64_t n_all = std::min<int64_t>(h->max_particles, h->n + ((h->has_north || h->has_south) ? h->ghost_cap : 0));
+    cudaError_t e = cudaMemcpyAsync(h->sp_snap, sp, (size_t)n_all, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(h->tile_scratch_used, 0, sizeof(unsigned long long), s);
+    if (e != cudaSuccess) return e;
+    TileArgs T;
+    T.sp_in = h->sp_snap; T.sp_out = sp; T.scratch = h->tile_scratch; T.scratch_used = h->tile_scratch_used;
+    T.cell_start = h->cell_start; T.hits = h->hits; T.rec = h->rec; T.rec2 = h->rec2;
+    T.rec_stride = h->max_cells; T.rec2_stride = h->max_particles / 32 + 2;
+    T.n_pairs = h->n_pairs_snap; T.cap_words = (unsigned long long)h->max_pairs;
+    T.ncx = h->grid.ncx; T.rows_owned = h->strip.rows_owned; T.rows_local = h->strip.rows_local;
+    T.first = first; T.last = last;
+    T.smem_cap = h->resolve_tile_smem;
+    T.heavy_min = h->resolve_heavy_min > 0 ? (unsigned int)h->resolve_heavy_min : 4u * HEAVY_MIN;
+    if (T.ncx <= 0 || T.rows_local <= 0) return cudaSuccess;
+    T.tiles_x = (T.ncx + TILE_X - 1) / TILE_X;
+    const long long tiles = (long long)T.tiles_x * ((T.rows_local + TILE_Y - 1) / TILE_Y);
+    e = cudaFuncSetAttribute(resolve_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_cap);
+    if (e != cudaSuccess) return e;
+    resolve_tiled_kernel<<<(unsigned)tiles, TILE_THREADS, (size_t)T.smem_cap, s>>>(T);
+    ++h->launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int last, cudaStream_t s)
 {
     if (h->rps_cap < 0) return cudaSuccess;
+    if (h->resolve_mode == 1) return launch_resolve_tiled(h, sp, first, last, s);
     ResolveArgs R;
     R.sp = sp; R.cell_start = h->cell_start; R.hits = h->hits;
     R.n_pairs = h->n_pairs_snap;
