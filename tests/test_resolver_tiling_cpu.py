@@ -79,3 +79,49 @@ def test_a_thinner_halo_is_not_enough():
         bad_rows += int((_tiled(sp0, order, u, cx, cy, 40, 22, 8, 4, HX, 1, p) != want).sum())
         bad_cols += int((_tiled(sp0, order, u, cx, cy, 40, 22, 8, 4, 2, HY, p) != want).sum())
     assert bad_rows > 0 and bad_cols > 0
+
+
+@pytest.mark.parametrize("first,last", [(0, 8), (0, 5), (6, 8)])
+@pytest.mark.parametrize("clustered", [False, True])
+def test_transliterated_kernels_on_the_emulated_hand_off(first, last, clustered):
+    """The index arithmetic of the CUDA resolvers (records, continuation segments, anchor / partner offsets, the tiled
+    kernel's row deltas and interior write-back), transliterated in tests/handoff_emulator.py and run on an emulated
+    hand-off: the nine-phase resolver validates the emulated layout against the oracle, the tiled one must agree."""
+    import handoff_emulator as he
+    p = (0.55, 0.6, 0.9)
+    ncx, ncy = 90, 21                                  # two tiles across, two up, ragged on both sides
+    rng = np.random.default_rng(7 + first)
+    r = 0.01
+    h = r * (1 + 2.0 ** -20)
+    grid = dict(x0=200.0, y0=30.0, inv_h=1.0 / h, ncx=ncx, ncy=ncy)
+    n = 5000
+    lon = 200.0 + ncx * h * rng.random(n)
+    lat = 30.0 + ncy * h * rng.random(n)
+    if clustered:                                      # cells with 40-70 microbes: segments continue across chunks
+        k = 0
+        for _ in range(12):
+            m = int(rng.integers(40, 71))
+            lon[k:k + m] = 200.0 + h * (int(rng.integers(0, ncx)) + rng.random(m))
+            lat[k:k + m] = 30.0 + h * (int(rng.integers(0, ncy)) + rng.random(m))
+            k += m
+    lon, lat = lon.astype(np.float32), lat.astype(np.float32)
+    sp0 = rng.integers(1, 4, n).astype(np.int8)
+    sp0[::41] = 0
+    pairs = opairs.query_pairs_reference_array(lon, lat, r)
+    order, phase = orps.cell_phase_order(pairs, lon, lat, grid)
+    u = philox.pair_uniforms(order[:, 0], order[:, 1], 2, 4)
+    H = he.build(lon, lat, order, u, p, grid)
+    if clustered:
+        assert (np.diff(H["cell_start"]) > 32).any()
+    sel_before = phase < first
+    sp_before, _ = orps.rps_sequential_c(sp0.copy(), order[sel_before], u[sel_before], *p)
+    sel = (phase >= first) & (phase <= last)
+    want, draws = orps.rps_sequential_c(sp_before.copy(), order[sel], u[sel], *p)
+    assert draws > 100
+    stored = sp_before[H["ids"]].astype(np.int64)       # storage order
+    got_phases = he.resolve_phases(H, stored.copy(), first, last)
+    assert np.array_equal(got_phases, want[H["ids"]]), "the emulated hand-off / phase walk disagrees with the oracle"
+    got_tiled = he.resolve_tiled(H, stored.copy(), first, last)
+    assert np.array_equal(got_tiled, want[H["ids"]]), "%d species differ" % int((got_tiled != want[H["ids"]]).sum())
+    small = he.resolve_tiled(H, stored.copy(), first, last, tile_x=16, tile_y=4)
+    assert np.array_equal(small, want[H["ids"]])
