@@ -281,7 +281,7 @@ int lm_phase_times(lm_handle h, float *ms_out);
  * which the reference's 1-based hist[bin] cannot hold), [bins + 1] = pairs beyond the last bin.  The entries always
  * sum to n (n - 1) / 2.  The bin is decided on the float32 haversine argument `a` against bin edges computed in
  * double, so a pair whose distance is within float32 rounding of an edge may land in the neighbouring bin compared
- * with a float32 evaluation of asin / log10 (tests/test_gpu_analysis.py states the band).  n < 2^24,
+ * with a float32 evaluation of asin / log10 (tests/test_gpu_zz_analysis.py states the band).  n < 2^24,
  * 1 <= bins <= LM_PDH_MAX_BINS (the reference uses 70).  Compute-bound: n^2 / 2 pair evaluations. */
 #define LM_PDH_MAX_BINS 126
 int lm_pair_distance_hist(const float *lat, const float *lon, int64_t n, float radius_m, int32_t bins,

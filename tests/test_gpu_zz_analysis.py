@@ -13,6 +13,8 @@ import pytest
 
 from oracle import analysis as oa
 
+# (File name: sorts after every verified GPU test, so that a fault in a kernel that has never run cannot poison the
+# CUDA context of the tests before it.)
 # These kernels were written after the round's GPU budget had been spent: until their first run on hardware the tests
 # are expected-to-fail-allowed (an XPASS in the log means parity is green; the marker goes away then).
 pytestmark = [pytest.mark.gpu,

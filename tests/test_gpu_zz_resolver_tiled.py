@@ -12,6 +12,8 @@ from oracle import pairs as opairs
 from oracle import philox
 from oracle import rps as orps
 
+# (File name: sorts after every verified GPU test, so that a fault in a kernel that has never run cannot poison the
+# CUDA context of the tests before it.)
 # Written after round 1's GPU budget had been spent: expected-to-fail-allowed until the first hardware run
 # (XPASS in the log = parity green; the marker goes away then).  The mode is off by default.
 pytestmark = [pytest.mark.gpu,

@@ -3,7 +3,7 @@
     python tools/tiled_sweep.py config2:1500:200 shard:0:20 shard:1000:20 config3:0:10 config3:400:10
 
 Each argument is workload:steps_before:timed_steps; consecutive arguments of one workload continue the same run.
-Both modes produce identical species (tests/test_gpu_resolver_tiled.py), so they can be switched inside one run.
+Both modes produce identical species (tests/test_gpu_zz_resolver_tiled.py), so they can be switched inside one run.
 Prints one JSON line per (state, setting): ms per step (CUDA events, side stream joined) and the event-timed phases."""
 import json
 import sys
