@@ -874,6 +874,8 @@ constexpr int TILE_X = 64, TILE_Y = 16, TILE_HX = 6, TILE_HY = 2;
 constexpr int TILE_LY = TILE_Y + 2 * TILE_HY;              // loaded rows
 constexpr int TILE_THREADS = 256;
 constexpr int TILE_HEAVY_Q = 128;                          // dense units queued per phase for whole warps
+constexpr int TILE_LX = TILE_X + 2 * TILE_HX;              // loaded columns
+constexpr int TILE_UPT = (TILE_LX * TILE_LY + TILE_THREADS - 1) / TILE_THREADS;   // units per thread and phase (6)
 
 struct TileArgs {
     const int8_t *__restrict__ sp_in;    // snapshot of the species before the first phase of this launch
@@ -969,13 +971,13 @@ __device__ __forceinline__ PhaseGeom phase_geom(int ph)
     return g;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS) resolve_tiled_kernel(TileArgs A)
+__global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs A)
 {
     extern __shared__ __align__(16) int8_t s_species[];    // [smem_cap]
     __shared__ int s_p0[TILE_LY], s_cnt[TILE_LY], s_delta[TILE_LY];   // loaded row: first particle, particles, index delta
     __shared__ long long s_off;                            // >= 0: this tile works in the global scratch
     __shared__ int s_heavy[TILE_HEAVY_Q];
-    __shared__ unsigned int s_nheavy;
+    __shared__ unsigned int s_nheavy, s_phase_pairs;
     if (*A.n_pairs > A.cap_words) return;                  // the hand-off overflowed: reported by lm_sync_stats
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncx = A.ncx;
@@ -1009,37 +1011,69 @@ __global__ void __launch_bounds__(TILE_THREADS) resolve_tiled_kernel(TileArgs A)
         const PhaseGeom G = phase_geom(ph);
         const uint2 *rec_d = A.rec + (size_t)G.d_idx * A.rec_stride;
         const uint2 *rec2_d = A.rec2 + (size_t)G.d_idx * A.rec2_stride;
-        if (tid == 0) s_nheavy = 0u;
+        if (tid == 0) { s_nheavy = 0u; s_phase_pairs = 0u; }
         __syncthreads();
-        for (int u = tid; u < lw * lh; u += TILE_THREADS) {
-            const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
-            int oy = cy, ox = cx;
-            bool on;
-            if (G.mode == MODE_SAME) on = cy < A.rows_owned;
-            else if (G.mode == MODE_EAST) { ox = cx + 1; on = cy < A.rows_owned && (cx & 1) == G.parity && ox < lx1; }
-            else { oy = cy + 1; ox = cx + G.dir; on = (cy & 1) == G.parity && oy < ly1 && ox >= lx0 && ox < lx1; }
-            if (!on) continue;
-            const int cell = cy * ncx + cx;
-            const int cs0 = __ldg(A.cell_start + cell), cs1 = __ldg(A.cell_start + cell + 1);
-            if (cs1 <= cs0) continue;                          // an empty cell's record is stale
-            const int ob = __ldg(A.cell_start + oy * ncx + ox);
-            uint2 r = __ldg(rec_d + cell);
-            unsigned int total = r.y;
-            for (int a0 = (cs0 | 31) + 1; a0 < cs1; a0 = (a0 | 31) + 1) total += __ldg(rec2_d + (a0 >> 5)).y;
-            if (total == 0u) continue;
-            if (total > A.heavy_min) {
+        // ---- pass 1: the units of this thread (u = tid, tid + 256, ...: at most TILE_UPT) and their pair counts.
+        // "Dense" is relative, as in resolve_phase_kernel: in a crowded tile every unit is long, the lanes are evenly
+        // loaded and the lane walk is the efficient way; only a unit far above a lane's fair share goes to a warp.
+        uint2 rr[TILE_UPT];
+        unsigned int tot[TILE_UPT];
+        unsigned int mine = 0;
+#pragma unroll
+        for (int k = 0; k < TILE_UPT; ++k) {
+            rr[k] = make_uint2(0u, 0u);
+            tot[k] = 0u;
+            const int u = tid + k * TILE_THREADS;
+            if (u < lw * lh) {
+                const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
+                bool on;
+                if (G.mode == MODE_SAME) on = cy < A.rows_owned;
+                else if (G.mode == MODE_EAST) on = cy < A.rows_owned && (cx & 1) == G.parity && cx + 1 < lx1;
+                else on = (cy & 1) == G.parity && cy + 1 < ly1 && cx + G.dir >= lx0 && cx + G.dir < lx1;
+                if (on) {
+                    const int cell = cy * ncx + cx;
+                    const int cs0 = __ldg(A.cell_start + cell), cs1 = __ldg(A.cell_start + cell + 1);
+                    if (cs1 > cs0) {                           // an empty cell's record is stale
+                        rr[k] = __ldg(rec_d + cell);
+                        unsigned int total = rr[k].y;
+                        for (int a0 = (cs0 | 31) + 1; a0 < cs1; a0 = (a0 | 31) + 1) total += __ldg(rec2_d + (a0 >> 5)).y;
+                        tot[k] = total;
+                        mine += total;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, dd);
+        if (lane == 0 && mine) atomicAdd(&s_phase_pairs, mine);
+        __syncthreads();
+        const unsigned int limit = max(A.heavy_min, 4u * (s_phase_pairs / (unsigned int)TILE_THREADS));
+        // ---- pass 2: walk them (or queue the dense ones for whole warps)
+#pragma unroll
+        for (int k = 0; k < TILE_UPT; ++k) {
+            if (tot[k] == 0u) continue;
+            const int u = tid + k * TILE_THREADS;
+            if (tot[k] > limit) {
                 const unsigned int q = atomicAdd(&s_nheavy, 1u);
                 if (q < (unsigned int)TILE_HEAVY_Q) { s_heavy[q] = u; continue; }
             }
+            const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
+            int oy = cy, ox = cx;
+            if (G.mode == MODE_EAST) ox = cx + 1;
+            else if (G.mode == MODE_CROSS) { oy = cy + 1; ox = cx + G.dir; }
+            const int cell = cy * ncx + cx;
+            const int cs0 = __ldg(A.cell_start + cell), cs1 = __ldg(A.cell_start + cell + 1);
+            const int ob = __ldg(A.cell_start + oy * ncx + ox);
+            uint2 r = rr[k];
             int8_t *spA = tsp + s_delta[ry], *spB = tsp + s_delta[oy - ly0];
             int cur_a = -1, sa = 0, sa0 = 0, a0 = cs0;
             while (true) {
                 const uint32_t *ent = A.hits + r.x;
-                for (unsigned int k = 0; k < r.y; k += 4) {
-                    const int nb = (int)min(4u, r.y - k);
+                for (unsigned int kk = 0; kk < r.y; kk += 4) {
+                    const int nb = (int)min(4u, r.y - kk);
                     uint32_t en[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) en[j] = j < nb ? __ldg(ent + k + j) : 0u;
+                    for (int j = 0; j < 4; ++j) en[j] = j < nb ? __ldg(ent + kk + j) : 0u;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         if (j < nb) {
