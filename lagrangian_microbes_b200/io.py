@@ -125,3 +125,40 @@ def write_png(filepath, rgb):
         f.write(chunk(b"IDAT", zlib.compress(raw.tobytes(), 6)))
         f.write(chunk(b"IEND", b""))
     return filepath
+
+
+class RecordAssembler:
+    """Dense (N, Nt) record arrays of a run, filled one step at a time, written in the layout of the reference's
+    ``microbe_data.nc`` (interaction_simulator.py:62-77, :108-110, :119-122).  ``stride`` keeps every stride-th step
+    (at 9 B per microbe-step the dense record of 490,000 microbes x 7,670 steps is 33.8 GB, which
+    the reference holds in RAM: docs/disk_usage.txt, interaction_simulator.py:62-66)."""
+
+    def __init__(self, n_particles, n_steps, start_time, dt, stride=1):
+        assert stride >= 1 and n_steps >= 0
+        self.stride = int(stride)
+        self.n_steps = int(n_steps)
+        self.kept_steps = list(range(0, self.n_steps, self.stride))
+        nt = len(self.kept_steps)
+        self.times = [start_time + k * dt for k in self.kept_steps]
+        self.longitude = np.zeros((n_particles, nt), dtype=np.float32)
+        self.latitude = np.zeros((n_particles, nt), dtype=np.float32)
+        self.species = np.zeros((n_particles, nt), dtype=np.int8)
+        self.filled = 0
+
+    def wants(self, step):
+        return 0 <= step < self.n_steps and step % self.stride == 0
+
+    def put(self, step, lon, lat, species):
+        assert self.wants(step)
+        col = step // self.stride
+        self.longitude[:, col] = lon
+        self.latitude[:, col] = lat
+        self.species[:, col] = species
+        self.filled += 1
+
+    def write(self, output_dir, filename="microbe_data.nc"):
+        assert self.filled == len(self.kept_steps), "%d of %d columns filled" % (self.filled, len(self.kept_steps))
+        os.makedirs(output_dir, exist_ok=True)
+        return write_particle_file(os.path.join(output_dir, filename),
+                                   {"longitude": self.longitude, "latitude": self.latitude, "species": self.species},
+                                   self.times)

@@ -199,6 +199,43 @@ class FusedSimulation:
         for _ in range(n_steps):
             self.step()
 
+    def run_to_file(self, output_dir, start_time, end_time, dt, stride=1, filename="microbe_data.nc"):
+        """The reference's end product in one pass: ``(end_time - start_time) // dt`` fused steps, their per-step
+        record written as ``microbe_data.nc`` -- what rock_paper_scissors_example.py:25-36 produces through
+        ParticleAdvecter.time_step + create_netcdf_file + InteractionSimulator.time_step, without the round trip
+        through ``particle_data.nc``.  Column k holds the positions after step k's advection and the species after
+        step k's interactions (particle_advecter.py:233-235 with its quirk Q2, interaction_simulator.py:108-110).
+        ``stride`` keeps every stride-th step.  Records travel in pairs of pinned buffers under the steps that follow
+        them (lm_record_next_step).  Returns (path, per-step species counts of the kept steps as an (nt, 3) array)."""
+        from . import io as lmio
+        from datetime import timedelta
+        assert isinstance(dt, timedelta) and abs(dt.total_seconds() - self.dt) < 1e-9, "dt differs from the simulation's"
+        n_steps = (end_time - start_time) // dt
+        asm = lmio.RecordAssembler(self.n, n_steps, start_time, dt, stride)
+        rec = [tuple(torch.empty(self.n, dtype=t).pin_memory() for t in (torch.float32, torch.float32, torch.int8))
+               for _ in range(2)]
+        in_flight = []                                   # (step, buffer set) whose copies have been issued
+
+        def drain():
+            self.engine.host_copies_sync()
+            for step, k in in_flight:
+                asm.put(step, rec[k][0].numpy(), rec[k][1].numpy(), rec[k][2].numpy())
+            in_flight.clear()
+
+        for step in range(n_steps):
+            if asm.wants(step):
+                if len(in_flight) == 2:
+                    drain()
+                k = len(in_flight)
+                self.step(record=rec[k])
+                in_flight.append((step, k))
+            else:
+                self.step()
+        drain()
+        path = asm.write(output_dir, filename)
+        counts = np.stack([(asm.species == s).sum(axis=0) for s in (1, 2, 3)], axis=1)
+        return path, counts
+
     def stats(self):
         """Counters of the most recent step (synchronises)."""
         return self.engine.sync_stats()

@@ -283,3 +283,27 @@ def test_cf_time_units():
     assert decode_cf_time(np.array([90], dtype=np.int64), "seconds since 1970-1-1 0:0:0")[0] == np.datetime64("1970-01-01T00:01:30")
     with pytest.raises(ValueError):
         decode_cf_time(np.array([1]), "fortnights since 2000-01-01")
+
+
+def test_record_assembler_keeps_every_stride_th_step_in_the_reference_layout(tmp_path):
+    from datetime import datetime, timedelta
+    from lagrangian_microbes_b200 import io as lmio
+    n, steps, stride = 50, 11, 3
+    t0, dt = datetime(2018, 1, 1), timedelta(hours=1)
+    asm = lmio.RecordAssembler(n, steps, t0, dt, stride)
+    assert asm.kept_steps == [0, 3, 6, 9] and [asm.wants(k) for k in (0, 1, 3, 11)] == [True, False, True, False]
+    rng = np.random.default_rng(0)
+    cols = {}
+    for k in asm.kept_steps:
+        cols[k] = (rng.random(n).astype(np.float32), rng.random(n).astype(np.float32), rng.integers(1, 4, n).astype(np.int8))
+        asm.put(k, *cols[k])
+    path = asm.write(str(tmp_path / "out"))
+    assert os.path.basename(path) == "microbe_data.nc"
+    back = lmio.read_particle_file(path)                         # dims ("particle number", "time"), interaction_simulator.py:68-77
+    assert back.times == [t0 + k * dt for k in asm.kept_steps]
+    for j, k in enumerate(asm.kept_steps):
+        assert np.array_equal(back["longitude"][:, j], cols[k][0]) and np.array_equal(back["species"][:, j], cols[k][2])
+    short = lmio.RecordAssembler(n, steps, t0, dt, stride)
+    short.put(0, *cols[0])
+    with pytest.raises(AssertionError):
+        short.write(str(tmp_path / "out2"))
