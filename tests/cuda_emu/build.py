@@ -1,0 +1,74 @@
+"""TEST INFRASTRUCTURE ONLY -- builds tests/cuda_emu/_build/libemu.so: csrc/pairs.cu and csrc/analysis.cu compiled by g++
+against the CPU stand-in for the CUDA execution model (cuda_runtime.h in this directory), so that the CPU test suite
+can EXECUTE the kernels.  The sources are used as they are, except for three mechanical rewrites that have no C++
+spelling:  kernel<<<grid, block, smem, stream>>>(args)  ->  emu::launch(grid, block, smem, [&] { kernel(args); }),
+extern __shared__ T name[]  ->  T *name = (T *)emu::dyn_smem,  and inline PTX (a prefetch hint) is dropped."""
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "lagrangian_microbes_b200", "csrc")
+OUT = os.path.join(HERE, "_build")
+SOURCES = ["pairs.cu", "analysis.cu"]
+
+
+def _split_top_level(s):
+    parts, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    parts.append(cur.strip())
+    return parts
+
+
+_LAUNCH = re.compile(r"([A-Za-z_]\w*(?:<[^<>;()]*>)?)<<<([^;]*?)>>>\(([^;]*)\);")
+_DYN = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([A-Za-z_][\w ]*?)\s+(\w+)\[\];")
+_ASM = re.compile(r'asm volatile\("[^"]*"[^;]*;')
+
+
+def transform(text):
+    def launch(m):
+        kernel, cfg, args = m.group(1), _split_top_level(m.group(2)), m.group(3)
+        assert len(cfg) in (2, 3, 4), cfg
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        return "emu::launch((unsigned int)(%s), (unsigned int)(%s), (size_t)(%s), [&] { %s(%s); });" % (cfg[0], cfg[1], smem, kernel, args)
+    text, n_launch = _LAUNCH.subn(launch, text)
+    text = _DYN.sub(lambda m: "%s *%s = reinterpret_cast<%s *>(emu::dyn_smem);" % (m.group(1), m.group(2), m.group(1)), text)
+    text = _ASM.sub(";", text)
+    assert "<<<" not in text and "extern __shared__" not in text
+    return text, n_launch
+
+
+def build(force=False):
+    so = os.path.join(OUT, "libemu.so")
+    deps = [os.path.join(CSRC, f) for f in SOURCES + ["lm_internal.cuh", "philox.cuh"]] + \
+           [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu.cpp", "harness.cpp", "build.py")]
+    if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
+        return so
+    os.makedirs(OUT, exist_ok=True)
+    cpps = []
+    for f in SOURCES:
+        text, n = transform(open(os.path.join(CSRC, f)).read())
+        assert n > 0, "no kernel launch found in " + f
+        path = os.path.join(OUT, f.replace(".cu", "_emu.cpp"))
+        with open(path, "w") as fh:
+            fh.write(text)
+        cpps.append(path)
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-fPIC", "-shared", "-ffp-contract=off", "-w",
+           "-I", HERE, "-I", CSRC, "-o", so + ".tmp"] + cpps + [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "harness.cpp")]
+    subprocess.check_call(cmd)
+    os.replace(so + ".tmp", so)
+    return so
+
+
+if __name__ == "__main__":
+    print(build(force=True))

@@ -1,0 +1,134 @@
+// TEST INFRASTRUCTURE ONLY.  A minimal CPU stand-in for the CUDA execution model, so that the kernels of
+// lagrangian_microbes_b200/csrc/*.cu can be EXECUTED by the CPU test suite (tests/test_kernels_emulated.py): one
+// std::thread per CUDA thread, one pthread barrier per CTA (__syncthreads) and per warp (__syncwarp and the
+// warp collectives), CTAs one after the other.  Data races, byte stores and atomics are the real thing; clocks,
+// memory spaces and scheduling are not modelled.  The product never includes this header: liblm_b200.so is built by
+// nvcc from the untouched sources, this shim is found first on the include path only by tests/cuda_emu/build.py.
+#pragma once
+#include <pthread.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __align__(n) alignas(n)
+#define __shared__ static          // function-local static: shared by the threads of the CTA (CTAs run one at a time)
+
+struct uint2 { unsigned int x, y; };
+struct int2 { int x, y; };
+struct alignas(16) uint4 { unsigned int x, y, z, w; };
+struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct uint3 { unsigned int x, y, z; };
+static inline uint2 make_uint2(unsigned int x, unsigned int y) { return uint2{x, y}; }
+static inline int2 make_int2(int x, int y) { return int2{x, y}; }
+static inline uint4 make_uint4(unsigned int x, unsigned int y, unsigned int z, unsigned int w) { return uint4{x, y, z, w}; }
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+constexpr cudaError_t cudaSuccess = 0;
+enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+
+namespace emu {
+struct Warp { pthread_barrier_t bar; unsigned long long slot[32]; };
+struct Cta { pthread_barrier_t bar; std::vector<Warp> warps; };
+extern thread_local Warp *t_warp;
+extern thread_local Cta *t_cta;
+extern thread_local int t_lane;
+extern void *dyn_smem;
+void launch(unsigned int grid, unsigned int block, size_t smem, const std::function<void()> &body);
+}  // namespace emu
+extern thread_local uint3 threadIdx, blockIdx, blockDim, gridDim;
+
+static inline void __syncthreads() { pthread_barrier_wait(&emu::t_cta->bar); }
+static inline void __syncwarp(unsigned int = 0xffffffffu) { pthread_barrier_wait(&emu::t_warp->bar); }
+
+template <class T> static inline T emu_exchange(T v, int src)
+{
+    static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    emu::t_warp->slot[emu::t_lane] = bits;
+    pthread_barrier_wait(&emu::t_warp->bar);
+    const unsigned long long got = emu::t_warp->slot[src & 31];
+    pthread_barrier_wait(&emu::t_warp->bar);
+    T r;
+    memcpy(&r, &got, sizeof(T));
+    return r;
+}
+template <class T> static inline T __shfl_sync(unsigned int, T v, int src) { return emu_exchange(v, src); }
+template <class T> static inline T __shfl_up_sync(unsigned int, T v, unsigned int d) { return emu_exchange(v, emu::t_lane >= (int)d ? emu::t_lane - (int)d : emu::t_lane); }
+template <class T> static inline T __shfl_xor_sync(unsigned int, T v, int m) { return emu_exchange(v, emu::t_lane ^ m); }
+static inline unsigned int __ballot_sync(unsigned int, int pred)
+{
+    emu::t_warp->slot[emu::t_lane] = pred ? 1ull : 0ull;
+    pthread_barrier_wait(&emu::t_warp->bar);
+    unsigned int m = 0;
+    for (int l = 0; l < 32; ++l) m |= (unsigned int)emu::t_warp->slot[l] << l;
+    pthread_barrier_wait(&emu::t_warp->bar);
+    return m;
+}
+static inline int __any_sync(unsigned int mask, int pred) { return __ballot_sync(mask, pred) != 0u; }
+
+template <class T> static inline T __ldg(const T *p) { return *p; }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicMax(int *p, int v)
+{
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+
+static inline int __popc(unsigned int x) { return __builtin_popcount(x); }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned int)x) : 32; }
+static inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((unsigned long long)a * b) >> 32); }
+static inline unsigned int __byte_perm(unsigned int a, unsigned int b, unsigned int sel)
+{
+    const unsigned long long src = ((unsigned long long)b << 32) | a;
+    unsigned int r = 0;
+    for (int i = 0; i < 4; ++i) r |= (unsigned int)((src >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);   // selector msb (sign replication) unused
+    return r;
+}
+// explicit-rounding intrinsics: plain IEEE operations (the emulator is compiled with -ffp-contract=off)
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline int __float2int_rn(float x)
+{
+    if (std::isnan(x)) return 0;
+    if (x >= 2147483648.0f) return 2147483647;
+    if (x <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)nearbyintf(x);
+}
+#define __log2f(x) log2f(x)          // glibc declares a private __log2f of its own
+static inline float sinpif(float x) { return (float)sin(M_PI * (double)x); }
+static inline float cospif(float x) { return (float)cos(M_PI * (double)x); }
+using std::max;
+using std::min;
+static inline unsigned int min(unsigned int a, int b) { return a < (unsigned int)b ? a : (unsigned int)b; }
+static inline long long max(long long a, int b) { return a > b ? a : b; }

@@ -1,0 +1,237 @@
+"""The CUDA kernels of csrc/pairs.cu and csrc/analysis.cu EXECUTED on the CPU (tests/cuda_emu: one std::thread per CUDA
+thread, barriers for __syncthreads / __syncwarp / the warp collectives) and held against the oracle.
+
+Why: kernels written when no GPU was at hand (the tiled resolver, the snapshot analyses) could otherwise only be
+compiled.  The emulator is itself checked by running the kernels that ARE verified on hardware -- the pair search and the
+nine-phase resolver -- through it: they must reproduce cKDTree's pair set and the reference's sequential rule
+(interactions.py:13-40 in canonical cell-phase order) here exactly as they do on the B200.  Sizes are tiny: a warp
+shuffle costs two pthread barriers."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import analysis as oa
+from oracle import pairs as opairs
+from oracle import philox
+from oracle import rps as orps
+from oracle.pairs import cell_index
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "cuda_emu"))
+
+P = (0.55, 0.6, 0.9)
+R = 0.01
+H = R * (1 + 2.0 ** -20)
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import build as emu_build
+    L = ctypes.CDLL(emu_build.build())
+    vp, i32, i64, u64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_double
+    L.emu_interact.restype = i64
+    L.emu_interact.argtypes = [vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, i32, i32, i32, i32, i32, dbl, dbl, dbl, dbl, u64, u64,
+                               i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp]
+    L.emu_pair_distance_hist.restype = i32
+    L.emu_pair_distance_hist.argtypes = [vp, vp, i64, ctypes.c_float, i32, vp]
+    L.emu_raster.restype = i32
+    L.emu_raster.argtypes = [vp, vp, vp, i64, dbl, dbl, dbl, dbl, i32, i32, vp, vp, i32, vp, vp]
+    return L
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else ctypes.c_void_p(0)
+
+
+class Cloud:
+    def __init__(self, seed, ncx, ncy, n, knots=0, knot_size=(10, 31)):
+        rng = np.random.default_rng(seed)
+        self.grid = dict(x0=200.0, y0=30.0, inv_h=1.0 / H, ncx=ncx, ncy=ncy)
+        lon = 200.0 + ncx * H * rng.random(n)
+        lat = 30.0 + ncy * H * rng.random(n)
+        k = 0
+        for _ in range(knots):
+            m = int(rng.integers(*knot_size))
+            lon[k:k + m] = 200.0 + H * (int(rng.integers(0, ncx)) + rng.random(m))
+            lat[k:k + m] = 30.0 + H * (int(rng.integers(0, ncy)) + rng.random(m))
+            k += m
+        self.lon, self.lat = lon.astype(np.float32), lat.astype(np.float32)
+        self.sp0 = rng.integers(1, 4, n).astype(np.int8)
+        self.sp0[::37] = 0                                  # species outside {1, 2, 3}
+        self.n = n
+        cx = cell_index(self.lon, 200.0, 1.0 / H, ncx)
+        cy = cell_index(self.lat, 30.0, 1.0 / H, ncy)
+        key = cy.astype(np.int64) * ncx + cx
+        self.ids = np.lexsort((np.arange(n), key)).astype(np.int32)            # storage slot -> id: (cell, id) order
+        self.cell_start = np.zeros(ncx * ncy + 1, dtype=np.int32)
+        np.cumsum(np.bincount(key, minlength=ncx * ncy), out=self.cell_start[1:])
+        self.pairs = opairs.query_pairs_reference_array(self.lon, self.lat, R)
+        self.order, self.phase = orps.cell_phase_order(self.pairs, self.lon, self.lat, self.grid)
+        self.u = philox.pair_uniforms(self.order[:, 0], self.order[:, 1], 17, 5)      # step 17, seed 5
+
+    def oracle(self, sp, first, last):
+        sel = (self.phase >= first) & (self.phase <= last)
+        out, _ = orps.rps_sequential_c(sp.copy(), self.order[sel], self.u[sel], *P)
+        return out
+
+    def run(self, emu, sp, mode, first=0, last=8, tile_smem=32768, heavy_min=0, batch=4, upl=0, find_path=0, want_pairs=False):
+        g = self.grid
+        lon_s, lat_s = np.ascontiguousarray(self.lon[self.ids]), np.ascontiguousarray(self.lat[self.ids])
+        sp_s = np.ascontiguousarray(sp[self.ids])
+        cap = self.pairs.shape[0] + 8
+        pairs_out = np.full((cap, 2), -1, dtype=np.int32) if want_pairs else None
+        ret = emu.emu_interact(_ptr(lon_s), _ptr(lat_s), _ptr(self.ids), _ptr(self.cell_start), _ptr(sp_s), self.n, self.n,
+                               g["x0"], g["y0"], g["inv_h"], g["ncx"], g["ncy"], 0, g["ncy"], g["ncy"], R, *P, 5, 17,
+                               mode, first, last, tile_smem, heavy_min, batch, upl, find_path, _ptr(pairs_out), cap, cap + 64,
+                               None, None, None)
+        assert ret >= 0
+        found, launches = ret & ((1 << 48) - 1), ret >> 48
+        assert found == self.pairs.shape[0], "pairs found"
+        out = np.empty_like(sp)
+        out[self.ids] = sp_s
+        if want_pairs:
+            return out, launches, opairs.sort_pairs(pairs_out[:found])
+        return out, launches
+
+
+@pytest.fixture(scope="module")
+def cloud():
+    return Cloud(1, 74, 19, 1800, knots=10)                  # two tiles across, two up, ragged; knots of 10-30 microbes
+
+
+def test_emulator_reproduces_the_hardware_verified_kernels(emu, cloud):
+    """Control: pair search + nine-phase resolver (verified on the B200) through the emulator."""
+    got, launches, pairs = cloud.run(emu, cloud.sp0, mode=0, want_pairs=True)
+    assert np.array_equal(pairs, cloud.pairs), "pair set differs from cKDTree.query_pairs"
+    want = cloud.oracle(cloud.sp0, 0, 8)
+    assert int((want != cloud.sp0).sum()) > 100
+    assert np.array_equal(got, want), "%d species differ" % int((got != want).sum())
+    assert launches == 10                                     # 1 search + 9 phases
+    got1, _ = cloud.run(emu, cloud.sp0, mode=0, batch=1, heavy_min=8, upl=2, find_path=1)     # other code paths of the same kernels
+    assert np.array_equal(got1, want)
+
+
+@pytest.mark.parametrize("tile_smem,heavy_min", [(32768, 0), (1024, 0), (32768, 8)])
+def test_tiled_resolver_executed(emu, cloud, tile_smem, heavy_min):
+    """resolve_tiled_kernel (LM_OPT_RESOLVE_MODE = 1): shared-memory tiles, scratch tiles (1 KB limit), whole-warp path."""
+    want = cloud.oracle(cloud.sp0, 0, 8)
+    got, launches = cloud.run(emu, cloud.sp0, mode=1, tile_smem=tile_smem, heavy_min=heavy_min)
+    assert np.array_equal(got, want), "%d species differ" % int((got != want).sum())
+    assert launches == 2                                      # 1 search + 1 tiled launch
+
+
+def test_tiled_resolver_phase_ranges(emu, cloud):
+    """The two ranges a strip launches around its halo exchange: 0-5, then 6-8 on the result."""
+    mid_want = cloud.oracle(cloud.sp0, 0, 5)
+    mid, _ = cloud.run(emu, cloud.sp0, mode=1, first=0, last=5)
+    assert np.array_equal(mid, mid_want)
+    end, _ = cloud.run(emu, mid, mode=1, first=6, last=8)
+    assert np.array_equal(end, cloud.oracle(cloud.sp0, 0, 8))
+
+
+def test_tiled_resolver_crowded_cells(emu):
+    """~12 microbes per cell: every unit is long, cells continue across 32-particle chunks, the relative dense limit
+    keeps the lane walk, a low absolute limit forces whole warps."""
+    c = Cloud(2, 20, 6, 1400, knots=3, knot_size=(40, 60))
+    want = c.oracle(c.sp0, 0, 8)
+    assert (np.diff(c.cell_start) > 32).any()
+    for heavy_min in (0, 16):
+        got, _ = c.run(emu, c.sp0, mode=1, heavy_min=heavy_min)
+        assert np.array_equal(got, want), "heavy_min %d: %d species differ" % (heavy_min, int((got != want).sum()))
+
+
+def test_pair_distance_histogram_executed(emu):
+    rng = np.random.default_rng(3)
+    for kind, n in (("patch", 700), ("clustered", 600), ("global", 1300)):
+        if kind == "patch":
+            lat, lon = 25 + 10 * rng.random(n), 205 + 10 * rng.random(n)
+        elif kind == "clustered":
+            lat = 30 + 1e-3 * rng.standard_normal(n) * rng.random(n) ** 4
+            lon = 210 + 1e-3 * rng.standard_normal(n) * rng.random(n) ** 4
+            lat[:20] = lat[20:40]; lon[:20] = lon[20:40]
+        else:
+            lat, lon = -80 + 160 * rng.random(n), 360 * rng.random(n)
+        lat, lon = lat.astype(np.float32), lon.astype(np.float32)
+        hist = np.full(72, 99, dtype=np.uint64)                  # the call zeroes its output
+        assert emu.emu_pair_distance_hist(_ptr(lat), _ptr(lon), n, 6371.228e3, 70, _ptr(hist)) == 0
+        h = hist.astype(np.int64)
+        lo, up = oa.pdh_bounds(lat, lon, bins=70)
+        assert h.sum() == n * (n - 1) // 2
+        assert np.all(lo <= h) and np.all(h <= up), (kind, h - lo, up - h)
+    hist = np.zeros(4, dtype=np.uint64)                          # bins = 2: nearly everything beyond the last bin
+    assert emu.emu_pair_distance_hist(_ptr(lat), _ptr(lon), n, 6371.228e3, 2, _ptr(hist)) == 0
+    assert hist.sum() == n * (n - 1) // 2 and hist[3] > 0
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_rasteriser_executed(emu, mode):
+    rng = np.random.default_rng(4)
+    n = 5000
+    lon = (204.0 + 12.0 * rng.random(n)).astype(np.float32)
+    lat = (24.0 + 12.0 * rng.random(n)).astype(np.float32)
+    lon[:5] = [205.0, 215.0, np.nextafter(np.float32(215.0), np.float32(0)), 210.0, np.nan]
+    lat[:5] = [25.0, 30.0, 30.0, 35.0, 30.0]
+    sp = rng.integers(0, 5, n).astype(np.int8)
+    w, h = 40, 24
+    pal = np.array([[255, 255, 255], [255, 0, 0], [50, 205, 50], [0, 0, 255]], dtype=np.uint8)
+    counts = np.full((3, h, w), 7, dtype=np.uint32)
+    top = np.full((h, w), 7, dtype=np.int32)
+    rgb = np.zeros((h, w, 3), dtype=np.uint8)
+    assert emu.emu_raster(_ptr(lon), _ptr(lat), _ptr(sp), n, 205.0, 215.0, 25.0, 35.0, w, h, _ptr(counts), _ptr(top), mode,
+                          _ptr(pal), _ptr(rgb)) == 0
+    want_counts, want_top = oa.raster_reference(lon, lat, sp, 205.0, 215.0, 25.0, 35.0, w, h)
+    assert np.array_equal(counts, want_counts) and np.array_equal(top, want_top)
+    assert np.array_equal(rgb, oa.compose_reference(want_counts, want_top, sp, pal, mode))
+
+
+@pytest.mark.parametrize("seed,ncx,ncy,n", [(11, 5, 3, 120), (12, 64, 16, 900), (13, 65, 17, 900), (14, 141, 5, 1200),
+                                             (15, 7, 40, 700)])
+def test_tiled_resolver_other_grids(emu, seed, ncx, ncy, n):
+    """Grids smaller than a tile, exactly one tile, one cell more than a tile, three tiles across, three up."""
+    c = Cloud(seed, ncx, ncy, n, knots=4)
+    want = c.oracle(c.sp0, 0, 8)
+    got, _ = c.run(emu, c.sp0, mode=1)
+    assert np.array_equal(got, want), "%d species differ" % int((got != want).sum())
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_strip_geometry(emu, mode):
+    """One latitude strip of a larger domain as the library holds it: rows [4, 12) owned, row 12 appended
+    as a ghost row whose microbes are partners only; phases 0-5, then 6-8, against the sequential order restricted to
+    the pairs this strip owns (anchor in an owned row).  mode 0 is the hardware-verified control."""
+    c = Cloud(21, 70, 19, 1700, knots=6)
+    g = c.grid
+    row0, rows_owned = 4, 8
+    cy = cell_index(c.lat, g["y0"], g["inv_h"], g["ncy"])
+    cx = cell_index(c.lon, g["x0"], g["inv_h"], g["ncx"])
+    local = (cy >= row0) & (cy <= row0 + rows_owned)                    # owned rows + the ghost row
+    idx = np.nonzero(local)[0]
+    key = (cy[idx] - row0).astype(np.int64) * g["ncx"] + cx[idx]
+    o = np.lexsort((idx, key))
+    ids = idx[o].astype(np.int32)                                       # storage slot -> global id; ghosts come last
+    n_all = ids.size
+    n_owned = int((cy[ids] < row0 + rows_owned).sum())
+    rows_local = rows_owned + 1
+    cell_start = np.zeros(g["ncx"] * rows_local + 1, dtype=np.int32)
+    np.cumsum(np.bincount(key, minlength=g["ncx"] * rows_local), out=cell_start[1:])
+    anchor_row = np.minimum(cy[c.order[:, 0]], cy[c.order[:, 1]])
+    mine = (anchor_row >= row0) & (anchor_row < row0 + rows_owned)
+    order, phase, u = c.order[mine], c.phase[mine], c.u[mine]
+    sp = c.sp0.copy()
+    lon_s, lat_s = np.ascontiguousarray(c.lon[ids]), np.ascontiguousarray(c.lat[ids])
+    for first, last in ((0, 5), (6, 8)):
+        sel = (phase >= first) & (phase <= last)
+        want, _ = orps.rps_sequential_c(sp.copy(), order[sel], u[sel], *P)
+        sp_s = np.ascontiguousarray(sp[ids])
+        cap = order.shape[0] + 64
+        ret = emu.emu_interact(_ptr(lon_s), _ptr(lat_s), _ptr(ids), _ptr(cell_start), _ptr(sp_s), n_owned, n_all,
+                               g["x0"], g["y0"], g["inv_h"], g["ncx"], g["ncy"], row0, rows_owned, rows_local, R, *P, 5, 17,
+                               mode, first, last, 32768, 0, 4, 0, 0, None, 0, cap, None, None, None)
+        assert ret >= 0 and (ret & ((1 << 48) - 1)) == order.shape[0]
+        got = sp.copy()
+        got[ids] = sp_s
+        assert np.array_equal(got, want), "phases %d-%d: %d species differ" % (first, last, int((got != want).sum()))
+        sp = want
+    assert (sp[ids[n_owned:]] != c.sp0[ids[n_owned:]]).any()            # the ghost row's microbes took part
