@@ -106,6 +106,13 @@ def lib():
     elif _stale() and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
         build()
     L = ctypes.CDLL(_SO)
+    declare(L)
+    _lib = L
+    return L
+
+
+def declare(L):
+    """argtypes / restypes of every entry point of include/lm_b200.h on a loaded library."""
     vp, i32, i64, u64, dbl, flt = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64,
                                   ctypes.c_double, ctypes.c_float)
     P = ctypes.POINTER
@@ -155,7 +162,6 @@ def lib():
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    _lib = L
     return L
 
 

@@ -1,4 +1,4 @@
-"""TEST INFRASTRUCTURE ONLY -- builds tests/cuda_emu/_build/libemu.so: csrc/pairs.cu and csrc/analysis.cu compiled by g++
+"""TEST INFRASTRUCTURE ONLY -- builds tests/cuda_emu/_build/libemu.so: every csrc/*.cu of the product compiled by g++
 against the CPU stand-in for the CUDA execution model (cuda_runtime.h in this directory), so that the CPU test suite
 can EXECUTE the kernels.  The sources are used as they are, except for three mechanical rewrites that have no C++
 spelling:  kernel<<<grid, block, smem, stream>>>(args)  ->  emu::launch(grid, block, smem, [&] { kernel(args); }),
@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "lagrangian_microbes_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["pairs.cu", "analysis.cu"]
+SOURCES = ["api.cu", "advect.cu", "bin.cu", "strip.cu", "pairs.cu", "resolve.cu", "analysis.cu"]    # = _lib._SOURCES
 
 
 def _split_top_level(s):
@@ -58,7 +58,7 @@ def build(force=False):
     cpps = []
     for f in SOURCES:
         text, n = transform(open(os.path.join(CSRC, f)).read())
-        assert n > 0, "no kernel launch found in " + f
+        assert n > 0 or f == "api.cu", "no kernel launch found in " + f
         path = os.path.join(OUT, f.replace(".cu", "_emu.cpp"))
         with open(path, "w") as fh:
             fh.write(text)

@@ -8,10 +8,6 @@
 
 using namespace lm;
 
-namespace lm {
-void set_last_cuda_error(cudaError_t, const char *) {}
-}
-
 template <class T> static T *zalloc(size_t count) { return static_cast<T *>(calloc(count ? count : 1, sizeof(T))); }
 
 extern "C" {

@@ -49,6 +49,9 @@ def test_product_never_imports_the_oracle():
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
             assert "scipy.spatial" not in src, fn
+            assert "cuda_emu" not in src and "libemu" not in src, fn       # the CPU emulator of the kernels is test-only
+    for bench_like in ("bench.py", "__graft_entry__.py"):
+        assert "cuda_emu" not in open(os.path.join(ROOT, bench_like)).read(), bench_like
 
 
 def test_utils_and_initial_condition():

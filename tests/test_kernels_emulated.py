@@ -235,3 +235,82 @@ def test_strip_geometry(emu, mode):
         assert np.array_equal(got, want), "phases %d-%d: %d species differ" % (first, last, int((got != want).sum()))
         sp = want
     assert (sp[ids[n_owned:]] != c.sp0[ids[n_owned:]]).any()            # the ghost row's microbes took part
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The whole C ABI (csrc/api.cu on top of every kernel), executed: lm_create .. lm_step .. lm_state_get on host arrays.
+@pytest.fixture(scope="module")
+def abi():
+    import build as emu_build
+    from lagrangian_microbes_b200 import _lib
+    return _lib.declare(ctypes.CDLL(emu_build.build()))
+
+
+def _small_field():
+    from conftest import golden
+    from oracle import rk4 as ork4
+    g = golden("rk4_small.npz")
+    return ork4.FieldSet(g["grid_lon"], g["grid_lat"], g["grid_time"], g["u"], g["v"])
+
+
+@pytest.mark.parametrize("resolve_mode,stats_every_step", [(0, True), (1, True), (1, False)])
+def test_fused_steps_through_the_c_abi(abi, resolve_mode, stats_every_step):
+    """Four lm_step calls (RK4 advection, binning, pair search, RPS, stats) on 1,200 microbes, step by step against the
+    oracle: positions vs the RK4 restatement from identical inputs, pairs vs cKDTree on the library's positions,
+    species vs the reference rule in canonical order -- tests/test_gpu_parity.py::test_fused_simulation_matches_oracle_loop
+    in miniature, on the emulator, with the nine-phase and the tiled resolver (one launch for all nine phases)."""
+    from lagrangian_microbes_b200 import _lib
+    from lagrangian_microbes_b200.engine import make_grid
+    from lagrangian_microbes_b200.particle_advecter import StageClock
+    from oracle import rk4 as ork4
+    L = abi
+    fs = _small_field()
+    n, r, p, seed, dt, n_steps = 1200, 0.01, (0.55, 0.6, 0.9), 5, 3600.0, 4
+    rng = np.random.default_rng(8)
+    lon = (201.5 + 0.25 * rng.random(n)).astype(np.float32)
+    lat = (32.5 + 0.16 * rng.random(n)).astype(np.float32)
+    sp0 = rng.integers(1, 4, n).astype(np.int8)
+    h = ctypes.c_void_p()
+    max_cells, cap = 1 << 16, 40 * n
+    assert L.lm_create(ctypes.byref(h), 0, n, max_cells, cap) == 0
+    try:
+        u, v = np.ascontiguousarray(fs.u), np.ascontiguousarray(fs.v)
+        glon, glat = np.ascontiguousarray(fs.lon), np.ascontiguousarray(fs.lat)
+        assert L.lm_set_field(h, _ptr(u), _ptr(v), _ptr(glon), _ptr(glat), *u.shape) == 0
+        grid = make_grid(float(lon.min()), float(lon.max()), float(lat.min()), float(lat.max()), r, n, max_cells, margin=0.1)
+        assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+        assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, resolve_mode) == 0
+        assert L.lm_state_set(h, _ptr(lon), _ptr(lat), _ptr(sp0), None, n, None) == 0
+        clock = StageClock(fs.time)
+        pairs = np.zeros((cap, 2), dtype=np.int32)
+        lon_prev, lat_prev, sp_ref = lon.copy(), lat.copy(), sp0.copy()
+        gl, ga, gs = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.int8)
+        t, ti, total, launches0 = 0.0, 0, 0, L.lm_launch_count(h)
+        flags = _lib.LM_STEP_ADVECT | _lib.LM_STEP_INTERACT | _lib.LM_STEP_EMIT_PAIRS
+        for step in range(n_steps):
+            st_times = clock.next_step(dt)
+            prm = _lib.RpsParams(*p, seed, step)
+            f = flags | (_lib.LM_STEP_STATS if stats_every_step else 0)
+            assert L.lm_step(h, f, ctypes.byref(st_times), dt, 0.0, r, ctypes.byref(prm), _ptr(pairs), cap, None) == 0
+            stats = _lib.Stats()
+            assert L.lm_sync_stats(h, ctypes.byref(stats), None) == 0
+            assert L.lm_state_get(h, _ptr(gl), _ptr(ga), _ptr(gs), None) == 0
+            a32, b32, ti_new, oob = ork4.rk4_step_f32(fs, lon_prev, lat_prev, t, dt, ti)
+            assert oob == 0 and stats.n_out_of_bounds == 0
+            assert np.max(np.abs(gl - a32) / np.abs(a32)) < 1e-6 and np.max(np.abs(ga - b32) / np.abs(b32)) < 1e-6
+            want_pairs = opairs.query_pairs_reference_array(gl, ga, r)
+            assert stats.n_pairs == want_pairs.shape[0]
+            assert np.array_equal(opairs.sort_pairs(pairs[:stats.n_pairs]), want_pairs)
+            order, _ = orps.cell_phase_order(want_pairs, gl, ga, grid.as_dict())
+            uu = philox.pair_uniforms(order[:, 0], order[:, 1], step, seed)
+            sp_ref, _ = orps.rps_sequential_c(sp_ref, order, uu, *p)
+            assert np.array_equal(gs, sp_ref), "step %d: %d species differ" % (step, int((gs != sp_ref).sum()))
+            if stats_every_step:
+                assert list(stats.species_count)[1:] == [int((sp_ref == s).sum()) for s in (1, 2, 3)]
+            lon_prev, lat_prev, t, ti = gl.copy(), ga.copy(), t + dt, ti_new
+            total += stats.n_pairs
+        assert total > 1500 and int((sp_ref != sp0).sum()) > 100
+        per_step = (L.lm_launch_count(h) - launches0) / float(n_steps)
+        assert per_step < 12 if resolve_mode == 1 else per_step >= 16          # one resolver launch instead of nine
+    finally:
+        assert L.lm_destroy(h) == 0
