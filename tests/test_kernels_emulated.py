@@ -314,3 +314,134 @@ def test_fused_steps_through_the_c_abi(abi, resolve_mode, stats_every_step):
         assert per_step < 12 if resolve_mode == 1 else per_step >= 16          # one resolver launch instead of nine
     finally:
         assert L.lm_destroy(h) == 0
+
+
+@pytest.mark.parametrize("n_strips,resolve_mode", [(2, 1), (3, 0)])
+def test_latitude_strips_through_the_c_abi(abi, n_strips, resolve_mode):
+    """The whole strip protocol executed: G handles, particles handed out in contiguous tiles, routing
+    passes until every microbe sits in its strip, then fused steps in the five stages of include/lm_b200.h with the
+    exchange buffers copied between neighbours -- against ONE handle stepping all microbes on the same grid.
+    Positions, pair set and species must agree bit for bit (strips with the tiled resolver vs a single handle with the
+    nine phases, and the other way round)."""
+    from lagrangian_microbes_b200 import _lib
+    from lagrangian_microbes_b200.engine import make_grid
+    from lagrangian_microbes_b200.particle_advecter import StageClock
+    from lagrangian_microbes_b200.strips import cell_rows, strip_edges
+    L, G = abi, n_strips
+    fs = _small_field()
+    n, r, p, seed, dt, n_steps = 1000, 0.01, (0.55, 0.6, 0.9), 3, 3600.0, 3
+    rng = np.random.default_rng(20 + G)
+    lon = (201.5 + 0.2 * rng.random(n)).astype(np.float32)
+    lat = (32.5 + 0.2 * rng.random(n)).astype(np.float32)
+    sp0 = rng.integers(1, 4, n).astype(np.int8)
+    ids = np.arange(n, dtype=np.int32)
+    u, v = np.ascontiguousarray(fs.u), np.ascontiguousarray(fs.v)
+    glon, glat = np.ascontiguousarray(fs.lon), np.ascontiguousarray(fs.lat)
+    max_cells, cap = 1 << 14, 40 * n
+    grid = make_grid(float(lon.min()), float(lon.max()), float(lat.min()), float(lat.max()), r, n, max_cells, margin=0.1)
+    edges = strip_edges(np.bincount(cell_rows(lat, grid), minlength=grid.ncy), G)
+    flags_full = _lib.LM_STEP_ADVECT | _lib.LM_STEP_INTERACT | _lib.LM_STEP_EMIT_PAIRS | _lib.LM_STEP_STATS
+
+    def make(mode):
+        h = ctypes.c_void_p()
+        assert L.lm_create(ctypes.byref(h), 0, n + 512, max_cells, cap) == 0
+        assert L.lm_set_field(h, _ptr(u), _ptr(v), _ptr(glon), _ptr(glat), *u.shape) == 0
+        assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, mode) == 0
+        return h
+
+    single = make(1 - resolve_mode)
+    strips = [make(resolve_mode) for _ in range(G)]
+    try:
+        assert L.lm_set_grid(single, ctypes.byref(grid)) == 0
+        assert L.lm_state_set(single, _ptr(lon), _ptr(lat), _ptr(sp0), None, n, None) == 0
+        bufs, pair_bufs = [], []
+        per = n // G
+        for k, h in enumerate(strips):
+            assert L.lm_strip_alloc(h, 512, 512, grid.ncx + 8) == 0
+            assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+            b = _lib.StripBuffers()
+            assert L.lm_strip_buffers_get(h, ctypes.byref(b)) == 0
+            bufs.append(b)
+            pair_bufs.append(np.zeros((cap, 2), dtype=np.int32))
+            sl = slice(k * per, (k + 1) * per if k < G - 1 else n)          # the reference's contiguous tiles
+            st = _lib.Strip(edges[k], edges[k + 1] - edges[k], int(k > 0), int(k < G - 1))
+            assert L.lm_set_strip(h, ctypes.byref(st)) == 0
+            a, b_, c_, d_ = (np.ascontiguousarray(x[sl]) for x in (lon, lat, sp0, ids))
+            assert L.lm_state_set(h, _ptr(a), _ptr(b_), _ptr(c_), _ptr(d_), a.size, None) == 0
+
+        def copy(dst, src, nbytes):
+            ctypes.memmove(dst, src, nbytes)
+
+        def staged(flags, st_times, prm):
+            for h in strips:
+                assert L.lm_step_move(h, flags, ctypes.byref(st_times) if st_times is not None else None, dt, 0.0,
+                                      ctypes.byref(prm), None) == 0
+            for k in range(G):                                            # index 0 = south side, 1 = north side
+                if k > 0:
+                    copy(bufs[k - 1].mig_recv[1], bufs[k].mig_send[0], bufs[k].mig_bytes)
+                if k < G - 1:
+                    copy(bufs[k + 1].mig_recv[0], bufs[k].mig_send[1], bufs[k].mig_bytes)
+            for h in strips:
+                assert L.lm_step_bin(h, None) == 0
+            halo = bool(flags & _lib.LM_STEP_INTERACT)
+            if halo:
+                for k in range(1, G):
+                    copy(bufs[k - 1].ghost_recv, bufs[k].ghost_send, bufs[k].ghost_bytes)
+            for k, h in enumerate(strips):
+                assert L.lm_step_interact_begin(h, r, _ptr(pair_bufs[k]), cap, None) == 0
+            if halo:
+                for k in range(1, G):
+                    copy(bufs[k - 1].gsp_recv, bufs[k].gsp_send, bufs[k].species_bytes)
+            for h in strips:
+                assert L.lm_step_interact_end(h, None) == 0
+            if halo:
+                for k in range(G - 1):
+                    copy(bufs[k + 1].gret_recv, bufs[k].gret_send, bufs[k].species_bytes)
+            for h in strips:
+                assert L.lm_step_finish(h, None) == 0
+
+        def strip_stats(h):
+            s = _lib.Stats()
+            rc = L.lm_sync_stats(h, ctypes.byref(s), None)
+            assert rc in (0, _lib.LM_ESTATE), rc                          # LM_ESTATE: misrouted microbes are still on their way
+            return s
+
+        prm0 = _lib.RpsParams(*p, seed, 0)
+        for _ in range(50):                                               # settle: one hop per pass
+            for k, h in enumerate(strips):
+                st = _lib.Strip(edges[k], edges[k + 1] - edges[k], int(k > 0), int(k < G - 1))
+                assert L.lm_set_strip(h, ctypes.byref(st)) == 0
+            staged(0, None, prm0)
+            if sum(strip_stats(h).n_misrouted for h in strips) == 0:
+                break
+        else:
+            raise AssertionError("routing did not converge")
+        assert sum(L.lm_state_size(h) for h in strips) == n
+
+        clock_a, clock_b = StageClock(fs.time), StageClock(fs.time)
+        pairs_single = np.zeros((cap, 2), dtype=np.int32)
+        moved = 0
+        for step in range(n_steps):
+            prm = _lib.RpsParams(*p, seed, step)
+            assert L.lm_step(single, flags_full, ctypes.byref(clock_a.next_step(dt)), dt, 0.0, r, ctypes.byref(prm),
+                             _ptr(pairs_single), cap, None) == 0
+            s1 = _lib.Stats()
+            assert L.lm_sync_stats(single, ctypes.byref(s1), None) == 0
+            staged(flags_full, clock_b.next_step(dt), prm)
+            st = [strip_stats(h) for h in strips]
+            assert sum(s.n_misrouted for s in st) == 0 and sum(s.n_particles for s in st) == n
+            assert sum(s.n_pairs for s in st) == s1.n_pairs
+            moved += sum(s.n_moved_in for s in st)
+            wl, wa, ws = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(n, np.int8)
+            assert L.lm_state_get(single, _ptr(wl), _ptr(wa), _ptr(ws), None) == 0
+            gl, ga, gs = np.full(n, np.nan, np.float32), np.full(n, np.nan, np.float32), np.full(n, -1, np.int8)
+            for h in strips:                                              # global ids: every strip fills its own microbes
+                assert L.lm_state_get(h, _ptr(gl), _ptr(ga), _ptr(gs), None) == 0
+            assert np.array_equal(gl, wl) and np.array_equal(ga, wa), "positions, step %d" % step
+            got = opairs.sort_pairs(np.concatenate([pb[:s.n_pairs] for pb, s in zip(pair_bufs, st)]))
+            assert np.array_equal(got, opairs.sort_pairs(pairs_single[:s1.n_pairs])), "pair set, step %d" % step
+            assert np.array_equal(gs, ws), "species, step %d: %d differ" % (step, int((gs != ws).sum()))
+        assert moved > 0                                                  # microbes did cross strip boundaries
+    finally:
+        for h in [single] + strips:
+            L.lm_destroy(h)
