@@ -975,6 +975,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
 {
     extern __shared__ __align__(16) int8_t s_species[];    // [smem_cap]
     __shared__ int s_p0[TILE_LY], s_cnt[TILE_LY], s_delta[TILE_LY];   // loaded row: first particle, particles, index delta
+    __shared__ int s_cs[TILE_LY][TILE_LX + 1];             // cell_start of the loaded cells (+ one past the end of each row)
     __shared__ long long s_off;                            // >= 0: this tile works in the global scratch
     __shared__ int s_heavy[TILE_HEAVY_Q];
     __shared__ unsigned int s_nheavy, s_phase_pairs;
@@ -987,11 +988,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
     const int lx0 = max(0, ix0 - TILE_HX), lx1 = min(ncx, ix1 + TILE_HX);
     const int ly0 = max(0, iy0 - TILE_HY), ly1 = min(A.rows_local, iy1 + TILE_HY);
     const int lw = lx1 - lx0, lh = ly1 - ly0;
-    if (tid < lh) {
-        const long long rc = (long long)(ly0 + tid) * ncx;
-        const int p0 = __ldg(A.cell_start + rc + lx0), p1 = __ldg(A.cell_start + rc + lx1);
-        s_p0[tid] = p0; s_cnt[tid] = p1 - p0;
+    for (int k = tid; k < lh * (lw + 1); k += TILE_THREADS) {
+        const int t = k / (lw + 1), x = k - t * (lw + 1);
+        s_cs[t][x] = __ldg(A.cell_start + (long long)(ly0 + t) * ncx + lx0 + x);
     }
+    __syncthreads();
+    if (tid < lh) { s_p0[tid] = s_cs[tid][0]; s_cnt[tid] = s_cs[tid][lw] - s_cs[tid][0]; }
     __syncthreads();
     if (tid == 0) {
         int off = 0;
@@ -1032,7 +1034,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
                 else on = (cy & 1) == G.parity && cy + 1 < ly1 && cx + G.dir >= lx0 && cx + G.dir < lx1;
                 if (on) {
                     const int cell = cy * ncx + cx;
-                    const int cs0 = __ldg(A.cell_start + cell), cs1 = __ldg(A.cell_start + cell + 1);
+                    const int cs0 = s_cs[ry][cx - lx0], cs1 = s_cs[ry][cx - lx0 + 1];
                     if (cs1 > cs0) {                           // an empty cell's record is stale
                         rr[k] = __ldg(rec_d + cell);
                         unsigned int total = rr[k].y;
@@ -1061,9 +1063,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
             int oy = cy, ox = cx;
             if (G.mode == MODE_EAST) ox = cx + 1;
             else if (G.mode == MODE_CROSS) { oy = cy + 1; ox = cx + G.dir; }
-            const int cell = cy * ncx + cx;
-            const int cs0 = __ldg(A.cell_start + cell), cs1 = __ldg(A.cell_start + cell + 1);
-            const int ob = __ldg(A.cell_start + oy * ncx + ox);
+            const int cs0 = s_cs[ry][cx - lx0], cs1 = s_cs[ry][cx - lx0 + 1];
+            const int ob = s_cs[oy - ly0][ox - lx0];
             uint2 r = rr[k];
             int8_t *spA = tsp + s_delta[ry], *spB = tsp + s_delta[oy - ly0];
             int cur_a = -1, sa = 0, sa0 = 0, a0 = cs0;
@@ -1104,17 +1105,15 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
             int oy = cy, ox = cx;
             if (G.mode == MODE_EAST) ox = cx + 1;
             else if (G.mode == MODE_CROSS) { oy = cy + 1; ox = cx + G.dir; }
-            const int cell = cy * ncx + cx;
-            resolve_unit_warp_tile(A.hits, rec_d, rec2_d, cell, __ldg(A.cell_start + cell), __ldg(A.cell_start + cell + 1),
-                                   __ldg(A.cell_start + oy * ncx + ox), tsp + s_delta[ry], tsp + s_delta[oy - ly0]);
+            resolve_unit_warp_tile(A.hits, rec_d, rec2_d, cy * ncx + cx, s_cs[ry][cx - lx0], s_cs[ry][cx - lx0 + 1],
+                                   s_cs[oy - ly0][ox - lx0], tsp + s_delta[ry], tsp + s_delta[oy - ly0]);
         }
         __syncthreads();                                       // the phase is complete on the whole loaded region
     }
 
     // the interior of the tile is exact: write it back
     for (int y = iy0; y < iy1; ++y) {
-        const long long rc = (long long)y * ncx;
-        const int p0 = __ldg(A.cell_start + rc + ix0), p1 = __ldg(A.cell_start + rc + ix1);
+        const int p0 = s_cs[y - ly0][ix0 - lx0], p1 = s_cs[y - ly0][ix1 - lx0];
         const int8_t *src = tsp + s_delta[y - ly0];
         for (int p = p0 + tid; p < p1; p += TILE_THREADS) A.sp_out[p] = src[p];
     }
