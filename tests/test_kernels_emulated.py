@@ -445,3 +445,78 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, resolve_mode):
     finally:
         for h in [single] + strips:
             L.lm_destroy(h)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The committed golden vectors (tests/golden/, made with the unmodified reference function and with SciPy) through the
+# emulated C ABI: the CPU suite pins the kernels' logic to the reference's own outputs, not only the GPU suite.
+@pytest.mark.parametrize("name,resolve_mode", [("rps_oddspecies", 0), ("rps_oddspecies", 1), ("rps_clustered", 1)])
+def test_golden_species_through_the_c_abi(abi, name, resolve_mode):
+    from conftest import golden
+    from lagrangian_microbes_b200 import _lib
+    L = abi
+    g = golden(name + ".npz")
+    n, n_pairs = g["lon"].size, g["pairs_ref_order"].shape[0]
+    h = ctypes.c_void_p()
+    assert L.lm_create(ctypes.byref(h), 0, n, 1 << 16, n_pairs + 64) == 0
+    try:
+        grid = _lib.Grid(float(g["grid"][0]), float(g["grid"][1]), float(g["grid"][2]), int(g["grid_n"][0]), int(g["grid_n"][1]))
+        assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+        assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, resolve_mode) == 0
+        lon, lat = np.ascontiguousarray(g["lon"]), np.ascontiguousarray(g["lat"])
+        # fused path, canonical cell-phase order: species made by the reference function fed that order
+        species = g["species0"].copy()
+        prm = _lib.RpsParams(float(g["pRS"]), float(g["pPR"]), float(g["pSP"]), int(g["seed"]), int(g["step"]))
+        found = np.zeros(1, dtype=np.int64)
+        assert L.lm_interact_rps(h, _ptr(lon), _ptr(lat), _ptr(species), n, float(g["r"]), ctypes.byref(prm), None, 0,
+                                 _ptr(found), None) == 0
+        stats = _lib.Stats()
+        assert L.lm_sync_stats(h, ctypes.byref(stats), None) == 0
+        assert stats.n_pairs == n_pairs == found[0]
+        assert np.array_equal(species, g["species_cell"])
+        if resolve_mode == 0:
+            # explicit-order resolver (M-ref): the reference's own set-iteration order and draws
+            species = g["species0"].copy()
+            pairs = np.ascontiguousarray(g["pairs_ref_order"], dtype=np.int32)
+            u = np.ascontiguousarray(g["u_ref"], dtype=np.float64)
+            rounds = ctypes.c_int32(0)
+            assert L.lm_resolve_rps(h, _ptr(pairs), _ptr(u), n_pairs, _ptr(species), n, float(g["pRS"]), float(g["pPR"]),
+                                    float(g["pSP"]), ctypes.byref(rounds), None) == 0
+            assert np.array_equal(species, g["species_ref"]) and rounds.value > 1
+    finally:
+        L.lm_destroy(h)
+
+
+def test_golden_pair_sets_through_the_c_abi(abi):
+    """SciPy's pair sets (p = 2, 1, inf) incl. points exactly r apart, duplicates and collinear points."""
+    from conftest import golden
+    from lagrangian_microbes_b200 import _lib
+    from lagrangian_microbes_b200.engine import make_grid
+    L = abi
+    cases = []
+    g = golden("pairs_cases.npz")
+    for name in ("exact345", "dups_collinear", "lattice"):
+        cases.append((g[name + "_lon"], g[name + "_lat"], float(g[name + "_r"]), g[name + "_pairs"], _lib.LM_NORM_2))
+    g = golden("pairs_norms.npz")
+    for tag, code in (("p1", _lib.LM_NORM_1), ("pinf", _lib.LM_NORM_INF)):
+        cases.append((g["exact_lon"], g["exact_lat"], float(g["exact_r"]), g["exact_pairs_" + tag], code))
+        cases.append((g["blob_lon"][:300], g["blob_lat"][:300], float(g["blob_r"]), None, code))
+    for lon, lat, r, want, code in cases:
+        lon, lat = np.ascontiguousarray(lon, dtype=np.float32), np.ascontiguousarray(lat, dtype=np.float32)
+        if want is None:
+            want = opairs.query_pairs_reference_array(lon, lat, r, p={_lib.LM_NORM_1: 1, _lib.LM_NORM_INF: np.inf}[code])
+        want = opairs.sort_pairs(np.asarray(want).reshape(-1, 2))
+        n, cap = lon.size, want.shape[0] + 16
+        h = ctypes.c_void_p()
+        assert L.lm_create(ctypes.byref(h), 0, n, 1 << 16, 0) == 0
+        try:
+            grid = make_grid(float(lon.min()), float(lon.max()), float(lat.min()), float(lat.max()), r, n, 1 << 16, margin=0.0)
+            assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+            assert L.lm_set_option(h, _lib.LM_OPT_NORM, code) == 0
+            pairs = np.zeros((cap, 2), dtype=np.int32)
+            found = np.zeros(1, dtype=np.int64)
+            assert L.lm_find_pairs(h, _ptr(lon), _ptr(lat), n, r, _ptr(pairs), cap, _ptr(found), None) == 0
+            assert found[0] == want.shape[0]
+            assert np.array_equal(opairs.sort_pairs(pairs[:found[0]]), want)
+        finally:
+            L.lm_destroy(h)
