@@ -256,9 +256,12 @@ int lm_reset_stats(lm_handle h, void *stream);
  *                   Switching it on allocates 5 bytes per particle + 1 per cell (the only allocation outside
  *                   lm_create); not allowed between the stages of a step (LM_ESTATE).
  *   LM_OPT_RESOLVE_TILE_SMEM  bytes of species a tile may keep in shared memory (default 32768); fuller tiles work on a
- *                   private slice of global memory instead. */
+ *                   private slice of global memory instead.
+ *   LM_OPT_RESOLVE_MEGA_MIN  tiled resolver: a unit with more pairs than this (0 = default, 8192: about 128 microbes in
+ *                   one cell) is resolved by the whole CTA, 256 partners of an anchor per scan, instead of by one warp. */
 #define LM_OPT_RESOLVE_MODE 8
 #define LM_OPT_RESOLVE_TILE_SMEM 9
+#define LM_OPT_RESOLVE_MEGA_MIN 10
 int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Make `stream` wait for work of the last lm_step that is still running on the handle's internal stream
  * (LM_OPT_OVERLAP).  Only needed before the caller reads the resident arrays through pointers obtained earlier,

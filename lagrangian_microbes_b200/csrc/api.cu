@@ -845,6 +845,10 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
             h->resolve_mode = (int)value;
             return LM_OK;
         }
+        case LM_OPT_RESOLVE_MEGA_MIN:
+            if (value < 0 || value > (1ll << 30)) return LM_EINVAL;
+            h->resolve_mega_min = (int)value;
+            return LM_OK;
         case LM_OPT_RESOLVE_TILE_SMEM:
             if (value < 1024 || value > 200 * 1024) return LM_EINVAL;
             h->resolve_tile_smem = (int)value;

@@ -874,6 +874,8 @@ constexpr int TILE_X = 64, TILE_Y = 16, TILE_HX = 6, TILE_HY = 2;
 constexpr int TILE_LY = TILE_Y + 2 * TILE_HY;              // loaded rows
 constexpr int TILE_THREADS = 256;
 constexpr int TILE_HEAVY_Q = 128;                          // dense units queued per phase for whole warps
+constexpr int TILE_MEGA_Q = 16;                            // ... and for the whole CTA (knots of hundreds of microbes per cell)
+constexpr unsigned int TILE_MEGA_MIN = 8192;               // ~128 microbes in one cell: 64 partners per anchor, where 256-wide scans win
 constexpr int TILE_LX = TILE_X + 2 * TILE_HX;              // loaded columns
 constexpr int TILE_UPT = (TILE_LX * TILE_LY + TILE_THREADS - 1) / TILE_THREADS;   // units per thread and phase (6)
 
@@ -894,6 +896,7 @@ struct TileArgs {
     int first, last;                     // phases
     int smem_cap;                        // bytes of species a CTA can hold in shared memory
     unsigned int heavy_min;
+    unsigned int mega_min;               // a unit with more pairs than this is resolved by the whole CTA
 };
 
 // Whole-warp resolution of one unit against the tile's private species (resolve_unit_warp above, with the two cells'
@@ -960,6 +963,87 @@ __device__ void resolve_unit_warp_tile(const uint32_t *__restrict__ hits, const 
     __syncwarp();
 }
 
+// Whole-CTA resolution of one unit (every thread of the CTA calls this with the same arguments).  For the knots a
+// long run produces -- several hundred microbes in one cell, 10^4..10^5 pairs in ONE unit -- the anchors are inherently
+// sequential, but each anchor's run of partners is a prefix scan over 3->3 maps: a warp takes it 32 partners at a
+// time (resolve_unit_warp_tile), the CTA takes 256 at a time, warp scans joined through shared memory.  Entries are
+// read 256 per chunk; the distinct anchors of a chunk (at most 32: a_rel is a 5-bit index) are visited in ascending
+// order through a presence mask, the anchor's species is carried in registers by every thread.
+__device__ void resolve_unit_cta_tile(const uint32_t *__restrict__ hits, const uint2 *__restrict__ rec_d,
+                                      const uint2 *__restrict__ rec2_d, int cell, int cs0, int cs1, int oBeg,
+                                      int8_t *spA, int8_t *spB)
+{
+    __shared__ uint32_t s_wmap[TILE_THREADS / 32];
+    __shared__ unsigned int s_present;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int cur_a = -1, sa = 0, sa0 = 0;
+    int a0 = cs0;
+    uint2 R = __ldg(rec_d + cell);
+    __syncthreads();
+    while (true) {
+        const uint32_t *ent = hits + R.x;
+        for (unsigned int k0 = 0; k0 < R.y; k0 += TILE_THREADS) {
+            const unsigned int k = k0 + tid;
+            const bool act = k < R.y;
+            const uint32_t en = act ? __ldg(ent + k) : 0u;
+            const int ar = (int)((en >> 24) & 31u);
+            if (tid == 0) s_present = 0u;
+            __syncthreads();
+            if (act) atomicOr(&s_present, 1u << ar);
+            __syncthreads();
+            unsigned int todo = s_present;
+            while (todo) {                                     // CTA-uniform
+                const int ar0 = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int a = a0 + ar0;
+                if (a != cur_a) {
+                    if (cur_a >= 0 && sa != sa0 && tid == 0) spA[cur_a] = (int8_t)sa;
+                    __syncthreads();
+                    cur_a = a;
+                    sa = sa0 = ((volatile int8_t *)spA)[a];
+                }
+                if (!is_rps(sa)) continue;                     // winner = None for every pair of this anchor (uniform)
+                const bool mine = act && ar == ar0;
+                uint32_t M = MAP_ID, dec = 0;
+                int b = 0, sb = 0;
+                if (mine) {
+                    b = oBeg + (int)(en & B_REL_MASK); dec = en >> 29;
+                    sb = ((volatile int8_t *)spB)[b];
+                    if (is_rps(sb)) M = map_of_partner(sb, dec);
+                }
+                uint32_t P = M;                                // inclusive scan of maps inside the warp, in partner order
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, P, dd);
+                    if (lane >= dd) P = map_compose(P, t);
+                }
+                uint32_t E = __shfl_up_sync(0xffffffffu, P, 1);
+                if (lane == 0) E = MAP_ID;
+                if (lane == 31) s_wmap[warp] = P;
+                __syncthreads();
+                uint32_t before = MAP_ID, total = MAP_ID;      // maps of the warps before mine | of all warps
+#pragma unroll
+                for (int w = 0; w < TILE_THREADS / 32; ++w) {
+                    const uint32_t mw = s_wmap[w];
+                    if (w < warp) before = map_compose(mw, before);
+                    total = map_compose(mw, total);
+                }
+                if (mine && is_rps(sb)) {
+                    const int s_before = map_apply(map_compose(E, before), sa);
+                    if (s_before != sb) spB[b] = (int8_t)rps_apply(s_before, sb, dec);
+                }
+                sa = map_apply(total, sa);
+                __syncthreads();                               // partner species written above are visible to later anchors
+            }
+        }
+        a0 = (a0 | 31) + 1;                                    // the cell continues in the next 32-particle chunk?
+        if (a0 >= cs1) break;
+        R = __ldg(rec2_d + (a0 >> 5));
+    }
+    if (cur_a >= 0 && sa != sa0 && tid == 0) spA[cur_a] = (int8_t)sa;
+    __syncthreads();
+}
+
 // geometry of phase ph: which direction table it reads and which cells anchor a unit
 struct PhaseGeom { int mode, parity, dir, d_idx; };
 __device__ __forceinline__ PhaseGeom phase_geom(int ph)
@@ -978,7 +1062,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
     __shared__ int s_cs[TILE_LY][TILE_LX + 1];             // cell_start of the loaded cells (+ one past the end of each row)
     __shared__ long long s_off;                            // >= 0: this tile works in the global scratch
     __shared__ int s_heavy[TILE_HEAVY_Q];
-    __shared__ unsigned int s_nheavy, s_phase_pairs;
+    __shared__ int s_mega[TILE_MEGA_Q];
+    __shared__ unsigned int s_nheavy, s_phase_pairs, s_nmega;
     if (*A.n_pairs > A.cap_words) return;                  // the hand-off overflowed: reported by lm_sync_stats
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ncx = A.ncx;
@@ -1013,7 +1098,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
         const PhaseGeom G = phase_geom(ph);
         const uint2 *rec_d = A.rec + (size_t)G.d_idx * A.rec_stride;
         const uint2 *rec2_d = A.rec2 + (size_t)G.d_idx * A.rec2_stride;
-        if (tid == 0) { s_nheavy = 0u; s_phase_pairs = 0u; }
+        if (tid == 0) { s_nheavy = 0u; s_phase_pairs = 0u; s_nmega = 0u; }
         __syncthreads();
         // ---- pass 1: the units of this thread (u = tid, tid + 256, ...: at most TILE_UPT) and their pair counts.
         // "Dense" is relative, as in resolve_phase_kernel: in a crowded tile every unit is long, the lanes are evenly
@@ -1055,6 +1140,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
         for (int k = 0; k < TILE_UPT; ++k) {
             if (tot[k] == 0u) continue;
             const int u = tid + k * TILE_THREADS;
+            if (tot[k] > A.mega_min) {
+                const unsigned int q = atomicAdd(&s_nmega, 1u);
+                if (q < (unsigned int)TILE_MEGA_Q) { s_mega[q] = u; continue; }
+            }
             if (tot[k] > limit) {
                 const unsigned int q = atomicAdd(&s_nheavy, 1u);
                 if (q < (unsigned int)TILE_HEAVY_Q) { s_heavy[q] = u; continue; }
@@ -1108,6 +1197,17 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
             resolve_unit_warp_tile(A.hits, rec_d, rec2_d, cy * ncx + cx, s_cs[ry][cx - lx0], s_cs[ry][cx - lx0 + 1],
                                    s_cs[oy - ly0][ox - lx0], tsp + s_delta[ry], tsp + s_delta[oy - ly0]);
         }
+        __syncthreads();
+        const unsigned int n_mega = min(s_nmega, (unsigned int)TILE_MEGA_Q);
+        for (unsigned int q = 0; q < n_mega; ++q) {                             // knots: the whole CTA, one after the other
+            const int u = s_mega[q];
+            const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
+            int oy = cy, ox = cx;
+            if (G.mode == MODE_EAST) ox = cx + 1;
+            else if (G.mode == MODE_CROSS) { oy = cy + 1; ox = cx + G.dir; }
+            resolve_unit_cta_tile(A.hits, rec_d, rec2_d, cy * ncx + cx, s_cs[ry][cx - lx0], s_cs[ry][cx - lx0 + 1],
+                                  s_cs[oy - ly0][ox - lx0], tsp + s_delta[ry], tsp + s_delta[oy - ly0]);
+        }
         __syncthreads();                                       // the phase is complete on the whole loaded region
     }
 
@@ -1147,6 +1247,7 @@ static cudaError_t launch_resolve_tiled(lm_handle_s *h, int8_t *sp, int first, i
     T.first = first; T.last = last;
     T.smem_cap = h->resolve_tile_smem;
     T.heavy_min = h->resolve_heavy_min > 0 ? (unsigned int)h->resolve_heavy_min : 4u * HEAVY_MIN;
+    T.mega_min = h->resolve_mega_min > 0 ? (unsigned int)h->resolve_mega_min : TILE_MEGA_MIN;
     if (T.ncx <= 0 || T.rows_local <= 0) return cudaSuccess;
     T.tiles_x = (T.ncx + TILE_X - 1) / TILE_X;
     const long long tiles = (long long)T.tiles_x * ((T.rows_local + TILE_Y - 1) / TILE_Y);

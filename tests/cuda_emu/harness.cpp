@@ -20,7 +20,7 @@ long long emu_interact(const float *lon, const float *lat, const int32_t *id, co
                        int n_owned, int n_all, double x0, double y0, double inv_h, int ncx, int ncy, int row0, int rows_owned,
                        int rows_local, double r, double pRS, double pPR, double pSP, unsigned long long seed,
                        unsigned long long step, int mode, int first, int last, int tile_smem, int heavy_min, int batch, int upl,
-                       int find_path, int32_t *pairs_out, long long cap, long long max_pairs, uint32_t *hits_out,
+                       int find_path, int mega_min, int32_t *pairs_out, long long cap, long long max_pairs, uint32_t *hits_out,
                        uint32_t *rec_out, uint32_t *rec2_out)
 {
     lm_handle_s *h = zalloc<lm_handle_s>(1);
@@ -45,7 +45,7 @@ long long emu_interact(const float *lon, const float *lat, const int32_t *id, co
     for (size_t k = 0; k < 5 * ((size_t)h->max_particles / 32 + 2); ++k) h->rec2[k] = make_uint2(0x7ffe0000u + (unsigned)k, 54321u);
     h->find_path = find_path;
     h->resolve_batch = batch; h->resolve_upl = upl; h->resolve_heavy_min = heavy_min;
-    h->resolve_mode = mode; h->resolve_tile_smem = tile_smem;
+    h->resolve_mode = mode; h->resolve_tile_smem = tile_smem; h->resolve_mega_min = mega_min;
     h->sp_snap = zalloc<int8_t>((size_t)h->max_particles);
     h->tile_scratch = zalloc<int8_t>(4 * (size_t)h->max_particles + (size_t)h->max_cells + 64);
     h->tile_scratch_used = zalloc<unsigned long long>(1);

@@ -98,6 +98,41 @@ def test_live_species(engine_factory, kind):
         assert bad == 0, "smem %d heavy_min %d: %d species differ" % (smem, heavy_min, bad)
 
 
+def test_knots_on_the_whole_cta(engine_factory):
+    """Knots of several hundred microbes in one cell (config 2 run past step 3,000): units of 10^4..10^5 pairs, resolved
+    by the whole CTA.  Default limit, a low limit (every unit above 48 pairs), and the global-scratch variant."""
+    from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_MEGA_MIN
+    from lagrangian_microbes_b200.engine import make_grid
+    rng = np.random.default_rng(23)
+    n, r = 30000, 0.01
+    lon, lat = 205 + 2.0 * rng.random(n), 25 + 2.0 * rng.random(n)
+    k = 0
+    for c in range(12):
+        m = int(rng.integers(150, 600))
+        lon[k:k + m] = 205.005 + 0.01 * int(rng.integers(0, 190)) + 0.006 * rng.random(m)
+        lat[k:k + m] = 25.005 + 0.01 * int(rng.integers(0, 190)) + 0.006 * rng.random(m)
+        k += m
+    lon, lat = lon.astype(np.float32), lat.astype(np.float32)
+    sp0 = rng.integers(1, 4, n).astype(np.int8)
+    p = (0.55, 0.6, 0.9)
+    want_pairs = opairs.query_pairs_reference_array(lon, lat, r)
+    eng = engine_factory(max_particles=n, max_cells=1 << 22, max_pairs=want_pairs.shape[0] + 64)
+    grid = make_grid(float(lon.min()), float(lon.max()), float(lat.min()), float(lat.max()), r, n, eng.max_cells, margin=0.1)
+    eng.set_grid(grid)
+    order, _ = orps.cell_phase_order(want_pairs, lon, lat, grid.as_dict())
+    u = philox.pair_uniforms(order[:, 0], order[:, 1], 17, 5)
+    want_sp, _ = orps.rps_sequential_c(sp0.copy(), order, u, *p)
+    lon_d, lat_d = dev(lon), dev(lat)
+    for mega_min, smem in [(0, 32768), (48, 32768), (48, 1024), (1 << 30, 32768)]:
+        tiled(eng, smem)
+        eng.set_option(LM_OPT_RESOLVE_MEGA_MIN, mega_min)
+        species = dev(sp0.copy())
+        eng.interact_rps(lon_d, lat_d, species, r, *p, 5, 17)
+        assert eng.sync_stats().n_pairs == want_pairs.shape[0]
+        bad = int((species.cpu().numpy() != want_sp).sum())
+        assert bad == 0, "mega_min %d smem %d: %d species differ" % (mega_min, smem, bad)
+
+
 def test_fused_loop_equals_the_phase_launches():
     """Twelve fused steps (advection, re-binning, regridding) with the tiled resolver against the default resolver."""
     from lagrangian_microbes_b200.simulation import FusedSimulation

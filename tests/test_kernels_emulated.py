@@ -33,7 +33,7 @@ def emu():
     vp, i32, i64, u64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_double
     L.emu_interact.restype = i64
     L.emu_interact.argtypes = [vp, vp, vp, vp, vp, i32, i32, dbl, dbl, dbl, i32, i32, i32, i32, i32, dbl, dbl, dbl, dbl, u64, u64,
-                               i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp]
+                               i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, i64, vp, vp, vp]
     L.emu_pair_distance_hist.restype = i32
     L.emu_pair_distance_hist.argtypes = [vp, vp, i64, ctypes.c_float, i32, vp]
     L.emu_raster.restype = i32
@@ -76,7 +76,8 @@ class Cloud:
         out, _ = orps.rps_sequential_c(sp.copy(), self.order[sel], self.u[sel], *P)
         return out
 
-    def run(self, emu, sp, mode, first=0, last=8, tile_smem=32768, heavy_min=0, batch=4, upl=0, find_path=0, want_pairs=False):
+    def run(self, emu, sp, mode, first=0, last=8, tile_smem=32768, heavy_min=0, batch=4, upl=0, find_path=0, want_pairs=False,
+            mega_min=0):
         g = self.grid
         lon_s, lat_s = np.ascontiguousarray(self.lon[self.ids]), np.ascontiguousarray(self.lat[self.ids])
         sp_s = np.ascontiguousarray(sp[self.ids])
@@ -84,7 +85,8 @@ class Cloud:
         pairs_out = np.full((cap, 2), -1, dtype=np.int32) if want_pairs else None
         ret = emu.emu_interact(_ptr(lon_s), _ptr(lat_s), _ptr(self.ids), _ptr(self.cell_start), _ptr(sp_s), self.n, self.n,
                                g["x0"], g["y0"], g["inv_h"], g["ncx"], g["ncy"], 0, g["ncy"], g["ncy"], R, *P, 5, 17,
-                               mode, first, last, tile_smem, heavy_min, batch, upl, find_path, _ptr(pairs_out), cap, cap + 64,
+                               mode, first, last, tile_smem, heavy_min, batch, upl, find_path, mega_min, _ptr(pairs_out), cap,
+                               cap + 64,
                                None, None, None)
         assert ret >= 0
         found, launches = ret & ((1 << 48) - 1), ret >> 48
@@ -140,6 +142,19 @@ def test_tiled_resolver_crowded_cells(emu):
     for heavy_min in (0, 16):
         got, _ = c.run(emu, c.sp0, mode=1, heavy_min=heavy_min)
         assert np.array_equal(got, want), "heavy_min %d: %d species differ" % (heavy_min, int((got != want).sum()))
+
+
+def test_tiled_resolver_knots_on_the_whole_cta(emu):
+    """Knots of 150-250 microbes in single cells (what a long run produces): units of 10^4 pairs and more go to the
+    whole-CTA path (256 partners of an anchor per scan); with a low limit every unit above 48 pairs does."""
+    c = Cloud(5, 24, 10, 900, knots=2, knot_size=(150, 251))
+    want = c.oracle(c.sp0, 0, 8)
+    assert np.diff(c.cell_start).max() >= 150 and c.pairs.shape[0] > 20000
+    for mega_min, smem in ((0, 32768), (48, 1024)):
+        got, _ = c.run(emu, c.sp0, mode=1, mega_min=mega_min, tile_smem=smem)
+        assert np.array_equal(got, want), "mega_min %d: %d species differ" % (mega_min, int((got != want).sum()))
+    got0, _ = c.run(emu, c.sp0, mode=0)                     # the nine-phase resolver on the same knots (control)
+    assert np.array_equal(got0, want)
 
 
 def test_pair_distance_histogram_executed(emu):
@@ -228,7 +243,7 @@ def test_strip_geometry(emu, mode):
         cap = order.shape[0] + 64
         ret = emu.emu_interact(_ptr(lon_s), _ptr(lat_s), _ptr(ids), _ptr(cell_start), _ptr(sp_s), n_owned, n_all,
                                g["x0"], g["y0"], g["inv_h"], g["ncx"], g["ncy"], row0, rows_owned, rows_local, R, *P, 5, 17,
-                               mode, first, last, 32768, 0, 4, 0, 0, None, 0, cap, None, None, None)
+                               mode, first, last, 32768, 0, 4, 0, 0, 0, None, 0, cap, None, None, None)
         assert ret >= 0 and (ret & ((1 << 48) - 1)) == order.shape[0]
         got = sp.copy()
         got[ids] = sp_s
