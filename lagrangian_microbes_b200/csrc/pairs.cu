@@ -992,6 +992,7 @@ __device__ void resolve_unit_cta_tile(const uint32_t *__restrict__ hits, const u
             if (act) atomicOr(&s_present, 1u << ar);
             __syncthreads();
             unsigned int todo = s_present;
+            __syncthreads();                                   // everyone has the mask before it is reset for the next chunk
             while (todo) {                                     // CTA-uniform
                 const int ar0 = __ffs(todo) - 1;
                 todo &= todo - 1;
