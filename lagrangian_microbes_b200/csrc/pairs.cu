@@ -1074,6 +1074,8 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
     const int lx0 = max(0, ix0 - TILE_HX), lx1 = min(ncx, ix1 + TILE_HX);
     const int ly0 = max(0, iy0 - TILE_HY), ly1 = min(A.rows_local, iy1 + TILE_HY);
     const int lw = lx1 - lx0, lh = ly1 - ly0;
+    const unsigned int inv_lw = ((1u << 20) + (unsigned int)lw - 1u) / (unsigned int)lw;   // u / lw == (u * inv_lw) >> 20 for u < 1536, lw <= 76
+    static_assert(TILE_LX * TILE_LY <= 1536 && TILE_LX <= 76, "reciprocal division range");
     for (int k = tid; k < lh * (lw + 1); k += TILE_THREADS) {
         const int t = k / (lw + 1), x = k - t * (lw + 1);
         s_cs[t][x] = __ldg(A.cell_start + (long long)(ly0 + t) * ncx + lx0 + x);
@@ -1113,7 +1115,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
             tot[k] = 0u;
             const int u = tid + k * TILE_THREADS;
             if (u < lw * lh) {
-                const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
+                const int ry = (int)(((unsigned int)u * inv_lw) >> 20), cy = ly0 + ry, cx = lx0 + (u - ry * lw);   // ry = u / lw
                 bool on;
                 if (G.mode == MODE_SAME) on = cy < A.rows_owned;
                 else if (G.mode == MODE_EAST) on = cy < A.rows_owned && (cx & 1) == G.parity && cx + 1 < lx1;
@@ -1149,7 +1151,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
                 const unsigned int q = atomicAdd(&s_nheavy, 1u);
                 if (q < (unsigned int)TILE_HEAVY_Q) { s_heavy[q] = u; continue; }
             }
-            const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
+            const int ry = (int)(((unsigned int)u * inv_lw) >> 20), cy = ly0 + ry, cx = lx0 + (u - ry * lw);   // ry = u / lw
             int oy = cy, ox = cx;
             if (G.mode == MODE_EAST) ox = cx + 1;
             else if (G.mode == MODE_CROSS) { oy = cy + 1; ox = cx + G.dir; }
@@ -1191,7 +1193,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
         const unsigned int n_heavy = min(s_nheavy, (unsigned int)TILE_HEAVY_Q);
         for (unsigned int q = warp; q < n_heavy; q += TILE_THREADS / 32) {      // dense units: one warp each
             const int u = s_heavy[q];
-            const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
+            const int ry = (int)(((unsigned int)u * inv_lw) >> 20), cy = ly0 + ry, cx = lx0 + (u - ry * lw);   // ry = u / lw
             int oy = cy, ox = cx;
             if (G.mode == MODE_EAST) ox = cx + 1;
             else if (G.mode == MODE_CROSS) { oy = cy + 1; ox = cx + G.dir; }
@@ -1202,7 +1204,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
         const unsigned int n_mega = min(s_nmega, (unsigned int)TILE_MEGA_Q);
         for (unsigned int q = 0; q < n_mega; ++q) {                             // knots: the whole CTA, one after the other
             const int u = s_mega[q];
-            const int ry = u / lw, cy = ly0 + ry, cx = lx0 + (u - ry * lw);
+            const int ry = (int)(((unsigned int)u * inv_lw) >> 20), cy = ly0 + ry, cx = lx0 + (u - ry * lw);   // ry = u / lw
             int oy = cy, ox = cx;
             if (G.mode == MODE_EAST) ox = cx + 1;
             else if (G.mode == MODE_CROSS) { oy = cy + 1; ox = cx + G.dir; }
