@@ -3,7 +3,7 @@
 // std::thread per CUDA thread, one pthread barrier per CTA (__syncthreads) and per warp (__syncwarp and the
 // warp collectives), CTAs one after the other.  Data races, byte stores and atomics are the real thing; clocks,
 // memory spaces and scheduling are not modelled.  The product never includes this header: liblm_b200.so is built by
-// nvcc from the untouched sources, this shim is found first on the include path only by tests/cuda_emu/build.py.
+// nvcc from the untouched sources, this shim is found first on the include path only by tests/cuda_emu/emu_build.py.
 #pragma once
 #include <pthread.h>
 #include <stdint.h>

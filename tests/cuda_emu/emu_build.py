@@ -51,7 +51,7 @@ def transform(text):
 def build(force=False):
     so = os.path.join(OUT, "libemu.so")
     deps = [os.path.join(CSRC, f) for f in SOURCES + ["lm_internal.cuh", "philox.cuh"]] + \
-           [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu.cpp", "harness.cpp", "build.py")]
+           [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu.cpp", "harness.cpp", "emu_build.py")]
     if not force and os.path.exists(so) and all(os.path.getmtime(so) >= os.path.getmtime(d) for d in deps):
         return so
     os.makedirs(OUT, exist_ok=True)

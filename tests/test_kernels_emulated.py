@@ -28,7 +28,7 @@ H = R * (1 + 2.0 ** -20)
 
 @pytest.fixture(scope="module")
 def emu():
-    import build as emu_build
+    import emu_build
     L = ctypes.CDLL(emu_build.build())
     vp, i32, i64, u64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_double
     L.emu_interact.restype = i64
@@ -256,7 +256,7 @@ def test_strip_geometry(emu, mode):
 # The whole C ABI (csrc/api.cu on top of every kernel), executed: lm_create .. lm_step .. lm_state_get on host arrays.
 @pytest.fixture(scope="module")
 def abi():
-    import build as emu_build
+    import emu_build
     from lagrangian_microbes_b200 import _lib
     return _lib.declare(ctypes.CDLL(emu_build.build()))
 
