@@ -8,6 +8,7 @@
 # 2. A/B of the tiled resolver on fresh and stirred states, bench lines with both resolvers
 # 3. timing of the analysis kernels against the reference's own benchmark size (10^4 points: 4.0 s on one Julia process)
 # 4. launch list + one ncu --set full capture of the tiled resolver
+# 5. pinned-memory PCIe bandwidth of the box (what bounds the end-to-end number)
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out/r2a
@@ -32,4 +33,6 @@ fi
 if grep -q "failed\|error" $O/pytest_analysis.log; then echo "analysis kernels NOT green: skipping their timing"; else
   timeout 300 python tools/analysis_probe.py > $O/analysis_probe.jsonl 2> $O/analysis_probe.err
 fi
+# is the end-to-end number (9 B per microbe-step D2H) at the PCIe roofline of this box?
+timeout 120 python tools/pcie_bandwidth.py > $O/pcie_bandwidth.txt 2>&1
 ls -la $O
