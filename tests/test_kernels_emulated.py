@@ -535,3 +535,30 @@ def test_golden_pair_sets_through_the_c_abi(abi):
             assert np.array_equal(opairs.sort_pairs(pairs[:found[0]]), want)
         finally:
             L.lm_destroy(h)
+
+
+@pytest.mark.parametrize("resolve_mode", [0, 1])
+def test_hand_off_overflow_is_reported_not_resolved(abi, resolve_mode):
+    """A hand-off buffer smaller than the pairs found: LM_ENOSPC from lm_sync_stats, the species left alone (both
+    resolvers give up before touching them), the true pair count reported so that the caller can size it and repeat."""
+    from conftest import golden
+    from lagrangian_microbes_b200 import _lib
+    L = abi
+    g = golden("rps_oddspecies.npz")
+    n, n_pairs = g["lon"].size, g["pairs_ref_order"].shape[0]
+    h = ctypes.c_void_p()
+    assert L.lm_create(ctypes.byref(h), 0, n, 1 << 16, n_pairs // 2) == 0
+    try:
+        grid = _lib.Grid(float(g["grid"][0]), float(g["grid"][1]), float(g["grid"][2]), int(g["grid_n"][0]), int(g["grid_n"][1]))
+        assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+        assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, resolve_mode) == 0
+        species = g["species0"].copy()
+        prm = _lib.RpsParams(float(g["pRS"]), float(g["pPR"]), float(g["pSP"]), int(g["seed"]), int(g["step"]))
+        assert L.lm_interact_rps(h, _ptr(np.ascontiguousarray(g["lon"])), _ptr(np.ascontiguousarray(g["lat"])), _ptr(species), n,
+                                 float(g["r"]), ctypes.byref(prm), None, 0, None, None) == 0
+        stats = _lib.Stats()
+        assert L.lm_sync_stats(h, ctypes.byref(stats), None) == _lib.LM_ENOSPC
+        assert stats.n_pairs == n_pairs
+        assert np.array_equal(species, g["species0"])
+    finally:
+        L.lm_destroy(h)
