@@ -689,6 +689,7 @@ __global__ void __launch_bounds__(RES_THREADS) resolve_phase_kernel(ResolveArgs 
                 hm &= hm - 1;
                 const int hc = __shfl_sync(0xffffffffu, cell[q], src), ho = __shfl_sync(0xffffffffu, other[q], src);
                 const unsigned int slot = s_ctr[3];            // warp-uniform
+                __syncwarp();                                  // every lane has read the counter before lane 0 advances it
                 if (slot < (unsigned int)HEAVY_CAP) {
                     if (lane == 0) { s_heavy[2 * slot] = hc; s_heavy[2 * slot + 1] = ho; s_ctr[3] = slot + 1; }
                     __syncwarp();

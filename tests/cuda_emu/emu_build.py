@@ -70,5 +70,23 @@ def build(force=False):
     return so
 
 
+def build_tsan():
+    """tests/cuda_emu/_build/tsan_driver: the emulated library + tsan_driver.cpp under ThreadSanitizer (see the driver)."""
+    os.makedirs(OUT, exist_ok=True)
+    cpps = []
+    for f in SOURCES:
+        text, _ = transform(open(os.path.join(CSRC, f)).read())
+        path = os.path.join(OUT, f.replace(".cu", "_emu.cpp"))
+        with open(path, "w") as fh:
+            fh.write(text)
+        cpps.append(path)
+    exe = os.path.join(OUT, "tsan_driver")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-fsanitize=thread", "-ffp-contract=off", "-w", "-I", HERE, "-I", CSRC,
+           "-o", exe] + cpps + [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "tsan_driver.cpp")]
+    subprocess.check_call(cmd)
+    return exe
+
+
 if __name__ == "__main__":
-    print(build(force=True))
+    import sys
+    print(build_tsan() if "--tsan" in sys.argv else build(force=True))
