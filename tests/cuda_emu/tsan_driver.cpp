@@ -62,6 +62,30 @@ int main()
         CHECK(lm_destroy(hd));
     }
 
+    // explicit-order resolver (mark / fire rounds with 64-bit atomicMin) on the pair list of a search, other norms
+    {
+        lm_handle hd = nullptr;
+        CHECK(lm_create(&hd, 0, n, 1 << 14, 60 * n));
+        CHECK(lm_set_grid(hd, &grid));
+        std::vector<int32_t> pairs(2 * 60 * n);
+        std::vector<long long> found(1);
+        CHECK(lm_find_pairs(hd, lon.data(), lat.data(), n, r, pairs.data(), 60 * n, (int64_t *)found.data(), nullptr));
+        lm_stats st;
+        CHECK(lm_sync_stats(hd, &st, nullptr));
+        std::vector<double> u(st.n_pairs);
+        CHECK(lm_pair_uniforms(pairs.data(), st.n_pairs, 5, 17, u.data(), nullptr));
+        std::vector<int8_t> sp(sp0);
+        int32_t rounds = 0;
+        CHECK(lm_resolve_rps(hd, pairs.data(), u.data(), st.n_pairs, sp.data(), n, 0.55, 0.6, 0.9, &rounds, nullptr));
+        printf("explicit resolver: %lld pairs, %d rounds\n", (long long)st.n_pairs, rounds);
+        for (long long norm : {LM_NORM_1, LM_NORM_INF}) {
+            CHECK(lm_set_option(hd, LM_OPT_NORM, norm));
+            CHECK(lm_find_pairs(hd, lon.data(), lat.data(), n, r, pairs.data(), 60 * n, nullptr, nullptr));
+            CHECK(lm_sync_stats(hd, &st, nullptr));
+        }
+        CHECK(lm_destroy(hd));
+    }
+
     // fused steps on a synthetic field (solid-body-like flow on a 12 x 10 grid, 3 time levels)
     const int T = 3, Y = 10, X = 12;
     std::vector<float> Uf(T * Y * X), Vf(T * Y * X), glon(X), glat(Y);
@@ -92,6 +116,16 @@ int main()
         std::vector<float> a(n), b(n);
         std::vector<int8_t> c(n);
         CHECK(lm_state_get(hd, a.data(), b.data(), c.data(), nullptr));
+        // the per-step record pipeline: next step scatters + copies its record, then the host-copy variant
+        CHECK(lm_record_next_step(hd, a.data(), b.data(), c.data()));
+        {
+            lm_stage_times stt = {{0, 0, 0, 0}, {1, 1, 1, 1}, {0.03f, 0.035f, 0.035f, 0.04f}};
+            lm_rps_params p2 = {0.55, 0.55, 0.55, 3, 3};
+            CHECK(lm_step(hd, LM_STEP_ADVECT | LM_STEP_INTERACT, &stt, 3600.f, 0.0, r, &p2, nullptr, 0, nullptr));
+        }
+        CHECK(lm_host_copies_sync(hd));
+        CHECK(lm_state_get_host(hd, a.data(), b.data(), c.data(), nullptr));
+        CHECK(lm_host_copies_sync(hd));
         CHECK(lm_destroy(hd));
     }
 
