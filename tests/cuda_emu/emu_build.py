@@ -70,8 +70,9 @@ def build(force=False):
     return so
 
 
-def build_tsan():
-    """tests/cuda_emu/_build/tsan_driver: the emulated library + tsan_driver.cpp under ThreadSanitizer (see the driver)."""
+def build_tsan(sanitizer="thread"):
+    """tests/cuda_emu/_build/tsan_driver: the emulated library + tsan_driver.cpp under ThreadSanitizer (see the driver);
+    sanitizer="address,undefined" builds asan_driver instead: out-of-bounds accesses of global / shared memory."""
     os.makedirs(OUT, exist_ok=True)
     cpps = []
     for f in SOURCES:
@@ -80,8 +81,8 @@ def build_tsan():
         with open(path, "w") as fh:
             fh.write(text)
         cpps.append(path)
-    exe = os.path.join(OUT, "tsan_driver")
-    cmd = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-fsanitize=thread", "-ffp-contract=off", "-w", "-I", HERE, "-I", CSRC,
+    exe = os.path.join(OUT, "tsan_driver" if sanitizer == "thread" else "asan_driver")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-fsanitize=" + sanitizer, "-fno-omit-frame-pointer", "-ffp-contract=off", "-w", "-I", HERE, "-I", CSRC,
            "-o", exe] + cpps + [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "tsan_driver.cpp")]
     subprocess.check_call(cmd)
     return exe
@@ -89,4 +90,9 @@ def build_tsan():
 
 if __name__ == "__main__":
     import sys
-    print(build_tsan() if "--tsan" in sys.argv else build(force=True))
+    if "--tsan" in sys.argv:
+        print(build_tsan())
+    elif "--asan" in sys.argv:
+        print(build_tsan("address,undefined"))
+    else:
+        print(build(force=True))
