@@ -19,8 +19,9 @@
 
 #define CHECK(x) do { int rc__ = (x); if (rc__ != 0) { fprintf(stderr, "%s -> %d\n", #x, rc__); return 1; } } while (0)
 
-int main()
+int main(int argc, char **argv)
 {
+    const bool quick = argc > 1 && strcmp(argv[1], "quick") == 0;      // the subset the CPU test suite runs (about a minute)
     std::mt19937 rng(7);
     std::uniform_real_distribution<double> U(0.0, 1.0);
     const int n = 900;
@@ -40,7 +41,9 @@ int main()
     // mode, tile smem, mega_min, heavy_min, resolver batch, units per lane, find path
     const long long opts[8][7] = {{0, 32768, 0, 0, 4, 0, 0}, {1, 32768, 0, 0, 4, 0, 0}, {1, 1024, 0, 0, 4, 0, 0}, {1, 32768, 48, 0, 4, 0, 0},
                                   {0, 32768, 0, 8, 1, 2, 1}, {0, 32768, 0, 24, 8, 8, 0}, {1, 32768, 0, 8, 4, 0, 1}, {0, 32768, 0, 1, 4, 1, 0}};
+    int n_opts = 0;
     for (auto &o : opts) {
+        if (quick && ++n_opts > 4) break;
         lm_handle hd = nullptr;
         CHECK(lm_create(&hd, 0, n, 1 << 14, 60 * n));
         CHECK(lm_set_grid(hd, &grid));
@@ -63,7 +66,7 @@ int main()
     }
 
     // explicit-order resolver (mark / fire rounds with 64-bit atomicMin) on the pair list of a search, other norms
-    {
+    if (!quick) {
         lm_handle hd = nullptr;
         CHECK(lm_create(&hd, 0, n, 1 << 14, 60 * n));
         CHECK(lm_set_grid(hd, &grid));
@@ -104,7 +107,7 @@ int main()
         CHECK(lm_set_option(hd, LM_OPT_RESOLVE_MODE, mode));
         CHECK(lm_state_set(hd, lon.data(), lat.data(), sp0.data(), nullptr, n, nullptr));
         std::vector<int32_t> pairs(2 * 60 * n);
-        for (int step = 0; step < 3; ++step) {
+        for (int step = 0; step < (quick ? 2 : 3); ++step) {
             lm_stage_times stt = {{0, 0, 0, 0}, {1, 1, 1, 1}, {0.01f * step, 0.01f * step + 0.005f, 0.01f * step + 0.005f, 0.01f * step + 0.01f}};
             lm_rps_params p2 = {0.55, 0.55, 0.55, 3, (uint64_t)step};
             CHECK(lm_step(hd, LM_STEP_ADVECT | LM_STEP_INTERACT | LM_STEP_EMIT_PAIRS | LM_STEP_STATS | (step ? LM_STEP_DIFFUSE : 0), &stt, 3600.f,
@@ -130,7 +133,7 @@ int main()
     }
 
     // two latitude strips: routing passes, then two staged steps with the exchange buffers copied between the neighbours
-    {
+    if (!quick) {
         lm_grid g2 = {200.9, 31.9, 1.0 / h, ncx + 20, 40};
         lm_handle hs[2] = {nullptr, nullptr};
         lm_strip_buffers bf[2];

@@ -562,3 +562,25 @@ def test_hand_off_overflow_is_reported_not_resolved(abi, resolve_mode):
         assert np.array_equal(species, g["species0"])
     finally:
         L.lm_destroy(h)
+
+
+def test_kernels_are_race_free_under_thread_sanitizer():
+    """The emulated library under -fsanitize=thread (tests/cuda_emu/tsan_driver.cpp, quick subset): both resolvers with
+    shared-memory / scratch tiles and the whole-warp / whole-CTA paths, fused steps with diffusion, the record pipeline,
+    the analysis kernels.  A missing __syncthreads() / __syncwarp() / atomic in a kernel is a data-race report here.
+    (The full driver -- all resolver options, explicit-order resolver, two strips -- is run by hand:
+    profiles/r1z_tsan_emulated.txt.)"""
+    import subprocess
+    import emu_build
+    try:
+        exe = emu_build.build_tsan()
+    except subprocess.CalledProcessError:
+        pytest.skip("g++ -fsanitize=thread is not available here")
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=0 history_size=4 exitcode=66")
+    res = subprocess.run([exe, "quick"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1500)
+    err = res.stderr.decode(errors="replace")
+    if "FATAL: ThreadSanitizer" in err:                      # the sanitizer runtime cannot start on this kernel (ASLR layout)
+        pytest.skip("ThreadSanitizer cannot run here: " + err.strip().splitlines()[0])
+    assert "ThreadSanitizer" not in err, err[:4000]
+    assert res.returncode == 0, (res.returncode, err[:2000])
+    assert b"done" in res.stdout
