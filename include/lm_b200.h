@@ -262,6 +262,9 @@ int lm_reset_stats(lm_handle h, void *stream);
 #define LM_OPT_RESOLVE_MODE 8
 #define LM_OPT_RESOLVE_TILE_SMEM 9
 #define LM_OPT_RESOLVE_MEGA_MIN 10
+/*   LM_OPT_RESOLVE_TILE_SHAPE  tiled resolver: cells per tile, 0 = 64 x 16 (default), 1 = 32 x 16, 2 = 128 x 16,
+ *                   3 = 64 x 32 (the halo is 6 columns / 2 rows in every case).  Same results; for A/B measurements. */
+#define LM_OPT_RESOLVE_TILE_SHAPE 11
 int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Make `stream` wait for work of the last lm_step that is still running on the handle's internal stream
  * (LM_OPT_OVERLAP).  Only needed before the caller reads the resident arrays through pointers obtained earlier,

@@ -845,6 +845,10 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
             h->resolve_mode = (int)value;
             return LM_OK;
         }
+        case LM_OPT_RESOLVE_TILE_SHAPE:
+            if (value < 0 || value > 3) return LM_EINVAL;
+            h->resolve_tile_shape = (int)value;
+            return LM_OK;
         case LM_OPT_RESOLVE_MEGA_MIN:
             if (value < 0 || value > (1ll << 30)) return LM_EINVAL;
             h->resolve_mega_min = (int)value;

@@ -96,6 +96,7 @@ struct lm_handle_s {
     // tiled resolver (LM_OPT_RESOLVE_MODE = 1; csrc/pairs.cu): allocated when the mode is first switched on
     int resolve_mode;      // 0: nine phase launches (default) | 1: one tiled launch per phase range
     int resolve_tile_smem; // LM_OPT_RESOLVE_TILE_SMEM: bytes of species a tile keeps in shared memory
+    int resolve_tile_shape; // LM_OPT_RESOLVE_TILE_SHAPE: 0 = 64 x 16 cells (default), 1 = 32 x 16, 2 = 128 x 16, 3 = 64 x 32
     int resolve_mega_min;  // LM_OPT_RESOLVE_MEGA_MIN: pairs above which a unit goes to the whole CTA (0 = default, 8192)
     bool resolve_all_in_begin;   // this step's phases 6-8 already ran with 0-5 (tiled, single handle)
     int8_t *sp_snap;       // [max_particles] species before the first phase of a tiled launch

@@ -871,14 +871,12 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
 // shared-memory accesses, there is one launch instead of nine, and a tile's slow unit delays only its own CTA.
 // A tile whose loaded region holds more microbes than fit the CTA's shared memory works on a private slice of a global
 // scratch array instead (same code through a generic pointer); a cell is loaded by at most four tiles, which bounds it.
-constexpr int TILE_X = 64, TILE_Y = 16, TILE_HX = 6, TILE_HY = 2;
-constexpr int TILE_LY = TILE_Y + 2 * TILE_HY;              // loaded rows
+constexpr int TILE_HX = 6, TILE_HY = 2;                    // halo; the tile itself (TILE_X x TILE_Y cells) is a template parameter:
+                                                           // 64 x 16 by default, LM_OPT_RESOLVE_TILE_SHAPE picks another for A/B runs
 constexpr int TILE_THREADS = 256;
 constexpr int TILE_HEAVY_Q = 128;                          // dense units queued per phase for whole warps
 constexpr int TILE_MEGA_Q = 16;                            // ... and for the whole CTA (knots of hundreds of microbes per cell)
 constexpr unsigned int TILE_MEGA_MIN = 8192;               // ~128 microbes in one cell: 64 partners per anchor, where 256-wide scans win
-constexpr int TILE_LX = TILE_X + 2 * TILE_HX;              // loaded columns
-constexpr int TILE_UPT = (TILE_LX * TILE_LY + TILE_THREADS - 1) / TILE_THREADS;   // units per thread and phase (6)
 
 struct TileArgs {
     const int8_t *__restrict__ sp_in;    // snapshot of the species before the first phase of this launch
@@ -1057,8 +1055,11 @@ __device__ __forceinline__ PhaseGeom phase_geom(int ph)
     return g;
 }
 
+template <int TILE_X, int TILE_Y>
 __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs A)
 {
+    constexpr int TILE_LX = TILE_X + 2 * TILE_HX, TILE_LY = TILE_Y + 2 * TILE_HY;         // loaded columns, rows
+    constexpr int TILE_UPT = (TILE_LX * TILE_LY + TILE_THREADS - 1) / TILE_THREADS;       // units per thread and phase (64 x 16: 6)
     extern __shared__ __align__(16) int8_t s_species[];    // [smem_cap]
     __shared__ int s_p0[TILE_LY], s_cnt[TILE_LY], s_delta[TILE_LY];   // loaded row: first particle, particles, index delta
     __shared__ int s_cs[TILE_LY][TILE_LX + 1];             // cell_start of the loaded cells (+ one past the end of each row)
@@ -1075,8 +1076,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 4) resolve_tiled_kernel(TileArgs
     const int lx0 = max(0, ix0 - TILE_HX), lx1 = min(ncx, ix1 + TILE_HX);
     const int ly0 = max(0, iy0 - TILE_HY), ly1 = min(A.rows_local, iy1 + TILE_HY);
     const int lw = lx1 - lx0, lh = ly1 - ly0;
-    const unsigned int inv_lw = ((1u << 20) + (unsigned int)lw - 1u) / (unsigned int)lw;   // u / lw == (u * inv_lw) >> 20 for u < 1536, lw <= 76
-    static_assert(TILE_LX * TILE_LY <= 1536 && TILE_LX <= 76, "reciprocal division range");
+    const unsigned int inv_lw = ((1u << 20) + (unsigned int)lw - 1u) / (unsigned int)lw;   // u / lw == (u * inv_lw) >> 20 while u * lw < 2^20
+    static_assert((long long)TILE_LX * TILE_LY * TILE_LX < (1ll << 20) && TILE_LX * TILE_LY < 4096, "reciprocal division range");
+    static_assert(TILE_X % 2 == 0 && TILE_Y % 2 == 0, "tile origins on even rows and columns");
     for (int k = tid; k < lh * (lw + 1); k += TILE_THREADS) {
         const int t = k / (lw + 1), x = k - t * (lw + 1);
         s_cs[t][x] = __ldg(A.cell_start + (long long)(ly0 + t) * ncx + lx0 + x);
@@ -1234,6 +1236,17 @@ static void launch_resolve_pb(const ResolveArgs &R, int upl, unsigned int blocks
 // phases [first, last] of the canonical cell-phase order on the local rows.  Strip boundaries sit on even
 // global rows, so local and global row parities agree; same-cell and east units cover the owned rows,
 // cross-row units may reach into the ghost row (local row rows_owned), only in phases 6-8.
+template <int TX, int TY>
+static cudaError_t launch_tiled_shape(TileArgs &T, cudaStream_t s)
+{
+    T.tiles_x = (T.ncx + TX - 1) / TX;
+    const long long tiles = (long long)T.tiles_x * ((T.rows_local + TY - 1) / TY);
+    cudaError_t e = cudaFuncSetAttribute(resolve_tiled_kernel<TX, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_cap);
+    if (e != cudaSuccess) return e;
+    resolve_tiled_kernel<TX, TY><<<(unsigned)tiles, TILE_THREADS, (size_t)T.smem_cap, s>>>(T);
+    return cudaGetLastError();
+}
+
 // LM_OPT_RESOLVE_MODE = 1: phases [first, last] as ONE launch of resolve_tiled_kernel on a snapshot of the species
 static cudaError_t launch_resolve_tiled(lm_handle_s *h, int8_t *sp, int first, int last, cudaStream_t s)
 {
@@ -1253,13 +1266,14 @@ static cudaError_t launch_resolve_tiled(lm_handle_s *h, int8_t *sp, int first, i
     T.heavy_min = h->resolve_heavy_min > 0 ? (unsigned int)h->resolve_heavy_min : 4u * HEAVY_MIN;
     T.mega_min = h->resolve_mega_min > 0 ? (unsigned int)h->resolve_mega_min : TILE_MEGA_MIN;
     if (T.ncx <= 0 || T.rows_local <= 0) return cudaSuccess;
-    T.tiles_x = (T.ncx + TILE_X - 1) / TILE_X;
-    const long long tiles = (long long)T.tiles_x * ((T.rows_local + TILE_Y - 1) / TILE_Y);
-    e = cudaFuncSetAttribute(resolve_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T.smem_cap);
-    if (e != cudaSuccess) return e;
-    resolve_tiled_kernel<<<(unsigned)tiles, TILE_THREADS, (size_t)T.smem_cap, s>>>(T);
+    switch (h->resolve_tile_shape) {                       // LM_OPT_RESOLVE_TILE_SHAPE
+        case 1: e = launch_tiled_shape<32, 16>(T, s); break;
+        case 2: e = launch_tiled_shape<128, 16>(T, s); break;
+        case 3: e = launch_tiled_shape<64, 32>(T, s); break;
+        default: e = launch_tiled_shape<64, 16>(T, s); break;
+    }
     ++h->launches;
-    return cudaGetLastError();
+    return e;
 }
 
 cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int last, cudaStream_t s)

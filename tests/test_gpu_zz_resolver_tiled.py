@@ -26,11 +26,13 @@ def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
-def tiled(eng, smem=32768, heavy_min=0):
-    from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_HEAVY_MIN, LM_OPT_RESOLVE_MODE, LM_OPT_RESOLVE_TILE_SMEM
+def tiled(eng, smem=32768, heavy_min=0, shape=0):
+    from lagrangian_microbes_b200._lib import (LM_OPT_RESOLVE_HEAVY_MIN, LM_OPT_RESOLVE_MODE, LM_OPT_RESOLVE_TILE_SHAPE,
+                                               LM_OPT_RESOLVE_TILE_SMEM)
     eng.set_option(LM_OPT_RESOLVE_MODE, 1)
     eng.set_option(LM_OPT_RESOLVE_TILE_SMEM, smem)
     eng.set_option(LM_OPT_RESOLVE_HEAVY_MIN, heavy_min)
+    eng.set_option(LM_OPT_RESOLVE_TILE_SHAPE, shape)
 
 
 @pytest.mark.parametrize("name", ["rps_uniform", "rps_clustered", "rps_oddspecies"])
@@ -89,13 +91,14 @@ def test_live_species(engine_factory, kind):
     lon_d, lat_d = dev(lon), dev(lat)
     # (shared memory per tile, whole-warp limit): default; every tile in the global scratch; every unit with more than
     # 8 pairs on the whole-warp path; no whole-warp path at all
-    for smem, heavy_min in [(32768, 0), (1024, 0), (32768, 8), (65536, 0xffff)]:
-        tiled(eng, smem, heavy_min)
+    for smem, heavy_min, shape in [(32768, 0, 0), (1024, 0, 0), (32768, 8, 0), (65536, 0xffff, 0), (32768, 0, 1), (32768, 0, 2),
+                                   (1024, 8, 3)]:
+        tiled(eng, smem, heavy_min, shape)
         species = dev(sp0.copy())
         eng.interact_rps(lon_d, lat_d, species, r, *p, 5, 17)
         assert eng.sync_stats().n_pairs == want_pairs.shape[0]
         bad = int((species.cpu().numpy() != want_sp).sum())
-        assert bad == 0, "smem %d heavy_min %d: %d species differ" % (smem, heavy_min, bad)
+        assert bad == 0, "smem %d heavy_min %d shape %d: %d species differ" % (smem, heavy_min, shape, bad)
 
 
 def test_knots_on_the_whole_cta(engine_factory):

@@ -584,3 +584,34 @@ def test_kernels_are_race_free_under_thread_sanitizer():
     assert "ThreadSanitizer" not in err, err[:4000]
     assert res.returncode == 0, (res.returncode, err[:2000])
     assert b"done" in res.stdout
+
+
+@pytest.mark.parametrize("shape", [1, 2, 3])
+def test_tiled_resolver_other_tile_shapes(abi, shape):
+    """LM_OPT_RESOLVE_TILE_SHAPE: 32 x 16, 128 x 16 and 64 x 32 cells per tile (same halo) on the clustered golden case and
+    on a grid with several tiles of every shape."""
+    from conftest import golden
+    from lagrangian_microbes_b200 import _lib
+    L = abi
+    g = golden("rps_clustered.npz")
+    c = Cloud(31 + shape, 150, 37, 2200, knots=6)
+    cases = [(np.ascontiguousarray(g["lon"]), np.ascontiguousarray(g["lat"]), g["species0"], float(g["r"]),
+              (float(g["pRS"]), float(g["pPR"]), float(g["pSP"])), int(g["seed"]), int(g["step"]), g["species_cell"],
+              _lib.Grid(float(g["grid"][0]), float(g["grid"][1]), float(g["grid"][2]), int(g["grid_n"][0]), int(g["grid_n"][1]))),
+             (c.lon, c.lat, c.sp0, R, P, 5, 17, c.oracle(c.sp0, 0, 8),
+              _lib.Grid(c.grid["x0"], c.grid["y0"], c.grid["inv_h"], c.grid["ncx"], c.grid["ncy"]))]
+    for lon, lat, sp0, r, p, seed, step, want, grid in cases:
+        n = lon.size
+        h = ctypes.c_void_p()
+        assert L.lm_create(ctypes.byref(h), 0, n, 1 << 16, 40 * n) == 0
+        try:
+            assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+            assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, 1) == 0
+            assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_TILE_SHAPE, shape) == 0
+            species = sp0.copy()
+            prm = _lib.RpsParams(*p, seed, step)
+            assert L.lm_interact_rps(h, _ptr(lon), _ptr(lat), _ptr(species), n, r, ctypes.byref(prm), None, 0, None, None) == 0
+            assert L.lm_sync_stats(h, None, None) == 0
+            assert np.array_equal(species, want), "shape %d: %d species differ" % (shape, int((species != want).sum()))
+        finally:
+            L.lm_destroy(h)

@@ -12,10 +12,12 @@ import torch
 
 sys.path.insert(0, '/root/repo')
 import bench  # noqa: E402
-from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_MODE, LM_OPT_RESOLVE_TILE_SMEM  # noqa: E402
+from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_MODE, LM_OPT_RESOLVE_TILE_SHAPE, LM_OPT_RESOLVE_TILE_SMEM  # noqa: E402
 from lagrangian_microbes_b200.simulation import FusedSimulation  # noqa: E402
 
-SETTINGS = [(0, 32768), (1, 16384), (1, 32768), (1, 65536), (1, 131072), (0, 32768)]     # (mode, shared memory per tile)
+# (mode, shared memory per tile, tile shape: 0 = 64 x 16 cells, 1 = 32 x 16, 2 = 128 x 16, 3 = 64 x 32)
+SETTINGS = [(0, 32768, 0), (1, 16384, 0), (1, 32768, 0), (1, 65536, 0), (1, 131072, 0), (1, 32768, 1), (1, 32768, 2), (1, 65536, 2),
+            (1, 32768, 3), (1, 65536, 3), (0, 32768, 0)]
 
 hfs = bench.make_fieldset(64)
 sims = {}
@@ -31,11 +33,12 @@ for arg in sys.argv[1:]:
     sim = sims[workload]
     while sim.iteration < before:
         sim.step()
-    for mode, smem in SETTINGS:
+    for mode, smem, shape in SETTINGS:
         sim.engine.join()
         torch.cuda.synchronize()
         sim.engine.set_option(LM_OPT_RESOLVE_MODE, mode)
         sim.engine.set_option(LM_OPT_RESOLVE_TILE_SMEM, smem)
+        sim.engine.set_option(LM_OPT_RESOLVE_TILE_SHAPE, shape)
         for _ in range(3):
             sim.step()
         sim.engine.join()
@@ -51,7 +54,7 @@ for arg in sys.argv[1:]:
         sim.step(timing=True)
         ph = sim.engine.phase_times()
         st = sim.stats()
-        print(json.dumps({"workload": workload, "step": sim.iteration, "mode": mode, "tile_smem": smem,
+        print(json.dumps({"workload": workload, "step": sim.iteration, "mode": mode, "tile_smem": smem, "tile_shape": shape,
                           "ms_per_step": round(ms, 4), "rps_ms": round(ph[3], 4), "find_ms": round(ph[2], 4),
                           "pairs": int(st.n_pairs), "species": [int(c) for c in st.species_count]}), flush=True)
     sim.engine.set_option(LM_OPT_RESOLVE_MODE, 0)
