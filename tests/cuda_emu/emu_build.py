@@ -70,18 +70,22 @@ def build(force=False):
     return so
 
 
-def build_tsan(sanitizer="thread"):
+def build_tsan(sanitizer="thread", force=False):
     """tests/cuda_emu/_build/tsan_driver: the emulated library + tsan_driver.cpp under ThreadSanitizer (see the driver);
     sanitizer="address,undefined" builds asan_driver instead: out-of-bounds accesses of global / shared memory."""
     os.makedirs(OUT, exist_ok=True)
+    exe = os.path.join(OUT, "tsan_driver" if sanitizer == "thread" else "asan_driver")
+    deps = [os.path.join(CSRC, f) for f in SOURCES + ["lm_internal.cuh", "philox.cuh"]] + \
+           [os.path.join(HERE, f) for f in ("cuda_runtime.h", "emu.cpp", "tsan_driver.cpp", "emu_build.py")]
+    if not force and os.path.exists(exe) and all(os.path.getmtime(exe) >= os.path.getmtime(d) for d in deps):
+        return exe
     cpps = []
     for f in SOURCES:
         text, _ = transform(open(os.path.join(CSRC, f)).read())
-        path = os.path.join(OUT, f.replace(".cu", "_emu.cpp"))
+        path = os.path.join(OUT, f.replace(".cu", "_san.cpp"))
         with open(path, "w") as fh:
             fh.write(text)
         cpps.append(path)
-    exe = os.path.join(OUT, "tsan_driver" if sanitizer == "thread" else "asan_driver")
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-pthread", "-fsanitize=" + sanitizer, "-fno-omit-frame-pointer", "-ffp-contract=off", "-w", "-I", HERE, "-I", CSRC,
            "-o", exe] + cpps + [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "tsan_driver.cpp")]
     subprocess.check_call(cmd)
@@ -91,8 +95,8 @@ def build_tsan(sanitizer="thread"):
 if __name__ == "__main__":
     import sys
     if "--tsan" in sys.argv:
-        print(build_tsan())
+        print(build_tsan(force=True))
     elif "--asan" in sys.argv:
-        print(build_tsan("address,undefined"))
+        print(build_tsan("address,undefined", force=True))
     else:
         print(build(force=True))
