@@ -28,7 +28,8 @@ def _cloud(kind, n, seed):
     elif kind == "clustered":
         lat = 30 + 1e-3 * rng.standard_normal(n) * rng.random(n) ** 4
         lon = 210 + 1e-3 * rng.standard_normal(n) * rng.random(n) ** 4
-        lat[:20] = lat[20:40]; lon[:20] = lon[20:40]
+        if n >= 40:
+            lat[:20] = lat[20:40]; lon[:20] = lon[20:40]
     else:
         lat = -80 + 160 * rng.random(n); lon = 360 * rng.random(n)
     return lat.astype(np.float32), lon.astype(np.float32)
