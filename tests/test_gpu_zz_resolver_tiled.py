@@ -142,7 +142,7 @@ def test_fused_loop_equals_the_phase_launches():
     from test_gpu_strips import P, R, particles, small_fs
     fs = small_fs()
     lon, lat, sp = particles(60000, 5, clustered=True)
-    sims = [FusedSimulation(lon, lat, sp, R, *P, fs, dt_seconds=3600.0, seed=3, emit_pairs=True, pair_capacity=40 * lon.size,
+    sims = [FusedSimulation(lon, lat, sp, R, *P, fs, dt_seconds=3600.0, seed=3, emit_pairs=True, pair_capacity=80 * lon.size,
                             regrid_every=4, grid_margin=0.25) for _ in range(2)]
     tiled(sims[1].engine)
     for step in range(12):
