@@ -34,4 +34,7 @@ def engine_factory():
         return e
     yield make
     for e in made:
-        e.close()
+        try:
+            e.close()
+        except Exception:      # a faulted context must not turn the whole session into an error
+            pass
