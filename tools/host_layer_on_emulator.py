@@ -9,7 +9,9 @@ Checks FusedSimulation.run_to_file (stride 2, regridding on) against a twin simu
 tests/test_gpu_zz_run_to_file.py -- and prints the per-step species census."""
 import ctypes, os, sys, contextlib, tempfile, numpy as np, torch
 from datetime import datetime, timedelta
-sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests/cuda_emu'); sys.path.insert(0,'/root/repo/tests')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests', 'cuda_emu')); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+assert not __debug__, 'run with python -O (the wrappers\' is_cuda asserts must be stripped for the emulator)'
 import emu_build
 from lagrangian_microbes_b200 import _lib
 _lib._lib = _lib.declare(ctypes.CDLL(emu_build.build()))
