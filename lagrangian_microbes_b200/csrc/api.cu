@@ -893,4 +893,16 @@ int lm_compose_frame(const uint32_t *counts, const int32_t *top, const int8_t *s
     return LM_OK;
 }
 
+// ---- lossless delta packing of the position record (csrc/record.cu); handle-free ----------------------------
+int lm_record_delta_pack(const float *prev_lon, const float *prev_lat, const float *lon, const float *lat, int64_t n,
+                         int16_t *dlon_out, int16_t *dlat_out, uint32_t *esc_out, int64_t esc_cap, uint32_t *esc_count,
+                         void *stream)
+{
+    if (n < 0 || n >= (1ll << 31) || esc_cap < 0 || !esc_count || (esc_cap > 0 && !esc_out)) return LM_EINVAL;
+    if (n > 0 && (!prev_lon || !prev_lat || !lon || !lat || !dlon_out || !dlat_out)) return LM_EINVAL;
+    LM_CUDA(launch_record_delta_pack(prev_lon, prev_lat, lon, lat, n, dlon_out, dlat_out, esc_out, esc_cap, esc_count,
+                                     as_stream(stream)));
+    return LM_OK;
+}
+
 }  // extern "C"

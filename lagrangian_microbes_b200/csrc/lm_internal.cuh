@@ -193,6 +193,11 @@ cudaError_t launch_raster(const float *lon, const float *lat, const int8_t *sp, 
 cudaError_t launch_compose(const uint32_t *counts, const int32_t *top, const int8_t *sp, int width, int height, int mode,
                            const uint8_t *palette_rgb, uint8_t *rgb, cudaStream_t s, int64_t *launches);
 
+// lossless delta packing of the position record (csrc/record.cu)
+cudaError_t launch_record_delta_pack(const float *prev_lon, const float *prev_lat, const float *lon, const float *lat, int64_t n,
+                                     int16_t *dlon, int16_t *dlat, uint32_t *esc, int64_t esc_cap, uint32_t *esc_count,
+                                     cudaStream_t s);
+
 void set_last_cuda_error(cudaError_t e, const char *where);
 
 }  // namespace lm

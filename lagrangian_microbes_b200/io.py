@@ -162,3 +162,38 @@ class RecordAssembler:
         return write_particle_file(os.path.join(output_dir, filename),
                                    {"longitude": self.longitude, "latitude": self.latitude, "species": self.species},
                                    self.times)
+
+
+# ---- the delta-packed position record (csrc/record.cu, lm_record_delta_pack) ------------------------------------------
+DELTA_ESCAPE = -32768
+
+
+def _mono_key(x):
+    """float32 array -> int64 keys monotone in the value (negative: ~bits, else bits | 0x80000000): a bijection on all
+    2^32 bit patterns, the same map as csrc/record.cu::mono_key."""
+    b = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    return np.where(b & np.uint32(0x80000000), ~b, b | np.uint32(0x80000000)).astype(np.int64)
+
+
+def _from_mono_key(k):
+    k = k.astype(np.uint32)
+    return np.where(k & np.uint32(0x80000000), k & np.uint32(0x7FFFFFFF), ~k).astype(np.uint32).view(np.float32)
+
+
+def unpack_delta_record(prev_lon, prev_lat, dlon, dlat, escapes):
+    """Host decoder of ``lm_record_delta_pack``: the float32 (lon, lat) of a step, BIT-EXACT, from the previous step's
+    record, the int16 ulp differences and the escape list (uint32 (m, 2): slot = 2 i + (0 lon | 1 lat), raw bits)."""
+    out = []
+    for prev, d in ((prev_lon, dlon), (prev_lat, dlat)):
+        d = np.asarray(d, dtype=np.int16)
+        out.append(_from_mono_key(_mono_key(prev) + np.where(d == DELTA_ESCAPE, 0, d.astype(np.int64))))
+    esc = np.asarray(escapes, dtype=np.uint32).reshape(-1, 2)
+    if esc.shape[0]:
+        idx, coord = (esc[:, 0] >> 1).astype(np.int64), esc[:, 0] & 1
+        for c in (0, 1):
+            sel = coord == c
+            out[c].view(np.uint32)[idx[sel]] = esc[sel, 1]
+    n_marked = int((np.asarray(dlon) == DELTA_ESCAPE).sum() + (np.asarray(dlat) == DELTA_ESCAPE).sum())
+    if n_marked != esc.shape[0]:
+        raise ValueError("delta record: %d escape markers but %d escape entries (list overflowed?)" % (n_marked, esc.shape[0]))
+    return out[0], out[1]

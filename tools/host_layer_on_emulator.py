@@ -72,3 +72,29 @@ with tempfile.TemporaryDirectory() as d:
             assert list(counts[col]) == [int((ws == s).sum()) for s in (1,2,3)]
             col += 1
     print("run_to_file ok:", data["species"].shape, data.times, counts.tolist())
+
+# ---- record.DeltaRecordPacker (lm_record_delta_pack + io.unpack_delta_record): a pipelined stream with overflow steps ----
+class _Ev:
+    def record(self, *a): pass
+    def synchronize(self): pass
+torch.cuda.Event = _Ev
+_S.synchronize = lambda self: None
+class _FakeCudaTensor(torch.Tensor):
+    is_cuda = property(lambda self: True)
+from lagrangian_microbes_b200.record import DeltaRecordPacker
+n = 5003
+packer = DeltaRecordPacker(n, escape_capacity=16, device=_dev)
+cur_lon = (205 + 10*rng.random(n)).astype(np.float32); cur_lat = (25 + 10*rng.random(n)).astype(np.float32)
+want = []
+for k in range(7):
+    cur_lon = (cur_lon + 0.02*(rng.random(n) - 0.5)).astype(np.float32); cur_lat = (cur_lat + 0.02*(rng.random(n) - 0.5)).astype(np.float32)
+    if k == 3: cur_lon[:5] += 3.0            # 5 escapes: fits the list
+    if k == 5: cur_lon[:40] += 2.0           # 40 escapes: overflows, resent as a key frame
+    packer.push(torch.from_numpy(cur_lon.copy()).as_subclass(_FakeCudaTensor), torch.from_numpy(cur_lat.copy()).as_subclass(_FakeCudaTensor))
+    want.append((cur_lon.copy(), cur_lat.copy()))
+    if k >= 1:
+        g = packer.pop()
+        assert np.array_equal(g[0].view(np.uint32), want[k-1][0].view(np.uint32)) and np.array_equal(g[1].view(np.uint32), want[k-1][1].view(np.uint32)), k
+g = packer.pop()
+assert np.array_equal(g[0].view(np.uint32), want[-1][0].view(np.uint32)) and np.array_equal(g[1].view(np.uint32), want[-1][1].view(np.uint32))
+print("delta record stream ok: %d B over the link for %d plain" % (packer.bytes_d2h, 8*n*7))
