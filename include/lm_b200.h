@@ -325,6 +325,13 @@ int lm_compose_frame(const uint32_t *counts, const int32_t *top, const int8_t *s
 int lm_record_delta_pack(const float *prev_lon, const float *prev_lat, const float *lon, const float *lat, int64_t n,
                          int16_t *dlon_out, int16_t *dlat_out, uint32_t *esc_out, int64_t esc_cap, uint32_t *esc_count,
                          void *stream);
+/* Host decoder of lm_record_delta_pack: all pointers are HOST arrays, no device work.  lon_out / lat_out (float32[n]) may
+ * alias prev_lon / prev_lat (decoding in place).  esc: uint32[n_esc][2].  n_threads host threads (>= 1) share the arrays.
+ * Bit-exact inverse of the packing.  LM_EINVAL if the number of LM_DELTA_ESCAPE markers differs from n_esc (the escape
+ * list overflowed: resend that step plain) or an escape entry points outside the arrays. */
+int lm_record_delta_unpack_host(const float *prev_lon, const float *prev_lat, const int16_t *dlon, const int16_t *dlat,
+                                const uint32_t *esc, int64_t n_esc, int64_t n, float *lon_out, float *lat_out,
+                                int32_t n_threads);
 
 #ifdef __cplusplus
 }

@@ -158,6 +158,7 @@ def declare(L):
         "lm_rasterize": (ctypes.c_int, [vp, vp, vp, i64, dbl, dbl, dbl, dbl, i32, i32, vp, vp, vp]),
         "lm_compose_frame": (ctypes.c_int, [vp, vp, vp, i32, i32, i32, ctypes.c_char_p, vp, vp]),
         "lm_record_delta_pack": (ctypes.c_int, [vp, vp, vp, vp, i64, vp, vp, vp, i64, vp, vp]),
+        "lm_record_delta_unpack_host": (ctypes.c_int, [vp, vp, vp, vp, vp, i64, i64, vp, vp, i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -172,7 +173,8 @@ EXPORTS = ["lm_version", "lm_error_string", "lm_last_cuda_error", "lm_create", "
            "lm_state_get_host", "lm_host_copies_sync", "lm_state_view", "lm_sync_stats", "lm_reset_stats", "lm_launch_count",
            "lm_phase_times", "lm_strip_alloc", "lm_set_strip", "lm_strip_buffers_get", "lm_step_move", "lm_step_bin",
            "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option", "lm_join", "lm_record_next_step",
-           "lm_pair_distance_hist", "lm_rasterize", "lm_compose_frame", "lm_record_delta_pack"]
+           "lm_pair_distance_hist", "lm_rasterize", "lm_compose_frame", "lm_record_delta_pack",
+           "lm_record_delta_unpack_host"]
 
 
 def check(code, what):

@@ -905,4 +905,14 @@ int lm_record_delta_pack(const float *prev_lon, const float *prev_lat, const flo
     return LM_OK;
 }
 
+int lm_record_delta_unpack_host(const float *prev_lon, const float *prev_lat, const int16_t *dlon, const int16_t *dlat,
+                                const uint32_t *esc, int64_t n_esc, int64_t n, float *lon_out, float *lat_out,
+                                int32_t n_threads)
+{
+    if (n < 0 || n >= (1ll << 31) || n_esc < 0 || (n_esc > 0 && !esc) || n_threads < 1 || n_threads > 1024) return LM_EINVAL;
+    if (n > 0 && (!prev_lon || !prev_lat || !dlon || !dlat || !lon_out || !lat_out)) return LM_EINVAL;
+    const int64_t marked = record_delta_unpack_host(prev_lon, prev_lat, dlon, dlat, esc, n_esc, n, lon_out, lat_out, n_threads);
+    return marked == n_esc ? LM_OK : LM_EINVAL;
+}
+
 }  // extern "C"

@@ -198,6 +198,9 @@ cudaError_t launch_record_delta_pack(const float *prev_lon, const float *prev_la
                                      int16_t *dlon, int16_t *dlat, uint32_t *esc, int64_t esc_cap, uint32_t *esc_count,
                                      cudaStream_t s);
 
+int64_t record_delta_unpack_host(const float *prev_lon, const float *prev_lat, const int16_t *dlon, const int16_t *dlat,
+                                 const uint32_t *esc, int64_t n_esc, int64_t n, float *lon_out, float *lat_out, int n_threads);
+
 void set_last_cuda_error(cudaError_t e, const char *where);
 
 }  // namespace lm

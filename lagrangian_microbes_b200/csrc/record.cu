@@ -14,6 +14,10 @@
 // 4 B instead of 8 B per microbe-step, bit-exact after decoding (io.py::unpack_delta_record adds the deltas to the
 // previous record's keys and applies the escapes).  HBM-bound: R 16 + W 4 B per microbe; four microbes per thread
 // with 16-byte loads and 8-byte stores when the arrays are aligned, a scalar path otherwise and for the tail.
+#include <algorithm>
+#include <thread>
+#include <vector>
+
 #include "lm_internal.cuh"
 
 namespace lm {
@@ -92,6 +96,58 @@ cudaError_t launch_record_delta_pack(const float *prev_lon, const float *prev_la
                                                                               esc2, (long long)esc_cap, esc_count);
     }
     return cudaGetLastError();
+}
+
+
+// ---- host decoder (plain C++ on HOST arrays; no device work) ---------------------------------------------------
+// branch-free forms of mono_key and its inverse (the loop below vectorises)
+static inline uint32_t host_key(uint32_t b) { return b ^ ((uint32_t)((int32_t)b >> 31) | 0x80000000u); }
+static inline uint32_t host_unkey(uint32_t k) { return k ^ (~(uint32_t)((int32_t)k >> 31) | 0x80000000u); }
+
+static int64_t unpack_range(const uint32_t *__restrict__ prev, const int16_t *__restrict__ d, uint32_t *out, int64_t a, int64_t b)
+{
+    int64_t marked = 0;
+    if (out == prev) {                                         // decoding in place
+        for (int64_t i = a; i < b; ++i) {
+            const int32_t v = d[i], is_esc = v == -32768;
+            marked += is_esc;
+            out[i] = host_unkey(host_key(out[i]) + (uint32_t)(v & (is_esc - 1)));
+        }
+        return marked;
+    }
+    uint32_t *__restrict__ o = out;
+    for (int64_t i = a; i < b; ++i) {
+        const int32_t v = d[i], is_esc = v == -32768;
+        marked += is_esc;
+        o[i] = host_unkey(host_key(prev[i]) + (uint32_t)(v & (is_esc - 1)));       // exact: the true key is in range
+    }
+    return marked;
+}
+
+// -> number of escape markers met, or -1 if an escape entry points outside the arrays
+int64_t record_delta_unpack_host(const float *prev_lon, const float *prev_lat, const int16_t *dlon, const int16_t *dlat,
+                                 const uint32_t *esc, int64_t n_esc, int64_t n, float *lon_out, float *lat_out, int n_threads)
+{
+    const uint32_t *pl = reinterpret_cast<const uint32_t *>(prev_lon), *pa = reinterpret_cast<const uint32_t *>(prev_lat);
+    uint32_t *ol = reinterpret_cast<uint32_t *>(lon_out), *oa = reinterpret_cast<uint32_t *>(lat_out);
+    const int T = (int)std::max<int64_t>(1, std::min<int64_t>(n_threads, n / 65536));          // a thread is not worth less than 64k microbes
+    std::vector<int64_t> marked((size_t)T, 0);
+    auto work = [&](int t) {
+        const int64_t a = n * t / T, b = n * (t + 1) / T;
+        marked[(size_t)t] = unpack_range(pl, dlon, ol, a, b) + unpack_range(pa, dlat, oa, a, b);
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto &th : pool) th.join();
+    int64_t total = 0;
+    for (int64_t m : marked) total += m;
+    for (int64_t k = 0; k < n_esc; ++k) {
+        const uint32_t slot = esc[2 * k];
+        if ((int64_t)(slot >> 1) >= n) return -1;
+        ((slot & 1u) ? oa : ol)[slot >> 1] = esc[2 * k + 1];
+    }
+    return total;
 }
 
 }  // namespace lm

@@ -1,6 +1,6 @@
 """The per-step position record over PCIe at 4 B instead of 8 B per microbe-step ("on-GPU
 quantise/delta-pack"): ``lm_record_delta_pack`` (csrc/record.cu) sends step k as int16 ulp differences to step k-1,
-lossless, and ``io.unpack_delta_record`` restores the float32 arrays the reference stores
+lossless, and ``lm_record_delta_unpack_host`` (host threads; NumPy twin: ``io.unpack_delta_record``) restores the float32 arrays the reference stores
 (/root/reference/particle_advecter.py:233-235, interaction_simulator.py:108-110) bit for bit.
 
     packer = DeltaRecordPacker(n)                    # device + pinned buffers, two sets
@@ -10,20 +10,44 @@ lossless, and ``io.unpack_delta_record`` restores the float32 arrays the referen
         ...                                          # (the next step may be enqueued here)
         lon, lat = packer.pop()                      # float32 numpy, bit-exact
 
-The first record and any step whose escape list overflows travel as plain float32 (a key frame)."""
+The first record and any step whose escape list overflows travel as plain float32 (a key frame).  Escapes are not
+only far jumps: within about a degree of the equator (or of longitude 0) float32 ulps are so fine that one step's
+displacement exceeds 32767 of them, so those microbes always go through the list -- 1-2 % of BASELINE config 4's microbes
+(lat 0-60); the default list holds n / 16 entries (0.5 B per microbe of D2H)."""
 import ctypes
 
 import numpy as np
 import torch
 
 from . import _lib
-from . import io as lmio
+
+
+def unpack_delta_record_native(prev_lon, prev_lat, dlon, dlat, escapes, n_threads=None, out=None):
+    """``io.unpack_delta_record`` through the library's multi-threaded host decoder (``lm_record_delta_unpack_host``):
+    float32 numpy arrays (lon, lat), bit-exact.  ``out`` = (lon, lat) arrays to fill (may be the ``prev`` arrays)."""
+    import os
+    L = _lib.lib()
+    c = lambda a, dt: np.ascontiguousarray(a, dtype=dt)
+    prev_lon, prev_lat = c(prev_lon, np.float32), c(prev_lat, np.float32)
+    dlon, dlat = c(dlon, np.int16), c(dlat, np.int16)
+    esc = c(escapes, np.uint32).reshape(-1, 2)
+    n = prev_lon.size
+    assert prev_lat.size == n and dlon.size == n and dlat.size == n
+    lon, lat = out if out is not None else (np.empty(n, dtype=np.float32), np.empty(n, dtype=np.float32))
+    assert lon.dtype == lat.dtype == np.float32 and lon.size == lat.size == n and lon.flags.c_contiguous and lat.flags.c_contiguous
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)
+    threads = int(n_threads) if n_threads else max(1, min(16, (os.cpu_count() or 1)))
+    rc = L.lm_record_delta_unpack_host(p(prev_lon), p(prev_lat), p(dlon), p(dlat), p(esc), esc.shape[0], n, p(lon), p(lat), threads)
+    if rc == _lib.LM_EINVAL:
+        raise ValueError("delta record: escape markers and escape entries disagree (list overflowed?)")
+    _lib.check(rc, "lm_record_delta_unpack_host")
+    return lon, lat
 
 
 class DeltaRecordPacker:
     def __init__(self, n, escape_capacity=None, device=None):
         self.n = int(n)
-        self.cap = int(escape_capacity if escape_capacity is not None else max(1024, self.n // 64))
+        self.cap = int(escape_capacity if escape_capacity is not None else max(1024, self.n // 16))
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
         self.L = _lib.lib()
         self.prev = None                                       # device (lon, lat) of the last pushed record
@@ -89,8 +113,8 @@ class DeltaRecordPacker:
                 kind = "key"
             else:
                 esc = self.esc_host[slot].numpy()[:m].view(np.uint32)
-                lon, lat = lmio.unpack_delta_record(self.host_prev[0], self.host_prev[1], self.d_host[slot][0].numpy(),
-                                                    self.d_host[slot][1].numpy(), esc)
+                lon, lat = unpack_delta_record_native(self.host_prev[0], self.host_prev[1], self.d_host[slot][0].numpy(),
+                                                      self.d_host[slot][1].numpy(), esc)
         if kind == "key":
             lon, lat = self.key_host[slot][0].numpy().copy(), self.key_host[slot][1].numpy().copy()
         self.host_prev = (lon, lat)

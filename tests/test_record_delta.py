@@ -82,6 +82,16 @@ def test_delta_pack_executed_against_the_oracle_and_round_trip(abi, n, offset):
     got_lon, got_lat = lmio.unpack_delta_record(prev_lon, prev_lat, dlon, dlat, esc[:m])
     assert np.array_equal(got_lon.view(np.uint32), lon.view(np.uint32))       # bit for bit, NaN payloads included
     assert np.array_equal(got_lat.view(np.uint32), lat.view(np.uint32))
+    # the library's own host decoder (lm_record_delta_unpack_host), separate outputs and in place
+    out_lon, out_lat = np.full(n, 7, dtype=np.float32), np.full(n, 7, dtype=np.float32)
+    e = np.ascontiguousarray(esc[:m])
+    assert abi.lm_record_delta_unpack_host(_ptr(prev_lon), _ptr(prev_lat), _ptr(dlon), _ptr(dlat), _ptr(e), m, n,
+                                           _ptr(out_lon), _ptr(out_lat), 3) == 0
+    assert np.array_equal(out_lon.view(np.uint32), lon.view(np.uint32)) and np.array_equal(out_lat.view(np.uint32), lat.view(np.uint32))
+    in_lon, in_lat = prev_lon.copy(), prev_lat.copy()
+    assert abi.lm_record_delta_unpack_host(_ptr(in_lon), _ptr(in_lat), _ptr(dlon), _ptr(dlat), _ptr(e), m, n,
+                                           _ptr(in_lon), _ptr(in_lat), 1) == 0
+    assert np.array_equal(in_lon.view(np.uint32), lon.view(np.uint32)) and np.array_equal(in_lat.view(np.uint32), lat.view(np.uint32))
 
 
 def test_escape_overflow_is_counted_not_written_past_the_list(abi):
@@ -94,6 +104,37 @@ def test_escape_overflow_is_counted_not_written_past_the_list(abi):
     assert (esc[:8, 0] != 0xABCDABCD).all() and esc.shape[0] == 8
     with pytest.raises(ValueError):
         lmio.unpack_delta_record(prev_lon, prev_lat, dlon, dlat, esc[:8])
+    from lagrangian_microbes_b200 import _lib
+    out, out2 = np.zeros(n, dtype=np.float32), np.zeros(n, dtype=np.float32)
+    e = np.ascontiguousarray(esc[:8])
+    assert abi.lm_record_delta_unpack_host(_ptr(prev_lon), _ptr(prev_lat), _ptr(dlon), _ptr(dlat), _ptr(e), 8, n, _ptr(out), _ptr(out2),
+                                           2) == _lib.LM_EINVAL
+    bad = np.array([[2 * n + 1, 0]], dtype=np.uint32)                         # an entry outside the arrays
+    assert abi.lm_record_delta_unpack_host(_ptr(prev_lon), _ptr(prev_lat), _ptr(dlon), _ptr(dlat), _ptr(bad), 1, n, _ptr(out), _ptr(out2),
+                                           2) == _lib.LM_EINVAL
+
+
+def test_host_decoder_of_the_shipped_library_many_threads():
+    """The product's own .so on the CPU (a host function: no device call): 300,000 microbes over 4 threads, packed by the
+    NumPy twin of the kernel's arithmetic (io._mono_key), decoded natively and by io.unpack_delta_record."""
+    from lagrangian_microbes_b200 import io as lmio
+    from lagrangian_microbes_b200.record import unpack_delta_record_native
+    n = 300_000
+    prev_lon, prev_lat, lon, lat = _records(n, seed=77)
+    esc = []
+    ds = []
+    for c, (prev, cur) in enumerate(((prev_lon, lon), (prev_lat, lat))):
+        d = lmio._mono_key(cur) - lmio._mono_key(prev)
+        far = np.abs(d) > 32767
+        ds.append(np.where(far, lmio.DELTA_ESCAPE, d).astype(np.int16))
+        esc += [(2 * int(i) + c, int(cur.view(np.uint32)[i])) for i in np.flatnonzero(far)]
+    esc = np.array(esc, dtype=np.uint32).reshape(-1, 2)
+    a = unpack_delta_record_native(prev_lon, prev_lat, ds[0], ds[1], esc, n_threads=4)
+    b = lmio.unpack_delta_record(prev_lon, prev_lat, ds[0], ds[1], esc)
+    for got in (a, b):
+        assert np.array_equal(got[0].view(np.uint32), lon.view(np.uint32)) and np.array_equal(got[1].view(np.uint32), lat.view(np.uint32))
+    with pytest.raises(ValueError):
+        unpack_delta_record_native(prev_lon, prev_lat, ds[0], ds[1], esc[:-1])
 
 
 def test_delta_pack_rejects_bad_arguments(abi):
