@@ -14,11 +14,11 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out/r2a
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $O/smoke.log 2>&1
-timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zz_analysis.py --deselect tests/test_gpu_zz_resolver_tiled.py --deselect tests/test_gpu_zz_run_to_file.py --deselect tests/test_gpu_zz_record_delta.py > $O/pytest_verified.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q --deselect tests/test_gpu_zz_analysis.py --deselect tests/test_gpu_zz_resolver_tiled.py --deselect tests/test_gpu_zz_run_to_file.py --deselect tests/test_gpu_zzz_record_delta.py > $O/pytest_verified.log 2>&1
 timeout 600 python -m pytest tests/test_gpu_zz_resolver_tiled.py -m gpu -rxX -v --runxfail > $O/pytest_tiled.log 2>&1
 timeout 600 python -m pytest tests/test_gpu_zz_analysis.py -m gpu -rxX -v --runxfail > $O/pytest_analysis.log 2>&1
 timeout 600 python -m pytest tests/test_gpu_zz_run_to_file.py -m gpu -rxX -v --runxfail > $O/pytest_run_to_file.log 2>&1
-timeout 300 python -m pytest tests/test_gpu_zz_record_delta.py -m gpu -rxX -v --runxfail > $O/pytest_record_delta.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_zzz_record_delta.py -m gpu -rxX -v --runxfail > $O/pytest_record_delta.log 2>&1
 tail -3 $O/pytest_verified.log $O/pytest_tiled.log $O/pytest_analysis.log $O/pytest_run_to_file.log $O/pytest_record_delta.log
 if grep -q "failed\|error" $O/pytest_tiled.log; then echo "tiled resolver NOT green: skipping its measurements"; else
   timeout 900 python tools/tiled_sweep.py config2:1500:200 shard:0:20 shard:1000:20 config3:0:10 config3:400:10 > $O/tiled_sweep.jsonl 2> $O/tiled_sweep.err
