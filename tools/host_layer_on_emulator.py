@@ -53,7 +53,7 @@ class HostFS:
     @staticmethod
     def to_device(device): return tuple(torch.from_numpy(a) for a in (fs0.u, fs0.v, fs0.lon, fs0.lat))
 rng = np.random.default_rng(9)
-n = 800
+n = n_sim = 800
 lon = (201.5 + 0.2*rng.random(n)).astype(np.float32); lat = (32.5 + 0.15*rng.random(n)).astype(np.float32)
 sp = rng.integers(1,4,n).astype(np.int8)
 mk = lambda: FusedSimulation(lon, lat, sp, 0.01, 0.55, 0.6, 0.9, HostFS, dt_seconds=3600.0, seed=4, emit_pairs=False, regrid_every=2, grid_margin=0.1, max_cells=1<<14, pair_capacity=40*n)
@@ -72,6 +72,8 @@ with tempfile.TemporaryDirectory() as d:
             assert list(counts[col]) == [int((ws == s).sum()) for s in (1,2,3)]
             col += 1
     print("run_to_file ok:", data["species"].shape, data.times, counts.tolist())
+    plain = {k: np.array(data[k]) for k in ("longitude", "latitude", "species")}
+
 
 # ---- record.DeltaRecordPacker (lm_record_delta_pack + io.unpack_delta_record): a pipelined stream with overflow steps ----
 class _Ev:
@@ -98,3 +100,14 @@ for k in range(7):
 g = packer.pop()
 assert np.array_equal(g[0].view(np.uint32), want[-1][0].view(np.uint32)) and np.array_equal(g[1].view(np.uint32), want[-1][1].view(np.uint32))
 print("delta record stream ok: %d B over the link for %d plain" % (packer.bytes_d2h, 8*n*7))
+
+# ---- run_to_file(packed=True): the same file as the plain record, bit for bit --------------------------------------------
+c = mk()
+with tempfile.TemporaryDirectory() as d:
+    path, counts2 = c.run_to_file(d, t0, t0 + steps*dt, dt, stride=stride, packed=True)
+    data2 = lmio.read_particle_file(path)
+    for k in ("longitude", "latitude", "species"):
+        a2 = np.array(data2[k])
+        assert np.array_equal(a2.view(np.uint32) if a2.dtype == np.float32 else a2, plain[k].view(np.uint32) if a2.dtype == np.float32 else plain[k]), k
+    assert np.array_equal(counts2, counts)
+    print("run_to_file(packed=True) ok: %d B of record over the link, plain %d" % (c.record_bytes_d2h, 9 * n_sim * data2["species"].shape[1]))
