@@ -8,7 +8,7 @@
 //
 // Workload: a random cloud with knots (so the whole-warp and whole-CTA resolver paths run), pair search + RPS through
 // lm_interact_rps with the nine-phase and the tiled resolver (shared-memory and scratch tiles; the two must agree),
-// three fused lm_step calls on a synthetic velocity field, a two-strip staged step, and the analysis kernels.
+// three fused lm_step calls on a synthetic velocity field, a two-strip staged step, the analysis kernels and the delta-packed record.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -197,6 +197,26 @@ int main(int argc, char **argv)
     const uint8_t pal[12] = {255, 255, 255, 255, 0, 0, 50, 205, 50, 0, 0, 255};
     CHECK(lm_rasterize(lon.data(), lat.data(), sp0.data(), n, 201.0, 201.7, 32.0, 32.2, 40, 24, counts.data(), top.data(), nullptr));
     CHECK(lm_compose_frame(counts.data(), top.data(), sp0.data(), 40, 24, LM_FRAME_LAST_DRAWN, pal, rgb.data(), nullptr));
+    // the delta-packed record: pack (vector and scalar paths, a small escape list that overflows), decode, compare
+    {
+        std::vector<float> cl(lon), ca(lat);
+        for (int i = 0; i < n; ++i) { cl[i] += (float)(0.01 * (U(rng) - 0.5)); ca[i] += (float)(0.01 * (U(rng) - 0.5)); }
+        for (int i = 0; i < 12; ++i) cl[7 * i] += 3.0f;                    // far jumps: escapes from several warps at once
+        std::vector<int16_t> dl(n + 1), da(n + 1);
+        for (int off = 0; off < 2; ++off) {                                // off = 1: int16 outputs not 8-byte aligned -> scalar kernel
+            std::vector<uint32_t> esc(2 * 64);
+            uint32_t n_esc = 0;
+            CHECK(lm_record_delta_pack(lon.data(), lat.data(), cl.data(), ca.data(), n, dl.data() + off, da.data() + off, esc.data(), 64, &n_esc, nullptr));
+            if (n_esc < 12 || n_esc > 64) { fprintf(stderr, "escapes %u\n", n_esc); return 4; }
+            std::vector<float> ol(n), oa(n);
+            CHECK(lm_record_delta_unpack_host(lon.data(), lat.data(), dl.data() + off, da.data() + off, esc.data(), n_esc, n, ol.data(), oa.data(), 2));
+            if (memcmp(ol.data(), cl.data(), 4 * n) || memcmp(oa.data(), ca.data(), 4 * n)) { fprintf(stderr, "delta record round trip\n"); return 4; }
+            uint32_t over = 0;
+            CHECK(lm_record_delta_pack(lon.data(), lat.data(), cl.data(), ca.data(), n, dl.data() + off, da.data() + off, esc.data(), 4, &over, nullptr));
+            if (over != n_esc) { fprintf(stderr, "overflow count %u vs %u\n", over, n_esc); return 4; }
+        }
+        printf("delta record: round trip exact\n");
+    }
     printf("done\n");
     return 0;
 }

@@ -1,4 +1,4 @@
-"""Developer tool, NOT part of the product or the test suite: runs the torch-side host layer (Engine, FusedSimulation,
+"""Developer tool, NOT part of the product (tests/test_host_layer_emulated.py runs it in a subprocess): runs the torch-side host layer (Engine, FusedSimulation,
 run_to_file and its record pipeline) against the CPU emulator of the kernels (tests/cuda_emu) when no GPU is at hand.
 torch.cuda is monkeypatched to the CPU inside this process only, and the script must be run with ``python -O`` so that the
 wrappers' ``is_cuda`` asserts are stripped:
