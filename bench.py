@@ -222,6 +222,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="microbes in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--packed-record", action="store_true",
+                    help="e2e (N = 1, experiment): positions leave as the lossless delta-packed record (DESIGN.md 4.7), "
+                         "stored packed -- not decoded inside the timed region")
     ap.add_argument("--resolve-upl", type=int, default=0, help="LM_OPT_RESOLVE_UPL (tuning experiments)")
     ap.add_argument("--no-overlap", action="store_true", help="LM_OPT_OVERLAP = 0 (tuning experiments)")
     ap.add_argument("--resolve-mode", type=int, default=0, choices=[0, 1],
@@ -388,8 +391,22 @@ def main():
             sim2.step()
         rec = [(torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(), torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(),
                 torch.empty(n_per_gpu, dtype=torch.int8).pin_memory()) if world == 1 else () for _ in range(2)]
+        packer = None
+        if args.packed_record:
+            assert world == 1, "--packed-record: single handle only"
+            from lagrangian_microbes_b200.record import DeltaRecordPacker
+            packer = DeltaRecordPacker(n_per_gpu)
+            lon_d = torch.empty(n_per_gpu, dtype=torch.float32, device="cuda"); lat_d = torch.empty_like(lon_d)
+
         def e2e_step(k):
-            if world == 1:
+            if packer is not None:
+                sim2.step()
+                if len(packer.pending) == 2:
+                    packer.pop(decode=False)       # the packed record of step k - 2 is in pinned memory
+                sim2.engine.state_get(lon_d, lat_d, None)
+                packer.push(lon_d, lat_d)
+                sim2.engine.state_get_host(None, None, rec[k & 1][2])
+            elif world == 1:
                 sim2.step(record=rec[k & 1])       # record scattered + copied under the step (lm_record_next_step)
             else:
                 sim2.step()
@@ -407,13 +424,22 @@ def main():
             e2e_step(k)
             h2d += sim2.h2d_bytes_last_step
         (sim2.ss if world > 1 else sim2.engine).host_copies_sync()
+        if packer is not None:
+            bytes0 = packer.bytes_d2h
+            while packer.pending:
+                last_packed = packer.pop(decode=False)
         e1.record()
         barrier()
         tw1 = time.perf_counter()
         ms_e2e = max(e0.elapsed_time(e1), 1e3 * (tw1 - tw0))     # device events and the host clock around the copies
         # N = 1: lon, lat, species in particle-id order (9 B); strips: ids travel with the record (13 B)
         e2e = {"ms": ms_e2e, "h2d": h2d / args.steps, "d2h": (9 if world == 1 else 13) * n_per_gpu}
-        if world == 1:
+        if packer is not None:
+            # every step after the first is a delta record: int16 lon + lat, the escape list, the counter, int8 species
+            e2e["d2h"] = 4 * n_per_gpu + 8 * packer.cap + 4 + n_per_gpu
+            e2e["record"] = "delta16 packed (lossless), stored packed: not decoded inside the timed region; last record: " + last_packed[0]
+            lon_chk = sim2.download()[0]
+        elif world == 1:
             lon_chk = rec[(args.steps - 1) & 1][0].numpy()
         else:
             lon_chk = sim2.ss._record["host"][1][sim2.k][:sim2.engine.state_size()].numpy()
@@ -481,6 +507,8 @@ def main():
     if e2e:
         line["e2e"] = {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": ms_e2e / args.steps}
+        if "record" in e2e:
+            line["e2e"]["record"] = e2e["record"]
     if world == 1 and not args.no_cpu_baseline:
         res = run_cpu_reference(args.workload, args.cpu_sample, 2, 1, args.modes)
         line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["threads"], "kind": "port",

@@ -100,22 +100,30 @@ class DeltaRecordPacker:
         self.pending.append((slot, "key"))
         self.bytes_d2h += 8 * self.n
 
-    def pop(self):
-        """The oldest pushed record as float32 numpy arrays (lon, lat), bit-exact."""
+    def pop(self, decode=True):
+        """The oldest pushed record as float32 numpy arrays (lon, lat), bit-exact.  ``decode=False`` hands out the record
+        as it crossed the link instead -- ("key", lon, lat) or ("delta", dlon, dlat, escapes), views of the pinned buffers,
+        valid until the second push from now -- for callers that store the packed stream and decode on read."""
         slot, kind = self.pending.pop(0)
         self.events[slot].synchronize()
+        if kind == "delta" and int(self.cnt_host[slot][0]) > self.cap:
+            self._key_frame(slot)                              # escape list overflowed: resend this step as a key frame
+            self.pending.pop()
+            torch.cuda.current_stream().synchronize()
+            kind = "key"
         if kind == "delta":
             m = int(self.cnt_host[slot][0])
-            if m > self.cap:                                   # escape list overflowed: resend this step as a key frame
-                self._key_frame(slot)
-                self.pending.pop()
-                torch.cuda.current_stream().synchronize()
-                kind = "key"
-            else:
-                esc = self.esc_host[slot].numpy()[:m].view(np.uint32)
-                lon, lat = unpack_delta_record_native(self.host_prev[0], self.host_prev[1], self.d_host[slot][0].numpy(),
-                                                      self.d_host[slot][1].numpy(), esc)
-        if kind == "key":
+            esc = self.esc_host[slot].numpy()[:m].view(np.uint32)
+            dlon, dlat = self.d_host[slot][0].numpy(), self.d_host[slot][1].numpy()
+            if not decode:
+                self.host_prev = None
+                return "delta", dlon, dlat, esc
+            assert self.host_prev is not None, "decode=True after decode=False: the previous record was not decoded"
+            lon, lat = unpack_delta_record_native(self.host_prev[0], self.host_prev[1], dlon, dlat, esc)
+        else:
+            if not decode:
+                self.host_prev = None
+                return "key", self.key_host[slot][0].numpy(), self.key_host[slot][1].numpy()
             lon, lat = self.key_host[slot][0].numpy().copy(), self.key_host[slot][1].numpy().copy()
         self.host_prev = (lon, lat)
         return lon, lat

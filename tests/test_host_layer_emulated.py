@@ -13,5 +13,5 @@ def test_host_layer_against_the_emulated_kernels():
     r = subprocess.run([sys.executable, "-O", os.path.join(ROOT, "tools", "host_layer_on_emulator.py")],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
-    for line in ("run_to_file ok:", "delta record stream ok:", "run_to_file(packed=True) ok:"):
+    for line in ("run_to_file ok:", "delta record stream ok:", "run_to_file(packed=True) ok:", "packed stream decoded on read ok"):
         assert line in r.stdout, r.stdout[-2000:]

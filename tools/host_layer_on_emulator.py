@@ -111,3 +111,18 @@ with tempfile.TemporaryDirectory() as d:
         assert np.array_equal(a2.view(np.uint32) if a2.dtype == np.float32 else a2, plain[k].view(np.uint32) if a2.dtype == np.float32 else plain[k]), k
     assert np.array_equal(counts2, counts)
     print("run_to_file(packed=True) ok: %d B of record over the link, plain %d" % (c.record_bytes_d2h, 9 * n_sim * data2["species"].shape[1]))
+
+# ---- DeltaRecordPacker.pop(decode=False): the packed stream as stored, decoded later (decode on read) -----------------
+packer = DeltaRecordPacker(n, escape_capacity=64, device=_dev)
+stored, truth = [], []
+for k in range(4):
+    cur_lon = (cur_lon + 0.02*(rng.random(n) - 0.5)).astype(np.float32); cur_lat = (cur_lat + 0.02*(rng.random(n) - 0.5)).astype(np.float32)
+    packer.push(torch.from_numpy(cur_lon.copy()).as_subclass(_FakeCudaTensor), torch.from_numpy(cur_lat.copy()).as_subclass(_FakeCudaTensor))
+    truth.append((cur_lon.copy(), cur_lat.copy()))
+    stored.append(tuple(np.array(x) if isinstance(x, np.ndarray) else x for x in packer.pop(decode=False)))
+assert [r[0] for r in stored] == ["key", "delta", "delta", "delta"]
+state = (stored[0][1], stored[0][2])
+for k in range(1, 4):
+    state = lmio.unpack_delta_record(state[0], state[1], *stored[k][1:])
+    assert np.array_equal(state[0].view(np.uint32), truth[k][0].view(np.uint32)) and np.array_equal(state[1].view(np.uint32), truth[k][1].view(np.uint32))
+print("packed stream decoded on read ok")

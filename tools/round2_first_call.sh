@@ -36,6 +36,7 @@ if grep -q "failed\|error" $O/pytest_analysis.log; then echo "analysis kernels N
 fi
 if grep -q "failed\|error" $O/pytest_record_delta.log; then echo "delta record NOT green: skipping its probe"; else
   timeout 120 python tools/record_pack_probe.py > $O/record_pack_probe.json 2> $O/record_pack_probe.err
+  timeout 600 python bench.py --no-cpu-baseline --packed-record > $O/bench_shard_packed_record.json 2> $O/bench_shard_packed_record.err
 fi
 # is the end-to-end number (9 B per microbe-step D2H) at the PCIe roofline of this box?
 timeout 120 python tools/pcie_bandwidth.py > $O/pcie_bandwidth.txt 2>&1
