@@ -17,4 +17,7 @@ Parity pins:
     2.0.0beta2 (environment.yml:80), which is neither vendored nor installable
     here and the reference has no test touching it.  ``oracle/rk4.py`` restates
     the published algorithm; it is anchored only by analytic known-answer tests.
+  * delta-packed record (``oracle/record.py``) -- PARITY UNPINNED by construction: the
+    format is this framework's own (the reference stores plain float32 columns);
+    its contract is the bit-exact round trip back to those columns.
 """

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY (never imported by the product): CPU restatement of the delta-packed position record of
 csrc/record.cu / lm_record_delta_pack.  The format is this framework's own (the reference stores plain float32 columns:
 /root/reference/particle_advecter.py:233-235, interaction_simulator.py:108-110), so there is no reference vector to pin
-it against; its contract is the round trip -- decoding must return the reference's float32 arrays bit for bit -- and
+it against (PARITY UNPINNED by construction); its contract is the round trip -- decoding must return the reference's float32 arrays bit for bit -- and
 this restatement states the encoding independently of both the kernel and the product's decoder (struct-based, one
 value at a time)."""
 import struct
