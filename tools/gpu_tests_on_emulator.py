@@ -4,7 +4,7 @@ torch-side wrappers.  Inside this process only, torch.cuda is monkeypatched to t
 subclass that reports is_cuda = True, so that Engine's argument checks hold.  Slow (minutes: the tests keep their GPU
 sizes); it found one bug in a test helper before any of this had seen hardware.
 
-    python tools/gpu_tests_on_emulator.py [analysis] [tiled-golden] [tiled-live] [tiled-knots] [tiled-fused]
+    python tools/gpu_tests_on_emulator.py [analysis] [tiled-golden] [tiled-live] [tiled-knots] [tiled-fused] [record] [record-sim]
 """
 import contextlib
 import ctypes
@@ -108,4 +108,19 @@ if any(w.startswith("tiled") for w in what):
         timed("tiled knots on the whole CTA (4 settings)", T.test_knots_on_the_whole_cta, factory)
     if "tiled-fused" in what:
         timed("tiled fused loop vs nine phases (12 steps)", T.test_fused_loop_equals_the_phase_launches)
+if "record" in what or "record-sim" in what:
+    class _Ev:
+        def __init__(self, *a, **k): pass
+        def record(self, *a): pass
+        def synchronize(self): pass
+    torch.cuda.Event = _Ev
+    _Stream.synchronize = lambda self: None
+    import test_gpu_zzz_record_delta as Rd
+    if "record" in what:
+        for n, off in ((0, 0), (5, 0), (4096, 0), (100003, 0), (100003, 1)):
+            timed("delta pack vs oracle n=%d offset=%d" % (n, off), Rd.test_delta_pack_against_the_oracle, n, off)
+    if "record-sim" in what:
+        timed("packed record stream of a stepping simulation", Rd.test_packed_record_stream_of_a_stepping_simulation_is_bit_exact)
+        with tempfile.TemporaryDirectory() as d:
+            timed("run_to_file packed = plain (stride 3)", Rd.test_run_to_file_packed_writes_the_same_file, pathlib.Path(d), 3)
 print("all requested GPU test bodies passed on the emulator")
