@@ -146,3 +146,36 @@ def test_delta_pack_rejects_bad_arguments(abi):
     assert abi.lm_record_delta_pack(P(a), P(a), P(a), P(a), 8, P(d), P(d), None, 4, P(c), None) == _lib.LM_EINVAL
     assert abi.lm_record_delta_pack(None, P(a), P(a), P(a), 8, P(d), P(d), P(e), 4, P(c), None) == _lib.LM_EINVAL
     assert abi.lm_record_delta_pack(P(a), P(a), P(a), P(a), 1 << 31, P(d), P(d), P(e), 4, P(c), None) == _lib.LM_EINVAL
+
+
+def test_round_trip_holds_for_arbitrary_bit_patterns(abi):
+    """Property: for ANY pair of float32 bit patterns (NaN payloads, subnormals, both signs) pack -> decode returns the
+    current record bit for bit, through the kernel (emulated) and both decoders; deltas agree with the oracle."""
+    from hypothesis import given, settings, strategies as st
+    from lagrangian_microbes_b200 import io as lmio
+
+    bits = st.integers(min_value=0, max_value=2 ** 32 - 1)
+    near = st.integers(min_value=-40000, max_value=40000)        # straddles the int16 limit
+
+    @settings(max_examples=60, deadline=None)
+    @given(st.lists(st.tuples(bits, bits, near, bits), min_size=1, max_size=40))
+    def check(rows):
+        prev_lon = np.array([r[0] for r in rows], dtype=np.uint32).view(np.float32)
+        lon = np.array([r[1] for r in rows], dtype=np.uint32).view(np.float32)
+        prev_lat = np.array([r[3] for r in rows], dtype=np.uint32).view(np.float32)
+        # latitude: a neighbour of prev_lat in key space, clipped to the key range
+        k = np.clip(lmio._mono_key(prev_lat) + np.array([r[2] for r in rows], dtype=np.int64), 0, 2 ** 32 - 1)
+        lat = lmio._from_mono_key(k)
+        n = len(rows)
+        dlon, dlat, esc, m = _run(abi, prev_lon, prev_lat, lon, lat, cap=2 * n)
+        w_dlon, w_dlat, w_esc = orec.pack_reference(prev_lon, prev_lat, lon, lat)
+        assert np.array_equal(dlon, w_dlon) and np.array_equal(dlat, w_dlat) and sorted(map(tuple, esc[:m].tolist())) == w_esc
+        a = lmio.unpack_delta_record(prev_lon, prev_lat, dlon, dlat, esc[:m])
+        out = (np.empty(n, np.float32), np.empty(n, np.float32))
+        e = np.ascontiguousarray(esc[:m])
+        assert abi.lm_record_delta_unpack_host(_ptr(prev_lon), _ptr(prev_lat), _ptr(dlon), _ptr(dlat), _ptr(e), m, n,
+                                               _ptr(out[0]), _ptr(out[1]), 1) == 0
+        for got in (a, out):
+            assert np.array_equal(got[0].view(np.uint32), lon.view(np.uint32)) and np.array_equal(got[1].view(np.uint32), lat.view(np.uint32))
+
+    check()
