@@ -420,12 +420,12 @@ def main():
         tw0 = time.perf_counter()
         e0.record()
         h2d = 0
+        packed_bytes0 = packer.bytes_d2h if packer is not None else 0
         for k in range(args.steps):
             e2e_step(k)
             h2d += sim2.h2d_bytes_last_step
         (sim2.ss if world > 1 else sim2.engine).host_copies_sync()
         if packer is not None:
-            bytes0 = packer.bytes_d2h
             while packer.pending:
                 last_packed = packer.pop(decode=False)
         e1.record()
@@ -435,8 +435,9 @@ def main():
         # N = 1: lon, lat, species in particle-id order (9 B); strips: ids travel with the record (13 B)
         e2e = {"ms": ms_e2e, "h2d": h2d / args.steps, "d2h": (9 if world == 1 else 13) * n_per_gpu}
         if packer is not None:
-            # every step after the first is a delta record: int16 lon + lat, the escape list, the counter, int8 species
-            e2e["d2h"] = 4 * n_per_gpu + 8 * packer.cap + 4 + n_per_gpu
+            # counted from the copies issued: int16 lon + lat, the escape list and its counter (or a plain key frame
+            # when the list overflowed), plus int8 species
+            e2e["d2h"] = (packer.bytes_d2h - packed_bytes0) / args.steps + n_per_gpu
             e2e["record"] = "delta16 packed (lossless), stored packed: not decoded inside the timed region; last record: " + last_packed[0]
             lon_chk = sim2.download()[0]
         elif world == 1:
