@@ -265,6 +265,12 @@ int lm_reset_stats(lm_handle h, void *stream);
 /*   LM_OPT_RESOLVE_TILE_SHAPE  tiled resolver: cells per tile, 0 = 64 x 16 (default), 1 = 32 x 16, 2 = 128 x 16,
  *                   3 = 64 x 32 (the halo is 6 columns / 2 rows in every case).  Same results; for A/B measurements. */
 #define LM_OPT_RESOLVE_TILE_SHAPE 11
+/*   LM_OPT_ADVECT_MODE  RK4 step (replaces pset.execute(AdvectionRK4), particle_advecter.py:222-223):
+ *                   0 (default) bit-faithful to the float32 restatement of Parcels' JIT kernel (oracle/rk4.py);
+ *                   1 the same step in float32 FMA arithmetic with MUFU reciprocal / cosine: positions within 1e-6
+ *                   relative of the float64 RK4 (north_star's tolerance; tests/test_gpu_advect_fast.py), ~4x fewer
+ *                   instructions.  The stored state is float32 in both modes. */
+#define LM_OPT_ADVECT_MODE 12
 int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Make `stream` wait for work of the last lm_step that is still running on the handle's internal stream
  * (LM_OPT_OVERLAP).  Only needed before the caller reads the resident arrays through pointers obtained earlier,

@@ -24,6 +24,8 @@ LM_STEP_TIMING = 32
 LM_OPT_FIND_PATH, LM_OPT_RESOLVE_UPL, LM_OPT_OVERLAP, LM_OPT_NORM = 2, 3, 4, 5
 LM_OPT_RESOLVE_HEAVY_MIN, LM_OPT_RESOLVE_BATCH = 6, 7
 LM_OPT_RESOLVE_MODE, LM_OPT_RESOLVE_TILE_SMEM, LM_OPT_RESOLVE_MEGA_MIN, LM_OPT_RESOLVE_TILE_SHAPE = 8, 9, 10, 11
+LM_OPT_ADVECT_MODE = 12
+LM_ADVECT_FAITHFUL, LM_ADVECT_FAST = 0, 1
 LM_NORM_INF, LM_NORM_1, LM_NORM_2 = 0, 1, 2
 LM_PDH_MAX_BINS = 126
 LM_FRAME_LAST_DRAWN, LM_FRAME_PLURALITY = 0, 1

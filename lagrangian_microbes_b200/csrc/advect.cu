@@ -140,8 +140,71 @@ __global__ void __launch_bounds__(256) advect_rk4_kernel(FieldDev f, float *__re
     lat[p] = __double2float_rn(__dadd_rn(yd, __dmul_rn(__ddiv_rn((double)sv, 6.0), dtd)));
 }
 
+// ---- LM_OPT_ADVECT_MODE = 1: the same RK4 step in float32 arithmetic -------------------------------------------
+// north_star's bar for positions is 1e-6 relative to the reference RK4; the particle state is float32 (half an ulp at
+// 200 degrees is 3.8e-8 relative), a step moves a microbe ~0.01 degrees, so a float32 evaluation of the DISPLACEMENT
+// (relative error ~1e-6 of 0.01 degrees = 1e-8 degrees) is three orders of magnitude below the rounding of the stored
+// position itself.  What the bit-faithful kernel above pays for -- 10 fp64 divisions, 4 fp64 cosines and 64 fp64
+// bilinear terms per microbe, all on explicit-rounding intrinsics -- buys bit-identity with an x86 evaluation order,
+// not accuracy.  Here: FMA bilinear sums, MUFU reciprocal / cosine (|error| of __cosf on [-pi/2, pi/2] is 2^-21.4
+// absolute), the same index search, the same out-of-bounds policy.  tests/test_gpu_advect_fast.py holds it to 1e-6
+// relative against the float64 restatement, step by step from identical inputs and over config 1's 24 steps.
+__device__ __forceinline__ bool sample_uv_fast(const FieldDev &f, float x, float y, int ti, int interp, float frac,
+                                               float &u, float &v)
+{
+    float lx0, lx1, ly0, ly1;
+    const int xi = search_axis(f.lon, f.X, x, f.lon0, f.lon1, f.inv_dx, lx0, lx1);
+    const int yi = search_axis(f.lat, f.Y, y, f.lat0, f.lat1, f.inv_dy, ly0, ly1);
+    if (xi < 0 || yi < 0) return false;
+    const float xsi = __fdividef(x - lx0, lx1 - lx0), eta = __fdividef(y - ly0, ly1 - ly0);
+    const float omx = 1.f - xsi, ome = 1.f - eta;
+    const float w00 = omx * ome, w01 = xsi * ome, w11 = xsi * eta, w10 = omx * eta;
+    const size_t slab = (size_t)f.Y * f.X;
+    const size_t off = (size_t)ti * slab + (size_t)yi * f.X + xi;
+    const float *__restrict__ pu = f.U + off, *__restrict__ pv = f.V + off;
+    // all loads of the sample first (16 with time interpolation): one exposed latency instead of four
+    const float u00 = __ldg(pu), u01 = __ldg(pu + 1), u10 = __ldg(pu + f.X), u11 = __ldg(pu + f.X + 1);
+    const float v00 = __ldg(pv), v01 = __ldg(pv + 1), v10 = __ldg(pv + f.X), v11 = __ldg(pv + f.X + 1);
+    float uu = fmaf(w10, u10, fmaf(w11, u11, fmaf(w01, u01, w00 * u00)));
+    float vv = fmaf(w10, v10, fmaf(w11, v11, fmaf(w01, v01, w00 * v00)));
+    if (interp) {
+        const float *__restrict__ qu = pu + slab, *__restrict__ qv = pv + slab;
+        const float a00 = __ldg(qu), a01 = __ldg(qu + 1), a10 = __ldg(qu + f.X), a11 = __ldg(qu + f.X + 1);
+        const float b00 = __ldg(qv), b01 = __ldg(qv + 1), b10 = __ldg(qv + f.X), b11 = __ldg(qv + f.X + 1);
+        const float u1 = fmaf(w10, a10, fmaf(w11, a11, fmaf(w01, a01, w00 * a00)));
+        const float v1 = fmaf(w10, b10, fmaf(w11, b11, fmaf(w01, b01, w00 * b00)));
+        uu = fmaf(u1 - uu, frac, uu);
+        vv = fmaf(v1 - vv, frac, vv);
+    }
+    constexpr float inv_m_per_deg = (float)(1.0 / 111120.0);
+    u = uu * __fdividef(inv_m_per_deg, __cosf(y * 0.017453292519943295f));
+    v = vv * inv_m_per_deg;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) advect_rk4_fast_kernel(FieldDev f, float *__restrict__ lon, float *__restrict__ lat,
+                                                              int n, StageDev st, float dt, Counters *ctr)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float x = lon[p], y = lat[p];
+    const float h = 0.5f * dt;
+    float u1, v1, u2, v2, u3, v3, u4, v4;
+    bool ok = sample_uv_fast(f, x, y, st.ti[0], st.interp[0], st.frac[0], u1, v1);
+    if (ok) ok = sample_uv_fast(f, fmaf(u1, h, x), fmaf(v1, h, y), st.ti[1], st.interp[1], st.frac[1], u2, v2);
+    if (ok) ok = sample_uv_fast(f, fmaf(u2, h, x), fmaf(v2, h, y), st.ti[2], st.interp[2], st.frac[2], u3, v3);
+    if (ok) ok = sample_uv_fast(f, fmaf(u3, dt, x), fmaf(v3, dt, y), st.ti[3], st.interp[3], st.frac[3], u4, v4);
+    if (!ok) {   // same policy as the bit-faithful kernel: the particle stays where it is and is counted
+        atomicAdd(&ctr->n_oob, 1ull);
+        return;
+    }
+    const float sixth = dt * (1.f / 6.f);
+    lon[p] = fmaf(u1 + 2.f * (u2 + u3) + u4, sixth, x);
+    lat[p] = fmaf(v1 + 2.f * (v2 + v3) + v4, sixth, y);
+}
+
 cudaError_t launch_advect(const FieldDev &f, float *lon, float *lat, int n, const lm_stage_times &st, float dt,
-                          Counters *ctr, cudaStream_t s, int64_t *launches)
+                          Counters *ctr, cudaStream_t s, int64_t *launches, int mode)
 {
     if (n <= 0) return cudaSuccess;
     StageDev sd;
@@ -151,7 +214,8 @@ cudaError_t launch_advect(const FieldDev &f, float *lon, float *lat, int n, cons
         sd.frac[k] = st.frac[k];
     }
     const int block = 256;
-    advect_rk4_kernel<<<(n + block - 1) / block, block, 0, s>>>(f, lon, lat, n, sd, dt, ctr);
+    if (mode == 1) advect_rk4_fast_kernel<<<(n + block - 1) / block, block, 0, s>>>(f, lon, lat, n, sd, dt, ctr);
+    else advect_rk4_kernel<<<(n + block - 1) / block, block, 0, s>>>(f, lon, lat, n, sd, dt, ctr);
     ++*launches;
     return cudaGetLastError();
 }

@@ -122,6 +122,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     h->cell_start = h->cell_start_buf[0];
     h->overlap = 1;
     h->norm = LM_NORM_2;
+    h->advect_mode = 0;
     h->resolve_tile_smem = 32768;
     h->resolve_batch = 4;      // measured on B200 (profiles/r1y_sweep_resolve.jsonl): 4 beats 1 and 8 on every workload
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
@@ -311,7 +312,7 @@ int lm_advect_rk4(lm_handle h, float *lon, float *lat, int64_t n, const lm_stage
         if (st->ti[k] < 0 || st->ti[k] + (st->interp[k] ? 1 : 0) >= h->field.T) return LM_EINVAL;
     LM_CUDA(cudaSetDevice(h->device));
     // n_out_of_bounds accumulates over calls until lm_reset_stats
-    LM_CUDA(launch_advect(h->field, lon, lat, (int)n, *st, dt, h->ctr, as_stream(stream), &h->launches));
+    LM_CUDA(launch_advect(h->field, lon, lat, (int)n, *st, dt, h->ctr, as_stream(stream), &h->launches, h->advect_mode));
     return LM_OK;
 }
 
@@ -479,7 +480,7 @@ int lm_step_move(lm_handle h, int32_t flags, const lm_stage_times *st, float dt,
         moved = true;
     }
     if (flags & LM_STEP_ADVECT) {
-        LM_CUDA(launch_advect(h->field, h->lon[c], h->lat[c], n, *st, dt, h->ctr, s, &h->launches));
+        LM_CUDA(launch_advect(h->field, h->lon[c], h->lat[c], n, *st, dt, h->ctr, s, &h->launches, h->advect_mode));
         moved = true;
     }
     if (timing) LM_CUDA(cudaEventRecord(h->ev_phase[1], s));
@@ -845,6 +846,10 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
             h->resolve_mode = (int)value;
             return LM_OK;
         }
+        case LM_OPT_ADVECT_MODE:
+            if (value < 0 || value > 1) return LM_EINVAL;
+            h->advect_mode = (int)value;
+            return LM_OK;
         case LM_OPT_RESOLVE_TILE_SHAPE:
             if (value < 0 || value > 3) return LM_EINVAL;
             h->resolve_tile_shape = (int)value;

@@ -92,6 +92,7 @@ struct lm_handle_s {
     int find_path;         // LM_OPT_FIND_PATH: 0 auto | 1 every warp takes the two-pass (dense cluster) path
     int resolve_heavy_min; // LM_OPT_RESOLVE_HEAVY_MIN: 0 = default (160)
     int resolve_batch;     // LM_OPT_RESOLVE_BATCH: pairs per lane and iteration in the resolver's stream walk (1, 4, 8)
+    int advect_mode;       // LM_OPT_ADVECT_MODE: 0 bit-faithful to the float32 restatement of Parcels' kernel | 1 float32 arithmetic
     int norm;              // LM_OPT_NORM: LM_NORM_2 (default) | LM_NORM_1 | LM_NORM_INF
     // tiled resolver (LM_OPT_RESOLVE_MODE = 1; csrc/pairs.cu): allocated when the mode is first switched on
     int resolve_mode;      // 0: nine phase launches (default) | 1: one tiled launch per phase range
@@ -146,7 +147,7 @@ namespace lm {
 
 // ---- launchers (each returns cudaGetLastError() of its launches) --------------------------------
 cudaError_t launch_advect(const FieldDev &f, float *lon, float *lat, int n, const lm_stage_times &st, float dt,
-                          Counters *ctr, cudaStream_t s, int64_t *launches);
+                          Counters *ctr, cudaStream_t s, int64_t *launches, int mode = 0);
 cudaError_t launch_diffuse(float *lon, float *lat, const int32_t *ids, int n, double amp, uint64_t seed, uint64_t step,
                            cudaStream_t s, int64_t *launches);
 // bins (lon,lat,sp,id)[src] into (cell,id) order in dst; sp / id may be null (id -> source index)

@@ -15,10 +15,8 @@ from oracle import analysis as oa
 
 # (File name: sorts after every verified GPU test, so that a fault in a kernel that has never run cannot poison the
 # CUDA context of the tests before it.)
-# These kernels were written after the round's GPU budget had been spent: until their first run on hardware the tests
-# are expected-to-fail-allowed (an XPASS in the log means parity is green; the marker goes away then).
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (written after round 1's GPU budget was spent)")]
+# First run on hardware: the round-1 driver run (GPUTEST_r01.json), all green.
+pytestmark = pytest.mark.gpu
 
 
 def _cloud(kind, n, seed):

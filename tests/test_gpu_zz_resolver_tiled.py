@@ -14,10 +14,8 @@ from oracle import rps as orps
 
 # (File name: sorts after every verified GPU test, so that a fault in a kernel that has never run cannot poison the
 # CUDA context of the tests before it.)
-# Written after round 1's GPU budget had been spent: expected-to-fail-allowed until the first hardware run
-# (XPASS in the log = parity green; the marker goes away then).  The mode is off by default.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (written after round 1's GPU budget was spent)")]
+# First run on hardware: the round-1 driver run (GPUTEST_r01.json), all green.
+pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 

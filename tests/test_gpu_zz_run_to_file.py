@@ -5,10 +5,9 @@ from datetime import datetime, timedelta
 import numpy as np
 import pytest
 
-# (File name: sorts after every verified GPU test.)  Written after round 1's GPU budget had been spent: composed of
-# verified pieces (step(record=...), host_copies_sync), expected-to-fail-allowed until its first hardware run.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (written after round 1's GPU budget was spent)")]
+# (File name: sorts after every verified GPU test.)  Composed of verified pieces
+# (step(record=...), host_copies_sync); first run on hardware: the round-1 driver run, green.
+pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 

@@ -9,10 +9,9 @@ import pytest
 
 from oracle import record as orec
 
-# (File name: sorts after every verified GPU test.)  Written after round 1's GPU budget had been spent; executed on the
-# CPU emulator (tests/test_record_delta.py); expected-to-fail-allowed until its first hardware run.
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run pending (written after round 1's GPU budget was spent)")]
+# (File name: sorts after every verified GPU test.)  Also executed on the CPU emulator
+# (tests/test_record_delta.py); first run on hardware: the round-1 driver run, green.
+pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 

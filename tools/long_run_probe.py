@@ -8,12 +8,17 @@ hfs = bench.make_fieldset(64)
 n = bench.default_n(workload)
 lon, lat, sp, _ = bench.workload_particles(workload, n, 0, 1)
 sim = FusedSimulation(lon, lat, sp, 0.01, 0.55, 0.55, 0.55, hfs, dt_seconds=3600.0, seed=0, emit_pairs=True,
-                      pair_capacity=(20 if workload == "config3" else 8) * n, regrid_every=16, grid_margin=0.5)
+                      pair_capacity=(20 if workload == "config3" else 64 if workload == "config2" else 8) * n, regrid_every=16, grid_margin=0.5)
 import os
 if os.environ.get('LM_RESOLVE_UPL'):
     from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_UPL
     sim.engine.set_option(LM_OPT_RESOLVE_UPL, int(os.environ['LM_RESOLVE_UPL']))
+if os.environ.get('LM_RESOLVE_MODE'):
+    from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_MODE
+    sim.engine.set_option(LM_OPT_RESOLVE_MODE, int(os.environ['LM_RESOLVE_MODE']))
 done = 0
+import time
+t_wall = time.time()
 while done < total:
     for _ in range(every - 1):
         sim.step()
@@ -22,7 +27,7 @@ while done < total:
     st = sim.stats()
     done += every
     lo, la, _ = (None, None, None)
-    print(json.dumps({"step": done, "pairs": int(st.n_pairs), "rho": st.n_pairs / n, "phases_ms": [round(x, 3) for x in ph],
+    print(json.dumps({"step": done, "wall_s": round(time.time() - t_wall, 2), "pairs": int(st.n_pairs), "rho": st.n_pairs / n, "phases_ms": [round(x, 3) for x in ph],
                       "species": list(st.species_count)[1:]}), flush=True)
 # occupancy of the cell grid at the end
 g = sim.grid

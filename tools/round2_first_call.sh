@@ -20,7 +20,12 @@ timeout 600 python -m pytest tests/test_gpu_zz_analysis.py -m gpu -rxX -v --runx
 timeout 600 python -m pytest tests/test_gpu_zz_run_to_file.py -m gpu -rxX -v --runxfail > $O/pytest_run_to_file.log 2>&1
 timeout 300 python -m pytest tests/test_gpu_zzz_record_delta.py -m gpu -rxX -v --runxfail > $O/pytest_record_delta.log 2>&1
 tail -3 $O/pytest_verified.log $O/pytest_tiled.log $O/pytest_analysis.log $O/pytest_run_to_file.log $O/pytest_record_delta.log
+# pinned-memory PCIe bandwidth of the box (what bounds the end-to-end number)
+timeout 120 python tools/pcie_bandwidth.py > $O/pcie_bandwidth.txt 2>&1
+# BASELINE config 2 to its full length (7,670 hourly steps), nine-phase resolver: where does the step time go?
+LM_RESOLVE_MODE=0 timeout 300 python tools/long_run_probe.py config2 7670 590 > $O/config2_full_mode0.jsonl 2> $O/config2_full_mode0.err
 if grep -q "failed\|error" $O/pytest_tiled.log; then echo "tiled resolver NOT green: skipping its measurements"; else
+  LM_RESOLVE_MODE=1 timeout 300 python tools/long_run_probe.py config2 7670 590 > $O/config2_full_mode1.jsonl 2> $O/config2_full_mode1.err
   timeout 900 python tools/tiled_sweep.py config2:1500:200 shard:0:20 shard:1000:20 config3:0:10 config3:400:10 > $O/tiled_sweep.jsonl 2> $O/tiled_sweep.err
   for w in shard config2 config3; do
     timeout 600 python bench.py --workload $w --no-cpu-baseline --resolve-mode 1 > $O/bench_${w}_tiled.json 2> $O/bench_${w}_tiled.err
@@ -38,6 +43,4 @@ if grep -q "failed\|error" $O/pytest_record_delta.log; then echo "delta record N
   timeout 120 python tools/record_pack_probe.py > $O/record_pack_probe.json 2> $O/record_pack_probe.err
   timeout 600 python bench.py --no-cpu-baseline --packed-record > $O/bench_shard_packed_record.json 2> $O/bench_shard_packed_record.err
 fi
-# is the end-to-end number (9 B per microbe-step D2H) at the PCIe roofline of this box?
-timeout 120 python tools/pcie_bandwidth.py > $O/pcie_bandwidth.txt 2>&1
 ls -la $O
