@@ -271,6 +271,24 @@ int lm_reset_stats(lm_handle h, void *stream);
  *                   relative of the float64 RK4 (north_star's tolerance; tests/test_gpu_advect_fast.py), ~4x fewer
  *                   instructions.  The stored state is float32 in both modes. */
 #define LM_OPT_ADVECT_MODE 12
+/*   LM_OPT_INTERACT_MODE  pair search + RPS resolution (replaces query_pairs + the pair loop,
+ *                   interaction_simulator.py:93-105):
+ *                   1 (default) ONE fused pass per tile of LM_TILE_W x LM_TILE_H cells in shared memory, pairs resolved
+ *                     in the tile-round order (rounds of matchings; csrc/interact.cu, oracle/rps.py::tile_round_order);
+ *                   0 the round-1 pipeline: pair search -> hand-off -> nine phase launches in the cell-phase order
+ *                     (csrc/pairs.cu, oracle/rps.py::cell_phase_order).  Same pair set; the species differ because the
+ *                     (arbitrary but fixed) sequential order differs -- each is exact against the reference rule run in
+ *                     its own order.
+ *   LM_OPT_DRAW_BATCH  fused pass: lanes waiting for a Philox draw that make their warp run the draws (0 = default 20)
+ *   LM_OPT_TILE_CAP    fused pass: microbes a tile stages in shared memory (0 = 1.5 x the mean tile occupancy); fuller
+ *                     tiles work on the global arrays through the same code */
+#define LM_OPT_INTERACT_MODE 13
+#define LM_OPT_DRAW_BATCH 14
+#define LM_OPT_TILE_CAP 15
+/* tile of the fused interaction pass, in cells: part of the definition of its canonical pair order.  Strip boundaries
+ * (lm_set_strip) must sit on multiples of LM_TILE_H rows in this mode. */
+#define LM_TILE_W 32
+#define LM_TILE_H 16
 int lm_set_option(lm_handle h, int32_t option, int64_t value);
 /* Make `stream` wait for work of the last lm_step that is still running on the handle's internal stream
  * (LM_OPT_OVERLAP).  Only needed before the caller reads the resident arrays through pointers obtained earlier,

@@ -12,7 +12,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 _SO = os.path.join(_HERE, "liblm_b200.so")
-_SOURCES = ["api.cu", "advect.cu", "bin.cu", "strip.cu", "pairs.cu", "resolve.cu", "analysis.cu", "record.cu"]
+_SOURCES = ["api.cu", "advect.cu", "bin.cu", "strip.cu", "pairs.cu", "interact.cu", "resolve.cu", "analysis.cu", "record.cu"]
 _HEADERS = ["lm_internal.cuh", "philox.cuh", os.path.join("..", "..", "include", "lm_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -25,6 +25,8 @@ LM_OPT_FIND_PATH, LM_OPT_RESOLVE_UPL, LM_OPT_OVERLAP, LM_OPT_NORM = 2, 3, 4, 5
 LM_OPT_RESOLVE_HEAVY_MIN, LM_OPT_RESOLVE_BATCH = 6, 7
 LM_OPT_RESOLVE_MODE, LM_OPT_RESOLVE_TILE_SMEM, LM_OPT_RESOLVE_MEGA_MIN, LM_OPT_RESOLVE_TILE_SHAPE = 8, 9, 10, 11
 LM_OPT_ADVECT_MODE = 12
+LM_OPT_INTERACT_MODE, LM_OPT_DRAW_BATCH, LM_OPT_TILE_CAP = 13, 14, 15
+LM_TILE_W, LM_TILE_H = 32, 16
 LM_ADVECT_FAITHFUL, LM_ADVECT_FAST = 0, 1
 LM_NORM_INF, LM_NORM_1, LM_NORM_2 = 0, 1, 2
 LM_PDH_MAX_BINS = 126

@@ -123,6 +123,9 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     h->overlap = 1;
     h->norm = LM_NORM_2;
     h->advect_mode = 0;
+    h->interact_mode = 1;
+    h->draw_batch = 0;
+    h->tile_cap = 0;
     h->resolve_tile_smem = 32768;
     h->resolve_batch = 4;      // measured on B200 (profiles/r1y_sweep_resolve.jsonl): 4 beats 1 and 8 on every workload
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
@@ -587,7 +590,7 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
         // Species never feed back into advection, so on a single handle the nine RPS phases -- latency
         // bound, half-empty warps -- go to a side stream and run under the issue-bound advection of the NEXT step;
         // whatever touches species, the hand-off or the state next waits for them (join_side).
-        h->resolve_on_side = h->overlap && !in_strip_mode(h) && !(h->step_flags & (LM_STEP_TIMING | LM_STEP_STATS)) && n > 0;
+        h->resolve_on_side = h->overlap && h->interact_mode == 0 && !in_strip_mode(h) && !(h->step_flags & (LM_STEP_TIMING | LM_STEP_STATS)) && n > 0;
         cudaStream_t rs = s;
         if (h->resolve_on_side) {
             LM_CUDA(cudaEventRecord(h->ev_find_done, s));
@@ -595,7 +598,7 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
             rs = h->side_stream;
         }
         // the tiled resolver takes all nine phases in one launch when no halo exchange has to happen after phase 5
-        h->resolve_all_in_begin = h->resolve_mode == 1 && !in_strip_mode(h);
+        h->resolve_all_in_begin = h->interact_mode == 0 && h->resolve_mode == 1 && !in_strip_mode(h);
         if (n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 0, h->resolve_all_in_begin ? 8 : 5, rs));
     }
     if (h->has_south && interact) LM_CUDA(launch_row0_species_pack(h, h->sp[c], s));
@@ -846,6 +849,19 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
             h->resolve_mode = (int)value;
             return LM_OK;
         }
+        case LM_OPT_INTERACT_MODE:
+            if (value < 0 || value > 1) return LM_EINVAL;
+            if (h->stage != 0) return LM_ESTATE;                 // not between the stages of a step
+            h->interact_mode = (int)value;
+            return LM_OK;
+        case LM_OPT_DRAW_BATCH:
+            if (value < 0 || value > 32) return LM_EINVAL;
+            h->draw_batch = (int)value;
+            return LM_OK;
+        case LM_OPT_TILE_CAP:
+            if (value < 0 || value > 16384) return LM_EINVAL;
+            h->tile_cap = (int)value;
+            return LM_OK;
         case LM_OPT_ADVECT_MODE:
             if (value < 0 || value > 1) return LM_EINVAL;
             h->advect_mode = (int)value;

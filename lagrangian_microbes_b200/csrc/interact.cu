@@ -1,0 +1,602 @@
+// Fused radius pair search + rock-paper-scissors resolution on the binned particle arrays: ONE pass, no hand-off.
+//
+// Replaces  kdt.query_pairs(r=interaction_radius, p=interaction_norm)   (interaction_simulator.py:93-98)
+// and       for pair in microbe_pairs: pair_interaction(...)            (interaction_simulator.py:104-105)
+//           -> rock_paper_scissors_interaction                          (interactions.py:13-40)
+//
+// Why this replaces the round-1 pipeline (find_pairs_kernel -> hits[] / rec[] hand-off -> nine resolve_phase launches,
+// csrc/pairs.cu, still selectable as LM_OPT_INTERACT_MODE = 0): that pipeline wrote 2.5x its algorithmic bytes to hand
+// every pair from the search to the resolver, paid a full Philox draw for every pair whether or not the rule consumes
+// it, and resolved a unit's pairs strictly one after the other in (id_a, id_b) order -- so the several-hundred-microbe
+// cells a long run collects serialised 10^4..10^5 pairs on one warp (BASELINE config 2 past step 2,000: 2.4 ms of a
+// 5 ms step; profiles/r2a_config2_full_mode0.jsonl).  The tiled variant of that resolver lost 2-2.7x on hardware
+// (profiles/r2a_tiled_sweep.jsonl).  Here the sequential order itself is chosen so that it parallelises:
+//
+// CANONICAL ORDER ("tile-round order", oracle/rps.py::tile_round_order).  Cells are grouped into tiles of 32 x 16
+// cells.  A unit is one cell or two adjacent cells (half stencil E, NW, N, NE).  Phases 0-8: the units inside one tile
+// (same cell | east, cx even / odd | NW, N, NE, cy even | the same, cy odd); phases 9-14: the units across a tile
+// boundary (east | NW, NE across a vertical boundary | NW, N, NE across a horizontal one).  Units of one phase touch
+// disjoint microbes.  Inside a unit the pairs are taken in ROUNDS OF MATCHINGS: two cells with m_a, m_b microbes
+// ranked by id, M = max(m_a, m_b): round k pairs rank i with rank (i + k) mod M; one cell: the circle method of
+// round-robin tournaments.  No microbe occurs twice in a round, so a round is order-free: a cell of 600 microbes is
+// 600 rounds of 300 independent pairs instead of 180,000 sequential ones.  The result is by construction the
+// reference's sequential in-place loop run in that total order (checked against the unmodified reference function).
+//
+// KERNELS.  interact_tile_kernel: one CTA per tile.  The tile's microbes (positions, ids, species: 13 B each) are
+// staged in shared memory (a tile that does not fit works on the global arrays through the same code), then phase
+// after phase with __syncthreads() in between: every lane walks the slots of its units -- distance test, pair
+// emission, species compare -- and the Philox draw, needed only when the two species differ at that moment
+// (interactions.py:17-20), is taken OUT of the walk: a lane that needs one parks, and the warp runs the ten Philox
+// rounds when enough lanes are parked, so the draw costs its ~100 instructions at a useful lane occupancy instead of
+// once per slot.  Units above 255 slots go to a queue and are resolved round by round by a whole warp, above 8,192 by
+// the whole CTA.  interact_cross_kernel: the same walk for the units of one boundary phase, from global memory
+// (a few per cent of the pairs).  Pairs are staged per CTA and flushed in blocks (one atomic per flush).
+//
+// Predicate: exactly SciPy's (float32 positions widened to double, s = fl(dx*dx); s = fl(s + fl(dy*dy)); s <= fl(r*r));
+// a float32 evaluation decides everything farther than 4e-6 (relative) from the threshold.  p = 1 / inf likewise.
+#include <algorithm>
+
+#include "lm_internal.cuh"
+#include "philox.cuh"
+
+namespace lm {
+namespace {
+
+constexpr int IT_TW = LM_TILE_W, IT_TH = LM_TILE_H;
+constexpr int IT_THREADS = 256;
+constexpr int IT_WARPS = IT_THREADS / 32;
+constexpr int IT_CELLS = IT_TW * IT_TH;
+constexpr int IT_UPT = IT_CELLS / IT_THREADS;            // cells a thread looks at when the units of a phase are listed
+constexpr int IT_STAGE = 1024;                            // pairs staged per CTA between flushes
+constexpr unsigned int IT_LIGHT_MAX = 255;                // slots of a unit that one lane walks alone
+constexpr unsigned int IT_MEGA_MIN = 8192;                // slots from which the whole CTA takes a unit
+constexpr unsigned int FULL = 0xffffffffu;
+static_assert(IT_TW == 32 && IT_TH % 2 == 0 && IT_CELLS % IT_THREADS == 0, "tile geometry");
+
+struct IArgs {
+    const float *__restrict__ lon;
+    const float *__restrict__ lat;
+    const int32_t *__restrict__ id;
+    int8_t *sp;                          // null: pair search only
+    const int32_t *__restrict__ cell_start;
+    int ncx, rows_owned, rows_local;     // strip-local rows (single GPU: ncy, ncy)
+    int tiles_x, tiles_y;
+    int norm;
+    float r2_lo, r2_hi;                  // float32 pre-filter window around the threshold
+    double r2;                           // the exact threshold (r*r for p = 2, r for p = 1 and p = inf)
+    uint32_t seed_lo, seed_hi, step_lo, step_hi;
+    unsigned long long thr[3];           // ceil(p * 2^53) for pRS, pPR, pSP
+    int2 *__restrict__ pairs;            // null: count only
+    unsigned long long cap_pairs;
+    Counters *ctr;
+    int tile_cap;                        // microbes a tile can stage in shared memory
+    int draw_batch;                      // parked lanes that trigger the warp's Philox rounds
+    int phase;                           // interact_cross_kernel: 9..14
+};
+
+// ---- the rule (interactions.py:13-40) for species s1 != s2, both in {1,2,3}: the species both end up with --------
+__device__ __forceinline__ int rps_apply(int s1, int s2, uint32_t dec)
+{
+    int d = s1 - s2;
+    if (d < 0) d += 3;
+    const int w = (d == 1) ? s1 : s2, l = (d == 1) ? s2 : s1;    // w: the forward winner (R > S, P > R, S > P)
+    return ((dec >> (w - 1)) & 1u) ? w : l;
+}
+__device__ __forceinline__ bool is_rps(int s) { return s >= 1 && s <= 3; }
+
+// three decision bits of the pair's draw: bit k set <=> u < p_k  (k = 0: pRS, 1: pPR, 2: pSP); u = m * 2^-53
+__device__ __forceinline__ uint32_t decision_bits(const IArgs &A, int i, int j)
+{
+    uint32_t x[4];
+    philox4x32_10((uint32_t)i, (uint32_t)j, A.step_lo, A.step_hi, A.seed_lo, A.seed_hi, x);
+    const unsigned long long m = ((unsigned long long)(x[0] >> 5) << 26) | (unsigned long long)(x[1] >> 6);
+    return (m < A.thr[0] ? 1u : 0u) | (m < A.thr[1] ? 2u : 0u) | (m < A.thr[2] ? 4u : 0u);
+}
+
+__device__ __forceinline__ bool within_exact(int norm, float2 a, float2 b, double thr)
+{
+    const double dx = __dsub_rn((double)a.x, (double)b.x), dy = __dsub_rn((double)a.y, (double)b.y);
+    if (norm == LM_NORM_2) return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)) <= thr;
+    if (norm == LM_NORM_1) return __dadd_rn(fabs(dx), fabs(dy)) <= thr;
+    return fmax(fabs(dx), fabs(dy)) <= thr;
+}
+
+__device__ __forceinline__ bool within(const IArgs &A, float2 a, float2 b)
+{
+    const float dx = a.x - b.x, dy = a.y - b.y;
+    const float d2 = A.norm == LM_NORM_2 ? fmaf(dx, dx, dy * dy)
+                                         : (A.norm == LM_NORM_1 ? fabsf(dx) + fabsf(dy) : fmaxf(fabsf(dx), fabsf(dy)));
+    if (d2 > A.r2_hi) return false;
+    if (d2 < A.r2_lo) return true;
+    return within_exact(A.norm, a, b, A.r2);
+}
+
+// ---- where a tile's microbes live: shared memory (staged) or the global arrays ----------------------------------
+struct SmemView {
+    const float2 *pos;
+    const int32_t *id;
+    int8_t *sp;
+    __device__ __forceinline__ float2 P(int i) const { return pos[i]; }
+    __device__ __forceinline__ int I(int i) const { return id[i]; }
+    __device__ __forceinline__ int S(int i) const { return ((volatile int8_t *)sp)[i]; }
+    __device__ __forceinline__ void W(int i, int s) const { ((volatile int8_t *)sp)[i] = (int8_t)s; }
+};
+struct GlobalView {
+    const float *lon, *lat;
+    const int32_t *id;
+    int8_t *sp;
+    __device__ __forceinline__ float2 P(int i) const { return make_float2(__ldg(lon + i), __ldg(lat + i)); }
+    __device__ __forceinline__ int I(int i) const { return __ldg(id + i); }
+    __device__ __forceinline__ int S(int i) const { return ((volatile int8_t *)sp)[i]; }
+    __device__ __forceinline__ void W(int i, int s) const { ((volatile int8_t *)sp)[i] = (int8_t)s; }
+};
+
+// ---- CTA-wide working set in shared memory ----------------------------------------------------------------------
+struct Shared {
+    int2 stage[IT_STAGE];                 // found pairs waiting for the next flush
+    uint4 unit[IT_CELLS];                 // units of the current phase: x a_base | y b_base | z m_a | w m_b (b_base == a_base: one cell)
+    unsigned int n_light, n_heavy;        // light units grow from the front of unit[], heavy ones from the back
+    unsigned int ticket, hticket;
+    unsigned int stage_cnt;
+    unsigned long long flush_base;
+};
+
+// One found pair per calling lane (`hit`); all 32 lanes of the warp call this converged.
+__device__ __forceinline__ void stage_pairs(const IArgs &A, Shared &sh, bool hit, int lo, int hi)
+{
+    const unsigned int mh = __ballot_sync(FULL, hit);
+    if (!mh) return;
+    const int lane = threadIdx.x & 31, leader = __ffs(mh) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(&sh.stage_cnt, (unsigned int)__popc(mh));
+    base = __shfl_sync(FULL, base, leader);
+    if (hit && A.pairs) {
+        const unsigned int k = base + __popc(mh & ((1u << lane) - 1u));
+        if (k < (unsigned int)IT_STAGE) sh.stage[k] = make_int2(lo, hi);
+        else {                                                        // the stage is full: straight to the list
+            const unsigned long long g = atomicAdd(&A.ctr->n_pairs, 1ull);
+            if (g < A.cap_pairs) A.pairs[g] = make_int2(lo, hi);
+        }
+    }
+}
+
+// Every thread of the CTA calls this at the same point; the caller has a __syncthreads() before it.
+__device__ void flush_pairs(const IArgs &A, Shared &sh, bool force)
+{
+    const unsigned int cnt = sh.stage_cnt;                            // CTA-uniform ...
+    __syncthreads();                                                  // ... because nobody stages before everybody has read it
+    if (cnt == 0 || (!force && cnt < (unsigned int)(IT_STAGE / 2))) return;
+    const unsigned int n_buf = A.pairs ? min(cnt, (unsigned int)IT_STAGE) : cnt;   // the overflow went out directly
+    if (threadIdx.x == 0) sh.flush_base = atomicAdd(&A.ctr->n_pairs, (unsigned long long)n_buf);
+    __syncthreads();
+    if (A.pairs) {
+        const unsigned long long base = sh.flush_base;
+        for (unsigned int k = threadIdx.x; k < n_buf; k += IT_THREADS)
+            if (base + k < A.cap_pairs) A.pairs[base + k] = sh.stage[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) sh.stage_cnt = 0;
+    __syncthreads();
+}
+
+// ---- slot generators --------------------------------------------------------------------------------------------
+// Two cells: round k in [0, M), slot i in [0, m_a): anchor rank i with partner rank (i + k) mod M  (valid if < m_b).
+struct CrossWalk {
+    int a_base, b_base, ma, mb, M, i, j, k;
+    __device__ __forceinline__ void init(const uint4 &u)
+    {
+        a_base = (int)u.x; b_base = (int)u.y; ma = (int)u.z; mb = (int)u.w;
+        M = max(ma, mb); i = 0; j = 0; k = 0;
+    }
+    __device__ __forceinline__ bool valid() const { return j < mb; }
+    __device__ __forceinline__ int a() const { return a_base + i; }
+    __device__ __forceinline__ int b() const { return b_base + j; }
+    __device__ __forceinline__ bool next()                           // false: the unit is done
+    {
+        ++i; ++j;
+        if (j == M) j = 0;
+        if (i == ma) { i = 0; ++k; j = k; if (k == M) return false; }
+        return true;
+    }
+};
+// One cell, m microbes, M = m rounded up to even: round k in [0, M - 1), slot 0: rank M - 1 with rank k;
+// slot jj in [1, M / 2): rank (k + jj) mod (M - 1) with rank (k - jj) mod (M - 1).  Rank m (m odd) is a phantom.
+struct SameWalk {
+    int base, m, M, n1, k, jj, p, q;
+    __device__ __forceinline__ void init(const uint4 &u)
+    {
+        base = (int)u.x; m = (int)u.z; M = m + (m & 1); n1 = M - 1; k = 0; jj = 0; p = 0; q = 0;
+    }
+    __device__ __forceinline__ int ra() const { return jj == 0 ? M - 1 : p; }
+    __device__ __forceinline__ int rb() const { return jj == 0 ? k : q; }
+    __device__ __forceinline__ bool valid() const { return ra() < m && rb() < m; }
+    __device__ __forceinline__ int a() const { return base + min(ra(), rb()); }     // smaller rank = smaller id first
+    __device__ __forceinline__ int b() const { return base + max(ra(), rb()); }
+    __device__ __forceinline__ bool next()
+    {
+        ++jj;
+        if (jj == (M >> 1)) { jj = 0; ++k; p = q = k; return k < n1; }
+        ++p; if (p >= n1) p -= n1;
+        --q; if (q < 0) q += n1;
+        return true;
+    }
+};
+
+// slots of a unit (what one lane would have to walk)
+__device__ __forceinline__ unsigned int unit_slots(bool same, unsigned int ma, unsigned int mb)
+{
+    if (same) { const unsigned int M = ma + (ma & 1u); return ma < 2 ? 0u : (M - 1u) * (M >> 1); }
+    return (ma == 0 || mb == 0) ? 0u : ma * max(ma, mb);
+}
+
+// ---- light units: every lane walks its own units, the Philox draws are batched per warp ------------------------
+template <class V, class Walk, bool DO_RPS>
+__device__ void walk_light(const IArgs &A, Shared &sh, const V &v)
+{
+    const unsigned int n_units = sh.n_light;
+    Walk w;
+    bool active = false, parked = false;
+    int pa = 0, pb = 0, plo = 0, phi = 0;                            // the parked pair: local indices, ids (lo < hi)
+    unsigned int t = threadIdx.x;                                     // the first unit of a lane is fixed: the ticket starts at IT_THREADS
+    if (t < n_units) { w.init(sh.unit[t]); active = true; }
+    while (true) {
+        const bool can = active && !parked;
+        const unsigned int m_can = __ballot_sync(FULL, can);
+        const unsigned int m_park = DO_RPS ? __ballot_sync(FULL, parked) : 0u;
+        if (!m_can && !m_park) break;
+        if (DO_RPS && m_park && (!m_can || __popc(m_park) >= A.draw_batch)) {
+            if (parked) {
+                const uint32_t dec = decision_bits(A, plo, phi);
+                const int sa = v.S(pa), sb = v.S(pb);                 // unchanged since the lane parked: units are disjoint
+                const int s = rps_apply(sa, sb, dec);
+                if (s != sa) v.W(pa, s); else v.W(pb, s);
+                parked = false;
+            }
+            continue;
+        }
+        bool hit = false;
+        int ia = 0, ib = 0;
+        if (can) {
+            if (w.valid()) {
+                ia = w.a(); ib = w.b();
+                hit = within(A, v.P(ia), v.P(ib));
+            }
+            if (!w.next()) {                                          // next unit (its first slot is taken next iteration)
+                t = atomicAdd(&sh.ticket, 1u);
+                if (t < n_units) w.init(sh.unit[t]); else active = false;
+            }
+        }
+        int lo = 0, hi = 0;
+        if (hit) { const int x = v.I(ia), y = v.I(ib); lo = min(x, y); hi = max(x, y); }
+        stage_pairs(A, sh, hit, lo, hi);
+        if (DO_RPS && hit) {
+            const int sa = v.S(ia), sb = v.S(ib);
+            if (sa != sb && is_rps(sa) && is_rps(sb)) { parked = true; pa = ia; pb = ib; plo = lo; phi = hi; }
+        }
+    }
+}
+
+// One slot of a cooperative (warp / CTA) round: everything inline, the lanes of a round hold disjoint pairs.
+template <class V, bool DO_RPS>
+__device__ __forceinline__ void slot_inline(const IArgs &A, Shared &sh, const V &v, bool valid, int ia, int ib)
+{
+    bool hit = false;
+    if (valid) hit = within(A, v.P(ia), v.P(ib));
+    int lo = 0, hi = 0;
+    if (hit) { const int x = v.I(ia), y = v.I(ib); lo = min(x, y); hi = max(x, y); }
+    stage_pairs(A, sh, hit, lo, hi);
+    if (DO_RPS && hit) {
+        const int sa = v.S(ia), sb = v.S(ib);
+        if (sa != sb && is_rps(sa) && is_rps(sb)) {
+            const int s = rps_apply(sa, sb, decision_bits(A, lo, hi));
+            if (s != sa) v.W(ia, s); else v.W(ib, s);
+        }
+    }
+}
+
+// A unit round by round with `nthr` threads (32: one warp, __syncwarp between rounds; IT_THREADS: the CTA,
+// __syncthreads between rounds -- then every thread of the CTA calls this with the same unit).
+template <class V, bool DO_RPS, bool CTA>
+__device__ void unit_rounds(const IArgs &A, Shared &sh, const V &v, const uint4 u)
+{
+    const int nthr = CTA ? IT_THREADS : 32;
+    const int me = CTA ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+    const int a_base = (int)u.x, b_base = (int)u.y, ma = (int)u.z, mb = (int)u.w;
+    if (a_base == b_base) {
+        const int m = ma, M = m + (m & 1), n1 = M - 1, half = M >> 1;
+        for (int k = 0; k < n1; ++k) {
+            for (int j0 = 0; j0 < half; j0 += nthr) {                 // uniform trip count: stage_pairs needs whole warps
+                const int jj = j0 + me;
+                int ra = 0, rb = 0;
+                bool valid = jj < half;
+                if (valid) {
+                    if (jj == 0) { ra = M - 1; rb = k; }
+                    else { ra = k + jj; if (ra >= n1) ra -= n1; rb = k - jj; if (rb < 0) rb += n1; }
+                    valid = ra < m && rb < m;
+                }
+                slot_inline<V, DO_RPS>(A, sh, v, valid, a_base + min(ra, rb), a_base + max(ra, rb));
+            }
+            if (CTA) { __syncthreads(); flush_pairs(A, sh, false); } else __syncwarp();
+        }
+    } else {
+        const int M = max(ma, mb);
+        for (int k = 0; k < M; ++k) {
+            for (int i0 = 0; i0 < ma; i0 += nthr) {
+                const int i = i0 + me;
+                int j = i + k;
+                if (j >= M) j -= M;
+                slot_inline<V, DO_RPS>(A, sh, v, i < ma && j < mb, a_base + i, b_base + j);
+            }
+            if (CTA) { __syncthreads(); flush_pairs(A, sh, false); } else __syncwarp();
+        }
+    }
+}
+
+// The units listed in sh.unit[] (light from the front, heavy from the back); every thread of the CTA calls this.
+template <class V, bool DO_RPS>
+__device__ void run_units(const IArgs &A, Shared &sh, const V &v, bool same)
+{
+    __syncthreads();                                                  // the list is complete
+    if (sh.n_light) {
+        if (same) walk_light<V, SameWalk, DO_RPS>(A, sh, v);
+        else walk_light<V, CrossWalk, DO_RPS>(A, sh, v);
+    }
+    const unsigned int n_heavy = sh.n_heavy;                          // CTA-uniform
+    if (n_heavy) {
+        // whole warps pull the heavy units; the very large ones are left to the whole CTA afterwards
+        const int lane = threadIdx.x & 31;
+        while (true) {
+            unsigned int hq = 0;
+            if (lane == 0) hq = atomicAdd(&sh.hticket, 1u);
+            hq = __shfl_sync(FULL, hq, 0);
+            if (hq >= n_heavy) break;
+            const uint4 u = sh.unit[IT_CELLS - 1 - hq];
+            if (unit_slots(u.x == u.y, u.z, u.w) >= IT_MEGA_MIN) continue;
+            unit_rounds<V, DO_RPS, false>(A, sh, v, u);
+        }
+        __syncthreads();
+        for (unsigned int hq = 0; hq < n_heavy; ++hq) {
+            const uint4 u = sh.unit[IT_CELLS - 1 - hq];
+            if (unit_slots(u.x == u.y, u.z, u.w) < IT_MEGA_MIN) continue;
+            unit_rounds<V, DO_RPS, true>(A, sh, v, u);
+        }
+    }
+    __syncthreads();
+    flush_pairs(A, sh, false);
+}
+
+// Append a unit to the list; all 32 lanes of the warp call this converged (`have`: this lane has one).
+__device__ __forceinline__ void push_unit(Shared &sh, bool have, bool same, uint4 u)
+{
+    const unsigned int slots = have ? unit_slots(same, u.z, u.w) : 0u;
+    const bool light = slots > 0 && slots <= IT_LIGHT_MAX, heavy = slots > IT_LIGHT_MAX;
+    const int lane = threadIdx.x & 31;
+    const unsigned int ml = __ballot_sync(FULL, light), mh = __ballot_sync(FULL, heavy);
+    if (ml) {
+        const int leader = __ffs(ml) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&sh.n_light, (unsigned int)__popc(ml));
+        base = __shfl_sync(FULL, base, leader);
+        if (light) sh.unit[base + __popc(ml & ((1u << lane) - 1u))] = u;
+    }
+    if (mh) {
+        const int leader = __ffs(mh) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&sh.n_heavy, (unsigned int)__popc(mh));
+        base = __shfl_sync(FULL, base, leader);
+        if (heavy) sh.unit[IT_CELLS - 1 - (base + __popc(mh & ((1u << lane) - 1u)))] = u;
+    }
+}
+
+// ---- stage I: the units inside one tile, phases 0..8 -----------------------------------------------------------
+template <class V, bool DO_RPS>
+__device__ void tile_phases(const IArgs &A, Shared &sh, const V &v, const int (*s_cs)[IT_TW + 1], const int *s_delta,
+                            int w, int hgt)
+{
+    const int tid = threadIdx.x;
+    for (int ph = 0; ph < 9; ++ph) {
+        if (tid == 0) { sh.n_light = 0; sh.n_heavy = 0; sh.ticket = IT_THREADS; sh.hticket = 0; }
+        __syncthreads();
+        const bool same = ph == 0;
+#pragma unroll
+        for (int q = 0; q < IT_UPT; ++q) {
+            const int e = tid + q * IT_THREADS;
+            const int t = e >> 5, x = e & 31;                         // IT_TW == 32
+            bool have = t < hgt && x < w;
+            int to = t, xo = x;
+            if (ph == 0) { }
+            else if (ph <= 2) { have = have && (x & 1) == ph - 1 && x + 1 < w; xo = x + 1; }
+            else {
+                const int par = (ph - 3) / 3, dir = (ph - 3) % 3 - 1;
+                xo = x + dir; to = t + 1;
+                have = have && (t & 1) == par && to < hgt && xo >= 0 && xo < w;
+            }
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (have) {
+                const int a0 = s_cs[t][x], a1 = s_cs[t][x + 1];
+                const int b0 = s_cs[to][xo], b1 = s_cs[to][xo + 1];
+                u = make_uint4((unsigned int)(a0 + s_delta[t]), (unsigned int)(b0 + s_delta[to]), (unsigned int)(a1 - a0),
+                               (unsigned int)(b1 - b0));
+            }
+            push_unit(sh, have, same, u);
+        }
+        run_units<V, DO_RPS>(A, sh, v, same);
+    }
+}
+
+template <bool DO_RPS>
+__global__ void __launch_bounds__(IT_THREADS) interact_tile_kernel(IArgs A)
+{
+    extern __shared__ __align__(16) unsigned char s_dyn[];            // float2 pos[cap] | int32 id[cap] | int8 sp[cap]
+    __shared__ Shared sh;
+    __shared__ int s_cs[IT_TH][IT_TW + 1];
+    __shared__ int s_delta[IT_TH];
+    __shared__ int s_total;
+    const int tid = threadIdx.x;
+    const int tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x;
+    const int x0 = tx * IT_TW, y0 = ty * IT_TH;
+    const int w = min(IT_TW, A.ncx - x0), hgt = min(IT_TH, A.rows_owned - y0);
+    for (int k = tid; k < hgt * (w + 1); k += IT_THREADS) {
+        const int t = k / (w + 1), x = k - t * (w + 1);
+        s_cs[t][x] = __ldg(A.cell_start + (long long)(y0 + t) * A.ncx + x0 + x);
+    }
+    if (tid == 0) sh.stage_cnt = 0;
+    __syncthreads();
+    if (tid == 0) {
+        int off = 0;
+        for (int t = 0; t < hgt; ++t) { s_delta[t] = off - s_cs[t][0]; off += s_cs[t][w] - s_cs[t][0]; }
+        s_total = off;
+    }
+    __syncthreads();
+    const int total = s_total;
+    if (total < 2) return;                                            // CTA-uniform: no pair inside this tile
+    if (total <= A.tile_cap) {
+        float2 *s_pos = reinterpret_cast<float2 *>(s_dyn);
+        int32_t *s_id = reinterpret_cast<int32_t *>(s_pos + A.tile_cap);
+        int8_t *s_sp = reinterpret_cast<int8_t *>(s_id + A.tile_cap);
+        for (int t = 0; t < hgt; ++t) {
+            const int p0 = s_cs[t][0], cnt = s_cs[t][w] - p0, d = s_delta[t] + p0;
+            for (int i = tid; i < cnt; i += IT_THREADS) {
+                s_pos[d + i] = make_float2(__ldg(A.lon + p0 + i), __ldg(A.lat + p0 + i));
+                s_id[d + i] = __ldg(A.id + p0 + i);
+                if (DO_RPS) s_sp[d + i] = A.sp[p0 + i];
+            }
+        }
+        __syncthreads();
+        SmemView v{s_pos, s_id, s_sp};
+        tile_phases<SmemView, DO_RPS>(A, sh, v, s_cs, s_delta, w, hgt);
+        if (DO_RPS) {
+            for (int t = 0; t < hgt; ++t) {
+                const int p0 = s_cs[t][0], cnt = s_cs[t][w] - p0, d = s_delta[t] + p0;
+                for (int i = tid; i < cnt; i += IT_THREADS) A.sp[p0 + i] = s_sp[d + i];
+            }
+        }
+    } else {
+        __syncthreads();
+        if (tid < hgt) s_delta[tid] = 0;                              // local index == global index
+        __syncthreads();
+        GlobalView v{A.lon, A.lat, A.id, A.sp};
+        tile_phases<GlobalView, DO_RPS>(A, sh, v, s_cs, s_delta, w, hgt);
+    }
+    __syncthreads();
+    flush_pairs(A, sh, true);
+}
+
+// ---- stage II: the units of ONE boundary phase (9..14), from global memory --------------------------------------
+//   9  east       anchor (bx*32 - 1, cy)             bx = 1 .. tiles_x - 1, every owned row
+//  10  NW, 11 NE  across a vertical boundary only:   anchor column bx*32 (NW) / bx*32 - 1 (NE), rows with cy % 16 != 15
+//  12  NW, 13 N, 14 NE across a horizontal boundary: anchor row by*16 - 1, by = 1 .. (rows_local - 1) / 16, every column
+// (the partner row of the last boundary may be the ghost row of a strip: rows_local = rows_owned + 1)
+template <bool DO_RPS>
+__global__ void __launch_bounds__(IT_THREADS) interact_cross_kernel(IArgs A, long long n_units)
+{
+    __shared__ Shared sh;
+    const int tid = threadIdx.x;
+    if (tid == 0) { sh.stage_cnt = 0; sh.n_light = 0; sh.n_heavy = 0; sh.ticket = IT_THREADS; sh.hticket = 0; }
+    __syncthreads();
+    const int nbx = A.tiles_x - 1;
+    const int ph = A.phase;
+    const long long base = (long long)blockIdx.x * IT_CELLS;
+#pragma unroll
+    for (int q = 0; q < IT_UPT; ++q) {
+        const long long e = base + tid + q * IT_THREADS;
+        bool have = e < n_units;
+        int cx = 0, cy = 0, ox = 0, oy = 0;
+        if (have) {
+            if (ph <= 11) {
+                cy = (int)(e / nbx);
+                const int bx = 1 + (int)(e - (long long)cy * nbx);
+                if (ph == 9) { cx = bx * IT_TW - 1; ox = cx + 1; oy = cy; }
+                else {
+                    cx = ph == 10 ? bx * IT_TW : bx * IT_TW - 1;
+                    ox = ph == 10 ? cx - 1 : cx + 1; oy = cy + 1;
+                    have = (cy % IT_TH) != IT_TH - 1 && oy < A.rows_local;
+                }
+            } else {
+                const int by = 1 + (int)(e / A.ncx);
+                cx = (int)(e - (long long)(by - 1) * A.ncx);
+                cy = by * IT_TH - 1; oy = cy + 1; ox = cx + (ph - 13);
+                have = ox >= 0 && ox < A.ncx;
+            }
+        }
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (have) {
+            const long long ca = (long long)cy * A.ncx + cx, cb = (long long)oy * A.ncx + ox;
+            const int a0 = __ldg(A.cell_start + ca), a1 = __ldg(A.cell_start + ca + 1);
+            const int b0 = __ldg(A.cell_start + cb), b1 = __ldg(A.cell_start + cb + 1);
+            u = make_uint4((unsigned int)a0, (unsigned int)b0, (unsigned int)(a1 - a0), (unsigned int)(b1 - b0));
+        }
+        push_unit(sh, have, false, u);
+    }
+    GlobalView v{A.lon, A.lat, A.id, A.sp};
+    run_units<GlobalView, DO_RPS>(A, sh, v, false);
+    __syncthreads();
+    flush_pairs(A, sh, true);
+}
+
+}  // namespace
+
+// Phases [first, last] of 0..14 (0..8 are ONE launch: any of them asks for all nine).
+cudaError_t launch_interact(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
+                            double r, const RpsDev *rps, int2 *pairs_out, int64_t cap, int first, int last,
+                            cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    IArgs A;
+    A.lon = lon; A.lat = lat; A.id = id; A.sp = rps ? sp : nullptr; A.cell_start = h->cell_start;
+    A.ncx = h->grid.ncx; A.rows_owned = h->strip.rows_owned; A.rows_local = h->strip.rows_local;
+    A.tiles_x = (A.ncx + IT_TW - 1) / IT_TW; A.tiles_y = (A.rows_owned + IT_TH - 1) / IT_TH;
+    A.norm = h->norm;
+    A.r2 = h->norm == LM_NORM_2 ? r * r : r;           // SciPy: tub = r*r for p=2, pow(r, 1) for p=1, r for p=inf
+    A.r2_lo = (float)(A.r2 * (1.0 - 4e-6));
+    A.r2_hi = (float)(A.r2 * (1.0 + 4e-6));
+    A.seed_lo = A.seed_hi = A.step_lo = A.step_hi = 0;
+    A.thr[0] = A.thr[1] = A.thr[2] = 0;
+    if (rps) {
+        A.seed_lo = rps->seed_lo; A.seed_hi = rps->seed_hi; A.step_lo = rps->step_lo; A.step_hi = rps->step_hi;
+        const double p[3] = {rps->pRS, rps->pPR, rps->pSP};
+        for (int k = 0; k < 3; ++k) {
+            // u = m * 2^-53 with integer m < 2^53:  u < p  <=>  m < ceil(p * 2^53)   (the scaling is exact)
+            if (!(p[k] > 0.0)) A.thr[k] = 0;
+            else if (p[k] >= 1.0) A.thr[k] = 1ull << 53;
+            else A.thr[k] = (unsigned long long)ceil(p[k] * 9007199254740992.0);
+        }
+    }
+    A.pairs = (pairs_out && cap > 0) ? pairs_out : nullptr;
+    A.cap_pairs = A.pairs ? (unsigned long long)cap : 0ull;
+    A.ctr = h->ctr;
+    A.draw_batch = h->draw_batch > 0 ? h->draw_batch : 20;
+    A.phase = 0;
+    // shared memory per tile: 1.5 x the mean occupancy of a tile, at least 1,024 microbes, at most 6,144 (80 KB: two CTAs per SM)
+    const long long tiles = (long long)A.tiles_x * A.tiles_y;
+    long long want = h->tile_cap > 0 ? h->tile_cap : std::max<long long>(1024, 3 * ((long long)n / std::max<long long>(1, tiles)) / 2 + 256);
+    want = std::min<long long>(want, 6144);
+    A.tile_cap = (int)((want + 255) / 256 * 256);
+    const size_t dyn = (size_t)A.tile_cap * 13;
+    cudaError_t e = cudaSuccess;
+    if (first <= 8) {
+        auto k = rps ? interact_tile_kernel<true> : interact_tile_kernel<false>;
+        e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        k<<<(unsigned int)tiles, IT_THREADS, dyn, s>>>(A);
+        ++h->launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    for (int ph = std::max(first, 9); ph <= last; ++ph) {
+        long long n_units;
+        if (ph <= 11) n_units = (long long)(A.tiles_x - 1) * A.rows_owned;
+        else n_units = (long long)((A.rows_local - 1) / IT_TH) * A.ncx;
+        if (n_units <= 0) continue;
+        A.phase = ph;
+        const unsigned int grid = (unsigned int)((n_units + IT_CELLS - 1) / IT_CELLS);
+        if (rps) interact_cross_kernel<true><<<grid, IT_THREADS, 0, s>>>(A, n_units);
+        else interact_cross_kernel<false><<<grid, IT_THREADS, 0, s>>>(A, n_units);
+        ++h->launches;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+}  // namespace lm

@@ -92,6 +92,19 @@ struct lm_handle_s {
     int find_path;         // LM_OPT_FIND_PATH: 0 auto | 1 every warp takes the two-pass (dense cluster) path
     int resolve_heavy_min; // LM_OPT_RESOLVE_HEAVY_MIN: 0 = default (160)
     int resolve_batch;     // LM_OPT_RESOLVE_BATCH: pairs per lane and iteration in the resolver's stream walk (1, 4, 8)
+    int interact_mode;     // LM_OPT_INTERACT_MODE: 1 (default) fused tile kernel, tile-round order (csrc/interact.cu) |
+                           //                       0 round-1 pipeline: pair search -> hand-off -> nine phase launches (csrc/pairs.cu)
+    int draw_batch;        // LM_OPT_DRAW_BATCH: parked lanes that trigger a warp's Philox rounds (0 = default, 20)
+    int tile_cap;          // LM_OPT_TILE_CAP: microbes a tile stages in shared memory (0 = from the mean occupancy)
+    // arguments of the interaction in flight (fused tile kernel: the boundary phases 12-14 run in lm_step_interact_end)
+    const float *ia_lon, *ia_lat;
+    const int32_t *ia_id;
+    int ia_n;
+    double ia_r;
+    lm::RpsDev ia_rps;
+    bool ia_have_rps;
+    int2 *ia_pairs;
+    int64_t ia_cap;
     int advect_mode;       // LM_OPT_ADVECT_MODE: 0 bit-faithful to the float32 restatement of Parcels' kernel | 1 float32 arithmetic
     int norm;              // LM_OPT_NORM: LM_NORM_2 (default) | LM_NORM_1 | LM_NORM_INF
     // tiled resolver (LM_OPT_RESOLVE_MODE = 1; csrc/pairs.cu): allocated when the mode is first switched on
@@ -180,6 +193,10 @@ cudaError_t launch_pairs(lm_handle_s *h, const float *lon, const float *lat, con
 cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int n, double r,
                         const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s);
 cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int last, cudaStream_t s);
+// fused tile kernel (csrc/interact.cu): phases [first, last] of the tile-round order, 0..14 (0..8 are one launch)
+cudaError_t launch_interact(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
+                            double r, const RpsDev *rps, int2 *pairs_out, int64_t cap, int first, int last,
+                            cudaStream_t s);
 cudaError_t launch_pair_uniforms(const int2 *pairs, int64_t np, uint64_t seed, uint64_t step, double *u,
                                  cudaStream_t s);
 int resolve_explicit(lm_handle_s *h, const int2 *pairs, const double *u, int64_t np, int8_t *species, int64_t n,

@@ -814,6 +814,16 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
                         const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s)
 {
     h->rps_cap = rps ? h->max_pairs : -1;
+    if (h->interact_mode == 1) {
+        // fused tile kernel: the tile phases and the vertical-boundary phases now, the horizontal-boundary phases
+        // (the only ones that cross a strip boundary) with launch_resolve_phases(.., 6, 8)
+        h->rps_cap = -1;                                   // no hand-off to overflow
+        h->ia_lon = lon; h->ia_lat = lat; h->ia_id = id; h->ia_n = n; h->ia_r = r;
+        h->ia_have_rps = rps != nullptr;
+        if (rps) h->ia_rps = *rps;
+        h->ia_pairs = pairs_out; h->ia_cap = cap;
+        return launch_interact(h, lon, lat, id, h->sp[h->cur], n, r, rps, pairs_out, cap, 0, 11, s);
+    }
     if (n <= 0) return cudaSuccess;
     FindArgs F;
     F.lon = lon; F.lat = lat; F.id = id; F.cell_start = h->cell_start;
@@ -1278,6 +1288,11 @@ static cudaError_t launch_resolve_tiled(lm_handle_s *h, int8_t *sp, int first, i
 
 cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int last, cudaStream_t s)
 {
+    if (h->interact_mode == 1) {
+        if (last < 6) return cudaSuccess;
+        return launch_interact(h, h->ia_lon, h->ia_lat, h->ia_id, sp, h->ia_n, h->ia_r, h->ia_have_rps ? &h->ia_rps : nullptr,
+                               h->ia_pairs, h->ia_cap, 12, 14, s);
+    }
     if (h->rps_cap < 0) return cudaSuccess;
     if (h->resolve_mode == 1) return launch_resolve_tiled(h, sp, first, last, s);
     ResolveArgs R;
@@ -1325,6 +1340,7 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
 cudaError_t launch_pairs(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
                          double r, const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s)
 {
+    if (h->interact_mode == 1) return launch_interact(h, lon, lat, id, sp, n, r, rps, pairs_out, cap, 0, 14, s);
     cudaError_t e = launch_find(h, lon, lat, id, n, r, rps, pairs_out, cap, s);
     if (e != cudaSuccess || !rps || n <= 0) return e;
     return launch_resolve_phases(h, sp, 0, 8, s);

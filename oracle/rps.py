@@ -148,3 +148,86 @@ def cell_phase_order(pairs, lon32, lat32, grid):
     unit = cya * np.int64(grid["ncx"]) + cxa
     order = np.lexsort((b, a, unit, phase))
     return pairs[order], phase[order]
+
+
+# ---------------------------------------------------------------------------------------------
+# Canonical pair order of the fused tile kernel ("tile-round order", DESIGN.md §4.3, csrc/interact.cu).
+# ---------------------------------------------------------------------------------------------
+TILE_W, TILE_H = 32, 16      # cells per tile of the device kernel: part of the definition of the order
+
+
+def cell_ranks(lon32, lat32, grid):
+    """Cell coordinates, rank of every particle among the particles of its cell (by id), cell occupancy."""
+    from .pairs import cell_index
+    n = np.asarray(lon32).shape[0]
+    cx = cell_index(lon32, grid["x0"], grid["inv_h"], grid["ncx"]).astype(np.int64)
+    cy = cell_index(lat32, grid["y0"], grid["inv_h"], grid["ncy"]).astype(np.int64)
+    key = cy * np.int64(grid["ncx"]) + cx
+    order = np.lexsort((np.arange(n), key))                    # storage order of the device: (cell, id)
+    sk = key[order]
+    pos = np.arange(n, dtype=np.int64)
+    first = np.r_[True, sk[1:] != sk[:-1]] if n else np.zeros(0, dtype=bool)
+    run_start = np.maximum.accumulate(np.where(first, pos, 0)) if n else pos
+    rank = np.empty(n, dtype=np.int64)
+    rank[order] = pos - run_start
+    occ = np.bincount(key, minlength=int(grid["ncx"]) * int(grid["ncy"]))[key] if n else pos
+    return cx, cy, rank, occ.astype(np.int64)
+
+
+def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
+    """Return ``pairs`` (rows i<j, original ids) re-ordered into the canonical order of the fused tile kernel.
+
+    Cells are grouped into tiles of ``tile`` = (32, 16) cells, origin at cell (0, 0) of the grid.  A *unit* is one
+    cell (the pairs inside it) or two adjacent cells (half stencil: E, NW, N, NE of the anchor cell).  Order key
+    (phase, unit, round, slot):
+
+      phase  0..8   units inside one tile, as in ``cell_phase_order``:
+                    0 same cell | 1 + (cx & 1) east | 3 (cy & 1) + 3, + 4, + 5  north-west, north, north-east
+             9..14  units across a tile boundary: 9 east | 10, 11 north-west, north-east across a vertical
+                    boundary only | 12, 13, 14 north-west, north, north-east across a horizontal boundary
+      unit   anchor cell (the western / southern one)
+      round, slot   the pairs of a unit are taken in ROUNDS OF MATCHINGS -- inside a round no microbe occurs
+                    twice, so a round is order-free and the device resolves it in parallel:
+             two cells, m_a and m_b microbes ranked by id, M = max(m_a, m_b): round k in [0, M) pairs rank i of
+                    the anchor cell with rank (i + k) mod M of the other cell; slot = i
+             one cell, m microbes, M = m rounded up to even (rank M - 1 is a phantom when m is odd): the circle
+                    method of round-robin tournaments -- round k in [0, M - 1) pairs rank M - 1 with rank k
+                    (slot 0) and rank (k + j) mod (M - 1) with rank (k - j) mod (M - 1) for j in [1, M / 2) (slot j)
+
+    Units of one phase touch disjoint microbes; their relative order is immaterial.
+    """
+    tw, th = tile
+    pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    cx, cy, rank, occ = cell_ranks(lon32, lat32, grid)
+    i, j = pairs[:, 0], pairs[:, 1]
+    cxi, cyi, cxj, cyj = cx[i], cy[i], cx[j], cy[j]
+    assert np.all(np.abs(cxi - cxj) <= 1) and np.all(np.abs(cyi - cyj) <= 1), "pair spans non-adjacent cells"
+    same = (cxi == cxj) & (cyi == cyj)
+    j_anchor = (cyj < cyi) | ((cyj == cyi) & (cxj < cxi))
+    a = np.where(j_anchor, j, i)
+    b = np.where(j_anchor, i, j)
+    cxa, cya, cxb, cyb = cx[a], cy[a], cx[b], cy[b]
+    d = cxb - cxa
+    inner = np.where(same, 0, np.where(cya == cyb, 1 + (cxa & 1), 3 * (cya & 1) + 4 + d))
+    cross_v = (cxa // tw) != (cxb // tw)
+    cross_h = (cya // th) != (cyb // th)
+    outer = np.where(cya == cyb, 9, np.where(cross_h, 13 + d, np.where(d < 0, 10, 11)))
+    phase = np.where(cross_v | cross_h, outer, inner)
+    unit = cya * np.int64(grid["ncx"]) + cxa
+    # rounds and slots
+    ra, rb, ma, mb = rank[a], rank[b], occ[a], occ[b]
+    big = np.maximum(ma, mb)
+    rnd_x = np.mod(rb - ra, big)
+    slot_x = ra
+    p, q = np.minimum(ra, rb), np.maximum(ra, rb)
+    m_even = ma + (ma & 1)
+    n1 = np.maximum(m_even - 1, 1)
+    fixed = q == m_even - 1                                    # the player that stays put (only real when m is even)
+    rnd_s = np.where(fixed, p, np.mod((p + q) * (m_even // 2), n1))
+    jp = np.mod(p - rnd_s, n1)
+    jq = np.mod(q - rnd_s, n1)
+    slot_s = np.where(fixed, 0, np.where((jp >= 1) & (jp < m_even // 2), jp, jq))
+    rnd = np.where(same, rnd_s, rnd_x)
+    slot = np.where(same, slot_s, slot_x)
+    order = np.lexsort((slot, rnd, unit, phase))
+    return pairs[order], phase[order]

@@ -31,6 +31,8 @@ struct int2 { int x, y; };
 struct alignas(16) uint4 { unsigned int x, y, z, w; };
 struct alignas(16) int4 { int x, y, z, w; };
 struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 struct uint3 { unsigned int x, y, z; };
 static inline uint2 make_uint2(unsigned int x, unsigned int y) { return uint2{x, y}; }
 static inline int2 make_int2(int x, int y) { return int2{x, y}; }
@@ -154,6 +156,9 @@ static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
 static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fdividef(float a, float b) { return a / b; }
+static inline float emu_fast_cosf(float a) { return cosf(a); }
+#define __cosf emu_fast_cosf
 static inline double __ddiv_rn(double a, double b) { return a / b; }
 static inline float __fsub_rn(float a, float b) { return a - b; }
 static inline float __fdiv_rn(float a, float b) { return a / b; }

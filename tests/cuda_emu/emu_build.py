@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "lagrangian_microbes_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
-SOURCES = ["api.cu", "advect.cu", "bin.cu", "strip.cu", "pairs.cu", "resolve.cu", "analysis.cu", "record.cu"]    # = _lib._SOURCES
+SOURCES = ["api.cu", "advect.cu", "bin.cu", "strip.cu", "pairs.cu", "interact.cu", "resolve.cu", "analysis.cu", "record.cu"]    # = _lib._SOURCES
 
 
 def _split_top_level(s):

@@ -65,6 +65,33 @@ long long emu_interact(const float *lon, const float *lat, const int32_t *id, co
     return e == cudaSuccess ? found + (launches << 48) : -1;
 }
 
+// The fused tile kernel (csrc/interact.cu): phases [first, last] of the tile-round order (0..14) on a binned state.
+// species may be null (pair search only); pairs_out may be null (count only).  Returns pairs found + launches << 48.
+long long emu_interact_tile(const float *lon, const float *lat, const int32_t *id, const int32_t *cell_start, int8_t *species,
+                            int n_owned, int ncx, int ncy, int row0, int rows_owned, int rows_local, double r, int norm,
+                            double pRS, double pPR, double pSP, unsigned long long seed, unsigned long long step, int first,
+                            int last, int tile_cap, int draw_batch, int32_t *pairs_out, long long cap)
+{
+    lm_handle_s *h = zalloc<lm_handle_s>(1);
+    h->grid.ncx = ncx; h->grid.ncy = ncy;
+    h->have_grid = true;
+    h->strip.row0 = row0; h->strip.rows_owned = rows_owned; h->strip.rows_local = rows_local;
+    h->n = n_owned;
+    h->norm = norm;
+    h->cell_start = const_cast<int32_t *>(cell_start);
+    h->ctr = zalloc<Counters>(1);
+    h->tile_cap = tile_cap; h->draw_batch = draw_batch;
+    RpsDev rd;
+    rd.pRS = pRS; rd.pPR = pPR; rd.pSP = pSP;
+    rd.seed_lo = (uint32_t)seed; rd.seed_hi = (uint32_t)(seed >> 32);
+    rd.step_lo = (uint32_t)step; rd.step_hi = (uint32_t)(step >> 32);
+    cudaError_t e = launch_interact(h, lon, lat, id, species, n_owned, r, species ? &rd : nullptr,
+                                    reinterpret_cast<int2 *>(pairs_out), pairs_out ? cap : 0, first, last, nullptr);
+    const long long found = (long long)h->ctr->n_pairs, launches = h->launches;
+    free(h->ctr); free(h);
+    return e == cudaSuccess ? found + (launches << 48) : -1;
+}
+
 int emu_pair_distance_hist(const float *lat, const float *lon, long long n, float radius_m, int bins, unsigned long long *hist)
 {
     return launch_pair_distance_hist(lat, lon, n, radius_m, bins, hist, nullptr, nullptr);
