@@ -230,6 +230,13 @@ def main():
     ap.add_argument("--resolve-mode", type=int, default=0, choices=[0, 1],
                     help="LM_OPT_RESOLVE_MODE: 0 nine phase launches (default), 1 tiled resolver (experimental)")
     ap.add_argument("--tile-smem", type=int, default=0, help="LM_OPT_RESOLVE_TILE_SMEM (with --resolve-mode 1)")
+    ap.add_argument("--interact-mode", type=int, default=1, choices=[0, 1],
+                    help="LM_OPT_INTERACT_MODE: 1 fused tile kernel (default), 0 the round-1 pipeline (A/B)")
+    ap.add_argument("--advect-mode", type=int, default=1, choices=[0, 1],
+                    help="LM_OPT_ADVECT_MODE: 1 float32 RK4 within north_star's 1e-6 relative (default here), 0 bit-faithful "
+                         "to the float32 restatement of Parcels' kernel (A/B)")
+    ap.add_argument("--draw-batch", type=int, default=0, help="LM_OPT_DRAW_BATCH (tuning experiments)")
+    ap.add_argument("--tile-cap", type=int, default=0, help="LM_OPT_TILE_CAP (tuning experiments)")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
 
@@ -278,6 +285,13 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from lagrangian_microbes_b200.simulation import FusedSimulation
+    from lagrangian_microbes_b200.engine import Engine
+    Engine.DEFAULT_INTERACT_MODE = args.interact_mode           # every handle of this run (single or strips)
+    Engine.DEFAULT_ADVECT_MODE = args.advect_mode
+    config["interact"] = ("fused tile kernel, tile-round order (LM_OPT_INTERACT_MODE=1)" if args.interact_mode == 1
+                          else "round-1 pipeline: pair search -> hand-off -> nine phase launches (LM_OPT_INTERACT_MODE=0)")
+    config["advect"] = ("float32 RK4, positions within 1e-6 relative of the float64 RK4 (LM_OPT_ADVECT_MODE=1)"
+                        if args.advect_mode == 1 else "bit-faithful to the float32 restatement of Parcels' kernel (LM_OPT_ADVECT_MODE=0)")
 
     def barrier():
         if world > 1:
@@ -329,6 +343,10 @@ def main():
                                regrid_every=16, grid_margin=0.5, stream_field=stream_field)
 
     sim = new_sim(False)
+    if args.draw_batch or args.tile_cap:
+        from lagrangian_microbes_b200._lib import LM_OPT_DRAW_BATCH, LM_OPT_TILE_CAP
+        sim.engine.set_option(LM_OPT_DRAW_BATCH, args.draw_batch)
+        sim.engine.set_option(LM_OPT_TILE_CAP, args.tile_cap)
     if args.resolve_upl:
         from lagrangian_microbes_b200._lib import LM_OPT_RESOLVE_UPL
         sim.engine.set_option(LM_OPT_RESOLVE_UPL, args.resolve_upl)

@@ -215,7 +215,10 @@ int lm_state_view(lm_handle h, float **lon, float **lat, int8_t **species, int32
 
 /* ---- status -------------------------------------------------------------------------------- */
 /* Synchronise the stream and copy the device counters; returns LM_ENOSPC if pairs overflowed the
- * emit capacity, LM_OK otherwise. */
+ * emit capacity (or another capacity: hand-off, exchange buffers), LM_ESTATE for misrouted particles, LM_OK otherwise.
+ * Faults are STICKY: a step latches the faults of the previous step before it zeroes the counters, so a fault in any
+ * step since the last lm_sync_stats / lm_reset_stats is reported here (once), whether or not that step asked for
+ * LM_STEP_STATS. */
 int lm_sync_stats(lm_handle h, lm_stats *out /* host */, void *stream);
 /* Zero the device counters (lm_step and the pair-search operators do this themselves). */
 int lm_reset_stats(lm_handle h, void *stream);

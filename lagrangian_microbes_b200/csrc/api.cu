@@ -72,6 +72,7 @@ int lm_destroy(lm_handle h)
     }
     cudaFree(h->keys); cudaFree(h->slots); cudaFree(h->cell_count); cudaFree(h->cell_start_buf[0]); cudaFree(h->cell_start_buf[1]);
     cudaFree(h->n_pairs_snap);
+    cudaFree(h->sticky);
     cudaFree(h->sp_snap); cudaFree(h->tile_scratch); cudaFree(h->tile_scratch_used);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_find_done) cudaEventDestroy(h->ev_find_done);
@@ -143,6 +144,8 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_pos_scattered, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_sp_ready, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaMemset(h->n_pairs_snap, 0, sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && dev_alloc(&h->sticky, 1);
+    if (ok) ok = cudaMemset(h->sticky, 0, sizeof(unsigned int)) == cudaSuccess;
     for (int k = 0; ok && k < 2; ++k) {
         ok = ok && cudaEventCreateWithFlags(&h->ev_scatter[k], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming) == cudaSuccess;
@@ -282,8 +285,28 @@ int lm_get_grid(lm_handle h, lm_grid *g)
     return LM_OK;
 }
 
+// Capacity faults of a step must not vanish with the counters the next step zeroes: before every reset they are
+// latched into h->sticky (bit 0 pair list truncated | 1 RPS hand-off overflowed: species invalid | 2 cell too full for
+// the packed counters | 3 migration / ghost buffer overflow | 4 misrouted particles), which only lm_sync_stats (which
+// reports them) and lm_reset_stats clear.
+__global__ void latch_faults_kernel(const Counters *c, unsigned int *sticky, long long emit_cap, long long rps_cap)
+{
+    unsigned int f = 0;
+    if (emit_cap >= 0 && (long long)c->n_pairs > emit_cap) f |= 1u;
+    if (rps_cap >= 0 && (long long)c->n_pairs > rps_cap) f |= 2u;
+    if (c->n_overflow) f |= 4u;
+    if (c->n_xfer_overflow) f |= 8u;
+    if (c->n_misrouted) f |= 16u;
+    if (f) atomicOr(sticky, f);
+}
+
 static int reset_counters(lm_handle h, cudaStream_t s)
 {
+    if (!h->ctr_reported) {          // counters nobody has read through lm_sync_stats: keep their faults
+        latch_faults_kernel<<<1, 1, 0, s>>>(h->ctr, h->sticky, (long long)h->emit_cap, (long long)h->rps_cap);
+        LM_CUDA(cudaGetLastError());
+    }
+    h->ctr_reported = false;
     LM_CUDA(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), s));
     return LM_OK;
 }
@@ -324,7 +347,9 @@ int lm_reset_stats(lm_handle h, void *stream)
     if (!h) return LM_EINVAL;
     LM_CUDA(cudaSetDevice(h->device));
     h->emit_cap = h->rps_cap = -1;
-    return reset_counters(h, as_stream(stream));
+    LM_CUDA(cudaMemsetAsync(h->ctr, 0, sizeof(Counters), as_stream(stream)));
+    LM_CUDA(cudaMemsetAsync(h->sticky, 0, sizeof(unsigned int), as_stream(stream)));
+    return LM_OK;
 }
 
 int lm_diffuse(lm_handle h, float *lon, float *lat, int64_t n, double amp_deg, uint64_t seed, uint64_t step,
@@ -771,8 +796,12 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
     LM_CUDA(cudaSetDevice(h->device));
     { const int rcj = join_side(h, as_stream(stream)); if (rcj) return rcj; }
     Counters c;
+    unsigned int sticky = 0;
     LM_CUDA(cudaMemcpyAsync(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost, as_stream(stream)));
+    LM_CUDA(cudaMemcpyAsync(&sticky, h->sticky, sizeof(sticky), cudaMemcpyDeviceToHost, as_stream(stream)));
+    LM_CUDA(cudaMemsetAsync(h->sticky, 0, sizeof(unsigned int), as_stream(stream)));      // reported once
     LM_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    h->ctr_reported = true;
     if (out) {
         out->n_pairs = (int64_t)c.n_pairs;
         out->n_out_of_bounds = (int64_t)c.n_oob;
@@ -792,6 +821,9 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
     if (h->emit_cap >= 0 && (int64_t)c.n_pairs > h->emit_cap) return LM_ENOSPC;   // pair list truncated
     if (h->rps_cap >= 0 && (int64_t)c.n_pairs > h->rps_cap) return LM_ENOSPC;     // RPS hand-off buffer too small: species invalid
     if (c.n_overflow) return LM_ENOSPC;
+    // faults of EARLIER steps whose counters have been zeroed since (steps run without LM_STEP_STATS in between)
+    if (sticky & (1u | 2u | 4u | 8u)) return LM_ENOSPC;
+    if (sticky & 16u) return LM_ESTATE;
     return LM_OK;
 }
 

@@ -75,6 +75,8 @@ struct lm_handle_s {
     int32_t *block_sums;   // [ceil(max_cells / SCAN_TILE) + 1]
     // counters
     lm::Counters *ctr;     // device
+    bool ctr_reported;     // the counters' current contents have been returned by lm_sync_stats
+    unsigned int *sticky;  // device: capacity faults latched before every counter reset (csrc/api.cu::latch_faults_kernel)
     int64_t emit_cap;      // capacity of the pair buffer passed to the last call (-1: none)
     int64_t rps_cap;       // capacity of hits[] if the last call resolved RPS (-1: it did not)
     // pair search -> resolver hand-off

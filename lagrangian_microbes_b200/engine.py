@@ -6,6 +6,7 @@ an ``Engine`` without a CUDA device raises.
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -68,6 +69,12 @@ def _f32(t, n=None):
 class Engine:
     """One lm_handle bound to one CUDA device."""
 
+    # LM_OPT_INTERACT_MODE / LM_OPT_ADVECT_MODE a new Engine starts with (None: the library's defaults -- fused tile
+    # kernel, bit-faithful RK4).  Class attributes so that a test module or a benchmark can pin the whole stack
+    # (FusedSimulation, StripSet, the drop-in classes) to one path.
+    DEFAULT_INTERACT_MODE = None
+    DEFAULT_ADVECT_MODE = None
+
     def __init__(self, max_particles, max_cells=None, max_pairs=0, device=None):
         if not torch.cuda.is_available():
             raise RuntimeError("lagrangian_microbes_b200 needs a CUDA device: the hot path has no CPU fallback")
@@ -82,6 +89,14 @@ class Engine:
         self.h = h
         self._field = None            # keeps the borrowed field tensors alive
         self._n_pairs_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.interact_mode = 1
+        # class attribute, else the environment (LM_INTERACT_MODE / LM_ADVECT_MODE: A/B runs of the tools), else the library's
+        im = self.DEFAULT_INTERACT_MODE if self.DEFAULT_INTERACT_MODE is not None else os.environ.get("LM_INTERACT_MODE")
+        am = self.DEFAULT_ADVECT_MODE if self.DEFAULT_ADVECT_MODE is not None else os.environ.get("LM_ADVECT_MODE")
+        if im is not None:
+            self.set_option(_lib.LM_OPT_INTERACT_MODE, int(im))
+        if am is not None:
+            self.set_option(_lib.LM_OPT_ADVECT_MODE, int(am))
 
     def close(self):
         if getattr(self, "h", None):
@@ -287,6 +302,8 @@ class Engine:
 
     def set_option(self, option, value):
         check(self.L.lm_set_option(self.h, int(option), int(value)), "lm_set_option")
+        if int(option) == _lib.LM_OPT_INTERACT_MODE:
+            self.interact_mode = int(value)
 
     def set_norm(self, p):
         """The Minkowski norm of the radius query: p = 1, 2 (default) or math.inf (``query_pairs(r, p)``)."""

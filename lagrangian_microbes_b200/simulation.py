@@ -99,8 +99,8 @@ class FusedSimulation:
         if max_cells is None:
             max_cells = int(max(4 * cells_per_particle * n, 1 << 20))
         if pair_capacity is None:
-            pair_capacity = max(1 << 20, 8 * n)
-        # max_pairs sizes the pair-search -> resolver hand-off buffer (4 B per pair per step)
+            pair_capacity = max(1 << 20, 24 * n)                 # BASELINE config 3 reaches 19 pairs per microbe
+        # max_pairs sizes the pair-search -> resolver hand-off buffer of the round-1 pipeline (4 B per pair per step)
         self.engine = Engine(max_particles=n, max_cells=max_cells, max_pairs=int(pair_capacity) if interact else 0,
                              device=device)
         self.engine.set_norm(interaction_norm)                   # query_pairs(r, p=interaction_norm)
@@ -121,8 +121,6 @@ class FusedSimulation:
 
         self.emit_pairs = bool(emit_pairs) and self.interact
         if self.emit_pairs:
-            if pair_capacity is None:
-                pair_capacity = max(1 << 20, 8 * n)
             self.pairs = torch.empty((int(pair_capacity), 2), dtype=torch.int32, device=dev)
         else:
             self.pairs = None
@@ -195,9 +193,16 @@ class FusedSimulation:
             return st
         return None
 
+    def check_faults(self):
+        """Raise if any step since the last check overflowed a capacity (pair list truncated, hand-off or exchange buffer
+        too small) -- the device latches such faults across steps (lm_sync_stats), so steps run without ``check=True``
+        cannot lose them.  Synchronises."""
+        self.engine.sync_stats()
+
     def run(self, n_steps):
         for _ in range(n_steps):
             self.step()
+        self.check_faults()
 
     def run_to_file(self, output_dir, start_time, end_time, dt, stride=1, filename="microbe_data.nc", packed=False):
         """The reference's end product in one pass: ``(end_time - start_time) // dt`` fused steps, their per-step
@@ -216,6 +221,7 @@ class FusedSimulation:
         asm = lmio.RecordAssembler(self.n, n_steps, start_time, dt, stride)
         if packed:
             self._run_packed(asm, n_steps)
+            self.check_faults()
             path = asm.write(output_dir, filename)
             return path, np.stack([(asm.species == s).sum(axis=0) for s in (1, 2, 3)], axis=1)
         rec = [tuple(torch.empty(self.n, dtype=t).pin_memory() for t in (torch.float32, torch.float32, torch.int8))
@@ -238,6 +244,7 @@ class FusedSimulation:
             else:
                 self.step()
         drain()
+        self.check_faults()                              # before anything is written: a truncated step must not reach the file
         path = asm.write(output_dir, filename)
         counts = np.stack([(asm.species == s).sum(axis=0) for s in (1, 2, 3)], axis=1)
         return path, counts

@@ -13,7 +13,7 @@ by all GPUs, and exchanges with its two neighbours only:
     lm_step_interact_end     "gret"  the same species after phase 8  south -> north
     lm_step_finish
 
-Strip boundaries sit on even cell rows, which makes the pair set, the species and the positions
+Strip boundaries sit on multiples of 16 cell rows (the tile height of the fused interaction pass), which makes the pair set, the species and the positions
 bit-identical to a single GPU running the same grid (tests/test_gpu_strips.py).
 
 ``StripSet`` drives any number of strips held by THIS process: one per process under torchrun
@@ -46,51 +46,61 @@ def cell_rows(lat, grid):
     return np.minimum(q, grid.ncy - 1).astype(np.int64)
 
 
-def strip_edges(row_counts, n_strips, max_rows=None):
-    """Row boundaries e[0] = 0 < e[1] < ... < e[G] = ncy, all interior ones EVEN, splitting the particles of
-    ``row_counts`` (particles per global cell row) as evenly as the rows allow.  Every strip gets at least two
-    rows and (optionally) at most ``max_rows``."""
+ROW_ALIGN = _lib.LM_TILE_H      # strip boundaries sit on multiples of the tile height of the fused interaction pass
+
+
+def _snap(e, align):
+    return int(e) - int(e) % align
+
+
+def strip_edges(row_counts, n_strips, max_rows=None, align=ROW_ALIGN):
+    """Row boundaries e[0] = 0 < e[1] < ... < e[G] = ncy, all interior ones multiples of ``align`` (the tile height of
+    the fused interaction pass; 16 is also even, which is all the round-1 pipeline needs), splitting the particles of
+    ``row_counts`` (particles per global cell row) as evenly as the rows allow.  Every strip gets at least
+    ``align`` rows and (optionally) at most ``max_rows``."""
     row_counts = np.asarray(row_counts, dtype=np.int64)
     ncy, G = int(row_counts.size), int(n_strips)
-    if G < 1 or ncy < 2 * G:
-        raise ValueError("need at least two cell rows per strip (ncy=%d, strips=%d)" % (ncy, G))
+    if G < 1 or (G > 1 and ncy < align * (G - 1) + 2):
+        raise ValueError("need at least %d cell rows per strip (ncy=%d, strips=%d)" % (align, ncy, G))
     cum = np.concatenate(([0], np.cumsum(row_counts)))   # cum[e] = particles in rows < e
     total = int(cum[-1])
     edges = [0]
     for g in range(1, G):
         target = total * g / float(G)
         e = int(np.searchsorted(cum, target, side="left"))
-        # nearest even row to the ideal cut
-        lo_e, hi_e = e - (e & 1), e + (e & 1)
+        # nearest aligned row to the ideal cut
+        lo_e = _snap(e, align)
+        hi_e = lo_e if lo_e == e else lo_e + align
         e = lo_e if abs(cum[min(lo_e, ncy)] - target) <= abs(cum[min(hi_e, ncy)] - target) else hi_e
-        lo = edges[-1] + 2
-        hi = ncy - 2 * (G - g)
-        hi -= hi & 1
+        lo = edges[-1] + align
+        hi = _snap(ncy - 2 - align * (G - g - 1), align)          # the strips above keep >= align rows, the last >= 2
         if max_rows is not None:
-            hi = min(hi, edges[-1] + (max_rows - (max_rows & 1)))
+            hi = min(hi, edges[-1] + _snap(max_rows, align))
             # leave the remaining strips enough room under max_rows as well
             need = ncy - max_rows * (G - g)
-            lo = max(lo, need + (need & 1))
+            lo = max(lo, need + (-need) % align)
         e = max(lo, min(e, hi))
         edges.append(e)
     edges.append(ncy)
+    if any(b <= a for a, b in zip(edges[:-1], edges[1:])):
+        raise ValueError("strips do not fit: %s (ncy=%d, align=%d)" % (edges, ncy, align))
     if max_rows is not None and max(b - a for a, b in zip(edges[:-1], edges[1:])) > max_rows:
         raise ValueError("strips do not fit max_rows=%d: %s" % (max_rows, edges))
     return edges
 
 
-def remap_edges(old_grid, old_edges, new_grid):
-    """Strip boundaries on a re-fitted grid: every interior boundary keeps (nearly) its latitude, snapped to an
-    even row of the new grid, every strip keeps at least two rows."""
+def remap_edges(old_grid, old_edges, new_grid, align=ROW_ALIGN):
+    """Strip boundaries on a re-fitted grid: every interior boundary keeps (nearly) its latitude, snapped to a
+    multiple of ``align`` rows of the new grid, every strip keeps at least ``align`` rows."""
     G = len(old_edges) - 1
-    if new_grid.ncy < 2 * G:
+    if G > 1 and new_grid.ncy < align * (G - 1) + 2:
         raise ValueError("the cell grid has %d rows: too few for %d strips" % (new_grid.ncy, G))
     edges = [0]
     for k in range(1, G):
         lat_edge = old_grid.y0 + old_edges[k] / old_grid.inv_h
-        e = 2 * int(round((lat_edge - new_grid.y0) * new_grid.inv_h / 2.0))
-        hi = new_grid.ncy - 2 * (G - k)
-        e = max(edges[-1] + 2, min(e, hi - (hi & 1)))
+        e = align * int(round((lat_edge - new_grid.y0) * new_grid.inv_h / float(align)))
+        hi = _snap(new_grid.ncy - 2 - align * (G - k - 1), align)
+        e = max(edges[-1] + align, min(e, hi))
         edges.append(e)
     edges.append(new_grid.ncy)
     return edges

@@ -231,3 +231,45 @@ def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
     slot = np.where(same, slot_s, slot_x)
     order = np.lexsort((slot, rnd, unit, phase))
     return pairs[order], phase[order]
+
+
+def canonical_order(pairs, lon32, lat32, grid, mode=1):
+    """The device's canonical pair order: LM_OPT_INTERACT_MODE 1 (default, fused tile kernel) = tile-round order,
+    0 (round-1 pipeline) = cell-phase order."""
+    if mode == 1:
+        return tile_round_order(pairs, lon32, lat32, grid)
+    return cell_phase_order(pairs, lon32, lat32, grid)
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's pair function at the reference's COST (bench.py --impl reference times it).
+# ---------------------------------------------------------------------------------------------
+def reference_pair_interaction(parameters, microbe_properties, p1, p2):
+    """interactions.py:13-40 restated with the reference's own signature and work per call: the species array and the
+    three probabilities are looked up in the dicts on every call and the draw is ``np.random.rand()`` (NumPy's global
+    MT19937), taken only when the species differ -- so a loop over it costs what the reference's loop
+    (interaction_simulator.py:104-105) costs, which ``rps_pair`` above (draw injected, probabilities as arguments)
+    would understate.  /root/reference cannot travel to the GPU box, hence a restatement; tests/test_oracle_rps.py
+    checks it call by call against the unmodified function in this container."""
+    species = microbe_properties["species"]
+    pRS, pPR, pSP = parameters["pRS"], parameters["pPR"], parameters["pSP"]
+    if species[p1] != species[p2]:
+        s1, s2 = species[p1], species[p2]
+        r = np.random.rand()
+        winner = None
+        if s1 == ROCK and s2 == SCISSORS:
+            winner = p1 if r < pRS else p2
+        elif s1 == ROCK and s2 == PAPER:
+            winner = p2 if r < pPR else p1
+        elif s1 == PAPER and s2 == ROCK:
+            winner = p1 if r < pPR else p2
+        elif s1 == PAPER and s2 == SCISSORS:
+            winner = p2 if r < pSP else p1
+        elif s1 == SCISSORS and s2 == ROCK:
+            winner = p2 if r < pRS else p1
+        elif s1 == SCISSORS and s2 == PAPER:
+            winner = p1 if r < pSP else p2
+        if winner == p1:
+            species[p2] = species[p1]
+        elif winner == p2:
+            species[p1] = species[p2]

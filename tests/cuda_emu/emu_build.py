@@ -82,7 +82,7 @@ def build_tsan(sanitizer="thread", force=False):
     cpps = []
     for f in SOURCES:
         text, _ = transform(open(os.path.join(CSRC, f)).read())
-        path = os.path.join(OUT, f.replace(".cu", "_san.cpp"))
+        path = os.path.join(OUT, f.replace(".cu", "_san_%s.cpp" % sanitizer.split(",")[0]))
         with open(path, "w") as fh:
             fh.write(text)
         cpps.append(path)

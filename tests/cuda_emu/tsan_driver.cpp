@@ -47,6 +47,7 @@ int main(int argc, char **argv)
         lm_handle hd = nullptr;
         CHECK(lm_create(&hd, 0, n, 1 << 14, 60 * n));
         CHECK(lm_set_grid(hd, &grid));
+        CHECK(lm_set_option(hd, LM_OPT_INTERACT_MODE, 0));             // the round-1 pipeline and its resolvers
         CHECK(lm_set_option(hd, LM_OPT_RESOLVE_MODE, o[0]));
         CHECK(lm_set_option(hd, LM_OPT_RESOLVE_TILE_SMEM, o[1]));
         CHECK(lm_set_option(hd, LM_OPT_RESOLVE_MEGA_MIN, o[2]));
@@ -63,6 +64,31 @@ int main(int argc, char **argv)
         if (ref.empty()) ref = sp;
         else if (memcmp(ref.data(), sp.data(), n) != 0) { fprintf(stderr, "resolvers disagree\n"); return 2; }
         CHECK(lm_destroy(hd));
+    }
+
+    // the fused tile kernel (LM_OPT_INTERACT_MODE = 1, the default): shared-memory tiles with the whole-warp and whole-CTA
+    // paths, draws one lane at a time, tiles too full for shared memory (global-memory path); all must agree
+    {
+        std::vector<int8_t> ref1;
+        const long long topts[3][2] = {{0, 0}, {0, 1}, {256, 32}};       // LM_OPT_TILE_CAP, LM_OPT_DRAW_BATCH
+        int k_opt = 0;
+        for (auto &o : topts) {
+            if (quick && ++k_opt == 2) continue;
+            lm_handle hd = nullptr;
+            CHECK(lm_create(&hd, 0, n, 1 << 14, 60 * n));
+            CHECK(lm_set_grid(hd, &grid));
+            CHECK(lm_set_option(hd, LM_OPT_TILE_CAP, o[0]));
+            CHECK(lm_set_option(hd, LM_OPT_DRAW_BATCH, o[1]));
+            std::vector<int8_t> sp(sp0);
+            std::vector<int32_t> pairs(2 * 60 * n);
+            CHECK(lm_interact_rps(hd, lon.data(), lat.data(), sp.data(), n, r, &prm, pairs.data(), 60 * n, nullptr, nullptr));
+            lm_stats st;
+            CHECK(lm_sync_stats(hd, &st, nullptr));
+            printf("fused tile kernel, tile cap %lld, draw batch %lld: %lld pairs\n", o[0], o[1], (long long)st.n_pairs);
+            if (ref1.empty()) ref1 = sp;
+            else if (memcmp(ref1.data(), sp.data(), n) != 0) { fprintf(stderr, "fused tile kernel: settings disagree\n"); return 2; }
+            CHECK(lm_destroy(hd));
+        }
     }
 
     // explicit-order resolver (mark / fire rounds with 64-bit atomicMin) on the pair list of a search, other norms
@@ -98,13 +124,15 @@ int main(int argc, char **argv)
         Uf[(t * Y + y) * X + x] = 0.2f * (float)(y - Y / 2) / Y + 0.02f * t;
         Vf[(t * Y + y) * X + x] = -0.2f * (float)(x - X / 2) / X;
     }
-    for (int mode = 0; mode < 2; ++mode) {
+    for (int mode = 0; mode < 3; ++mode) {                                 // 0, 1: round-1 pipeline, nine phases / tiled; 2: fused tile kernel
         lm_handle hd = nullptr;
         CHECK(lm_create(&hd, 0, n, 1 << 14, 60 * n));
         CHECK(lm_set_field(hd, Uf.data(), Vf.data(), glon.data(), glat.data(), T, Y, X));
         lm_grid g2 = {200.9, 31.9, 1.0 / h, ncx + 20, ncy + 20};
         CHECK(lm_set_grid(hd, &g2));
-        CHECK(lm_set_option(hd, LM_OPT_RESOLVE_MODE, mode));
+        CHECK(lm_set_option(hd, LM_OPT_INTERACT_MODE, mode == 2));
+        CHECK(lm_set_option(hd, LM_OPT_ADVECT_MODE, mode == 2));
+        if (mode < 2) CHECK(lm_set_option(hd, LM_OPT_RESOLVE_MODE, mode));
         CHECK(lm_state_set(hd, lon.data(), lat.data(), sp0.data(), nullptr, n, nullptr));
         std::vector<int32_t> pairs(2 * 60 * n);
         for (int step = 0; step < (quick ? 1 : 3); ++step) {
@@ -145,7 +173,7 @@ int main(int argc, char **argv)
             CHECK(lm_set_field(hs[s], Uf.data(), Vf.data(), glon.data(), glat.data(), T, Y, X));
             CHECK(lm_strip_alloc(hs[s], 1024, 1024, g2.ncx + 8));
             CHECK(lm_set_grid(hs[s], &g2));
-            CHECK(lm_set_option(hs[s], LM_OPT_RESOLVE_MODE, s));                 // one strip per resolver
+            // (fused tile kernel on both strips: the default)
             lm_strip st = {s ? 16 : 0, s ? 24 : 16, s, 1 - s};
             CHECK(lm_set_strip(hs[s], &st));
             CHECK(lm_strip_buffers_get(hs[s], &bf[s]));

@@ -12,7 +12,10 @@ What is pinned by what:
                per pair rather than per draw.  Two orders per case:
                  *_ref   the CPython-set iteration order of ``cKDTree.query_pairs`` -- literally
                          what the reference iterates over;
-                 *_cell  the canonical cell-phase order of the fused device path for a fixed grid.
+                 *_cell  the canonical cell-phase order of the round-1 device pipeline (LM_OPT_INTERACT_MODE = 0)
+                         for a fixed grid;
+                 *_tile  the canonical tile-round order of the fused tile kernel (the default device path,
+                         oracle/rps.py::tile_round_order) for the same grid.
   pairs_*.npz  pair sets from ``cKDTree(...).query_pairs(r, p=2)`` -- the library call the
                reference makes (interaction_simulator.py:93,98).
   rk4_*.npz    outputs of oracle/rk4.py (regression only -- parity unpinned, see that file).
@@ -71,14 +74,20 @@ def rps_case(name, lon, lat, species0, r, params, seed, step, grid_k=1):
     u_cell = philox.pair_uniforms(cell_order[:, 0], cell_order[:, 1], step, seed)
     species_cell = run_reference_rps(species0, [tuple(map(int, p)) for p in cell_order], u_cell, params)
 
+    tile_order, _ = orps.tile_round_order(opairs.pairs_from_set(pair_set), lon, lat, grid)
+    u_tile = philox.pair_uniforms(tile_order[:, 0], tile_order[:, 1], step, seed)
+    species_tile = run_reference_rps(species0, [tuple(map(int, p)) for p in tile_order], u_tile, params)
+
     np.savez_compressed(os.path.join(HERE, name + ".npz"), lon=lon, lat=lat, r=np.float64(r), species0=species0,
+                        pairs_tile_order=tile_order.astype(np.int32), species_tile=species_tile,
                         pRS=params["pRS"], pPR=params["pPR"], pSP=params["pSP"], seed=np.int64(seed),
                         step=np.int64(step), pairs_ref_order=ref_order.astype(np.int32), u_ref=u_ref,
                         species_ref=species_ref, grid=np.array([grid["x0"], grid["y0"], grid["inv_h"]]),
                         grid_n=np.array([grid["ncx"], grid["ncy"]], dtype=np.int32),
                         pairs_cell_order=cell_order.astype(np.int32), species_cell=species_cell)
-    print("%-16s N=%d P=%d changed(ref)=%d changed(cell)=%d" % (
-        name, lon.size, ref_order.shape[0], int((species_ref != species0).sum()), int((species_cell != species0).sum())))
+    print("%-16s N=%d P=%d changed(ref)=%d changed(cell)=%d changed(tile)=%d" % (
+        name, lon.size, ref_order.shape[0], int((species_ref != species0).sum()), int((species_cell != species0).sum()),
+        int((species_tile != species0).sum())))
 
 
 def make_rps():

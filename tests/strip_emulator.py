@@ -4,9 +4,10 @@ Each emulated strip runs the five stages of include/lm_b200.h's staged step with
 compute (cKDTree pair query, the restated RPS loop) and the PRODUCT's host logic doing everything else:
 ``strips.strip_edges`` / ``strips.cell_rows`` for the partition, ``strips.EXCHANGES`` + a product transport
 (``DistTransport`` over gloo, or ``LocalTransport``) for the messages.  The claim under test is the one the
-CUDA path relies on: with strip boundaries on even cell rows, "phases 0-5, hand the first
-row's species south, phases 6-8, hand them back" equals the single-domain sequential loop in the canonical
-cell-phase order -- for any number of strips.
+CUDA path relies on: with strip boundaries on multiples of the tile height, "phases 0-11 (inside tiles
+and across vertical tile boundaries), hand the first row's species south, phases 12-14 (across horizontal tile
+boundaries), hand them back" equals the single-domain sequential loop in the canonical tile-round order -- for any
+number of strips.
 """
 import numpy as np
 import torch
@@ -107,33 +108,16 @@ class NumpyStrip:
         self.sp_all = np.concatenate((self.sp, np.zeros(self.n_ghost, np.int8)))
         loc = opairs.query_pairs_reference_array(lon, lat, RADIUS).reshape(-1, 2)
         loc = loc[(loc[:, 0] < n) | (loc[:, 1] < n)]              # ghost-ghost pairs belong to the strip to the north
-        order, phase = orps.cell_phase_order(loc, lon, lat, grid_dict(self.grid))
-        # the canonical order sorts by particle ID inside a unit, cell_phase_order by the local index: re-sort
-        self.order, self.phase = self._canonical(order, phase, lon, lat, ids)
+        # the tile-round order ranks the microbes of a cell by storage index; storage is in (cell, id) order on both
+        # sides of the boundary (the ghost row arrives sorted), so that is the rank by particle id the device uses
+        self.order, self.phase = orps.tile_round_order(loc, lon, lat, grid_dict(self.grid))
         gi, gj = ids[self.order[:, 0]].astype(np.int64), ids[self.order[:, 1]].astype(np.int64)
         self.u = philox.pair_uniforms(np.minimum(gi, gj), np.maximum(gi, gj), step, seed)
         self.pairs = np.stack((np.minimum(gi, gj), np.maximum(gi, gj)), -1)
-        lo = self.phase <= 5
+        lo = self.phase <= 11             # the tile phases and the vertical-boundary phases
         self.sp_all, _ = orps.rps_sequential_c(self.sp_all, self.order[lo], self.u[lo], *P_RPS)
         if self.index > 0:
             self._pack(self.buffers["gsp_send"], self.sp_all[:self.n_row0])
-
-    def _canonical(self, order, phase, lon, lat, ids):
-        """cell_phase_order keys on the indices it is given; the device keys on particle ids.  Redo the sort
-        with ids as the within-unit key (anchor id, other id)."""
-        g = self.grid
-        cx = opairs.cell_index(lon, g.x0, g.inv_h, g.ncx)
-        cy = opairs.cell_index(lat, g.y0, g.inv_h, g.ncy)
-        i, j = order[:, 0], order[:, 1]
-        j_anchor = (cy[j] < cy[i]) | ((cy[j] == cy[i]) & (cx[j] < cx[i]))
-        same = (cx[i] == cx[j]) & (cy[i] == cy[j])
-        a = np.where(j_anchor, j, i)
-        b = np.where(j_anchor, i, j)
-        swap = same & (ids[a] > ids[b])
-        a, b = np.where(swap, b, a), np.where(swap, a, b)
-        unit = cy[a].astype(np.int64) * g.ncx + cx[a]
-        k = np.lexsort((ids[b], ids[a], unit, phase))
-        return np.stack((a, b), -1)[k], phase[k]
 
     def interact_end(self):
         n = self.lon.size
@@ -141,7 +125,7 @@ class NumpyStrip:
             (gsp,) = self._unpack(self.buffers["gsp_recv"], (np.int8,))
             assert gsp.size == self.n_ghost
             self.sp_all[n:] = gsp
-        hi = self.phase >= 6
+        hi = self.phase >= 12             # the horizontal-boundary phases: the only ones that cross a strip boundary
         self.sp_all, _ = orps.rps_sequential_c(self.sp_all, self.order[hi], self.u[hi], *P_RPS)
         if self.index < self.n_strips - 1:
             self._pack(self.buffers["gret_send"], self.sp_all[n:])
@@ -184,7 +168,7 @@ def run_single(grid, lon, lat, sp, ids, n_steps, seed):
         dx, dy = displacement(ids, step)
         lon, lat = (lon + dx).astype(np.float32), (lat + dy).astype(np.float32)
         prs = opairs.query_pairs_reference_array(lon, lat, RADIUS)
-        order, _ = orps.cell_phase_order(prs, lon, lat, grid_dict(grid))
+        order, _ = orps.tile_round_order(prs, lon, lat, grid_dict(grid))
         u = philox.pair_uniforms(order[:, 0], order[:, 1], step, seed)
         sp, _ = orps.rps_sequential_c(sp, order, u, *P_RPS)
         out.append((lon.copy(), lat.copy(), sp.copy(), opairs.sort_pairs(prs)))

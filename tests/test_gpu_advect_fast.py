@@ -1,0 +1,99 @@
+"""LM_OPT_ADVECT_MODE = 1 (float32 FMA arithmetic, MUFU reciprocal / cosine) against the float64 RK4 restatement
+(oracle/rk4.py, restating parcels' AdvectionRK4 -- /root/reference/particle_advecter.py:222-223 delegates to it): north_star's
+bar is 1e-6 relative on positions.  Checked step by step from identical inputs over the 130-step golden (irregular time
+axis, a snapshot boundary, land, particles on grid lines and out of bounds), over BASELINE config 1's 24 steps accumulated
+(the fast and the bit-faithful mode each run their own trajectory), and through the fused step (lm_step)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import rk4 as ork4
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+TOL = 1e-6          # north_star: positions within 1e-6 relative (fp64) of the reference RK4 on the same field
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_fast_rk4_single_steps_within_tolerance_over_130_steps(engine_factory):
+    from lagrangian_microbes_b200._lib import LM_OPT_ADVECT_MODE
+    from lagrangian_microbes_b200.particle_advecter import StageClock
+    g = golden("rk4_small.npz")
+    fs = ork4.FieldSet(g["grid_lon"], g["grid_lat"], g["grid_time"], g["u"], g["v"])
+    n = g["lon0"].size
+    eng = engine_factory(max_particles=n, max_cells=1024)
+    eng.set_option(LM_OPT_ADVECT_MODE, 1)
+    eng.set_field(dev(fs.u), dev(fs.v), dev(fs.lon), dev(fs.lat))
+    lon, lat = dev(g["lon0"].copy()), dev(g["lat0"].copy())
+    clock = StageClock(fs.time)
+    t, ti, worst, worst_ulp = 0.0, 0, 0.0, 0.0
+    eng.reset_stats()
+    for step in range(int(g["steps"])):
+        prev_lon, prev_lat = lon.cpu().numpy(), lat.cpu().numpy()
+        eng.advect_rk4(lon, lat, clock.next_step(3600.0), 3600.0)
+        a64, b64, ti_new, _ = ork4.rk4_step_f64(fs, prev_lon, prev_lat, t, 3600.0, ti)
+        gl, ga = lon.cpu().numpy(), lat.cpu().numpy()
+        # a particle within one step of the grid edge can be out of bounds in one precision and not in the other
+        ok = ((gl != prev_lon) | (ga != prev_lat)) & ((a64 != prev_lon) | (b64 != prev_lat))
+        worst = max(worst, np.max(np.abs(gl - a64)[ok] / np.abs(a64)[ok]), np.max(np.abs(ga - b64)[ok] / np.abs(b64)[ok]))
+        worst_ulp = max(worst_ulp, np.max(np.abs(gl - a64)[ok] / np.spacing(np.abs(a64[ok]).astype(np.float32))))
+        t, ti = t + 3600.0, ti_new
+    print("fast RK4: worst relative error vs float64 over %d single steps %.3g (%.2f float32 ulps of longitude)"
+          % (int(g["steps"]), worst, worst_ulp))
+    assert worst < TOL
+    assert worst_ulp <= 1.5            # the error IS the rounding of the float32 state: the displacement arithmetic adds < 1 ulp
+    assert eng.sync_stats().n_out_of_bounds >= 5 * int(g["steps"])      # same out-of-bounds policy
+
+
+def test_fast_rk4_config1_24_steps_accumulated():
+    """BASELINE config 1: 490,000 microbes on the 700 x 700 lattice, steady field, 24 hourly steps -- the fast mode's own
+    trajectory against the float64 oracle's own trajectory (errors accumulate), still within 1e-6 relative."""
+    import lagrangian_microbes_b200 as lm
+    from lagrangian_microbes_b200 import velocity_fields
+    from lagrangian_microbes_b200._lib import LM_OPT_ADVECT_MODE
+    from lagrangian_microbes_b200.particle_advecter import HostFieldSet
+    from lagrangian_microbes_b200.simulation import FusedSimulation
+    n = 490_000
+    velocity_fields.configure_synthetic(kind="steady", seed=0, n_modes=64, rms_speed=0.2)
+    try:
+        hfs = HostFieldSet(velocity_fields.oscar_dataset(2017))
+        fs = ork4.FieldSet(hfs.lon, hfs.lat, hfs.time, hfs.u, hfs.v)
+        lons, lats = lm.uniform_particle_locations(n, 25, 35, 205, 215)
+        sp = np.ones(n, dtype=np.int8)
+        sims = {}
+        for mode in (0, 1):
+            sims[mode] = FusedSimulation(lons, lats, sp, 0.01, 0.55, 0.55, 0.55, hfs, dt_seconds=3600.0, seed=0, emit_pairs=False,
+                                         interact=False)
+            sims[mode].engine.set_option(LM_OPT_ADVECT_MODE, mode)
+        l64, a64 = lons.astype(np.float32).astype(np.float64), lats.astype(np.float32).astype(np.float64)
+        t, ti = 0.0, 0
+        for step in range(24):
+            for s in sims.values():
+                s.step()
+            l64, a64, ti, _ = ork4.rk4_step_f64(fs, l64, a64, t, 3600.0, ti)
+            t += 3600.0
+        err = {}
+        for mode, s in sims.items():
+            gl, ga, _ = s.download()
+            err[mode] = max(np.max(np.abs(gl - l64) / np.abs(l64)), np.max(np.abs(ga - a64) / np.abs(a64)))
+        print("config 1, 24 steps accumulated, relative error vs the float64 trajectory: bit-faithful mode %.3g, fast mode %.3g"
+              % (err[0], err[1]))
+        assert err[1] < TOL and err[0] < TOL
+    finally:
+        velocity_fields.configure_synthetic(kind="random_fourier", seed=0, n_modes=64, rms_speed=0.2)
+
+
+def test_option_validation(engine_factory):
+    from lagrangian_microbes_b200._lib import LM_EINVAL, LM_OPT_ADVECT_MODE, LM_OPT_DRAW_BATCH, LM_OPT_INTERACT_MODE, LmError
+    eng = engine_factory(max_particles=64, max_cells=1024)
+    for opt, bad in ((LM_OPT_ADVECT_MODE, 2), (LM_OPT_INTERACT_MODE, 2), (LM_OPT_DRAW_BATCH, 33), (LM_OPT_ADVECT_MODE, -1)):
+        with pytest.raises(LmError) as ei:
+            eng.set_option(opt, bad)
+        assert ei.value.code == LM_EINVAL
+    eng.set_option(LM_OPT_ADVECT_MODE, 1)
+    eng.set_option(LM_OPT_INTERACT_MODE, 0)

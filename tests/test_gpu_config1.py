@@ -54,7 +54,7 @@ def test_config1_24_steps_against_the_cpu_oracle():
             want_pairs = opairs.query_pairs_reference_array(gl, ga, r)
             assert st.n_pairs == want_pairs.shape[0], "step %d" % step
             assert np.array_equal(opairs.sort_pairs(sim.pairs[:st.n_pairs].cpu().numpy()), want_pairs)
-            order, _ = orps.cell_phase_order(want_pairs, gl, ga, grid)
+            order, _ = orps.canonical_order(want_pairs, gl, ga, grid)
             u = philox.pair_uniforms(order[:, 0], order[:, 1], step, seed)
             sp_ref, _ = orps.rps_sequential_c(sp_ref, order, u, *p)
             assert np.array_equal(gs, sp_ref), "species differ at step %d" % step

@@ -79,7 +79,7 @@ def test_reference_call_sequence_end_to_end(tmp_path):
             assert isim.pairs_found[i] == want_pairs.shape[0]
             grid = make_grid(float(lo.min()), float(lo.max()), float(la.min()), float(la.max()), r, N,
                              isim._engine.max_cells, margin=0.0).as_dict()
-            order, _ = orps.cell_phase_order(want_pairs, lo, la, grid)
+            order, _ = orps.canonical_order(want_pairs, lo, la, grid)
             u = philox.pair_uniforms(order[:, 0], order[:, 1], i, 9)
             sp, _ = orps.rps_sequential_c(sp, order, u, 0.55, 0.55, 0.55)
             assert np.array_equal(mdata["species"][:, i], sp)

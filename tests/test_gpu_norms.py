@@ -35,16 +35,18 @@ def gpu_pairs(eng, lon, lat, r, cap):
     return opairs.sort_pairs(out[:n_pairs].cpu().numpy())
 
 
-@pytest.mark.parametrize("mode", [0, 1])             # LM_OPT_FIND_PATH: auto / every warp on the two-pass path
+# (LM_OPT_INTERACT_MODE, LM_OPT_FIND_PATH): fused tile kernel | round-1 pair search, auto / every warp on the two-pass path
+@pytest.mark.parametrize("imode,mode", [(1, 0), (0, 0), (0, 1)])
 @pytest.mark.parametrize("tag,p", NORMS)
 @pytest.mark.parametrize("name", NORM_CASES)
-def test_find_pairs_other_norms_golden(engine_factory, name, tag, p, mode):
-    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH
+def test_find_pairs_other_norms_golden(engine_factory, name, tag, p, imode, mode):
+    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH, LM_OPT_INTERACT_MODE
     g = golden("pairs_norms.npz")
     lon, lat, r = g[name + "_lon"], g[name + "_lat"], float(g[name + "_r"])
     want = g["%s_pairs_%s" % (name, tag)].astype(np.int64)
     eng = engine_factory(max_particles=max(lon.size, 16), max_cells=1 << 20)
     eng.set_norm(p)
+    eng.set_option(LM_OPT_INTERACT_MODE, imode)
     eng.set_option(LM_OPT_FIND_PATH, mode)
     fit_grid(eng, lon, lat, r, margin=0.0)
     assert np.array_equal(gpu_pairs(eng, lon, lat, r, want.shape[0] + 64), want)
@@ -96,7 +98,7 @@ def test_interact_rps_other_norms_vs_oracle(engine_factory, p):
     st = eng.sync_stats()
     assert st.n_pairs == want.shape[0]
     assert np.array_equal(opairs.sort_pairs(out[:st.n_pairs].cpu().numpy()), want)
-    order, _ = orps.cell_phase_order(want, lon, lat, grid.as_dict())
+    order, _ = orps.canonical_order(want, lon, lat, grid.as_dict())
     u = philox.pair_uniforms(order[:, 0], order[:, 1], 31, 9)
     want_sp, draws = orps.rps_sequential_c(sp0.copy(), order, u, *prob)
     assert draws > 0 and np.array_equal(species.cpu().numpy(), want_sp)

@@ -144,7 +144,7 @@ def test_find_pairs_property_based(engine_factory):
         st = eng.sync_stats()
         assert st.n_pairs == want.shape[0]
         assert np.array_equal(opairs.sort_pairs(out[:st.n_pairs].cpu().numpy()), want)
-        order, _ = orps.cell_phase_order(want, lon, lat, grid.as_dict())
+        order, _ = orps.canonical_order(want, lon, lat, grid.as_dict())
         u = philox.pair_uniforms(order[:, 0], order[:, 1], seed % 7, seed % 1000)
         want_sp, _ = orps.rps_sequential_c(sp0.copy(), order, u, 0.3, 0.6, 0.9)
         assert np.array_equal(species.cpu().numpy(), want_sp)
@@ -171,7 +171,7 @@ def test_dense_uniform_cloud_fills_both_mask_words_and_the_fill_buffer(engine_fa
     st = eng.sync_stats()
     assert st.n_pairs == want.shape[0]
     assert np.array_equal(opairs.sort_pairs(out[:st.n_pairs].cpu().numpy()), want)
-    order, _ = orps.cell_phase_order(want, lon, lat, grid.as_dict())
+    order, _ = orps.canonical_order(want, lon, lat, grid.as_dict())
     u = philox.pair_uniforms(order[:, 0], order[:, 1], 2, 4)
     want_sp, _ = orps.rps_sequential_c(sp0.copy(), order, u, 0.55, 0.55, 0.55)
     assert np.array_equal(species.cpu().numpy(), want_sp)
@@ -237,18 +237,23 @@ def test_resolve_rps_lexicographic_and_reversed_orders(engine_factory, name):
         assert np.array_equal(species.cpu().numpy(), want)
 
 
-RESOLVE_MODES = [0, 1]      # LM_OPT_FIND_PATH: 0 = auto; 1 = every warp takes the two-pass (dense cluster) path
+# (LM_OPT_INTERACT_MODE, LM_OPT_FIND_PATH): the fused tile kernel (default) | the round-1 pipeline, auto | the
+# round-1 pipeline with every warp of its pair search on the two-pass (dense cluster) path
+RESOLVE_MODES = [(1, 0), (0, 0), (0, 1)]
 
 
-@pytest.mark.parametrize("mode", RESOLVE_MODES)
+@pytest.mark.parametrize("imode,mode", RESOLVE_MODES)
 @pytest.mark.parametrize("name", RPS_CASES)
-def test_interact_rps_cell_phase_order_golden(engine_factory, name, mode):
+def test_interact_rps_canonical_order_golden(engine_factory, name, imode, mode):
     """Fused pair search + RPS on the grid the golden was made for; golden species come from the
-    unmodified reference function run in the canonical cell-phase order."""
-    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH
+    unmodified reference function run in the device's canonical order (tile-round order for the fused tile
+    kernel, cell-phase order for the round-1 pipeline)."""
+    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH, LM_OPT_INTERACT_MODE
     g = golden(name + ".npz")
+    g = dict(g, species_cell=g["species_tile"] if imode == 1 else g["species_cell"])
     n = g["lon"].size
     eng = engine_factory(max_particles=n, max_cells=1 << 22, max_pairs=g["pairs_ref_order"].shape[0] + 64)
+    eng.set_option(LM_OPT_INTERACT_MODE, imode)
     eng.set_option(LM_OPT_FIND_PATH, mode)
     eng.set_grid(grid_from_golden(g))
     species = dev(g["species0"].copy())
@@ -267,11 +272,11 @@ def test_interact_rps_cell_phase_order_golden(engine_factory, name, mode):
     assert np.array_equal(species2.cpu().numpy(), g["species_cell"])
 
 
-@pytest.mark.parametrize("mode", RESOLVE_MODES)
+@pytest.mark.parametrize("imode,mode", RESOLVE_MODES)
 @pytest.mark.parametrize("n,r,p", [(100000, 0.01, (0.55, 0.55, 0.55)), (150000, 0.02, (0.5, 0.6, 0.9)),
                                    (40000, 0.05, (0.9, 0.9, 0.9)), (600000, 0.004, (0.55, 0.55, 0.55))])
-def test_interact_rps_vs_oracle_live(engine_factory, n, r, p, mode):
-    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH
+def test_interact_rps_vs_oracle_live(engine_factory, n, r, p, imode, mode):
+    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH, LM_OPT_INTERACT_MODE
     rng = np.random.default_rng(n + 1)
     side = np.sqrt(n / 4900.0)
     lon = (205 + side * rng.random(n)).astype(np.float32)
@@ -279,6 +284,7 @@ def test_interact_rps_vs_oracle_live(engine_factory, n, r, p, mode):
     sp0 = rng.integers(1, 4, n).astype(np.int8)
     want_pairs = opairs.query_pairs_reference_array(lon, lat, r)
     eng = engine_factory(max_particles=n, max_cells=1 << 22, max_pairs=want_pairs.shape[0] + 64)
+    eng.set_option(LM_OPT_INTERACT_MODE, imode)
     eng.set_option(LM_OPT_FIND_PATH, mode)
     grid = auto_grid(eng, lon, lat, r, margin=0.25)       # the 600k case: 2770 x 2770 cells, several warps per row
     out = torch.empty((want_pairs.shape[0] + 64, 2), dtype=torch.int32, device="cuda")
@@ -287,7 +293,7 @@ def test_interact_rps_vs_oracle_live(engine_factory, n, r, p, mode):
     st = eng.sync_stats()
     assert st.n_pairs == want_pairs.shape[0]
     assert np.array_equal(opairs.sort_pairs(out[:st.n_pairs].cpu().numpy()), want_pairs)
-    order, _ = orps.cell_phase_order(want_pairs, lon, lat, grid.as_dict())
+    order, _ = orps.canonical_order(want_pairs, lon, lat, grid.as_dict(), mode=imode)
     u = philox.pair_uniforms(order[:, 0], order[:, 1], 1234, 77)
     want_sp, draws = orps.rps_sequential_c(sp0.copy(), order, u, *p)
     assert draws > 0 and np.array_equal(species.cpu().numpy(), want_sp)
@@ -466,7 +472,7 @@ def test_fused_simulation_matches_oracle_loop(engine_factory):
         assert npairs == want_pairs.shape[0]
         got_pairs = opairs.sort_pairs(sim.pairs[:npairs].cpu().numpy())
         assert np.array_equal(got_pairs, want_pairs)
-        order, _ = orps.cell_phase_order(want_pairs, gl, ga, grid)
+        order, _ = orps.canonical_order(want_pairs, gl, ga, grid)
         u = philox.pair_uniforms(order[:, 0], order[:, 1], step, 5)
         sp_ref, _ = orps.rps_sequential_c(sp_ref, order, u, *p)
         assert np.array_equal(gs, sp_ref)
@@ -517,8 +523,8 @@ def test_overlapped_record_and_side_stream_phases_match_the_serial_path(engine_f
     assert int((ws != sp0).sum()) > 1000
 
 
-@pytest.mark.parametrize("mode", RESOLVE_MODES)
-def test_interact_rps_dense_clusters_take_the_warp_cooperative_path(engine_factory, mode):
+@pytest.mark.parametrize("imode,mode", RESOLVE_MODES)
+def test_interact_rps_dense_clusters_take_the_warp_cooperative_path(engine_factory, imode, mode):
     """Clusters of ~1500 microbes inside one or two cells: candidate pairs per unit >> HEAVY_TESTS, so the
     units are resolved by the whole warp (prefix scan over 3->3 species maps) and the pair search takes
     its direct (unstaged) path.  Same bit-exact bar."""
@@ -535,8 +541,9 @@ def test_interact_rps_dense_clusters_take_the_warp_cooperative_path(engine_facto
     r, p = 0.01, (0.55, 0.6, 0.5)
     want_pairs = opairs.query_pairs_reference_array(lon, lat, r)
     assert want_pairs.shape[0] > 2_000_000
-    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH
+    from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH, LM_OPT_INTERACT_MODE
     eng = engine_factory(max_particles=n, max_cells=1 << 20, max_pairs=want_pairs.shape[0] + 64)
+    eng.set_option(LM_OPT_INTERACT_MODE, imode)
     eng.set_option(LM_OPT_FIND_PATH, mode)
     grid = auto_grid(eng, lon, lat, r, margin=0.1)
     out = torch.empty((want_pairs.shape[0] + 64, 2), dtype=torch.int32, device="cuda")
@@ -545,7 +552,7 @@ def test_interact_rps_dense_clusters_take_the_warp_cooperative_path(engine_facto
     st = eng.sync_stats()
     assert st.n_pairs == want_pairs.shape[0]
     assert np.array_equal(opairs.sort_pairs(out[:st.n_pairs].cpu().numpy()), want_pairs)
-    order, _ = orps.cell_phase_order(want_pairs, lon, lat, grid.as_dict())
+    order, _ = orps.canonical_order(want_pairs, lon, lat, grid.as_dict(), mode=imode)
     u = philox.pair_uniforms(order[:, 0], order[:, 1], 8, 3)
     want_sp, _ = orps.rps_sequential_c(sp0.copy(), order, u, *p)
     assert np.array_equal(species.cpu().numpy(), want_sp)
@@ -558,6 +565,8 @@ def test_rps_hand_off_capacity_overflow_is_reported(engine_factory):
     lon = (205 + 0.5 * rng.random(n)).astype(np.float32)
     lat = (25 + 0.5 * rng.random(n)).astype(np.float32)
     eng = engine_factory(max_particles=n, max_cells=1 << 20, max_pairs=100)           # far too small
+    from lagrangian_microbes_b200._lib import LM_OPT_INTERACT_MODE
+    eng.set_option(LM_OPT_INTERACT_MODE, 0)      # only the round-1 pipeline has a hand-off; the fused tile kernel has none
     auto_grid(eng, lon, lat, 0.02)
     species = dev(rng.integers(1, 4, n).astype(np.int8))
     eng.interact_rps(dev(lon), dev(lat), species, 0.02, 0.5, 0.5, 0.5, 0, 0)

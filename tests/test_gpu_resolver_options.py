@@ -14,6 +14,14 @@ pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
+
+@pytest.fixture(autouse=True)
+def _round1_pipeline(monkeypatch):
+    """These tests cover the round-1 pipeline (pair search -> hand-off -> nine phase launches / tiled resolver,
+    csrc/pairs.cu, cell-phase order), still shipped as LM_OPT_INTERACT_MODE = 0."""
+    from lagrangian_microbes_b200.engine import Engine
+    monkeypatch.setattr(Engine, "DEFAULT_INTERACT_MODE", 0)
+
 # (LM_OPT_RESOLVE_BATCH, LM_OPT_RESOLVE_HEAVY_MIN, LM_OPT_RESOLVE_UPL)
 SETTINGS = [(4, 0, 0), (8, 0, 0), (4, 24, 1), (8, 0xffff, 2), (1, 24, 4), (8, 8, 8)]
 

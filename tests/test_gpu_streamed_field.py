@@ -1,0 +1,62 @@
+"""The streamed velocity input path (simulation.FieldWindowStreamer: snapshots in pinned host memory, the two or three
+time levels a step brackets uploaded into one of two device windows on a side stream, time indices rebased) against the
+resident field, bit for bit, across snapshot boundaries of an IRREGULAR time axis.  This is the path bench.py's `e2e`
+measures; the reference re-opens the year's file per time_step call instead (/root/reference/particle_advecter.py:160-183)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+from oracle import rk4 as ork4
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+class _HostFS:
+    def __init__(self, fs):
+        self.u, self.v, self.lon, self.lat, self.time = fs.u, fs.v, fs.lon, fs.lat, fs.time
+
+    def to_device(self, device):
+        return tuple(torch.from_numpy(a).to(device) for a in (self.u, self.v, self.lon, self.lat))
+
+
+@pytest.mark.parametrize("advect_mode", [0, 1])
+def test_streamed_windows_equal_the_resident_field_across_snapshot_boundaries(advect_mode):
+    from lagrangian_microbes_b200._lib import LM_OPT_ADVECT_MODE
+    from lagrangian_microbes_b200.simulation import FusedSimulation
+    g = golden("rk4_small.npz")
+    fs = ork4.FieldSet(g["grid_lon"], g["grid_lat"], g["grid_time"], g["u"], g["v"])
+    assert np.unique(np.diff(fs.time)).size > 1                       # irregular axis: 0, 400000, 864000, 1512000, 2160000 s
+    hfs = _HostFS(fs)
+    rng = np.random.default_rng(4)
+    n = 20000
+    lon = (205.0 + 4.0 * rng.random(n)).astype(np.float32)
+    lat = (33.0 + 3.0 * rng.random(n)).astype(np.float32)
+    sp = rng.integers(1, 4, n).astype(np.int8)
+    mk = lambda stream: FusedSimulation(lon, lat, sp, 0.02, 0.55, 0.6, 0.9, hfs, dt_seconds=3600.0, seed=2, emit_pairs=False,  # noqa: E731
+                                        regrid_every=8, stream_field=stream)
+    a, b = mk(False), mk(True)
+    for s in (a, b):
+        s.engine.set_option(LM_OPT_ADVECT_MODE, advect_mode)
+    n_steps = 250                                                      # snapshots at steps 111.1 and 240: two boundaries crossed
+    seen = set()
+    for step in range(n_steps):
+        a.step()
+        b.step()
+        seen.add(a.clock.ti)
+        assert b.h2d_bytes_last_step in (2 * 2 * fs.u[0].size * 4, 2 * 3 * fs.u[0].size * 4)   # two or three levels of U and V
+        if step % 25 == 24 or step in (110, 111, 112, 239, 240, 241):
+            la, aa, sa = a.download()
+            lb, ab, sb = b.download()
+            assert np.array_equal(la, lb) and np.array_equal(aa, ab) and np.array_equal(sa, sb), "step %d" % step
+    assert seen >= {0, 1, 2}
+    # and the trajectory is the oracle's (single steps are checked elsewhere; here: the clock / index handling over the run)
+    l64, a64 = lon.astype(np.float64), lat.astype(np.float64)
+    t, ti = 0.0, 0
+    for step in range(n_steps):
+        l64, a64, ti, _ = ork4.rk4_step_f64(fs, l64, a64, t, 3600.0, ti)
+        t += 3600.0
+    gl, ga, _ = b.download()
+    assert np.max(np.abs(gl - l64) / np.abs(l64)) < 1e-5 and np.max(np.abs(ga - a64) / np.abs(a64)) < 1e-5   # 250 steps accumulated
+    b.check_faults()

@@ -20,6 +20,14 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
+@pytest.fixture(autouse=True)
+def _round1_pipeline(monkeypatch):
+    """These tests cover the round-1 pipeline (pair search -> hand-off -> nine phase launches / tiled resolver,
+    csrc/pairs.cu, cell-phase order), still shipped as LM_OPT_INTERACT_MODE = 0."""
+    from lagrangian_microbes_b200.engine import Engine
+    monkeypatch.setattr(Engine, "DEFAULT_INTERACT_MODE", 0)
+
+
 def dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 

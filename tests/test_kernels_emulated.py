@@ -268,12 +268,14 @@ def _small_field():
     return ork4.FieldSet(g["grid_lon"], g["grid_lat"], g["grid_time"], g["u"], g["v"])
 
 
-@pytest.mark.parametrize("resolve_mode,stats_every_step", [(0, True), (1, True), (1, False)])
-def test_fused_steps_through_the_c_abi(abi, resolve_mode, stats_every_step):
+@pytest.mark.parametrize("interact_mode,resolve_mode,stats_every_step", [(1, 0, True), (1, 0, False), (0, 0, True), (0, 1, True),
+                                                                         (0, 1, False)])
+def test_fused_steps_through_the_c_abi(abi, interact_mode, resolve_mode, stats_every_step):
     """Four lm_step calls (RK4 advection, binning, pair search, RPS, stats) on 1,200 microbes, step by step against the
     oracle: positions vs the RK4 restatement from identical inputs, pairs vs cKDTree on the library's positions,
     species vs the reference rule in canonical order -- tests/test_gpu_parity.py::test_fused_simulation_matches_oracle_loop
-    in miniature, on the emulator, with the nine-phase and the tiled resolver (one launch for all nine phases)."""
+    in miniature, on the emulator, with the fused tile kernel (the default) and with the round-1 pipeline (nine-phase and
+    tiled resolver)."""
     from lagrangian_microbes_b200 import _lib
     from lagrangian_microbes_b200.engine import make_grid
     from lagrangian_microbes_b200.particle_advecter import StageClock
@@ -294,6 +296,7 @@ def test_fused_steps_through_the_c_abi(abi, resolve_mode, stats_every_step):
         assert L.lm_set_field(h, _ptr(u), _ptr(v), _ptr(glon), _ptr(glat), *u.shape) == 0
         grid = make_grid(float(lon.min()), float(lon.max()), float(lat.min()), float(lat.max()), r, n, max_cells, margin=0.1)
         assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+        assert L.lm_set_option(h, _lib.LM_OPT_INTERACT_MODE, interact_mode) == 0
         assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, resolve_mode) == 0
         assert L.lm_state_set(h, _ptr(lon), _ptr(lat), _ptr(sp0), None, n, None) == 0
         clock = StageClock(fs.time)
@@ -316,7 +319,7 @@ def test_fused_steps_through_the_c_abi(abi, resolve_mode, stats_every_step):
             want_pairs = opairs.query_pairs_reference_array(gl, ga, r)
             assert stats.n_pairs == want_pairs.shape[0]
             assert np.array_equal(opairs.sort_pairs(pairs[:stats.n_pairs]), want_pairs)
-            order, _ = orps.cell_phase_order(want_pairs, gl, ga, grid.as_dict())
+            order, _ = orps.canonical_order(want_pairs, gl, ga, grid.as_dict(), mode=interact_mode)
             uu = philox.pair_uniforms(order[:, 0], order[:, 1], step, seed)
             sp_ref, _ = orps.rps_sequential_c(sp_ref, order, uu, *p)
             assert np.array_equal(gs, sp_ref), "step %d: %d species differ" % (step, int((gs != sp_ref).sum()))
@@ -326,13 +329,16 @@ def test_fused_steps_through_the_c_abi(abi, resolve_mode, stats_every_step):
             total += stats.n_pairs
         assert total > 1500 and int((sp_ref != sp0).sum()) > 100
         per_step = (L.lm_launch_count(h) - launches0) / float(n_steps)
-        assert per_step < 12 if resolve_mode == 1 else per_step >= 16          # one resolver launch instead of nine
+        if interact_mode == 1:
+            assert per_step <= 17                 # advection, binning (6), one tile launch + at most six boundary launches
+        else:
+            assert per_step < 12 if resolve_mode == 1 else per_step >= 16      # one resolver launch instead of nine
     finally:
         assert L.lm_destroy(h) == 0
 
 
-@pytest.mark.parametrize("n_strips,resolve_mode", [(2, 1), (3, 0)])
-def test_latitude_strips_through_the_c_abi(abi, n_strips, resolve_mode):
+@pytest.mark.parametrize("n_strips,interact_mode,resolve_mode", [(2, 1, 0), (3, 1, 0), (2, 0, 1), (3, 0, 0)])
+def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve_mode):
     """The whole strip protocol executed: G handles, particles handed out in contiguous tiles, routing
     passes until every microbe sits in its strip, then fused steps in the five stages of include/lm_b200.h with the
     exchange buffers copied between neighbours -- against ONE handle stepping all microbes on the same grid.
@@ -361,6 +367,7 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, resolve_mode):
         h = ctypes.c_void_p()
         assert L.lm_create(ctypes.byref(h), 0, n + 512, max_cells, cap) == 0
         assert L.lm_set_field(h, _ptr(u), _ptr(v), _ptr(glon), _ptr(glat), *u.shape) == 0
+        assert L.lm_set_option(h, _lib.LM_OPT_INTERACT_MODE, interact_mode) == 0
         assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, mode) == 0
         return h
 
@@ -465,8 +472,10 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, resolve_mode):
 # ----------------------------------------------------------------------------------------------------------------------
 # The committed golden vectors (tests/golden/, made with the unmodified reference function and with SciPy) through the
 # emulated C ABI: the CPU suite pins the kernels' logic to the reference's own outputs, not only the GPU suite.
-@pytest.mark.parametrize("name,resolve_mode", [("rps_oddspecies", 0), ("rps_oddspecies", 1), ("rps_clustered", 1)])
-def test_golden_species_through_the_c_abi(abi, name, resolve_mode):
+@pytest.mark.parametrize("name,interact_mode,resolve_mode", [("rps_oddspecies", 1, 0), ("rps_clustered", 1, 0), ("rps_uniform", 1, 0),
+                                                              ("rps_oddspecies", 0, 0), ("rps_oddspecies", 0, 1),
+                                                              ("rps_clustered", 0, 1)])
+def test_golden_species_through_the_c_abi(abi, name, interact_mode, resolve_mode):
     from conftest import golden
     from lagrangian_microbes_b200 import _lib
     L = abi
@@ -477,9 +486,11 @@ def test_golden_species_through_the_c_abi(abi, name, resolve_mode):
     try:
         grid = _lib.Grid(float(g["grid"][0]), float(g["grid"][1]), float(g["grid"][2]), int(g["grid_n"][0]), int(g["grid_n"][1]))
         assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+        assert L.lm_set_option(h, _lib.LM_OPT_INTERACT_MODE, interact_mode) == 0
         assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, resolve_mode) == 0
         lon, lat = np.ascontiguousarray(g["lon"]), np.ascontiguousarray(g["lat"])
-        # fused path, canonical cell-phase order: species made by the reference function fed that order
+        # fused path, canonical order (tile-round for the fused tile kernel, cell-phase for the round-1 pipeline):
+        # species made by the unmodified reference function fed that order
         species = g["species0"].copy()
         prm = _lib.RpsParams(float(g["pRS"]), float(g["pPR"]), float(g["pSP"]), int(g["seed"]), int(g["step"]))
         found = np.zeros(1, dtype=np.int64)
@@ -488,7 +499,7 @@ def test_golden_species_through_the_c_abi(abi, name, resolve_mode):
         stats = _lib.Stats()
         assert L.lm_sync_stats(h, ctypes.byref(stats), None) == 0
         assert stats.n_pairs == n_pairs == found[0]
-        assert np.array_equal(species, g["species_cell"])
+        assert np.array_equal(species, g["species_tile" if interact_mode == 1 else "species_cell"])
         if resolve_mode == 0:
             # explicit-order resolver (M-ref): the reference's own set-iteration order and draws
             species = g["species0"].copy()
@@ -551,6 +562,7 @@ def test_hand_off_overflow_is_reported_not_resolved(abi, resolve_mode):
     try:
         grid = _lib.Grid(float(g["grid"][0]), float(g["grid"][1]), float(g["grid"][2]), int(g["grid_n"][0]), int(g["grid_n"][1]))
         assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+        assert L.lm_set_option(h, _lib.LM_OPT_INTERACT_MODE, 0) == 0     # the round-1 pipeline; the fused tile kernel has no hand-off
         assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, resolve_mode) == 0
         species = g["species0"].copy()
         prm = _lib.RpsParams(float(g["pRS"]), float(g["pPR"]), float(g["pSP"]), int(g["seed"]), int(g["step"]))
@@ -615,3 +627,67 @@ def test_tiled_resolver_other_tile_shapes(abi, shape):
             assert np.array_equal(species, want), "shape %d: %d species differ" % (shape, int((species != want).sum()))
         finally:
             L.lm_destroy(h)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The fused tile kernel (csrc/interact.cu, LM_OPT_INTERACT_MODE = 1, the default device path): pair search + RPS in one
+# pass, canonical tile-round order (oracle/rps.py::tile_round_order).  Pair set vs cKDTree, species vs the reference rule.
+@pytest.fixture(scope="module")
+def emu_tile():
+    import emu_build
+    L = ctypes.CDLL(emu_build.build())
+    vp, i32, i64, u64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_double
+    L.emu_interact_tile.restype = i64
+    L.emu_interact_tile.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, dbl, i32, dbl, dbl, dbl, u64, u64, i32, i32,
+                                    i32, i32, vp, i64]
+    return L
+
+
+class TileCloud(Cloud):
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.order, self.phase = orps.tile_round_order(self.pairs, self.lon, self.lat, self.grid)
+        self.u = philox.pair_uniforms(self.order[:, 0], self.order[:, 1], 17, 5)
+
+    def run_tile(self, L, sp, first=0, last=14, tile_cap=0, draw_batch=0, rps=True):
+        g = self.grid
+        lon_s, lat_s = np.ascontiguousarray(self.lon[self.ids]), np.ascontiguousarray(self.lat[self.ids])
+        sp_s = np.ascontiguousarray(sp[self.ids])
+        cap = self.pairs.shape[0] + 8
+        pairs_out = np.full((cap, 2), -1, dtype=np.int32)
+        ret = L.emu_interact_tile(_ptr(lon_s), _ptr(lat_s), _ptr(self.ids), _ptr(self.cell_start), _ptr(sp_s) if rps else None,
+                                  self.n, g["ncx"], g["ncy"], 0, g["ncy"], g["ncy"], R, 2, *P, 5, 17, first, last, tile_cap,
+                                  draw_batch, _ptr(pairs_out), cap)
+        assert ret >= 0
+        found, launches = ret & ((1 << 48) - 1), ret >> 48
+        out = np.empty_like(sp)
+        out[self.ids] = sp_s
+        return out, launches, opairs.sort_pairs(pairs_out[:found])
+
+
+@pytest.mark.parametrize("seed,ncx,ncy,n,knots,knot_size,tile_cap,draw_batch", [
+    (1, 74, 19, 1800, 10, (10, 31), 0, 0),        # three tiles across, two up, ragged; knots on the whole-warp path
+    (2, 74, 37, 3000, 6, (40, 60), 0, 1),         # ... draws taken one lane at a time
+    (3, 40, 20, 1500, 2, (150, 200), 256, 32),    # 18,000-slot cells on the whole-CTA path; tiles too full for shared memory
+])
+def test_fused_tile_kernel_executed(emu_tile, seed, ncx, ncy, n, knots, knot_size, tile_cap, draw_batch):
+    c = TileCloud(seed, ncx, ncy, n, knots=knots, knot_size=knot_size)
+    want = c.oracle(c.sp0, 0, 14)
+    assert int((want != c.sp0).sum()) > 100 and set(np.unique(c.phase)) >= set(range(15))
+    got, launches, pairs = c.run_tile(emu_tile, c.sp0, tile_cap=tile_cap, draw_batch=draw_batch)
+    assert np.array_equal(pairs, c.pairs), "pair set differs from cKDTree.query_pairs"
+    assert np.array_equal(got, want), "%d species differ" % int((got != want).sum())
+    assert launches == 7                                       # one tile launch + six boundary phases
+
+
+def test_fused_tile_kernel_phase_ranges_and_pair_search_alone(emu_tile):
+    """The two ranges a strip launches around its halo exchange (0-11, then 12-14 on the result) and the pair search
+    without species (lm_find_pairs)."""
+    c = TileCloud(4, 70, 33, 2500, knots=4, knot_size=(30, 50))
+    mid, _, p_lo = c.run_tile(emu_tile, c.sp0, first=0, last=11)
+    assert np.array_equal(mid, c.oracle(c.sp0, 0, 11))
+    end, _, p_hi = c.run_tile(emu_tile, mid, first=12, last=14)
+    assert np.array_equal(end, c.oracle(c.sp0, 0, 14))
+    assert np.array_equal(opairs.sort_pairs(np.concatenate((p_lo, p_hi))), c.pairs)      # every pair exactly once
+    same, _, pairs = c.run_tile(emu_tile, c.sp0, rps=False)
+    assert np.array_equal(pairs, c.pairs) and np.array_equal(same, c.sp0)

@@ -85,3 +85,78 @@ def test_rule_table():
         sp = np.array([s1, s2], dtype=np.int8)
         orps.rps_sequential_c(sp, np.array([[0, 1]]), np.array([r]), 0.2, 0.5, 0.8)
         assert tuple(sp) == want
+
+
+# ---- the tile-round order of the fused tile kernel (LM_OPT_INTERACT_MODE = 1) ------------------------------------
+@pytest.mark.parametrize("name", CASES)
+def test_restatement_matches_reference_in_tile_round_order(name):
+    """species_tile was produced by the UNMODIFIED reference function fed the tile-round order (make_golden.py)."""
+    g = golden(name + ".npz")
+    order = g["pairs_tile_order"]
+    sp, _ = orps.rps_sequential_c(g["species0"].copy(), order, philox.pair_uniforms(order[:, 0], order[:, 1], int(g["step"]), int(g["seed"])),
+                                  float(g["pRS"]), float(g["pPR"]), float(g["pSP"]))
+    assert np.array_equal(sp, g["species_tile"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_tile_round_order_is_reproducible_and_its_rounds_are_matchings(name):
+    g = golden(name + ".npz")
+    lon, lat, grid = g["lon"], g["lat"], _grid(g)
+    pairs = opairs.sort_pairs(g["pairs_ref_order"])
+    order, phase = orps.tile_round_order(pairs, lon, lat, grid)
+    assert np.array_equal(order.astype(np.int32), g["pairs_tile_order"])
+    assert np.array_equal(opairs.sort_pairs(order), pairs)                     # a permutation of the pair set
+    assert np.all(np.diff(phase) >= 0) and phase.min() >= 0 and phase.max() <= 14
+    # inside one phase no microbe may occur in two units; inside one round of a unit no microbe may occur twice.
+    # Walk the order: a new (phase, unit) or a microbe seen in the current round starts a new round; the number of
+    # rounds a unit needs is then at most max(m_a, m_b) (two cells) or m - 1 + (m odd) (one cell): the matchings bound
+    cx, cy, rank, occ = orps.cell_ranks(lon, lat, grid)
+    key = cy * grid["ncx"] + cx
+    for ph in np.unique(phase):
+        sel = order[phase == ph]
+        ka, kb = key[sel[:, 0]], key[sel[:, 1]]
+        unit_of_cell = {}
+        for a, b in zip(ka.tolist(), kb.tolist()):
+            u = (min(a, b), max(a, b))
+            for c in u:
+                assert unit_of_cell.setdefault(c, u) == u, "phase %d: cell %d in two units" % (ph, c)
+    rounds, cur_unit, seen, cur_key = {}, None, set(), None
+    for k in range(order.shape[0]):
+        i, j = int(order[k, 0]), int(order[k, 1])
+        unit = (int(phase[k]), min(key[i], key[j]), max(key[i], key[j]))
+        if unit != cur_unit or i in seen or j in seen:
+            if unit != cur_unit:
+                cur_unit = unit
+            rounds[unit] = rounds.get(unit, 0) + 1
+            seen = set()
+        seen.add(i)
+        seen.add(j)
+    for (ph, ca, cb), nr in rounds.items():
+        ma, mb = int((key == ca).sum()), int((key == cb).sum())
+        bound = max(ma, mb) if ca != cb else ma - 1 + (ma & 1)
+        assert nr <= bound, "unit %r needs %d rounds, bound %d" % ((ph, ca, cb), nr, bound)
+
+
+def test_reference_cost_pair_function_equals_the_unmodified_reference_call_by_call():
+    """oracle.rps.reference_pair_interaction (what bench.py --impl reference loops over on the GPU box, where
+    /root/reference does not exist) against /root/reference/interactions.py::rock_paper_scissors_interaction: same
+    NumPy global stream, same species after every call."""
+    import os
+    import sys
+    if not os.path.exists("/root/reference/interactions.py"):
+        pytest.skip("the reference tree is only present in the authoring container")
+    sys.path.insert(0, "/root/reference")
+    import interactions as ref
+    g = golden("rps_oddspecies.npz")
+    params = {"pRS": 0.3, "pPR": 0.7, "pSP": 0.5}
+    a, b = {"species": g["species0"].copy()}, {"species": g["species0"].copy()}
+    pairs = [tuple(map(int, p)) for p in g["pairs_ref_order"][:1500]]
+    np.random.seed(123)
+    for p1, p2 in pairs:
+        ref.rock_paper_scissors_interaction(params, a, p1, p2)
+    state_ref = np.random.get_state()[2]
+    np.random.seed(123)
+    for p1, p2 in pairs:
+        orps.reference_pair_interaction(params, b, p1, p2)
+    assert np.array_equal(a["species"], b["species"]) and np.random.get_state()[2] == state_ref      # same draws consumed
+    assert int((a["species"] != g["species0"]).sum()) > 50

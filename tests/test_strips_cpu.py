@@ -19,10 +19,11 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def test_strip_edges_are_even_balanced_and_cover_all_rows():
-    from lagrangian_microbes_b200.strips import strip_edges
+def test_strip_edges_are_tile_aligned_balanced_and_cover_all_rows():
+    from lagrangian_microbes_b200.strips import ROW_ALIGN, strip_edges
+    assert ROW_ALIGN == 16                                       # LM_TILE_H: the tile height of the fused interaction pass
     rng = np.random.default_rng(0)
-    for ncy, G in ((16, 2), (101, 8), (64, 3), (1000, 8), (17, 8)):
+    for ncy, G in ((40, 2), (200, 8), (64, 3), (1000, 8), (130, 8), (18, 2), (7, 1)):
         for kind in ("uniform", "blob", "random"):
             if kind == "uniform":
                 h = np.full(ncy, 100)
@@ -33,18 +34,21 @@ def test_strip_edges_are_even_balanced_and_cover_all_rows():
                 h = rng.integers(0, 500, ncy)
             e = strip_edges(h, G)
             assert e[0] == 0 and e[-1] == ncy and len(e) == G + 1
-            assert all(b - a >= 2 for a, b in zip(e[:-1], e[1:]))
-            assert all(x % 2 == 0 for x in e[:-1])
-            if kind == "uniform" and ncy >= 8 * G:
+            assert all(b - a >= 16 for a, b in zip(e[:-2], e[1:-1])) and e[-1] - e[-2] >= 2
+            assert all(x % 16 == 0 for x in e[:-1])
+            if kind == "uniform" and ncy >= 64 * G:
                 share = np.add.reduceat(h, e[:-1])
-                assert share.max() - share.min() <= 2 * 100 * 2      # within two rows of each other
+                assert share.max() - share.min() <= 2 * 100 * 16     # within two aligned rows of each other
     with pytest.raises(ValueError):
         strip_edges(np.ones(7), 4)
+    with pytest.raises(ValueError):
+        strip_edges(np.ones(17), 2)
+    assert strip_edges(np.ones(101), 8, align=2)[1] % 2 == 0     # the round-1 pipeline only needs even rows
     e = strip_edges(np.r_[np.zeros(30), np.full(10, 50)], 2, max_rows=24)
     assert max(b - a for a, b in zip(e[:-1], e[1:])) <= 24
 
 
-def test_remap_edges_keeps_latitudes_even_rows_and_room_for_every_strip():
+def test_remap_edges_keeps_latitudes_aligned_rows_and_room_for_every_strip():
     from lagrangian_microbes_b200.engine import make_grid
     from lagrangian_microbes_b200.strips import remap_edges, strip_edges
     old = make_grid(200.0, 210.0, 20.0, 40.0, 0.01, 4_000_000, 1 << 24)
@@ -54,11 +58,11 @@ def test_remap_edges_keeps_latitudes_even_rows_and_room_for_every_strip():
             new = make_grid(*box, r, 4_000_000, 1 << 24)
             e = remap_edges(old, edges, new)
             assert e[0] == 0 and e[-1] == new.ncy and len(e) == 9
-            assert all(x % 2 == 0 for x in e[:-1]) and all(b - a >= 2 for a, b in zip(e[:-1], e[1:]))
+            assert all(x % 16 == 0 for x in e[:-1]) and all(b - a >= 16 for a, b in zip(e[:-2], e[1:-1])) and e[-1] - e[-2] >= 2
             lat_old = [old.y0 + k / old.inv_h for k in edges[1:-1]]
             lat_new = [new.y0 + k / new.inv_h for k in e[1:-1]]
             inside = [(a, b) for a, b in zip(lat_old, lat_new) if new.y0 + 4 / new.inv_h < a < new.y0 + (new.ncy - 4) / new.inv_h]
-            assert inside and all(abs(a - b) <= 1.01 / new.inv_h for a, b in inside)       # within one (even) row
+            assert inside and all(abs(a - b) <= 8.01 / new.inv_h for a, b in inside)       # within half a tile height
     tiny = make_grid(200.0, 200.01, 20.0, 20.01, 0.01, 100, 1 << 16, margin=0.0)
     with pytest.raises(ValueError):
         remap_edges(old, edges, tiny)
