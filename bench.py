@@ -19,6 +19,11 @@ Workloads (``config.workload``):
   config2  BASELINE config 2: 490,000 microbes (700x700 lattice, 25-35N 205-215E), time-varying field,
            spun up ``--spinup`` steps so that the timed steps see the stirred state.
   config3  BASELINE config 3: 10M microbes uniform in the 10x10-degree patch (rho = 15.7).
+  config1  BASELINE config 1, the reference's own CPU-runnable case: 490,000 microbes on the 700x700 lattice, STEADY
+           synthetic velocity, 24 hourly steps.  The lattice spacing exceeds r, so the configuration as specified has no
+           pairs; ``--spinup`` (default 120) advection-only steps strain the lattice first so that the timed steps
+           interact.  ``--impl reference`` runs the SAME 490,000 microbes through the reference's CPU path: the one
+           same-size GPU/CPU comparison.
 Inputs are larger than L2 for shard/config3 (state 162 MB + pair list 440 MB per step vs 126 MB L2).
 """
 import argparse
@@ -62,7 +67,7 @@ def workload_particles(name, n, rank, world, seed=0):
         lon = 205.0 + 10.0 * rng.random(n)
         lat = 25.0 + 10.0 * rng.random(n)
         desc = dict(lon=[205.0, 215.0], lat=[25.0, 35.0])
-    elif name == "config2":
+    elif name in ("config2", "config1"):
         from lagrangian_microbes_b200.particle_advecter import uniform_particle_locations
         lon, lat = uniform_particle_locations(n, 25, 35, 205, 215)
         desc = dict(lon=[205.0, 215.0], lat=[25.0, 35.0])
@@ -73,14 +78,18 @@ def workload_particles(name, n, rank, world, seed=0):
 
 
 def default_n(name):
-    return {"shard": 12_500_000, "config3": 10_000_000, "config2": 490_000}[name]
+    return {"shard": 12_500_000, "config3": 10_000_000, "config2": 490_000, "config1": 490_000}[name]
 
 
-def make_fieldset(n_modes):
+def make_fieldset(n_modes, kind="random_fourier"):
     from lagrangian_microbes_b200 import velocity_fields
     from lagrangian_microbes_b200.particle_advecter import HostFieldSet
-    velocity_fields.configure_synthetic(kind="random_fourier", seed=0, n_modes=n_modes, rms_speed=0.2)
+    velocity_fields.configure_synthetic(kind=kind, seed=0, n_modes=n_modes, rms_speed=0.2)
     return HostFieldSet(velocity_fields.oscar_dataset(2017))
+
+
+def field_kind(workload):
+    return "steady" if workload == "config1" else "random_fourier"
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -139,66 +148,63 @@ class ClockSampler:
 # CPU reference arm / baseline
 # ------------------------------------------------------------------------------------------------------
 def cpu_reference_step_setup(workload, n_sample, n_modes):
-    """A bounded sample of the workload: the same areal density, fewer microbes."""
+    """The workload itself (config1, config2: the 490,000 microbes of the configuration) or a bounded sample of it:
+    the same areal density, fewer microbes (shard, config3)."""
     from oracle import rk4 as ork4
     n_full = default_n(workload)
-    lon, lat, species, desc = workload_particles(workload, n_full if workload == "config2" else n_sample, 0, 1)
-    if workload != "config2":
+    lattice = workload in ("config1", "config2")
+    lon, lat, species, desc = workload_particles(workload, n_full if lattice else n_sample, 0, 1)
+    if not lattice:
         # shrink the box so that the density (hence pairs per microbe) is that of the full workload
         frac = n_sample / float(n_full)
-        lon_w, lat_w = desc["lon"][1] - desc["lon"][0], desc["lat"][1] - desc["lat"][0]
         if workload == "shard":
-            lat_w = 7.5
             lat_lo = 30.0 - 3.75
         else:
             lat_lo = desc["lat"][0]
         s = np.sqrt(frac)
         lon = desc["lon"][0] + (lon - desc["lon"][0]) * s
         lat = lat_lo + (lat - lat_lo) * s
-    elif n_sample < n_full:
-        lon, lat, species = lon[:n_sample], lat[:n_sample], species[:n_sample]
-    hfs = make_fieldset(n_modes)
+    hfs = make_fieldset(n_modes, field_kind(workload))
     fs = ork4.FieldSet(hfs.lon, hfs.lat, hfs.time, hfs.u, hfs.v)
     return fs, lon.astype(np.float32), lat.astype(np.float32), species
 
 
-def cpu_reference_step(fs, lon, lat, species, t, ti, step, threads):
+def cpu_reference_step(fs, lon, lat, params, props, t, ti, threads):
     """One step of the reference's CPU path.  Returns (ti, n_pairs, dict of phase seconds)."""
-    from oracle import pairs as opairs, philox, rk4 as ork4, rps as orps
+    from oracle import pairs as opairs, rk4 as ork4, rps as orps
     t0 = time.perf_counter()
-    ti, _ = ork4.rk4_step_c(fs, lon, lat, t, DT, ti, threads=threads)            # parcels' JIT'd C, restated
+    ti, _ = ork4.rk4_step_c(fs, lon, lat, t, DT, ti, threads=threads)            # parcels' JIT'd C, restated; tiles over all cores
     t1 = time.perf_counter()
-    pair_set = opairs.query_pairs_reference(lon, lat, RADIUS)                    # cKDTree build + query_pairs (set)
+    pair_set = opairs.query_pairs_reference(lon, lat, RADIUS)                    # cKDTree build + query_pairs (set): the reference's call
     t2 = time.perf_counter()
-    # the reference's Python loop over the set (interaction_simulator.py:104-105), rule restated in Python
-    pr = np.array(list(pair_set), dtype=np.int64).reshape(-1, 2)
-    u = philox.pair_uniforms(np.minimum(pr[:, 0], pr[:, 1]), np.maximum(pr[:, 0], pr[:, 1]), step, 0)
-    t3 = time.perf_counter()
-    k = 0
+    # the reference's loop (interaction_simulator.py:104-105) over the set, calling the pair function with the reference's
+    # signature and per-call work (dict look-ups, np.random.rand() when the species differ): interactions.py:13-40
+    fn = orps.reference_pair_interaction
     for pair in pair_set:
-        orps.rps_pair(species, pair[0], pair[1], u[k], *P_RPS)
-        k += 1
-    t4 = time.perf_counter()
-    return ti, len(pair_set), {"advect_s": t1 - t0, "tree_query_s": t2 - t1, "rps_loop_s": t4 - t3}
+        fn(params, props, pair[0], pair[1])
+    t3 = time.perf_counter()
+    return ti, len(pair_set), {"advect_s": t1 - t0, "tree_query_s": t2 - t1, "rps_loop_s": t3 - t2}
 
 
-def run_cpu_reference(workload, n_sample, steps, warmup, n_modes):
-    from oracle import rps as orps
+def run_cpu_reference(workload, n_sample, steps, warmup, n_modes, spinup=0):
+    from oracle import rk4 as ork4, rps as orps
     orps.build_c()
     threads = os.cpu_count() or 1
     fs, lon, lat, species = cpu_reference_step_setup(workload, n_sample, n_modes)
+    params = {"pRS": P_RPS[0], "pPR": P_RPS[1], "pSP": P_RPS[2]}
+    props = {"species": species}
+    np.random.seed(0)
     t, ti = 0.0, 0
+    for _ in range(spinup):                      # advection only (untimed): strain the lattice until pairs exist
+        ti, _ = ork4.rk4_step_c(fs, lon, lat, t, DT, ti, threads=threads)
+        t += DT
     phases = {"advect_s": 0.0, "tree_query_s": 0.0, "rps_loop_s": 0.0}
     pairs = 0
     tot = 0.0
     for s in range(warmup + steps):
-        t0 = time.perf_counter()
-        ti, npairs, ph = cpu_reference_step(fs, lon, lat, species, t, ti, s, threads)
-        el = time.perf_counter() - t0
+        ti, npairs, ph = cpu_reference_step(fs, lon, lat, params, props, t, ti, threads)
         t += DT
         if s >= warmup:
-            # only the reference's own phases count (advect, tree build + query, pair loop); building the
-            # injected per-pair stream is harness work that np.random.rand() does inside the loop upstream
             tot += ph["advect_s"] + ph["tree_query_s"] + ph["rps_loop_s"]
             pairs += npairs
             for k2 in phases:
@@ -209,19 +215,105 @@ def run_cpu_reference(workload, n_sample, steps, warmup, n_modes):
 
 
 # ------------------------------------------------------------------------------------------------------
+# parity twin: correctness evidence printed WITH the throughput (outside the timed region)
+# ------------------------------------------------------------------------------------------------------
+def parity_twin(world, rank, hfs, steps=4, per_rank=40_000):
+    """A reduced-size twin of the workload (same areal density, same field, same code path as the timed run) stepped
+    ``steps`` times.  N = 1: every step checked against the CPU oracle -- positions vs the float64 RK4 restatement
+    (1e-6 relative), the emitted pair set vs cKDTree.query_pairs (exact), the species vs the reference rule run
+    sequentially in the canonical order (exact).  N > 1: the twin is sharded over the N ranks as latitude strips (NCCL
+    halo exchange + migration, as in the timed run) AND stepped by one handle on rank 0; positions and species of every
+    microbe must agree bit for bit.  Returns the ``parity`` block of the JSON line (identical on all ranks)."""
+    import hashlib
+    import torch
+    from lagrangian_microbes_b200.simulation import FusedSimulation
+    n = per_rank * world
+    rng = np.random.default_rng(12345)
+    side = float(np.sqrt(n / 27_800.0))                 # the shard's areal density: rho ~ 4.4 pairs per microbe
+    lon = (200.0 + side * rng.random(n)).astype(np.float32)
+    lat = (30.0 + side * rng.random(n)).astype(np.float32)
+    sp = rng.integers(1, 4, n).astype(np.int8)
+    out = {"twin_microbes": n, "steps": steps}
+
+    def digest(a, b, c):
+        h = hashlib.sha256()
+        for x in (a, b, c):
+            h.update(np.ascontiguousarray(x).tobytes())
+        return h.hexdigest()[:16]
+
+    single = None
+    if rank == 0:
+        single = FusedSimulation(lon, lat, sp, RADIUS, *P_RPS, hfs, dt_seconds=DT, seed=7, emit_pairs=(world == 1),
+                                 pair_capacity=24 * n, regrid_every=2, grid_margin=0.5)
+    if world == 1:
+        from oracle import pairs as opairs, philox, rk4 as ork4, rps as orps
+        fs = ork4.FieldSet(hfs.lon, hfs.lat, hfs.time, hfs.u, hfs.v)
+        pairs_ok = species_ok = True
+        rel, pairs_total = 0.0, 0
+        l0, a0, s0 = lon, lat, sp
+        for step in range(steps):
+            grid = single.grid.as_dict()
+            t0, ti0 = single.clock.t, single.clock.ti
+            st = single.step(check=True)
+            gl, ga, gs = single.download()
+            a64, b64, _, _ = ork4.rk4_step_f64(fs, l0, a0, t0, DT, ti0)
+            rel = max(rel, float(np.max(np.abs(gl - a64) / np.abs(a64))), float(np.max(np.abs(ga - b64) / np.abs(b64))))
+            want = opairs.query_pairs_reference_array(gl, ga, RADIUS)
+            got = opairs.sort_pairs(single.pairs[:st.n_pairs].cpu().numpy())
+            pairs_ok = pairs_ok and st.n_pairs == want.shape[0] and bool(np.array_equal(got, want))
+            order, _ = orps.canonical_order(want, gl, ga, grid, mode=single.engine.interact_mode)
+            u = philox.pair_uniforms(order[:, 0], order[:, 1], step, 7)
+            s_ref, _ = orps.rps_sequential_c(s0.copy(), order, u, *P_RPS)
+            species_ok = species_ok and bool(np.array_equal(gs, s_ref))
+            pairs_total += int(st.n_pairs)
+            l0, a0, s0 = gl, ga, gs
+        out.update({"against": "CPU oracle (float64 RK4 restatement, cKDTree.query_pairs, reference rule in canonical order)",
+                    "positions_rel_err": rel, "pairs_exact": pairs_ok, "species_exact": species_ok, "pairs": pairs_total,
+                    "checksum": digest(l0, a0, s0), "match": bool(pairs_ok and species_ok and rel < 1e-6)})
+        single.engine.close()
+        return out
+    from lagrangian_microbes_b200.strips import DistTransport, StripSet
+    import torch.distributed as dist
+    mine = slice(rank * per_rank, (rank + 1) * per_rank)                  # the reference's contiguous tiles
+    ids = np.arange(n, dtype=np.int32)
+    ss = StripSet(DistTransport(), lon[mine], lat[mine], sp[mine], ids[mine], n, RADIUS, *P_RPS, hfs, dt_seconds=DT, seed=7,
+                  emit_pairs=False, slack=1.6, grid_margin=0.5, regrid_every=2)
+    for _ in range(steps):
+        ss.step()
+        if single is not None:
+            single.step()
+    gl, ga, gs = ss.gather()                                               # every rank: all microbes in id order
+    ok = torch.ones(1, dtype=torch.int32, device="cuda")
+    if single is not None:
+        wl, wa, ws = single.download()
+        same = bool(np.array_equal(gl, wl) and np.array_equal(ga, wa) and np.array_equal(gs, ws))
+        ok[0] = 1 if same else 0
+        out["checksum_single_handle"] = digest(wl, wa, ws)
+        single.engine.close()
+    dist.broadcast(ok, src=0)
+    moved = ss.transport.all_sum([[float(s.engine.sync_stats().n_moved_in)] for s in ss.strips])
+    out.update({"against": "one handle stepping all twin microbes on rank 0 (bit for bit: positions, species)",
+                "checksum_strips": digest(gl, ga, gs), "strip_edges": [int(e) for e in ss.edges],
+                "migrated_last_step": int(moved[0]), "match": bool(int(ok[0]) == 1)})
+    ss.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (default 200; config1: the configuration's 24)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="shard", choices=["shard", "config2", "config3"])
+    ap.add_argument("--workload", default="shard", choices=["shard", "config1", "config2", "config3"])
     ap.add_argument("--microbes", type=int, default=0, help="microbes per GPU (0 = the workload's size)")
-    ap.add_argument("--spinup", type=int, default=-1, help="untimed steps before warm-up (config2 default 1500)")
+    ap.add_argument("--spinup", type=int, default=-1, help="untimed steps before warm-up (config2 default 1500; config1 default 120, advection only)")
     ap.add_argument("--modes", type=int, default=64, help="Fourier modes of the synthetic velocity field")
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="microbes in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity twin (tuning sweeps)")
     ap.add_argument("--packed-record", action="store_true",
                     help="e2e (N = 1, experiment): positions leave as the lossless delta-packed record (DESIGN.md 4.7), "
                          "stored packed -- not decoded inside the timed region")
@@ -239,14 +331,17 @@ def main():
     ap.add_argument("--tile-cap", type=int, default=0, help="LM_OPT_TILE_CAP (tuning experiments)")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+    if args.steps <= 0:
+        args.steps = 24 if args.workload == "config1" else 200
+    spinup = args.spinup if args.spinup >= 0 else {"config2": 1500, "config1": 120}.get(args.workload, 0)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n_per_gpu = args.microbes or default_n(args.workload)
     config = {"workload": args.workload, "microbes_per_gpu": n_per_gpu, "microbes_total": n_per_gpu * world,
-              "radius_deg": RADIUS, "p": P_RPS[0], "dt_s": DT, "field": "synthetic random-Fourier, OSCAR 1/3-degree grid "
-              "(72x481x1201), %d modes" % args.modes, "l2": "inputs larger than L2" if n_per_gpu >= 5_000_000
+              "radius_deg": RADIUS, "p": P_RPS[0], "dt_s": DT, "field": "synthetic %s, OSCAR 1/3-degree grid "
+              "(72x481x1201), %d modes" % ("steady eddy field" if args.workload == "config1" else "random-Fourier", args.modes), "l2": "inputs larger than L2" if n_per_gpu >= 5_000_000
               else "state fits L2 (config as specified)",
               "regrid": "bounding box read back every 16 steps (one small sync), cell grid re-fitted when the cloud nears its edge"}
 
@@ -255,20 +350,30 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 3))
+        same_size = args.workload in ("config1", "config2")
+        steps = max(1, min(args.steps, 24 if args.workload == "config1" else 3))
         warm = 1 if args.warmup > 0 else 0
-        res = run_cpu_reference(args.workload, args.cpu_sample, steps, warm, args.modes)
-        sample = "%d steps of a %d-microbe sub-box of the workload at the same areal density (%.0f pairs/step)" % (
-            steps, res["n_sample"], res["pairs_per_step"])
+        res = run_cpu_reference(args.workload, args.cpu_sample, steps, warm, args.modes, spinup=spinup)
+        if same_size:
+            sample = "the configuration itself: all %d microbes, %d steps after %d advection-only spin-up steps (%.0f pairs/step)" % (
+                res["n_sample"], steps, spinup, res["pairs_per_step"])
+        else:
+            sample = "%d steps of a %d-microbe sub-box of the workload at the same areal density (%.0f pairs/step)" % (
+                steps, res["n_sample"], res["pairs_per_step"])
+        # the reference line describes what the reference arm RAN: the sample, not the GPU arm's particle count
+        config["microbes_per_gpu"] = config["microbes_total"] = res["n_sample"]
+        config["sample_of"] = None if same_size else "%d microbes per GPU in the b200 arm" % n_per_gpu
         line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": steps, "warmup": warm, "ms_per_step": 1e3 * res["seconds"] / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 state / f64 arithmetic", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["threads"], "kind": "port",
                                  "sample": sample, "phases_s_per_step": res["phases_s_per_step"],
-                                 "note": "advect: C restatement of parcels' JIT kernel, OpenMP over all cores; pair "
-                                         "search: the reference's own cKDTree.query_pairs (1 core); RPS: the reference's "
-                                         "Python loop over the set with the rule restated in Python (1 core)"},
+                                 "note": "advect: C restatement of parcels' JIT kernel, contiguous tiles over all cores "
+                                         "(particle_advecter.py:143-148); pair search: the reference's own "
+                                         "cKDTree.query_pairs (1 core); RPS: the reference's Python loop over the set "
+                                         "calling the pair function restated with the reference's signature, dict look-ups "
+                                         "and np.random.rand() (1 core; interactions.py:13-40, interaction_simulator.py:104-105)"},
                 "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -299,7 +404,7 @@ def main():
         torch.cuda.synchronize()
 
     t_setup = time.time()
-    hfs = make_fieldset(args.modes)
+    hfs = make_fieldset(args.modes, field_kind(args.workload))
     lon, lat, species, desc = workload_particles(args.workload, n_per_gpu, rank, world)
     config.update(desc)
     log("[rank %d] setup: field + particles in %.1f s" % (rank, time.time() - t_setup))
@@ -342,6 +447,13 @@ def main():
                                pair_capacity=int(max(1 << 20, ppp * n_per_gpu)),
                                regrid_every=16, grid_margin=0.5, stream_field=stream_field)
 
+    parity = None
+    if not args.no_parity:
+        t_par = time.time()
+        parity = parity_twin(world, rank, hfs)
+        log("[rank %d] parity twin: %s in %.1f s" % (rank, "MATCH" if parity["match"] else "MISMATCH", time.time() - t_par))
+        torch.cuda.empty_cache()
+
     sim = new_sim(False)
     if args.draw_batch or args.tile_cap:
         from lagrangian_microbes_b200._lib import LM_OPT_DRAW_BATCH, LM_OPT_TILE_CAP
@@ -358,10 +470,20 @@ def main():
         sim.engine.set_option(LM_OPT_RESOLVE_MODE, args.resolve_mode)
         if args.tile_smem:
             sim.engine.set_option(LM_OPT_RESOLVE_TILE_SMEM, args.tile_smem)
-    spinup = args.spinup if args.spinup >= 0 else (1500 if args.workload == "config2" else 0)
-    for _ in range(spinup):
-        sim.step()
-    if args.workload == "config2":
+    def spin(sm):
+        if args.workload == "config1":               # advection only: strain the lattice until pairs exist (both arms do this)
+            assert world == 1
+            sm.interact, emit = False, sm.emit_pairs
+            sm.emit_pairs = False
+            for _ in range(spinup):
+                sm.step()
+            sm.interact, sm.emit_pairs = True, emit
+        else:
+            for _ in range(spinup):
+                sm.step()
+
+    spin(sim)
+    if args.workload in ("config1", "config2"):
         sim.step(check=True)
     for _ in range(args.warmup):
         sim.step()
@@ -405,8 +527,7 @@ def main():
         del sim
         torch.cuda.empty_cache()
         sim2 = new_sim(True)
-        for _ in range(spinup):
-            sim2.step()
+        spin(sim2)
         rec = [(torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(), torch.empty(n_per_gpu, dtype=torch.float32).pin_memory(),
                 torch.empty(n_per_gpu, dtype=torch.int8).pin_memory()) if world == 1 else () for _ in range(2)]
         packer = None
@@ -511,6 +632,7 @@ def main():
         "dtype": "f32 state / f64 arithmetic", "data": "synthetic", "config": config,
         "pairs_per_step": pairs_total, "pairs_per_s": pairs_total * args.steps / (ms * 1e-3), "rho": rho,
         "gpu_launches": launches_total,
+        "parity": parity,
         "clocks": clocks,
         "phases_ms": {"advect": float(phase[0]), "bin": float(phase[1]), "pair_search": float(phase[2]),
                       "rps_resolve": float(phase[3]), "stats": float(phase[4])},
@@ -529,9 +651,11 @@ def main():
         if "record" in e2e:
             line["e2e"]["record"] = e2e["record"]
     if world == 1 and not args.no_cpu_baseline:
-        res = run_cpu_reference(args.workload, args.cpu_sample, 2, 1, args.modes)
+        res = run_cpu_reference(args.workload, args.cpu_sample, 2, 1, args.modes, spinup=spinup)
         line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["threads"], "kind": "port",
-                                "sample": "2 steps of a %d-microbe sub-box at the workload's areal density (%.0f pairs/step)"
+                                "sample": ("2 steps of the configuration itself, all %d microbes (%.0f pairs/step)"
+                                           if args.workload in ("config1", "config2") else
+                                           "2 steps of a %d-microbe sub-box at the workload's areal density (%.0f pairs/step)")
                                           % (res["n_sample"], res["pairs_per_step"]),
                                 "phases_s_per_step": res["phases_s_per_step"]}
     sys.stdout.flush()

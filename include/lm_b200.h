@@ -282,12 +282,18 @@ int lm_reset_stats(lm_handle h, void *stream);
  *                     (csrc/pairs.cu, oracle/rps.py::cell_phase_order).  Same pair set; the species differ because the
  *                     (arbitrary but fixed) sequential order differs -- each is exact against the reference rule run in
  *                     its own order.
- *   LM_OPT_DRAW_BATCH  fused pass: lanes waiting for a Philox draw that make their warp run the draws (0 = default 20)
+ *   LM_OPT_DRAW_BATCH  fused pass, lane walk: lanes waiting for a Philox draw that make their warp run the draws (0 = default 8)
  *   LM_OPT_TILE_CAP    fused pass: microbes a tile stages in shared memory (0 = 1.5 x the mean tile occupancy); fuller
  *                     tiles work on the global arrays through the same code */
 #define LM_OPT_INTERACT_MODE 13
 #define LM_OPT_DRAW_BATCH 14
 #define LM_OPT_TILE_CAP 15
+/*   LM_OPT_TILE_REC_CAP  fused pass: records (found pairs of one direction) a tile holds in shared memory (0 = twice the
+ *                     staged microbes); a direction with more takes the lane walk (same results)
+ *   LM_OPT_TILE_PATH   fused pass: 0 (default) records in shared memory wherever they fit; 1 the lane walk everywhere --
+ *                     same results, for tests and A/B measurements */
+#define LM_OPT_TILE_REC_CAP 16
+#define LM_OPT_TILE_PATH 17
 /* tile of the fused interaction pass, in cells: part of the definition of its canonical pair order.  Strip boundaries
  * (lm_set_strip) must sit on multiples of LM_TILE_H rows in this mode. */
 #define LM_TILE_W 32

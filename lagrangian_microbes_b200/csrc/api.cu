@@ -5,6 +5,7 @@
 #include <new>
 
 #include "lm_internal.cuh"
+#include "philox.cuh"
 
 namespace lm {
 
@@ -127,6 +128,8 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     h->interact_mode = 1;
     h->draw_batch = 0;
     h->tile_cap = 0;
+    h->tile_rec_cap = 0;
+    h->tile_path = 0;
     h->resolve_tile_smem = 32768;
     h->resolve_batch = 4;      // measured on B200 (profiles/r1y_sweep_resolve.jsonl): 4 beats 1 and 8 on every workload
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
@@ -430,6 +433,7 @@ static RpsDev to_dev(const lm_rps_params *p)
     d.pRS = p->pRS; d.pPR = p->pPR; d.pSP = p->pSP;
     d.seed_lo = (uint32_t)p->seed; d.seed_hi = (uint32_t)(p->seed >> 32);
     d.step_lo = (uint32_t)p->step; d.step_hi = (uint32_t)(p->step >> 32);
+    d.pair_key = pair_stream_key(p->seed, p->step);
     return d;
 }
 
@@ -891,8 +895,16 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
             h->draw_batch = (int)value;
             return LM_OK;
         case LM_OPT_TILE_CAP:
-            if (value < 0 || value > 16384) return LM_EINVAL;
+            if (value < 0 || value > 6144) return LM_EINVAL;
             h->tile_cap = (int)value;
+            return LM_OK;
+        case LM_OPT_TILE_REC_CAP:
+            if (value < 0 || value > 16384) return LM_EINVAL;
+            h->tile_rec_cap = (int)value;
+            return LM_OK;
+        case LM_OPT_TILE_PATH:
+            if (value < 0 || value > 1) return LM_EINVAL;
+            h->tile_path = (int)value;
             return LM_OK;
         case LM_OPT_ADVECT_MODE:
             if (value < 0 || value > 1) return LM_EINVAL;

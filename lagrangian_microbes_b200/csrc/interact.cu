@@ -14,23 +14,29 @@
 //
 // CANONICAL ORDER ("tile-round order", oracle/rps.py::tile_round_order).  Cells are grouped into tiles of 32 x 16
 // cells.  A unit is one cell or two adjacent cells (half stencil E, NW, N, NE).  Phases 0-8: the units inside one tile
-// (same cell | east, cx even / odd | NW, N, NE, cy even | the same, cy odd); phases 9-14: the units across a tile
-// boundary (east | NW, NE across a vertical boundary | NW, N, NE across a horizontal one).  Units of one phase touch
-// disjoint microbes.  Inside a unit the pairs are taken in ROUNDS OF MATCHINGS: two cells with m_a, m_b microbes
-// ranked by id, M = max(m_a, m_b): round k pairs rank i with rank (i + k) mod M; one cell: the circle method of
-// round-robin tournaments.  No microbe occurs twice in a round, so a round is order-free: a cell of 600 microbes is
-// 600 rounds of 300 independent pairs instead of 180,000 sequential ones.  The result is by construction the
-// reference's sequential in-place loop run in that total order (checked against the unmodified reference function).
+// (0 same cell | 1, 2 east, cx even / odd | 3, 4 north-west, cy even / odd | 5, 6 north | 7, 8 north-east); phases 9-14:
+// the units across a tile boundary (east | NW, NE across a vertical boundary | NW, N, NE across a horizontal one).
+// Units of one phase touch disjoint microbes.  Inside a unit:
+//   LIGHT units (two cells: m_a * m_b <= 256 and m_b <= 64; one cell: m <= 23) -- (rank in the anchor cell, rank in the
+//       other cell) lexicographic, ranks by particle id; a handful of pairs, walked by one lane;
+//   HEAVY units -- ROUNDS OF MATCHINGS: two cells, M = max(m_a, m_b): round k pairs rank i with rank (i + k) mod M; one
+//       cell: the circle method of round-robin tournaments.  No microbe occurs twice in a round, so a round is
+//       order-free: a cell of 600 microbes is 600 rounds of 300 independent pairs instead of 180,000 sequential ones.
+// The result is by construction the reference's sequential in-place loop run in that total order (checked against the
+// unmodified reference function).
 //
-// KERNELS.  interact_tile_kernel: one CTA per tile.  The tile's microbes (positions, ids, species: 13 B each) are
-// staged in shared memory (a tile that does not fit works on the global arrays through the same code), then phase
-// after phase with __syncthreads() in between: every lane walks the slots of its units -- distance test, pair
-// emission, species compare -- and the Philox draw, needed only when the two species differ at that moment
-// (interactions.py:17-20), is taken OUT of the walk: a lane that needs one parks, and the warp runs the ten Philox
-// rounds when enough lanes are parked, so the draw costs its ~100 instructions at a useful lane occupancy instead of
-// once per slot.  Units above 255 slots go to a queue and are resolved round by round by a whole warp, above 8,192 by
-// the whole CTA.  interact_cross_kernel: the same walk for the units of one boundary phase, from global memory
-// (a few per cent of the pairs).  Pairs are staged per CTA and flushed in blocks (one atomic per flush).
+// KERNELS.  interact_tile_kernel: one CTA per tile, the tile's microbes (positions, ids, species, cell) staged in
+// shared memory.  Per direction (same cell, E, NW, N, NE):
+//   F  every microbe is a lane: distance tests against the partner cell, hits recorded as (anchor, partner) records in
+//      shared memory, contiguous per anchor; then the records are finished DENSELY, lanes <-> records of the whole tile:
+//      ids, pair emission (coalesced, one atomic per CTA and direction), and the Philox draw for the records whose two
+//      species differ at that moment -- so the draw, the most expensive operation of the step, runs at full lane
+//      occupancy and only where the rule can consume it (interactions.py:17-20);
+//   R  per parity (one phase each): a lane walks the records of its unit in canonical order against the species in
+//      shared memory (a record without a draw whose species have meanwhile come to differ draws on the spot).
+// Heavy units go to a queue and are resolved round by round by a whole warp (above 8,192 slots by the whole CTA).  A
+// tile that does not fit in shared memory, or whose records overflow, runs the same order through a plain lane walk
+// (walk_light) -- as do the units of the boundary phases in interact_cross_kernel (a few per cent of the pairs).
 //
 // Predicate: exactly SciPy's (float32 positions widened to double, s = fl(dx*dx); s = fl(s + fl(dy*dy)); s <= fl(r*r));
 // a float32 evaluation decides everything farther than 4e-6 (relative) from the threshold.  p = 1 / inf likewise.
@@ -44,12 +50,13 @@ namespace {
 
 constexpr int IT_TW = LM_TILE_W, IT_TH = LM_TILE_H;
 constexpr int IT_THREADS = 256;
-constexpr int IT_WARPS = IT_THREADS / 32;
 constexpr int IT_CELLS = IT_TW * IT_TH;
 constexpr int IT_UPT = IT_CELLS / IT_THREADS;            // cells a thread looks at when the units of a phase are listed
-constexpr int IT_STAGE = 1024;                            // pairs staged per CTA between flushes
-constexpr unsigned int IT_LIGHT_MAX = 255;                // slots of a unit that one lane walks alone
-constexpr unsigned int IT_MEGA_MIN = 8192;                // slots from which the whole CTA takes a unit
+constexpr int IT_STAGE = 512;                             // pairs staged per CTA between flushes (walk / heavy paths)
+constexpr unsigned int IT_MEGA_MIN = 8192;                // slots from which the whole CTA takes a heavy unit
+constexpr int IT_MAX_TILE_CAP = 6144;                     // microbes a tile can stage (13-bit local indices in a record)
+constexpr unsigned int REC_IDX = 0x1fffu;                 // record: anchor (13 bits) | partner << 13 | draw bits << 26 | has draw << 29
+constexpr unsigned int REC_HAS_DRAW = 1u << 29;
 constexpr unsigned int FULL = 0xffffffffu;
 static_assert(IT_TW == 32 && IT_TH % 2 == 0 && IT_CELLS % IT_THREADS == 0, "tile geometry");
 
@@ -64,13 +71,15 @@ struct IArgs {
     int norm;
     float r2_lo, r2_hi;                  // float32 pre-filter window around the threshold
     double r2;                           // the exact threshold (r*r for p = 2, r for p = 1 and p = inf)
-    uint32_t seed_lo, seed_hi, step_lo, step_hi;
+    uint32_t pair_key;                   // key of this step's per-pair Philox2x32 stream (philox.cuh)
     unsigned long long thr[3];           // ceil(p * 2^53) for pRS, pPR, pSP
     int2 *__restrict__ pairs;            // null: count only
     unsigned long long cap_pairs;
     Counters *ctr;
     int tile_cap;                        // microbes a tile can stage in shared memory
-    int draw_batch;                      // parked lanes that trigger the warp's Philox rounds
+    int rec_cap;                         // records (hits of one direction) a tile can hold in shared memory
+    int draw_batch;                      // lane walk: parked lanes that trigger the warp's Philox rounds
+    int force_walk;                      // LM_OPT_TILE_PATH = 1: staged tiles take the lane walk too (tests)
     int phase;                           // interact_cross_kernel: 9..14
 };
 
@@ -87,9 +96,7 @@ __device__ __forceinline__ bool is_rps(int s) { return s >= 1 && s <= 3; }
 // three decision bits of the pair's draw: bit k set <=> u < p_k  (k = 0: pRS, 1: pPR, 2: pSP); u = m * 2^-53
 __device__ __forceinline__ uint32_t decision_bits(const IArgs &A, int i, int j)
 {
-    uint32_t x[4];
-    philox4x32_10((uint32_t)i, (uint32_t)j, A.step_lo, A.step_hi, A.seed_lo, A.seed_hi, x);
-    const unsigned long long m = ((unsigned long long)(x[0] >> 5) << 26) | (unsigned long long)(x[1] >> 6);
+    const unsigned long long m = pair_draw_m((uint32_t)i, (uint32_t)j, A.pair_key);
     return (m < A.thr[0] ? 1u : 0u) | (m < A.thr[1] ? 2u : 0u) | (m < A.thr[2] ? 4u : 0u);
 }
 
@@ -111,17 +118,39 @@ __device__ __forceinline__ bool within(const IArgs &A, float2 a, float2 b)
     return within_exact(A.norm, a, b, A.r2);
 }
 
+// ---- light / heavy: part of the definition of the canonical order (oracle/rps.py::tile_round_order) -------------
+__device__ __forceinline__ bool unit_is_light(bool same, unsigned int ma, unsigned int mb)
+{
+    return same ? ma <= 23u : (ma * mb <= 256u && mb <= 64u);
+}
+__device__ __forceinline__ bool unit_has_pairs(bool same, unsigned int ma, unsigned int mb)
+{
+    return same ? ma >= 2u : (ma >= 1u && mb >= 1u);
+}
+// slots of a heavy unit walked in rounds (decides warp vs whole CTA)
+__device__ __forceinline__ unsigned int unit_slots(bool same, unsigned int ma, unsigned int mb)
+{
+    if (same) { const unsigned int M = ma + (ma & 1u); return (M - 1u) * (M >> 1); }
+    return ma * max(ma, mb);
+}
+
 // ---- where a tile's microbes live: shared memory (staged) or the global arrays ----------------------------------
 struct SmemView {
+    static constexpr bool kStaged = true;
     const float2 *pos;
     const int32_t *id;
     int8_t *sp;
+    const uint16_t *pcell;               // (row in tile) << 5 | column in tile
+    uint16_t *hstart;                    // first record of the microbe in the current direction
+    uint8_t *hcnt;                       // its records
+    uint32_t *rec;                       // records of the current direction
     __device__ __forceinline__ float2 P(int i) const { return pos[i]; }
     __device__ __forceinline__ int I(int i) const { return id[i]; }
     __device__ __forceinline__ int S(int i) const { return ((volatile int8_t *)sp)[i]; }
     __device__ __forceinline__ void W(int i, int s) const { ((volatile int8_t *)sp)[i] = (int8_t)s; }
 };
 struct GlobalView {
+    static constexpr bool kStaged = false;
     const float *lon, *lat;
     const int32_t *id;
     int8_t *sp;
@@ -133,11 +162,12 @@ struct GlobalView {
 
 // ---- CTA-wide working set in shared memory ----------------------------------------------------------------------
 struct Shared {
-    int2 stage[IT_STAGE];                 // found pairs waiting for the next flush
+    int2 stage[IT_STAGE];                 // found pairs waiting for the next flush (walk / heavy paths)
     uint4 unit[IT_CELLS];                 // units of the current phase: x a_base | y b_base | z m_a | w m_b (b_base == a_base: one cell)
     unsigned int n_light, n_heavy;        // light units grow from the front of unit[], heavy ones from the back
     unsigned int ticket, hticket;
     unsigned int stage_cnt;
+    unsigned int rec_used;                // records of the current direction
     unsigned long long flush_base;
 };
 
@@ -179,57 +209,24 @@ __device__ void flush_pairs(const IArgs &A, Shared &sh, bool force)
     __syncthreads();
 }
 
-// ---- slot generators --------------------------------------------------------------------------------------------
-// Two cells: round k in [0, M), slot i in [0, m_a): anchor rank i with partner rank (i + k) mod M  (valid if < m_b).
+// ---- light units walked by one lane: (anchor rank, partner rank) lexicographic ----------------------------------
 struct CrossWalk {
-    int a_base, b_base, ma, mb, M, i, j, k;
-    __device__ __forceinline__ void init(const uint4 &u)
-    {
-        a_base = (int)u.x; b_base = (int)u.y; ma = (int)u.z; mb = (int)u.w;
-        M = max(ma, mb); i = 0; j = 0; k = 0;
-    }
-    __device__ __forceinline__ bool valid() const { return j < mb; }
+    int a_base, b_base, ma, mb, i, j;
+    __device__ __forceinline__ void init(const uint4 &u) { a_base = (int)u.x; b_base = (int)u.y; ma = (int)u.z; mb = (int)u.w; i = 0; j = 0; }
     __device__ __forceinline__ int a() const { return a_base + i; }
     __device__ __forceinline__ int b() const { return b_base + j; }
-    __device__ __forceinline__ bool next()                           // false: the unit is done
-    {
-        ++i; ++j;
-        if (j == M) j = 0;
-        if (i == ma) { i = 0; ++k; j = k; if (k == M) return false; }
-        return true;
-    }
+    __device__ __forceinline__ bool next() { if (++j == mb) { j = 0; if (++i == ma) return false; } return true; }   // false: done
 };
-// One cell, m microbes, M = m rounded up to even: round k in [0, M - 1), slot 0: rank M - 1 with rank k;
-// slot jj in [1, M / 2): rank (k + jj) mod (M - 1) with rank (k - jj) mod (M - 1).  Rank m (m odd) is a phantom.
 struct SameWalk {
-    int base, m, M, n1, k, jj, p, q;
-    __device__ __forceinline__ void init(const uint4 &u)
-    {
-        base = (int)u.x; m = (int)u.z; M = m + (m & 1); n1 = M - 1; k = 0; jj = 0; p = 0; q = 0;
-    }
-    __device__ __forceinline__ int ra() const { return jj == 0 ? M - 1 : p; }
-    __device__ __forceinline__ int rb() const { return jj == 0 ? k : q; }
-    __device__ __forceinline__ bool valid() const { return ra() < m && rb() < m; }
-    __device__ __forceinline__ int a() const { return base + min(ra(), rb()); }     // smaller rank = smaller id first
-    __device__ __forceinline__ int b() const { return base + max(ra(), rb()); }
-    __device__ __forceinline__ bool next()
-    {
-        ++jj;
-        if (jj == (M >> 1)) { jj = 0; ++k; p = q = k; return k < n1; }
-        ++p; if (p >= n1) p -= n1;
-        --q; if (q < 0) q += n1;
-        return true;
-    }
+    int base, m, i, j;
+    __device__ __forceinline__ void init(const uint4 &u) { base = (int)u.x; m = (int)u.z; i = 0; j = 1; }
+    __device__ __forceinline__ int a() const { return base + i; }
+    __device__ __forceinline__ int b() const { return base + j; }
+    __device__ __forceinline__ bool next() { if (++j == m) { ++i; j = i + 1; if (j >= m) return false; } return true; }
 };
 
-// slots of a unit (what one lane would have to walk)
-__device__ __forceinline__ unsigned int unit_slots(bool same, unsigned int ma, unsigned int mb)
-{
-    if (same) { const unsigned int M = ma + (ma & 1u); return ma < 2 ? 0u : (M - 1u) * (M >> 1); }
-    return (ma == 0 || mb == 0) ? 0u : ma * max(ma, mb);
-}
-
-// ---- light units: every lane walks its own units, the Philox draws are batched per warp ------------------------
+// Every lane walks its own units; a lane whose pair needs a draw parks, and the warp runs the Philox rounds when enough
+// lanes are parked (or nobody can advance), so that the draw is paid at a useful lane occupancy.
 template <class V, class Walk, bool DO_RPS>
 __device__ void walk_light(const IArgs &A, Shared &sh, const V &v)
 {
@@ -257,11 +254,9 @@ __device__ void walk_light(const IArgs &A, Shared &sh, const V &v)
         bool hit = false;
         int ia = 0, ib = 0;
         if (can) {
-            if (w.valid()) {
-                ia = w.a(); ib = w.b();
-                hit = within(A, v.P(ia), v.P(ib));
-            }
-            if (!w.next()) {                                          // next unit (its first slot is taken next iteration)
+            ia = w.a(); ib = w.b();
+            hit = within(A, v.P(ia), v.P(ib));
+            if (!w.next()) {                                          // next unit (its first pair is taken next iteration)
                 t = atomicAdd(&sh.ticket, 1u);
                 if (t < n_units) w.init(sh.unit[t]); else active = false;
             }
@@ -276,6 +271,7 @@ __device__ void walk_light(const IArgs &A, Shared &sh, const V &v)
     }
 }
 
+// ---- heavy units: rounds of matchings ---------------------------------------------------------------------------
 // One slot of a cooperative (warp / CTA) round: everything inline, the lanes of a round hold disjoint pairs.
 template <class V, bool DO_RPS>
 __device__ __forceinline__ void slot_inline(const IArgs &A, Shared &sh, const V &v, bool valid, int ia, int ib)
@@ -296,6 +292,9 @@ __device__ __forceinline__ void slot_inline(const IArgs &A, Shared &sh, const V 
 
 // A unit round by round with `nthr` threads (32: one warp, __syncwarp between rounds; IT_THREADS: the CTA,
 // __syncthreads between rounds -- then every thread of the CTA calls this with the same unit).
+//   two cells, M = max(m_a, m_b): round k in [0, M) pairs rank i of the anchor cell with rank (i + k) mod M of the other
+//   one cell, M = m rounded up to even (rank M - 1 is a phantom when m is odd): round k in [0, M - 1) pairs rank M - 1
+//       with rank k and rank (k + j) mod (M - 1) with rank (k - j) mod (M - 1) for j in [1, M / 2)
 template <class V, bool DO_RPS, bool CTA>
 __device__ void unit_rounds(const IArgs &A, Shared &sh, const V &v, const uint4 u)
 {
@@ -365,11 +364,9 @@ __device__ void run_units(const IArgs &A, Shared &sh, const V &v, bool same)
     flush_pairs(A, sh, false);
 }
 
-// Append a unit to the list; all 32 lanes of the warp call this converged (`have`: this lane has one).
-__device__ __forceinline__ void push_unit(Shared &sh, bool have, bool same, uint4 u)
+// Append a unit to the list; all 32 lanes of the warp call this converged (`light` / `heavy`: this lane has one).
+__device__ __forceinline__ void push_unit(Shared &sh, bool light, bool heavy, uint4 u)
 {
-    const unsigned int slots = have ? unit_slots(same, u.z, u.w) : 0u;
-    const bool light = slots > 0 && slots <= IT_LIGHT_MAX, heavy = slots > IT_LIGHT_MAX;
     const int lane = threadIdx.x & 31;
     const unsigned int ml = __ballot_sync(FULL, light), mh = __ballot_sync(FULL, heavy);
     if (ml) {
@@ -388,46 +385,156 @@ __device__ __forceinline__ void push_unit(Shared &sh, bool have, bool same, uint
     }
 }
 
-// ---- stage I: the units inside one tile, phases 0..8 -----------------------------------------------------------
+// ---- stage I: the units inside one tile ---------------------------------------------------------------------------
+// direction of a group: 0 same cell, 1 E, 2 NW, 3 N, 4 NE; phases: 0 | 1, 2 | 3, 4 | 5, 6 | 7, 8 (parity of cx for E, of cy else)
+struct TileGeom {
+    const int (*cs)[IT_TW + 1];          // cell_start of the tile's cells (global particle indices), one more per row
+    const int *delta;                    // local index = global index + delta[row]
+    int w, hgt;
+};
+
+// the unit anchored at cell (t, x) in direction g: false if its partner cell is not in this tile
+__device__ __forceinline__ bool unit_of_cell(const TileGeom &G, int g, int t, int x, uint4 &u)
+{
+    int to = t, xo = x;
+    if (g == 1) xo = x + 1;
+    else if (g >= 2) { to = t + 1; xo = x + (g - 3); }
+    if (t >= G.hgt || x >= G.w || to >= G.hgt || xo < 0 || xo >= G.w) return false;
+    const int a0 = G.cs[t][x], a1 = G.cs[t][x + 1], b0 = G.cs[to][xo], b1 = G.cs[to][xo + 1];
+    u = make_uint4((unsigned int)(a0 + G.delta[t]), (unsigned int)(b0 + G.delta[to]), (unsigned int)(a1 - a0), (unsigned int)(b1 - b0));
+    return true;
+}
+
+// F of one direction on a staged tile: records of every light unit of direction g, contiguous per anchor.  Returns
+// false (CTA-uniform) if they do not fit -- nothing has been emitted then, and the direction takes the lane walk.
+template <bool DO_RPS>
+__device__ bool find_direction(const IArgs &A, Shared &sh, const SmemView &v, const TileGeom &G, int g, int total)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) sh.rec_used = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < total; p0 += IT_THREADS) {
+        const int p = p0 + tid;
+        int nc = 0, beg = 0;
+        float2 pa = make_float2(0.f, 0.f);
+        if (p < total) {
+            const int pc = v.pcell[p];
+            uint4 u;
+            if (unit_of_cell(G, g, pc >> 5, pc & 31, u) && unit_is_light(g == 0, u.z, u.w)) {
+                if (g == 0) { beg = p + 1; nc = (int)(u.x + u.z) - beg; }
+                else { beg = (int)u.y; nc = (int)u.w; }
+                pa = v.pos[p];
+            }
+        }
+        unsigned long long mask = 0;
+        for (int i = 0; i < nc; ++i)
+            if (within(A, pa, v.pos[beg + i])) mask |= 1ull << i;
+        const unsigned int cnt = (unsigned int)__popcll(mask);
+        unsigned int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int up = __shfl_up_sync(FULL, incl, d);
+            if (lane >= d) incl += up;
+        }
+        const unsigned int wtotal = __shfl_sync(FULL, incl, 31);
+        unsigned int wbase = 0;
+        if (lane == 0 && wtotal) wbase = atomicAdd(&sh.rec_used, wtotal);
+        wbase = __shfl_sync(FULL, wbase, 0);
+        unsigned int pos = wbase + incl - cnt;
+        if (p < total) { v.hstart[p] = (uint16_t)min(pos, 0xffffu); v.hcnt[p] = (uint8_t)cnt; }
+        if (wbase + wtotal <= (unsigned int)A.rec_cap)
+            for (; mask; mask &= mask - 1)
+                v.rec[pos++] = (unsigned int)p | ((unsigned int)(beg + __ffsll((long long)mask) - 1) << 13);
+    }
+    __syncthreads();
+    const unsigned int n_rec = sh.rec_used;                           // CTA-uniform
+    if (n_rec > (unsigned int)A.rec_cap) return false;
+    // ---- finish densely: lanes <-> records of the whole tile
+    if (n_rec) {
+        if (tid == 0) sh.flush_base = atomicAdd(&A.ctr->n_pairs, (unsigned long long)n_rec);
+        __syncthreads();
+        const unsigned long long base = sh.flush_base;
+        for (unsigned int e = tid; e < n_rec; e += IT_THREADS) {
+            unsigned int r = v.rec[e];
+            const int a = (int)(r & REC_IDX), b = (int)((r >> 13) & REC_IDX);
+            const int x = v.id[a], y = v.id[b];
+            const int lo = min(x, y), hi = max(x, y);
+            if (A.pairs && base + e < A.cap_pairs) A.pairs[base + e] = make_int2(lo, hi);
+            if (DO_RPS) {
+                const int sa = v.sp[a], sb = v.sp[b];
+                if (sa != sb && is_rps(sa) && is_rps(sb)) v.rec[e] = r | (decision_bits(A, lo, hi) << 26) | REC_HAS_DRAW;
+            }
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
+// R: one lane resolves one light unit from its records, in canonical order (anchor rank, partner rank)
+__device__ __forceinline__ void resolve_records(const IArgs &A, const SmemView &v, const uint4 &u)
+{
+    const int a_end = (int)(u.x + u.z);
+    for (int a = (int)u.x; a < a_end; ++a) {
+        const int hc = v.hcnt[a];
+        if (!hc) continue;
+        const uint32_t *r = v.rec + v.hstart[a];
+        const int sa0 = v.sp[a];
+        int sa = sa0;
+        for (int h = 0; h < hc; ++h) {
+            const uint32_t e = r[h];
+            const int b = (int)((e >> 13) & REC_IDX);
+            const int sb = v.sp[b];
+            if (sa != sb && is_rps(sa) && is_rps(sb)) {
+                uint32_t dec;
+                if (e & REC_HAS_DRAW) dec = (e >> 26) & 7u;
+                else { const int x = v.id[a], y = v.id[b]; dec = decision_bits(A, min(x, y), max(x, y)); }   // came to differ since F
+                const int s = rps_apply(sa, sb, dec);
+                if (s != sa) sa = s; else v.sp[b] = (int8_t)s;
+            }
+        }
+        if (sa != sa0) v.sp[a] = (int8_t)sa;
+    }
+}
+
 template <class V, bool DO_RPS>
-__device__ void tile_phases(const IArgs &A, Shared &sh, const V &v, const int (*s_cs)[IT_TW + 1], const int *s_delta,
-                            int w, int hgt)
+__device__ void tile_phases(const IArgs &A, Shared &sh, const V &v, const TileGeom &G, int total)
 {
     const int tid = threadIdx.x;
-    for (int ph = 0; ph < 9; ++ph) {
-        if (tid == 0) { sh.n_light = 0; sh.n_heavy = 0; sh.ticket = IT_THREADS; sh.hticket = 0; }
-        __syncthreads();
-        const bool same = ph == 0;
-#pragma unroll
-        for (int q = 0; q < IT_UPT; ++q) {
-            const int e = tid + q * IT_THREADS;
-            const int t = e >> 5, x = e & 31;                         // IT_TW == 32
-            bool have = t < hgt && x < w;
-            int to = t, xo = x;
-            if (ph == 0) { }
-            else if (ph <= 2) { have = have && (x & 1) == ph - 1 && x + 1 < w; xo = x + 1; }
-            else {
-                const int par = (ph - 3) / 3, dir = (ph - 3) % 3 - 1;
-                xo = x + dir; to = t + 1;
-                have = have && (t & 1) == par && to < hgt && xo >= 0 && xo < w;
-            }
-            uint4 u = make_uint4(0u, 0u, 0u, 0u);
-            if (have) {
-                const int a0 = s_cs[t][x], a1 = s_cs[t][x + 1];
-                const int b0 = s_cs[to][xo], b1 = s_cs[to][xo + 1];
-                u = make_uint4((unsigned int)(a0 + s_delta[t]), (unsigned int)(b0 + s_delta[to]), (unsigned int)(a1 - a0),
-                               (unsigned int)(b1 - b0));
-            }
-            push_unit(sh, have, same, u);
+    for (int g = 0; g < 5; ++g) {
+        bool records = false;
+        if constexpr (V::kStaged) {
+            if (!A.force_walk) records = find_direction<DO_RPS>(A, sh, v, G, g, total);
         }
-        run_units<V, DO_RPS>(A, sh, v, same);
+        for (int par = 0; par < (g == 0 ? 1 : 2); ++par) {            // one phase
+            if (tid == 0) { sh.n_light = 0; sh.n_heavy = 0; sh.ticket = IT_THREADS; sh.hticket = 0; }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < IT_UPT; ++q) {
+                const int e = tid + q * IT_THREADS;
+                const int t = e >> 5, x = e & 31;                     // IT_TW == 32
+                uint4 u = make_uint4(0u, 0u, 0u, 0u);
+                bool have = (g == 0 || ((g == 1 ? x : t) & 1) == par) && unit_of_cell(G, g, t, x, u);
+                have = have && unit_has_pairs(g == 0, u.z, u.w);
+                const bool light = have && unit_is_light(g == 0, u.z, u.w);
+                bool listed = light;
+                if constexpr (V::kStaged) {
+                    if (records) {
+                        listed = false;
+                        if (DO_RPS && light) resolve_records(A, v, u);
+                    }
+                }
+                push_unit(sh, listed, have && !light, u);
+            }
+            run_units<V, DO_RPS>(A, sh, v, g == 0);
+        }
     }
 }
 
 template <bool DO_RPS>
 __global__ void __launch_bounds__(IT_THREADS) interact_tile_kernel(IArgs A)
 {
-    extern __shared__ __align__(16) unsigned char s_dyn[];            // float2 pos[cap] | int32 id[cap] | int8 sp[cap]
+    // float2 pos[cap] | uint32 rec[rec_cap] | int32 id[cap] | uint16 pcell[cap] | uint16 hstart[cap] | int8 sp[cap] | uint8 hcnt[cap]
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ Shared sh;
     __shared__ int s_cs[IT_TH][IT_TW + 1];
     __shared__ int s_delta[IT_TH];
@@ -435,7 +542,10 @@ __global__ void __launch_bounds__(IT_THREADS) interact_tile_kernel(IArgs A)
     const int tid = threadIdx.x;
     const int tx = blockIdx.x % A.tiles_x, ty = blockIdx.x / A.tiles_x;
     const int x0 = tx * IT_TW, y0 = ty * IT_TH;
-    const int w = min(IT_TW, A.ncx - x0), hgt = min(IT_TH, A.rows_owned - y0);
+    TileGeom G;
+    G.cs = s_cs; G.delta = s_delta;
+    G.w = min(IT_TW, A.ncx - x0); G.hgt = min(IT_TH, A.rows_owned - y0);
+    const int w = G.w, hgt = G.hgt;
     for (int k = tid; k < hgt * (w + 1); k += IT_THREADS) {
         const int t = k / (w + 1), x = k - t * (w + 1);
         s_cs[t][x] = __ldg(A.cell_start + (long long)(y0 + t) * A.ncx + x0 + x);
@@ -451,20 +561,29 @@ __global__ void __launch_bounds__(IT_THREADS) interact_tile_kernel(IArgs A)
     const int total = s_total;
     if (total < 2) return;                                            // CTA-uniform: no pair inside this tile
     if (total <= A.tile_cap) {
+        const int cap = A.tile_cap;
         float2 *s_pos = reinterpret_cast<float2 *>(s_dyn);
-        int32_t *s_id = reinterpret_cast<int32_t *>(s_pos + A.tile_cap);
-        int8_t *s_sp = reinterpret_cast<int8_t *>(s_id + A.tile_cap);
+        uint32_t *s_rec = reinterpret_cast<uint32_t *>(s_pos + cap);
+        int32_t *s_id = reinterpret_cast<int32_t *>(s_rec + A.rec_cap);
+        uint16_t *s_pcell = reinterpret_cast<uint16_t *>(s_id + cap);
+        uint16_t *s_hstart = s_pcell + cap;
+        int8_t *s_sp = reinterpret_cast<int8_t *>(s_hstart + cap);
+        uint8_t *s_hcnt = reinterpret_cast<uint8_t *>(s_sp + cap);
         for (int t = 0; t < hgt; ++t) {
             const int p0 = s_cs[t][0], cnt = s_cs[t][w] - p0, d = s_delta[t] + p0;
             for (int i = tid; i < cnt; i += IT_THREADS) {
-                s_pos[d + i] = make_float2(__ldg(A.lon + p0 + i), __ldg(A.lat + p0 + i));
-                s_id[d + i] = __ldg(A.id + p0 + i);
-                if (DO_RPS) s_sp[d + i] = A.sp[p0 + i];
+                const int gi = p0 + i;
+                s_pos[d + i] = make_float2(__ldg(A.lon + gi), __ldg(A.lat + gi));
+                s_id[d + i] = __ldg(A.id + gi);
+                if (DO_RPS) s_sp[d + i] = A.sp[gi];
+                int lo = 0, hi = w;                                   // the cell: cs[t][lo] <= gi < cs[t][lo + 1]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_cs[t][mid] <= gi) lo = mid; else hi = mid; }
+                s_pcell[d + i] = (uint16_t)((t << 5) | lo);
             }
         }
         __syncthreads();
-        SmemView v{s_pos, s_id, s_sp};
-        tile_phases<SmemView, DO_RPS>(A, sh, v, s_cs, s_delta, w, hgt);
+        SmemView v{s_pos, s_id, s_sp, s_pcell, s_hstart, s_hcnt, s_rec};
+        tile_phases<SmemView, DO_RPS>(A, sh, v, G, total);
         if (DO_RPS) {
             for (int t = 0; t < hgt; ++t) {
                 const int p0 = s_cs[t][0], cnt = s_cs[t][w] - p0, d = s_delta[t] + p0;
@@ -476,7 +595,7 @@ __global__ void __launch_bounds__(IT_THREADS) interact_tile_kernel(IArgs A)
         if (tid < hgt) s_delta[tid] = 0;                              // local index == global index
         __syncthreads();
         GlobalView v{A.lon, A.lat, A.id, A.sp};
-        tile_phases<GlobalView, DO_RPS>(A, sh, v, s_cs, s_delta, w, hgt);
+        tile_phases<GlobalView, DO_RPS>(A, sh, v, G, total);
     }
     __syncthreads();
     flush_pairs(A, sh, true);
@@ -526,7 +645,9 @@ __global__ void __launch_bounds__(IT_THREADS) interact_cross_kernel(IArgs A, lon
             const int b0 = __ldg(A.cell_start + cb), b1 = __ldg(A.cell_start + cb + 1);
             u = make_uint4((unsigned int)a0, (unsigned int)b0, (unsigned int)(a1 - a0), (unsigned int)(b1 - b0));
         }
-        push_unit(sh, have, false, u);
+        have = have && unit_has_pairs(false, u.z, u.w);
+        const bool light = have && unit_is_light(false, u.z, u.w);
+        push_unit(sh, light, have && !light, u);
     }
     GlobalView v{A.lon, A.lat, A.id, A.sp};
     run_units<GlobalView, DO_RPS>(A, sh, v, false);
@@ -550,10 +671,10 @@ cudaError_t launch_interact(lm_handle_s *h, const float *lon, const float *lat, 
     A.r2 = h->norm == LM_NORM_2 ? r * r : r;           // SciPy: tub = r*r for p=2, pow(r, 1) for p=1, r for p=inf
     A.r2_lo = (float)(A.r2 * (1.0 - 4e-6));
     A.r2_hi = (float)(A.r2 * (1.0 + 4e-6));
-    A.seed_lo = A.seed_hi = A.step_lo = A.step_hi = 0;
+    A.pair_key = 0;
     A.thr[0] = A.thr[1] = A.thr[2] = 0;
     if (rps) {
-        A.seed_lo = rps->seed_lo; A.seed_hi = rps->seed_hi; A.step_lo = rps->step_lo; A.step_hi = rps->step_hi;
+        A.pair_key = rps->pair_key;
         const double p[3] = {rps->pRS, rps->pPR, rps->pSP};
         for (int k = 0; k < 3; ++k) {
             // u = m * 2^-53 with integer m < 2^53:  u < p  <=>  m < ceil(p * 2^53)   (the scaling is exact)
@@ -565,14 +686,17 @@ cudaError_t launch_interact(lm_handle_s *h, const float *lon, const float *lat, 
     A.pairs = (pairs_out && cap > 0) ? pairs_out : nullptr;
     A.cap_pairs = A.pairs ? (unsigned long long)cap : 0ull;
     A.ctr = h->ctr;
-    A.draw_batch = h->draw_batch > 0 ? h->draw_batch : 20;
+    A.draw_batch = h->draw_batch > 0 ? h->draw_batch : 8;
+    A.force_walk = h->tile_path == 1 ? 1 : 0;
     A.phase = 0;
-    // shared memory per tile: 1.5 x the mean occupancy of a tile, at least 1,024 microbes, at most 6,144 (80 KB: two CTAs per SM)
+    // shared memory per tile: room for 1.5 x the mean occupancy of a tile (at least 1,024 microbes, at most 6,144) and for
+    // two records per staged microbe and direction (the mean is below one); fuller tiles / directions take the lane walk
     const long long tiles = (long long)A.tiles_x * A.tiles_y;
     long long want = h->tile_cap > 0 ? h->tile_cap : std::max<long long>(1024, 3 * ((long long)n / std::max<long long>(1, tiles)) / 2 + 256);
-    want = std::min<long long>(want, 6144);
+    want = std::min<long long>(want, IT_MAX_TILE_CAP);
     A.tile_cap = (int)((want + 255) / 256 * 256);
-    const size_t dyn = (size_t)A.tile_cap * 13;
+    A.rec_cap = h->tile_rec_cap > 0 ? h->tile_rec_cap : std::min(2 * A.tile_cap, 16384);
+    const size_t dyn = (size_t)A.tile_cap * 18 + (size_t)A.rec_cap * 4;
     cudaError_t e = cudaSuccess;
     if (first <= 8) {
         auto k = rps ? interact_tile_kernel<true> : interact_tile_kernel<false>;

@@ -43,6 +43,7 @@ constexpr int GHOST_HDR = 4;
 struct RpsDev {
     double pRS, pPR, pSP;
     uint32_t seed_lo, seed_hi, step_lo, step_hi;
+    uint32_t pair_key;     // philox.cuh::pair_stream_key(seed, step): key of this step's per-pair Philox2x32 stream
 };
 
 }  // namespace lm
@@ -98,6 +99,8 @@ struct lm_handle_s {
                            //                       0 round-1 pipeline: pair search -> hand-off -> nine phase launches (csrc/pairs.cu)
     int draw_batch;        // LM_OPT_DRAW_BATCH: parked lanes that trigger a warp's Philox rounds (0 = default, 20)
     int tile_cap;          // LM_OPT_TILE_CAP: microbes a tile stages in shared memory (0 = from the mean occupancy)
+    int tile_rec_cap;      // LM_OPT_TILE_REC_CAP: records (hits of one direction) a tile holds in shared memory (0 = 2 x tile_cap)
+    int tile_path;         // LM_OPT_TILE_PATH: 0 records in shared memory where they fit (default) | 1 lane walk everywhere (tests)
     // arguments of the interaction in flight (fused tile kernel: the boundary phases 12-14 run in lm_step_interact_end)
     const float *ia_lon, *ia_lat;
     const int32_t *ia_id;

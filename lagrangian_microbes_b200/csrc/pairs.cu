@@ -72,7 +72,7 @@ struct FindArgs {
     int force_two_pass;                  // LM_OPT_FIND_PATH = 1 (tests)
     float r2_lo, r2_hi;                  // float32 pre-filter window around the threshold (r*r for p=2, r for p=1 and p=inf)
     double r2;                           // the exact threshold
-    uint32_t seed_lo, seed_hi, step_lo, step_hi;
+    uint32_t pair_key;                   // key of this step's per-pair Philox2x32 stream (philox.cuh)
     unsigned long long thr[3];           // ceil(p * 2^53) for pRS, pPR, pSP
     uint32_t *__restrict__ hits;
     uint2 *__restrict__ rec;             // [5][rec_stride]
@@ -114,9 +114,7 @@ __device__ __forceinline__ bool within(const FindArgs &A, float xa, float ya, in
 // three decision bits of the pair's draw: bit k set <=> u < p_k  (k = 0: pRS, 1: pPR, 2: pSP)
 __device__ __forceinline__ uint32_t decision_bits(const FindArgs &A, int i, int j)
 {
-    uint32_t x[4];
-    philox4x32_10((uint32_t)i, (uint32_t)j, A.step_lo, A.step_hi, A.seed_lo, A.seed_hi, x);
-    const unsigned long long m = ((unsigned long long)(x[0] >> 5) << 26) | (unsigned long long)(x[1] >> 6);
+    const unsigned long long m = pair_draw_m((uint32_t)i, (uint32_t)j, A.pair_key);
     return (m < A.thr[0] ? 1u : 0u) | (m < A.thr[1] ? 2u : 0u) | (m < A.thr[2] ? 4u : 0u);
 }
 
@@ -833,10 +831,10 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
     F.r2 = h->norm == LM_NORM_2 ? r * r : r;           // SciPy: tub = r*r for p=2, pow(r, 1) for p=1, r for p=inf
     F.r2_lo = (float)(F.r2 * (1.0 - 4e-6));
     F.r2_hi = (float)(F.r2 * (1.0 + 4e-6));
-    F.seed_lo = F.seed_hi = F.step_lo = F.step_hi = 0;
+    F.pair_key = 0;
     F.thr[0] = F.thr[1] = F.thr[2] = 0;
     if (rps) {
-        F.seed_lo = rps->seed_lo; F.seed_hi = rps->seed_hi; F.step_lo = rps->step_lo; F.step_hi = rps->step_hi;
+        F.pair_key = rps->pair_key;
         const double p[3] = {rps->pRS, rps->pPR, rps->pSP};
         for (int k = 0; k < 3; ++k) {
             // u = m * 2^-53 with integer m < 2^53:  u < p  <=>  m < ceil(p * 2^53)   (the scaling is exact)

@@ -22,14 +22,13 @@ namespace lm {
 constexpr unsigned long long ROUND_MAX = (1ull << 23) - 1;
 
 __global__ void __launch_bounds__(256) pair_uniforms_kernel(const int2 *__restrict__ pairs, long long np,
-                                                            uint32_t seed_lo, uint32_t seed_hi, uint32_t step_lo,
-                                                            uint32_t step_hi, double *__restrict__ u)
+                                                            uint32_t key, double *__restrict__ u)
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= np) return;
     const int2 p = pairs[k];
     const uint32_t i = (uint32_t)min(p.x, p.y), j = (uint32_t)max(p.x, p.y);
-    u[k] = pair_uniform(i, j, step_lo, step_hi, seed_lo, seed_hi);
+    u[k] = pair_uniform(i, j, key);
 }
 
 cudaError_t launch_pair_uniforms(const int2 *pairs, int64_t np, uint64_t seed, uint64_t step, double *u, cudaStream_t s)
@@ -37,7 +36,7 @@ cudaError_t launch_pair_uniforms(const int2 *pairs, int64_t np, uint64_t seed, u
     if (np <= 0) return cudaSuccess;
     const int block = 256;
     pair_uniforms_kernel<<<(unsigned)((np + block - 1) / block), block, 0, s>>>(
-        pairs, np, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)step, (uint32_t)(step >> 32), u);
+        pairs, np, pair_stream_key(seed, step), u);
     return cudaGetLastError();
 }
 

@@ -256,10 +256,11 @@ class StripSet:
         self.grid = make_grid(x0, x1, y0, y1, self.radius, self.n_total, cells_budget, margin=grid_margin,
                               cells_per_particle=cells_per_particle)
         g = self.grid
-        if g.ncy < 2 * G:
-            raise ValueError("the cell grid has %d rows: too few for %d strips" % (g.ncy, G))
+        if G > 1 and g.ncy < ROW_ALIGN * (G - 1) + 2:
+            raise ValueError("the cell grid has %d rows: too few for %d strips (boundaries sit on multiples of %d rows)"
+                             % (g.ncy, G, ROW_ALIGN))
         # rows a strip may own: room for the balanced share with the same slack as the particles
-        self.max_rows = min(g.ncy, max(4, int(slack * math.ceil(g.ncy / float(G))) + 2))
+        self.max_rows = min(g.ncy, max(2 * ROW_ALIGN, int(slack * math.ceil(g.ncy / float(G))) + ROW_ALIGN))
         self.max_cells = int(cells_headroom * (self.max_rows + 1) * g.ncx)      # room for re-fitted grids
         self._bbox = (x0, x1, y0, y1)
         row_density = self.n_total / float(g.ncy)

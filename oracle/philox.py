@@ -1,4 +1,4 @@
-"""Philox4x32-10 counter-based RNG, NumPy restatement (TEST INFRASTRUCTURE ONLY).
+"""Philox counter-based RNGs (4x32-10 and 2x32-10), NumPy restatement (TEST INFRASTRUCTURE ONLY).
 
 The reference draws its per-pair random number from NumPy's global MT19937
 stream (``np.random.rand()``, /root/reference/interactions.py:20), one draw per
@@ -8,13 +8,15 @@ reproduced in parallel, so parity is defined with an injected *per-pair* stream
 same function on the device (csrc/philox.cuh); tests compare them bit for bit.
 
 Algorithm: Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11),
-Philox-4x32 with 10 rounds; known-answer vectors from Random123's kat_vectors
-are checked in tests/test_philox.py.
+Philox-4x32 and Philox-2x32 with 10 rounds; known-answer vectors from Random123's
+kat_vectors are checked in tests/test_philox.py.
 
-Counter / key layout (shared with the device code):
-    counter = (i, j, step & 0xffffffff, step >> 32)   with i < j the pair's particle ids
-    key     = (seed & 0xffffffff, seed >> 32)
-    u       = ((x0 >> 5) * 2**26 + (x1 >> 6)) / 2**53          (53-bit, in [0, 1))
+Per-pair stream (shared with the device code, csrc/philox.cuh):
+    key(seed, step) = word 0 of Philox4x32-10(counter = (step & 0xffffffff, step >> 32, 'RPS1', 0),
+                                              key = (seed & 0xffffffff, seed >> 32))
+    (x0, x1)        = Philox2x32-10(counter = (i, j), key = key(seed, step))     i < j the pair's particle ids
+    u               = ((x0 >> 5) * 2**26 + (x1 >> 6)) / 2**53                    (53-bit, in [0, 1))
+Philox2x32 yields exactly the 64 bits one draw needs at half the multiplications of Philox4x32.
 """
 import numpy as np
 
@@ -56,14 +58,39 @@ def u53(x0, x1):
     return (a * 67108864.0 + b) / 9007199254740992.0
 
 
+_M2 = np.uint64(0xD256D193)
+
+
+def philox2x32_10(c0, c1, k):
+    """Vectorised Philox2x32-10.  c0, c1 broadcastable uint32-valued arrays, k a 32-bit key.  Returns (x0, x1)."""
+    c0 = np.asarray(c0, dtype=np.uint64) & _MASK
+    c1 = np.asarray(c1, dtype=np.uint64) & _MASK
+    c0, c1 = np.broadcast_arrays(c0, c1)
+    k = int(k) & 0xFFFFFFFF
+    for _ in range(10):
+        p = _M2 * c0
+        hi, lo = p >> _S32, p & _MASK
+        c0, c1 = hi ^ np.uint64(k) ^ c1, lo
+        k = (k + _W0) & 0xFFFFFFFF
+    return c0.astype(np.uint32), c1.astype(np.uint32)
+
+
+PAIR_STREAM_TAG = 0x52505331          # 'RPS1'
+
+
+def pair_stream_key(step, seed):
+    """The 32-bit Philox2x32 key of one step's per-pair stream."""
+    step, seed = int(step), int(seed)
+    x0, _, _, _ = philox4x32_10(step & 0xFFFFFFFF, (step >> 32) & 0xFFFFFFFF, PAIR_STREAM_TAG, 0,
+                                seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    return int(x0)
+
+
 def pair_uniforms(i, j, step, seed):
     """Per-pair uniform u(i, j, step, seed) in [0,1), float64.  Requires i < j elementwise."""
     i = np.asarray(i, dtype=np.uint64)
     j = np.asarray(j, dtype=np.uint64)
-    step = int(step)
-    seed = int(seed)
-    x0, x1, _, _ = philox4x32_10(i, j, step & 0xFFFFFFFF, (step >> 32) & 0xFFFFFFFF,
-                                 seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    x0, x1 = philox2x32_10(i, j, pair_stream_key(step, seed))
     return u53(x0, x1)
 
 

@@ -174,22 +174,30 @@ def cell_ranks(lon32, lat32, grid):
     return cx, cy, rank, occ.astype(np.int64)
 
 
+def unit_is_light(same, ma, mb):
+    """csrc/interact.cu::unit_is_light -- part of the definition of the order: a unit of two cells is LIGHT when
+    m_a * m_b <= 256 and m_b <= 64, a unit of one cell when m <= 23; otherwise it is HEAVY."""
+    return np.where(same, ma <= 23, (ma * mb <= 256) & (mb <= 64))
+
+
 def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
     """Return ``pairs`` (rows i<j, original ids) re-ordered into the canonical order of the fused tile kernel.
 
     Cells are grouped into tiles of ``tile`` = (32, 16) cells, origin at cell (0, 0) of the grid.  A *unit* is one
     cell (the pairs inside it) or two adjacent cells (half stencil: E, NW, N, NE of the anchor cell).  Order key
-    (phase, unit, round, slot):
+    (phase, unit, then inside the unit):
 
-      phase  0..8   units inside one tile, as in ``cell_phase_order``:
-                    0 same cell | 1 + (cx & 1) east | 3 (cy & 1) + 3, + 4, + 5  north-west, north, north-east
+      phase  0..8   units inside one tile: 0 same cell | 1 + (cx & 1) east | 3 + (cy & 1) north-west |
+                    5 + (cy & 1) north | 7 + (cy & 1) north-east
              9..14  units across a tile boundary: 9 east | 10, 11 north-west, north-east across a vertical
                     boundary only | 12, 13, 14 north-west, north, north-east across a horizontal boundary
       unit   anchor cell (the western / southern one)
-      round, slot   the pairs of a unit are taken in ROUNDS OF MATCHINGS -- inside a round no microbe occurs
-                    twice, so a round is order-free and the device resolves it in parallel:
-             two cells, m_a and m_b microbes ranked by id, M = max(m_a, m_b): round k in [0, M) pairs rank i of
-                    the anchor cell with rank (i + k) mod M of the other cell; slot = i
+      inside a LIGHT unit (``unit_is_light``): (rank in the anchor cell, rank in the other cell) lexicographic, ranks by
+             particle id (one cell: smaller rank, larger rank)
+      inside a HEAVY unit: ROUNDS OF MATCHINGS -- inside a round no microbe occurs twice, so a round is order-free
+             and the device resolves it in parallel:
+             two cells, m_a and m_b microbes, M = max(m_a, m_b): round k in [0, M) pairs rank i of the anchor cell
+                    with rank (i + k) mod M of the other cell; slot = i
              one cell, m microbes, M = m rounded up to even (rank M - 1 is a phantom when m is odd): the circle
                     method of round-robin tournaments -- round k in [0, M - 1) pairs rank M - 1 with rank k
                     (slot 0) and rank (k + j) mod (M - 1) with rank (k - j) mod (M - 1) for j in [1, M / 2) (slot j)
@@ -208,14 +216,15 @@ def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
     b = np.where(j_anchor, i, j)
     cxa, cya, cxb, cyb = cx[a], cy[a], cx[b], cy[b]
     d = cxb - cxa
-    inner = np.where(same, 0, np.where(cya == cyb, 1 + (cxa & 1), 3 * (cya & 1) + 4 + d))
+    inner = np.where(same, 0, np.where(cya == cyb, 1 + (cxa & 1), 5 + 2 * d + (cya & 1)))
     cross_v = (cxa // tw) != (cxb // tw)
     cross_h = (cya // th) != (cyb // th)
     outer = np.where(cya == cyb, 9, np.where(cross_h, 13 + d, np.where(d < 0, 10, 11)))
     phase = np.where(cross_v | cross_h, outer, inner)
     unit = cya * np.int64(grid["ncx"]) + cxa
-    # rounds and slots
     ra, rb, ma, mb = rank[a], rank[b], occ[a], occ[b]
+    light = unit_is_light(same, ma, mb)
+    # heavy units: rounds and slots
     big = np.maximum(ma, mb)
     rnd_x = np.mod(rb - ra, big)
     slot_x = ra
@@ -227,9 +236,9 @@ def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
     jp = np.mod(p - rnd_s, n1)
     jq = np.mod(q - rnd_s, n1)
     slot_s = np.where(fixed, 0, np.where((jp >= 1) & (jp < m_even // 2), jp, jq))
-    rnd = np.where(same, rnd_s, rnd_x)
-    slot = np.where(same, slot_s, slot_x)
-    order = np.lexsort((slot, rnd, unit, phase))
+    k1 = np.where(light, np.where(same, p, ra), np.where(same, rnd_s, rnd_x))
+    k2 = np.where(light, np.where(same, q, rb), np.where(same, slot_s, slot_x))
+    order = np.lexsort((k2, k1, unit, phase))
     return pairs[order], phase[order]
 
 

@@ -141,6 +141,7 @@ static inline int atomicMax(int *p, int v)
 static inline int __popc(unsigned int x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned int)x) : 32; }
 static inline unsigned int __umulhi(unsigned int a, unsigned int b) { return (unsigned int)(((unsigned long long)a * b) >> 32); }
 static inline unsigned int __byte_perm(unsigned int a, unsigned int b, unsigned int sel)

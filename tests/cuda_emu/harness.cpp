@@ -5,6 +5,7 @@
 #include <cstdio>
 
 #include "lm_internal.cuh"
+#include "philox.cuh"
 
 using namespace lm;
 
@@ -53,6 +54,7 @@ long long emu_interact(const float *lon, const float *lat, const int32_t *id, co
     rd.pRS = pRS; rd.pPR = pPR; rd.pSP = pSP;
     rd.seed_lo = (uint32_t)seed; rd.seed_hi = (uint32_t)(seed >> 32);
     rd.step_lo = (uint32_t)step; rd.step_hi = (uint32_t)(step >> 32);
+    rd.pair_key = pair_stream_key(seed, step);
     cudaError_t e = launch_find(h, lon, lat, id, n_owned, r, &rd, reinterpret_cast<int2 *>(pairs_out), pairs_out ? cap : 0, nullptr);
     if (e == cudaSuccess && n_owned > 0) e = launch_resolve_phases(h, species, first, last, nullptr);
     const long long found = (long long)h->ctr->n_pairs;
@@ -70,7 +72,7 @@ long long emu_interact(const float *lon, const float *lat, const int32_t *id, co
 long long emu_interact_tile(const float *lon, const float *lat, const int32_t *id, const int32_t *cell_start, int8_t *species,
                             int n_owned, int ncx, int ncy, int row0, int rows_owned, int rows_local, double r, int norm,
                             double pRS, double pPR, double pSP, unsigned long long seed, unsigned long long step, int first,
-                            int last, int tile_cap, int draw_batch, int32_t *pairs_out, long long cap)
+                            int last, int tile_cap, int draw_batch, int tile_rec_cap, int tile_path, int32_t *pairs_out, long long cap)
 {
     lm_handle_s *h = zalloc<lm_handle_s>(1);
     h->grid.ncx = ncx; h->grid.ncy = ncy;
@@ -80,11 +82,12 @@ long long emu_interact_tile(const float *lon, const float *lat, const int32_t *i
     h->norm = norm;
     h->cell_start = const_cast<int32_t *>(cell_start);
     h->ctr = zalloc<Counters>(1);
-    h->tile_cap = tile_cap; h->draw_batch = draw_batch;
+    h->tile_cap = tile_cap; h->draw_batch = draw_batch; h->tile_rec_cap = tile_rec_cap; h->tile_path = tile_path;
     RpsDev rd;
     rd.pRS = pRS; rd.pPR = pPR; rd.pSP = pSP;
     rd.seed_lo = (uint32_t)seed; rd.seed_hi = (uint32_t)(seed >> 32);
     rd.step_lo = (uint32_t)step; rd.step_hi = (uint32_t)(step >> 32);
+    rd.pair_key = pair_stream_key(seed, step);
     cudaError_t e = launch_interact(h, lon, lat, id, species, n_owned, r, species ? &rd : nullptr,
                                     reinterpret_cast<int2 *>(pairs_out), pairs_out ? cap : 0, first, last, nullptr);
     const long long found = (long long)h->ctr->n_pairs, launches = h->launches;

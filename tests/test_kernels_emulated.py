@@ -618,6 +618,7 @@ def test_tiled_resolver_other_tile_shapes(abi, shape):
         assert L.lm_create(ctypes.byref(h), 0, n, 1 << 16, 40 * n) == 0
         try:
             assert L.lm_set_grid(h, ctypes.byref(grid)) == 0
+            assert L.lm_set_option(h, _lib.LM_OPT_INTERACT_MODE, 0) == 0        # the round-1 pipeline
             assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_MODE, 1) == 0
             assert L.lm_set_option(h, _lib.LM_OPT_RESOLVE_TILE_SHAPE, shape) == 0
             species = sp0.copy()
@@ -639,7 +640,7 @@ def emu_tile():
     vp, i32, i64, u64, dbl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_ulonglong, ctypes.c_double
     L.emu_interact_tile.restype = i64
     L.emu_interact_tile.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, dbl, i32, dbl, dbl, dbl, u64, u64, i32, i32,
-                                    i32, i32, vp, i64]
+                                    i32, i32, i32, i32, vp, i64]
     return L
 
 
@@ -649,7 +650,7 @@ class TileCloud(Cloud):
         self.order, self.phase = orps.tile_round_order(self.pairs, self.lon, self.lat, self.grid)
         self.u = philox.pair_uniforms(self.order[:, 0], self.order[:, 1], 17, 5)
 
-    def run_tile(self, L, sp, first=0, last=14, tile_cap=0, draw_batch=0, rps=True):
+    def run_tile(self, L, sp, first=0, last=14, tile_cap=0, draw_batch=0, rps=True, rec_cap=0, path=0):
         g = self.grid
         lon_s, lat_s = np.ascontiguousarray(self.lon[self.ids]), np.ascontiguousarray(self.lat[self.ids])
         sp_s = np.ascontiguousarray(sp[self.ids])
@@ -657,7 +658,7 @@ class TileCloud(Cloud):
         pairs_out = np.full((cap, 2), -1, dtype=np.int32)
         ret = L.emu_interact_tile(_ptr(lon_s), _ptr(lat_s), _ptr(self.ids), _ptr(self.cell_start), _ptr(sp_s) if rps else None,
                                   self.n, g["ncx"], g["ncy"], 0, g["ncy"], g["ncy"], R, 2, *P, 5, 17, first, last, tile_cap,
-                                  draw_batch, _ptr(pairs_out), cap)
+                                  draw_batch, rec_cap, path, _ptr(pairs_out), cap)
         assert ret >= 0
         found, launches = ret & ((1 << 48) - 1), ret >> 48
         out = np.empty_like(sp)
@@ -665,16 +666,19 @@ class TileCloud(Cloud):
         return out, launches, opairs.sort_pairs(pairs_out[:found])
 
 
-@pytest.mark.parametrize("seed,ncx,ncy,n,knots,knot_size,tile_cap,draw_batch", [
-    (1, 74, 19, 1800, 10, (10, 31), 0, 0),        # three tiles across, two up, ragged; knots on the whole-warp path
-    (2, 74, 37, 3000, 6, (40, 60), 0, 1),         # ... draws taken one lane at a time
-    (3, 40, 20, 1500, 2, (150, 200), 256, 32),    # 18,000-slot cells on the whole-CTA path; tiles too full for shared memory
+@pytest.mark.parametrize("seed,ncx,ncy,n,knots,knot_size,tile_cap,draw_batch,rec_cap,path", [
+    (1, 74, 19, 1800, 10, (10, 31), 0, 0, 0, 0),      # three tiles across, two up, ragged; records in shared memory; knots on the whole-warp path
+    (1, 74, 19, 1800, 10, (10, 31), 0, 0, 0, 1),      # ... the lane walk on the same tiles
+    (1, 74, 19, 1800, 10, (10, 31), 0, 0, 512, 0),    # ... record buffer too small in some directions of some tiles: both paths side by side
+    (2, 74, 37, 3000, 6, (40, 60), 0, 1, 0, 1),       # lane walk, draws taken one lane at a time
+    (2, 74, 37, 3000, 6, (40, 60), 0, 1, 0, 0),
+    (3, 40, 20, 1500, 2, (150, 200), 256, 32, 0, 0),  # 18,000-slot cells on the whole-CTA path; tiles too full for shared memory
 ])
-def test_fused_tile_kernel_executed(emu_tile, seed, ncx, ncy, n, knots, knot_size, tile_cap, draw_batch):
+def test_fused_tile_kernel_executed(emu_tile, seed, ncx, ncy, n, knots, knot_size, tile_cap, draw_batch, rec_cap, path):
     c = TileCloud(seed, ncx, ncy, n, knots=knots, knot_size=knot_size)
     want = c.oracle(c.sp0, 0, 14)
     assert int((want != c.sp0).sum()) > 100 and set(np.unique(c.phase)) >= set(range(15))
-    got, launches, pairs = c.run_tile(emu_tile, c.sp0, tile_cap=tile_cap, draw_batch=draw_batch)
+    got, launches, pairs = c.run_tile(emu_tile, c.sp0, tile_cap=tile_cap, draw_batch=draw_batch, rec_cap=rec_cap, path=path)
     assert np.array_equal(pairs, c.pairs), "pair set differs from cKDTree.query_pairs"
     assert np.array_equal(got, want), "%d species differ" % int((got != want).sum())
     assert launches == 7                                       # one tile launch + six boundary phases

@@ -26,3 +26,21 @@ def test_uniform_range_and_determinism():
     # 64-bit step / seed use both key / counter words
     assert not np.array_equal(philox.pair_uniforms(i, i + 1, 1, 1), philox.pair_uniforms(i, i + 1, 1 + 2**32, 1))
     assert not np.array_equal(philox.pair_uniforms(i, i + 1, 1, 1), philox.pair_uniforms(i, i + 1, 1, 1 + 2**32))
+
+
+def test_philox2x32_kat_vectors():
+    """Random123 kat_vectors, philox2x32 with 10 rounds."""
+    kat = [((0, 0), 0, (0xff1dae59, 0x6cd10df2)),
+           ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+           ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12))]
+    for c, k, want in kat:
+        got = philox.philox2x32_10(np.array([c[0]]), np.array([c[1]]), k)
+        assert tuple(int(x[0]) for x in got) == want
+
+
+def test_pair_stream_is_philox2x32_keyed_per_step():
+    i, j = np.array([5, 7, 2**31 + 3]), np.array([9, 8, 2**32 - 1])
+    key = philox.pair_stream_key(12, 2**40 + 5)
+    assert 0 <= key < 2**32 and key != philox.pair_stream_key(13, 2**40 + 5) != philox.pair_stream_key(12, 2**40 + 6)
+    x0, x1 = philox.philox2x32_10(i, j, key)
+    assert np.array_equal(philox.pair_uniforms(i, j, 12, 2**40 + 5), philox.u53(x0, x1))
