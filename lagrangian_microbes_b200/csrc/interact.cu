@@ -426,10 +426,24 @@ __device__ bool find_direction(const IArgs &A, Shared &sh, const SmemView &v, co
                 pa = v.pos[p];
             }
         }
-        unsigned long long mask = 0;
-        for (int i = 0; i < nc; ++i)
-            if (within(A, pa, v.pos[beg + i])) mask |= 1ull << i;
-        const unsigned int cnt = (unsigned int)__popcll(mask);
+        // hit bits of candidates 0..31 | 32..63 (two 32-bit words: cheaper to build and to walk than one 64-bit mask)
+        unsigned int m_lo = 0, m_hi = 0;
+        {
+            const int n_lo = min(nc, 32);
+            if (A.norm == LM_NORM_2) {                                // the reference's norm: no selects in the loop
+                for (int i = 0; i < n_lo; ++i) {
+                    const float2 pb = v.pos[beg + i];
+                    const float dx = pa.x - pb.x, dy = pa.y - pb.y, d2 = fmaf(dx, dx, dy * dy);
+                    if (d2 <= A.r2_hi && (d2 < A.r2_lo || within_exact(LM_NORM_2, pa, pb, A.r2))) m_lo |= 1u << i;
+                }
+            } else {
+                for (int i = 0; i < n_lo; ++i)
+                    if (within(A, pa, v.pos[beg + i])) m_lo |= 1u << i;
+            }
+            for (int i = 32; i < nc; ++i)
+                if (within(A, pa, v.pos[beg + i])) m_hi |= 1u << (i - 32);
+        }
+        const unsigned int cnt = (unsigned int)(__popc(m_lo) + __popc(m_hi));
         unsigned int incl = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -442,9 +456,11 @@ __device__ bool find_direction(const IArgs &A, Shared &sh, const SmemView &v, co
         wbase = __shfl_sync(FULL, wbase, 0);
         unsigned int pos = wbase + incl - cnt;
         if (p < total) { v.hstart[p] = (uint16_t)min(pos, 0xffffu); v.hcnt[p] = (uint8_t)cnt; }
-        if (wbase + wtotal <= (unsigned int)A.rec_cap)
-            for (; mask; mask &= mask - 1)
-                v.rec[pos++] = (unsigned int)p | ((unsigned int)(beg + __ffsll((long long)mask) - 1) << 13);
+        if (wbase + wtotal <= (unsigned int)A.rec_cap) {
+            const unsigned int lo_part = (unsigned int)p | ((unsigned int)beg << 13);
+            for (; m_lo; m_lo &= m_lo - 1) v.rec[pos++] = lo_part + ((unsigned int)(__ffs((int)m_lo) - 1) << 13);
+            for (; m_hi; m_hi &= m_hi - 1) v.rec[pos++] = lo_part + ((unsigned int)(__ffs((int)m_hi) + 31) << 13);
+        }
     }
     __syncthreads();
     const unsigned int n_rec = sh.rec_used;                           // CTA-uniform
@@ -470,29 +486,61 @@ __device__ bool find_direction(const IArgs &A, Shared &sh, const SmemView &v, co
     return true;
 }
 
-// R: one lane resolves one light unit from its records, in canonical order (anchor rank, partner rank)
+// R: one lane resolves one light unit from its records, in canonical order (anchor rank, partner rank).  The records
+// of one anchor are contiguous; those of a cell's anchors are contiguous too when the anchors sat in one warp of F
+// (same 32-aligned block of local indices: 9 in 10 cells) -- then the lane walks ONE run of records and never looks at
+// an anchor without records.
+__device__ __forceinline__ void resolve_one(const IArgs &A, const SmemView &v, uint32_t e, int a, int &sa)
+{
+    const int b = (int)((e >> 13) & REC_IDX);
+    const int sb = v.sp[b];
+    if (sa != sb && is_rps(sa) && is_rps(sb)) {
+        uint32_t dec;
+        if (e & REC_HAS_DRAW) dec = (e >> 26) & 7u;
+        else { const int x = v.id[a], y = v.id[b]; dec = decision_bits(A, min(x, y), max(x, y)); }   // came to differ since F
+        const int s = rps_apply(sa, sb, dec);
+        if (s != sa) sa = s; else v.sp[b] = (int8_t)s;
+    }
+}
+
+// u.x first record | u.y records (0xffffffff: the cell's anchors straddle two warps of F, walk anchor by anchor) | u.z first anchor | u.w anchors
 __device__ __forceinline__ void resolve_records(const IArgs &A, const SmemView &v, const uint4 &u)
 {
-    const int a_end = (int)(u.x + u.z);
-    for (int a = (int)u.x; a < a_end; ++a) {
+    if (u.y != 0xffffffffu) {
+        int cur = -1, sa = 0, sa0 = 0;
+        const uint32_t *r = v.rec + u.x;
+        for (unsigned int h = 0; h < u.y; ++h) {
+            const uint32_t e = r[h];
+            const int a = (int)(e & REC_IDX);
+            if (a != cur) {
+                if (cur >= 0 && sa != sa0) v.sp[cur] = (int8_t)sa;   // a same-cell partner may be this very microbe later: write first
+                cur = a; sa = sa0 = v.sp[a];
+            }
+            resolve_one(A, v, e, a, sa);
+        }
+        if (cur >= 0 && sa != sa0) v.sp[cur] = (int8_t)sa;
+        return;
+    }
+    const int a_end = (int)(u.z + u.w);
+    for (int a = (int)u.z; a < a_end; ++a) {
         const int hc = v.hcnt[a];
         if (!hc) continue;
         const uint32_t *r = v.rec + v.hstart[a];
         const int sa0 = v.sp[a];
         int sa = sa0;
-        for (int h = 0; h < hc; ++h) {
-            const uint32_t e = r[h];
-            const int b = (int)((e >> 13) & REC_IDX);
-            const int sb = v.sp[b];
-            if (sa != sb && is_rps(sa) && is_rps(sb)) {
-                uint32_t dec;
-                if (e & REC_HAS_DRAW) dec = (e >> 26) & 7u;
-                else { const int x = v.id[a], y = v.id[b]; dec = decision_bits(A, min(x, y), max(x, y)); }   // came to differ since F
-                const int s = rps_apply(sa, sb, dec);
-                if (s != sa) sa = s; else v.sp[b] = (int8_t)s;
-            }
-        }
+        for (int h = 0; h < hc; ++h) resolve_one(A, v, r[h], a, sa);
         if (sa != sa0) v.sp[a] = (int8_t)sa;
+    }
+}
+
+// every lane takes units with records from the list (dynamic ticket) until it is empty
+__device__ void walk_records(const IArgs &A, Shared &sh, const SmemView &v)
+{
+    const unsigned int n_units = sh.n_light;
+    unsigned int t = threadIdx.x;
+    while (t < n_units) {
+        resolve_records(A, v, sh.unit[t]);
+        t = atomicAdd(&sh.ticket, 1u);
     }
 }
 
@@ -517,13 +565,33 @@ __device__ void tile_phases(const IArgs &A, Shared &sh, const V &v, const TileGe
                 have = have && unit_has_pairs(g == 0, u.z, u.w);
                 const bool light = have && unit_is_light(g == 0, u.z, u.w);
                 bool listed = light;
+                uint4 w4 = u;
                 if constexpr (V::kStaged) {
                     if (records) {
                         listed = false;
-                        if (DO_RPS && light) resolve_records(A, v, u);
+                        if (DO_RPS && light) {
+                            // the unit's records: one run if its anchors sat in one warp of F, else anchor by anchor
+                            const int a0 = (int)u.x, al = (int)(u.x + u.z) - 1;
+                            if ((a0 >> 5) == (al >> 5)) {
+                                const unsigned int rs = v.hstart[a0], re = (unsigned int)v.hstart[al] + v.hcnt[al];
+                                w4 = make_uint4(rs, re - rs, u.x, u.z);
+                                listed = re > rs;
+                            } else {
+                                w4 = make_uint4(0u, 0xffffffffu, u.x, u.z);
+                                listed = true;
+                            }
+                        }
                     }
                 }
-                push_unit(sh, listed, have && !light, u);
+                push_unit(sh, listed, have && !light, listed ? w4 : u);
+            }
+            if constexpr (V::kStaged) {
+                if (records) {
+                    __syncthreads();                                   // the list is complete
+                    if (DO_RPS && sh.n_light) walk_records(A, sh, v);
+                    __syncthreads();
+                    if (tid == 0) sh.n_light = 0;                      // run_units: only the heavy units are left
+                }
             }
             run_units<V, DO_RPS>(A, sh, v, g == 0);
         }
@@ -689,10 +757,10 @@ cudaError_t launch_interact(lm_handle_s *h, const float *lon, const float *lat, 
     A.draw_batch = h->draw_batch > 0 ? h->draw_batch : 8;
     A.force_walk = h->tile_path == 1 ? 1 : 0;
     A.phase = 0;
-    // shared memory per tile: room for 1.5 x the mean occupancy of a tile (at least 1,024 microbes, at most 6,144) and for
+    // shared memory per tile: room for 1.5 x the mean occupancy of a tile (at least 2,048 microbes, at most 6,144) and for
     // two records per staged microbe and direction (the mean is below one); fuller tiles / directions take the lane walk
     const long long tiles = (long long)A.tiles_x * A.tiles_y;
-    long long want = h->tile_cap > 0 ? h->tile_cap : std::max<long long>(1024, 3 * ((long long)n / std::max<long long>(1, tiles)) / 2 + 256);
+    long long want = h->tile_cap > 0 ? h->tile_cap : std::max<long long>(2048, 3 * ((long long)n / std::max<long long>(1, tiles)) / 2 + 256);
     want = std::min<long long>(want, IT_MAX_TILE_CAP);
     A.tile_cap = (int)((want + 255) / 256 * 256);
     A.rec_cap = h->tile_rec_cap > 0 ? h->tile_rec_cap : std::min(2 * A.tile_cap, 16384);

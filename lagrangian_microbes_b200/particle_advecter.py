@@ -70,6 +70,7 @@ class HostFieldSet:
         nominal_depth = dataset["depth"].values[0]
         sub = dataset.sel(depth=nominal_depth)
         times = sub["time"].values
+        self.t0 = times[0]                       # calendar time of the first snapshot (numpy datetime64)
         self.time = np.array([(times[i] - times[0]) // np.timedelta64(1, "s") for i in range(times.size)],
                              dtype=np.float64)
         lon = np.asarray(sub["longitude"].values, dtype=np.float32)
@@ -86,6 +87,26 @@ class HostFieldSet:
     def to_device(self, device):
         import torch
         return tuple(torch.from_numpy(a).to(device) for a in (self.u, self.v, self.lon, self.lat))
+
+    @classmethod
+    def from_years(cls, years):
+        """The datasets of consecutive years as ONE field: snapshots concatenated along time, seconds counted from the
+        first snapshot of the first year.  (The reference opens one year per ``time_step`` call and restarts the particle
+        clock at that file's first snapshot -- quirk Q1; this is what ``calendar_time=True`` uses instead.)"""
+        parts = [cls(oscar_dataset(int(y))) for y in years]
+        out = parts[0]
+        for nxt in parts[1:]:
+            assert np.array_equal(nxt.lon, out.lon) and np.array_equal(nxt.lat, out.lat), "the years' grids differ"
+            shift = float((nxt.t0 - out.t0) // np.timedelta64(1, "s"))
+            assert shift > out.time[-1], "the years' time axes overlap"
+            out.time = np.concatenate((out.time, nxt.time + shift))
+            out.u = np.ascontiguousarray(np.concatenate((out.u, nxt.u), axis=0))
+            out.v = np.ascontiguousarray(np.concatenate((out.v, nxt.v), axis=0))
+        return out
+
+    def seconds_since_first_snapshot(self, when):
+        """Particle-clock value of the calendar time ``when`` (datetime)."""
+        return float((np.datetime64(when, "us") - self.t0.astype("datetime64[us]")) / np.timedelta64(1, "s"))
 
 
 class StageClock:
@@ -138,6 +159,7 @@ class ParticleAdvecter:
         output_chunk_iters=100,
         Kh=0,
         seed=0,
+        calendar_time=False,
     ):
         assert velocity_field == "OSCAR", "OSCAR is the only supported velocity field right now."
         assert 1 <= N_procs or N_procs == -1, "Number of processors N_procs must be a positive integer " \
@@ -168,6 +190,11 @@ class ParticleAdvecter:
         self.output_chunk_iters = output_chunk_iters
         self.Kh = Kh / 1e10  # [m^2/s] -> [deg^2/s] assuming 1 deg = 100 km (particle_advecter.py:121)
         self.seed = seed
+        # False (default): the reference's behaviour, quirk Q1 -- every time_step call samples the velocity of
+        # start_time.year's file from its FIRST snapshot on, whatever start_time is (particle_advecter.py:160,186-187).
+        # True: the particle clock is the calendar -- a call starts at start_time inside its year's file, and a call that
+        # runs past the end of a year continues in the next year's file ("year roll-over, fixing Q1").
+        self.calendar_time = bool(calendar_time)
         self._engine = None
         self._field_year = None
 
@@ -178,7 +205,7 @@ class ParticleAdvecter:
         if self._engine is None:
             self._engine = Engine(max_particles=self.N_particles, max_cells=1 << 16, max_pairs=0)
         if self._field_year != year:
-            fs = HostFieldSet(oscar_dataset(year))
+            fs = HostFieldSet.from_years(year) if isinstance(year, tuple) else HostFieldSet(oscar_dataset(year))
             self._fieldset = fs
             self._engine.set_field(*fs.to_device(self._engine.device))
             self._field_year = year
@@ -198,7 +225,16 @@ class ParticleAdvecter:
 
         logger.info("Starting time stepping: {:} -> {:} (dt={:}) on {:d} tile(s)."
                     .format(start_time, end_time, dt, self.N_procs))
-        eng = self._ensure_engine(start_time.year)
+        if self.calendar_time:
+            # the last sample of the last step is taken AT end_time: the next year's file is needed if that lies beyond
+            # this year's last snapshot (the files hold 72 five-day snapshots: the last ~10 days of a year have none)
+            years = list(range(start_time.year, end_time.year + 1))
+            last = HostFieldSet(oscar_dataset(years[-1]))
+            if last.seconds_since_first_snapshot(end_time) > last.time[-1]:
+                years.append(years[-1] + 1)
+            eng = self._ensure_engine(tuple(years))
+        else:
+            eng = self._ensure_engine(start_time.year)
         dev = eng.device
         N, per_tile = self.N_particles, self.particles_per_tile
         dt_s = dt.total_seconds()
@@ -206,7 +242,8 @@ class ParticleAdvecter:
         # Parcels casts particle lon/lat to float32 (JITParticle); one fresh particle set per call (Q1)
         lon = torch.from_numpy(np.concatenate(self.particle_lons).astype(np.float32)).to(dev)
         lat = torch.from_numpy(np.concatenate(self.particle_lats).astype(np.float32)).to(dev)
-        clock = StageClock(self._fieldset.time)
+        clock = StageClock(self._fieldset.time,
+                           t0=self._fieldset.seconds_since_first_snapshot(start_time) if self.calendar_time else None)
         amp = float(np.sqrt(6 * np.fabs(np.float32(dt_s)) * self.Kh))
 
         t = start_time

@@ -306,8 +306,12 @@ def oscar_dataset(year):
     if key not in _CACHE:
         lon, lat = oscar_grid()
         times_s = OSCAR_DT_SECONDS * np.arange(OSCAR_NT, dtype=np.int64)
-        u, v = synthetic_uv(lon, lat, times_s, **_CONFIG)
-        time = np.datetime64("%04d-01-01T00:00:00" % year, "s") + times_s.astype("timedelta64[s]")
+        first = np.datetime64("%04d-01-01T00:00:00" % year, "s")
+        # the synthetic flow is a function of ABSOLUTE time (seconds since 2017-01-01, so 2017 is what it always was): the
+        # files of consecutive years continue one flow, which is what a run across a year boundary needs
+        since_epoch = int((first - np.datetime64("2017-01-01T00:00:00", "s")) // np.timedelta64(1, "s"))
+        u, v = synthetic_uv(lon, lat, times_s + since_epoch, **_CONFIG)
+        time = first + times_s.astype("timedelta64[s]")
         _CACHE.clear()                                  # hold one year at a time (332 MB each)
         _CACHE[key] = SyntheticDataset({
             "time": time.astype("datetime64[ns]"),

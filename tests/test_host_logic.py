@@ -310,3 +310,39 @@ def test_record_assembler_keeps_every_stride_th_step_in_the_reference_layout(tmp
     short.put(0, *cols[0])
     with pytest.raises(AssertionError):
         short.write(str(tmp_path / "out2"))
+
+
+def test_years_concatenate_into_one_calendar_field_and_the_clock_starts_at_start_time():
+    """calendar_time=True (the fix of quirk Q1 behind an option; default = the reference's behaviour): consecutive years'
+    files become one field with a continuous time axis, the particle clock of a time_step call is the calendar time
+    inside it, and the stage decisions across the year boundary are the oracle's."""
+    from datetime import datetime
+    from lagrangian_microbes_b200 import velocity_fields
+    from lagrangian_microbes_b200.particle_advecter import HostFieldSet, StageClock
+    from oracle import rk4 as ork4
+    velocity_fields.configure_synthetic(kind="random_fourier", seed=3, n_modes=4, rms_speed=0.2)
+    try:
+        a = HostFieldSet(velocity_fields.oscar_dataset(2017))
+        t_last_2017 = a.time[-1]
+        fs = HostFieldSet.from_years((2017, 2018))
+        assert fs.u.shape[0] == 144 and fs.time.shape == (144,) and np.all(np.diff(fs.time) > 0)
+        assert fs.time[71] == t_last_2017 == 71 * 432000.0 and fs.time[72] == 365 * 86400.0        # 2018-01-01 since 2017-01-01
+        assert np.array_equal(fs.u[:72], a.u)
+        b = HostFieldSet(velocity_fields.oscar_dataset(2018))
+        assert np.array_equal(fs.u[72:], b.u) and not np.array_equal(a.u[:5], b.u[:5])           # one flow, continued: 2018 differs from 2017
+        start = datetime(2017, 12, 20, 6, 0, 0)
+        t0 = fs.seconds_since_first_snapshot(start)
+        assert t0 == (353 * 24 + 6) * 3600.0
+        clock = StageClock(fs.time, t0=t0)
+        ofs = ork4.FieldSet(fs.lon, fs.lat, fs.time, fs.u, fs.v)
+        t, ti = t0, 0
+        crossed = False
+        for _ in range(24 * 14):                                       # two weeks of hourly steps: over the gap between the years' files
+            st = clock.next_step(3600.0)
+            want, ti = ork4.stage_times(ofs, t, 3600.0, ti)
+            assert [(st.ti[k], st.interp[k], st.frac[k]) for k in range(4)] == [(w[0], int(w[1]), np.float32(w[2])) for w in want]
+            crossed = crossed or st.ti[0] == 71
+            t += 3600.0
+        assert crossed and clock.ti == 72
+    finally:
+        velocity_fields.configure_synthetic(kind="random_fourier", seed=0, n_modes=64, rms_speed=0.2)

@@ -107,9 +107,7 @@ def test_tile_round_order_is_reproducible_and_its_rounds_are_matchings(name):
     assert np.array_equal(order.astype(np.int32), g["pairs_tile_order"])
     assert np.array_equal(opairs.sort_pairs(order), pairs)                     # a permutation of the pair set
     assert np.all(np.diff(phase) >= 0) and phase.min() >= 0 and phase.max() <= 14
-    # inside one phase no microbe may occur in two units; inside one round of a unit no microbe may occur twice.
-    # Walk the order: a new (phase, unit) or a microbe seen in the current round starts a new round; the number of
-    # rounds a unit needs is then at most max(m_a, m_b) (two cells) or m - 1 + (m odd) (one cell): the matchings bound
+    # inside one phase no microbe may occur in two units
     cx, cy, rank, occ = orps.cell_ranks(lon, lat, grid)
     key = cy * grid["ncx"] + cx
     for ph in np.unique(phase):
@@ -120,21 +118,40 @@ def test_tile_round_order_is_reproducible_and_its_rounds_are_matchings(name):
             u = (min(a, b), max(a, b))
             for c in u:
                 assert unit_of_cell.setdefault(c, u) == u, "phase %d: cell %d in two units" % (ph, c)
-    rounds, cur_unit, seen, cur_key = {}, None, set(), None
+    # LIGHT units: (rank in the anchor cell, rank in the other cell) lexicographic.  HEAVY units: rounds of matchings --
+    # walk the order: a new unit or a microbe already seen in the current round starts a new round; a unit then needs at
+    # most max(m_a, m_b) rounds (two cells) or m - 1 + (m odd) rounds (one cell)
+    rounds, cur_unit, seen, prev = {}, None, set(), None
+    n_heavy_pairs = 0
     for k in range(order.shape[0]):
         i, j = int(order[k, 0]), int(order[k, 1])
-        unit = (int(phase[k]), min(key[i], key[j]), max(key[i], key[j]))
-        if unit != cur_unit or i in seen or j in seen:
-            if unit != cur_unit:
-                cur_unit = unit
-            rounds[unit] = rounds.get(unit, 0) + 1
-            seen = set()
-        seen.add(i)
-        seen.add(j)
+        ki, kj = int(key[i]), int(key[j])
+        same = ki == kj
+        # anchor = the microbe of the western / southern cell (same cell: the smaller rank)
+        a, b = (i, j) if ((cy[i], cx[i]) < (cy[j], cx[j]) or (same and rank[i] < rank[j])) else (j, i)
+        unit = (int(phase[k]), min(ki, kj), max(ki, kj))
+        light = bool(orps.unit_is_light(np.bool_(same), occ[a], occ[b]))
+        if light:
+            if unit == cur_unit:
+                assert (rank[a], rank[b]) > prev, "light unit %r not in lexicographic rank order" % (unit,)
+            prev = (rank[a], rank[b])
+        else:
+            n_heavy_pairs += 1
+            if unit != cur_unit or i in seen or j in seen:
+                rounds[unit] = rounds.get(unit, 0) + 1
+                seen = set()
+            seen.add(i)
+            seen.add(j)
+        if unit != cur_unit:
+            cur_unit = unit
+            if light:
+                seen = set()
     for (ph, ca, cb), nr in rounds.items():
         ma, mb = int((key == ca).sum()), int((key == cb).sum())
         bound = max(ma, mb) if ca != cb else ma - 1 + (ma & 1)
         assert nr <= bound, "unit %r needs %d rounds, bound %d" % ((ph, ca, cb), nr, bound)
+    if name == "rps_clustered":
+        assert n_heavy_pairs > 1000 and len(rounds) > 5          # the clustered case does exercise the heavy order
 
 
 def test_reference_cost_pair_function_equals_the_unmodified_reference_call_by_call():
