@@ -322,8 +322,9 @@ def main():
     ap.add_argument("--resolve-mode", type=int, default=0, choices=[0, 1],
                     help="LM_OPT_RESOLVE_MODE: 0 nine phase launches (default), 1 tiled resolver (experimental)")
     ap.add_argument("--tile-smem", type=int, default=0, help="LM_OPT_RESOLVE_TILE_SMEM (with --resolve-mode 1)")
-    ap.add_argument("--interact-mode", type=int, default=1, choices=[0, 1],
-                    help="LM_OPT_INTERACT_MODE: 1 fused tile kernel (default), 0 the round-1 pipeline (A/B)")
+    ap.add_argument("--interact-mode", type=int, default=2, choices=[0, 1, 2],
+                    help="LM_OPT_INTERACT_MODE: 2 hybrid (default: round-1 pipeline for the light units + rounds of matchings for "
+                         "the queued heavy units), 1 fused tile kernel, 0 the round-1 pipeline alone (A/B)")
     ap.add_argument("--advect-mode", type=int, default=1, choices=[0, 1],
                     help="LM_OPT_ADVECT_MODE: 1 float32 RK4 within north_star's 1e-6 relative (default here), 0 bit-faithful "
                          "to the float32 restatement of Parcels' kernel (A/B)")
@@ -393,8 +394,10 @@ def main():
     from lagrangian_microbes_b200.engine import Engine
     Engine.DEFAULT_INTERACT_MODE = args.interact_mode           # every handle of this run (single or strips)
     Engine.DEFAULT_ADVECT_MODE = args.advect_mode
-    config["interact"] = ("fused tile kernel, tile-round order (LM_OPT_INTERACT_MODE=1)" if args.interact_mode == 1
-                          else "round-1 pipeline: pair search -> hand-off -> nine phase launches (LM_OPT_INTERACT_MODE=0)")
+    config["interact"] = {2: "hybrid: pair search -> hand-off -> nine phase launches for the light units, device-wide queue of "
+                             "heavy units resolved in rounds of matchings; cell-round order (LM_OPT_INTERACT_MODE=2)",
+                          1: "fused tile kernel, tile-round order (LM_OPT_INTERACT_MODE=1)",
+                          0: "round-1 pipeline: pair search -> hand-off -> nine phase launches (LM_OPT_INTERACT_MODE=0)"}[args.interact_mode]
     config["advect"] = ("float32 RK4, positions within 1e-6 relative of the float64 RK4 (LM_OPT_ADVECT_MODE=1)"
                         if args.advect_mode == 1 else "bit-faithful to the float32 restatement of Parcels' kernel (LM_OPT_ADVECT_MODE=0)")
 

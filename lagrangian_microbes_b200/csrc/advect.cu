@@ -15,6 +15,8 @@
 // 32 particles of a warp sit within a few 0.01-degree cells and their 16 corner reads per stage
 // collapse to a handful of broadcast L1 hits: the kernel is bound by its fp64 arithmetic
 // (4 x cos + 8 x div per particle), not by HBM (16 B per particle).
+#include <algorithm>
+
 #include "lm_internal.cuh"
 #include "philox.cuh"
 
@@ -24,6 +26,9 @@ struct StageDev {
     int ti[4];
     int interp[4];
     float frac[4];
+    // float32 RK4 on the interleaved field: time interval ti2 and which of its two levels: 0 the earlier, 1 the later, 2 both (interpolate)
+    int ti2[4];
+    int pick[4];
 };
 
 // Index search on one grid axis (parcels.h::search_indices_rectilinear restated): the cell i with
@@ -182,6 +187,69 @@ __device__ __forceinline__ bool sample_uv_fast(const FieldDev &f, float x, float
     return true;
 }
 
+// the same sample from the interleaved copy: (u_t, v_t, u_t+1, v_t+1) of one grid point and time interval in ONE 16-byte load
+__device__ __forceinline__ bool sample_uv4(const FieldDev &f, float x, float y, int ti2, int pick, float frac, float &u, float &v)
+{
+    float lx0, lx1, ly0, ly1;
+    const int xi = search_axis(f.lon, f.X, x, f.lon0, f.lon1, f.inv_dx, lx0, lx1);
+    const int yi = search_axis(f.lat, f.Y, y, f.lat0, f.lat1, f.inv_dy, ly0, ly1);
+    if (xi < 0 || yi < 0) return false;
+    const float xsi = __fdividef(x - lx0, lx1 - lx0), eta = __fdividef(y - ly0, ly1 - ly0);
+    const float omx = 1.f - xsi, ome = 1.f - eta;
+    const float w00 = omx * ome, w01 = xsi * ome, w11 = xsi * eta, w10 = omx * eta;
+    const float4 *__restrict__ p = f.UV4 + ((size_t)ti2 * f.Y + yi) * f.X + xi;
+    const float4 c00 = __ldg(p), c01 = __ldg(p + 1), c10 = __ldg(p + f.X), c11 = __ldg(p + f.X + 1);
+    const float u0 = fmaf(w10, c10.x, fmaf(w11, c11.x, fmaf(w01, c01.x, w00 * c00.x)));
+    const float v0 = fmaf(w10, c10.y, fmaf(w11, c11.y, fmaf(w01, c01.y, w00 * c00.y)));
+    const float u1 = fmaf(w10, c10.z, fmaf(w11, c11.z, fmaf(w01, c01.z, w00 * c00.z)));
+    const float v1 = fmaf(w10, c10.w, fmaf(w11, c11.w, fmaf(w01, c01.w, w00 * c00.w)));
+    // the same arithmetic as sample_uv_fast on the same values: the two layouts give identical positions
+    const float uu = pick == 2 ? fmaf(u1 - u0, frac, u0) : (pick == 1 ? u1 : u0);
+    const float vv = pick == 2 ? fmaf(v1 - v0, frac, v0) : (pick == 1 ? v1 : v0);
+    constexpr float inv_m_per_deg = (float)(1.0 / 111120.0);
+    u = uu * __fdividef(inv_m_per_deg, __cosf(y * 0.017453292519943295f));
+    v = vv * inv_m_per_deg;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) advect_rk4_uv4_kernel(FieldDev f, float *__restrict__ lon, float *__restrict__ lat,
+                                                             int n, StageDev st, float dt, Counters *ctr)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float x = lon[p], y = lat[p];
+    const float h = 0.5f * dt;
+    float u1, v1, u2, v2, u3, v3, u4, v4;
+    bool ok = sample_uv4(f, x, y, st.ti2[0], st.pick[0], st.frac[0], u1, v1);
+    if (ok) ok = sample_uv4(f, fmaf(u1, h, x), fmaf(v1, h, y), st.ti2[1], st.pick[1], st.frac[1], u2, v2);
+    if (ok) ok = sample_uv4(f, fmaf(u2, h, x), fmaf(v2, h, y), st.ti2[2], st.pick[2], st.frac[2], u3, v3);
+    if (ok) ok = sample_uv4(f, fmaf(u3, dt, x), fmaf(v3, dt, y), st.ti2[3], st.pick[3], st.frac[3], u4, v4);
+    if (!ok) {
+        atomicAdd(&ctr->n_oob, 1ull);
+        return;
+    }
+    const float sixth = dt * (1.f / 6.f);
+    lon[p] = fmaf(u1 + 2.f * (u2 + u3) + u4, sixth, x);
+    lat[p] = fmaf(v1 + 2.f * (v2 + v3) + v4, sixth, y);
+}
+
+__global__ void __launch_bounds__(256) interleave_field_kernel(const float *__restrict__ U, const float *__restrict__ V,
+                                                               float4 *__restrict__ out, size_t slab, size_t total)
+{
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x)
+        out[k] = make_float4(__ldg(U + k), __ldg(V + k), __ldg(U + k + slab), __ldg(V + k + slab));
+}
+
+cudaError_t launch_interleave_field(const FieldDev &f, float4 *uv4, cudaStream_t s, int64_t *launches)
+{
+    const size_t slab = (size_t)f.Y * f.X, total = (size_t)(f.T - 1) * slab;
+    if (total == 0) return cudaSuccess;
+    const unsigned int grid = (unsigned int)std::min<size_t>((total + 255) / 256, (size_t)kNumSMs * 16);
+    interleave_field_kernel<<<grid, 256, 0, s>>>(f.U, f.V, uv4, slab, total);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(256) advect_rk4_fast_kernel(FieldDev f, float *__restrict__ lon, float *__restrict__ lat,
                                                               int n, StageDev st, float dt, Counters *ctr)
 {
@@ -212,9 +280,15 @@ cudaError_t launch_advect(const FieldDev &f, float *lon, float *lat, int n, cons
         sd.ti[k] = st.ti[k];
         sd.interp[k] = st.interp[k];
         sd.frac[k] = st.frac[k];
+        // interleaved layout: interval ti (both levels when interpolating, else its earlier level), or -- at the last
+        // level, which starts no interval -- the later level of the interval before
+        const bool last = !st.interp[k] && st.ti[k] >= f.T - 1;
+        sd.ti2[k] = last ? st.ti[k] - 1 : st.ti[k];
+        sd.pick[k] = st.interp[k] ? 2 : (last ? 1 : 0);
     }
     const int block = 256;
-    if (mode == 1) advect_rk4_fast_kernel<<<(n + block - 1) / block, block, 0, s>>>(f, lon, lat, n, sd, dt, ctr);
+    if (mode == 1 && f.UV4) advect_rk4_uv4_kernel<<<(n + block - 1) / block, block, 0, s>>>(f, lon, lat, n, sd, dt, ctr);
+    else if (mode == 1) advect_rk4_fast_kernel<<<(n + block - 1) / block, block, 0, s>>>(f, lon, lat, n, sd, dt, ctr);
     else advect_rk4_kernel<<<(n + block - 1) / block, block, 0, s>>>(f, lon, lat, n, sd, dt, ctr);
     ++*launches;
     return cudaGetLastError();

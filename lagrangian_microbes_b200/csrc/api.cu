@@ -3,6 +3,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <algorithm>
 
 #include "lm_internal.cuh"
 #include "philox.cuh"
@@ -74,6 +75,8 @@ int lm_destroy(lm_handle h)
     cudaFree(h->keys); cudaFree(h->slots); cudaFree(h->cell_count); cudaFree(h->cell_start_buf[0]); cudaFree(h->cell_start_buf[1]);
     cudaFree(h->n_pairs_snap);
     cudaFree(h->sticky);
+    cudaFree(h->heavy_list); cudaFree(h->heavy_cnt);
+    cudaFree(h->uv4);
     cudaFree(h->sp_snap); cudaFree(h->tile_scratch); cudaFree(h->tile_scratch_used);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_find_done) cudaEventDestroy(h->ev_find_done);
@@ -125,7 +128,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     h->overlap = 1;
     h->norm = LM_NORM_2;
     h->advect_mode = 0;
-    h->interact_mode = 1;
+    h->interact_mode = 2;
     h->draw_batch = 0;
     h->tile_cap = 0;
     h->tile_rec_cap = 0;
@@ -148,6 +151,10 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_sp_ready, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaMemset(h->n_pairs_snap, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && dev_alloc(&h->sticky, 1);
+    // hybrid mode: queues of heavy units, per phase; a heavy unit needs >= 17 microbes in two cells, so N / 8 per phase is ample
+    h->heavy_cap = std::max<int64_t>(1024, max_particles / 8);
+    ok = ok && dev_alloc(&h->heavy_list, (size_t)18 * h->heavy_cap) && dev_alloc(&h->heavy_cnt, 36);
+    if (ok) ok = cudaMemset(h->heavy_cnt, 0, 36 * sizeof(unsigned int)) == cudaSuccess;
     if (ok) ok = cudaMemset(h->sticky, 0, sizeof(unsigned int)) == cudaSuccess;
     for (int k = 0; ok && k < 2; ++k) {
         ok = ok && cudaEventCreateWithFlags(&h->ev_scatter[k], cudaEventDisableTiming) == cudaSuccess;
@@ -181,6 +188,8 @@ int lm_set_field(lm_handle h, const float *U, const float *V, const float *lon, 
     h->field.lon1 = ends[1]; h->field.lat1 = ends[3];
     h->field.inv_dx = (float)(X - 1) / (ends[1] - ends[0]);
     h->field.inv_dy = (float)(Y - 1) / (ends[3] - ends[2]);
+    h->field.UV4 = nullptr;
+    h->uv4_stale = true;
     h->have_field = true;
     return LM_OK;
 }
@@ -190,6 +199,8 @@ int lm_update_field_data(lm_handle h, const float *U, const float *V, int32_t T)
     if (!h || !U || !V || T < 1) return LM_EINVAL;
     if (!h->have_field) return LM_ESTATE;
     h->field.U = U; h->field.V = V; h->field.T = T;
+    h->field.UV4 = nullptr;
+    h->uv4_stale = true;
     return LM_OK;
 }
 
@@ -298,9 +309,31 @@ __global__ void latch_faults_kernel(const Counters *c, unsigned int *sticky, lon
     if (emit_cap >= 0 && (long long)c->n_pairs > emit_cap) f |= 1u;
     if (rps_cap >= 0 && (long long)c->n_pairs > rps_cap) f |= 2u;
     if (c->n_overflow) f |= 4u;
-    if (c->n_xfer_overflow) f |= 8u;
+    if (c->n_xfer_overflow || c->n_heavy_overflow) f |= 8u;
     if (c->n_misrouted) f |= 16u;
     if (f) atomicOr(sticky, f);
+}
+
+// LM_OPT_ADVECT_MODE = 1 samples an interleaved copy of the field (one 16-byte load per corner instead of four 4-byte
+// loads): (re)built on the advecting stream after lm_set_field / lm_update_field_data.  A single time level has no
+// interval to interleave: the kernel then reads U and V directly.
+static int ensure_uv4(lm_handle h, cudaStream_t s)
+{
+    if (h->advect_mode != 1 || !h->have_field) return LM_OK;
+    if (h->field.T < 2) { h->field.UV4 = nullptr; return LM_OK; }
+    if (!h->uv4_stale && h->field.UV4) return LM_OK;
+    const size_t need = (size_t)(h->field.T - 1) * h->field.Y * h->field.X;
+    if (need > h->uv4_elems) {
+        LM_CUDA(cudaStreamSynchronize(s));               // nothing may still read the old copy
+        cudaFree(h->uv4);
+        h->uv4 = nullptr; h->uv4_elems = 0;
+        if (cudaMalloc(reinterpret_cast<void **>(&h->uv4), need * sizeof(float4)) != cudaSuccess) { cudaGetLastError(); return LM_ENOMEM; }
+        h->uv4_elems = need;
+    }
+    LM_CUDA(launch_interleave_field(h->field, h->uv4, s, &h->launches));
+    h->field.UV4 = h->uv4;
+    h->uv4_stale = false;
+    return LM_OK;
 }
 
 static int reset_counters(lm_handle h, cudaStream_t s)
@@ -341,6 +374,7 @@ int lm_advect_rk4(lm_handle h, float *lon, float *lat, int64_t n, const lm_stage
         if (st->ti[k] < 0 || st->ti[k] + (st->interp[k] ? 1 : 0) >= h->field.T) return LM_EINVAL;
     LM_CUDA(cudaSetDevice(h->device));
     // n_out_of_bounds accumulates over calls until lm_reset_stats
+    { const int rcu = ensure_uv4(h, as_stream(stream)); if (rcu) return rcu; }
     LM_CUDA(launch_advect(h->field, lon, lat, (int)n, *st, dt, h->ctr, as_stream(stream), &h->launches, h->advect_mode));
     return LM_OK;
 }
@@ -512,6 +546,7 @@ int lm_step_move(lm_handle h, int32_t flags, const lm_stage_times *st, float dt,
         moved = true;
     }
     if (flags & LM_STEP_ADVECT) {
+        { const int rcu = ensure_uv4(h, s); if (rcu) return rcu; }
         LM_CUDA(launch_advect(h->field, h->lon[c], h->lat[c], n, *st, dt, h->ctr, s, &h->launches, h->advect_mode));
         moved = true;
     }
@@ -627,7 +662,7 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
             rs = h->side_stream;
         }
         // the tiled resolver takes all nine phases in one launch when no halo exchange has to happen after phase 5
-        h->resolve_all_in_begin = h->interact_mode == 0 && h->resolve_mode == 1 && !in_strip_mode(h);
+        h->resolve_all_in_begin = h->interact_mode == 0 && h->resolve_mode == 1 && !in_strip_mode(h);   // (the hybrid mode interleaves phases: nine launches)
         if (n > 0) LM_CUDA(launch_resolve_phases(h, h->sp[c], 0, h->resolve_all_in_begin ? 8 : 5, rs));
     }
     if (h->has_south && interact) LM_CUDA(launch_row0_species_pack(h, h->sp[c], s));
@@ -821,6 +856,7 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
         out->n_misrouted = (int64_t)c.n_misrouted;
     }
     if (c.n_xfer_overflow) return LM_ENOSPC;                                       // migration / ghost buffers too small
+    if (c.n_heavy_overflow) return LM_ENOSPC;                                      // heavy-unit queue too small: species invalid
     if (c.n_misrouted) return LM_ESTATE;   // particles held by a strip that does not own them (see bin.cu)
     if (h->emit_cap >= 0 && (int64_t)c.n_pairs > h->emit_cap) return LM_ENOSPC;   // pair list truncated
     if (h->rps_cap >= 0 && (int64_t)c.n_pairs > h->rps_cap) return LM_ENOSPC;     // RPS hand-off buffer too small: species invalid
@@ -886,7 +922,7 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
             return LM_OK;
         }
         case LM_OPT_INTERACT_MODE:
-            if (value < 0 || value > 1) return LM_EINVAL;
+            if (value < 0 || value > 2) return LM_EINVAL;
             if (h->stage != 0) return LM_ESTATE;                 // not between the stages of a step
             h->interact_mode = (int)value;
             return LM_OK;
@@ -909,6 +945,7 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
         case LM_OPT_ADVECT_MODE:
             if (value < 0 || value > 1) return LM_EINVAL;
             h->advect_mode = (int)value;
+            h->uv4_stale = true;
             return LM_OK;
         case LM_OPT_RESOLVE_TILE_SHAPE:
             if (value < 0 || value > 3) return LM_EINVAL;

@@ -723,15 +723,128 @@ __global__ void __launch_bounds__(IT_THREADS) interact_cross_kernel(IArgs A, lon
     flush_pairs(A, sh, true);
 }
 
+// ---- LM_OPT_INTERACT_MODE = 2 (hybrid): the HEAVY units of one phase of the cell-round order, from a device-wide queue.
+// The pair search of the round-1 pipeline (csrc/pairs.cu) leaves the heavy units out and queues them per phase; here
+// whole warps take them round by round (the large ones the whole CTA).  The microbes of the unit's one or two cells are
+// staged in shared memory first -- a round is then a shared-memory round trip, not a global one: the rounds are what is
+// sequential, a cell of 340 microbes has 339 of them -- distance tests, pair emission, draws and species updates inline;
+// every lane of a round holds a pair of its own.
+constexpr int HV_WARP_CAP = 256;                          // microbes of a unit one warp stages (13 B each)
+constexpr int HV_CTA_CAP = 4096;                          // ... the whole CTA (larger units work on the global arrays)
+struct UnitView {
+    static constexpr bool kStaged = true;
+    const float2 *pos;
+    const int32_t *id;
+    int8_t *sp;
+    __device__ __forceinline__ float2 P(int i) const { return pos[i]; }
+    __device__ __forceinline__ int I(int i) const { return id[i]; }
+    __device__ __forceinline__ int S(int i) const { return ((volatile int8_t *)sp)[i]; }
+    __device__ __forceinline__ void W(int i, int s) const { ((volatile int8_t *)sp)[i] = (int8_t)s; }
+};
+
+// ug: x, y first microbe of the anchor / other cell (global indices; equal: one cell) | z, w their sizes.  buf: room for
+// `cap` microbes.  Called by all lanes of a warp (CTA = false) or all threads of the CTA (CTA = true) with the same unit.
+template <bool DO_RPS, bool CTA>
+__device__ void heavy_unit(const IArgs &A, Shared &sh, const uint4 ug, unsigned char *buf, int cap)
+{
+    const int nthr = CTA ? IT_THREADS : 32;
+    const int me = CTA ? (int)threadIdx.x : (int)(threadIdx.x & 31);
+    const bool same = ug.x == ug.y;
+    const int ma = (int)ug.z, mb = same ? 0 : (int)ug.w, n = ma + mb;
+    if (n > cap) {
+        GlobalView g{A.lon, A.lat, A.id, A.sp};
+        unit_rounds<GlobalView, DO_RPS, CTA>(A, sh, g, ug);
+        return;
+    }
+    float2 *s_pos = reinterpret_cast<float2 *>(buf);
+    int32_t *s_id = reinterpret_cast<int32_t *>(s_pos + cap);
+    int8_t *s_sp = reinterpret_cast<int8_t *>(s_id + cap);
+    if (CTA) __syncthreads(); else __syncwarp();                      // the buffer's previous unit is done with
+    for (int i = me; i < n; i += nthr) {
+        const int g = i < ma ? (int)ug.x + i : (int)ug.y + (i - ma);
+        s_pos[i] = make_float2(__ldg(A.lon + g), __ldg(A.lat + g));
+        s_id[i] = __ldg(A.id + g);
+        if (DO_RPS) s_sp[i] = A.sp[g];
+    }
+    if (CTA) __syncthreads(); else __syncwarp();
+    UnitView v{s_pos, s_id, s_sp};
+    unit_rounds<UnitView, DO_RPS, CTA>(A, sh, v, make_uint4(0u, same ? 0u : (unsigned int)ma, ug.z, ug.w));
+    if (CTA) __syncthreads(); else __syncwarp();
+    if (DO_RPS)
+        for (int i = me; i < n; i += nthr) A.sp[i < ma ? (int)ug.x + i : (int)ug.y + (i - ma)] = s_sp[i];
+}
+
+template <bool DO_RPS>
+__global__ void __launch_bounds__(IT_THREADS) interact_heavy_kernel(IArgs A, const int2 *__restrict__ list_w, const int2 *__restrict__ list_m,
+                                                                    unsigned int *cnt, unsigned int cap)
+{
+    // cnt: [0] queued warp units | [1] queued CTA units | [2] warp ticket | [3] CTA ticket   (of this phase)
+    extern __shared__ __align__(16) unsigned char s_buf[];            // HV_CTA_CAP * 13 bytes: 8 warp buffers, or one for the CTA
+    __shared__ Shared sh;
+    __shared__ unsigned int s_t;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int n_w = min(cnt[0], cap), n_m = min(cnt[1], cap);
+    if (n_w == 0 && n_m == 0) return;
+    if (tid == 0) sh.stage_cnt = 0;
+    __syncthreads();
+    auto unit_of = [&](int2 cc) {
+        const int a0 = __ldg(A.cell_start + cc.x), a1 = __ldg(A.cell_start + cc.x + 1);
+        const int b0 = __ldg(A.cell_start + cc.y), b1 = __ldg(A.cell_start + cc.y + 1);
+        return make_uint4((unsigned int)a0, (unsigned int)b0, (unsigned int)(a1 - a0), (unsigned int)(b1 - b0));
+    };
+    while (true) {
+        unsigned int t = 0;
+        if (lane == 0) t = atomicAdd(&cnt[2], 1u);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= n_w) break;
+        heavy_unit<DO_RPS, false>(A, sh, unit_of(list_w[t]), s_buf + (size_t)warp * (HV_WARP_CAP * 13), HV_WARP_CAP);
+    }
+    __syncthreads();
+    flush_pairs(A, sh, false);
+    while (true) {
+        if (tid == 0) s_t = atomicAdd(&cnt[3], 1u);
+        __syncthreads();
+        const unsigned int t = s_t;
+        __syncthreads();
+        if (t >= n_m) break;
+        heavy_unit<DO_RPS, true>(A, sh, unit_of(list_m[t]), s_buf, HV_CTA_CAP);
+    }
+    __syncthreads();
+    flush_pairs(A, sh, true);
+}
+
+static void fill_args(IArgs &A, lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, double r,
+                      const RpsDev *rps, int2 *pairs_out, int64_t cap);
+
 }  // namespace
 
-// Phases [first, last] of 0..14 (0..8 are ONE launch: any of them asks for all nine).
-cudaError_t launch_interact(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
-                            double r, const RpsDev *rps, int2 *pairs_out, int64_t cap, int first, int last,
-                            cudaStream_t s)
+// hybrid mode: the queued heavy units of phase `ph` (0..8, cell-phase numbering); arguments as saved by launch_find
+cudaError_t launch_interact_heavy(lm_handle_s *h, int8_t *sp, int ph, cudaStream_t s)
 {
-    if (n <= 0) return cudaSuccess;
+    if (h->ia_n <= 0 || !h->heavy_list) return cudaSuccess;
     IArgs A;
+    fill_args(A, h, h->ia_lon, h->ia_lat, h->ia_id, sp, h->ia_r, h->ia_have_rps ? &h->ia_rps : nullptr, h->ia_pairs, h->ia_cap);
+    const int2 *lw = h->heavy_list + (size_t)(2 * ph) * h->heavy_cap, *lm_ = h->heavy_list + (size_t)(2 * ph + 1) * h->heavy_cap;
+    unsigned int *cnt = h->heavy_cnt + 4 * ph;
+    const unsigned int grid = 2 * kNumSMs;
+    const size_t dyn = (size_t)HV_CTA_CAP * 13;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(interact_heavy_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(interact_heavy_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    if (h->ia_have_rps) interact_heavy_kernel<true><<<grid, IT_THREADS, dyn, s>>>(A, lw, lm_, cnt, (unsigned int)h->heavy_cap);
+    else interact_heavy_kernel<false><<<grid, IT_THREADS, dyn, s>>>(A, lw, lm_, cnt, (unsigned int)h->heavy_cap);
+    ++h->launches;
+    return cudaGetLastError();
+}
+
+namespace {
+static void fill_args(IArgs &A, lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, double r,
+                      const RpsDev *rps, int2 *pairs_out, int64_t cap)
+{
     A.lon = lon; A.lat = lat; A.id = id; A.sp = rps ? sp : nullptr; A.cell_start = h->cell_start;
     A.ncx = h->grid.ncx; A.rows_owned = h->strip.rows_owned; A.rows_local = h->strip.rows_local;
     A.tiles_x = (A.ncx + IT_TW - 1) / IT_TW; A.tiles_y = (A.rows_owned + IT_TH - 1) / IT_TH;
@@ -757,6 +870,18 @@ cudaError_t launch_interact(lm_handle_s *h, const float *lon, const float *lat, 
     A.draw_batch = h->draw_batch > 0 ? h->draw_batch : 8;
     A.force_walk = h->tile_path == 1 ? 1 : 0;
     A.phase = 0;
+    A.tile_cap = A.rec_cap = 0;
+}
+}  // namespace
+
+// Phases [first, last] of 0..14 (0..8 are ONE launch: any of them asks for all nine).
+cudaError_t launch_interact(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
+                            double r, const RpsDev *rps, int2 *pairs_out, int64_t cap, int first, int last,
+                            cudaStream_t s)
+{
+    if (n <= 0) return cudaSuccess;
+    IArgs A;
+    fill_args(A, h, lon, lat, id, sp, r, rps, pairs_out, cap);
     // shared memory per tile: room for 1.5 x the mean occupancy of a tile (at least 2,048 microbes, at most 6,144) and for
     // two records per staged microbe and direction (the mean is below one); fuller tiles / directions take the lane walk
     const long long tiles = (long long)A.tiles_x * A.tiles_y;

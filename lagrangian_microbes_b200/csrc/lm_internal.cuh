@@ -11,6 +11,7 @@ constexpr int kNumSMs = 148;   // B200
 
 struct FieldDev {
     const float *U, *V, *lon, *lat;
+    const float4 *UV4;                   // LM_OPT_ADVECT_MODE = 1: [T - 1][Y][X] (u_t, v_t, u_t+1, v_t+1) per grid point and time interval
     int T, Y, X;
     float lon0, lat0, lon1, lat1, inv_dx, inv_dy;   // axis ends; index guess: i = (x - lon0) * inv_dx
 };
@@ -26,6 +27,7 @@ struct Counters {
     unsigned int n_leave[2];         // particles that left the strip this step: [0] southwards, [1] northwards
     unsigned int n_misrouted;        // arrivals that belong to neither this strip nor ... (moved > 1 strip in a step)
     unsigned int n_xfer_overflow;    // migration / ghost records that did not fit the exchange buffers
+    unsigned int n_heavy_overflow;   // heavy units that did not fit the queue (hybrid mode): species invalid
 };
 
 // Strip geometry of one handle inside the GLOBAL cell grid (multi-GPU latitude strips).
@@ -54,6 +56,9 @@ struct lm_handle_s {
     // velocity field (borrowed)
     lm::FieldDev field;
     bool have_field;
+    float4 *uv4;           // the handle's interleaved copy of the field for the float32 RK4 (built lazily on the advecting stream)
+    size_t uv4_elems;
+    bool uv4_stale;
     // cell grid
     lm_grid grid;
     bool have_grid;
@@ -95,8 +100,13 @@ struct lm_handle_s {
     int find_path;         // LM_OPT_FIND_PATH: 0 auto | 1 every warp takes the two-pass (dense cluster) path
     int resolve_heavy_min; // LM_OPT_RESOLVE_HEAVY_MIN: 0 = default (160)
     int resolve_batch;     // LM_OPT_RESOLVE_BATCH: pairs per lane and iteration in the resolver's stream walk (1, 4, 8)
-    int interact_mode;     // LM_OPT_INTERACT_MODE: 1 (default) fused tile kernel, tile-round order (csrc/interact.cu) |
+    int interact_mode;     // LM_OPT_INTERACT_MODE: 2 (default) hybrid: round-1 pipeline for the light units + a device-wide queue of heavy
+                           //                         units resolved in rounds of matchings (cell-round order) |
+                           //                       1 fused tile kernel, tile-round order (csrc/interact.cu) |
                            //                       0 round-1 pipeline: pair search -> hand-off -> nine phase launches (csrc/pairs.cu)
+    int2 *heavy_list;      // [9 phases][2: warp units | CTA units][heavy_cap] (anchor cell, other cell) queued by the pair search
+    unsigned int *heavy_cnt;   // [9][4] queued warp units | queued CTA units | warp ticket | CTA ticket
+    int64_t heavy_cap;
     int draw_batch;        // LM_OPT_DRAW_BATCH: parked lanes that trigger a warp's Philox rounds (0 = default, 20)
     int tile_cap;          // LM_OPT_TILE_CAP: microbes a tile stages in shared memory (0 = from the mean occupancy)
     int tile_rec_cap;      // LM_OPT_TILE_REC_CAP: records (hits of one direction) a tile holds in shared memory (0 = 2 x tile_cap)
@@ -166,6 +176,7 @@ namespace lm {
 // ---- launchers (each returns cudaGetLastError() of its launches) --------------------------------
 cudaError_t launch_advect(const FieldDev &f, float *lon, float *lat, int n, const lm_stage_times &st, float dt,
                           Counters *ctr, cudaStream_t s, int64_t *launches, int mode = 0);
+cudaError_t launch_interleave_field(const FieldDev &f, float4 *uv4, cudaStream_t s, int64_t *launches);
 cudaError_t launch_diffuse(float *lon, float *lat, const int32_t *ids, int n, double amp, uint64_t seed, uint64_t step,
                            cudaStream_t s, int64_t *launches);
 // bins (lon,lat,sp,id)[src] into (cell,id) order in dst; sp / id may be null (id -> source index)
@@ -202,6 +213,7 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
 cudaError_t launch_interact(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, int8_t *sp, int n,
                             double r, const RpsDev *rps, int2 *pairs_out, int64_t cap, int first, int last,
                             cudaStream_t s);
+cudaError_t launch_interact_heavy(lm_handle_s *h, int8_t *sp, int phase, cudaStream_t s);
 cudaError_t launch_pair_uniforms(const int2 *pairs, int64_t np, uint64_t seed, uint64_t step, double *u,
                                  cudaStream_t s);
 int resolve_explicit(lm_handle_s *h, const int2 *pairs, const double *u, int64_t np, int8_t *species, int64_t n,

@@ -81,6 +81,12 @@ struct FindArgs {
     int2 *__restrict__ pairs;
     unsigned long long cap_words, cap_pairs;
     Counters *ctr;
+    // LM_OPT_INTERACT_MODE = 2 (hybrid): HEAVY units (csrc/interact.cu::unit_is_light, part of the cell-round order) are left
+    // out here and queued per phase for interact_heavy_kernel
+    int hybrid;
+    int2 *heavy_list;                    // [9][2][heavy_cap]
+    unsigned int *heavy_cnt;             // [9][4]
+    unsigned int heavy_cap;
 };
 
 __device__ __forceinline__ int cell_coord2(float v, double origin, double inv_h, int n)
@@ -184,6 +190,34 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
         }
     }
 
+    // ---- hybrid mode: which of my five units are heavy?  (two cells: m_a * m_b > 256 or m_b > 64; one cell: m > 23.)  Their
+    // hits are dropped below; the first microbe of the cell queues them for the rounds-of-matchings kernel.
+    unsigned int heavy_dirs = 0;
+    if (A.hybrid && valid) {
+        const unsigned int ma = (unsigned int)(sE - base0);
+        const unsigned int mb[5] = {ma, (unsigned int)(endE - sE), (unsigned int)(sN - begNW), (unsigned int)(sNE - sN),
+                                    (unsigned int)(endNE - sNE)};
+        if (ma >= 24u) heavy_dirs |= 1u;
+#pragma unroll
+        for (int d = 1; d < 5; ++d)
+            if (mb[d] >= 1u && ((unsigned long long)ma * mb[d] > 256ull || mb[d] > 64u)) heavy_dirs |= 1u << d;
+        if (heavy_dirs && a == base0) {
+            const int ncx = A.g.ncx, cx = c % ncx, cy = c / ncx;
+#pragma unroll
+            for (int d = 0; d < 5; ++d) {
+                if (!((heavy_dirs >> d) & 1u)) continue;
+                const int other = d == 0 ? c : (d == 1 ? c + 1 : c + ncx + (d - 3));
+                const int ph = d == 0 ? 0 : (d == 1 ? 1 + (cx & 1) : 3 * (cy & 1) + 1 + d);
+                const unsigned long long M = d == 0 ? (unsigned long long)(ma + (ma & 1u)) : (unsigned long long)max(ma, mb[d]);
+                const unsigned long long slots = d == 0 ? (M - 1ull) * (M >> 1) : (unsigned long long)ma * M;
+                // the whole CTA takes it: many slots (interact.cu::IT_MEGA_MIN) or more microbes than a warp stages (HV_WARP_CAP)
+                const int big = (slots >= 8192ull || (d == 0 ? ma : ma + mb[d]) > 256u) ? 1 : 0;
+                const unsigned int k = atomicAdd(&A.heavy_cnt[4 * ph + big], 1u);
+                if (k < A.heavy_cap) A.heavy_list[(size_t)(2 * ph + big) * A.heavy_cap + k] = make_int2(c, other);
+                else atomicAdd(&A.ctr->n_heavy_overflow, 1u);
+            }
+        }
+    }
     // ---- the candidates of a lane: the concatenation of two index ranges (same row: rest of its cell + E;
     // next row: NW, N, NE), i = 0 .. ntot-1.  ONE loop, so a warp iterates max-of-sums, not sum-of-maxes, of
     // its lanes' candidate counts; hits are recorded as bits of a 64-bit mask -- nothing else happens in the
@@ -203,6 +237,12 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
             if (within<NORM>(A, xa, ya, b)) mask |= bit;
             ++b;
             bit <<= 1;
+        }
+        if (heavy_dirs) {                                      // hybrid mode: the hits of heavy units are not mine
+            const int lo[5] = {0, t1, n1, t3, t4}, hi[5] = {t1, n1, t3, t4, ntot};
+#pragma unroll
+            for (int d = 0; d < 5; ++d)
+                if ((heavy_dirs >> d) & 1u) mask &= ~(bits_below(hi[d]) & ~bits_below(lo[d]));
         }
         const unsigned int p1 = __popcll(mask & bits_below(t1)), p2 = __popcll(mask & bits_below(n1));
         const unsigned int p3 = __popcll(mask & bits_below(t3)), p4 = __popcll(mask & bits_below(t4));
@@ -225,6 +265,15 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
             ++b;
             bit <<= 1;
         }
+        if (heavy_dirs) {
+            const int lo[5] = {0, t1, n1, t3, t4}, hi[5] = {t1, n1, t3, t4, ntot};
+#pragma unroll
+            for (int d = 0; d < 5; ++d)
+                if ((heavy_dirs >> d) & 1u) {
+                    mask &= ~(bits_below(hi[d]) & ~bits_below(lo[d]));
+                    mask_hi &= ~(bits_below(hi[d] - 64) & ~bits_below(lo[d] - 64));
+                }
+        }
         const unsigned int p1 = __popcll(mask & bits_below(t1)) + __popcll(mask_hi & bits_below(t1 - 64));
         const unsigned int p2 = __popcll(mask & bits_below(n1)) + __popcll(mask_hi & bits_below(n1 - 64));
         const unsigned int p3 = __popcll(mask & bits_below(t3)) + __popcll(mask_hi & bits_below(t3 - 64));
@@ -235,8 +284,8 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
         unsigned long long acc0 = 0, acc1 = 0;                 // hit counters, CELL_BITS each: d0 d1 d2 | d3 d4
         for (int i = 0; i < ntot; ++i) {
             const int b = (i < n1) ? beg0 + i : begNW + (i - n1);
-            if (within<NORM>(A, xa, ya, b)) {
-                const int d = (i >= t1) + (i >= n1) + (i >= t3) + (i >= t4);
+            const int d = (i >= t1) + (i >= n1) + (i >= t3) + (i >= t4);
+            if (!((heavy_dirs >> d) & 1u) && within<NORM>(A, xa, ya, b)) {
                 if (d < 3) acc0 += 1ull << (CELL_BITS * d); else acc1 += 1ull << (CELL_BITS * (d - 3));
             }
         }
@@ -358,8 +407,8 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
         unsigned int kk = 0;
         for (int i = 0; i < ntot; ++i) {
             const int b = (i < n1) ? beg0 + i : begNW + (i - n1);
-            if (within<NORM>(A, xa, ya, b)) {
-                const int d = (i >= t1) + (i >= n1) + (i >= t3) + (i >= t4);
+            const int d = (i >= t1) + (i >= n1) + (i >= t3) + (i >= t4);
+            if (!((heavy_dirs >> d) & 1u) && within<NORM>(A, xa, ya, b)) {
                 const int ib = __ldg(A.id + b);
                 const int lo = min(my_id, ib), hi = max(my_id, ib);
                 const unsigned long long r_d = d == 0 ? rel[0] : (d == 1 ? rel[1] : (d == 2 ? rel[2] : (d == 3 ? rel[3] : rel[4])));
@@ -812,6 +861,14 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
                         const RpsDev *rps, int2 *pairs_out, int64_t cap, cudaStream_t s)
 {
     h->rps_cap = rps ? h->max_pairs : -1;
+    if (h->interact_mode == 2) {                           // hybrid: the heavy units' kernel needs these (launch_resolve_phases)
+        h->ia_lon = lon; h->ia_lat = lat; h->ia_id = id; h->ia_n = n; h->ia_r = r;
+        h->ia_have_rps = rps != nullptr;
+        if (rps) h->ia_rps = *rps;
+        h->ia_pairs = pairs_out; h->ia_cap = cap;
+        cudaError_t e0 = cudaMemsetAsync(h->heavy_cnt, 0, 36 * sizeof(unsigned int), s);
+        if (e0 != cudaSuccess) return e0;
+    }
     if (h->interact_mode == 1) {
         // fused tile kernel: the tile phases and the vertical-boundary phases now, the horizontal-boundary phases
         // (the only ones that cross a strip boundary) with launch_resolve_phases(.., 6, 8)
@@ -848,6 +905,8 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
     F.cap_words = rps ? (unsigned long long)h->max_pairs : 0ull;
     F.cap_pairs = (pairs_out && cap > 0) ? (unsigned long long)cap : 0ull;
     F.ctr = h->ctr;
+    F.hybrid = h->interact_mode == 2 ? 1 : 0;
+    F.heavy_list = h->heavy_list; F.heavy_cnt = h->heavy_cnt; F.heavy_cap = (unsigned int)h->heavy_cap;
     const bool emit = F.cap_pairs > 0;
     const int grid = (n + FIND_THREADS - 1) / FIND_THREADS;
     ++h->launches;
@@ -1291,8 +1350,10 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
         return launch_interact(h, h->ia_lon, h->ia_lat, h->ia_id, sp, h->ia_n, h->ia_r, h->ia_have_rps ? &h->ia_rps : nullptr,
                                h->ia_pairs, h->ia_cap, 12, 14, s);
     }
-    if (h->rps_cap < 0) return cudaSuccess;
-    if (h->resolve_mode == 1) return launch_resolve_tiled(h, sp, first, last, s);
+    const bool hybrid = h->interact_mode == 2;             // the heavy units of every phase follow its light units
+    const bool light = h->rps_cap >= 0;                    // false: pair search only (the heavy units' pairs still have to be found)
+    if (!light && !hybrid) return cudaSuccess;
+    if (h->resolve_mode == 1 && !hybrid) return launch_resolve_tiled(h, sp, first, last, s);
     ResolveArgs R;
     R.sp = sp; R.cell_start = h->cell_start; R.hits = h->hits;
     R.n_pairs = h->n_pairs_snap;
@@ -1314,6 +1375,11 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
         R.rec = h->rec + (size_t)d_idx * h->max_cells;
         R.rec2 = h->rec2 + (size_t)d_idx * (h->max_particles / 32 + 2);
         if (rows <= 0 || R.units_per_row <= 0) continue;
+        if (hybrid) {
+            cudaError_t eh = launch_interact_heavy(h, sp, ph, s);
+            if (eh != cudaSuccess) return eh;
+        }
+        if (!light) continue;
         // units per lane, measured on B200 (profiles/): 8 wins on large sparse grids (12.5 M microbes, 5.2 M
         // cells, 2 pairs per unit: 0.81 vs 0.90 ms), 4 on smaller / denser ones (10 M microbes, 1.2 M cells, 27
         // pairs per unit: 2.2 vs 3.6 ms) where eight long streams per lane leave too few warps in flight
@@ -1340,7 +1406,7 @@ cudaError_t launch_pairs(lm_handle_s *h, const float *lon, const float *lat, con
 {
     if (h->interact_mode == 1) return launch_interact(h, lon, lat, id, sp, n, r, rps, pairs_out, cap, 0, 14, s);
     cudaError_t e = launch_find(h, lon, lat, id, n, r, rps, pairs_out, cap, s);
-    if (e != cudaSuccess || !rps || n <= 0) return e;
+    if (e != cudaSuccess || n <= 0 || (!rps && h->interact_mode != 2)) return e;
     return launch_resolve_phases(h, sp, 0, 8, s);
 }
 

@@ -89,7 +89,7 @@ class Engine:
         self.h = h
         self._field = None            # keeps the borrowed field tensors alive
         self._n_pairs_dev = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self.interact_mode = 1
+        self.interact_mode = 2                       # the library's default (hybrid)
         # class attribute, else the environment (LM_INTERACT_MODE / LM_ADVECT_MODE: A/B runs of the tools), else the library's
         im = self.DEFAULT_INTERACT_MODE if self.DEFAULT_INTERACT_MODE is not None else os.environ.get("LM_INTERACT_MODE")
         am = self.DEFAULT_ADVECT_MODE if self.DEFAULT_ADVECT_MODE is not None else os.environ.get("LM_ADVECT_MODE")

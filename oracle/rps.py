@@ -204,7 +204,21 @@ def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
 
     Units of one phase touch disjoint microbes; their relative order is immaterial.
     """
-    tw, th = tile
+    return _round_order(pairs, lon32, lat32, grid, tile)
+
+
+def cell_round_order(pairs, lon32, lat32, grid):
+    """The canonical order of the HYBRID device path (LM_OPT_INTERACT_MODE = 2, the default): the nine phases of
+    ``cell_phase_order`` (0 same cell | 1 + (cx & 1) east | 3 (cy & 1) + 3, + 4, + 5 north-west, north, north-east), units
+    by anchor cell, and inside a unit the rule of ``tile_round_order``: LIGHT units (``unit_is_light``) in (rank in the
+    anchor cell, rank in the other cell) lexicographic order -- which is ``cell_phase_order``'s (id_a, id_b) -- and HEAVY
+    units in rounds of matchings.  The round-1 pipeline resolves the light units, a device-wide queue of heavy units is
+    resolved round by round by whole warps / CTAs (csrc/interact.cu::interact_heavy_kernel)."""
+    return _round_order(pairs, lon32, lat32, grid, None)
+
+
+def _round_order(pairs, lon32, lat32, grid, tile):
+    tw, th = tile if tile is not None else (1 << 30, 1 << 30)
     pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
     cx, cy, rank, occ = cell_ranks(lon32, lat32, grid)
     i, j = pairs[:, 0], pairs[:, 1]
@@ -216,7 +230,10 @@ def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
     b = np.where(j_anchor, i, j)
     cxa, cya, cxb, cyb = cx[a], cy[a], cx[b], cy[b]
     d = cxb - cxa
-    inner = np.where(same, 0, np.where(cya == cyb, 1 + (cxa & 1), 5 + 2 * d + (cya & 1)))
+    if tile is not None:
+        inner = np.where(same, 0, np.where(cya == cyb, 1 + (cxa & 1), 5 + 2 * d + (cya & 1)))
+    else:
+        inner = np.where(same, 0, np.where(cya == cyb, 1 + (cxa & 1), 3 * (cya & 1) + 4 + d))
     cross_v = (cxa // tw) != (cxb // tw)
     cross_h = (cya // th) != (cyb // th)
     outer = np.where(cya == cyb, 9, np.where(cross_h, 13 + d, np.where(d < 0, 10, 11)))
@@ -242,9 +259,11 @@ def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
     return pairs[order], phase[order]
 
 
-def canonical_order(pairs, lon32, lat32, grid, mode=1):
-    """The device's canonical pair order: LM_OPT_INTERACT_MODE 1 (default, fused tile kernel) = tile-round order,
-    0 (round-1 pipeline) = cell-phase order."""
+def canonical_order(pairs, lon32, lat32, grid, mode=2):
+    """The device's canonical pair order: LM_OPT_INTERACT_MODE 2 (default, hybrid) = cell-round order, 1 (fused tile
+    kernel) = tile-round order, 0 (round-1 pipeline) = cell-phase order."""
+    if mode == 2:
+        return cell_round_order(pairs, lon32, lat32, grid)
     if mode == 1:
         return tile_round_order(pairs, lon32, lat32, grid)
     return cell_phase_order(pairs, lon32, lat32, grid)

@@ -14,7 +14,9 @@ What is pinned by what:
                          what the reference iterates over;
                  *_cell  the canonical cell-phase order of the round-1 device pipeline (LM_OPT_INTERACT_MODE = 0)
                          for a fixed grid;
-                 *_tile  the canonical tile-round order of the fused tile kernel (the default device path,
+                 *_round the canonical cell-round order of the hybrid device path (LM_OPT_INTERACT_MODE = 2, the default:
+                         oracle/rps.py::cell_round_order) for the same grid;
+                 *_tile  the canonical tile-round order of the fused tile kernel (LM_OPT_INTERACT_MODE = 1,
                          oracle/rps.py::tile_round_order) for the same grid.
   pairs_*.npz  pair sets from ``cKDTree(...).query_pairs(r, p=2)`` -- the library call the
                reference makes (interaction_simulator.py:93,98).
@@ -74,12 +76,17 @@ def rps_case(name, lon, lat, species0, r, params, seed, step, grid_k=1):
     u_cell = philox.pair_uniforms(cell_order[:, 0], cell_order[:, 1], step, seed)
     species_cell = run_reference_rps(species0, [tuple(map(int, p)) for p in cell_order], u_cell, params)
 
+    round_order, _ = orps.cell_round_order(opairs.pairs_from_set(pair_set), lon, lat, grid)
+    u_round = philox.pair_uniforms(round_order[:, 0], round_order[:, 1], step, seed)
+    species_round = run_reference_rps(species0, [tuple(map(int, p)) for p in round_order], u_round, params)
+
     tile_order, _ = orps.tile_round_order(opairs.pairs_from_set(pair_set), lon, lat, grid)
     u_tile = philox.pair_uniforms(tile_order[:, 0], tile_order[:, 1], step, seed)
     species_tile = run_reference_rps(species0, [tuple(map(int, p)) for p in tile_order], u_tile, params)
 
     np.savez_compressed(os.path.join(HERE, name + ".npz"), lon=lon, lat=lat, r=np.float64(r), species0=species0,
                         pairs_tile_order=tile_order.astype(np.int32), species_tile=species_tile,
+                        pairs_round_order=round_order.astype(np.int32), species_round=species_round,
                         pRS=params["pRS"], pPR=params["pPR"], pSP=params["pSP"], seed=np.int64(seed),
                         step=np.int64(step), pairs_ref_order=ref_order.astype(np.int32), u_ref=u_ref,
                         species_ref=species_ref, grid=np.array([grid["x0"], grid["y0"], grid["inv_h"]]),

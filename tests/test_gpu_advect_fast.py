@@ -94,7 +94,7 @@ def test_fast_rk4_config1_24_steps_accumulated():
 def test_option_validation(engine_factory):
     from lagrangian_microbes_b200._lib import LM_EINVAL, LM_OPT_ADVECT_MODE, LM_OPT_DRAW_BATCH, LM_OPT_INTERACT_MODE, LmError
     eng = engine_factory(max_particles=64, max_cells=1024)
-    for opt, bad in ((LM_OPT_ADVECT_MODE, 2), (LM_OPT_INTERACT_MODE, 2), (LM_OPT_DRAW_BATCH, 33), (LM_OPT_ADVECT_MODE, -1)):
+    for opt, bad in ((LM_OPT_ADVECT_MODE, 2), (LM_OPT_INTERACT_MODE, 3), (LM_OPT_DRAW_BATCH, 33), (LM_OPT_ADVECT_MODE, -1)):
         with pytest.raises(LmError) as ei:
             eng.set_option(opt, bad)
         assert ei.value.code == LM_EINVAL

@@ -20,6 +20,7 @@ def _dataset_with_land(year, land_box=(30.0, 32.0, 206.0, 209.0)):
     """OSCAR-grid synthetic year with a NaN (land) block, as the product stores land."""
     from lagrangian_microbes_b200 import velocity_fields as vf
     vf.configure_synthetic(kind="random_fourier", seed=5, n_modes=8, rms_speed=0.3)
+    vf.register_dataset_provider(None)                                   # the plain synthetic year underneath
     ds = vf.oscar_dataset(year)
     lat, lon = ds["latitude"].values, ds["longitude"].values
     u, v = ds["u"].values.copy(), ds["v"].values.copy()
@@ -34,8 +35,8 @@ def test_land_is_still_water_and_leaving_the_grid_raises(tmp_path):
     import lagrangian_microbes_b200 as lm
     from lagrangian_microbes_b200 import velocity_fields as vf
     from lagrangian_microbes_b200.particle_advecter import HostFieldSet, OutOfBoundsError
-    cache = {}
-    vf.register_dataset_provider(lambda year: cache.setdefault(year, _dataset_with_land(year)))
+    cache = {2017: _dataset_with_land(2017)}
+    vf.register_dataset_provider(lambda year: cache[year])
     try:
         fs = HostFieldSet(vf.oscar_dataset(2017))
         assert (fs.u == 0).any() and not np.isnan(fs.u).any()

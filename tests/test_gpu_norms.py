@@ -36,7 +36,7 @@ def gpu_pairs(eng, lon, lat, r, cap):
 
 
 # (LM_OPT_INTERACT_MODE, LM_OPT_FIND_PATH): fused tile kernel | round-1 pair search, auto / every warp on the two-pass path
-@pytest.mark.parametrize("imode,mode", [(1, 0), (0, 0), (0, 1)])
+@pytest.mark.parametrize("imode,mode", [(2, 0), (2, 1), (1, 0), (0, 0)])
 @pytest.mark.parametrize("tag,p", NORMS)
 @pytest.mark.parametrize("name", NORM_CASES)
 def test_find_pairs_other_norms_golden(engine_factory, name, tag, p, imode, mode):

@@ -237,20 +237,22 @@ def test_resolve_rps_lexicographic_and_reversed_orders(engine_factory, name):
         assert np.array_equal(species.cpu().numpy(), want)
 
 
-# (LM_OPT_INTERACT_MODE, LM_OPT_FIND_PATH): the fused tile kernel (default) | the round-1 pipeline, auto | the
-# round-1 pipeline with every warp of its pair search on the two-pass (dense cluster) path
-RESOLVE_MODES = [(1, 0), (0, 0), (0, 1)]
+# (LM_OPT_INTERACT_MODE, LM_OPT_FIND_PATH): the hybrid path (default: round-1 pipeline for the light units + rounds of
+# matchings for the queued heavy units), auto / every warp of its pair search on the two-pass (dense cluster) path | the
+# fused tile kernel | the round-1 pipeline alone, auto / two-pass
+RESOLVE_MODES = [(2, 0), (2, 1), (1, 0), (0, 0), (0, 1)]
+GOLDEN_SPECIES = {2: "species_round", 1: "species_tile", 0: "species_cell"}
 
 
 @pytest.mark.parametrize("imode,mode", RESOLVE_MODES)
 @pytest.mark.parametrize("name", RPS_CASES)
 def test_interact_rps_canonical_order_golden(engine_factory, name, imode, mode):
     """Fused pair search + RPS on the grid the golden was made for; golden species come from the
-    unmodified reference function run in the device's canonical order (tile-round order for the fused tile
-    kernel, cell-phase order for the round-1 pipeline)."""
+    unmodified reference function run in the device's canonical order (cell-round order for the hybrid path, tile-round
+    order for the fused tile kernel, cell-phase order for the round-1 pipeline)."""
     from lagrangian_microbes_b200._lib import LM_OPT_FIND_PATH, LM_OPT_INTERACT_MODE
     g = golden(name + ".npz")
-    g = dict(g, species_cell=g["species_tile"] if imode == 1 else g["species_cell"])
+    g = dict(g, species_cell=g[GOLDEN_SPECIES[imode]])
     n = g["lon"].size
     eng = engine_factory(max_particles=n, max_cells=1 << 22, max_pairs=g["pairs_ref_order"].shape[0] + 64)
     eng.set_option(LM_OPT_INTERACT_MODE, imode)

@@ -268,8 +268,8 @@ def _small_field():
     return ork4.FieldSet(g["grid_lon"], g["grid_lat"], g["grid_time"], g["u"], g["v"])
 
 
-@pytest.mark.parametrize("interact_mode,resolve_mode,stats_every_step", [(1, 0, True), (1, 0, False), (0, 0, True), (0, 1, True),
-                                                                         (0, 1, False)])
+@pytest.mark.parametrize("interact_mode,resolve_mode,stats_every_step", [(2, 0, True), (2, 0, False), (1, 0, True), (1, 0, False),
+                                                                         (0, 0, True), (0, 1, True), (0, 1, False)])
 def test_fused_steps_through_the_c_abi(abi, interact_mode, resolve_mode, stats_every_step):
     """Four lm_step calls (RK4 advection, binning, pair search, RPS, stats) on 1,200 microbes, step by step against the
     oracle: positions vs the RK4 restatement from identical inputs, pairs vs cKDTree on the library's positions,
@@ -329,7 +329,9 @@ def test_fused_steps_through_the_c_abi(abi, interact_mode, resolve_mode, stats_e
             total += stats.n_pairs
         assert total > 1500 and int((sp_ref != sp0).sum()) > 100
         per_step = (L.lm_launch_count(h) - launches0) / float(n_steps)
-        if interact_mode == 1:
+        if interact_mode == 2:
+            assert 25 <= per_step <= 28           # advection, binning (6), pair search, nine phase launches + nine heavy-unit launches
+        elif interact_mode == 1:
             assert per_step <= 17                 # advection, binning (6), one tile launch + at most six boundary launches
         else:
             assert per_step < 12 if resolve_mode == 1 else per_step >= 16      # one resolver launch instead of nine
@@ -337,7 +339,7 @@ def test_fused_steps_through_the_c_abi(abi, interact_mode, resolve_mode, stats_e
         assert L.lm_destroy(h) == 0
 
 
-@pytest.mark.parametrize("n_strips,interact_mode,resolve_mode", [(2, 1, 0), (3, 1, 0), (2, 0, 1), (3, 0, 0)])
+@pytest.mark.parametrize("n_strips,interact_mode,resolve_mode", [(2, 2, 0), (3, 2, 0), (2, 1, 0), (3, 1, 0), (2, 0, 1), (3, 0, 0)])
 def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve_mode):
     """The whole strip protocol executed: G handles, particles handed out in contiguous tiles, routing
     passes until every microbe sits in its strip, then fused steps in the five stages of include/lm_b200.h with the
@@ -472,7 +474,8 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve
 # ----------------------------------------------------------------------------------------------------------------------
 # The committed golden vectors (tests/golden/, made with the unmodified reference function and with SciPy) through the
 # emulated C ABI: the CPU suite pins the kernels' logic to the reference's own outputs, not only the GPU suite.
-@pytest.mark.parametrize("name,interact_mode,resolve_mode", [("rps_oddspecies", 1, 0), ("rps_clustered", 1, 0), ("rps_uniform", 1, 0),
+@pytest.mark.parametrize("name,interact_mode,resolve_mode", [("rps_oddspecies", 2, 0), ("rps_clustered", 2, 0), ("rps_uniform", 2, 0),
+                                                              ("rps_oddspecies", 1, 0), ("rps_clustered", 1, 0), ("rps_uniform", 1, 0),
                                                               ("rps_oddspecies", 0, 0), ("rps_oddspecies", 0, 1),
                                                               ("rps_clustered", 0, 1)])
 def test_golden_species_through_the_c_abi(abi, name, interact_mode, resolve_mode):
@@ -499,7 +502,7 @@ def test_golden_species_through_the_c_abi(abi, name, interact_mode, resolve_mode
         stats = _lib.Stats()
         assert L.lm_sync_stats(h, ctypes.byref(stats), None) == 0
         assert stats.n_pairs == n_pairs == found[0]
-        assert np.array_equal(species, g["species_tile" if interact_mode == 1 else "species_cell"])
+        assert np.array_equal(species, g[{2: "species_round", 1: "species_tile", 0: "species_cell"}[interact_mode]])
         if resolve_mode == 0:
             # explicit-order resolver (M-ref): the reference's own set-iteration order and draws
             species = g["species0"].copy()
