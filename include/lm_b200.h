@@ -294,6 +294,11 @@ int lm_reset_stats(lm_handle h, void *stream);
  *                     same results, for tests and A/B measurements */
 #define LM_OPT_TILE_REC_CAP 16
 #define LM_OPT_TILE_PATH 17
+/*   LM_OPT_HEAVY_MIN   hybrid mode: candidate pairs (m_a * m_b; one cell: m (m - 1) / 2) above which a unit is HEAVY, i.e.
+ *                     left out of the pair search's hand-off and resolved in rounds of matchings.  0 = default, 1,024 -- the
+ *                     value is part of the definition of the cell-round order (oracle/rps.py::cell_round_order takes
+ *                     it as a parameter); other values are for A/B measurements. */
+#define LM_OPT_HEAVY_MIN 18
 /* tile of the fused interaction pass, in cells: part of the definition of its canonical pair order.  Strip boundaries
  * (lm_set_strip) must sit on multiples of LM_TILE_H rows in this mode. */
 #define LM_TILE_W 32

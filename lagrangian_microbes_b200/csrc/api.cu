@@ -938,6 +938,10 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
             if (value < 0 || value > 16384) return LM_EINVAL;
             h->tile_rec_cap = (int)value;
             return LM_OK;
+        case LM_OPT_HEAVY_MIN:
+            if (value < 0 || value > (1ll << 40)) return LM_EINVAL;
+            h->heavy_min = value;
+            return LM_OK;
         case LM_OPT_TILE_PATH:
             if (value < 0 || value > 1) return LM_EINVAL;
             h->tile_path = (int)value;

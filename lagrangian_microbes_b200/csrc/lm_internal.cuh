@@ -107,6 +107,8 @@ struct lm_handle_s {
     int2 *heavy_list;      // [9 phases][2: warp units | CTA units][heavy_cap] (anchor cell, other cell) queued by the pair search
     unsigned int *heavy_cnt;   // [9][4] queued warp units | queued CTA units | warp ticket | CTA ticket
     int64_t heavy_cap;
+    int64_t heavy_min;     // LM_OPT_HEAVY_MIN: candidate pairs above which a unit is heavy in the hybrid mode (0 = default, 1024: part of the
+                           // definition of the cell-round order; other values are for A/B measurements)
     int draw_batch;        // LM_OPT_DRAW_BATCH: parked lanes that trigger a warp's Philox rounds (0 = default, 20)
     int tile_cap;          // LM_OPT_TILE_CAP: microbes a tile stages in shared memory (0 = from the mean occupancy)
     int tile_rec_cap;      // LM_OPT_TILE_REC_CAP: records (hits of one direction) a tile holds in shared memory (0 = 2 x tile_cap)

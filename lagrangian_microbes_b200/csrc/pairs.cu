@@ -87,6 +87,7 @@ struct FindArgs {
     int2 *heavy_list;                    // [9][2][heavy_cap]
     unsigned int *heavy_cnt;             // [9][4]
     unsigned int heavy_cap;
+    unsigned long long heavy_min;        // a unit is heavy when its candidate pairs (m_a * m_b; one cell: m (m - 1) / 2) exceed this
 };
 
 __device__ __forceinline__ int cell_coord2(float v, double origin, double inv_h, int n)
@@ -190,17 +191,17 @@ __global__ void __launch_bounds__(FIND_THREADS, 5) find_pairs_kernel(FindArgs A)
         }
     }
 
-    // ---- hybrid mode: which of my five units are heavy?  (two cells: m_a * m_b > 256 or m_b > 64; one cell: m > 23.)  Their
+    // ---- hybrid mode: which of my five units are heavy?  (two cells: m_a * m_b > 1,024; one cell: m (m - 1) / 2 > 1,024.)  Their
     // hits are dropped below; the first microbe of the cell queues them for the rounds-of-matchings kernel.
     unsigned int heavy_dirs = 0;
     if (A.hybrid && valid) {
         const unsigned int ma = (unsigned int)(sE - base0);
         const unsigned int mb[5] = {ma, (unsigned int)(endE - sE), (unsigned int)(sN - begNW), (unsigned int)(sNE - sN),
                                     (unsigned int)(endNE - sNE)};
-        if (ma >= 24u) heavy_dirs |= 1u;
+        if ((unsigned long long)ma * (ma - 1u) / 2ull > A.heavy_min) heavy_dirs |= 1u;
 #pragma unroll
         for (int d = 1; d < 5; ++d)
-            if (mb[d] >= 1u && ((unsigned long long)ma * mb[d] > 256ull || mb[d] > 64u)) heavy_dirs |= 1u << d;
+            if ((unsigned long long)ma * mb[d] > A.heavy_min) heavy_dirs |= 1u << d;
         if (heavy_dirs && a == base0) {
             const int ncx = A.g.ncx, cx = c % ncx, cy = c / ncx;
 #pragma unroll
@@ -907,6 +908,10 @@ cudaError_t launch_find(lm_handle_s *h, const float *lon, const float *lat, cons
     F.ctr = h->ctr;
     F.hybrid = h->interact_mode == 2 ? 1 : 0;
     F.heavy_list = h->heavy_list; F.heavy_cnt = h->heavy_cnt; F.heavy_cap = (unsigned int)h->heavy_cap;
+    // measured on B200 (profiles/r2g_heavy_sweep.jsonl): 1,024 -- up to 32 x 32 microbes -- is the best compromise: BASELINE config 3
+    // stirred (12 microbes per cell) 10.9 -> 7.4 ms per step against the round-1 pipeline alone; 256 floods the queue with
+    // medium units that leave half a warp idle (9.9 ms), 16,384 and up leave the long lane walks in (8.1 - 10.5 ms)
+    F.heavy_min = h->heavy_min > 0 ? (unsigned long long)h->heavy_min : 1024ull;
     const bool emit = F.cap_pairs > 0;
     const int grid = (n + FIND_THREADS - 1) / FIND_THREADS;
     ++h->launches;

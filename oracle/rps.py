@@ -174,10 +174,14 @@ def cell_ranks(lon32, lat32, grid):
     return cx, cy, rank, occ.astype(np.int64)
 
 
-def unit_is_light(same, ma, mb):
-    """csrc/interact.cu::unit_is_light -- part of the definition of the order: a unit of two cells is LIGHT when
-    m_a * m_b <= 256 and m_b <= 64, a unit of one cell when m <= 23; otherwise it is HEAVY."""
-    return np.where(same, ma <= 23, (ma * mb <= 256) & (mb <= 64))
+def unit_is_light(same, ma, mb, tile=True, heavy_min=1024):
+    """Part of the definition of the orders.  Fused tile kernel (csrc/interact.cu::unit_is_light): a unit of two cells is
+    LIGHT when m_a * m_b <= 256 and m_b <= 64, a unit of one cell when m <= 23; otherwise it is HEAVY.  Hybrid path
+    (csrc/pairs.cu, ``heavy_dirs``): LIGHT when its candidate pairs -- m_a * m_b, one cell: m (m - 1) / 2 -- do not exceed
+    ``heavy_min`` = 1,024 (LM_OPT_HEAVY_MIN)."""
+    if tile:
+        return np.where(same, ma <= 23, (ma * mb <= 256) & (mb <= 64))
+    return np.where(same, ma * (ma - 1) // 2 <= heavy_min, ma * mb <= heavy_min)
 
 
 def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
@@ -207,17 +211,17 @@ def tile_round_order(pairs, lon32, lat32, grid, tile=(TILE_W, TILE_H)):
     return _round_order(pairs, lon32, lat32, grid, tile)
 
 
-def cell_round_order(pairs, lon32, lat32, grid):
+def cell_round_order(pairs, lon32, lat32, grid, heavy_min=1024):
     """The canonical order of the HYBRID device path (LM_OPT_INTERACT_MODE = 2, the default): the nine phases of
     ``cell_phase_order`` (0 same cell | 1 + (cx & 1) east | 3 (cy & 1) + 3, + 4, + 5 north-west, north, north-east), units
-    by anchor cell, and inside a unit the rule of ``tile_round_order``: LIGHT units (``unit_is_light``) in (rank in the
+    by anchor cell, and inside a unit the rule of ``tile_round_order``: LIGHT units (``unit_is_light`` with tile=False) in (rank in the
     anchor cell, rank in the other cell) lexicographic order -- which is ``cell_phase_order``'s (id_a, id_b) -- and HEAVY
     units in rounds of matchings.  The round-1 pipeline resolves the light units, a device-wide queue of heavy units is
     resolved round by round by whole warps / CTAs (csrc/interact.cu::interact_heavy_kernel)."""
-    return _round_order(pairs, lon32, lat32, grid, None)
+    return _round_order(pairs, lon32, lat32, grid, None, heavy_min)
 
 
-def _round_order(pairs, lon32, lat32, grid, tile):
+def _round_order(pairs, lon32, lat32, grid, tile, heavy_min=1024):
     tw, th = tile if tile is not None else (1 << 30, 1 << 30)
     pairs = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
     cx, cy, rank, occ = cell_ranks(lon32, lat32, grid)
@@ -240,7 +244,7 @@ def _round_order(pairs, lon32, lat32, grid, tile):
     phase = np.where(cross_v | cross_h, outer, inner)
     unit = cya * np.int64(grid["ncx"]) + cxa
     ra, rb, ma, mb = rank[a], rank[b], occ[a], occ[b]
-    light = unit_is_light(same, ma, mb)
+    light = unit_is_light(same, ma, mb, tile is not None, heavy_min)
     # heavy units: rounds and slots
     big = np.maximum(ma, mb)
     rnd_x = np.mod(rb - ra, big)

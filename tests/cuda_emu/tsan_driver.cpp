@@ -77,6 +77,7 @@ int main(int argc, char **argv)
             lm_handle hd = nullptr;
             CHECK(lm_create(&hd, 0, n, 1 << 14, 60 * n));
             CHECK(lm_set_grid(hd, &grid));
+            CHECK(lm_set_option(hd, LM_OPT_INTERACT_MODE, 1));
             CHECK(lm_set_option(hd, LM_OPT_TILE_CAP, o[0]));
             CHECK(lm_set_option(hd, LM_OPT_DRAW_BATCH, o[1]));
             std::vector<int8_t> sp(sp0);
@@ -87,6 +88,25 @@ int main(int argc, char **argv)
             printf("fused tile kernel, tile cap %lld, draw batch %lld: %lld pairs\n", o[0], o[1], (long long)st.n_pairs);
             if (ref1.empty()) ref1 = sp;
             else if (memcmp(ref1.data(), sp.data(), n) != 0) { fprintf(stderr, "fused tile kernel: settings disagree\n"); return 2; }
+            CHECK(lm_destroy(hd));
+        }
+    }
+
+    // the hybrid path (LM_OPT_INTERACT_MODE = 2, the default): round-1 pipeline for the light units, heavy units queued per phase
+    // and resolved in rounds of matchings from shared memory by whole warps / the whole CTA; a low LM_OPT_HEAVY_MIN queues many
+    {
+        for (long long hmin : {0ll, 40ll}) {
+            if (quick && hmin) continue;
+            lm_handle hd = nullptr;
+            CHECK(lm_create(&hd, 0, n, 1 << 14, 60 * n));
+            CHECK(lm_set_grid(hd, &grid));
+            CHECK(lm_set_option(hd, LM_OPT_HEAVY_MIN, hmin));
+            std::vector<int8_t> sp(sp0);
+            std::vector<int32_t> pairs(2 * 60 * n);
+            CHECK(lm_interact_rps(hd, lon.data(), lat.data(), sp.data(), n, r, &prm, pairs.data(), 60 * n, nullptr, nullptr));
+            lm_stats st;
+            CHECK(lm_sync_stats(hd, &st, nullptr));
+            printf("hybrid path, heavy_min %lld: %lld pairs\n", hmin, (long long)st.n_pairs);
             CHECK(lm_destroy(hd));
         }
     }
@@ -124,14 +144,14 @@ int main(int argc, char **argv)
         Uf[(t * Y + y) * X + x] = 0.2f * (float)(y - Y / 2) / Y + 0.02f * t;
         Vf[(t * Y + y) * X + x] = -0.2f * (float)(x - X / 2) / X;
     }
-    for (int mode = 0; mode < 3; ++mode) {                                 // 0, 1: round-1 pipeline, nine phases / tiled; 2: fused tile kernel
+    for (int mode = 0; mode < 4; ++mode) {                                 // 0, 1: round-1 pipeline, nine phases / tiled; 2: fused tile kernel; 3: hybrid
         lm_handle hd = nullptr;
         CHECK(lm_create(&hd, 0, n, 1 << 14, 60 * n));
         CHECK(lm_set_field(hd, Uf.data(), Vf.data(), glon.data(), glat.data(), T, Y, X));
         lm_grid g2 = {200.9, 31.9, 1.0 / h, ncx + 20, ncy + 20};
         CHECK(lm_set_grid(hd, &g2));
-        CHECK(lm_set_option(hd, LM_OPT_INTERACT_MODE, mode == 2));
-        CHECK(lm_set_option(hd, LM_OPT_ADVECT_MODE, mode == 2));
+        CHECK(lm_set_option(hd, LM_OPT_INTERACT_MODE, mode == 2 ? 1 : (mode == 3 ? 2 : 0)));
+        CHECK(lm_set_option(hd, LM_OPT_ADVECT_MODE, mode >= 2));
         if (mode < 2) CHECK(lm_set_option(hd, LM_OPT_RESOLVE_MODE, mode));
         CHECK(lm_state_set(hd, lon.data(), lat.data(), sp0.data(), nullptr, n, nullptr));
         std::vector<int32_t> pairs(2 * 60 * n);

@@ -123,6 +123,21 @@ def make_rps():
     sp = rng.integers(0, 5, n).astype(np.int8)
     rps_case("rps_oddspecies", lon, lat, sp, 0.02, {"pRS": 0.3, "pPR": 0.7, "pSP": 0.5}, seed=3, step=0)
 
+    # knots: 50-90 microbes inside one or two cells on a sparse background -- HEAVY units of the hybrid path (more than 1,024
+    # candidate pairs: rounds of matchings) next to light ones
+    n = 800
+    lon = 207.0 + 0.4 * rng.random(n)
+    lat = 31.0 + 0.4 * rng.random(n)
+    k = 0
+    for m, (cxk, cyk, sig) in zip((90, 70, 50), ((207.105, 31.105, 0.0015), (207.2999, 31.2501, 0.003), (207.25, 31.1, 0.002))):
+        lon[k:k + m] = cxk + sig * rng.standard_normal(m)
+        lat[k:k + m] = cyk + sig * rng.standard_normal(m)
+        k += m
+    perm = rng.permutation(n)
+    np.random.seed(2)
+    _, params, props = ref_interactions.rock_paper_scissors(n, 0.55, 0.6, 0.5)
+    rps_case("rps_knots", lon[perm], lat[perm], props["species"], 0.01, params, seed=11, step=3)
+
 
 def make_pairs():
     rng = np.random.default_rng(2)

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 PAIR_CASES = ["exact345", "dups_collinear", "lattice", "uniform", "tiny_lat", "empty", "single"]
-RPS_CASES = ["rps_uniform", "rps_clustered", "rps_oddspecies"]
+RPS_CASES = ["rps_uniform", "rps_clustered", "rps_oddspecies", "rps_knots"]
 
 
 def dev(a):

@@ -475,6 +475,7 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve
 # The committed golden vectors (tests/golden/, made with the unmodified reference function and with SciPy) through the
 # emulated C ABI: the CPU suite pins the kernels' logic to the reference's own outputs, not only the GPU suite.
 @pytest.mark.parametrize("name,interact_mode,resolve_mode", [("rps_oddspecies", 2, 0), ("rps_clustered", 2, 0), ("rps_uniform", 2, 0),
+                                                              ("rps_knots", 2, 0), ("rps_knots", 1, 0), ("rps_knots", 0, 0),
                                                               ("rps_oddspecies", 1, 0), ("rps_clustered", 1, 0), ("rps_uniform", 1, 0),
                                                               ("rps_oddspecies", 0, 0), ("rps_oddspecies", 0, 1),
                                                               ("rps_clustered", 0, 1)])

@@ -7,7 +7,7 @@ from oracle import pairs as opairs
 from oracle import philox
 from oracle import rps as orps
 
-CASES = ["rps_uniform", "rps_clustered", "rps_oddspecies"]
+CASES = ["rps_uniform", "rps_clustered", "rps_oddspecies", "rps_knots"]
 
 
 def _grid(g):
@@ -89,6 +89,20 @@ def test_rule_table():
 
 # ---- the tile-round order of the fused tile kernel (LM_OPT_INTERACT_MODE = 1) ------------------------------------
 @pytest.mark.parametrize("name", CASES)
+def test_restatement_matches_reference_in_cell_round_order(name):
+    """species_round: the UNMODIFIED reference function fed the cell-round order of the hybrid device path."""
+    g = golden(name + ".npz")
+    lon, lat, grid = g["lon"], g["lat"], _grid(g)
+    order, _ = orps.cell_round_order(opairs.sort_pairs(g["pairs_ref_order"]), lon, lat, grid)
+    assert np.array_equal(order.astype(np.int32), g["pairs_round_order"])
+    sp, _ = orps.rps_sequential_c(g["species0"].copy(), order, philox.pair_uniforms(order[:, 0], order[:, 1], int(g["step"]), int(g["seed"])),
+                                  float(g["pRS"]), float(g["pPR"]), float(g["pSP"]))
+    assert np.array_equal(sp, g["species_round"])
+    if name == "rps_knots":
+        assert not np.array_equal(g["species_round"], g["species_cell"])       # the heavy units' rounds do change the outcome
+
+
+@pytest.mark.parametrize("name", CASES)
 def test_restatement_matches_reference_in_tile_round_order(name):
     """species_tile was produced by the UNMODIFIED reference function fed the tile-round order (make_golden.py)."""
     g = golden(name + ".npz")
@@ -150,8 +164,8 @@ def test_tile_round_order_is_reproducible_and_its_rounds_are_matchings(name):
         ma, mb = int((key == ca).sum()), int((key == cb).sum())
         bound = max(ma, mb) if ca != cb else ma - 1 + (ma & 1)
         assert nr <= bound, "unit %r needs %d rounds, bound %d" % ((ph, ca, cb), nr, bound)
-    if name == "rps_clustered":
-        assert n_heavy_pairs > 1000 and len(rounds) > 5          # the clustered case does exercise the heavy order
+    if name in ("rps_clustered", "rps_knots"):
+        assert n_heavy_pairs > 1000 and len(rounds) > 5          # these cases do exercise the heavy order
 
 
 def test_reference_cost_pair_function_equals_the_unmodified_reference_call_by_call():
