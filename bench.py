@@ -339,7 +339,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n_per_gpu = args.microbes or default_n(args.workload)
+    # shard: weak scaling (the per-GPU shard of config 4 on every GPU).  config3 is ONE configuration -- 10 M microbes in the
+    # dense patch -- on 1 or 2 GPUs (BASELINE.json: "1xB200 vs 2xB200 latitude-strip sharding"): strong scaling.
+    strong = args.workload == "config3" and world > 1
+    n_per_gpu = args.microbes or (default_n(args.workload) // world if strong else default_n(args.workload))
     config = {"workload": args.workload, "microbes_per_gpu": n_per_gpu, "microbes_total": n_per_gpu * world,
               "radius_deg": RADIUS, "p": P_RPS[0], "dt_s": DT, "field": "synthetic %s, OSCAR 1/3-degree grid "
               "(72x481x1201), %d modes" % ("steady eddy field" if args.workload == "config1" else "random-Fourier", args.modes), "l2": "inputs larger than L2" if n_per_gpu >= 5_000_000
@@ -424,7 +427,7 @@ def main():
             ids = (rank * n_per_gpu + np.arange(n_per_gpu)).astype(np.int32)
             self.ss = StripSet(DistTransport(), lon, lat, species, ids, n_per_gpu * world, RADIUS, *P_RPS, hfs,
                                dt_seconds=DT, seed=0, emit_pairs=True, pairs_per_particle=ppp, slack=1.4,
-                               grid_margin=0.5, stream_field=stream_field, regrid_every=16)
+                               grid_margin=0.5, stream_field=stream_field, regrid_every=16, rebalance_every=64)
             self.engine = self.ss.strips[0].engine
             self.regrid_every = 0
             self.k = 0
@@ -629,10 +632,30 @@ def main():
         prof = json.load(open(prof_path)).get(args.workload, {}).get("find_pairs_kernel")
         if prof and prof.get("microbes_per_gpu") == n_per_gpu:
             traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+    if args.interact_mode == 1:
+        # fused tile kernel: pair search + RPS in one launch: (10 + 8 rho) N algorithmic bytes (positions 8, species R 1 + W 1, pairs 8 rho)
+        kname, kbytes, kms = "interact_tile_kernel<RPS> (1 launch per step)", (10.0 + 8.0 * rho) * n_per_gpu, float(phase[2])
+        knote = ("shared-memory tiles: DRAM traffic ~1.02x the algorithmic bytes, but ~135 warp instructions per microbe at 16 of 32 "
+                 "lanes: issue-bound (profiles/)")
+        kprof = "interact_tile_kernel"
+    else:
+        kname, kbytes, kms = "find_pairs_kernel<RPS,EMIT> (1 launch per step)", pair_bytes, float(phase[2])
+        knote = ("issue-bound, not HBM-bound: ~2,000 warp instructions per 32 microbes (13 distance tests + 4.4 Philox2x32-10 draws "
+                 "per microbe + the hand-off layout), sm__throughput ~70 % of peak in ncu")
+        kprof = "find_pairs_kernel"
+    kgbs = kbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+    traffic = None
+    if os.path.exists(prof_path):
+        prof = json.load(open(prof_path)).get(args.workload, {}).get(kprof)
+        if prof and prof.get("microbes_per_gpu") == n_per_gpu:
+            traffic = prof["dram_bytes_read"] + prof["dram_bytes_write"]
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": kgbs, "peak": peak, "unit": "GB/s", "frac": kgbs / peak,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes, "launch_ms": kms, "note": knote}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 state / f64 arithmetic", "data": "synthetic", "config": config,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+        "dtype": ("f32 state; f32 RK4 arithmetic (positions within 1e-6 relative of the f64 RK4), f64-exact pair predicate"
+                  if args.advect_mode == 1 else "f32 state / f64 arithmetic"), "data": "synthetic", "config": config,
         "pairs_per_step": pairs_total, "pairs_per_s": pairs_total * args.steps / (ms * 1e-3), "rho": rho,
         "gpu_launches": launches_total,
         "parity": parity,
@@ -641,12 +664,7 @@ def main():
                       "rps_resolve": float(phase[3]), "stats": float(phase[4])},
         "step_roofline": {"b_alg_bytes_per_microbe_step": b_alg, "achieved_gbs_per_gpu": value * b_alg / 1e9 / world,
                           "frac": value * b_alg / 1e9 / world / peak},
-        "roofline": {"kernel": "find_pairs_kernel<RPS,EMIT> (1 launch per step)", "bound": "hbm",
-                     "achieved": pair_gbs, "peak": peak, "unit": "GB/s", "frac": pair_gbs / peak, "traffic": traffic,
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": pair_bytes,
-                     "launch_ms": float(phase[2]),
-                     "note": "issue-bound, not HBM-bound: ~2200 warp instructions per 32 microbes (13 distance tests + "
-                             "4.4 Philox4x32-10 draws per microbe), sm__throughput 69 % of peak in ncu"},
+        "roofline": roofline,
     }
     if e2e:
         line["e2e"] = {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],

@@ -81,6 +81,8 @@ int lm_destroy(lm_handle h)
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_find_done) cudaEventDestroy(h->ev_find_done);
     if (h->ev_resolve_done) cudaEventDestroy(h->ev_resolve_done);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_pos_ready) cudaEventDestroy(h->ev_pos_ready);
     if (h->ev_pos_scattered) cudaEventDestroy(h->ev_pos_scattered);
     if (h->ev_sp_ready) cudaEventDestroy(h->ev_sp_ready);
@@ -146,6 +148,8 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     if (ok) ok = cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_find_done, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_resolve_done, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_pos_ready, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_pos_scattered, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_sp_ready, cudaEventDisableTiming) == cudaSuccess;

@@ -92,6 +92,7 @@ struct lm_handle_s {
     // RPS phases of step k on a side stream, under the advection of step k+1 (single handle, no strips)
     cudaStream_t side_stream;
     cudaEvent_t ev_find_done, ev_resolve_done;
+    cudaEvent_t ev_fork, ev_join;   // hybrid mode: the heavy units of a phase run on side_stream beside the phase's light units
     bool resolve_pending;  // ev_resolve_done has not been waited for yet
     bool resolve_on_side;  // this step's phases go to the side stream
     int overlap;           // LM_OPT_OVERLAP (default 1)

@@ -1380,8 +1380,17 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
         R.rec = h->rec + (size_t)d_idx * h->max_cells;
         R.rec2 = h->rec2 + (size_t)d_idx * (h->max_particles / 32 + 2);
         if (rows <= 0 || R.units_per_row <= 0) continue;
+        // the heavy units of the phase run beside its light units (disjoint microbes) on the handle's side stream: fork here,
+        // join after the light launch -- the phase costs the longer of the two, and a lone knot does not hold up the SMs
+        const bool forked = hybrid && light && h->side_stream && h->side_stream != s;
         if (hybrid) {
-            cudaError_t eh = launch_interact_heavy(h, sp, ph, s);
+            cudaError_t eh = cudaSuccess;
+            if (forked) {
+                eh = cudaEventRecord(h->ev_fork, s);
+                if (eh == cudaSuccess) eh = cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0);
+                if (eh == cudaSuccess) eh = launch_interact_heavy(h, sp, ph, h->side_stream);
+                if (eh == cudaSuccess) eh = cudaEventRecord(h->ev_join, h->side_stream);
+            } else eh = launch_interact_heavy(h, sp, ph, s);
             if (eh != cudaSuccess) return eh;
         }
         if (!light) continue;
@@ -1402,6 +1411,10 @@ cudaError_t launch_resolve_phases(lm_handle_s *h, int8_t *sp, int first, int las
         ++h->launches;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
+        if (forked) {
+            e = cudaStreamWaitEvent(s, h->ev_join, 0);
+            if (e != cudaSuccess) return e;
+        }
     }
     return cudaSuccess;
 }

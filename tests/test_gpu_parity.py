@@ -220,7 +220,7 @@ def test_resolve_rps_in_the_references_own_pair_order(engine_factory, name):
     rounds = eng.resolve_rps(dev(g["pairs_ref_order"]), dev(g["u_ref"]), species, float(g["pRS"]), float(g["pPR"]),
                              float(g["pSP"]))
     assert np.array_equal(species.cpu().numpy(), g["species_ref"])
-    assert 1 <= rounds < 200
+    assert 1 <= rounds < (2000 if name == "rps_knots" else 200)      # at least the largest degree: a knot of 90 has chains of hundreds
 
 
 @pytest.mark.parametrize("name", RPS_CASES)
