@@ -19,6 +19,9 @@ Workloads (``config.workload``):
   config2  BASELINE config 2: 490,000 microbes (700x700 lattice, 25-35N 205-215E), time-varying field,
            spun up ``--spinup`` steps so that the timed steps see the stirred state.
   config3  BASELINE config 3: 10M microbes uniform in the 10x10-degree patch (rho = 15.7).
+  config5  BASELINE config 5, one point of the interaction-only sweep: ``--microbes`` (default 50 M) uniform-random at the
+           config-1 areal density (4,900 per square degree), ``--radius`` (default 0.01), NO advection -- pair search + RPS on
+           resident positions, the pair list emitted.  tools/sweep_interact.py runs the whole sweep (1-50 M, 0.5-5 km, p).
   config1  BASELINE config 1, the reference's own CPU-runnable case: 490,000 microbes on the 700x700 lattice, STEADY
            synthetic velocity, 24 hourly steps.  The lattice spacing exceeds r, so the configuration as specified has no
            pairs; ``--spinup`` (default 120) advection-only steps strain the lattice first so that the timed steps
@@ -67,6 +70,11 @@ def workload_particles(name, n, rank, world, seed=0):
         lon = 205.0 + 10.0 * rng.random(n)
         lat = 25.0 + 10.0 * rng.random(n)
         desc = dict(lon=[205.0, 215.0], lat=[25.0, 35.0])
+    elif name == "config5":
+        side = float(np.sqrt(n / 4900.0))
+        lon = 205.0 + side * rng.random(n)
+        lat = 10.0 + side * rng.random(n)
+        desc = dict(lon=[205.0, 205.0 + side], lat=[10.0, 10.0 + side])
     elif name in ("config2", "config1"):
         from lagrangian_microbes_b200.particle_advecter import uniform_particle_locations
         lon, lat = uniform_particle_locations(n, 25, 35, 205, 215)
@@ -78,7 +86,7 @@ def workload_particles(name, n, rank, world, seed=0):
 
 
 def default_n(name):
-    return {"shard": 12_500_000, "config3": 10_000_000, "config2": 490_000, "config1": 490_000}[name]
+    return {"shard": 12_500_000, "config3": 10_000_000, "config2": 490_000, "config1": 490_000, "config5": 50_000_000}[name]
 
 
 def make_fieldset(n_modes, kind="random_fourier"):
@@ -217,7 +225,7 @@ def run_cpu_reference(workload, n_sample, steps, warmup, n_modes, spinup=0):
 # ------------------------------------------------------------------------------------------------------
 # parity twin: correctness evidence printed WITH the throughput (outside the timed region)
 # ------------------------------------------------------------------------------------------------------
-def parity_twin(world, rank, hfs, steps=4, per_rank=40_000):
+def parity_twin(world, rank, hfs, steps=4, per_rank=40_000, transport="peer"):
     """A reduced-size twin of the workload (same areal density, same field, same code path as the timed run) stepped
     ``steps`` times.  N = 1: every step checked against the CPU oracle -- positions vs the float64 RK4 restatement
     (1e-6 relative), the emitted pair set vs cKDTree.query_pairs (exact), the species vs the reference rule run
@@ -272,11 +280,11 @@ def parity_twin(world, rank, hfs, steps=4, per_rank=40_000):
                     "checksum": digest(l0, a0, s0), "match": bool(pairs_ok and species_ok and rel < 1e-6)})
         single.engine.close()
         return out
-    from lagrangian_microbes_b200.strips import DistTransport, StripSet
+    from lagrangian_microbes_b200.strips import DistTransport, PeerTransport, StripSet
     import torch.distributed as dist
     mine = slice(rank * per_rank, (rank + 1) * per_rank)                  # the reference's contiguous tiles
     ids = np.arange(n, dtype=np.int32)
-    ss = StripSet(DistTransport(), lon[mine], lat[mine], sp[mine], ids[mine], n, RADIUS, *P_RPS, hfs, dt_seconds=DT, seed=7,
+    ss = StripSet(PeerTransport() if transport == "peer" else DistTransport(), lon[mine], lat[mine], sp[mine], ids[mine], n, RADIUS, *P_RPS, hfs, dt_seconds=DT, seed=7,
                   emit_pairs=False, slack=1.6, grid_margin=0.5, regrid_every=2)
     for _ in range(steps):
         ss.step()
@@ -306,7 +314,8 @@ def main():
     ap.add_argument("--steps", type=int, default=0, help="timed steps (default 200; config1: the configuration's 24)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="shard", choices=["shard", "config1", "config2", "config3"])
+    ap.add_argument("--workload", default="shard", choices=["shard", "config1", "config2", "config3", "config5"])
+    ap.add_argument("--radius", type=float, default=0.01, help="config5: interaction radius in degrees (0.005 - 0.05 = 0.5 - 5 km)")
     ap.add_argument("--microbes", type=int, default=0, help="microbes per GPU (0 = the workload's size)")
     ap.add_argument("--spinup", type=int, default=-1, help="untimed steps before warm-up (config2 default 1500; config1 default 120, advection only)")
     ap.add_argument("--modes", type=int, default=64, help="Fourier modes of the synthetic velocity field")
@@ -328,12 +337,20 @@ def main():
     ap.add_argument("--advect-mode", type=int, default=1, choices=[0, 1],
                     help="LM_OPT_ADVECT_MODE: 1 float32 RK4 within north_star's 1e-6 relative (default here), 0 bit-faithful "
                          "to the float32 restatement of Parcels' kernel (A/B)")
+    ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: strip exchange through peer memory (CUDA IPC, peer stores + flags; default) or NCCL send/recv (A/B)")
     ap.add_argument("--draw-batch", type=int, default=0, help="LM_OPT_DRAW_BATCH (tuning experiments)")
     ap.add_argument("--tile-cap", type=int, default=0, help="LM_OPT_TILE_CAP (tuning experiments)")
     args = ap.parse_args()
     assert args.warmup >= 3 or args.impl == "reference", "timing rules: at least 3 warm-up steps"
+    global RADIUS
+    interact_only = args.workload == "config5"
+    if interact_only:
+        RADIUS = args.radius
+        args.no_e2e = True              # no advection, no record: the device-timed interaction step is the figure
+        assert args.impl == "b200" and int(os.environ.get("WORLD_SIZE", "1")) == 1, "config5: one GPU, b200 arm"
     if args.steps <= 0:
-        args.steps = 24 if args.workload == "config1" else 200
+        args.steps = 24 if args.workload == "config1" else (20 if interact_only else 200)
     spinup = args.spinup if args.spinup >= 0 else {"config2": 1500, "config1": 120}.get(args.workload, 0)
 
     rank = int(os.environ.get("RANK", "0"))
@@ -344,8 +361,8 @@ def main():
     strong = args.workload == "config3" and world > 1
     n_per_gpu = args.microbes or (default_n(args.workload) // world if strong else default_n(args.workload))
     config = {"workload": args.workload, "microbes_per_gpu": n_per_gpu, "microbes_total": n_per_gpu * world,
-              "radius_deg": RADIUS, "p": P_RPS[0], "dt_s": DT, "field": "synthetic %s, OSCAR 1/3-degree grid "
-              "(72x481x1201), %d modes" % ("steady eddy field" if args.workload == "config1" else "random-Fourier", args.modes), "l2": "inputs larger than L2" if n_per_gpu >= 5_000_000
+              "radius_deg": RADIUS, "p": P_RPS[0], "dt_s": DT, "field": ("none (interaction only)" if args.workload == "config5" else "synthetic %s, OSCAR 1/3-degree grid "
+              "(72x481x1201), %d modes" % ("steady eddy field" if args.workload == "config1" else "random-Fourier", args.modes)), "l2": "inputs larger than L2" if n_per_gpu >= 5_000_000
               else "state fits L2 (config as specified)",
               "regrid": "bounding box read back every 16 steps (one small sync), cell grid re-fitted when the cloud nears its edge"}
 
@@ -410,7 +427,7 @@ def main():
         torch.cuda.synchronize()
 
     t_setup = time.time()
-    hfs = make_fieldset(args.modes, field_kind(args.workload))
+    hfs = None if interact_only else make_fieldset(args.modes, field_kind(args.workload))
     lon, lat, species, desc = workload_particles(args.workload, n_per_gpu, rank, world)
     config.update(desc)
     log("[rank %d] setup: field + particles in %.1f s" % (rank, time.time() - t_setup))
@@ -418,14 +435,17 @@ def main():
     # pair-list capacity per microbe: rho grows as the flow gathers the microbes (4.4 -> 6.9 after 1,000 steps of the
     # default workload, 15.7 -> 18.9 after 400 of config 3); an overflow is an error, not a silent truncation
     ppp = 14 if args.workload != "config3" else 36
+    if interact_only:
+        rho_est = 0.5 * np.pi * RADIUS * RADIUS * 4900.0
+        ppp = 1.3 * rho_est + 4.0 * np.sqrt(rho_est / n_per_gpu) + 0.05
 
     class Sharded:
         """N > 1: one latitude strip per rank (lagrangian_microbes_b200/strips.py), NCCL between neighbours."""
 
         def __init__(self, stream_field):
-            from lagrangian_microbes_b200.strips import DistTransport, StripSet
+            from lagrangian_microbes_b200.strips import DistTransport, PeerTransport, StripSet
             ids = (rank * n_per_gpu + np.arange(n_per_gpu)).astype(np.int32)
-            self.ss = StripSet(DistTransport(), lon, lat, species, ids, n_per_gpu * world, RADIUS, *P_RPS, hfs,
+            self.ss = StripSet(PeerTransport() if args.transport == "peer" else DistTransport(), lon, lat, species, ids, n_per_gpu * world, RADIUS, *P_RPS, hfs,
                                dt_seconds=DT, seed=0, emit_pairs=True, pairs_per_particle=ppp, slack=1.4,
                                grid_margin=0.5, stream_field=stream_field, regrid_every=16, rebalance_every=64)
             self.engine = self.ss.strips[0].engine
@@ -450,13 +470,14 @@ def main():
         if world > 1:
             return Sharded(stream_field)
         return FusedSimulation(lon, lat, species, RADIUS, *P_RPS, hfs, dt_seconds=DT, seed=0, emit_pairs=True,
-                               pair_capacity=int(max(1 << 20, ppp * n_per_gpu)),
-                               regrid_every=16, grid_margin=0.5, stream_field=stream_field)
+                               pair_capacity=int(max(1 << 20, ppp * n_per_gpu)), advect=not interact_only,
+                               regrid_every=0 if interact_only else 16, grid_margin=0.1 if interact_only else 0.5,
+                               stream_field=stream_field and not interact_only)
 
     parity = None
-    if not args.no_parity:
+    if not args.no_parity and not interact_only:
         t_par = time.time()
-        parity = parity_twin(world, rank, hfs)
+        parity = parity_twin(world, rank, hfs, transport=args.transport)
         log("[rank %d] parity twin: %s in %.1f s" % (rank, "MATCH" if parity["match"] else "MISMATCH", time.time() - t_par))
         torch.cuda.empty_cache()
 
@@ -515,8 +536,9 @@ def main():
     st = sim.stats()
     rho = st.n_pairs / float(n_per_gpu)
     if world > 1:
-        config["parallelism"] = "%d latitude strips (one per GPU), NCCL send/recv between neighbours: migration + " \
-                                "one-row halo + boundary species, strip edges %s" % (world, sim.ss.edges)
+        config["parallelism"] = "%d latitude strips (one per GPU), %s between neighbours: migration + one-row halo + boundary " \
+                                "species, strip edges %s" % (world, "peer-memory stores over NVLink (CUDA IPC) + flags" if args.transport == "peer"
+                                                             else "NCCL send/recv", sim.ss.edges)
 
     # per-phase device times (3 extra steps with events between the phases)
     phase = np.zeros(5)
@@ -617,8 +639,9 @@ def main():
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    field_bytes = 2 * 2 * hfs.u.shape[1] * hfs.u.shape[2] * 4              # two snapshots of U and V
-    b_alg = 26.0 + 8.0 * rho + field_bytes / float(n_per_gpu)             # bytes per microbe-step
+    field_bytes = 0 if interact_only else 2 * 2 * hfs.u.shape[1] * hfs.u.shape[2] * 4   # two snapshots of U and V
+    # bytes per microbe-step; interaction only: no advection R/W (16 B)
+    b_alg = (10.0 if interact_only else 26.0) + 8.0 * rho + field_bytes / float(n_per_gpu)
     # Dominant kernel: find_pairs_kernel<RPS,EMIT> -- ONE launch per step (radius search + Philox decision bits +
     # pair list + hand-off), timed live with CUDA events recorded around it on the launching stream
     # (LM_STEP_TIMING).  Algorithmic bytes of the pair search: read lon/lat 8 B per microbe, write
@@ -652,7 +675,7 @@ def main():
     roofline = {"kernel": kname, "bound": "hbm", "achieved": kgbs, "peak": peak, "unit": "GB/s", "frac": kgbs / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": kbytes, "launch_ms": kms, "note": knote}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if not interact_only else "microbe-steps/sec (interact only: BASELINE config 5)", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": ("f32 state; f32 RK4 arithmetic (positions within 1e-6 relative of the f64 RK4), f64-exact pair predicate"
                   if args.advect_mode == 1 else "f32 state / f64 arithmetic"), "data": "synthetic", "config": config,
@@ -671,7 +694,7 @@ def main():
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": ms_e2e / args.steps}
         if "record" in e2e:
             line["e2e"]["record"] = e2e["record"]
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not interact_only:
         res = run_cpu_reference(args.workload, args.cpu_sample, 2, 1, args.modes, spinup=spinup)
         line["cpu_baseline"] = {"value": res["value"], "unit": UNIT, "cores": res["threads"], "kind": "port",
                                 "sample": ("2 steps of the configuration itself, all %d microbes (%.0f pairs/step)"

@@ -103,6 +103,24 @@ typedef struct {
     int64_t species_bytes;
 } lm_strip_buffers;
 
+/* Peer-memory exchange (NVLink / NVSwitch peer stores instead of NCCL send/recv).  A strip exports the addresses of its
+ * five RECEIVE buffers and of its flag words -- as CUDA IPC handles for a neighbour in another process, or as plain device
+ * pointers for a neighbour in the same process -- and connects to its neighbours' exports.  Once connected, the kernels that
+ * pack the ghost row and the boundary species write STRAIGHT into the neighbour's receive buffer, the migrants are copied
+ * there by one kernel that moves the live records only, each message is followed by a flag store (sequence number) into the
+ * neighbour's flag words, and the stage that consumes a message first spins on its flag: stream-ordered on both sides, no
+ * collective library, no host involvement.  lm_step_push(kind) replaces the caller's transfer of `kind` (LM_XCHG_*). */
+#define LM_IPC_HANDLE_BYTES 64
+#define LM_PEER_BUFFERS 6 /* mig_recv[0], mig_recv[1], ghost_recv, gsp_recv, gret_recv, flags */
+typedef struct {
+    unsigned char ipc[LM_PEER_BUFFERS][LM_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle_t of each buffer */
+    void *ptr[LM_PEER_BUFFERS];                                /* the same buffers as device pointers (same process only) */
+} lm_peer_export;
+#define LM_XCHG_MIG 0
+#define LM_XCHG_GHOST 1
+#define LM_XCHG_GSP 2
+#define LM_XCHG_GRET 3
+
 int lm_version(void);
 const char *lm_error_string(int code);
 const char *lm_last_cuda_error(void);
@@ -191,6 +209,13 @@ int lm_step(lm_handle h, int32_t flags, const lm_stage_times *st /* host */, flo
 int lm_strip_alloc(lm_handle h, int64_t send_cap, int64_t ghost_cap, int32_t row_cap);
 int lm_set_strip(lm_handle h, const lm_strip *strip /* host */);   /* after lm_set_grid (which resets it) */
 int lm_strip_buffers_get(lm_handle h, lm_strip_buffers *out /* host */);
+/* peer-memory exchange: see lm_peer_export.  side: 0 = the southern neighbour, 1 = the northern one; use_ipc: open the IPC
+ * handles (neighbour in another process) or take the pointers (same process).  Connect resets the sequence numbers: every
+ * strip of the set connects before the first step.  lm_step_push: after the stage that produced `kind` (MIG: lm_step_move;
+ * GHOST: lm_step_bin; GSP: lm_step_interact_begin; GRET: lm_step_interact_end). */
+int lm_strip_peer_export(lm_handle h, lm_peer_export *out /* host */);
+int lm_strip_peer_connect(lm_handle h, int32_t side, const lm_peer_export *peer /* host */, int32_t use_ipc);
+int lm_step_push(lm_handle h, int32_t kind, void *stream);
 int lm_step_move(lm_handle h, int32_t flags, const lm_stage_times *st /* host */, float dt, double diffuse_amp_deg,
                  const lm_rps_params *prm /* host */, void *stream);
 int lm_step_bin(lm_handle h, void *stream);

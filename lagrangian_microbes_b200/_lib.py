@@ -69,6 +69,15 @@ class Strip(ctypes.Structure):
                 ("has_north", ctypes.c_int32)]
 
 
+LM_IPC_HANDLE_BYTES, LM_PEER_BUFFERS = 64, 6
+LM_XCHG_MIG, LM_XCHG_GHOST, LM_XCHG_GSP, LM_XCHG_GRET = 0, 1, 2, 3
+
+
+class PeerExport(ctypes.Structure):
+    """lm_peer_export: IPC handles (another process) and plain device pointers (same process) of a strip's receive buffers + flags."""
+    _fields_ = [("ipc", (ctypes.c_ubyte * LM_IPC_HANDLE_BYTES) * LM_PEER_BUFFERS), ("ptr", ctypes.c_void_p * LM_PEER_BUFFERS)]
+
+
 class StripBuffers(ctypes.Structure):
     _fields_ = [("mig_send", ctypes.c_void_p * 2), ("mig_recv", ctypes.c_void_p * 2), ("mig_bytes", ctypes.c_int64),
                 ("ghost_send", ctypes.c_void_p), ("ghost_recv", ctypes.c_void_p), ("ghost_bytes", ctypes.c_int64),
@@ -143,6 +152,9 @@ def declare(L):
         "lm_strip_alloc": (ctypes.c_int, [vp, i64, i64, i32]),
         "lm_set_strip": (ctypes.c_int, [vp, P(Strip)]),
         "lm_strip_buffers_get": (ctypes.c_int, [vp, P(StripBuffers)]),
+        "lm_strip_peer_export": (ctypes.c_int, [vp, P(PeerExport)]),
+        "lm_strip_peer_connect": (ctypes.c_int, [vp, i32, P(PeerExport), i32]),
+        "lm_step_push": (ctypes.c_int, [vp, i32, vp]),
         "lm_step_move": (ctypes.c_int, [vp, i32, P(StageTimes), flt, dbl, P(RpsParams), vp]),
         "lm_step_bin": (ctypes.c_int, [vp, vp]),
         "lm_step_interact_begin": (ctypes.c_int, [vp, dbl, vp, i64, vp]),
@@ -176,7 +188,8 @@ EXPORTS = ["lm_version", "lm_error_string", "lm_last_cuda_error", "lm_create", "
            "lm_update_field_data", "lm_set_grid", "lm_get_grid", "lm_advect_rk4", "lm_diffuse", "lm_find_pairs", "lm_interact_rps",
            "lm_pair_uniforms", "lm_resolve_rps", "lm_state_set", "lm_state_size", "lm_step", "lm_state_get",
            "lm_state_get_host", "lm_host_copies_sync", "lm_state_view", "lm_sync_stats", "lm_reset_stats", "lm_launch_count",
-           "lm_phase_times", "lm_strip_alloc", "lm_set_strip", "lm_strip_buffers_get", "lm_step_move", "lm_step_bin",
+           "lm_phase_times", "lm_strip_alloc", "lm_set_strip", "lm_strip_buffers_get", "lm_strip_peer_export", "lm_strip_peer_connect", "lm_step_push",
+           "lm_step_move", "lm_step_bin",
            "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option", "lm_join", "lm_record_next_step",
            "lm_pair_distance_hist", "lm_rasterize", "lm_compose_frame", "lm_record_delta_pack",
            "lm_record_delta_unpack_host"]

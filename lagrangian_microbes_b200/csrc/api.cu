@@ -93,6 +93,10 @@ int lm_destroy(lm_handle h)
     cudaFree(h->ghost_send); cudaFree(h->ghost_recv);
     cudaFree(h->gsp_send); cudaFree(h->gsp_recv); cudaFree(h->gret_send); cudaFree(h->gret_recv);
     if (h->xfer_counts_host) cudaFreeHost(h->xfer_counts_host);
+    for (int sd = 0; sd < 2; ++sd)
+        if (h->peer[sd].connected && h->peer[sd].ipc)
+            for (int k = 0; k < LM_PEER_BUFFERS; ++k) if (h->peer[sd].base[k]) cudaIpcCloseMemHandle(h->peer[sd].base[k]);
+    cudaFree(h->xflags);
     for (int k = 0; k < 6; ++k)
         if (h->ev_phase[k]) cudaEventDestroy(h->ev_phase[k]);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -239,6 +243,8 @@ int lm_strip_alloc(lm_handle h, int64_t send_cap, int64_t ghost_cap, int32_t row
     ok = ok && dev_alloc(&h->gsp_send, ghost_cap) && dev_alloc(&h->gsp_recv, ghost_cap);
     ok = ok && dev_alloc(&h->gret_send, ghost_cap) && dev_alloc(&h->gret_recv, ghost_cap);
     ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&h->xfer_counts_host), 4 * sizeof(int32_t), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && dev_alloc(&h->xflags, 8);
+    if (ok) ok = cudaMemset(h->xflags, 0, 8 * sizeof(unsigned int)) == cudaSuccess;
     for (int k = 0; ok && k < 2; ++k) {
         ok = ok && cudaMemset(h->mig_send[k], 0, (size_t)(send_cap + 1) * sizeof(int4)) == cudaSuccess;
         ok = ok && cudaMemset(h->mig_recv[k], 0, (size_t)(send_cap + 1) * sizeof(int4)) == cudaSuccess;
@@ -278,6 +284,82 @@ int lm_set_strip(lm_handle h, const lm_strip *st)
     h->has_north = st->has_north != 0;
     h->binned = false;
     h->stage = 0;
+    return LM_OK;
+}
+
+// ---- peer-memory exchange (include/lm_b200.h: lm_peer_export) ----------------------------------------------------------
+int lm_strip_peer_export(lm_handle h, lm_peer_export *out)
+{
+    if (!h || !out) return LM_EINVAL;
+    if (!h->send_cap) return LM_ESTATE;
+    LM_CUDA(cudaSetDevice(h->device));
+    void *buf[LM_PEER_BUFFERS] = {h->mig_recv[0], h->mig_recv[1], h->ghost_recv, h->gsp_recv, h->gret_recv, h->xflags};
+    memset(out, 0, sizeof(*out));
+    for (int k = 0; k < LM_PEER_BUFFERS; ++k) {
+        out->ptr[k] = buf[k];
+        cudaIpcMemHandle_t hd;
+        static_assert(sizeof(cudaIpcMemHandle_t) == LM_IPC_HANDLE_BYTES, "IPC handle size");
+        if (cudaIpcGetMemHandle(&hd, buf[k]) == cudaSuccess) memcpy(out->ipc[k], &hd, sizeof(hd));
+        else cudaGetLastError();               // no IPC on this platform: the pointers still serve a same-process neighbour
+    }
+    return LM_OK;
+}
+
+int lm_strip_peer_connect(lm_handle h, int32_t side, const lm_peer_export *peer, int32_t use_ipc)
+{
+    if (!h || !peer || side < 0 || side > 1) return LM_EINVAL;
+    if (!h->send_cap) return LM_ESTATE;
+    LM_CUDA(cudaSetDevice(h->device));
+    lm_handle_s::Peer &P = h->peer[side];
+    if (P.connected) return LM_ESTATE;
+    void *m[LM_PEER_BUFFERS];
+    for (int k = 0; k < LM_PEER_BUFFERS; ++k) {
+        P.base[k] = nullptr;
+        if (use_ipc) {
+            cudaIpcMemHandle_t hd;
+            memcpy(&hd, peer->ipc[k], sizeof(hd));
+            LM_CUDA(cudaIpcOpenMemHandle(&m[k], hd, cudaIpcMemLazyEnablePeerAccess));
+            P.base[k] = m[k];
+        } else m[k] = peer->ptr[k];
+        if (!m[k]) return LM_EINVAL;
+    }
+    // my southern neighbour receives what I send south in ITS northern slot (mig_recv[1]) and vice versa
+    P.mig_recv = static_cast<int4 *>(m[side == 0 ? 1 : 0]);
+    P.ghost_recv = static_cast<int32_t *>(m[2]);
+    P.gsp_recv = static_cast<int8_t *>(m[3]);
+    P.gret_recv = static_cast<int8_t *>(m[4]);
+    P.flags = static_cast<unsigned int *>(m[5]);
+    P.ipc = use_ipc != 0;
+    P.connected = true;
+    h->xseq = 0;
+    LM_CUDA(cudaMemset(h->xflags, 0, 8 * sizeof(unsigned int)));
+    return LM_OK;
+}
+
+// flag words of a strip: [0] migrants from the south arrived | [1] from the north | [2] ghost row | [3] its species (gsp) |
+// [4] the species coming back (gret) | [5] the southern neighbour has consumed my migrants | [6] the northern one has
+int lm_step_push(lm_handle h, int32_t kind, void *stream)
+{
+    if (!h || kind < LM_XCHG_MIG || kind > LM_XCHG_GRET) return LM_EINVAL;
+    LM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = as_stream(stream);
+    const unsigned int seq = h->xseq;
+    if (kind == LM_XCHG_MIG) {
+        for (int d = 0; d < 2; ++d) {
+            if (!(d ? h->has_north : h->has_south) || !h->peer[d].connected) continue;
+            // the neighbour's buffer is free once it has consumed the previous message (its acknowledgement lands in my flags)
+            if (seq > 1) LM_CUDA(launch_peer_wait(h->xflags + 5 + d, seq - 1, s, &h->launches));
+            LM_CUDA(launch_peer_push_mig(h->mig_send[d], h->peer[d].mig_recv, h->send_cap, s, &h->launches));
+            LM_CUDA(launch_peer_signal(h->peer[d].flags + (d == 0 ? 1 : 0), seq, s, &h->launches));   // I am its northern / southern side
+        }
+        return LM_OK;
+    }
+    // the other messages were written into the neighbour's buffer by their pack kernels: only the flag is left
+    const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
+    if (!interact) return LM_OK;
+    if (kind == LM_XCHG_GHOST && h->has_south && h->peer[0].connected) LM_CUDA(launch_peer_signal(h->peer[0].flags + 2, seq, s, &h->launches));
+    if (kind == LM_XCHG_GSP && h->has_south && h->peer[0].connected) LM_CUDA(launch_peer_signal(h->peer[0].flags + 3, seq, s, &h->launches));
+    if (kind == LM_XCHG_GRET && h->has_north && h->peer[1].connected) LM_CUDA(launch_peer_signal(h->peer[1].flags + 4, seq, s, &h->launches));
     return LM_OK;
 }
 
@@ -563,6 +645,7 @@ int lm_step_move(lm_handle h, int32_t flags, const lm_stage_times *st, float dt,
     }
     h->step_flags = flags;
     if (prm) h->step_rps = to_dev(prm);
+    ++h->xseq;                            // peer-memory exchange: the messages of this step carry this number
     h->stage = 1;
     return LM_OK;
 }
@@ -574,6 +657,8 @@ int lm_step_bin(lm_handle h, void *stream)
     LM_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = as_stream(stream);
     int c = h->cur;
+    for (int d = 0; d < 2; ++d)          // peer-memory exchange: the neighbours' migrants of this step have landed
+        if ((d ? h->has_north : h->has_south) && h->peer[d].connected) LM_CUDA(launch_peer_wait(h->xflags + d, h->xseq, s, &h->launches));
     if (h->step_moved) {
         // the re-binning gathers species: the previous step's RPS phases must be done
         { const int rcj = join_side(h, s); if (rcj) return rcj; }
@@ -613,6 +698,9 @@ int lm_step_bin(lm_handle h, void *stream)
         h->n = n_out;
         h->binned = true;
     }
+    for (int d = 0; d < 2; ++d)          // ... and are consumed (or were not needed): the neighbour may overwrite them
+        if ((d ? h->has_north : h->has_south) && h->peer[d].connected)
+            LM_CUDA(launch_peer_signal(h->peer[d].flags + 5 + (d == 0 ? 1 : 0), h->xseq, s, &h->launches));
     if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[2], s));
     if (h->rec_active) {
         // positions and ids of this step are final: scatter them to id order and send them to the host on the copy
@@ -644,6 +732,7 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
     { const int rcj = join_side(h, s); if (rcj) return rcj; }
     const int c = h->cur, n = (int)h->n;
     const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
+    if (h->has_north && interact && h->peer[1].connected) LM_CUDA(launch_peer_wait(h->xflags + 2, h->xseq, s, &h->launches));
     if (h->has_north && interact) LM_CUDA(launch_ghost_unpack(h, h->lon[c], h->lat[c], h->id[c], n, s));
     h->rps_cap = -1;
     h->emit_cap = -1;
@@ -682,6 +771,7 @@ int lm_step_interact_end(lm_handle h, void *stream)
     cudaStream_t s = as_stream(stream);
     const int c = h->cur, n = (int)h->n;
     const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
+    if (h->has_north && interact && h->peer[1].connected) LM_CUDA(launch_peer_wait(h->xflags + 3, h->xseq, s, &h->launches));
     if (h->has_north && interact) LM_CUDA(launch_ghost_species_unpack(h, h->sp[c], n, s));
     if (interact && n > 0) {
         if (!h->resolve_all_in_begin) LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, h->resolve_on_side ? h->side_stream : s));
@@ -708,6 +798,8 @@ int lm_step_finish(lm_handle h, void *stream)
     LM_CUDA(cudaSetDevice(h->device));
     cudaStream_t s = as_stream(stream);
     const int c = h->cur, n = (int)h->n;
+    if (h->has_south && (h->step_flags & LM_STEP_INTERACT) && h->peer[0].connected)
+        LM_CUDA(launch_peer_wait(h->xflags + 4, h->xseq, s, &h->launches));
     if (h->has_south && (h->step_flags & LM_STEP_INTERACT)) LM_CUDA(launch_row0_species_unpack(h, h->sp[c], s));
     if (h->step_flags & LM_STEP_STATS) LM_CUDA(launch_stats(h->lon[c], h->lat[c], h->sp[c], n, h->ctr, s, &h->launches));
     if (h->step_flags & LM_STEP_TIMING) {

@@ -52,7 +52,7 @@ constexpr int IT_TW = LM_TILE_W, IT_TH = LM_TILE_H;
 constexpr int IT_THREADS = 256;
 constexpr int IT_CELLS = IT_TW * IT_TH;
 constexpr int IT_UPT = IT_CELLS / IT_THREADS;            // cells a thread looks at when the units of a phase are listed
-constexpr int IT_STAGE = 2048;                            // pairs staged per CTA between flushes (walk / heavy paths)
+constexpr int IT_STAGE = 512;                             // pairs staged per CTA between flushes (walk / heavy paths)
 constexpr unsigned int IT_MEGA_MIN = 8192;                // slots from which the whole CTA takes a heavy unit
 constexpr int IT_MAX_TILE_CAP = 6144;                     // microbes a tile can stage (13-bit local indices in a record)
 constexpr unsigned int REC_IDX = 0x1fffu;                 // record: anchor (13 bits) | partner << 13 | draw bits << 26 | has draw << 29
@@ -731,10 +731,8 @@ __global__ void __launch_bounds__(IT_THREADS) interact_cross_kernel(IArgs A, lon
 // every lane of a round holds a pair of its own.
 constexpr int HV_WARP_CAP = 256;                          // microbes of a unit one warp stages (13 B each)
 constexpr int HV_CTA_CAP = 4096;                          // ... the whole CTA (larger units work on the global arrays)
-constexpr int HV_WARP_CODES = 4096;                       // slot codes of a chunk of rounds, per warp
-constexpr int HV_CTA_CODES = 16384;                       // ... per CTA
-constexpr int HV_WARP_BYTES = HV_WARP_CAP * 13 + HV_WARP_CODES;
-constexpr int HV_CTA_BYTES = HV_CTA_CAP * 13 + HV_CTA_CODES;
+constexpr int HV_WARP_BYTES = HV_WARP_CAP * 13;
+constexpr int HV_CTA_BYTES = HV_CTA_CAP * 13;
 constexpr int HV_DYN_BYTES = HV_CTA_BYTES > 8 * HV_WARP_BYTES ? HV_CTA_BYTES : 8 * HV_WARP_BYTES;
 static_assert(HV_WARP_BYTES % 16 == 0 && (HV_WARP_CAP * 13) % 16 == 0 && (HV_CTA_CAP * 13) % 16 == 0, "alignment of the staging buffers");
 struct UnitView {
@@ -748,83 +746,10 @@ struct UnitView {
     __device__ __forceinline__ void W(int i, int s) const { ((volatile int8_t *)sp)[i] = (int8_t)s; }
 };
 
-// The rounds of a STAGED unit in two sweeps per chunk of rounds.  What makes a round expensive -- the distance test, the
-// pair emission, the Philox draw -- does not depend on the species, only the 3-instruction rule does; so the slots of a
-// whole chunk of rounds are evaluated first, all independent of each other (no barrier, full pipelining), into one code
-// byte per slot (bit 0 hit | bits 1-3 draw bits | bit 4 draw present: taken when the species differ at that moment), and
-// the rounds themselves, the only sequential part, become: code byte, two species bytes, rule, one store.  A code without
-// a draw whose species have come to differ draws on the spot.
-template <bool DO_RPS, bool CTA>
-__device__ void unit_rounds_staged(const IArgs &A, Shared &sh, const UnitView &v, const uint4 u, uint8_t *code, int code_cap)
-{
-    const int nthr = CTA ? IT_THREADS : 32;
-    const int me = CTA ? (int)threadIdx.x : (int)(threadIdx.x & 31);
-    const int a_base = (int)u.x, b_base = (int)u.y, ma = (int)u.z, mb = (int)u.w;
-    const bool same = a_base == b_base;
-    const int m = ma, Me = m + (m & 1), n1 = Me - 1, half = Me >> 1, Mx = max(ma, mb);
-    const int rounds = same ? n1 : Mx, spr = same ? half : ma;        // slots per round
-    if (spr > code_cap) { unit_rounds<UnitView, DO_RPS, CTA>(A, sh, v, u); return; }
-    const int rpc = max(1, code_cap / spr);                           // rounds per chunk
-    auto slot = [&](int k, int i, int &ia, int &ib) -> bool {
-        if (i >= spr) return false;
-        if (same) {
-            int ra, rb;
-            if (i == 0) { ra = Me - 1; rb = k; }
-            else { ra = k + i; if (ra >= n1) ra -= n1; rb = k - i; if (rb < 0) rb += n1; }
-            ia = a_base + min(ra, rb); ib = a_base + max(ra, rb);
-            return ra < m && rb < m;
-        }
-        int j = i + k;
-        if (j >= Mx) j -= Mx;
-        ia = a_base + i; ib = b_base + j;
-        return j < mb;
-    };
-    for (int k0 = 0; k0 < rounds; k0 += rpc) {
-        const int k1 = min(rounds, k0 + rpc);
-        for (int k = k0; k < k1; ++k) {
-            for (int i0 = 0; i0 < spr; i0 += nthr) {                  // uniform trip count: stage_pairs needs whole warps
-                const int i = i0 + me;
-                int ia = 0, ib = 0;
-                const bool valid = slot(k, i, ia, ib);
-                const bool hit = valid && within(A, v.P(ia), v.P(ib));
-                int lo = 0, hi = 0;
-                if (hit) { const int x = v.I(ia), y = v.I(ib); lo = min(x, y); hi = max(x, y); }
-                stage_pairs(A, sh, hit, lo, hi);
-                unsigned int c = hit ? 1u : 0u;
-                if (DO_RPS && hit) {
-                    const int sa = v.S(ia), sb = v.S(ib);
-                    if (sa != sb && is_rps(sa) && is_rps(sb)) c |= (decision_bits(A, lo, hi) << 1) | 16u;
-                }
-                if (i < spr) code[(k - k0) * spr + i] = (uint8_t)c;
-            }
-            if (CTA) { __syncthreads(); flush_pairs(A, sh, false); }
-        }
-        if (CTA) __syncthreads(); else __syncwarp();
-        if (DO_RPS) {
-            for (int k = k0; k < k1; ++k) {
-                for (int i0 = 0; i0 < spr; i0 += nthr) {
-                    const int i = i0 + me;
-                    const unsigned int c = i < spr ? code[(k - k0) * spr + i] : 0u;
-                    if (c & 1u) {
-                        int ia = 0, ib = 0;
-                        slot(k, i, ia, ib);
-                        const int sa = v.S(ia), sb = v.S(ib);
-                        if (sa != sb && is_rps(sa) && is_rps(sb)) {
-                            uint32_t dec;
-                            if (c & 16u) dec = (c >> 1) & 7u;
-                            else { const int x = v.I(ia), y = v.I(ib); dec = decision_bits(A, min(x, y), max(x, y)); }
-                            const int s = rps_apply(sa, sb, dec);
-                            if (s != sa) v.W(ia, s); else v.W(ib, s);
-                        }
-                    }
-                }
-                if (CTA) __syncthreads(); else __syncwarp();
-            }
-        }
-        if (CTA) __syncthreads(); else __syncwarp();                  // the codes are free for the next chunk
-    }
-}
-
+// (Tried and measured, profiles/r2k_config2_probe_two_sweep_rounds.jsonl: evaluating the slots of a chunk of rounds first --
+// distance test, emission and draw do not depend on species -- into one code byte per slot, and keeping only the rule in
+// the sequential rounds.  Slower: BASELINE config 2's worst step 1.39 -> 2.07 ms.  One warp issues the same instructions
+// either way, and the second sweep plus the code bytes come on top; the round is bound by issue, not by its dependences.)
 // ug: x, y first microbe of the anchor / other cell (global indices; equal: one cell) | z, w their sizes.  buf: room for
 // `cap` microbes.  Called by all lanes of a warp (CTA = false) or all threads of the CTA (CTA = true) with the same unit.
 template <bool DO_RPS, bool CTA>
@@ -851,8 +776,7 @@ __device__ void heavy_unit(const IArgs &A, Shared &sh, const uint4 ug, unsigned 
     }
     if (CTA) __syncthreads(); else __syncwarp();
     UnitView v{s_pos, s_id, s_sp};
-    unit_rounds_staged<DO_RPS, CTA>(A, sh, v, make_uint4(0u, same ? 0u : (unsigned int)ma, ug.z, ug.w),
-                                    reinterpret_cast<uint8_t *>(buf) + (size_t)cap * 13, CTA ? HV_CTA_CODES : HV_WARP_CODES);
+    unit_rounds<UnitView, DO_RPS, CTA>(A, sh, v, make_uint4(0u, same ? 0u : (unsigned int)ma, ug.z, ug.w));
     if (CTA) __syncthreads(); else __syncwarp();
     if (DO_RPS)
         for (int i = me; i < n; i += nthr) A.sp[i < ma ? (int)ug.x + i : (int)ug.y + (i - ma)] = s_sp[i];
@@ -863,7 +787,7 @@ __global__ void __launch_bounds__(IT_THREADS) interact_heavy_kernel(IArgs A, con
                                                                     unsigned int *cnt, unsigned int cap)
 {
     // cnt: [0] queued warp units | [1] queued CTA units | [2] warp ticket | [3] CTA ticket   (of this phase)
-    extern __shared__ __align__(16) unsigned char s_buf[];            // HV_DYN_BYTES: 8 warp buffers (microbes + slot codes), or one for the CTA
+    extern __shared__ __align__(16) unsigned char s_buf[];            // HV_DYN_BYTES: 8 warp buffers, or one for the CTA
     __shared__ Shared sh;
     __shared__ unsigned int s_t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

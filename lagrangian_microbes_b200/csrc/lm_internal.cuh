@@ -163,6 +163,17 @@ struct lm_handle_s {
     int8_t *gsp_send, *gsp_recv;         // [ghost_cap] species of the ghost row, north -> south after phase 5
     int8_t *gret_send, *gret_recv;       // [ghost_cap] species of the ghost row, south -> north after phase 8
     int32_t *xfer_counts_host;           // pinned: n_leave[2], n_arrive[2]
+    // peer-memory exchange (lm_strip_peer_connect): the neighbours' receive buffers and flag words, mapped into this process
+    struct Peer {
+        bool connected, ipc;
+        int4 *mig_recv;                  // the neighbour's mig_recv on the side that faces this strip
+        int32_t *ghost_recv;
+        int8_t *gsp_recv, *gret_recv;
+        unsigned int *flags;
+        void *base[LM_PEER_BUFFERS];     // what cudaIpcOpenMemHandle returned (to close)
+    } peer[2];
+    unsigned int *xflags;                // [8] mine: mig from S | mig from N | ghost | gsp | gret | mig ack from S | mig ack from N
+    unsigned int xseq;                   // sequence number of the staged step in flight
     int n_moved_in, n_moved_out;         // last step (host copies)
     // staged step (lm_step_move .. lm_step_finish)
     int32_t step_flags;
@@ -194,6 +205,10 @@ cudaError_t launch_bin_finish(lm_handle_s *h, const float *lon, const float *lat
 cudaError_t launch_unpack_arrivals(lm_handle_s *h, int dir, int n_arrive, int first, float *lon, float *lat, int8_t *sp,
                                    int32_t *id, cudaStream_t s);
 cudaError_t launch_ghost_pack(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, cudaStream_t s);
+// peer-memory exchange (csrc/strip.cu)
+cudaError_t launch_peer_signal(unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches);
+cudaError_t launch_peer_wait(const unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches);
+cudaError_t launch_peer_push_mig(const int4 *src, int4 *dst, int64_t send_cap, cudaStream_t s, int64_t *launches);
 cudaError_t launch_ghost_unpack(lm_handle_s *h, float *lon, float *lat, int32_t *id, int n_owned, cudaStream_t s);
 // species of the first owned row -> gsp_send (pack) / gsp_recv -> ghost particles (unpack); and the way back
 cudaError_t launch_row0_species_pack(lm_handle_s *h, const int8_t *sp, cudaStream_t s);

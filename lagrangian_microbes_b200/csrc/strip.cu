@@ -75,8 +75,10 @@ __global__ void __launch_bounds__(256) ghost_pack_kernel(const float *__restrict
 cudaError_t launch_ghost_pack(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, cudaStream_t s)
 {
     const int work = (int)((h->ghost_cap > h->grid.ncx + 1) ? h->ghost_cap : h->grid.ncx + 1);
+    // peer-memory exchange: packed straight into the southern neighbour's receive buffer (peer stores over NVLink)
+    int32_t *msg = h->peer[0].connected ? h->peer[0].ghost_recv : h->ghost_send;
     ghost_pack_kernel<<<(work + 255) / 256, 256, 0, s>>>(lon, lat, id, h->cell_start, h->grid.ncx, (int)h->row_cap,
-                                                          (int)h->ghost_cap, h->ghost_send, h->ctr);
+                                                          (int)h->ghost_cap, msg, h->ctr);
     ++h->launches;
     return cudaGetLastError();
 }
@@ -139,7 +141,8 @@ static cudaError_t species_copy(lm_handle_s *h, const int8_t *src, int8_t *dst, 
 
 cudaError_t launch_row0_species_pack(lm_handle_s *h, const int8_t *sp, cudaStream_t s)
 {
-    return species_copy(h, sp, h->gsp_send, h->cell_start + h->grid.ncx, nullptr, false, false, s);
+    return species_copy(h, sp, h->peer[0].connected ? h->peer[0].gsp_recv : h->gsp_send, h->cell_start + h->grid.ncx, nullptr, false,
+                        false, s);
 }
 
 cudaError_t launch_row0_species_unpack(lm_handle_s *h, int8_t *sp, cudaStream_t s)
@@ -156,7 +159,51 @@ cudaError_t launch_ghost_species_unpack(lm_handle_s *h, int8_t *sp, int /*n_owne
 cudaError_t launch_ghost_species_pack(lm_handle_s *h, const int8_t *sp, int /*n_owned*/, cudaStream_t s)
 {
     const int32_t *beg = h->cell_start + (size_t)h->strip.rows_owned * h->grid.ncx;
-    return species_copy(h, sp, h->gret_send, beg + h->grid.ncx, beg, true, false, s);
+    return species_copy(h, sp, h->peer[1].connected ? h->peer[1].gret_recv : h->gret_send, beg + h->grid.ncx, beg, true, false, s);
+}
+
+// ---- peer-memory exchange: flags and the migrants' copy ---------------------------------------------------------------------
+// A message is complete at the neighbour when its flag holds the step's sequence number: the flag store follows the kernel that
+// wrote the message on the same stream, behind a system-scope fence; the consumer spins on its own flag word (written by the
+// peer over NVLink), then fences.
+__global__ void peer_signal_kernel(unsigned int *flag, unsigned int seq)
+{
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned int *>(flag) = seq;
+}
+
+__global__ void peer_wait_kernel(const unsigned int *flag, unsigned int seq)
+{
+    while ((int)(*reinterpret_cast<const volatile unsigned int *>(flag) - seq) < 0) { }   // wrap-safe: flag >= seq
+    __threadfence_system();
+}
+
+// the live part of a migration message: [0].x records behind the header
+__global__ void __launch_bounds__(256) peer_push_mig_kernel(const int4 *__restrict__ src, int4 *__restrict__ dst, int send_cap)
+{
+    const int n = 1 + min(max(src[0].x, 0), send_cap);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst[k] = src[k];
+}
+
+cudaError_t launch_peer_signal(unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches)
+{
+    peer_signal_kernel<<<1, 1, 0, s>>>(flag, seq);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_wait(const unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches)
+{
+    peer_wait_kernel<<<1, 1, 0, s>>>(flag, seq);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_peer_push_mig(const int4 *src, int4 *dst, int64_t send_cap, cudaStream_t s, int64_t *launches)
+{
+    peer_push_mig_kernel<<<64, 256, 0, s>>>(src, dst, (int)send_cap);
+    ++*launches;
+    return cudaGetLastError();
 }
 
 }  // namespace lm

@@ -211,6 +211,20 @@ class Engine:
         st = Strip(int(row0), int(rows_owned), int(bool(has_south)), int(bool(has_north)))
         check(self.L.lm_set_strip(self.h, ctypes.byref(st)), "lm_set_strip")
 
+    def peer_export(self):
+        """lm_strip_peer_export as ``bytes`` (to hand to a neighbour, possibly through torch.distributed)."""
+        e = _lib.PeerExport()
+        check(self.L.lm_strip_peer_export(self.h, ctypes.byref(e)), "lm_strip_peer_export")
+        return bytes(e)
+
+    def peer_connect(self, side, export_bytes, use_ipc):
+        """Connect to the neighbour on ``side`` (0 south, 1 north) whose ``peer_export()`` is ``export_bytes``."""
+        e = _lib.PeerExport.from_buffer_copy(export_bytes)
+        check(self.L.lm_strip_peer_connect(self.h, int(side), ctypes.byref(e), 1 if use_ipc else 0), "lm_strip_peer_connect")
+
+    def step_push(self, kind):
+        check(self.L.lm_step_push(self.h, int(kind), self._stream()), "lm_step_push")
+
     def strip_buffers(self):
         """Exchange buffers as uint8 CUDA tensors (no copy): dict name -> tensor / [south, north] pair."""
         b = StripBuffers()

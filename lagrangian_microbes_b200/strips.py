@@ -192,6 +192,44 @@ class DistTransport:
         return out
 
 
+class _PeerMixin:
+    """Peer-memory exchange (include/lm_b200.h: lm_peer_export): the packing kernels of a strip write straight into the
+    neighbour's receive buffers over NVLink / NVSwitch, a flag store follows each message and the consuming stage spins on its
+    flag -- stream-ordered on both sides, no NCCL send / recv on the data path.  ``connect`` is called once by StripSet."""
+
+    XCHG = {"mig": _lib.LM_XCHG_MIG, "ghost": _lib.LM_XCHG_GHOST, "gsp": _lib.LM_XCHG_GSP, "gret": _lib.LM_XCHG_GRET}
+    peer = True
+
+    def exchange(self, kind, strips):
+        for s in strips:
+            s.engine.step_push(self.XCHG[kind])
+
+
+class LocalPeerTransport(_PeerMixin, LocalTransport):
+    """Several strips in this process, exchanging through each other's device pointers (single-GPU tests of the peer path)."""
+
+    def connect(self, strips):
+        exports = {s.index: s.engine.peer_export() for s in strips}
+        for s in strips:
+            for side, nb in ((0, s.index - 1), (1, s.index + 1)):
+                if nb in exports:
+                    s.engine.peer_connect(side, exports[nb], use_ipc=False)
+
+
+class PeerTransport(_PeerMixin, DistTransport):
+    """One strip per rank; the neighbours' buffers are mapped through CUDA IPC.  torch.distributed carries the handles once
+    (and the small host-side reductions: counts, bounding boxes); the per-step messages never touch it."""
+
+    def connect(self, strips):
+        (s,) = strips
+        exports = [None] * self.n_strips
+        self.dist.all_gather_object(exports, s.engine.peer_export(), group=self.group)
+        for side, nb in ((0, self.rank - 1), (1, self.rank + 1)):
+            if 0 <= nb < self.n_strips:
+                s.engine.peer_connect(side, exports[nb], use_ipc=True)
+        self.dist.barrier(group=self.group)            # nobody steps before everybody is connected (flags zeroed)
+
+
 # ------------------------------------------------------------------------------------------------------
 class Strip:
     """One latitude strip: an Engine (one lm_handle) + its exchange buffers + its pair list."""
@@ -292,6 +330,8 @@ class StripSet:
             from .simulation import FieldWindowStreamer
             self.streamer = FieldWindowStreamer(fieldset, [s.engine for s in self.strips])
         self._record = None
+        if getattr(transport, "peer", False):
+            transport.connect(self.strips)
         self._apply_edges()
         for s, lo, la, sp, i in zip(self.strips, lons, lats, species, ids):
             if lo.size > s.engine.max_particles:

@@ -54,6 +54,12 @@ template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAtt
 enum { cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0 };
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+// CUDA IPC: not available on the emulator (one process); lm_strip_peer_export falls back to plain pointers
+struct cudaIpcMemHandle_t { char reserved[64]; };
+constexpr unsigned int cudaIpcMemLazyEnablePeerAccess = 1;
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *, void *) { return 1; }
+static inline cudaError_t cudaIpcOpenMemHandle(void **, cudaIpcMemHandle_t, unsigned int) { return 1; }
+static inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
 static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int) { *p = calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
@@ -139,6 +145,7 @@ static inline int atomicMax(int *p, int v)
 }
 
 static inline int __popc(unsigned int x) { return __builtin_popcount(x); }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }

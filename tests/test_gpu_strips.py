@@ -74,9 +74,14 @@ def compare_step(ss, sim, step):
     return st.n_pairs
 
 
-@pytest.mark.parametrize("G,clustered", [(2, False), (3, True), (4, False), (7, True)])
-def test_strips_on_one_device_equal_single_handle(G, clustered):
-    from lagrangian_microbes_b200.strips import LocalTransport, StripSet
+# peer = True: the strips exchange through each other's device pointers -- the peer-memory path of the multi-GPU run (packing
+# kernels writing into the neighbour's receive buffer, flag stores, spinning consumers) on one device
+@pytest.mark.parametrize("G,clustered,peer", [(2, False, False), (3, True, False), (4, False, False), (7, True, False),
+                                              (2, False, True), (3, True, True), (5, False, True)])
+def test_strips_on_one_device_equal_single_handle(G, clustered, peer):
+    from lagrangian_microbes_b200.strips import LocalPeerTransport, StripSet
+    from lagrangian_microbes_b200.strips import LocalTransport as _Copy
+    LocalTransport = LocalPeerTransport if peer else _Copy
     n, seed = 40000, 11 + G
     fs = small_fs()
     lon, lat, sp = particles(n, seed, clustered)
@@ -87,7 +92,7 @@ def test_strips_on_one_device_equal_single_handle(G, clustered):
     ss = StripSet(LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
                   [ids[c] for c in cut], n, R, *P, fs, seed=seed, local_strips=list(range(G)), slack=3.0,
                   pairs_per_particle=40 * G, grid_margin=0.25, regrid_every=0)     # a dense blob puts most pairs into one strip
-    assert all(e % 2 == 0 for e in ss.edges[:-1]) and ss.edges[-1] == ss.grid.ncy
+    assert all(e % 16 == 0 for e in ss.edges[:-1]) and ss.edges[-1] == ss.grid.ncy
     sim = single(lon, lat, sp, ss.grid, fs, seed)
     total, moved = 0, 0
     for step in range(6):
@@ -119,10 +124,13 @@ def test_strips_with_diffusion_and_rebalancing():
     ss.close()
 
 
-def test_strips_regrid_with_the_single_handle():
+@pytest.mark.parametrize("peer", [False, True])
+def test_strips_regrid_with_the_single_handle(peer):
     """A tight grid (margin 0.03 degrees) that has to be re-fitted as the cloud moves: strips and single handle
     follow the same policy, must pick the same grids at the same steps and stay bit-identical."""
-    from lagrangian_microbes_b200.strips import LocalTransport, StripSet
+    from lagrangian_microbes_b200.strips import LocalPeerTransport, StripSet
+    from lagrangian_microbes_b200.strips import LocalTransport as _Copy
+    LocalTransport = LocalPeerTransport if peer else _Copy
     G, n, seed = 3, 30000, 8
     fs = small_fs()
     lon, lat, sp = particles(n, seed)
@@ -173,20 +181,21 @@ def test_exchange_buffer_overflow_is_reported():
 
 
 # ------------------------------------------------------------------------------------------------------
-def _nccl_worker(rank, world, port, n, seed, steps, out_dir):
+def _nccl_worker(rank, world, port, n, seed, steps, out_dir, kind="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        from lagrangian_microbes_b200.strips import DistTransport, StripSet
+        from lagrangian_microbes_b200.strips import DistTransport, PeerTransport, StripSet
         fs = small_fs()
         lon, lat, sp = particles(n, seed, clustered=True)
         ids = np.arange(n, dtype=np.int32)
         per = n // world
         c = slice(rank * per, (rank + 1) * per if rank < world - 1 else n)
-        ss = StripSet(DistTransport(), lon[c], lat[c], sp[c], ids[c], n, R, *P, fs, seed=seed, slack=3.0,
+        # "nccl": send / recv between neighbours; "peer": the neighbours' buffers mapped through CUDA IPC, peer stores + flags
+        ss = StripSet(PeerTransport() if kind == "peer" else DistTransport(), lon[c], lat[c], sp[c], ids[c], n, R, *P, fs, seed=seed, slack=3.0,
                       pairs_per_particle=40, grid_margin=0.05, regrid_every=4, cells_headroom=3.0)
         grid0 = (ss.grid.x0, ss.grid.y0, ss.grid.inv_h, ss.grid.ncx, ss.grid.ncy)      # the grid of step 0 (re-fitted later)
         rec = []
@@ -206,8 +215,8 @@ def _nccl_worker(rank, world, port, n, seed, steps, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_strips_over_nccl_equal_single_handle(tmp_path, world):
+@pytest.mark.parametrize("world,kind", [(2, "nccl"), (2, "peer"), (4, "nccl"), (4, "peer")])
+def test_strips_over_nccl_equal_single_handle(tmp_path, world, kind):
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
@@ -216,7 +225,7 @@ def test_strips_over_nccl_equal_single_handle(tmp_path, world):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mp.spawn(_nccl_worker, args=(world, port, n, seed, steps, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, port, n, seed, steps, str(tmp_path), kind), nprocs=world, join=True)
     parts = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
     g = parts[0]
     grid = Grid(float(g["grid"][0]), float(g["grid"][1]), float(g["grid"][2]), int(g["grid_n"][0]), int(g["grid_n"][1]))

@@ -339,8 +339,9 @@ def test_fused_steps_through_the_c_abi(abi, interact_mode, resolve_mode, stats_e
         assert L.lm_destroy(h) == 0
 
 
-@pytest.mark.parametrize("n_strips,interact_mode,resolve_mode", [(2, 2, 0), (3, 2, 0), (2, 1, 0), (3, 1, 0), (2, 0, 1), (3, 0, 0)])
-def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve_mode):
+@pytest.mark.parametrize("n_strips,interact_mode,resolve_mode,peer", [(2, 2, 0, False), (3, 2, 0, False), (3, 2, 0, True), (2, 1, 0, False),
+                                                                      (3, 1, 0, True), (2, 0, 1, False), (3, 0, 0, False)])
+def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve_mode, peer):
     """The whole strip protocol executed: G handles, particles handed out in contiguous tiles, routing
     passes until every microbe sits in its strip, then fused steps in the five stages of include/lm_b200.h with the
     exchange buffers copied between neighbours -- against ONE handle stepping all microbes on the same grid.
@@ -392,9 +393,28 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve
             assert L.lm_set_strip(h, ctypes.byref(st)) == 0
             a, b_, c_, d_ = (np.ascontiguousarray(x[sl]) for x in (lon, lat, sp0, ids))
             assert L.lm_state_set(h, _ptr(a), _ptr(b_), _ptr(c_), _ptr(d_), a.size, None) == 0
+        if peer:
+            # the peer-memory exchange of the multi-GPU run: every strip connects to its neighbours' receive buffers (plain
+            # pointers: one process), the packing kernels write there and lm_step_push posts the flags -- no copies by the caller
+            exports = []
+            for h in strips:
+                e = _lib.PeerExport()
+                assert L.lm_strip_peer_export(h, ctypes.byref(e)) == 0
+                exports.append(e)
+            for k, h in enumerate(strips):
+                if k > 0:
+                    assert L.lm_strip_peer_connect(h, 0, ctypes.byref(exports[k - 1]), 0) == 0
+                if k < G - 1:
+                    assert L.lm_strip_peer_connect(h, 1, ctypes.byref(exports[k + 1]), 0) == 0
 
         def copy(dst, src, nbytes):
-            ctypes.memmove(dst, src, nbytes)
+            if not peer:
+                ctypes.memmove(dst, src, nbytes)
+
+        def push(kind):
+            if peer:
+                for h in strips:
+                    assert L.lm_step_push(h, kind, None) == 0
 
         def staged(flags, st_times, prm):
             for h in strips:
@@ -405,22 +425,26 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve
                     copy(bufs[k - 1].mig_recv[1], bufs[k].mig_send[0], bufs[k].mig_bytes)
                 if k < G - 1:
                     copy(bufs[k + 1].mig_recv[0], bufs[k].mig_send[1], bufs[k].mig_bytes)
+            push(_lib.LM_XCHG_MIG)
             for h in strips:
                 assert L.lm_step_bin(h, None) == 0
             halo = bool(flags & _lib.LM_STEP_INTERACT)
             if halo:
                 for k in range(1, G):
                     copy(bufs[k - 1].ghost_recv, bufs[k].ghost_send, bufs[k].ghost_bytes)
+            push(_lib.LM_XCHG_GHOST)
             for k, h in enumerate(strips):
                 assert L.lm_step_interact_begin(h, r, _ptr(pair_bufs[k]), cap, None) == 0
             if halo:
                 for k in range(1, G):
                     copy(bufs[k - 1].gsp_recv, bufs[k].gsp_send, bufs[k].species_bytes)
+            push(_lib.LM_XCHG_GSP)
             for h in strips:
                 assert L.lm_step_interact_end(h, None) == 0
             if halo:
                 for k in range(G - 1):
                     copy(bufs[k + 1].gret_recv, bufs[k].gret_send, bufs[k].species_bytes)
+            push(_lib.LM_XCHG_GRET)
             for h in strips:
                 assert L.lm_step_finish(h, None) == 0
 

@@ -14,7 +14,7 @@ import bench  # noqa: E402
 from lagrangian_microbes_b200._lib import LM_OPT_ADVECT_MODE, LM_OPT_HEAVY_MIN, LM_OPT_INTERACT_MODE  # noqa: E402
 from lagrangian_microbes_b200.simulation import FusedSimulation  # noqa: E402
 
-SETTINGS = [(2, 256), (2, 1024), (2, 4096), (2, 16384), (2, 65536), (0, 0), (2, 256)]
+SETTINGS = [(2, 1024), (2, 2048), (2, 4096), (2, 8192), (2, 16384), (2, 65536), (0, 0), (2, 1024)]
 
 hfs = bench.make_fieldset(64)
 sims = {}
