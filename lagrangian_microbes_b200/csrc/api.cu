@@ -139,6 +139,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     h->tile_cap = 0;
     h->tile_rec_cap = 0;
     h->tile_path = 0;
+    h->scatter_passes = 0;
     h->resolve_tile_smem = 32768;
     h->resolve_batch = 4;      // measured on B200 (profiles/r1y_sweep_resolve.jsonl): 4 beats 1 and 8 on every workload
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
@@ -435,6 +436,16 @@ static int reset_counters(lm_handle h, cudaStream_t s)
 
 // RPS phases of the last step may still be running on the side stream: make `s` wait for them before it
 // touches species / the hand-off / the state.
+// id windows of a scatter into ``arrays`` float32 targets: each window's targets are to stay L2-resident
+static int scatter_windows(const lm_handle_s *h, int arrays)
+{
+    if (h->scatter_passes > 0) return h->scatter_passes;
+    if (arrays == 0) return 1;
+    const int64_t bytes = (int64_t)h->n * 4 * arrays;
+    const int64_t window = 32ll << 20;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(16, (bytes + window - 1) / window));
+}
+
 static int join_side(lm_handle h, cudaStream_t s)
 {
     if (h->resolve_pending) {
@@ -711,7 +722,8 @@ int lm_step_bin(lm_handle h, void *stream)
         LM_CUDA(cudaEventRecord(h->ev_pos_ready, s));
         LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_pos_ready, 0));
         LM_CUDA(launch_scatter_by_id(h->lon[c], h->lat[c], nullptr, h->id[c], (int)nn, h->rec_lon_host ? h->stage_lon[k] : nullptr,
-                                     h->rec_lat_host ? h->stage_lat[k] : nullptr, nullptr, h->copy_stream, &h->launches));
+                                     h->rec_lat_host ? h->stage_lat[k] : nullptr, nullptr, h->copy_stream, &h->launches,
+                                     scatter_windows(h, (h->rec_lon_host ? 1 : 0) + (h->rec_lat_host ? 1 : 0)), (int)nn));
         LM_CUDA(cudaEventRecord(h->ev_pos_scattered, h->copy_stream));
         h->pos_scatter_pending = true;
         if (h->rec_lon_host) LM_CUDA(cudaMemcpyAsync(h->rec_lon_host, h->stage_lon[k], nn * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
@@ -858,7 +870,7 @@ int lm_state_get(lm_handle h, float *lon_out, float *lat_out, int8_t *species_ou
     const int c = h->cur;
     { const int rcj = join_side(h, as_stream(stream)); if (rcj) return rcj; }
     LM_CUDA(launch_scatter_by_id(h->lon[c], h->lat[c], h->sp[c], h->id[c], (int)h->n, lon_out, lat_out, species_out,
-                                 as_stream(stream), &h->launches));
+                                 as_stream(stream), &h->launches, scatter_windows(h, (lon_out ? 1 : 0) + (lat_out ? 1 : 0)), (int)h->n));
     return LM_OK;
 }
 
@@ -874,7 +886,7 @@ int lm_state_get_host(lm_handle h, float *lon_host, float *lat_host, int8_t *spe
     LM_CUDA(cudaStreamWaitEvent(s, h->ev_copied[k], 0));
     LM_CUDA(launch_scatter_by_id(h->lon[c], h->lat[c], h->sp[c], h->id[c], (int)n, lon_host ? h->stage_lon[k] : nullptr,
                                  lat_host ? h->stage_lat[k] : nullptr, species_host ? h->stage_sp[k] : nullptr, s,
-                                 &h->launches));
+                                 &h->launches, scatter_windows(h, (lon_host ? 1 : 0) + (lat_host ? 1 : 0)), (int)n));
     LM_CUDA(cudaEventRecord(h->ev_scatter[k], s));
     LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_scatter[k], 0));
     if (lon_host) LM_CUDA(cudaMemcpyAsync(lon_host, h->stage_lon[k], n * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
@@ -1037,6 +1049,10 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
         case LM_OPT_HEAVY_MIN:
             if (value < 0 || value > (1ll << 40)) return LM_EINVAL;
             h->heavy_min = value;
+            return LM_OK;
+        case LM_OPT_SCATTER_PASSES:
+            if (value < 0 || value > 64) return LM_EINVAL;
+            h->scatter_passes = (int)value;
             return LM_OK;
         case LM_OPT_TILE_PATH:
             if (value < 0 || value > 1) return LM_EINVAL;

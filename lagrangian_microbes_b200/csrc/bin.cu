@@ -14,6 +14,7 @@
 // Step 4 makes the storage order canonical -- (cell, id) -- independent of atomic arrival order,
 // of the previous storage order and (multi-GPU) of how particles were distributed over ranks.
 // The fused RPS resolver's pair order is defined on it (oracle/rps.py::cell_phase_order).
+#include <climits>
 #include "lm_internal.cuh"
 
 namespace lm {
@@ -273,27 +274,43 @@ cudaError_t launch_bin(lm_handle_s *h, const float *lon, const float *lat, const
 
 // out[id[p]] = value[p]   (the reference's per-step record is in particle-id order:
 // interaction_simulator.py:108-110, particle_advecter.py:233-235)
+// The record leaves in particle-id order (the reference's [particle][time] columns), the state lives in cell order:
+// one random 4-byte store per value.  A store that misses L2 costs a whole 32-byte sector twice (fill + write-back),
+// so the ids are taken in ``passes`` windows: window w only stores ids in [w n / passes, (w + 1) n / passes), whose
+// targets (n / passes values per array) stay resident in L2 until every byte of a sector has been written.  The
+// sources are streamed (evict-first) so that they do not push the window out.
 __global__ void __launch_bounds__(256) scatter_by_id_kernel(const float *__restrict__ lon, const float *__restrict__ lat,
                                                             const int8_t *__restrict__ sp,
-                                                            const int32_t *__restrict__ id, int n,
+                                                            const int32_t *__restrict__ id, int n, int id_lo, int id_hi,
                                                             float *__restrict__ lon_o, float *__restrict__ lat_o,
                                                             int8_t *__restrict__ sp_o)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const int d = id[p];
-    if (lon_o) lon_o[d] = lon[p];
-    if (lat_o) lat_o[d] = lat[p];
+    const int d = __ldcs(id + p);
+    if (d < id_lo || d >= id_hi) return;
+    if (lon_o) lon_o[d] = __ldcs(lon + p);
+    if (lat_o) lat_o[d] = __ldcs(lat + p);
     if (sp_o) sp_o[d] = sp[p];
 }
 
 cudaError_t launch_scatter_by_id(const float *lon, const float *lat, const int8_t *sp, const int32_t *id, int n,
-                                 float *lon_o, float *lat_o, int8_t *sp_o, cudaStream_t s, int64_t *launches)
+                                 float *lon_o, float *lat_o, int8_t *sp_o, cudaStream_t s, int64_t *launches, int passes,
+                                 int id_span)
 {
     if (n <= 0) return cudaSuccess;
     const int block = 256;
-    scatter_by_id_kernel<<<(n + block - 1) / block, block, 0, s>>>(lon, lat, sp, id, n, lon_o, lat_o, sp_o);
-    ++*launches;
+    if (passes <= 1 || id_span <= 0) {
+        scatter_by_id_kernel<<<(n + block - 1) / block, block, 0, s>>>(lon, lat, sp, id, n, INT_MIN, INT_MAX, lon_o, lat_o, sp_o);
+        ++*launches;
+        return cudaGetLastError();
+    }
+    for (int w = 0; w < passes; ++w) {
+        const int lo = w == 0 ? INT_MIN : (int)((long long)id_span * w / passes);
+        const int hi = w == passes - 1 ? INT_MAX : (int)((long long)id_span * (w + 1) / passes);
+        scatter_by_id_kernel<<<(n + block - 1) / block, block, 0, s>>>(lon, lat, sp, id, n, lo, hi, lon_o, lat_o, sp_o);
+        ++*launches;
+    }
     return cudaGetLastError();
 }
 

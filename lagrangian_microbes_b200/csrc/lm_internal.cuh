@@ -108,6 +108,7 @@ struct lm_handle_s {
     int2 *heavy_list;      // [9 phases][2: warp units | CTA units][heavy_cap] (anchor cell, other cell) queued by the pair search
     unsigned int *heavy_cnt;   // [9][4] queued warp units | queued CTA units | warp ticket | CTA ticket
     int64_t heavy_cap;
+    int scatter_passes;    // LM_OPT_SCATTER_PASSES: id windows of the record scatter (0 = auto, see scatter_windows)
     int64_t heavy_min;     // LM_OPT_HEAVY_MIN: candidate pairs above which a unit is heavy in the hybrid mode (0 = default, 1024: part of the
                            // definition of the cell-round order; other values are for A/B measurements)
     int draw_batch;        // LM_OPT_DRAW_BATCH: parked lanes that trigger a warp's Philox rounds (0 = default, 20)
@@ -216,7 +217,8 @@ cudaError_t launch_ghost_species_unpack(lm_handle_s *h, int8_t *sp, int n_owned,
 cudaError_t launch_ghost_species_pack(lm_handle_s *h, const int8_t *sp, int n_owned, cudaStream_t s);
 cudaError_t launch_row0_species_unpack(lm_handle_s *h, int8_t *sp, cudaStream_t s);
 cudaError_t launch_scatter_by_id(const float *lon, const float *lat, const int8_t *sp, const int32_t *id, int n,
-                                 float *lon_o, float *lat_o, int8_t *sp_o, cudaStream_t s, int64_t *launches);
+                                 float *lon_o, float *lat_o, int8_t *sp_o, cudaStream_t s, int64_t *launches, int passes = 1,
+                                 int id_span = 0);
 cudaError_t launch_stats(const float *lon, const float *lat, const int8_t *sp, int n, Counters *ctr, cudaStream_t s,
                          int64_t *launches);
 // pair search (+ optional fused RPS in canonical cell-phase order) on binned arrays

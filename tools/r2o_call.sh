@@ -17,4 +17,5 @@ ncu -i $O/step_full.ncu-rep --page source --csv --kernel-name regex:find_pairs -
 rm -f $O/step_full.ncu-rep          # gpurun brings back at most 64 MiB: keep the exports, not the report
 timeout 900 python tools/sweep_interact.py --max-n 50000000 > $O/sweep_config5.jsonl 2> $O/sweep_config5.err; cut -c1-200 $O/sweep_config5.jsonl; tail -2 $O/sweep_config5.err
 timeout 600 python bench.py --workload config5 > $O/bench_config5.json 2> $O/bench_config5.err; cut -c1-400 $O/bench_config5.json; tail -2 $O/bench_config5.err
+timeout 900 python tools/scatter_probe.py > $O/scatter_probe.jsonl 2> $O/scatter_probe.err; cat $O/scatter_probe.jsonl; tail -3 $O/scatter_probe.err
 ls -la $O
