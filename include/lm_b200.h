@@ -326,7 +326,7 @@ int lm_reset_stats(lm_handle h, void *stream);
 #define LM_OPT_HEAVY_MIN 18
 /*   LM_OPT_SCATTER_PASSES  the record leaves in particle-id order: the scatter from cell order takes the ids in this many
  *                     windows so that a window's targets stay in L2 until their sectors are complete (0 = auto: windows of
- *                     about 32 MB; 1 = one pass) */
+ *                     about 64 MB; 1 = one pass) */
 #define LM_OPT_SCATTER_PASSES 19
 /* tile of the fused interaction pass, in cells: part of the definition of its canonical pair order.  Strip boundaries
  * (lm_set_strip) must sit on multiples of LM_TILE_H rows in this mode. */

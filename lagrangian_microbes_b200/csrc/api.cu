@@ -442,7 +442,7 @@ static int scatter_windows(const lm_handle_s *h, int arrays)
     if (h->scatter_passes > 0) return h->scatter_passes;
     if (arrays == 0) return 1;
     const int64_t bytes = (int64_t)h->n * 4 * arrays;
-    const int64_t window = 32ll << 20;
+    const int64_t window = 64ll << 20;   // measured: 12.5 M microbes, lon + lat (100 MB): 0.34 ms in one pass, 0.26 in two, 0.36 in four
     return (int)std::max<int64_t>(1, std::min<int64_t>(16, (bytes + window - 1) / window));
 }
 

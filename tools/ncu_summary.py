@@ -29,7 +29,7 @@ hdr, units = rows[0], rows[1]
 ik = hdr.index("Kernel Name")
 acc = collections.OrderedDict()
 for r in rows[2:]:
-    name = r[ik].split("(")[0].replace("void ", "").split("<")[0].replace("lm::", "")
+    name = r[ik].replace("<unnamed>::", "").split("(")[0].replace("void ", "").split("<")[0].replace("lm::", "")
     a = acc.setdefault(name, collections.defaultdict(list))
     for m, key in WANT.items():
         if m in hdr:
