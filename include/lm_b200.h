@@ -153,6 +153,10 @@ int lm_advect_rk4(lm_handle h, float *lon, float *lat, int64_t n, const lm_stage
 /* (A5) lat += U(-1,1)*amp, then lon += U(-1,1)*amp; Philox keyed (seed, step, id = array index). */
 int lm_diffuse(lm_handle h, float *lon, float *lat, int64_t n, double amp_deg, uint64_t seed, uint64_t step,
                void *stream);
+/* The same with explicit particle ids (device int32[n]; NULL = array index): a process that holds only some of the
+ * reference's N_procs tiles (particle_advecter.py:143-148) kicks its particles exactly as one process holding all would. */
+int lm_diffuse_ids(lm_handle h, float *lon, float *lat, const int32_t *ids, int64_t n, double amp_deg, uint64_t seed,
+                   uint64_t step, void *stream);
 /* (P1/P2) All pairs (i<j, array indices) with dx*dx + dy*dy <= r*r evaluated exactly as SciPy does
  * (float32 positions widened to double; other norms: LM_OPT_NORM).  pairs_out int32[cap][2] in unspecified order;
  * *n_pairs_out (device int64) receives the number found; LM_ENOSPC is reported by

@@ -142,6 +142,7 @@ def declare(L):
         "lm_get_grid": (ctypes.c_int, [vp, P(Grid)]),
         "lm_advect_rk4": (ctypes.c_int, [vp, vp, vp, i64, P(StageTimes), flt, vp]),
         "lm_diffuse": (ctypes.c_int, [vp, vp, vp, i64, dbl, u64, u64, vp]),
+        "lm_diffuse_ids": (ctypes.c_int, [vp, vp, vp, vp, i64, dbl, u64, u64, vp]),
         "lm_find_pairs": (ctypes.c_int, [vp, vp, vp, i64, dbl, vp, i64, vp, vp]),
         "lm_interact_rps": (ctypes.c_int, [vp, vp, vp, vp, i64, dbl, P(RpsParams), vp, i64, vp, vp]),
         "lm_pair_uniforms": (ctypes.c_int, [vp, i64, u64, u64, vp, vp]),
@@ -185,7 +186,7 @@ def declare(L):
 
 
 EXPORTS = ["lm_version", "lm_error_string", "lm_last_cuda_error", "lm_create", "lm_destroy", "lm_set_field",
-           "lm_update_field_data", "lm_set_grid", "lm_get_grid", "lm_advect_rk4", "lm_diffuse", "lm_find_pairs", "lm_interact_rps",
+           "lm_update_field_data", "lm_set_grid", "lm_get_grid", "lm_advect_rk4", "lm_diffuse", "lm_diffuse_ids", "lm_find_pairs", "lm_interact_rps",
            "lm_pair_uniforms", "lm_resolve_rps", "lm_state_set", "lm_state_size", "lm_step", "lm_state_get",
            "lm_state_get_host", "lm_host_copies_sync", "lm_state_view", "lm_sync_stats", "lm_reset_stats", "lm_launch_count",
            "lm_phase_times", "lm_strip_alloc", "lm_set_strip", "lm_strip_buffers_get", "lm_strip_peer_export", "lm_strip_peer_connect", "lm_step_push",

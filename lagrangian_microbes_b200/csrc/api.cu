@@ -495,6 +495,15 @@ int lm_diffuse(lm_handle h, float *lon, float *lat, int64_t n, double amp_deg, u
     return LM_OK;
 }
 
+int lm_diffuse_ids(lm_handle h, float *lon, float *lat, const int32_t *ids, int64_t n, double amp_deg, uint64_t seed,
+                   uint64_t step, void *stream)
+{
+    if (!h || !lon || !lat || n < 0 || n > h->max_particles) return LM_EINVAL;
+    LM_CUDA(cudaSetDevice(h->device));
+    LM_CUDA(launch_diffuse(lon, lat, ids, (int)n, amp_deg, seed, step, as_stream(stream), &h->launches));
+    return LM_OK;
+}
+
 int lm_state_set(lm_handle h, const float *lon, const float *lat, const int8_t *species, const int32_t *ids, int64_t n,
                  void *stream)
 {

@@ -143,10 +143,16 @@ class Engine:
         check(self.L.lm_advect_rk4(self.h, _ptr(_f32(lon)), _ptr(_f32(lat, n)), n, ctypes.byref(stage_times),
                                    float(dt), self._stream()), "lm_advect_rk4")
 
-    def diffuse(self, lon, lat, amp_deg, seed, step):
+    def diffuse(self, lon, lat, amp_deg, seed, step, ids=None):
+        """``ids``: CUDA int32 [n] global particle ids keying the kicks (default: the array index)."""
         n = lon.numel()
-        check(self.L.lm_diffuse(self.h, _ptr(_f32(lon)), _ptr(_f32(lat, n)), n, float(amp_deg), int(seed), int(step),
-                                self._stream()), "lm_diffuse")
+        if ids is None:
+            check(self.L.lm_diffuse(self.h, _ptr(_f32(lon)), _ptr(_f32(lat, n)), n, float(amp_deg), int(seed), int(step),
+                                    self._stream()), "lm_diffuse")
+            return
+        assert ids.is_cuda and ids.dtype == torch.int32 and ids.is_contiguous() and ids.numel() == n
+        check(self.L.lm_diffuse_ids(self.h, _ptr(_f32(lon)), _ptr(_f32(lat, n)), _ptr(ids), n, float(amp_deg), int(seed),
+                                    int(step), self._stream()), "lm_diffuse_ids")
 
     def find_pairs(self, lon, lat, r, pairs_out):
         """pairs_out: CUDA int32 (cap, 2).  Returns the number of pairs found (host int, synchronises)."""

@@ -14,8 +14,10 @@ Reference behaviours kept on purpose:
       grid.time[0]); ``start_time`` only labels the output.
   Q2  stored row n holds the state AFTER step n+1 and is labelled ``start_time + (n+1)*dt`` in the
       pickle (:226-235) but ``start_time + n*dt`` in particle_data.nc (:266).
-``N_procs`` keeps its output meaning (number of contiguous particle tiles = pickles per chunk);
-all tiles are advected together on the current CUDA device.
+``N_procs`` keeps its output meaning (number of contiguous particle tiles = pickles per chunk).  In one process all
+tiles are advected together on the current CUDA device; under ``torchrun`` (an initialised ``torch.distributed`` group)
+the tiles are dealt out over the ranks in contiguous blocks -- the reference's joblib workers (particle_advecter.py:143-148)
+become one GPU each, with no communication on the data path, exactly as there.
 """
 import logging
 import os
@@ -59,6 +61,22 @@ def distribute_particles_across_tiles(particle_lons, particle_lats, tiles):
     lons = [particle_lons[i * per_tile:(i + 1) * per_tile] for i in range(tiles)]
     lats = [particle_lats[i * per_tile:(i + 1) * per_tile] for i in range(tiles)]
     return lons, lats
+
+
+def tiles_of_rank(N_tiles, rank, world):
+    """The contiguous block of tiles a rank advects (balanced: sizes differ by at most one; a rank may get none)."""
+    return list(range(N_tiles * rank // world, N_tiles * (rank + 1) // world))
+
+
+def _process_group():
+    """(rank, world, dist) of the initialised torch.distributed group, or (0, 1, None)."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size(), dist
+    except ImportError:
+        pass
+    return 0, 1, None
 
 
 class HostFieldSet:
@@ -164,9 +182,11 @@ class ParticleAdvecter:
         assert velocity_field == "OSCAR", "OSCAR is the only supported velocity field right now."
         assert 1 <= N_procs or N_procs == -1, "Number of processors N_procs must be a positive integer " \
                                               "or -1 (use all processors)."
-        # The reference clamps to joblib.cpu_count() worker processes; here N_procs only fixes the
-        # number of output tiles, all advected on one GPU.  -1 ("all processors") -> one tile.
-        N_procs = N_procs if N_procs >= 1 else 1
+        # The reference clamps to joblib.cpu_count() worker processes (particle_advecter.py:86-94); here a worker is a
+        # GPU: N_procs fixes the number of tiles, dealt out over the ranks of the process group (one process: all
+        # tiles on one GPU).  -1 ("all processors") -> one tile per rank.
+        self.rank, self.world, self._dist = _process_group()
+        N_procs = N_procs if N_procs >= 1 else self.world
 
         particle_lons = np.asarray(particle_lons)
         particle_lats = np.asarray(particle_lats)
@@ -186,6 +206,7 @@ class ParticleAdvecter:
         self.N_particles = N_particles
         self.N_procs = N_procs
         self.particles_per_tile = N_particles // N_procs
+        self.my_tiles = tiles_of_rank(N_procs, self.rank, self.world)
         self.output_dir = output_dir
         self.output_chunk_iters = output_chunk_iters
         self.Kh = Kh / 1e10  # [m^2/s] -> [deg^2/s] assuming 1 deg = 100 km (particle_advecter.py:121)
@@ -203,7 +224,7 @@ class ParticleAdvecter:
         import torch
         from .engine import Engine
         if self._engine is None:
-            self._engine = Engine(max_particles=self.N_particles, max_cells=1 << 16, max_pairs=0)
+            self._engine = Engine(max_particles=max(1, len(self.my_tiles) * self.particles_per_tile), max_cells=1 << 16, max_pairs=0)
         if self._field_year != year:
             fs = HostFieldSet.from_years(year) if isinstance(year, tuple) else HostFieldSet(oscar_dataset(year))
             self._fieldset = fs
@@ -219,6 +240,8 @@ class ParticleAdvecter:
             import joblib
             for pkl_filepath in pkl_files[-self.N_procs:]:
                 _, _, tile_id = lmio.parse_chunk_name(pkl_filepath)
+                if tile_id not in self.my_tiles:
+                    continue
                 chunk = joblib.load(pkl_filepath)
                 self.particle_lons[tile_id] = chunk["lon"][-1, :]
                 self.particle_lats[tile_id] = chunk["lat"][-1, :]
@@ -236,12 +259,19 @@ class ParticleAdvecter:
         else:
             eng = self._ensure_engine(start_time.year)
         dev = eng.device
-        N, per_tile = self.N_particles, self.particles_per_tile
+        per_tile = self.particles_per_tile
+        mine = self.my_tiles
+        N = len(mine) * per_tile                                 # this rank's particles: its tiles, in tile order
         dt_s = dt.total_seconds()
 
         # Parcels casts particle lon/lat to float32 (JITParticle); one fresh particle set per call (Q1)
-        lon = torch.from_numpy(np.concatenate(self.particle_lons).astype(np.float32)).to(dev)
-        lat = torch.from_numpy(np.concatenate(self.particle_lats).astype(np.float32)).to(dev)
+        cat = lambda tiles: np.concatenate([tiles[t] for t in mine]) if mine else np.zeros(0)
+        lon = torch.from_numpy(cat(self.particle_lons).astype(np.float32)).to(dev)
+        lat = torch.from_numpy(cat(self.particle_lats).astype(np.float32)).to(dev)
+        # global particle index of each local one: the diffusion kicks are keyed by it, whoever holds the particle
+        ids = None
+        if self.world > 1 and N:
+            ids = torch.from_numpy(np.concatenate([np.arange(t * per_tile, (t + 1) * per_tile, dtype=np.int32) for t in mine])).to(dev)
         clock = StageClock(self._fieldset.time,
                            t0=self._fieldset.seconds_since_first_snapshot(start_time) if self.calendar_time else None)
         amp = float(np.sqrt(6 * np.fabs(np.float32(dt_s)) * self.Kh))
@@ -263,36 +293,60 @@ class ParticleAdvecter:
             ev0.record()
             eng.reset_stats()
             for n in range(iters_to_do):
-                eng.advect_rk4(lon, lat, clock.next_step(dt_s), dt_s)            # :222-223
+                st = clock.next_step(dt_s)
+                if N:
+                    eng.advect_rk4(lon, lat, st, dt_s)                            # :222-223
                 t = t + dt
                 iteration += 1
                 times[n] = t
                 out_lon[n].copy_(lon, non_blocking=True)                          # :233-235
                 out_lat[n].copy_(lat, non_blocking=True)
-                if self.Kh > 0:
-                    eng.diffuse(lon, lat, amp, self.seed, iteration - 1)          # :240-242
+                if self.Kh > 0 and N:
+                    eng.diffuse(lon, lat, amp, self.seed, iteration - 1, ids=ids)  # :240-242
             ev1.record()
             n_oob = eng.sync_stats().n_out_of_bounds                              # synchronises the stream
+            n_oob = self._sum_over_ranks(n_oob)                                   # every rank raises, or none does
             if n_oob:
                 raise OutOfBoundsError("%d particle-step(s) left the velocity grid in iterations %d..%d"
                                        % (n_oob, start_iter, end_iter))
             logger.info("Advecting + storing particles: {:s}.".format(pretty_time(ev0.elapsed_time(ev1) * 1e-3)))
 
             lon_np, lat_np = out_lon.numpy(), out_lat.numpy()
-            for tile_id in range(self.N_procs):
-                sl = slice(tile_id * per_tile, (tile_id + 1) * per_tile)
+            for k, tile_id in enumerate(mine):
+                sl = slice(k * per_tile, (k + 1) * per_tile)
                 path = os.path.join(self.output_dir, lmio.chunk_pickle_name(start_iter, end_iter, tile_id))
                 logger.info("Dumping intermediate output: {:s}".format(path))
                 lmio.dump_chunk(path, times, np.ascontiguousarray(lat_np[:, sl]), np.ascontiguousarray(lon_np[:, sl]))
 
         # keep the final positions for callers that chain time_step without going through disk
+        # (tiles of other ranks keep their previous values here; the next call restores from the pickles, as the reference does)
         final_lon, final_lat = lon.cpu().numpy(), lat.cpu().numpy()
-        self.particle_lons, self.particle_lats = distribute_particles_across_tiles(final_lon, final_lat, self.N_procs)
+        for k, tile_id in enumerate(mine):
+            self.particle_lons[tile_id] = final_lon[k * per_tile:(k + 1) * per_tile]
+            self.particle_lats[tile_id] = final_lat[k * per_tile:(k + 1) * per_tile]
         iters = (end_time - start_time) // dt
         self.iteration += iters
+        self._barrier()                                          # every tile's pickles are on disk when any rank returns
+
+    def _barrier(self):
+        if self._dist is not None and self.world > 1:
+            self._dist.barrier()
+
+    def _sum_over_ranks(self, value):
+        if self._dist is None or self.world == 1:
+            return int(value)
+        import torch
+        on_gpu = self._dist.get_backend() == "nccl"
+        v = torch.tensor([int(value)], dtype=torch.int64, device=self._engine.device if on_gpu else "cpu")
+        self._dist.all_reduce(v)
+        return int(v.item())
 
     def create_netcdf_file(self, start_time, end_time, dt):
         import joblib
+        self._barrier()
+        if self.rank != 0:                                       # one writer: the merge is rank 0's, as it is the parent's
+            self._barrier()                                      # in the reference (particle_advecter.py:262-307)
+            return
         iters = (end_time - start_time) // dt
         times = [start_time + n * dt for n in range(iters)]
         plons = np.zeros((self.N_particles, iters), dtype=float32)
@@ -310,3 +364,4 @@ class ParticleAdvecter:
         lmio.write_particle_file(nc_filepath, {"longitude": plons, "latitude": plats}, times)
         for pkl_filepath in pkl_files:
             os.remove(pkl_filepath)
+        self._barrier()

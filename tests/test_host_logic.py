@@ -346,3 +346,15 @@ def test_years_concatenate_into_one_calendar_field_and_the_clock_starts_at_start
         assert crossed and clock.ti == 72
     finally:
         velocity_fields.configure_synthetic(kind="random_fourier", seed=0, n_modes=64, rms_speed=0.2)
+
+
+def test_tiles_are_dealt_out_over_ranks_in_contiguous_balanced_blocks():
+    """N_procs tiles (particle_advecter.py:143-148: one joblib worker each) -> one rank (GPU) each, in order."""
+    from lagrangian_microbes_b200.particle_advecter import tiles_of_rank
+    for tiles in (1, 2, 5, 6, 8, 40):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [tiles_of_rank(tiles, r, world) for r in range(world)]
+            assert sum(blocks, []) == list(range(tiles))                          # every tile once, in order
+            sizes = [len(b) for b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    assert tiles_of_rank(6, 1, 4) == [1, 2] and tiles_of_rank(2, 3, 4) == [1] and tiles_of_rank(2, 0, 4) == []
