@@ -577,7 +577,8 @@ def main():
                 sim2.step(record=rec[k & 1])       # record scattered + copied under the step (lm_record_next_step)
             else:
                 sim2.step()
-                sim2.record_to_host()
+                if os.environ.get("LM_E2E_VARIANT", "") != "norecord":    # (measurement only)
+                    sim2.record_to_host()
 
         for k in range(args.warmup):
             e2e_step(k)

@@ -332,6 +332,9 @@ int lm_reset_stats(lm_handle h, void *stream);
  *                     windows so that a window's targets stay in L2 until their sectors are complete (0 = auto: windows of
  *                     about 64 MB; 1 = one pass) */
 #define LM_OPT_SCATTER_PASSES 19
+/*   LM_OPT_RECORD_DEBUG  MEASUREMENT ONLY (the record is then incomplete): bit 0 leaves out the D2H copies of the in-step
+ *                     record, bit 1 the scatter to id order -- what each costs the end-to-end loop (tools/scatter_probe.py) */
+#define LM_OPT_RECORD_DEBUG 20
 /* tile of the fused interaction pass, in cells: part of the definition of its canonical pair order.  Strip boundaries
  * (lm_set_strip) must sit on multiples of LM_TILE_H rows in this mode. */
 #define LM_TILE_W 32

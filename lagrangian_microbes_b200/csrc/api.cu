@@ -86,6 +86,7 @@ int lm_destroy(lm_handle h)
     if (h->ev_pos_ready) cudaEventDestroy(h->ev_pos_ready);
     if (h->ev_pos_scattered) cudaEventDestroy(h->ev_pos_scattered);
     if (h->ev_sp_ready) cudaEventDestroy(h->ev_sp_ready);
+    if (h->ev_sp_scattered) cudaEventDestroy(h->ev_sp_scattered);
     cudaFree(h->cell_cursor); cudaFree(h->block_sums); cudaFree(h->ctr); cudaFree(h->head);
     cudaFree(h->pending_cnt);
     cudaFree(h->hits); cudaFree(h->rec); cudaFree(h->rec2);
@@ -109,6 +110,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     if (!out || max_particles <= 0 || max_cells <= 0 || max_pairs < 0) return LM_EINVAL;
     if (max_particles >= (1ll << 31) - 64 || max_cells >= (1ll << 31) - 64) return LM_EINVAL;
     if (max_pairs > 0 && max_particles >= (1ll << 29)) return LM_EINVAL;     // staged hits carry a 29-bit partner index
+    if (max_pairs >= (1ll << 32) - 8) return LM_EINVAL;                      // 32-bit entry offsets
     *out = nullptr;
     LM_CUDA(cudaSetDevice(device));
     lm_handle h = new (std::nothrow) lm_handle_s();
@@ -140,10 +142,10 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     h->tile_rec_cap = 0;
     h->tile_path = 0;
     h->scatter_passes = 0;
+    h->record_debug = 0;
     h->resolve_tile_smem = 32768;
     h->resolve_batch = 4;      // measured on B200 (profiles/r1y_sweep_resolve.jsonl): 4 beats 1 and 8 on every workload
     ok = ok && dev_alloc(&h->cell_cursor, max_cells) && dev_alloc(&h->block_sums, max_cells / 4096 + 2);
-    if (max_pairs >= (1ll << 32) - 8) return (delete h, LM_EINVAL);          // 32-bit entry offsets
     ok = ok && dev_alloc(&h->hits, max_pairs + 4);
     if (max_pairs > 0) ok = ok && dev_alloc(&h->rec, 5 * max_cells) && dev_alloc(&h->rec2, 5 * (max_particles / 32 + 2));
     ok = ok && dev_alloc(&h->ctr, 1) && dev_alloc(&h->head, max_particles) && dev_alloc(&h->pending_cnt, 4);
@@ -158,6 +160,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_pos_ready, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_pos_scattered, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_sp_ready, cudaEventDisableTiming) == cudaSuccess;
+    if (ok) ok = cudaEventCreateWithFlags(&h->ev_sp_scattered, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaMemset(h->n_pairs_snap, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && dev_alloc(&h->sticky, 1);
     // hybrid mode: queues of heavy units, per phase; a heavy unit needs >= 17 microbes in two cells, so N / 8 per phase is ample
@@ -712,6 +715,9 @@ int lm_step_bin(lm_handle h, void *stream)
             h->n_moved_in = n_arr;
         }
         const int d = c ^ 1;
+        // buffers [d] held the state two steps ago: a species record of that step (scattered on the copy stream, behind its
+        // position copies) may still be reading them when no record of the step in between orders the streams (stride >= 2)
+        if (h->sp_scatter_age > 0 && --h->sp_scatter_age == 0) LM_CUDA(cudaStreamWaitEvent(s, h->ev_sp_scattered, 0));
         LM_CUDA(launch_bin_finish(h, h->lon[c], h->lat[c], h->sp[c], h->id[c], n_in, n_out, h->lon[d], h->lat[d],
                                   h->sp[d], h->id[d], s));
         h->cur = c = d;
@@ -730,13 +736,16 @@ int lm_step_bin(lm_handle h, void *stream)
         const size_t nn = (size_t)h->n;
         LM_CUDA(cudaEventRecord(h->ev_pos_ready, s));
         LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_pos_ready, 0));
-        LM_CUDA(launch_scatter_by_id(h->lon[c], h->lat[c], nullptr, h->id[c], (int)nn, h->rec_lon_host ? h->stage_lon[k] : nullptr,
-                                     h->rec_lat_host ? h->stage_lat[k] : nullptr, nullptr, h->copy_stream, &h->launches,
-                                     scatter_windows(h, (h->rec_lon_host ? 1 : 0) + (h->rec_lat_host ? 1 : 0)), (int)nn));
+        if (!(h->record_debug & 2))
+            LM_CUDA(launch_scatter_by_id(h->lon[c], h->lat[c], nullptr, h->id[c], (int)nn, h->rec_lon_host ? h->stage_lon[k] : nullptr,
+                                         h->rec_lat_host ? h->stage_lat[k] : nullptr, nullptr, h->copy_stream, &h->launches,
+                                         scatter_windows(h, (h->rec_lon_host ? 1 : 0) + (h->rec_lat_host ? 1 : 0)), (int)nn));
         LM_CUDA(cudaEventRecord(h->ev_pos_scattered, h->copy_stream));
         h->pos_scatter_pending = true;
-        if (h->rec_lon_host) LM_CUDA(cudaMemcpyAsync(h->rec_lon_host, h->stage_lon[k], nn * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
-        if (h->rec_lat_host) LM_CUDA(cudaMemcpyAsync(h->rec_lat_host, h->stage_lat[k], nn * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+        if (!(h->record_debug & 1)) {
+            if (h->rec_lon_host) LM_CUDA(cudaMemcpyAsync(h->rec_lon_host, h->stage_lon[k], nn * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+            if (h->rec_lat_host) LM_CUDA(cudaMemcpyAsync(h->rec_lat_host, h->stage_lat[k], nn * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+        }
     }
     // the halo is only needed by (and only sized for) interacting steps; routing passes skip it
     if (h->has_south && (h->step_flags & LM_STEP_INTERACT)) LM_CUDA(launch_ghost_pack(h, h->lon[c], h->lat[c], h->id[c], s));
@@ -837,9 +846,13 @@ int lm_step_finish(lm_handle h, void *stream)
                 LM_CUDA(cudaEventRecord(h->ev_sp_ready, s));
                 LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_sp_ready, 0));
             }
-            LM_CUDA(launch_scatter_by_id(nullptr, nullptr, h->sp[c], h->id[c], n, nullptr, nullptr, h->stage_sp[k], h->copy_stream,
-                                         &h->launches));
-            LM_CUDA(cudaMemcpyAsync(h->rec_sp_host, h->stage_sp[k], (size_t)n, cudaMemcpyDeviceToHost, h->copy_stream));
+            if (!(h->record_debug & 2))
+                LM_CUDA(launch_scatter_by_id(nullptr, nullptr, h->sp[c], h->id[c], n, nullptr, nullptr, h->stage_sp[k], h->copy_stream,
+                                             &h->launches));
+            LM_CUDA(cudaEventRecord(h->ev_sp_scattered, h->copy_stream));
+            h->sp_scatter_age = 2;
+            if (!(h->record_debug & 1))
+                LM_CUDA(cudaMemcpyAsync(h->rec_sp_host, h->stage_sp[k], (size_t)n, cudaMemcpyDeviceToHost, h->copy_stream));
         }
         LM_CUDA(cudaEventRecord(h->ev_copied[k], h->copy_stream));
         h->rec_active = false;
@@ -1058,6 +1071,10 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
         case LM_OPT_HEAVY_MIN:
             if (value < 0 || value > (1ll << 40)) return LM_EINVAL;
             h->heavy_min = value;
+            return LM_OK;
+        case LM_OPT_RECORD_DEBUG:
+            if (value < 0 || value > 3) return LM_EINVAL;
+            h->record_debug = (int)value;
             return LM_OK;
         case LM_OPT_SCATTER_PASSES:
             if (value < 0 || value > 64) return LM_EINVAL;

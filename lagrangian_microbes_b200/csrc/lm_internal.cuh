@@ -108,6 +108,7 @@ struct lm_handle_s {
     int2 *heavy_list;      // [9 phases][2: warp units | CTA units][heavy_cap] (anchor cell, other cell) queued by the pair search
     unsigned int *heavy_cnt;   // [9][4] queued warp units | queued CTA units | warp ticket | CTA ticket
     int64_t heavy_cap;
+    int record_debug;      // LM_OPT_RECORD_DEBUG (measurement only)
     int scatter_passes;    // LM_OPT_SCATTER_PASSES: id windows of the record scatter (0 = auto, see scatter_windows)
     int64_t heavy_min;     // LM_OPT_HEAVY_MIN: candidate pairs above which a unit is heavy in the hybrid mode (0 = default, 1024: part of the
                            // definition of the cell-round order; other values are for A/B measurements)
@@ -152,7 +153,8 @@ struct lm_handle_s {
     int8_t *rec_sp_host;
     bool rec_armed, rec_active;      // armed: next step records; active: this step is recording
     int rec_slot;
-    cudaEvent_t ev_pos_ready, ev_pos_scattered, ev_sp_ready;
+    cudaEvent_t ev_pos_ready, ev_pos_scattered, ev_sp_ready, ev_sp_scattered;
+    int sp_scatter_age;              // 2 after a species record was scattered: the re-binning two steps later waits for ev_sp_scattered
     bool pos_scatter_pending;        // the in-place advection of the next step must wait for ev_pos_scattered
     int64_t launches;
     // ---- latitude-strip decomposition (lm_strip_alloc / lm_set_strip); all zero for a single GPU

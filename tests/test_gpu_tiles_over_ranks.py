@@ -64,7 +64,7 @@ def test_tiles_over_ranks_equal_one_process(tmp_path, world, kh):
     run_advecter(out_1, kh)
     a = lmio.read_particle_file(os.path.join(out_w, "particle_data.nc"))
     b = lmio.read_particle_file(os.path.join(out_1, "particle_data.nc"))
-    assert a["longitude"].shape == (N, 8)
+    assert a["longitude"].shape == (N, 9)
     assert np.array_equal(a["longitude"], b["longitude"]) and np.array_equal(a["latitude"], b["latitude"])
     # the tiles moved (and, with Kh > 0, were kicked)
     assert np.abs(a["longitude"][:, -1] - a["longitude"][:, 0]).max() > 1e-4

@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round 2, two GPUs: tiles-over-ranks + strips tests, and what the strip record costs the end-to-end loop at N = 2
+# (full record | staged but not copied to the host | no record).
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+O=gpurun_out/r2q
+mkdir -p $O
+python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
+timeout 900 python -m pytest tests/test_gpu_tiles_over_ranks.py tests/test_gpu_strips.py -x -q -m gpu > $O/pytest_2gpu.log 2>&1; tail -3 $O/pytest_2gpu.log
+for v in full nocopy norecord; do
+  LM_E2E_VARIANT=$v timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+      bench.py --gpus 2 --steps 40 --warmup 5 --no-parity > $O/bench_n2_$v.json 2>$O/bench_n2_$v.err
+  python -c "
+import json,sys
+d=json.loads(open('$O/bench_n2_$v.json').read().strip().splitlines()[-1]); print('$v', d['ms_per_step'], d['e2e'])"
+done
+ls -la $O

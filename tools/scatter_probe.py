@@ -67,6 +67,30 @@ def e2e(passes, mode, steps=60):
     return ms
 
 
+def e2e_debug(debug, mode="full", steps=60):
+    """The e2e loop with parts of the record left out (LM_OPT_RECORD_DEBUG): 1 = no D2H copies, 2 = no scatter."""
+    sim = new_sim()
+    sim.engine.set_option(_lib.LM_OPT_RECORD_DEBUG, debug)
+    rec = [(torch.empty(n, dtype=torch.float32).pin_memory(), torch.empty(n, dtype=torch.float32).pin_memory(),
+            torch.empty(n, dtype=torch.int8).pin_memory()) for _ in range(2)]
+    for k in range(6):
+        sim.step(record=rec[k & 1])
+    sim.engine.host_copies_sync(); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(steps):
+        sim.step(record=rec[k & 1])
+    sim.engine.host_copies_sync(); sim.engine.join(); torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3 / steps
+    sim.engine.close()
+    return ms
+
+
+if len(sys.argv) > 2 and sys.argv[2] == "decompose":
+    print(json.dumps({"probe": "e2e loop", "record": "none", "ms_per_step": round(e2e(0, "none"), 4)}), flush=True)
+    for debug, what in ((0, "scatter + D2H (the record)"), (1, "scatter only, no D2H"), (2, "D2H only, no scatter"), (3, "neither (events only)")):
+        print(json.dumps({"probe": "e2e loop, parts of the record", "what": what, "ms_per_step": round(e2e_debug(debug), 4)}), flush=True)
+    sys.exit(0)
+
 sim = new_sim()
 for _ in range(4):
     sim.step()
@@ -77,6 +101,6 @@ for what in ("lon+lat", "lon", "species", "all"):
 sim.engine.close()
 del sim
 print(json.dumps({"probe": "e2e loop", "record": "none", "ms_per_step": round(e2e(1, "none"), 4)}), flush=True)
-for passes in (1, 2, 4, 8):
+for passes in (0, 1, 2):
     for mode in ("pos", "full"):
         print(json.dumps({"probe": "e2e loop", "record": mode, "passes": passes, "ms_per_step": round(e2e(passes, mode), 4)}), flush=True)
