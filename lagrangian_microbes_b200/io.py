@@ -80,8 +80,59 @@ def write_particle_file(filepath, variables, times):
     return d
 
 
+HDF5_MAGIC = b"\x89HDF\r\n\x1a\n"
+
+
+def _read_netcdf4(filepath):
+    """particle_data.nc / microbe_data.nc as the REFERENCE writes them when netCDF4 is installed next to xarray
+    (``xarray.Dataset.to_netcdf``: NetCDF-4 = HDF5; particle_advecter.py:300-305, interaction_simulator.py:119-121).
+    SciPy reads NetCDF-3 only, so these go through whichever HDF5 reader the environment has."""
+    try:
+        import netCDF4
+    except ImportError:
+        netCDF4 = None
+    if netCDF4 is not None:
+        with netCDF4.Dataset(filepath, "r") as nc:
+            nc.set_auto_mask(False)
+            names = [k for k in nc.variables if k not in ("particle number", "time")]
+            variables = {k: np.ascontiguousarray(nc.variables[k][:]) for k in names}
+            return variables, np.array(nc.variables["time"][:], dtype=np.float64), str(nc.variables["time"].units)
+    try:
+        import h5py
+    except ImportError:
+        h5py = None
+    if h5py is not None:
+        with h5py.File(filepath, "r") as f:
+            names = [k for k in f.keys() if k not in ("particle number", "time")]
+            variables = {k: np.ascontiguousarray(f[k][...]) for k in names}
+            units = f["time"].attrs["units"]
+            return variables, np.array(f["time"][...], dtype=np.float64), units.decode() if isinstance(units, bytes) else str(units)
+    raise OSError("%s is a NetCDF-4 (HDF5) file -- what xarray writes when netCDF4 is installed -- and neither netCDF4 nor "
+                  "h5py is importable here; convert it with `nccopy -k classic` (or xarray's to_netcdf(format="
+                  "'NETCDF3_64BIT')), or install one of the two readers" % filepath)
+
+
+def _parse_time_units(units):
+    """'<unit> since <origin>' of a CF time axis -> (seconds per unit, origin)."""
+    unit, _, origin = units.partition(" since ")
+    scale = {"seconds": 1.0, "second": 1.0, "minutes": 60.0, "hours": 3600.0, "hour": 3600.0, "days": 86400.0, "day": 86400.0}[unit.strip()]
+    origin = origin.strip().replace("T", " ")
+    for fmt in ("%Y-%m-%d %H:%M:%S.%f", "%Y-%m-%d %H:%M:%S", "%Y-%m-%d %H:%M", "%Y-%m-%d"):
+        try:
+            return scale, datetime.strptime(origin, fmt)
+        except ValueError:
+            pass
+    raise ValueError("time units not understood: %r" % units)
+
+
 def read_particle_file(filepath):
     if os.path.isfile(filepath):
+        with open(filepath, "rb") as f:
+            magic = f.read(8)
+        if magic == HDF5_MAGIC:
+            variables, secs, units = _read_netcdf4(filepath)
+            scale, t0 = _parse_time_units(units)
+            return ParticleFile(variables, [t0 + timedelta(seconds=float(s) * scale) for s in secs])
         from scipy.io import netcdf_file
         with netcdf_file(filepath, "r", mmap=False) as nc:
             names = [k for k in nc.variables if k not in ("particle number", "time")]

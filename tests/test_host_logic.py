@@ -358,3 +358,27 @@ def test_tiles_are_dealt_out_over_ranks_in_contiguous_balanced_blocks():
             sizes = [len(b) for b in blocks]
             assert max(sizes) - min(sizes) <= 1
     assert tiles_of_rank(6, 1, 4) == [1, 2] and tiles_of_rank(2, 3, 4) == [1] and tiles_of_rank(2, 0, 4) == []
+
+
+def test_netcdf4_files_of_the_reference_are_recognised(tmp_path):
+    """xarray.to_netcdf writes NetCDF-4 (HDF5) when netCDF4 is installed (particle_advecter.py:300-305): such a file is
+    detected by its signature and read through netCDF4 / h5py when present, else refused with a message that says what
+    it is -- not passed to SciPy's NetCDF-3 reader."""
+    from lagrangian_microbes_b200 import io as lmio
+    p = tmp_path / "particle_data.nc"
+    p.write_bytes(lmio.HDF5_MAGIC + b"\0" * 64)
+    try:
+        import netCDF4  # noqa: F401
+        have = True
+    except ImportError:
+        try:
+            import h5py  # noqa: F401
+            have = True
+        except ImportError:
+            have = False
+    if not have:
+        with pytest.raises(OSError, match="NetCDF-4"):
+            lmio.read_particle_file(str(p))
+    assert lmio._parse_time_units("seconds since 2017-01-01 00:00:00") == (1.0, datetime(2017, 1, 1))
+    assert lmio._parse_time_units("hours since 2017-01-01T06:00:00") == (3600.0, datetime(2017, 1, 1, 6))
+    assert lmio._parse_time_units("days since 1992-10-05") == (86400.0, datetime(1992, 10, 5))
