@@ -565,6 +565,8 @@ def main():
             packer = DeltaRecordPacker(n_per_gpu)
             lon_d = torch.empty(n_per_gpu, dtype=torch.float32, device="cuda"); lat_d = torch.empty_like(lon_d)
 
+        host_in_record = []
+
         def e2e_step(k):
             if packer is not None:
                 sim2.step()
@@ -575,10 +577,16 @@ def main():
                 sim2.engine.state_get_host(None, None, rec[k & 1][2])
             elif world == 1:
                 sim2.step(record=rec[k & 1])       # record scattered + copied under the step (lm_record_next_step)
-            else:
+            elif os.environ.get("LM_E2E_VARIANT", "") == "after":         # (measurement only: the record issued after the step)
                 sim2.step()
-                if os.environ.get("LM_E2E_VARIANT", "") != "norecord":    # (measurement only)
-                    sim2.record_to_host()
+                th = time.perf_counter()
+                sim2.record_to_host()
+                host_in_record.append(time.perf_counter() - th)
+            elif os.environ.get("LM_E2E_VARIANT", "") == "norecord":      # (measurement only)
+                sim2.step()
+            else:
+                sim2.k ^= 1
+                sim2.ss.step(record=sim2.k)        # the strip's record copied inside the step (lm_record_next_step_ids)
 
         for k in range(args.warmup):
             e2e_step(k)
@@ -610,9 +618,17 @@ def main():
             lon_chk = sim2.download()[0]
         elif world == 1:
             lon_chk = rec[(args.steps - 1) & 1][0].numpy()
+        elif os.environ.get("LM_E2E_VARIANT", "") == "":
+            lon_chk = sim2.ss.record_view(sim2.k)[1]
+            assert lon_chk.size == sim2.engine.state_size()
         else:
-            lon_chk = sim2.ss._record["host"][1][sim2.k][:sim2.engine.state_size()].numpy()
-        assert np.isfinite(lon_chk).all() and lon_chk.min() > 100.0
+            lon_chk = None
+        if lon_chk is not None:
+            assert np.isfinite(lon_chk).all() and lon_chk.min() > 100.0
+        if world > 1 and sim2.ss._record is not None and sim2.ss._record.get("timing"):
+            tm = sim2.ss._record["timing"][-args.steps:]
+            e2e["record_d2h_ms_on_its_stream"] = float(np.mean([a.elapsed_time(b) for a, b in tm]))
+            e2e["host_ms_inside_record_to_host"] = 1e3 * float(np.mean(host_in_record[-args.steps:]))
         sim = sim2
 
     # max over ranks
@@ -693,6 +709,9 @@ def main():
     if e2e:
         line["e2e"] = {"value": n_total * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": ms_e2e / args.steps}
+        for key in ("record_d2h_ms_on_its_stream", "host_ms_inside_record_to_host"):
+            if key in e2e:
+                line["e2e"][key] = e2e[key]
         if "record" in e2e:
             line["e2e"]["record"] = e2e["record"]
     if world == 1 and not args.no_cpu_baseline and not interact_only:

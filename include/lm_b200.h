@@ -236,6 +236,14 @@ int lm_state_get_host(lm_handle h, float *lon_host, float *lat_host, int8_t *spe
  * (particle_advecter.py:233-235, interaction_simulator.py:108-110).  Complete after lm_host_copies_sync; alternate
  * two sets of buffers.  Single handle only (strips: lm_state_view + the ids). */
 int lm_record_next_step(lm_handle h, float *lon_host, float *lat_host, int8_t *species_host);
+/* The same for a handle that holds ANY subset of the particles (a latitude strip): the record of the next step in STORAGE
+ * order with the particle ids beside it -- ids_host int32, lon_host / lat_host float32 (optional), species_host int8
+ * (optional), pinned, each with room for the handle's max_particles.  Positions and ids are copied under the pair search,
+ * species after the RPS phases, all on the library's copy stream (lm_host_copies_sync); lm_record_count = the number of
+ * particles of the last such record (known when lm_step_bin has returned).  What a per-strip output file holds, like the
+ * reference's per-tile chunk pickles (particle_advecter.py:201-214). */
+int lm_record_next_step_ids(lm_handle h, int32_t *ids_host, float *lon_host, float *lat_host, int8_t *species_host);
+int64_t lm_record_count(lm_handle h);
 /* Wait for every D2H copy issued by lm_state_get_host (they run on an internal copy stream so
  * that the next step's kernels overlap them; up to two may be in flight). */
 int lm_host_copies_sync(lm_handle h);

@@ -164,6 +164,8 @@ def declare(L):
         "lm_state_get": (ctypes.c_int, [vp, vp, vp, vp, vp]),
         "lm_state_get_host": (ctypes.c_int, [vp, vp, vp, vp, vp]),
         "lm_record_next_step": (ctypes.c_int, [vp, vp, vp, vp]),
+        "lm_record_next_step_ids": (ctypes.c_int, [vp, vp, vp, vp, vp]),
+        "lm_record_count": (ctypes.c_int64, [vp]),
         "lm_host_copies_sync": (ctypes.c_int, [vp]),
         "lm_state_view": (ctypes.c_int, [vp, P(vp), P(vp), P(vp), P(vp), P(vp)]),
         "lm_sync_stats": (ctypes.c_int, [vp, P(Stats), vp]),
@@ -191,7 +193,7 @@ EXPORTS = ["lm_version", "lm_error_string", "lm_last_cuda_error", "lm_create", "
            "lm_state_get_host", "lm_host_copies_sync", "lm_state_view", "lm_sync_stats", "lm_reset_stats", "lm_launch_count",
            "lm_phase_times", "lm_strip_alloc", "lm_set_strip", "lm_strip_buffers_get", "lm_strip_peer_export", "lm_strip_peer_connect", "lm_step_push",
            "lm_step_move", "lm_step_bin",
-           "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option", "lm_join", "lm_record_next_step",
+           "lm_step_interact_begin", "lm_step_interact_end", "lm_step_finish", "lm_set_option", "lm_join", "lm_record_next_step", "lm_record_next_step_ids", "lm_record_count",
            "lm_pair_distance_hist", "lm_rasterize", "lm_compose_frame", "lm_record_delta_pack",
            "lm_record_delta_unpack_host"]
 

@@ -639,7 +639,8 @@ int lm_step_move(lm_handle h, int32_t flags, const lm_stage_times *st, float dt,
         LM_CUDA(cudaStreamWaitEvent(s, h->ev_pos_scattered, 0));
         h->pos_scatter_pending = false;
     }
-    h->rec_active = h->rec_armed && !in_strip_mode(h);
+    h->rec_active = h->rec_armed && (h->rec_ids_host || !in_strip_mode(h));
+    h->rec_by_ids = h->rec_active && h->rec_ids_host != nullptr;
     h->rec_armed = false;
     const int c = h->cur;
     bool moved = false;
@@ -728,7 +729,26 @@ int lm_step_bin(lm_handle h, void *stream)
         if ((d ? h->has_north : h->has_south) && h->peer[d].connected)
             LM_CUDA(launch_peer_signal(h->peer[d].flags + 5 + (d == 0 ? 1 : 0), h->xseq, s, &h->launches));
     if (h->step_flags & LM_STEP_TIMING) LM_CUDA(cudaEventRecord(h->ev_phase[2], s));
-    if (h->rec_active) {
+    if (h->rec_active && h->rec_by_ids) {
+        // the record in STORAGE order with the ids beside it (strips: the owned particles of this strip).  lon / lat are
+        // advected in place by the next step, so they are staged (device to device, on the copy stream); ids and species
+        // stay where they are until the re-binning two steps on (sp_scatter_age) and are copied from there.
+        const int k = h->rec_slot = h->stage_idx;
+        h->stage_idx = k ^ 1;
+        const size_t nn = (size_t)h->n;
+        LM_CUDA(cudaEventRecord(h->ev_pos_ready, s));
+        LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_pos_ready, 0));
+        if (nn && h->rec_lon_host) LM_CUDA(cudaMemcpyAsync(h->stage_lon[k], h->lon[c], nn * sizeof(float), cudaMemcpyDeviceToDevice, h->copy_stream));
+        if (nn && h->rec_lat_host) LM_CUDA(cudaMemcpyAsync(h->stage_lat[k], h->lat[c], nn * sizeof(float), cudaMemcpyDeviceToDevice, h->copy_stream));
+        LM_CUDA(cudaEventRecord(h->ev_pos_scattered, h->copy_stream));
+        h->pos_scatter_pending = true;
+        if (nn && !(h->record_debug & 1)) {
+            LM_CUDA(cudaMemcpyAsync(h->rec_ids_host, h->id[c], nn * sizeof(int32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+            if (h->rec_lon_host) LM_CUDA(cudaMemcpyAsync(h->rec_lon_host, h->stage_lon[k], nn * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+            if (h->rec_lat_host) LM_CUDA(cudaMemcpyAsync(h->rec_lat_host, h->stage_lat[k], nn * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+        h->rec_count = (int64_t)nn;
+    } else if (h->rec_active) {
         // positions and ids of this step are final: scatter them to id order and send them to the host on the copy
         // stream, under the pair search (which only reads them)
         const int k = h->rec_slot = h->stage_idx;
@@ -840,7 +860,19 @@ int lm_step_finish(lm_handle h, void *stream)
         // species after this step's interactions (interaction_simulator.py:108-110): after the RPS phases, wherever
         // they run; the copy stream does not hold up the caller's stream
         const int k = h->rec_slot;
-        if (h->rec_sp_host) {
+        if (h->rec_by_ids) {
+            if (h->rec_sp_host && n > 0) {
+                if (h->resolve_pending) LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_resolve_done, 0));
+                else {
+                    LM_CUDA(cudaEventRecord(h->ev_sp_ready, s));
+                    LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_sp_ready, 0));
+                }
+                if (!(h->record_debug & 1))
+                    LM_CUDA(cudaMemcpyAsync(h->rec_sp_host, h->sp[c], (size_t)n, cudaMemcpyDeviceToHost, h->copy_stream));
+            }
+            LM_CUDA(cudaEventRecord(h->ev_sp_scattered, h->copy_stream));      // ids and species of buffers [c] have been read
+            h->sp_scatter_age = 2;
+        } else if (h->rec_sp_host) {
             if (h->resolve_pending) LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_resolve_done, 0));
             else {
                 LM_CUDA(cudaEventRecord(h->ev_sp_ready, s));
@@ -924,9 +956,21 @@ int lm_record_next_step(lm_handle h, float *lon_host, float *lat_host, int8_t *s
     if (!h) return LM_EINVAL;
     if (h->has_south || h->has_north) return LM_ESTATE;      // strips: ids travel with the record, see lm_state_view
     h->rec_lon_host = lon_host; h->rec_lat_host = lat_host; h->rec_sp_host = species_host;
+    h->rec_ids_host = nullptr;
     h->rec_armed = lon_host || lat_host || species_host;
     return LM_OK;
 }
+
+int lm_record_next_step_ids(lm_handle h, int32_t *ids_host, float *lon_host, float *lat_host, int8_t *species_host)
+{
+    if (!h || !ids_host) return LM_EINVAL;
+    h->rec_lon_host = lon_host; h->rec_lat_host = lat_host; h->rec_sp_host = species_host;
+    h->rec_ids_host = ids_host;
+    h->rec_armed = true;
+    return LM_OK;
+}
+
+int64_t lm_record_count(lm_handle h) { return h ? h->rec_count : -1; }
 
 int lm_host_copies_sync(lm_handle h)
 {

@@ -151,6 +151,9 @@ struct lm_handle_s {
     // per-step record requested for the next step (lm_record_next_step): scattered + copied on copy_stream
     float *rec_lon_host, *rec_lat_host;
     int8_t *rec_sp_host;
+    int32_t *rec_ids_host;           // lm_record_next_step_ids: the record in storage order, ids beside it
+    bool rec_by_ids;
+    int64_t rec_count;               // particles in the last record by ids
     bool rec_armed, rec_active;      // armed: next step records; active: this step is recording
     int rec_slot;
     cudaEvent_t ev_pos_ready, ev_pos_scattered, ev_sp_ready, ev_sp_scattered;

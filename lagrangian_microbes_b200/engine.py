@@ -279,6 +279,18 @@ class Engine:
             assert t is None or (not t.is_cuda and t.is_pinned() and t.is_contiguous())
         check(self.L.lm_record_next_step(self.h, _ptr(lon_host), _ptr(lat_host), _ptr(species_host)), "lm_record_next_step")
 
+    def record_next_step_ids(self, ids_host, lon_host=None, lat_host=None, species_host=None):
+        """Arm the next step to write its record in STORAGE order with the particle ids beside it (pinned CPU tensors with
+        room for max_particles): the form that works for a latitude strip.  ``record_count()`` particles were written."""
+        for t in (ids_host, lon_host, lat_host, species_host):
+            assert t is None or (not t.is_cuda and t.is_pinned() and t.is_contiguous() and t.numel() >= self.max_particles)
+        assert ids_host is not None and ids_host.dtype == torch.int32
+        check(self.L.lm_record_next_step_ids(self.h, _ptr(ids_host), _ptr(lon_host), _ptr(lat_host), _ptr(species_host)),
+              "lm_record_next_step_ids")
+
+    def record_count(self):
+        return int(self.L.lm_record_count(self.h))
+
     def host_copies_sync(self):
         check(self.L.lm_host_copies_sync(self.h), "lm_host_copies_sync")
 

@@ -332,6 +332,9 @@ class StripSet:
             from .simulation import FieldWindowStreamer
             self.streamer = FieldWindowStreamer(fieldset, [s.engine for s in self.strips])
         self._record = None
+        self._record_pinned = None
+        self._record_slot_count = [None, None]
+        self._record_last = None
         if getattr(transport, "peer", False):
             transport.connect(self.strips)
         self._apply_edges()
@@ -449,7 +452,24 @@ class StripSet:
         return self.edges
 
     # ---- stepping -----------------------------------------------------------------------------------
-    def step(self, check=False, timing=False):
+    def _record_buffers(self):
+        if self._record_pinned is None:
+            cap = self.strips[0].engine.max_particles
+            pin = lambda dt: [torch.empty(cap, dtype=dt).pin_memory() for _ in range(2)]
+            self._record_pinned = [pin(torch.int32), pin(torch.float32), pin(torch.float32), pin(torch.int8)]
+        return self._record_pinned
+
+    def step(self, check=False, timing=False, record=None):
+        """One step of every local strip.  ``record`` = 0 / 1: the FIRST local strip writes this step's record -- (ids, lon,
+        lat, species) of its owned particles in storage order, what a per-strip output file holds, like the reference's
+        per-tile chunk pickles (particle_advecter.py:201-214) -- into slot ``record`` of two sets of pinned host buffers,
+        inside the step: positions and ids are copied under the pair search, species after the RPS phases, on the
+        library's copy stream (lm_record_next_step_ids).  ``record_view(slot)`` after ``host_copies_sync()``."""
+        if record is not None:
+            bufs = self._record_buffers()
+            self.strips[0].engine.record_next_step_ids(*(b[record] for b in bufs))
+            self._record_slot_count[record] = None
+            self._record_last = record
         flags = 0
         st_times = None
         win = None
@@ -472,6 +492,8 @@ class StripSet:
         if check or regrid_now:
             flags |= _lib.LM_STEP_STATS
         self._staged(flags, st_times)
+        if record is not None:
+            self._record_slot_count[record] = self.strips[0].engine.record_count()
         if win is not None:
             self.streamer.release(win)
         out = None
@@ -538,17 +560,31 @@ class StripSet:
             R["stage"][k][slot][:n].copy_(src[:n], non_blocking=True)
         staged = torch.cuda.Event()
         staged.record(cur)
+        timing = os.environ.get("LM_RECORD_TIMING", "") == "1"      # (measurement only: how long the copies take on their stream)
         with torch.cuda.stream(R["stream"]):
             R["stream"].wait_event(staged)
+            if timing:
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                t0.record(R["stream"])
             if os.environ.get("LM_E2E_VARIANT", "") != "nocopy":          # (measurement only: the record without its D2H copies)
                 for k in range(4):
                     R["host"][k][slot][:n].copy_(R["stage"][k][slot][:n], non_blocking=True)
+            if timing:
+                t1.record(R["stream"])
+                R.setdefault("timing", []).append((t0, t1))
             R["copied"][slot].record(R["stream"])
         return n
+
+    def record_view(self, slot):
+        """(ids, lon, lat, species) NumPy views of record slot ``slot`` (valid until that slot is armed again)."""
+        n = self._record_slot_count[slot]
+        return tuple(b[slot][:n].numpy() for b in self._record_pinned)
 
     def host_copies_sync(self):
         if self._record is not None:
             self._record["stream"].synchronize()
+        if self._record_pinned is not None:
+            self.strips[0].engine.host_copies_sync()
 
     def gather(self):
         """Global (lon, lat, species) in particle-id order on every process (the reference's per-step record,

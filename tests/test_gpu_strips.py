@@ -103,6 +103,62 @@ def test_strips_on_one_device_equal_single_handle(G, clustered, peer):
     ss.close()
 
 
+@pytest.mark.parametrize("peer", [False, True])
+def test_in_step_record_of_a_strip(peer):
+    """StripSet.step(record=slot): (ids, lon, lat, species) of the first strip's owned microbes, copied inside the step on
+    the library's copy stream (lm_record_next_step_ids) -- equal to the state read back after the step, on steps with
+    and without a record in between (the re-binning two steps on must wait for a lagging species copy)."""
+    from lagrangian_microbes_b200.strips import LocalPeerTransport, LocalTransport, StripSet
+    G, n, seed = 3, 50000, 5
+    fs = small_fs()
+    lon, lat, sp = particles(n, seed, clustered=True)
+    ids = np.arange(n, dtype=np.int32)
+    cut = [slice(g, n, G) for g in range(G)]
+    ss = StripSet((LocalPeerTransport if peer else LocalTransport)(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
+                  [ids[c] for c in cut], n, R, *P, fs, seed=seed, local_strips=list(range(G)), slack=3.0,
+                  pairs_per_particle=40 * G, grid_margin=0.25, regrid_every=4)
+    sim = single(lon, lat, sp, ss.grid, fs, seed, regrid_every=4, grid_margin=0.25)
+    kept = []
+    for step in range(9):
+        slot = None if step % 3 == 1 else (len(kept) & 1)
+        ss.step(record=slot)
+        sim.step()
+        if slot is None:
+            continue
+        want = ss.local_state()[0]                              # read back after the step (synchronises)
+        ss.host_copies_sync()
+        got = ss.record_view(slot)
+        assert got[0].size == want[0].size > 0
+        for a, b, what in zip(got, want, ("ids", "lon", "lat", "species")):
+            assert np.array_equal(a, b), "%s of the record differ at step %d" % (what, step)
+        wl, wa, ws = sim.download()                             # and they are the single handle's values of those microbes
+        assert np.array_equal(wl[got[0]], got[1]) and np.array_equal(wa[got[0]], got[2]) and np.array_equal(ws[got[0]], got[3])
+        kept.append(step)
+    assert len(kept) == 6
+    ss.close()
+
+
+def test_record_by_ids_on_a_single_handle():
+    """lm_record_next_step_ids without strips: the whole state in storage order, every id once."""
+    from lagrangian_microbes_b200.simulation import FusedSimulation
+    n, seed = 30000, 8
+    fs = small_fs()
+    lon, lat, sp = particles(n, seed)
+    sim = FusedSimulation(lon, lat, sp, R, *P, fs, seed=seed, pair_capacity=40 * n, regrid_every=0, grid_margin=0.25)
+    pin = lambda dt: torch.empty(n, dtype=dt).pin_memory()
+    bufs = [(pin(torch.int32), pin(torch.float32), pin(torch.float32), pin(torch.int8)) for _ in range(2)]
+    for step in range(5):
+        sim.engine.record_next_step_ids(*bufs[step & 1])
+        sim.step()
+        sim.engine.host_copies_sync()
+        assert sim.engine.record_count() == n
+        ri, rl, ra, rs = (b.numpy() for b in bufs[step & 1])
+        wl, wa, ws = sim.download()
+        assert np.array_equal(np.sort(ri), np.arange(n))
+        assert np.array_equal(wl[ri], rl) and np.array_equal(wa[ri], ra) and np.array_equal(ws[ri], rs)
+    sim.engine.close()
+
+
 def test_strips_with_diffusion_and_rebalancing():
     from lagrangian_microbes_b200.strips import LocalTransport, StripSet
     G, n, seed = 3, 30000, 3

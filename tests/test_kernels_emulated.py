@@ -468,6 +468,7 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve
 
         clock_a, clock_b = StageClock(fs.time), StageClock(fs.time)
         pairs_single = np.zeros((cap, 2), dtype=np.int32)
+        rec_bufs = [(np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(n, np.int8)) for _ in range(2)]
         moved = 0
         for step in range(n_steps):
             prm = _lib.RpsParams(*p, seed, step)
@@ -475,7 +476,19 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve
                              _ptr(pairs_single), cap, None) == 0
             s1 = _lib.Stats()
             assert L.lm_sync_stats(single, ctypes.byref(s1), None) == 0
+            rec_h = strips[min(1, G - 1)]                                  # the in-step record by ids of one strip, on two steps of three
+            if step % 3 != 1:
+                assert L.lm_record_next_step_ids(rec_h, *(_ptr(a) for a in rec_bufs[step & 1])) == 0
             staged(flags_full, clock_b.next_step(dt), prm)
+            if step % 3 != 1:
+                assert L.lm_host_copies_sync(rec_h) == 0
+                m = L.lm_record_count(rec_h)
+                assert m == L.lm_state_size(rec_h) and m > 0
+                ri, rl, ra, rs = (a[:m] for a in rec_bufs[step & 1])
+                fl, fa, fsp = np.full(n, np.nan, np.float32), np.full(n, np.nan, np.float32), np.full(n, -1, np.int8)
+                assert L.lm_state_get(rec_h, _ptr(fl), _ptr(fa), _ptr(fsp), None) == 0
+                assert np.unique(ri).size == m and np.array_equal(fl[ri], rl) and np.array_equal(fa[ri], ra) and np.array_equal(fsp[ri], rs)
+                assert np.isnan(np.delete(fl, ri)).all()                   # exactly the strip's microbes
             st = [strip_stats(h) for h in strips]
             assert sum(s.n_misrouted for s in st) == 0 and sum(s.n_particles for s in st) == n
             assert sum(s.n_pairs for s in st) == s1.n_pairs

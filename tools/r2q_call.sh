@@ -1,14 +1,15 @@
 #!/bin/bash
 # Round 2, two GPUs: tiles-over-ranks + strips tests, and what the strip record costs the end-to-end loop at N = 2
-# (full record | staged but not copied to the host | no record).
+# (record copied inside the step by the library | record issued after the step from Python | no record).
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out/r2q
 mkdir -p $O
 python -c "import __graft_entry__ as g; g.build()" > $O/build.log 2>&1
-timeout 900 python -m pytest tests/test_gpu_tiles_over_ranks.py tests/test_gpu_strips.py -x -q -m gpu > $O/pytest_2gpu.log 2>&1; tail -3 $O/pytest_2gpu.log
-for v in full nocopy norecord; do
-  LM_E2E_VARIANT=$v timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
+timeout 900 python -m pytest tests/test_gpu_strips.py -x -q -m gpu > $O/pytest_2gpu.log 2>&1; tail -3 $O/pytest_2gpu.log
+for v in instep after norecord; do
+  vv=$v; [ $v = instep ] && vv=""
+  LM_RECORD_TIMING=1 LM_E2E_VARIANT=$vv timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 \
       bench.py --gpus 2 --steps 40 --warmup 5 --no-parity > $O/bench_n2_$v.json 2>$O/bench_n2_$v.err
   python -c "
 import json,sys
