@@ -86,7 +86,8 @@ int lm_destroy(lm_handle h)
     if (h->ev_pos_ready) cudaEventDestroy(h->ev_pos_ready);
     if (h->ev_pos_scattered) cudaEventDestroy(h->ev_pos_scattered);
     if (h->ev_sp_ready) cudaEventDestroy(h->ev_sp_ready);
-    if (h->ev_sp_scattered) cudaEventDestroy(h->ev_sp_scattered);
+    for (int k = 0; k < 2; ++k)
+        if (h->ev_rec_reads[k]) cudaEventDestroy(h->ev_rec_reads[k]);
     cudaFree(h->cell_cursor); cudaFree(h->block_sums); cudaFree(h->ctr); cudaFree(h->head);
     cudaFree(h->pending_cnt);
     cudaFree(h->hits); cudaFree(h->rec); cudaFree(h->rec2);
@@ -94,6 +95,7 @@ int lm_destroy(lm_handle h)
     cudaFree(h->ghost_send); cudaFree(h->ghost_recv);
     cudaFree(h->gsp_send); cudaFree(h->gsp_recv); cudaFree(h->gret_send); cudaFree(h->gret_recv);
     if (h->xfer_counts_host) cudaFreeHost(h->xfer_counts_host);
+    if (h->stats_host) cudaFreeHost(h->stats_host);
     for (int sd = 0; sd < 2; ++sd)
         if (h->peer[sd].connected && h->peer[sd].ipc)
             for (int k = 0; k < LM_PEER_BUFFERS; ++k) if (h->peer[sd].base[k]) cudaIpcCloseMemHandle(h->peer[sd].base[k]);
@@ -132,6 +134,8 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     ok = ok && dev_alloc(&h->keys, max_particles) && dev_alloc(&h->slots, max_particles);
     ok = ok && dev_alloc(&h->cell_count, max_cells) && dev_alloc(&h->cell_start_buf[0], max_cells + 1);
     ok = ok && dev_alloc(&h->cell_start_buf[1], max_cells + 1) && dev_alloc(&h->n_pairs_snap, 1);
+    ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&h->stats_host), sizeof(Counters) + 16, cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->stats_dev), h->stats_host, 0) == cudaSuccess;
     h->cell_start = h->cell_start_buf[0];
     h->overlap = 1;
     h->norm = LM_NORM_2;
@@ -160,7 +164,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_pos_ready, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_pos_scattered, cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaEventCreateWithFlags(&h->ev_sp_ready, cudaEventDisableTiming) == cudaSuccess;
-    if (ok) ok = cudaEventCreateWithFlags(&h->ev_sp_scattered, cudaEventDisableTiming) == cudaSuccess;
+    for (int k = 0; k < 2 && ok; ++k) ok = cudaEventCreateWithFlags(&h->ev_rec_reads[k], cudaEventDisableTiming) == cudaSuccess;
     if (ok) ok = cudaMemset(h->n_pairs_snap, 0, sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && dev_alloc(&h->sticky, 1);
     // hybrid mode: queues of heavy units, per phase; a heavy unit needs >= 17 microbes in two cells, so N / 8 per phase is ample
@@ -246,7 +250,8 @@ int lm_strip_alloc(lm_handle h, int64_t send_cap, int64_t ghost_cap, int32_t row
     ok = ok && dev_alloc(&h->ghost_send, ghost_words) && dev_alloc(&h->ghost_recv, ghost_words);
     ok = ok && dev_alloc(&h->gsp_send, ghost_cap) && dev_alloc(&h->gsp_recv, ghost_cap);
     ok = ok && dev_alloc(&h->gret_send, ghost_cap) && dev_alloc(&h->gret_recv, ghost_cap);
-    ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&h->xfer_counts_host), 4 * sizeof(int32_t), cudaHostAllocDefault) == cudaSuccess;
+    ok = ok && cudaHostAlloc(reinterpret_cast<void **>(&h->xfer_counts_host), 4 * sizeof(int32_t), cudaHostAllocMapped) == cudaSuccess;
+    ok = ok && cudaHostGetDevicePointer(reinterpret_cast<void **>(&h->xfer_counts_dev), h->xfer_counts_host, 0) == cudaSuccess;
     ok = ok && dev_alloc(&h->xflags, 8);
     if (ok) ok = cudaMemset(h->xflags, 0, 8 * sizeof(unsigned int)) == cudaSuccess;
     for (int k = 0; ok && k < 2; ++k) {
@@ -692,11 +697,9 @@ int lm_step_bin(lm_handle h, void *stream)
             // the one host synchronisation of a multi-GPU step: how many left, how many arrived
             int32_t *cnt = h->xfer_counts_host;
             cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0;
-            for (int d = 0; d < 2; ++d) {
-                if (!(d ? h->has_north : h->has_south)) continue;
-                LM_CUDA(cudaMemcpyAsync(cnt + d, h->mig_send[d], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-                LM_CUDA(cudaMemcpyAsync(cnt + 2 + d, h->mig_recv[d], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-            }
+            LM_CUDA(launch_xfer_counts(h->has_south ? h->mig_send[0] : nullptr, h->has_north ? h->mig_send[1] : nullptr,
+                                       h->has_south ? h->mig_recv[0] : nullptr, h->has_north ? h->mig_recv[1] : nullptr,
+                                       h->xfer_counts_dev, s, &h->launches));
             LM_CUDA(cudaStreamSynchronize(s));
             for (int k = 0; k < 4; ++k) {       // a full message holds send_cap records; the rest stayed behind
                 if (cnt[k] < 0) return LM_EINVAL;
@@ -718,7 +721,8 @@ int lm_step_bin(lm_handle h, void *stream)
         const int d = c ^ 1;
         // buffers [d] held the state two steps ago: a species record of that step (scattered on the copy stream, behind its
         // position copies) may still be reading them when no record of the step in between orders the streams (stride >= 2)
-        if (h->sp_scatter_age > 0 && --h->sp_scatter_age == 0) LM_CUDA(cudaStreamWaitEvent(s, h->ev_sp_scattered, 0));
+        for (int k = 0; k < 2; ++k)
+            if (h->rec_reads_age[k] > 0 && --h->rec_reads_age[k] == 0) LM_CUDA(cudaStreamWaitEvent(s, h->ev_rec_reads[k], 0));
         LM_CUDA(launch_bin_finish(h, h->lon[c], h->lat[c], h->sp[c], h->id[c], n_in, n_out, h->lon[d], h->lat[d],
                                   h->sp[d], h->id[d], s));
         h->cur = c = d;
@@ -870,8 +874,8 @@ int lm_step_finish(lm_handle h, void *stream)
                 if (!(h->record_debug & 1))
                     LM_CUDA(cudaMemcpyAsync(h->rec_sp_host, h->sp[c], (size_t)n, cudaMemcpyDeviceToHost, h->copy_stream));
             }
-            LM_CUDA(cudaEventRecord(h->ev_sp_scattered, h->copy_stream));      // ids and species of buffers [c] have been read
-            h->sp_scatter_age = 2;
+            LM_CUDA(cudaEventRecord(h->ev_rec_reads[k], h->copy_stream));      // ids and species of buffers [c] have been read
+            h->rec_reads_age[k] = 2;
         } else if (h->rec_sp_host) {
             if (h->resolve_pending) LM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_resolve_done, 0));
             else {
@@ -881,8 +885,8 @@ int lm_step_finish(lm_handle h, void *stream)
             if (!(h->record_debug & 2))
                 LM_CUDA(launch_scatter_by_id(nullptr, nullptr, h->sp[c], h->id[c], n, nullptr, nullptr, h->stage_sp[k], h->copy_stream,
                                              &h->launches));
-            LM_CUDA(cudaEventRecord(h->ev_sp_scattered, h->copy_stream));
-            h->sp_scatter_age = 2;
+            LM_CUDA(cudaEventRecord(h->ev_rec_reads[k], h->copy_stream));
+            h->rec_reads_age[k] = 2;
             if (!(h->record_debug & 1))
                 LM_CUDA(cudaMemcpyAsync(h->rec_sp_host, h->stage_sp[k], (size_t)n, cudaMemcpyDeviceToHost, h->copy_stream));
         }
@@ -1008,12 +1012,17 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
     if (!h) return LM_EINVAL;
     LM_CUDA(cudaSetDevice(h->device));
     { const int rcj = join_side(h, as_stream(stream)); if (rcj) return rcj; }
-    Counters c;
-    unsigned int sticky = 0;
-    LM_CUDA(cudaMemcpyAsync(&c, h->ctr, sizeof(c), cudaMemcpyDeviceToHost, as_stream(stream)));
-    LM_CUDA(cudaMemcpyAsync(&sticky, h->sticky, sizeof(sticky), cudaMemcpyDeviceToHost, as_stream(stream)));
+    // the counters reach the host as stores of a small kernel into mapped pinned memory: a D2H copy would wait on the copy
+    // engine behind the bulk copies of the per-step record (see xfer_counts_kernel)
+    static_assert(sizeof(Counters) % 4 == 0, "Counters is copied word by word");
+    LM_CUDA(launch_words_to_host(reinterpret_cast<const uint32_t *>(h->ctr), h->sticky, h->stats_dev, (int)(sizeof(Counters) / 4),
+                                 as_stream(stream), &h->launches));
     LM_CUDA(cudaMemsetAsync(h->sticky, 0, sizeof(unsigned int), as_stream(stream)));      // reported once
     LM_CUDA(cudaStreamSynchronize(as_stream(stream)));
+    Counters c;
+    unsigned int sticky = 0;
+    memcpy(&c, h->stats_host, sizeof(c));
+    memcpy(&sticky, h->stats_host + sizeof(Counters) / 4, sizeof(sticky));
     h->ctr_reported = true;
     if (out) {
         out->n_pairs = (int64_t)c.n_pairs;

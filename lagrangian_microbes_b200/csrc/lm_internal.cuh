@@ -156,8 +156,9 @@ struct lm_handle_s {
     int64_t rec_count;               // particles in the last record by ids
     bool rec_armed, rec_active;      // armed: next step records; active: this step is recording
     int rec_slot;
-    cudaEvent_t ev_pos_ready, ev_pos_scattered, ev_sp_ready, ev_sp_scattered;
-    int sp_scatter_age;              // 2 after a species record was scattered: the re-binning two steps later waits for ev_sp_scattered
+    cudaEvent_t ev_pos_ready, ev_pos_scattered, ev_sp_ready;
+    cudaEvent_t ev_rec_reads[2];     // per record slot: the copy stream has read ids / species of the state buffers of that step
+    int rec_reads_age[2];            // 2 when a record has been issued: the re-binning TWO steps on overwrites those buffers and waits
     bool pos_scatter_pending;        // the in-place advection of the next step must wait for ev_pos_scattered
     int64_t launches;
     // ---- latitude-strip decomposition (lm_strip_alloc / lm_set_strip); all zero for a single GPU
@@ -168,7 +169,9 @@ struct lm_handle_s {
     int32_t *ghost_send, *ghost_recv;    // GHOST_HDR + row_cap + 1 + 3 * ghost_cap words
     int8_t *gsp_send, *gsp_recv;         // [ghost_cap] species of the ghost row, north -> south after phase 5
     int8_t *gret_send, *gret_recv;       // [ghost_cap] species of the ghost row, south -> north after phase 8
-    int32_t *xfer_counts_host;           // pinned: n_leave[2], n_arrive[2]
+    int32_t *xfer_counts_host;           // pinned + mapped: n_leave[2], n_arrive[2], stored by the device (xfer_counts_kernel)
+    int32_t *xfer_counts_dev;            // the same memory as the device sees it
+    uint32_t *stats_host, *stats_dev;    // pinned + mapped: Counters + the sticky fault word, stored by the device (lm_sync_stats)
     // peer-memory exchange (lm_strip_peer_connect): the neighbours' receive buffers and flag words, mapped into this process
     struct Peer {
         bool connected, ipc;
@@ -212,6 +215,9 @@ cudaError_t launch_unpack_arrivals(lm_handle_s *h, int dir, int n_arrive, int fi
                                    int32_t *id, cudaStream_t s);
 cudaError_t launch_ghost_pack(lm_handle_s *h, const float *lon, const float *lat, const int32_t *id, cudaStream_t s);
 // peer-memory exchange (csrc/strip.cu)
+cudaError_t launch_words_to_host(const uint32_t *src, const uint32_t *last, uint32_t *host_dev, int words, cudaStream_t s, int64_t *launches);
+cudaError_t launch_xfer_counts(const void *send0, const void *send1, const void *recv0, const void *recv1, int32_t *host_counts_dev,
+                               cudaStream_t s, int64_t *launches);
 cudaError_t launch_peer_signal(unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches);
 cudaError_t launch_peer_wait(const unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches);
 cudaError_t launch_peer_push_mig(const int4 *src, int4 *dst, int64_t send_cap, cudaStream_t s, int64_t *launches);

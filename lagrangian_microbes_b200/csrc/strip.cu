@@ -185,6 +185,45 @@ __global__ void __launch_bounds__(256) peer_push_mig_kernel(const int4 *__restri
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) dst[k] = src[k];
 }
 
+// The migration counts of a step, stored by the device straight into mapped pinned host memory.  A cudaMemcpyAsync of
+// the same 16 bytes would queue on the D2H copy engine BEHIND the bulk copies of the per-step record (2.7 ms for a 12.5 M
+// microbe strip) and with it stall the whole step: a store from an SM is a posted write over PCIe and passes them.
+__global__ void xfer_counts_kernel(const int32_t *send0, const int32_t *send1, const int32_t *recv0, const int32_t *recv1,
+                                   volatile int32_t *host_counts)
+{
+    if (threadIdx.x == 0) {
+        host_counts[0] = send0 ? *send0 : 0;
+        host_counts[1] = send1 ? *send1 : 0;
+        host_counts[2] = recv0 ? *recv0 : 0;
+        host_counts[3] = recv1 ? *recv1 : 0;
+        __threadfence_system();
+    }
+}
+
+__global__ void words_to_host_kernel(const uint32_t *__restrict__ src, const uint32_t *__restrict__ last, volatile uint32_t *host, int words)
+{
+    for (int k = threadIdx.x; k < words; k += blockDim.x) host[k] = src[k];
+    if (threadIdx.x == 0 && last) host[words] = *last;
+    __threadfence_system();
+}
+
+// ``words`` 32-bit words of src, then one word of ``last`` (optional), into mapped pinned host memory
+cudaError_t launch_words_to_host(const uint32_t *src, const uint32_t *last, uint32_t *host_dev, int words, cudaStream_t s, int64_t *launches)
+{
+    words_to_host_kernel<<<1, 64, 0, s>>>(src, last, host_dev, words);
+    ++*launches;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xfer_counts(const void *send0, const void *send1, const void *recv0, const void *recv1, int32_t *host_counts_dev,
+                               cudaStream_t s, int64_t *launches)
+{
+    xfer_counts_kernel<<<1, 32, 0, s>>>(static_cast<const int32_t *>(send0), static_cast<const int32_t *>(send1),
+                                        static_cast<const int32_t *>(recv0), static_cast<const int32_t *>(recv1), host_counts_dev);
+    ++*launches;
+    return cudaGetLastError();
+}
+
 cudaError_t launch_peer_signal(unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches)
 {
     peer_signal_kernel<<<1, 1, 0, s>>>(flag, seq);

@@ -51,7 +51,7 @@ static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t
 template <class F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 // the rest of the runtime API the C ABI layer (csrc/api.cu) uses: memory is host memory, every "stream" is synchronous,
 // events are inert (elapsed time 0)
-enum { cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0 };
+enum { cudaEventDisableTiming = 2, cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaHostAllocMapped = 2 };
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 // CUDA IPC: not available on the emulator (one process); lm_strip_peer_export falls back to plain pointers
@@ -64,6 +64,7 @@ static inline cudaError_t cudaMalloc(void **p, size_t n) { *p = calloc(n ? n : 1
 static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaHostAlloc(void **p, size_t n, unsigned int) { *p = calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaHostGetDevicePointer(void **d, void *h, unsigned int) { *d = h; return cudaSuccess; }
 static inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned int) { *s = nullptr; return cudaSuccess; }

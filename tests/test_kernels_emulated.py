@@ -329,6 +329,7 @@ def test_fused_steps_through_the_c_abi(abi, interact_mode, resolve_mode, stats_e
             total += stats.n_pairs
         assert total > 1500 and int((sp_ref != sp0).sum()) > 100
         per_step = (L.lm_launch_count(h) - launches0) / float(n_steps)
+        per_step -= 1                             # lm_sync_stats after every step: one small kernel stores the counters into mapped host memory
         if interact_mode == 2:
             assert 25 <= per_step <= 28           # advection, binning (6), pair search, nine phase launches + nine heavy-unit launches
         elif interact_mode == 1:
