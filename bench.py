@@ -285,7 +285,9 @@ def parity_twin(world, rank, hfs, steps=4, per_rank=40_000, transport="peer"):
     mine = slice(rank * per_rank, (rank + 1) * per_rank)                  # the reference's contiguous tiles
     ids = np.arange(n, dtype=np.int32)
     ss = StripSet(PeerTransport() if transport == "peer" else DistTransport(), lon[mine], lat[mine], sp[mine], ids[mine], n, RADIUS, *P_RPS, hfs, dt_seconds=DT, seed=7,
-                  emit_pairs=False, slack=1.6, grid_margin=0.5, regrid_every=2)
+                  emit_pairs=False, slack=max(1.6, float(world)), grid_margin=0.5, regrid_every=2)
+    # (slack: the twin hands every rank a contiguous TILE of ids, i.e. microbes from all over the domain, and settle() routes
+    #  them one strip per pass -- the inner strips hold the traffic of both directions on the way: room for all of it)
     for _ in range(steps):
         ss.step()
         if single is not None:

@@ -4,6 +4,7 @@ fused step BIT FOR BIT (positions, pair set, species), which in turn is checked 
 tests/test_gpu_parity.py::test_fused_simulation_matches_oracle_loop."""
 import os
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -251,8 +252,9 @@ def _nccl_worker(rank, world, port, n, seed, steps, out_dir, kind="nccl"):
         per = n // world
         c = slice(rank * per, (rank + 1) * per if rank < world - 1 else n)
         # "nccl": send / recv between neighbours; "peer": the neighbours' buffers mapped through CUDA IPC, peer stores + flags
+        # (pairs_per_particle: strips are cut on 16-row boundaries, so the dense blob of the test lies in one or two of them)
         ss = StripSet(PeerTransport() if kind == "peer" else DistTransport(), lon[c], lat[c], sp[c], ids[c], n, R, *P, fs, seed=seed, slack=3.0,
-                      pairs_per_particle=40, grid_margin=0.05, regrid_every=4, cells_headroom=3.0)
+                      pairs_per_particle=40 * world, grid_margin=0.05, regrid_every=4, cells_headroom=3.0)
         grid0 = (ss.grid.x0, ss.grid.y0, ss.grid.inv_h, ss.grid.ncx, ss.grid.ncy)      # the grid of step 0 (re-fitted later)
         rec = []
         for step in range(steps):
@@ -267,10 +269,17 @@ def _nccl_worker(rank, world, port, n, seed, steps, out_dir, kind="nccl"):
                      **{"lon%d" % k: r[1] for k, r in enumerate(rec)}, **{"lat%d" % k: r[2] for k, r in enumerate(rec)},
                      **{"sp%d" % k: r[3] for k, r in enumerate(rec)}, **{"pairs%d" % k: r[4] for k, r in enumerate(rec)})
         ss.close()
-    finally:
-        dist.destroy_process_group()
+    except BaseException:
+        # a rank that fails must not wait for the others (they are inside a collective or spin on a flag this rank would
+        # have raised): report and leave at once, so that mp.spawn ends the remaining ranks instead of hanging the test
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
+    dist.destroy_process_group()
 
 
+@pytest.mark.timeout(900)
 @pytest.mark.parametrize("world,kind", [(2, "nccl"), (2, "peer"), (4, "nccl"), (4, "peer")])
 def test_strips_over_nccl_equal_single_handle(tmp_path, world, kind):
     if torch.cuda.device_count() < world:

@@ -16,4 +16,9 @@ for n in 8 4; do
 import json
 d=json.loads(open('$O/bench_shard_n$n.json').read().strip().splitlines()[-1]); print($n, d['value'], d['ms_per_step'], d['e2e'], d.get('parity'))"
 done
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29530 \
+    bench.py --gpus 8 --steps 50 --warmup 5 --transport nccl --no-e2e --no-parity > $O/bench_shard_n8_nccl.json 2>$O/bench_n8_nccl.err
+python -c "
+import json
+d=json.loads(open('$O/bench_shard_n8_nccl.json').read().strip().splitlines()[-1]); print('8 nccl', d['value'], d['ms_per_step'])"
 ls -la $O
