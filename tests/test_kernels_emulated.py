@@ -340,8 +340,9 @@ def test_fused_steps_through_the_c_abi(abi, interact_mode, resolve_mode, stats_e
         assert L.lm_destroy(h) == 0
 
 
+# (the GPU suite runs every mode x transport; here: the default mode on both transports, one case each of the other modes)
 @pytest.mark.parametrize("n_strips,interact_mode,resolve_mode,peer", [(2, 2, 0, False), (3, 2, 0, True), (3, 1, 0, True),
-                                                                      (2, 0, 1, False), (3, 0, 0, False)])
+                                                                      (2, 0, 1, False)])
 def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve_mode, peer):
     """The whole strip protocol executed: G handles, particles handed out in contiguous tiles, routing
     passes until every microbe sits in its strip, then fused steps in the five stages of include/lm_b200.h with the
@@ -513,7 +514,7 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve
 # The committed golden vectors (tests/golden/, made with the unmodified reference function and with SciPy) through the
 # emulated C ABI: the CPU suite pins the kernels' logic to the reference's own outputs, not only the GPU suite.
 @pytest.mark.parametrize("name,interact_mode,resolve_mode", [("rps_oddspecies", 2, 0), ("rps_clustered", 2, 0),
-                                                              ("rps_knots", 2, 0), ("rps_knots", 1, 0), ("rps_knots", 0, 0),
+                                                              ("rps_knots", 2, 0),
                                                               ("rps_oddspecies", 1, 0), ("rps_clustered", 1, 0),
                                                               ("rps_oddspecies", 0, 0), ("rps_oddspecies", 0, 1),
                                                               ("rps_clustered", 0, 1)])
