@@ -329,6 +329,13 @@ def test_fused_steps_through_the_c_abi(abi, interact_mode, resolve_mode, stats_e
             total += stats.n_pairs
         assert total > 1500 and int((sp_ref != sp0).sum()) > 100
         per_step = (L.lm_launch_count(h) - launches0) / float(n_steps)
+        # the scatter to id order in id windows (LM_OPT_SCATTER_PASSES; auto only splits above 8 M microbes): same arrays
+        for passes in (2, 3, 7):
+            assert L.lm_set_option(h, _lib.LM_OPT_SCATTER_PASSES, passes) == 0
+            wl, wa, ws = np.full(n, np.nan, np.float32), np.full(n, np.nan, np.float32), np.full(n, -1, np.int8)
+            assert L.lm_state_get(h, _ptr(wl), _ptr(wa), _ptr(ws), None) == 0
+            assert np.array_equal(wl, gl) and np.array_equal(wa, ga) and np.array_equal(ws, gs)
+        assert L.lm_set_option(h, _lib.LM_OPT_SCATTER_PASSES, 65) == _lib.LM_EINVAL
         per_step -= 1                             # lm_sync_stats after every step: one small kernel stores the counters into mapped host memory
         if interact_mode == 2:
             assert 25 <= per_step <= 28           # advection, binning (6), pair search, nine phase launches + nine heavy-unit launches

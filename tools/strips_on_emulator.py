@@ -52,9 +52,9 @@ if len(sys.argv) > 5 and sys.argv[5] == "twin":
     sp = rng.integers(1, 4, n).astype(np.int8)
     ids = np.arange(n, dtype=np.int32)
     cut = [slice(r * per_rank, (r + 1) * per_rank) for r in range(G)]
-    for slack in (1.6, max(1.6, float(G))):
+    for slack in ((max(1.6, float(G)),) if peer else (1.6, max(1.6, float(G)))):
         try:
-            ss = strips.StripSet(strips.LocalTransport(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
+            ss = strips.StripSet((strips.LocalPeerTransport if peer else strips.LocalTransport)(G), [lon[c] for c in cut], [lat[c] for c in cut], [sp[c] for c in cut],
                                  [ids[c] for c in cut], n, bench.RADIUS, *bench.P_RPS, hfs, dt_seconds=bench.DT, seed=7, local_strips=list(range(G)),
                                  emit_pairs=False, slack=slack, grid_margin=0.5, regrid_every=2)
             print("twin, slack %.1f: settled, edges %s, sizes %s, capacity %d" % (slack, ss.edges, [s.engine.state_size() for s in ss.strips],
