@@ -612,6 +612,12 @@ def main():
         ms_e2e = max(e0.elapsed_time(e1), 1e3 * (tw1 - tw0))     # device events and the host clock around the copies
         # N = 1: lon, lat, species in particle-id order (9 B); strips: ids travel with the record (13 B)
         e2e = {"ms": ms_e2e, "h2d": h2d / args.steps, "d2h": (9 if world == 1 else 13) * n_per_gpu}
+        if world == 1 and packer is None:
+            e2e["record"] = "lon, lat, species in particle-id order: scattered and copied inside the step (lm_record_next_step)"
+        elif world > 1 and os.environ.get("LM_E2E_VARIANT", "") == "":
+            e2e["d2h"] = 13 * int(sim2.ss._record_slot_count[sim2.k])        # this rank's strip at the last step
+            e2e["record"] = ("ids, lon, lat, species of the rank's strip in storage order: copied inside the step "
+                             "(lm_record_next_step_ids); bytes of rank 0's strip at the last step")
         if packer is not None:
             # counted from the copies issued: int16 lon + lat, the escape list and its counter (or a plain key frame
             # when the list overflowed), plus int8 species
