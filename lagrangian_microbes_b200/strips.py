@@ -22,8 +22,6 @@ device in one process (``LocalTransport``: device copies; used by the single-GPU
 """
 import math
 
-import os
-
 import numpy as np
 import torch
 
@@ -536,7 +534,9 @@ class StripSet:
         return [s.pairs[:x.n_pairs].cpu().numpy() for s, x in zip(self.strips, st)]
 
     def record_to_host(self, slot):
-        """Asynchronous per-step record of the FIRST local strip into pinned host buffers: (ids, lon, lat,
+        """(Kept for callers that decide AFTER a step that they want its record; ``step(record=slot)`` copies the same
+        record inside the step and is what overlaps with the pair search.)
+        Asynchronous per-step record of the FIRST local strip into pinned host buffers: (ids, lon, lat,
         species) of its owned particles in storage order -- what a per-strip output file holds, like the
         reference's per-tile chunk pickles (particle_advecter.py:201-214).  Two slots alternate; returns the
         number of particles recorded.  Call ``host_copies_sync()`` before reading the buffers."""
@@ -560,18 +560,10 @@ class StripSet:
             R["stage"][k][slot][:n].copy_(src[:n], non_blocking=True)
         staged = torch.cuda.Event()
         staged.record(cur)
-        timing = os.environ.get("LM_RECORD_TIMING", "") == "1"      # (measurement only: how long the copies take on their stream)
         with torch.cuda.stream(R["stream"]):
             R["stream"].wait_event(staged)
-            if timing:
-                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                t0.record(R["stream"])
-            if os.environ.get("LM_E2E_VARIANT", "") != "nocopy":          # (measurement only: the record without its D2H copies)
-                for k in range(4):
-                    R["host"][k][slot][:n].copy_(R["stage"][k][slot][:n], non_blocking=True)
-            if timing:
-                t1.record(R["stream"])
-                R.setdefault("timing", []).append((t0, t1))
+            for k in range(4):
+                R["host"][k][slot][:n].copy_(R["stage"][k][slot][:n], non_blocking=True)
             R["copied"][slot].record(R["stream"])
         return n
 
