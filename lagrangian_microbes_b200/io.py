@@ -125,6 +125,79 @@ def _parse_time_units(units):
     raise ValueError("time units not understood: %r" % units)
 
 
+class ParticleFileWriter:
+    """``particle_data.nc`` / ``microbe_data.nc`` written piece by piece.
+
+    The reference allocates the whole (N, Nt) arrays on the host and hands them to xarray (particle_advecter.py:269-270,
+    interaction_simulator.py:80-82): 33.8 GB for its own 490,000-microbe, 7,670-step run.  This writer keeps the same
+    file for runs that fit NetCDF-3 (arrays in memory, ``write_particle_file`` at ``close()``) and, for larger ones, fills
+    the ``<file>.npz.d/`` layout that ``write_particle_file`` falls back to -- memory-mapped ``.npy`` files, written in
+    blocks of whole time columns, so the host holds ``block_bytes`` instead of the run.  Cells never written stay 0, as in
+    the reference's ``zeros`` arrays."""
+
+    def __init__(self, filepath, variables, N, times, var_limit=None, block_bytes=256 << 20):
+        self.filepath, self.N, self.times = filepath, int(N), list(times)
+        self.Nt = len(self.times)
+        self.dtypes = {k: np.dtype(v) for k, v in variables.items()}
+        limit = _NC3_VAR_LIMIT if var_limit is None else var_limit
+        self.large = any(self.N * self.Nt * dt.itemsize > limit for dt in self.dtypes.values())
+        self._n_buf, self._t0 = 0, 0
+        if not self.large:
+            self.arrays = {k: np.zeros((self.N, self.Nt), dtype=dt) for k, dt in self.dtypes.items()}
+            return
+        self.dir = filepath + ".npz.d"
+        os.makedirs(self.dir, exist_ok=True)
+        self.arrays = {k: np.lib.format.open_memmap(os.path.join(self.dir, k + ".npy"), mode="w+", dtype=dt, shape=(self.N, self.Nt))
+                       for k, dt in self.dtypes.items()}
+        per_column = self.N * sum(dt.itemsize for dt in self.dtypes.values())
+        self.block = int(max(1, min(self.Nt, block_bytes // max(per_column, 1))))
+        self._buf = {k: np.zeros((self.N, self.block), dtype=dt) for k, dt in self.dtypes.items()}
+
+    def put(self, i, **columns):
+        """Time column ``i`` of the named variables (arrays of N values)."""
+        if not self.large:
+            for k, v in columns.items():
+                self.arrays[k][:, i] = v
+            return
+        if self._n_buf and (i != self._t0 + self._n_buf or self._n_buf == self.block):
+            self._flush()
+        if self._n_buf == 0:
+            self._t0 = i
+            for b in self._buf.values():
+                b[:] = 0
+        for k, v in columns.items():
+            self._buf[k][:, self._n_buf] = v
+        self._n_buf += 1
+
+    def put_block(self, rows, t1, t2, **blocks):
+        """A sub-block: particles ``rows`` (a slice) x time columns [t1, t2), arrays of shape (rows, t2 - t1)."""
+        if self.large:
+            self._flush()
+        for k, v in blocks.items():
+            self.arrays[k][rows, t1:t2] = v
+
+    def _flush(self):
+        if self.large and self._n_buf:
+            # only the variables that were given columns carry data; the others hold zeros, which is what the file has
+            for k, b in self._buf.items():
+                self.arrays[k][:, self._t0:self._t0 + self._n_buf] = b[:, :self._n_buf]
+            self._n_buf = 0
+
+    def close(self):
+        """-> the path written (the ``.nc`` file, or the ``.npz.d`` directory of a large run)."""
+        if not self.large:
+            return write_particle_file(self.filepath, self.arrays, self.times)
+        self._flush()
+        t0 = self.times[0] if self.times else datetime(1970, 1, 1)
+        np.save(os.path.join(self.dir, "time_seconds.npy"), np.array([(t - t0).total_seconds() for t in self.times], dtype=np.float64))
+        with open(os.path.join(self.dir, "time_origin.txt"), "w") as f:
+            f.write(t0.strftime("%Y-%m-%d %H:%M:%S"))
+        for a in self.arrays.values():
+            a.flush()
+        self.arrays = self._buf = None
+        return self.dir
+
+
 def read_particle_file(filepath):
     if os.path.isfile(filepath):
         with open(filepath, "rb") as f:

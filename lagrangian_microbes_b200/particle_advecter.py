@@ -349,19 +349,19 @@ class ParticleAdvecter:
             return
         iters = (end_time - start_time) // dt
         times = [start_time + n * dt for n in range(iters)]
-        plons = np.zeros((self.N_particles, iters), dtype=float32)
-        plats = np.zeros((self.N_particles, iters), dtype=float32)
+        # (the reference merges into two dense (N, iters) host arrays, :269-270: 30 GB for its 490,000 x 7,670 run; the
+        #  writer keeps them in memory while the file fits NetCDF-3 and goes through memory-mapped files beyond)
+        nc_filepath = os.path.join(self.output_dir, "particle_data.nc")
+        out = lmio.ParticleFileWriter(nc_filepath, {"longitude": float32, "latitude": float32}, self.N_particles, times)
         pkl_files = sorted(glob(os.path.join(self.output_dir, "particle_locations_*.pickle")))
         for pkl_filepath in pkl_files:
             logger.info("Collecting particle locations from {:s}...".format(pkl_filepath))
             t1, t2, tile_id = lmio.parse_chunk_name(pkl_filepath)
             chunk = joblib.load(pkl_filepath)
             i1, i2 = tile_id * self.particles_per_tile, (tile_id + 1) * self.particles_per_tile
-            plons[i1:i2, t1:t2] = np.transpose(chunk["lon"])
-            plats[i1:i2, t1:t2] = np.transpose(chunk["lat"])
-        nc_filepath = os.path.join(self.output_dir, "particle_data.nc")
+            out.put_block(slice(i1, i2), t1, t2, longitude=np.transpose(chunk["lon"]), latitude=np.transpose(chunk["lat"]))
         logger.info("Writing particle locations to {:s}...".format(nc_filepath))
-        lmio.write_particle_file(nc_filepath, {"longitude": plons, "latitude": plats}, times)
+        out.close()
         for pkl_filepath in pkl_files:
             os.remove(pkl_filepath)
         self._barrier()

@@ -165,3 +165,38 @@ def test_large_n_properties():
         assert bool((species_b == species).all())
     finally:
         eng.close()
+
+
+def test_runs_beyond_netcdf3_go_through_memory_mapped_files(tmp_path, monkeypatch):
+    """The reference's own headline run (490,000 microbes x 7,670 steps) does not fit NetCDF-3 variables, and its dense
+    (N, Nt) host arrays (particle_advecter.py:269-270, interaction_simulator.py:80-82) would be 33.8 GB: beyond the
+    limit the drop-in classes write ``<file>.npz.d/`` (memory-mapped .npy files, filled in blocks) and read it back
+    lazily.  Here the limit is lowered so that a small run takes that path: same numbers as the in-memory path."""
+    import lagrangian_microbes_b200 as lm
+    from lagrangian_microbes_b200 import io as lmio, velocity_fields
+    velocity_fields.configure_synthetic(n_modes=8, rms_speed=0.4, seed=3)
+    try:
+        N, r = 3000, 0.03
+        start, end, dt = datetime(2017, 1, 1), datetime(2017, 1, 1, 7), timedelta(hours=1)
+        lons, lats = lm.uniform_particle_locations(N_particles=N, lat_min=30, lat_max=31.2, lon_min=208, lon_max=209.2)
+        results = []
+        for tag, limit in (("nc3", None), ("mapped", 4 * N * 3)):          # "mapped": variables above three columns
+            if limit is not None:
+                monkeypatch.setattr(lmio, "_NC3_VAR_LIMIT", limit)
+            out = str(tmp_path / tag)
+            pa = lm.ParticleAdvecter(lons, lats, N_procs=3, output_dir=out, output_chunk_iters=4, Kh=0)
+            pa.time_step(start, end, dt)
+            pa.create_netcdf_file(start, end, dt)
+            np.random.seed(0)
+            rps = lm.rock_paper_scissors(N_microbes=N, pRS=0.55, pPR=0.55, pSP=0.55)
+            isim = lm.InteractionSimulator(pair_interaction=rps, interaction_radius=r, advection_dir=out, output_dir=out, seed=9)
+            isim.time_step(start, end, dt)
+            names = sorted(os.listdir(out))
+            assert names == (["microbe_data.nc", "particle_data.nc"] if limit is None else ["microbe_data.nc.npz.d", "particle_data.nc.npz.d"])
+            m = lmio.read_particle_file(os.path.join(out, "microbe_data.nc"))
+            results.append({k: np.array(m[k]) for k in ("longitude", "latitude", "species")})
+            assert m.times == [start + k * dt for k in range(7)] and sum(isim.pairs_found) > 0
+        for k in ("longitude", "latitude", "species"):
+            assert results[0][k].shape == (N, 7) and np.array_equal(results[0][k], results[1][k]), k
+    finally:
+        velocity_fields.configure_synthetic(n_modes=64, rms_speed=0.2, seed=0)

@@ -382,3 +382,38 @@ def test_netcdf4_files_of_the_reference_are_recognised(tmp_path):
     assert lmio._parse_time_units("seconds since 2017-01-01 00:00:00") == (1.0, datetime(2017, 1, 1))
     assert lmio._parse_time_units("hours since 2017-01-01T06:00:00") == (3600.0, datetime(2017, 1, 1, 6))
     assert lmio._parse_time_units("days since 1992-10-05") == (86400.0, datetime(1992, 10, 5))
+
+
+@pytest.mark.parametrize("mode", ["in memory", "mapped", "mapped, one column per block"])
+def test_particle_file_writer_fills_the_same_file_piece_by_piece(tmp_path, mode):
+    """io.ParticleFileWriter: time columns (InteractionSimulator) or particle x time blocks (create_netcdf_file) instead
+    of the reference's dense (N, Nt) host arrays; beyond NetCDF-3's variable limit the memory-mapped directory layout."""
+    N, Nt = 37, 11
+    times = [datetime(2017, 1, 1) + k * timedelta(hours=1) for k in range(Nt)]
+    rng = np.random.default_rng(0)
+    lon, lat = rng.random((N, Nt)).astype(np.float32), rng.random((N, Nt)).astype(np.float32)
+    sp = rng.integers(1, 4, (N, Nt)).astype(np.int8)
+    kw = {"in memory": {}, "mapped": dict(var_limit=100, block_bytes=4 * N * 9),
+          "mapped, one column per block": dict(var_limit=100, block_bytes=1)}[mode]
+    path = str(tmp_path / "microbe_data.nc")
+    w = lmio.ParticleFileWriter(path, {"longitude": np.float32, "latitude": np.float32, "species": np.int8}, N, times, **kw)
+    assert w.large == (mode != "in memory")
+    for i in range(Nt):
+        if i != 5:                                               # a column never written stays zero (the reference's zeros())
+            w.put(i, longitude=lon[:, i], latitude=lat[:, i], species=sp[:, i])
+    written = w.close()
+    assert written == (path if mode == "in memory" else path + ".npz.d") and os.path.exists(written)
+    f = lmio.read_particle_file(path)
+    want_lon, want_sp = lon.copy(), sp.copy()
+    want_lon[:, 5], want_sp[:, 5] = 0, 0
+    assert np.array_equal(np.asarray(f["longitude"]), want_lon) and np.array_equal(np.asarray(f["species"]), want_sp)
+    assert f.times == times and np.asarray(f["species"]).dtype == np.int8
+    # blocks of particles x time ranges, as the chunk pickles arrive
+    path2 = str(tmp_path / "particle_data.nc")
+    w = lmio.ParticleFileWriter(path2, {"longitude": np.float32, "latitude": np.float32}, N, times, **kw)
+    for rows in (slice(0, 20), slice(20, N)):
+        for t1, t2 in ((0, 6), (6, Nt)):
+            w.put_block(rows, t1, t2, longitude=lon[rows, t1:t2], latitude=lat[rows, t1:t2])
+    w.close()
+    f = lmio.read_particle_file(path2)
+    assert np.array_equal(np.asarray(f["longitude"]), lon) and np.array_equal(np.asarray(f["latitude"]), lat)

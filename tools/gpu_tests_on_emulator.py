@@ -4,7 +4,7 @@ torch-side wrappers.  Inside this process only, torch.cuda is monkeypatched to t
 subclass that reports is_cuda = True, so that Engine's argument checks hold.  Slow (minutes: the tests keep their GPU
 sizes); it found one bug in a test helper before any of this had seen hardware.
 
-    python tools/gpu_tests_on_emulator.py [analysis] [tiled-golden] [tiled-live] [tiled-knots] [tiled-fused] [record] [record-sim]
+    python tools/gpu_tests_on_emulator.py [analysis] [tiled-golden] [tiled-live] [tiled-knots] [tiled-fused] [record] [record-sim] [driver]
 """
 import contextlib
 import ctypes
@@ -123,4 +123,28 @@ if "record" in what or "record-sim" in what:
         timed("packed record stream of a stepping simulation", Rd.test_packed_record_stream_of_a_stepping_simulation_is_bit_exact)
         with tempfile.TemporaryDirectory() as d:
             timed("run_to_file packed = plain (stride 3)", Rd.test_run_to_file_packed_writes_the_same_file, pathlib.Path(d), 3)
+if "driver" in what:
+    # the reference's call sequence through the drop-in classes (uniform_particle_locations -> ParticleAdvecter.time_step x 2
+    # -> create_netcdf_file -> rock_paper_scissors -> InteractionSimulator.time_step) against the oracle pipeline
+    class _Ev2:
+        def __init__(self, *a, **k): pass
+        def record(self, *a): pass
+        def synchronize(self): pass
+        def elapsed_time(self, other): return 0.0
+    torch.cuda.Event = _Ev2
+    import test_gpu_driver as D
+    with tempfile.TemporaryDirectory() as d:
+        if "driver-mapped-only" not in what:
+            timed("reference call sequence end to end (N = 10,000)", D.test_reference_call_sequence_end_to_end, pathlib.Path(d))
+
+    class _MonkeyPatch:                                        # pytest's fixture, as far as the test uses it
+        def setattr(self, obj, name, value):
+            setattr(obj, name, value)
+    with tempfile.TemporaryDirectory() as d:
+        from lagrangian_microbes_b200 import io as _lmio
+        saved = _lmio._NC3_VAR_LIMIT
+        try:
+            timed("runs beyond NetCDF-3 through memory-mapped files", D.test_runs_beyond_netcdf3_go_through_memory_mapped_files, pathlib.Path(d), _MonkeyPatch())
+        finally:
+            _lmio._NC3_VAR_LIMIT = saved
 print("all requested GPU test bodies passed on the emulator")
