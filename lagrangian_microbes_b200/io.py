@@ -252,22 +252,35 @@ def write_png(filepath, rgb):
 
 
 class RecordAssembler:
-    """Dense (N, Nt) record arrays of a run, filled one step at a time, written in the layout of the reference's
+    """The (N, Nt) record of a run, filled one step at a time, written in the layout of the reference's
     ``microbe_data.nc`` (interaction_simulator.py:62-77, :108-110, :119-122).  ``stride`` keeps every stride-th step
     (at 9 B per microbe-step the dense record of 490,000 microbes x 7,670 steps is 33.8 GB, which
-    the reference holds in RAM: docs/disk_usage.txt, interaction_simulator.py:62-66)."""
+    the reference holds in RAM: docs/disk_usage.txt, interaction_simulator.py:62-66).  With ``output_dir`` given up
+    front, a record beyond NetCDF-3's variable limit goes straight to memory-mapped files in blocks of time columns
+    (ParticleFileWriter) instead of dense host arrays.  ``counts`` = microbes of species 1 / 2 / 3 per kept step."""
 
-    def __init__(self, n_particles, n_steps, start_time, dt, stride=1):
+    def __init__(self, n_particles, n_steps, start_time, dt, stride=1, output_dir=None, filename="microbe_data.nc"):
         assert stride >= 1 and n_steps >= 0
         self.stride = int(stride)
         self.n_steps = int(n_steps)
         self.kept_steps = list(range(0, self.n_steps, self.stride))
         nt = len(self.kept_steps)
         self.times = [start_time + k * dt for k in self.kept_steps]
-        self.longitude = np.zeros((n_particles, nt), dtype=np.float32)
-        self.latitude = np.zeros((n_particles, nt), dtype=np.float32)
-        self.species = np.zeros((n_particles, nt), dtype=np.int8)
+        self.counts = np.zeros((nt, 3), dtype=np.int64)
         self.filled = 0
+        self._n = int(n_particles)
+        self._spec = {"longitude": np.float32, "latitude": np.float32, "species": np.int8}
+        self._target = None
+        self._writer = None
+        if output_dir is not None:
+            self._open(output_dir, filename)
+        else:                                   # destination not known yet: in memory, whatever the size
+            self._writer = ParticleFileWriter(None, self._spec, self._n, self.times, var_limit=float("inf"))
+
+    def _open(self, output_dir, filename):
+        os.makedirs(output_dir, exist_ok=True)
+        self._target = os.path.join(output_dir, filename)
+        self._writer = ParticleFileWriter(self._target, self._spec, self._n, self.times)
 
     def wants(self, step):
         return 0 <= step < self.n_steps and step % self.stride == 0
@@ -275,17 +288,20 @@ class RecordAssembler:
     def put(self, step, lon, lat, species):
         assert self.wants(step)
         col = step // self.stride
-        self.longitude[:, col] = lon
-        self.latitude[:, col] = lat
-        self.species[:, col] = species
+        self._writer.put(col, longitude=lon, latitude=lat, species=species)
+        sp = np.asarray(species)
+        self.counts[col] = [int((sp == s).sum()) for s in (1, 2, 3)]
         self.filled += 1
 
     def write(self, output_dir, filename="microbe_data.nc"):
         assert self.filled == len(self.kept_steps), "%d of %d columns filled" % (self.filled, len(self.kept_steps))
         os.makedirs(output_dir, exist_ok=True)
-        return write_particle_file(os.path.join(output_dir, filename),
-                                   {"longitude": self.longitude, "latitude": self.latitude, "species": self.species},
-                                   self.times)
+        target = os.path.join(output_dir, filename)
+        if self._target is None:
+            self._writer.filepath = target
+        else:
+            assert os.path.abspath(target) == os.path.abspath(self._target), "the assembler was opened on %s" % self._target
+        return self._writer.close()
 
 
 # ---- the delta-packed position record (csrc/record.cu, lm_record_delta_pack) ------------------------------------------

@@ -218,12 +218,12 @@ class FusedSimulation:
         from datetime import timedelta
         assert isinstance(dt, timedelta) and abs(dt.total_seconds() - self.dt) < 1e-9, "dt differs from the simulation's"
         n_steps = (end_time - start_time) // dt
-        asm = lmio.RecordAssembler(self.n, n_steps, start_time, dt, stride)
+        asm = lmio.RecordAssembler(self.n, n_steps, start_time, dt, stride, output_dir=output_dir, filename=filename)
         if packed:
             self._run_packed(asm, n_steps)
             self.check_faults()
             path = asm.write(output_dir, filename)
-            return path, np.stack([(asm.species == s).sum(axis=0) for s in (1, 2, 3)], axis=1)
+            return path, asm.counts
         rec = [tuple(torch.empty(self.n, dtype=t).pin_memory() for t in (torch.float32, torch.float32, torch.int8))
                for _ in range(2)]
         in_flight = []                                   # (step, buffer set) whose copies have been issued
@@ -246,8 +246,7 @@ class FusedSimulation:
         drain()
         self.check_faults()                              # before anything is written: a truncated step must not reach the file
         path = asm.write(output_dir, filename)
-        counts = np.stack([(asm.species == s).sum(axis=0) for s in (1, 2, 3)], axis=1)
-        return path, counts
+        return path, asm.counts
 
     def _run_packed(self, asm, n_steps):
         """run_to_file's loop with the delta-packed position record: state in id order on the device (lm_state_get),

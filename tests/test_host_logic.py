@@ -417,3 +417,29 @@ def test_particle_file_writer_fills_the_same_file_piece_by_piece(tmp_path, mode)
     w.close()
     f = lmio.read_particle_file(path2)
     assert np.array_equal(np.asarray(f["longitude"]), lon) and np.array_equal(np.asarray(f["latitude"]), lat)
+
+
+def test_record_assembler_opened_on_its_destination_maps_large_records(tmp_path, monkeypatch):
+    """FusedSimulation.run_to_file hands the assembler its destination up front: a record beyond NetCDF-3's variable limit
+    is then filled through memory-mapped files, column block by column block; species counts are kept per column."""
+    n, steps = 40, 9
+    t0, dt = datetime(2018, 1, 1), timedelta(hours=1)
+    rng = np.random.default_rng(1)
+    cols = [(rng.random(n).astype(np.float32), rng.random(n).astype(np.float32), rng.integers(0, 5, n).astype(np.int8)) for _ in range(steps)]
+    outs = []
+    for tag, limit in (("nc3", None), ("mapped", 4 * n * 2)):
+        if limit is not None:
+            monkeypatch.setattr(lmio, "_NC3_VAR_LIMIT", limit)
+        asm = lmio.RecordAssembler(n, steps, t0, dt, 2, output_dir=str(tmp_path / tag))
+        for k in asm.kept_steps:
+            asm.put(k, *cols[k])
+        with pytest.raises(AssertionError):
+            asm.write(str(tmp_path / "elsewhere"))                # opened on another destination
+        path = asm.write(str(tmp_path / tag))
+        assert path.endswith("microbe_data.nc" if limit is None else "microbe_data.nc.npz.d")
+        back = lmio.read_particle_file(os.path.join(str(tmp_path / tag), "microbe_data.nc"))
+        outs.append({k: np.array(back[k]) for k in ("longitude", "latitude", "species")})
+        assert [list(c) for c in asm.counts] == [[int((cols[k][2] == s).sum()) for s in (1, 2, 3)] for k in asm.kept_steps]
+    for k in outs[0]:
+        assert np.array_equal(outs[0][k], outs[1][k]) and outs[0][k].shape == (n, 5)
+        assert np.array_equal(outs[0][k][:, 1], cols[2][("longitude", "latitude", "species").index(k)])
