@@ -13,6 +13,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # pytest-timeout registers this itself when it is installed; without the plug-in the mark is inert, not an error
+    config.addinivalue_line("markers", "timeout(seconds): multi-rank tests must fail, not hang, when a rank is lost")
 
 
 def pytest_collection_modifyitems(config, items):
