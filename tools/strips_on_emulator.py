@@ -88,4 +88,13 @@ for k in range(steps):
                   "particles", c.n_particles, "max", st.engine.max_particles, "moved in/out", c.n_moved_in, c.n_moved_out)
         raise
     print("step %d: %d pairs, edges %s, sizes %s" % (k, pairs, ss.edges, [s.engine.state_size() for s in ss.strips]), flush=True)
+# the in-step record of the first strip (StripSet.step(record=slot)) against the state read back after the step
+for k in range(3):
+    ss.step(record=k & 1)
+    sim.step()
+    want = ss.local_state()[0]
+    ss.host_copies_sync()
+    got = ss.record_view(k & 1)
+    assert all(np.array_equal(a, b) for a, b in zip(got, want)) and got[0].size == want[0].size > 0
+print("in-step strip record ok")
 print("ok")
