@@ -55,7 +55,9 @@ def write_particle_file(filepath, variables, times):
     N, Nt = first.shape
     t0 = times[0] if len(times) else datetime(1970, 1, 1)
     secs = np.array([(t - t0).total_seconds() for t in times], dtype=np.float64)
-    if all(v.nbytes <= _NC3_VAR_LIMIT for v in variables.values()):
+    # (a file without time columns -- a time_step call with start_time == end_time -- has no NetCDF-3 spelling with time as
+    #  the second dimension: a zero-length dimension is the record dimension there; it takes the directory layout)
+    if Nt > 0 and all(v.nbytes <= _NC3_VAR_LIMIT for v in variables.values()):
         from scipy.io import netcdf_file
         with netcdf_file(filepath, "w", version=2) as nc:
             nc.createDimension("particle number", N)

@@ -443,3 +443,14 @@ def test_record_assembler_opened_on_its_destination_maps_large_records(tmp_path,
     for k in outs[0]:
         assert np.array_equal(outs[0][k], outs[1][k]) and outs[0][k].shape == (n, 5)
         assert np.array_equal(outs[0][k][:, 1], cols[2][("longitude", "latitude", "species").index(k)])
+
+
+def test_files_without_columns_or_particles_round_trip(tmp_path):
+    """Edge cases of the file layer: a time_step call with start_time == end_time (no columns) and an empty particle set."""
+    for N, Nt in ((5, 0), (0, 3), (0, 0)):
+        times = [datetime(2017, 1, 1) + k * timedelta(hours=1) for k in range(Nt)]
+        path = str(tmp_path / ("f%d_%d.nc" % (N, Nt)))
+        w = lmio.ParticleFileWriter(path, {"longitude": np.float32, "latitude": np.float32, "species": np.int8}, N, times)
+        w.close()
+        f = lmio.read_particle_file(path)
+        assert np.asarray(f["longitude"]).shape == (N, Nt) and np.asarray(f["species"]).dtype == np.int8 and f.times == times
