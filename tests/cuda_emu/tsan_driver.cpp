@@ -24,7 +24,7 @@ int main(int argc, char **argv)
     const bool quick = argc > 1 && strcmp(argv[1], "quick") == 0;      // the subset the CPU test suite runs (about a minute)
     std::mt19937 rng(7);
     std::uniform_real_distribution<double> U(0.0, 1.0);
-    const int n = quick ? 450 : 900;
+    const int n = quick ? 320 : 900;
     const double r = 0.01, h = r * (1.0 + 1.0 / 1048576.0);
     const int ncx = 70, ncy = 19;
     std::vector<float> lon(n), lat(n);

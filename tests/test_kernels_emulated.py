@@ -362,7 +362,7 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve
     from lagrangian_microbes_b200.strips import cell_rows, strip_edges
     L, G = abi, n_strips
     fs = _small_field()
-    n, r, p, seed, dt, n_steps = 1000, 0.01, (0.55, 0.6, 0.9), 3, 3600.0, 3
+    n, r, p, seed, dt, n_steps = 700, 0.01, (0.55, 0.6, 0.9), 3, 3600.0, 3
     rng = np.random.default_rng(20 + G)
     lon = (201.5 + 0.2 * rng.random(n)).astype(np.float32)
     lat = (32.5 + 0.2 * rng.random(n)).astype(np.float32)
