@@ -343,6 +343,11 @@ int lm_reset_stats(lm_handle h, void *stream);
 /*   LM_OPT_RECORD_DEBUG  MEASUREMENT ONLY (the record is then incomplete): bit 0 leaves out the D2H copies of the in-step
  *                     record, bit 1 the scatter to id order -- what each costs the end-to-end loop (tools/scatter_probe.py) */
 #define LM_OPT_RECORD_DEBUG 20
+/*   LM_OPT_PEER_WAIT_CYCLES  peer-memory exchange: SM clocks a stage spins for a neighbour's message before it gives up
+ *                     (default 1.2e11, about a minute): the neighbour is gone -- the wait latches a fault that the next
+ *                     lm_sync_stats reports as LM_ESTATE, and later waits of the handle return at once, so a lost rank ends
+ *                     the run with an error instead of leaving the device spinning */
+#define LM_OPT_PEER_WAIT_CYCLES 21
 /* tile of the fused interaction pass, in cells: part of the definition of its canonical pair order.  Strip boundaries
  * (lm_set_strip) must sit on multiples of LM_TILE_H rows in this mode. */
 #define LM_TILE_W 32

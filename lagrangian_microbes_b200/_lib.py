@@ -27,6 +27,7 @@ LM_OPT_RESOLVE_MODE, LM_OPT_RESOLVE_TILE_SMEM, LM_OPT_RESOLVE_MEGA_MIN, LM_OPT_R
 LM_OPT_ADVECT_MODE = 12
 LM_OPT_INTERACT_MODE, LM_OPT_DRAW_BATCH, LM_OPT_TILE_CAP = 13, 14, 15
 LM_OPT_TILE_REC_CAP, LM_OPT_TILE_PATH, LM_OPT_HEAVY_MIN, LM_OPT_SCATTER_PASSES, LM_OPT_RECORD_DEBUG = 16, 17, 18, 19, 20
+LM_OPT_PEER_WAIT_CYCLES = 21
 LM_TILE_W, LM_TILE_H = 32, 16
 LM_ADVECT_FAITHFUL, LM_ADVECT_FAST = 0, 1
 LM_NORM_INF, LM_NORM_1, LM_NORM_2 = 0, 1, 2

@@ -146,6 +146,7 @@ int lm_create(lm_handle *out, int device, int64_t max_particles, int64_t max_cel
     h->tile_rec_cap = 0;
     h->tile_path = 0;
     h->scatter_passes = 0;
+    h->peer_wait_cycles = 120000000000ll;          // about a minute of SM clocks
     h->record_debug = 0;
     h->resolve_tile_smem = 32768;
     h->resolve_batch = 4;      // measured on B200 (profiles/r1y_sweep_resolve.jsonl): 4 beats 1 and 8 on every workload
@@ -357,7 +358,7 @@ int lm_step_push(lm_handle h, int32_t kind, void *stream)
         for (int d = 0; d < 2; ++d) {
             if (!(d ? h->has_north : h->has_south) || !h->peer[d].connected) continue;
             // the neighbour's buffer is free once it has consumed the previous message (its acknowledgement lands in my flags)
-            if (seq > 1) LM_CUDA(launch_peer_wait(h->xflags + 5 + d, seq - 1, s, &h->launches));
+            if (seq > 1) LM_CUDA(launch_peer_wait(h->xflags + 5 + d, seq - 1, h->sticky, h->peer_wait_cycles, s, &h->launches));
             LM_CUDA(launch_peer_push_mig(h->mig_send[d], h->peer[d].mig_recv, h->send_cap, s, &h->launches));
             LM_CUDA(launch_peer_signal(h->peer[d].flags + (d == 0 ? 1 : 0), seq, s, &h->launches));   // I am its northern / southern side
         }
@@ -687,7 +688,7 @@ int lm_step_bin(lm_handle h, void *stream)
     cudaStream_t s = as_stream(stream);
     int c = h->cur;
     for (int d = 0; d < 2; ++d)          // peer-memory exchange: the neighbours' migrants of this step have landed
-        if ((d ? h->has_north : h->has_south) && h->peer[d].connected) LM_CUDA(launch_peer_wait(h->xflags + d, h->xseq, s, &h->launches));
+        if ((d ? h->has_north : h->has_south) && h->peer[d].connected) LM_CUDA(launch_peer_wait(h->xflags + d, h->xseq, h->sticky, h->peer_wait_cycles, s, &h->launches));
     if (h->step_moved) {
         // the re-binning gathers species: the previous step's RPS phases must be done
         { const int rcj = join_side(h, s); if (rcj) return rcj; }
@@ -786,7 +787,7 @@ int lm_step_interact_begin(lm_handle h, double r, int32_t *pairs_out, int64_t ca
     { const int rcj = join_side(h, s); if (rcj) return rcj; }
     const int c = h->cur, n = (int)h->n;
     const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
-    if (h->has_north && interact && h->peer[1].connected) LM_CUDA(launch_peer_wait(h->xflags + 2, h->xseq, s, &h->launches));
+    if (h->has_north && interact && h->peer[1].connected) LM_CUDA(launch_peer_wait(h->xflags + 2, h->xseq, h->sticky, h->peer_wait_cycles, s, &h->launches));
     if (h->has_north && interact) LM_CUDA(launch_ghost_unpack(h, h->lon[c], h->lat[c], h->id[c], n, s));
     h->rps_cap = -1;
     h->emit_cap = -1;
@@ -825,7 +826,7 @@ int lm_step_interact_end(lm_handle h, void *stream)
     cudaStream_t s = as_stream(stream);
     const int c = h->cur, n = (int)h->n;
     const bool interact = (h->step_flags & LM_STEP_INTERACT) != 0;
-    if (h->has_north && interact && h->peer[1].connected) LM_CUDA(launch_peer_wait(h->xflags + 3, h->xseq, s, &h->launches));
+    if (h->has_north && interact && h->peer[1].connected) LM_CUDA(launch_peer_wait(h->xflags + 3, h->xseq, h->sticky, h->peer_wait_cycles, s, &h->launches));
     if (h->has_north && interact) LM_CUDA(launch_ghost_species_unpack(h, h->sp[c], n, s));
     if (interact && n > 0) {
         if (!h->resolve_all_in_begin) LM_CUDA(launch_resolve_phases(h, h->sp[c], 6, 8, h->resolve_on_side ? h->side_stream : s));
@@ -853,7 +854,7 @@ int lm_step_finish(lm_handle h, void *stream)
     cudaStream_t s = as_stream(stream);
     const int c = h->cur, n = (int)h->n;
     if (h->has_south && (h->step_flags & LM_STEP_INTERACT) && h->peer[0].connected)
-        LM_CUDA(launch_peer_wait(h->xflags + 4, h->xseq, s, &h->launches));
+        LM_CUDA(launch_peer_wait(h->xflags + 4, h->xseq, h->sticky, h->peer_wait_cycles, s, &h->launches));
     if (h->has_south && (h->step_flags & LM_STEP_INTERACT)) LM_CUDA(launch_row0_species_unpack(h, h->sp[c], s));
     if (h->step_flags & LM_STEP_STATS) LM_CUDA(launch_stats(h->lon[c], h->lat[c], h->sp[c], n, h->ctr, s, &h->launches));
     if (h->step_flags & LM_STEP_TIMING) {
@@ -1047,6 +1048,7 @@ int lm_sync_stats(lm_handle h, lm_stats *out, void *stream)
     // faults of EARLIER steps whose counters have been zeroed since (steps run without LM_STEP_STATS in between)
     if (sticky & (1u | 2u | 4u | 8u)) return LM_ENOSPC;
     if (sticky & 16u) return LM_ESTATE;
+    if (sticky & 32u) return LM_ESTATE;                                            // a neighbour strip's message never came (peer_wait_kernel gave up)
     return LM_OK;
 }
 
@@ -1124,6 +1126,10 @@ int lm_set_option(lm_handle h, int32_t option, int64_t value)
         case LM_OPT_HEAVY_MIN:
             if (value < 0 || value > (1ll << 40)) return LM_EINVAL;
             h->heavy_min = value;
+            return LM_OK;
+        case LM_OPT_PEER_WAIT_CYCLES:
+            if (value < 1) return LM_EINVAL;
+            h->peer_wait_cycles = (long long)value;
             return LM_OK;
         case LM_OPT_RECORD_DEBUG:
             if (value < 0 || value > 3) return LM_EINVAL;

@@ -171,6 +171,7 @@ struct lm_handle_s {
     int8_t *gret_send, *gret_recv;       // [ghost_cap] species of the ghost row, south -> north after phase 8
     int32_t *xfer_counts_host;           // pinned + mapped: n_leave[2], n_arrive[2], stored by the device (xfer_counts_kernel)
     int32_t *xfer_counts_dev;            // the same memory as the device sees it
+    long long peer_wait_cycles;          // LM_OPT_PEER_WAIT_CYCLES: SM clocks after which a wait for a neighbour's message gives up
     uint32_t *stats_host, *stats_dev;    // pinned + mapped: Counters + the sticky fault word, stored by the device (lm_sync_stats)
     // peer-memory exchange (lm_strip_peer_connect): the neighbours' receive buffers and flag words, mapped into this process
     struct Peer {
@@ -219,7 +220,8 @@ cudaError_t launch_words_to_host(const uint32_t *src, const uint32_t *last, uint
 cudaError_t launch_xfer_counts(const void *send0, const void *send1, const void *recv0, const void *recv1, int32_t *host_counts_dev,
                                cudaStream_t s, int64_t *launches);
 cudaError_t launch_peer_signal(unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches);
-cudaError_t launch_peer_wait(const unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches);
+cudaError_t launch_peer_wait(const unsigned int *flag, unsigned int seq, unsigned int *sticky, long long limit_cycles, cudaStream_t s,
+                             int64_t *launches);
 cudaError_t launch_peer_push_mig(const int4 *src, int4 *dst, int64_t send_cap, cudaStream_t s, int64_t *launches);
 cudaError_t launch_ghost_unpack(lm_handle_s *h, float *lon, float *lat, int32_t *id, int n_owned, cudaStream_t s);
 // species of the first owned row -> gsp_send (pack) / gsp_recv -> ghost particles (unpack); and the way back

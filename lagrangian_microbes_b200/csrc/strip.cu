@@ -172,9 +172,19 @@ __global__ void peer_signal_kernel(unsigned int *flag, unsigned int seq)
     *reinterpret_cast<volatile unsigned int *>(flag) = seq;
 }
 
-__global__ void peer_wait_kernel(const unsigned int *flag, unsigned int seq)
+// The spin is bounded: a neighbour that died (or raised and left) would otherwise leave this GPU spinning for ever -- after
+// about a minute of SM clocks the wait gives up, latches fault bit 5 (lm_sync_stats: LM_ESTATE) and every later wait of the
+// handle returns at once, so the run ends with an error instead of a hung device.
+__global__ void peer_wait_kernel(const unsigned int *flag, unsigned int seq, unsigned int *sticky, long long limit_cycles)
 {
-    while ((int)(*reinterpret_cast<const volatile unsigned int *>(flag) - seq) < 0) { }   // wrap-safe: flag >= seq
+    if (*reinterpret_cast<volatile unsigned int *>(sticky) & 32u) return;
+    const long long t0 = clock64();
+    while ((int)(*reinterpret_cast<const volatile unsigned int *>(flag) - seq) < 0) {     // wrap-safe: flag >= seq
+        if (clock64() - t0 > limit_cycles) {
+            atomicOr(sticky, 32u);
+            break;
+        }
+    }
     __threadfence_system();
 }
 
@@ -231,9 +241,10 @@ cudaError_t launch_peer_signal(unsigned int *flag, unsigned int seq, cudaStream_
     return cudaGetLastError();
 }
 
-cudaError_t launch_peer_wait(const unsigned int *flag, unsigned int seq, cudaStream_t s, int64_t *launches)
+cudaError_t launch_peer_wait(const unsigned int *flag, unsigned int seq, unsigned int *sticky, long long limit_cycles, cudaStream_t s,
+                             int64_t *launches)
 {
-    peer_wait_kernel<<<1, 1, 0, s>>>(flag, seq);
+    peer_wait_kernel<<<1, 1, 0, s>>>(flag, seq, sticky, limit_cycles);
     ++*launches;
     return cudaGetLastError();
 }

@@ -5,6 +5,7 @@
 // memory spaces and scheduling are not modelled.  The product never includes this header: liblm_b200.so is built by
 // nvcc from the untouched sources, this shim is found first on the include path only by tests/cuda_emu/emu_build.py.
 #pragma once
+#include <chrono>
 #include <pthread.h>
 #include <stdint.h>
 
@@ -148,6 +149,7 @@ static inline int atomicMax(int *p, int v)
 
 static inline int __popc(unsigned int x) { return __builtin_popcount(x); }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+static inline long long clock64() { return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }

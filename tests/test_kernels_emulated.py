@@ -512,6 +512,21 @@ def test_latitude_strips_through_the_c_abi(abi, n_strips, interact_mode, resolve
             assert np.array_equal(got, opairs.sort_pairs(pairs_single[:s1.n_pairs])), "pair set, step %d" % step
             assert np.array_equal(gs, ws), "species, step %d: %d differ" % (step, int((gs != ws).sum()))
         assert moved > 0                                                  # microbes did cross strip boundaries
+        if peer:
+            # a neighbour that never sends (it died, or raised and left): the stage that waits for its message gives up
+            # after LM_OPT_PEER_WAIT_CYCLES instead of spinning for ever, the fault is reported once as LM_ESTATE, and
+            # further waits of the handle return at once
+            lone = strips[0]
+            assert L.lm_set_option(lone, _lib.LM_OPT_PEER_WAIT_CYCLES, 0) == _lib.LM_EINVAL
+            assert L.lm_set_option(lone, _lib.LM_OPT_PEER_WAIT_CYCLES, 2000000) == 0       # emulator clock: 2 ms
+            prm = _lib.RpsParams(*p, seed, n_steps)
+            import time as _time
+            t0 = _time.time()
+            assert L.lm_step_move(lone, flags_full, ctypes.byref(clock_b.next_step(dt)), dt, 0.0, ctypes.byref(prm), None) == 0
+            assert L.lm_step_push(lone, _lib.LM_XCHG_MIG, None) == 0
+            assert L.lm_step_bin(lone, None) == 0                         # its northern neighbour has not stepped
+            assert L.lm_sync_stats(lone, ctypes.byref(_lib.Stats()), None) == _lib.LM_ESTATE
+            assert _time.time() - t0 < 30.0
     finally:
         for h in [single] + strips:
             L.lm_destroy(h)
